@@ -1,0 +1,1121 @@
+// cfo_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+//
+// A dependency-free C++17 (+OpenMP) restatement of the cajitafluids hot path
+// (divergence -> Jacobi-PCG -> gradient subtraction, RK3 semi-Lagrangian advection,
+// inflow/body-force inputs) used ONLY as the checker in tests/, in
+// __graft_entry__.smoke() and as bench.py's cpu_baseline / --impl reference leg.
+// Nothing in cajitafluids_b200/ (the product) links, loads or calls this file.
+//
+// PARITY UNPINNED: the reference cannot be built here (Kokkos, Cabana/Cajita, MPI, Silo
+// absent) and none of its tests touches this path, so this
+// restatement is pinned only by (a) the geometry assertions of tests/tstMesh.cpp and
+// tests/tstProblemManager.cpp re-expressed in tests/test_oracle_geometry.py and (b) the
+// analytic known-answer tests of SURVEY.md §8c.  Third-party arithmetic that is NOT in the
+// reference tree — Cabana (ECP-copa/Cabana, Cajita sub-library, unpinned: `cabana@master`
+// in configs/llnl-lassen/spack.yaml:12, API level ~0.5) — is restated from its published
+// algorithm and marked [Cajita-mem].
+//
+// The reference is 2-D only.  dim == 2 follows it statement by statement;
+// dim == 3 is the obvious extension, every 3-D choice is marked [3D-ext].
+//
+// Data structures deliberately mirror the reference so this doubles as the CPU baseline:
+// ghosted arrays (halo 3 on every side, also on physical walls), a stored 2*D+1 coefficient
+// matrix + stored inverse diagonal, the 4-kernel / 3-reduction Cajita CG, one loop nest per
+// advected field, a full field gather before the divergence.
+//
+// All file:line citations are relative to the cajitafluids tree.
+
+#include "../include/cfb.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace
+{
+
+using clk = std::chrono::steady_clock;
+
+// ---------------------------------------------------------------------------------------
+// A ghosted array of one entity type (Cajita::Array with one dof), x fastest.
+// Entity: 0 = Cell, 1 = Face<I>, 2 = Face<J>, 3 = Face<K>.
+struct Arr
+{
+    int e[3] = { 1, 1, 1 }; // ghosted extents
+    std::vector<double> a;
+    void alloc( const int ext[3] )
+    {
+        for ( int d = 0; d < 3; ++d )
+            e[d] = ext[d];
+        // Cajita::ArrayOp::assign( ..., 0.0, Ghost() )  src/ProblemManager.hpp:149-165
+        a.assign( (size_t)e[0] * e[1] * e[2], 0.0 );
+    }
+    inline size_t idx( int i, int j, int k ) const
+    {
+        return ( (size_t)k * e[1] + j ) * e[0] + i;
+    }
+    inline double& operator()( int i, int j, int k ) { return a[idx( i, j, k )]; }
+    inline double operator()( int i, int j, int k ) const { return a[idx( i, j, k )]; }
+};
+
+struct Space
+{
+    int lo[3], hi[3];
+};
+
+typedef void ( *gather_cb )( void* user, int what );
+typedef void ( *allreduce_cb )( void* user, double* vals, int n );
+
+} // namespace
+
+struct cfo_ctx
+{
+    cfb_config cfg;
+    int D;
+    int h;         // halo cell width
+    int n[3];      // owned cells of this block
+    int off[3];    // global cell offset of this block
+    bool hi_bd[3]; // block touches the high physical boundary in dim d
+    bool lo_bd[3];
+    double cell;   // Mesh::cellSize
+    double dt;     // clamped
+    double time;
+    double ghost_low[3]; // LocalMesh ghosted low corner [Cajita-mem]
+    int bc_min[3], bc_max[3];
+
+    // ProblemManager state: [entity][version]
+    Arr fld[4][2];
+    int cur[4];
+
+    // VelocityCorrector
+    Arr lhs, rhs;
+    int nst;                // 2*D+1
+    std::vector<double> A;  // (cell, c) c fastest  -- getMatrixValues()
+    std::vector<double> Mi; // getPreconditionerValues()
+    Arr cg_p, cg_z, cg_r, cg_q;
+    int num_iter;
+    double resid; // sqrt(sum r^2)
+    std::vector<double> hist;
+
+    // distributed hooks (tests drive halo exchange / allreduce over gloo)
+    gather_cb gcb = nullptr;
+    allreduce_cb acb = nullptr;
+    void* cb_user = nullptr;
+
+    double t_phase[8] = { 0 };
+    long long cg_total = 0;
+    long long steps = 0;
+    std::string err;
+};
+
+namespace
+{
+
+std::string g_err;
+
+// ---------------------------------------------------------------------------------------
+// Cajita GlobalGrid block partition [Cajita-mem]: n/nb cells per block, the first n%nb
+// blocks get one more.
+void partition( int n, int nb, int b, int& owned, int& offset )
+{
+    int base = n / nb, rem = n % nb;
+    owned = base + ( b < rem ? 1 : 0 );
+    offset = b * base + std::min( b, rem );
+}
+
+// Ghosted extents of an entity: owned cells + 2*halo (+1 along the face normal).
+// tests/tstMesh.cpp:61-68 pins n + 2*halo + 1 by n + 2*halo for Face<I> on one rank.
+void ghost_ext( const cfo_ctx& c, int ent, int ext[3] )
+{
+    for ( int d = 0; d < 3; ++d )
+    {
+        if ( d < c.D )
+            ext[d] = c.n[d] + 2 * c.h + ( ent - 1 == d ? 1 : 0 );
+        else
+            ext[d] = 1;
+    }
+}
+
+// LocalGrid::indexSpace( Own(), entity, Local() ) [Cajita-mem]: cells [h, h+n); faces get one
+// more along their normal only on the block touching the high (non-periodic) wall.
+Space own_space( const cfo_ctx& c, int ent )
+{
+    Space s;
+    for ( int d = 0; d < 3; ++d )
+    {
+        if ( d < c.D )
+        {
+            s.lo[d] = c.h;
+            s.hi[d] = c.h + c.n[d] + ( ( ent - 1 == d && c.hi_bd[d] ) ? 1 : 0 );
+        }
+        else
+        {
+            s.lo[d] = 0;
+            s.hi[d] = 1;
+        }
+    }
+    return s;
+}
+
+// LocalMesh::coordinates( entity, idx, x ) [Cajita-mem]:
+//   x[d] = ghost_low[d] + (idx[d] + 0.5) * cell   for cells and tangential face dirs
+//   x[d] = ghost_low[d] +  idx[d]        * cell   along the face normal
+inline void coordinates( const cfo_ctx& c, int ent, const int idx[3], double x[3] )
+{
+    for ( int d = 0; d < c.D; ++d )
+    {
+        if ( ent - 1 == d )
+            x[d] = c.ghost_low[d] + double( idx[d] ) * c.cell;
+        else
+            x[d] = c.ghost_low[d] + ( double( idx[d] ) + 0.5 ) * c.cell;
+    }
+}
+
+// IndexConversion::createL2G [Cajita-mem]
+inline int l2g( const cfo_ctx& c, int d, int i ) { return i - c.h + c.off[d]; }
+
+// ---------------------------------------------------------------------------------------
+// Cajita::Spline<1> / Spline<3> + evaluateSpline + G2P::value [Cajita-mem]
+//   logical coordinate  xl = (x - x_of_entity_0) * (1/cell)
+//   order 1: s = int(xl), int(xl)+1 ; w = 1-f, f            with f = xl - int(xl)
+//   order 3: s = int(xl)-1 .. int(xl)+2 ; cubic B-spline weights evaluated from the distance
+//            to the first knot, xn = f + 1, stepping xn -= 1 per knot.
+inline void spline1( double xl, int s[2], double w[2] )
+{
+    int i0 = static_cast<int>( xl );
+    s[0] = i0;
+    s[1] = i0 + 1;
+    double xn = xl - double( i0 );
+    w[0] = 1.0 - xn;
+    w[1] = xn;
+}
+inline void spline3( double xl, int s[4], double w[4] )
+{
+    int i0 = static_cast<int>( xl );
+    s[0] = i0 - 1;
+    s[1] = i0;
+    s[2] = i0 + 1;
+    s[3] = i0 + 2;
+    const double one_sixth = 1.0 / 6.0;
+    const double two_thirds = one_sixth * 4.0;
+    const double four_thirds = 2.0 * two_thirds;
+    double xn = xl - double( i0 ) + 1.0;
+    double xn2 = xn * xn;
+    w[0] = -xn * xn2 * one_sixth + xn2 - 2.0 * xn + four_thirds;
+    xn -= 1.0;
+    xn2 = xn * xn;
+    w[1] = 0.5 * xn * xn2 - xn2 + two_thirds;
+    xn -= 1.0;
+    xn2 = xn * xn;
+    w[2] = -0.5 * xn * xn2 - xn2 + two_thirds;
+    xn -= 1.0;
+    xn2 = xn * xn;
+    w[3] = xn * xn2 * one_sixth + xn2 + 2.0 * xn + four_thirds;
+}
+
+// Interpolation::interpolateField<D, order, Entity>  src/Interpolation.hpp:30-41
+// The reference reads whatever index the spline produces (no clamping; leaving the halo is
+// UB there).  We clamp the index into the allocation so a bad CFL cannot segfault the
+// checker; parity is only defined for foot points inside the halo.
+template <int ORDER>
+inline double interpolate_field( const cfo_ctx& c, int ent, const double loc[3],
+                                 const Arr& f )
+{
+    constexpr int NK = ORDER + 1;
+    int s[3][NK];
+    double w[3][NK];
+    const int zero[3] = { 0, 0, 0 };
+    double low[3];
+    coordinates( c, ent, zero, low );
+    const double rdx = 1.0 / c.cell;
+    for ( int d = 0; d < c.D; ++d )
+    {
+        double xl = ( loc[d] - low[d] ) * rdx;
+        if ( ORDER == 1 )
+            spline1( xl, s[d], w[d] );
+        else
+            spline3( xl, s[d], w[d] );
+        for ( int a = 0; a < NK; ++a )
+            s[d][a] = std::min( std::max( s[d][a], 0 ), f.e[d] - 1 );
+    }
+    double value = 0.0;
+    if ( c.D == 2 )
+    {
+        for ( int a = 0; a < NK; ++a )
+            for ( int b = 0; b < NK; ++b )
+                value += f( s[0][a], s[1][b], 0 ) * w[0][a] * w[1][b];
+    }
+    else
+    {
+        for ( int a = 0; a < NK; ++a )
+            for ( int b = 0; b < NK; ++b )
+                for ( int g = 0; g < NK; ++g )
+                    value += f( s[0][a], s[1][b], s[2][g] ) * w[0][a] * w[1][b] * w[2][g];
+    }
+    return value;
+}
+
+// Interpolation::interpolateVelocity<D,1>  src/Interpolation.hpp:43-54  (+ w: [3D-ext])
+inline void interpolate_velocity( const cfo_ctx& c, const double loc[3], double vel[3] )
+{
+    for ( int d = 0; d < c.D; ++d )
+        vel[d] = interpolate_field<1>( c, 1 + d, loc, c.fld[1 + d][c.cur[1 + d]] );
+}
+
+// TimeIntegrator::rk3  src/TimeIntegrator.hpp:36-77
+// Q2: the third stage uses v0 (":57-58"); the 3-D stub at :59-60 writes x1[2] instead of
+// x2[2] — [3D-ext] fills x2[2] properly but keeps the Q2 choice of v0.
+inline void rk3( const cfo_ctx& c, const double x0[3], double dt, double trace[3] )
+{
+    double v0[3], x1[3], v1[3], x2[3], v2[3];
+    interpolate_velocity( c, x0, v0 );
+    for ( int d = 0; d < c.D; ++d )
+        x1[d] = x0[d] - 0.5 * dt * v0[d];
+    interpolate_velocity( c, x1, v1 );
+    const double* vs = c.cfg.quirk_rk3_stage3_v0 ? v0 : v1;
+    for ( int d = 0; d < c.D; ++d )
+        x2[d] = x0[d] - 0.75 * dt * vs[d];
+    interpolate_velocity( c, x2, v2 );
+    for ( int d = 0; d < c.D; ++d )
+        trace[d] = x0[d] - dt * ( ( 2.0 / 9.0 ) * v0[d] + ( 3.0 / 9.0 ) * v1[d] +
+                                  ( 4.0 / 9.0 ) * v2[d] );
+}
+
+// TimeIntegrator::advect  src/TimeIntegrator.hpp:81-116
+void advect( cfo_ctx& c, int ent )
+{
+    const Arr& fc = c.fld[ent][c.cur[ent]];
+    Arr& fn = c.fld[ent][1 - c.cur[ent]];
+    Space s = own_space( c, ent );
+    const int order = c.cfg.field_interp_order;
+    const double dt = c.dt;
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+            {
+                int idx[3] = { i, j, k };
+                double start[3], trace[3];
+                coordinates( c, ent, idx, start );
+                rk3( c, start, dt, trace );
+                fn( i, j, k ) = ( order == 1 ) ? interpolate_field<1>( c, ent, trace, fc )
+                                               : interpolate_field<3>( c, ent, trace, fc );
+            }
+}
+
+inline void do_gather( cfo_ctx& c, int what )
+{
+    if ( c.gcb )
+        c.gcb( c.cb_user, what );
+}
+inline void do_allreduce( cfo_ctx& c, double* v, int n )
+{
+    if ( c.acb )
+        c.acb( c.cb_user, v, n );
+}
+
+// TimeIntegrator::step  src/TimeIntegrator.hpp:120-177
+void time_integrator_step( cfo_ctx& c )
+{
+    auto t0 = clk::now();
+    do_gather( c, 0 ); // pm.gather( Version::Current() )   :131
+    for ( int ent = 0; ent <= c.D; ++ent )
+        advect( c, ent ); // :137-160
+    for ( int ent = 0; ent <= c.D; ++ent )
+        c.cur[ent] = 1 - c.cur[ent]; // pm.advance   :167-172
+    c.t_phase[0] += std::chrono::duration<double>( clk::now() - t0 ).count();
+}
+
+// BoundaryCondition::operator()( Face<d>, ... )  src/BoundaryConditions.hpp:102-129
+inline void bc_face( const cfo_ctx& c, int d, Arr& f, const int g[3], int i, int j, int k )
+{
+    if ( g[d] <= c.bc_min[d] && c.cfg.boundary_type[d] == CFB_SOLID )
+        f( i, j, k ) = 0;
+    if ( g[d] > c.bc_max[d] && c.cfg.boundary_type[c.D + d] == CFB_SOLID )
+        f( i, j, k ) = 0;
+}
+
+// InflowSource box test  src/InflowSource.hpp:40-41 (+ z: [3D-ext])
+inline bool in_inflow( const cfo_ctx& c, const double x[3] )
+{
+    for ( int d = 0; d < c.D; ++d )
+    {
+        double lo = c.cfg.inflow_location[d];
+        double hi = c.cfg.inflow_location[d] + c.cfg.inflow_size[d];
+        if ( !( x[d] >= lo && x[d] < hi ) )
+            return false;
+    }
+    return true;
+}
+
+// Solver::_addInputs  src/Solver.hpp:181-263
+void add_inputs( cfo_ctx& c )
+{
+    auto t0 = clk::now();
+    {
+        Arr& q = c.fld[0][c.cur[0]];
+        Space s = own_space( c, 0 );
+#pragma omp parallel for collapse( 2 ) schedule( static )
+        for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+            for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                {
+                    int idx[3] = { i, j, k };
+                    double x[3];
+                    coordinates( c, 0, idx, x );
+                    // InflowSource( Cell )  src/InflowSource.hpp:33-50
+                    if ( in_inflow( c, x ) && q( i, j, k ) < c.cfg.inflow_quantity )
+                        q( i, j, k ) = c.cfg.inflow_quantity;
+                    // BodyForce( Cell ) is empty  src/BodyForce.hpp:33-41
+                }
+    }
+    for ( int d = 0; d < c.D; ++d )
+    {
+        Arr& u = c.fld[1 + d][c.cur[1 + d]];
+        Space s = own_space( c, 1 + d );
+        const double V = c.cfg.inflow_velocity[d];
+        const double fdt = c.cfg.body_force[d] * c.dt;
+#pragma omp parallel for collapse( 2 ) schedule( static )
+        for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+            for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                {
+                    int idx[3] = { i, j, k };
+                    double x[3];
+                    coordinates( c, 1 + d, idx, x );
+                    int g[3] = { l2g( c, 0, i ), l2g( c, 1, j ), c.D == 3 ? l2g( c, 2, k ) : 0 };
+                    // InflowSource( Face )  src/InflowSource.hpp:52-78
+                    if ( in_inflow( c, x ) && std::fabs( u( i, j, k ) ) < std::fabs( V ) )
+                        u( i, j, k ) = V;
+                    // BodyForce( Face )  src/BodyForce.hpp:43-60
+                    u( i, j, k ) += fdt;
+                    bc_face( c, d, u, g, i, j, k );
+                }
+    }
+    c.t_phase[1] += std::chrono::duration<double>( clk::now() - t0 ).count();
+}
+
+// VelocityCorrector::initializeMatrixValues + BoundaryCondition::build_matrix +
+// fillMatrixValues( reference )   src/VelocityCorrector.hpp:116-144,158-180
+// src/BoundaryConditions.hpp:56-97.   Stencil order {0},{-x},{+x},{-y},{+y}(,{-z},{+z}).
+void fill_matrix( cfo_ctx& c )
+{
+    Space s = own_space( c, 0 );
+    const double scale = c.dt / ( c.cfg.density * c.cell * c.cell ); // :128
+    const int nst = c.nst;
+    const Arr& L = c.lhs;
+    c.A.assign( L.a.size() * nst, 0.0 );
+    c.Mi.assign( L.a.size(), 0.0 );
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+            {
+                double* m = &c.A[L.idx( i, j, k ) * nst];
+                int g[3] = { l2g( c, 0, i ), l2g( c, 1, j ), c.D == 3 ? l2g( c, 2, k ) : 0 };
+                m[0] = ( 2.0 * c.D ) * scale; // 4.0 * scale  :137  (6.0 in 3-D [3D-ext])
+                for ( int e = 1; e < nst; ++e )
+                    m[e] = -1.0 * scale;
+                for ( int d = 0; d < c.D; ++d )
+                {
+                    if ( g[d] <= c.bc_min[d] )
+                    { // low wall of dim d
+                        m[1 + 2 * d] = 0;
+                        if ( c.cfg.boundary_type[d] == CFB_SOLID )
+                            m[0] -= scale;
+                    }
+                    if ( g[d] > c.bc_max[d] - 1 )
+                    { // high wall of dim d
+                        m[2 + 2 * d] = 0;
+                        if ( c.cfg.boundary_type[c.D + d] == CFB_SOLID )
+                            m[0] -= scale;
+                    }
+                }
+                c.Mi[L.idx( i, j, k )] = 1.0 / m[0]; // :178
+            }
+}
+
+// VelocityCorrector::_buildRHS  src/VelocityCorrector.hpp:182-212
+void build_rhs( cfo_ctx& c )
+{
+    auto t0 = clk::now();
+    do_gather( c, 0 ); // _pm->gather( Version::Current() )  :190  (Q7)
+    Space s = own_space( c, 0 );
+    const double scale = 1.0 / c.cell;
+    const Arr& u = c.fld[1][c.cur[1]];
+    const Arr& v = c.fld[2][c.cur[2]];
+    const Arr* w = c.D == 3 ? &c.fld[3][c.cur[3]] : nullptr;
+    Arr& rhs = c.rhs;
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+            {
+                double div = u( i + 1, j, k ) - u( i, j, k ) + v( i, j + 1, k ) - v( i, j, k );
+                if ( w )
+                    div = div + ( *w )( i, j, k + 1 ) - ( *w )( i, j, k ); // [3D-ext]
+                rhs( i, j, k ) = -scale * div;
+            }
+    // Cajita::ArrayOp::assign( *_lhs, 0.0, Own() )   :272
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                c.lhs( i, j, k ) = 0.0;
+    c.t_phase[2] += std::chrono::duration<double>( clk::now() - t0 ).count();
+}
+
+// sum_c A(cell,c) * x(cell + off_c), in stencil order, each term accumulated with one fused
+// multiply-add (what `Ax += A * x` compiles to on an FMA machine).
+inline double apply_A( const cfo_ctx& c, const Arr& x, int i, int j, int k )
+{
+    const double* m = &c.A[x.idx( i, j, k ) * c.nst];
+    double Ax = 0.0;
+    Ax = std::fma( m[0], x( i, j, k ), Ax );
+    Ax = std::fma( m[1], x( i - 1, j, k ), Ax );
+    Ax = std::fma( m[2], x( i + 1, j, k ), Ax );
+    Ax = std::fma( m[3], x( i, j - 1, k ), Ax );
+    Ax = std::fma( m[4], x( i, j + 1, k ), Ax );
+    if ( c.D == 3 )
+    {
+        Ax = std::fma( m[5], x( i, j, k - 1 ), Ax );
+        Ax = std::fma( m[6], x( i, j, k + 1 ), Ax );
+    }
+    return Ax;
+}
+
+// Cajita::ReferenceConjugateGradient::solve( b, x ) [Cajita-mem]  
+// driven from src/VelocityCorrector.hpp:276 with tol 1e-6 / max_iter 2000 (:103-104),
+// diagonal preconditioner (:166-179).  Absolute 2-norm stopping test.
+// gather ids: 1 = x halo, 2 = r halo (width 0 for a diagonal M: no-op), 3 = p halo.
+int cg_solve( cfo_ctx& c )
+{
+    auto t0 = clk::now();
+    Space s = own_space( c, 0 );
+    const Arr& b = c.rhs;
+    Arr& x = c.lhs;
+    Arr &p = c.cg_p, &z = c.cg_z, &r = c.cg_r, &q = c.cg_q;
+    const double tol = c.cfg.cg_tolerance;
+    const int max_iter = c.cfg.cg_fixed_iters > 0 ? c.cfg.cg_fixed_iters : c.cfg.cg_max_iter;
+    const bool fixed = c.cfg.cg_fixed_iters > 0;
+    c.num_iter = 0;
+    c.hist.clear();
+    double thresh = tol;
+
+    // r0 = b - A x0 ; rr
+    do_gather( c, 1 );
+    double rr = 0.0;
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : rr )
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+            {
+                double r_new = b( i, j, k ) - apply_A( c, x, i, j, k );
+                r( i, j, k ) = r_new;
+                rr += r_new * r_new;
+            }
+    do_allreduce( c, &rr, 1 );
+    c.resid = std::sqrt( rr );
+    if ( c.cfg.cg_stop_rule == CFB_STOP_REL )
+        thresh = tol * c.resid; // x0 = 0 => r0 = b
+    if ( !fixed && c.resid <= thresh )
+    {
+        c.t_phase[3] += std::chrono::duration<double>( clk::now() - t0 ).count();
+        return CFB_OK;
+    }
+
+    // z0 = M r0 ; p0 = z0 ; zTr
+    do_gather( c, 2 );
+    double zTr_old = 0.0;
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : zTr_old )
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+            {
+                double Mr = c.Mi[r.idx( i, j, k )] * r( i, j, k );
+                z( i, j, k ) = Mr;
+                p( i, j, k ) = Mr;
+                zTr_old += Mr * r( i, j, k );
+            }
+    do_allreduce( c, &zTr_old, 1 );
+
+    // q0 = A p0 ; pTAp
+    do_gather( c, 3 );
+    double pTAp = 0.0;
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : pTAp )
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+            {
+                double Ap = apply_A( c, p, i, j, k );
+                q( i, j, k ) = Ap;
+                pTAp += p( i, j, k ) * Ap;
+            }
+    do_allreduce( c, &pTAp, 1 );
+
+    bool converged = false;
+    while ( c.num_iter < max_iter )
+    {
+        // kernel 1: x += alpha p ; r -= alpha q ; rr
+        const double alpha = zTr_old / pTAp;
+        rr = 0.0;
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : rr )
+        for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+            for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                {
+                    x( i, j, k ) = std::fma( alpha, p( i, j, k ), x( i, j, k ) );
+                    double r_new = std::fma( -alpha, q( i, j, k ), r( i, j, k ) );
+                    r( i, j, k ) = r_new;
+                    rr += r_new * r_new;
+                }
+        do_allreduce( c, &rr, 1 );
+        c.resid = std::sqrt( rr );
+        ++c.num_iter;
+        c.hist.push_back( c.resid );
+        if ( c.cfg.cg_print_level == 2 && c.cfg.world_rank == 0 )
+            std::printf( "Cajita CG Iteration %d: |r|_2 = %g\n", c.num_iter, c.resid );
+        if ( !fixed && c.resid <= thresh )
+        {
+            converged = true;
+            break;
+        }
+
+        // kernel 2: z = M r ; zTr
+        do_gather( c, 2 );
+        double zTr_new = 0.0;
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : zTr_new )
+        for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+            for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                {
+                    double Mr = c.Mi[r.idx( i, j, k )] * r( i, j, k );
+                    z( i, j, k ) = Mr;
+                    zTr_new += Mr * r( i, j, k );
+                }
+        do_allreduce( c, &zTr_new, 1 );
+
+        // kernel 3: p = z + beta p
+        const double beta = zTr_new / zTr_old;
+#pragma omp parallel for collapse( 2 ) schedule( static )
+        for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+            for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                    p( i, j, k ) = std::fma( beta, p( i, j, k ), z( i, j, k ) );
+
+        // kernel 4: q = A p ; pTAp
+        do_gather( c, 3 );
+        pTAp = 0.0;
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : pTAp )
+        for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+            for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                {
+                    double Ap = apply_A( c, p, i, j, k );
+                    q( i, j, k ) = Ap;
+                    pTAp += p( i, j, k ) * Ap;
+                }
+        do_allreduce( c, &pTAp, 1 );
+        zTr_old = zTr_new;
+    }
+    c.cg_total += c.num_iter;
+    if ( c.cfg.cg_print_level > 0 && c.cfg.world_rank == 0 )
+        std::printf( "Cajita CG Finished in %d iterations, |r|_2 = %g\n", c.num_iter, c.resid );
+    c.t_phase[3] += std::chrono::duration<double>( clk::now() - t0 ).count();
+    if ( !converged && !fixed )
+    {
+        c.err = "Cajita CG solver did not converge";
+        return CFB_ERR_NOT_CONVERGED;
+    }
+    return CFB_OK;
+}
+
+// VelocityCorrector::_applyPressure  src/VelocityCorrector.hpp:214-264
+void apply_pressure( cfo_ctx& c )
+{
+    auto t0 = clk::now();
+    const double scale = c.dt / ( c.cfg.density * c.cell ); // :217
+    do_gather( c, 4 ); // _pressure_halo->gather( lhs )  :236
+    const Arr& p = c.lhs;
+    Arr& u = c.fld[1][c.cur[1]];
+    for ( int d = 0; d < c.D; ++d )
+    {
+        Arr& f = c.fld[1 + d][c.cur[1 + d]];
+        Space s = own_space( c, 1 + d );
+        const int di = d == 0, dj = d == 1, dk = d == 2;
+        // Q1 (src/VelocityCorrector.hpp:260): the FaceJ kernel hands `u` to the boundary
+        // functor, so the FaceJ wall test zeroes u(i,j) instead of v(i,j).
+        const bool q1 = ( d == 1 ) && c.cfg.quirk_applypressure_bc;
+        // The quirk writes u(i, j) for J-face indices; rows of different j never alias, and
+        // within this loop nest only u (not f == v) is written by the functor: race-free.
+#pragma omp parallel for collapse( 2 ) schedule( static )
+        for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+            for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                {
+                    f( i, j, k ) -= scale * ( p( i, j, k ) - p( i - di, j - dj, k - dk ) );
+                    int g[3] = { l2g( c, 0, i ), l2g( c, 1, j ), c.D == 3 ? l2g( c, 2, k ) : 0 };
+                    if ( q1 )
+                        bc_face( c, 1, u, g, i, j, k );
+                    else
+                        bc_face( c, d, f, g, i, j, k );
+                }
+    }
+    c.t_phase[4] += std::chrono::duration<double>( clk::now() - t0 ).count();
+}
+
+// VelocityCorrector::correctVelocity  src/VelocityCorrector.hpp:266-282
+int correct_velocity( cfo_ctx& c )
+{
+    build_rhs( c );
+    int rc = cg_solve( c );
+    if ( rc != CFB_OK )
+        return rc;
+    apply_pressure( c );
+    return CFB_OK;
+}
+
+int field_arr( cfo_ctx& c, int field, int version, Arr** out )
+{
+    if ( field >= CFB_QUANTITY && field <= CFB_W )
+    {
+        if ( field > c.D )
+            return CFB_ERR_INVALID;
+        int v = ( version == CFB_CURRENT ) ? c.cur[field] : 1 - c.cur[field];
+        *out = &c.fld[field][v];
+        return CFB_OK;
+    }
+    switch ( field )
+    {
+    case CFB_PRESSURE:
+        *out = &c.lhs;
+        return CFB_OK;
+    case CFB_RHS:
+        *out = &c.rhs;
+        return CFB_OK;
+    case CFB_CG_R:
+        *out = &c.cg_r;
+        return CFB_OK;
+    case CFB_CG_P:
+        *out = &c.cg_p;
+        return CFB_OK;
+    case CFB_CG_Q:
+        *out = &c.cg_q;
+        return CFB_OK;
+    }
+    return CFB_ERR_INVALID;
+}
+inline int field_entity( int field ) { return ( field >= CFB_U && field <= CFB_W ) ? field : 0; }
+
+} // namespace
+
+extern "C" {
+
+const char* cfo_last_error( const cfo_ctx* c ) { return c ? c->err.c_str() : g_err.c_str(); }
+
+int cfo_create( const cfb_config* cfg, cfo_ctx** out )
+{
+    *out = nullptr;
+    if ( !cfg || cfg->struct_size != (int)sizeof( cfb_config ) || ( cfg->dim != 2 && cfg->dim != 3 ) )
+    {
+        g_err = "invalid config";
+        return CFB_ERR_INVALID;
+    }
+    cfo_ctx* c = new cfo_ctx();
+    c->cfg = *cfg;
+    c->D = cfg->dim;
+    c->h = cfg->halo_cell_width;
+    c->time = 0.0;
+    const int D = c->D;
+
+    // Mesh ctor  src/Mesh.hpp:41-103
+    c->cell = ( cfg->global_bounding_box[3] - cfg->global_bounding_box[0] ) /
+              cfg->global_num_cell[0]; // :50-51
+    for ( int d = 0; d < D; ++d )
+    {
+        double extent = cfg->global_num_cell[d] * c->cell;
+        if ( std::abs( extent - ( cfg->global_bounding_box[3 + d] - cfg->global_bounding_box[d] ) ) >
+             10.0 * std::numeric_limits<double>::epsilon() ) // :56-64
+        {
+            g_err = "Extent not evenly divisible by uniform cell size";
+            delete c;
+            return CFB_ERR_MESH_EXTENT;
+        }
+    }
+    for ( int d = 0; d < 3; ++d )
+    {
+        if ( d < D )
+        {
+            partition( cfg->global_num_cell[d], cfg->ranks_per_dim[d], cfg->block_id[d], c->n[d],
+                       c->off[d] );
+            c->lo_bd[d] = cfg->block_id[d] == 0;
+            c->hi_bd[d] = cfg->block_id[d] == cfg->ranks_per_dim[d] - 1;
+            c->bc_min[d] = 0;                           // :74-78
+            c->bc_max[d] = cfg->global_num_cell[d] - 1; // src/Solver.hpp:109-110
+            // LocalMesh [Cajita-mem]: own low corner = global low + cell * global offset;
+            // ghosted low corner = own low corner - halo * cell.
+            double own_low = cfg->global_bounding_box[d] + c->cell * c->off[d];
+            c->ghost_low[d] = own_low - c->h * c->cell;
+        }
+        else
+        {
+            c->n[d] = 1;
+            c->off[d] = 0;
+            c->lo_bd[d] = c->hi_bd[d] = true;
+            c->bc_min[d] = c->bc_max[d] = 0;
+            c->ghost_low[d] = 0;
+        }
+    }
+
+    // Solver ctor dt clamp  src/Solver.hpp:96-106   (+ z components: [3D-ext])
+    c->dt = cfg->delta_t;
+    if ( cfg->clamp_dt )
+    {
+        double f2 = 0, vmax = 0;
+        for ( int d = 0; d < D; ++d )
+        {
+            f2 += cfg->body_force[d] * cfg->body_force[d];
+            vmax = std::fmax( vmax, std::fabs( cfg->inflow_velocity[d] ) );
+        }
+        double forcemax = std::sqrt( f2 );
+        double umax = vmax + std::sqrt( forcemax * c->cell );
+        if ( umax > 0 && c->dt > c->cell / umax )
+            c->dt = c->cell / umax;
+    }
+
+    // ProblemManager ctor  src/ProblemManager.hpp:127-180
+    for ( int ent = 0; ent <= D; ++ent )
+    {
+        int ext[3];
+        ghost_ext( *c, ent, ext );
+        c->fld[ent][0].alloc( ext );
+        c->fld[ent][1].alloc( ext );
+        c->cur[ent] = 0;
+        // initialize( create_functor )  :186-263 with MeshInitFunc  examples/advection.cpp:382-435
+        Space s = own_space( *c, ent );
+        double val = ent == 0 ? cfg->init_quantity : cfg->init_velocity[ent - 1];
+        for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+            for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                    c->fld[ent][0]( i, j, k ) = val;
+    }
+
+    // VelocityCorrector ctor  src/VelocityCorrector.hpp:70-114
+    {
+        int ext[3];
+        ghost_ext( *c, 0, ext );
+        c->lhs.alloc( ext );
+        c->rhs.alloc( ext );
+        c->cg_p.alloc( ext );
+        c->cg_z.alloc( ext );
+        c->cg_r.alloc( ext );
+        c->cg_q.alloc( ext );
+        c->nst = 2 * D + 1;
+        fill_matrix( *c );
+    }
+    *out = c;
+    return CFB_OK;
+}
+
+int cfo_destroy( cfo_ctx* c )
+{
+    delete c;
+    return CFB_OK;
+}
+
+int cfo_set_callbacks( cfo_ctx* c, gather_cb g, allreduce_cb a, void* user )
+{
+    c->gcb = g;
+    c->acb = a;
+    c->cb_user = user;
+    return CFB_OK;
+}
+
+int cfo_get_scalars( const cfo_ctx* c, double* cell, double* dt, double* time )
+{
+    if ( cell )
+        *cell = c->cell;
+    if ( dt )
+        *dt = c->dt;
+    if ( time )
+        *time = c->time;
+    return CFB_OK;
+}
+
+int cfo_owned_extent( const cfo_ctx* c, int field, int ext[3] )
+{
+    Space s = own_space( *c, field_entity( field ) );
+    for ( int d = 0; d < 3; ++d )
+        ext[d] = s.hi[d] - s.lo[d];
+    return CFB_OK;
+}
+int cfo_global_offset( const cfo_ctx* c, int off[3] )
+{
+    for ( int d = 0; d < 3; ++d )
+        off[d] = c->off[d];
+    return CFB_OK;
+}
+
+// Borrowed pointer to the ghosted array (reference layout: local ghosted indices).
+int cfo_field_ptr( cfo_ctx* c, int field, int version, double** ptr, int ext[3] )
+{
+    Arr* a;
+    int rc = field_arr( *c, field, version, &a );
+    if ( rc )
+        return rc;
+    *ptr = a->a.data();
+    for ( int d = 0; d < 3; ++d )
+        ext[d] = a->e[d];
+    return CFB_OK;
+}
+
+int cfo_upload( cfo_ctx* c, int field, int version, int region, const double* host )
+{
+    Arr* a;
+    int rc = field_arr( *c, field, version, &a );
+    if ( rc )
+        return rc;
+    if ( region == CFB_GHOSTED )
+    {
+        std::memcpy( a->a.data(), host, a->a.size() * sizeof( double ) );
+        return CFB_OK;
+    }
+    Space s = own_space( *c, field_entity( field ) );
+    size_t n = 0;
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                ( *a )( i, j, k ) = host[n++];
+    return CFB_OK;
+}
+int cfo_download( cfo_ctx* c, int field, int version, int region, double* host )
+{
+    Arr* a;
+    int rc = field_arr( *c, field, version, &a );
+    if ( rc )
+        return rc;
+    if ( region == CFB_GHOSTED )
+    {
+        std::memcpy( host, a->a.data(), a->a.size() * sizeof( double ) );
+        return CFB_OK;
+    }
+    Space s = own_space( *c, field_entity( field ) );
+    size_t n = 0;
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                host[n++] = ( *a )( i, j, k );
+    return CFB_OK;
+}
+
+int cfo_advance( cfo_ctx* c, int field )
+{
+    if ( field < 0 || field > c->D )
+        return CFB_ERR_INVALID;
+    c->cur[field] = 1 - c->cur[field];
+    return CFB_OK;
+}
+
+int cfo_add_inputs( cfo_ctx* c )
+{
+    add_inputs( *c );
+    return CFB_OK;
+}
+int cfo_time_integrator_step( cfo_ctx* c )
+{
+    time_integrator_step( *c );
+    return CFB_OK;
+}
+int cfo_build_rhs( cfo_ctx* c )
+{
+    build_rhs( *c );
+    return CFB_OK;
+}
+int cfo_pcg_solve( cfo_ctx* c, int* num_iter, double* resid )
+{
+    int rc = cg_solve( *c );
+    if ( num_iter )
+        *num_iter = c->num_iter;
+    if ( resid )
+        *resid = c->resid;
+    return rc;
+}
+int cfo_apply_pressure( cfo_ctx* c )
+{
+    apply_pressure( *c );
+    return CFB_OK;
+}
+int cfo_correct_velocity( cfo_ctx* c, int* num_iter, double* resid )
+{
+    int rc = correct_velocity( *c );
+    if ( num_iter )
+        *num_iter = c->num_iter;
+    if ( resid )
+        *resid = c->resid;
+    return rc;
+}
+// Solver::setup  src/Solver.hpp:125-133
+int cfo_setup( cfo_ctx* c )
+{
+    add_inputs( *c );
+    return correct_velocity( *c );
+}
+// Solver::step  src/Solver.hpp:135-147
+int cfo_step( cfo_ctx* c )
+{
+    time_integrator_step( *c );
+    add_inputs( *c );
+    int rc = correct_velocity( *c );
+    c->time += c->dt;
+    c->steps++;
+    return rc;
+}
+// Solver::solve  src/Solver.hpp:149-177 (Silo output omitted)
+int cfo_solve( cfo_ctx* c, double t_final, int write_freq, int* steps_taken )
+{
+    int t = 0;
+    int num_step = (int)( t_final / c->dt );
+    int rc = cfo_setup( c );
+    if ( rc )
+        return rc;
+    do
+    {
+        if ( c->cfg.world_rank == 0 && write_freq > 0 && 0 == t % write_freq )
+            std::printf( "Step %d / %d at time = %f\n", t, num_step, c->time );
+        rc = cfo_step( c );
+        if ( rc )
+            return rc;
+        t++;
+    } while ( c->time < t_final );
+    if ( steps_taken )
+        *steps_taken = t;
+    return CFB_OK;
+}
+
+// q = A p on the CG work vectors + sum(p*q): CG kernel 4 in isolation.
+int cfo_stencil_dot( cfo_ctx* c, int reps, double* dot, double* ms_per_launch )
+{
+    Space s = own_space( *c, 0 );
+    const Arr& p = c->cg_p;
+    Arr& q = c->cg_q;
+    double pTAp = 0;
+    auto t0 = clk::now();
+    for ( int it = 0; it < reps; ++it )
+    {
+        pTAp = 0;
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : pTAp )
+        for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+            for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                {
+                    double Ap = apply_A( *c, p, i, j, k );
+                    q( i, j, k ) = Ap;
+                    pTAp += p( i, j, k ) * Ap;
+                }
+    }
+    double sec = std::chrono::duration<double>( clk::now() - t0 ).count();
+    if ( dot )
+        *dot = pTAp;
+    if ( ms_per_launch )
+        *ms_per_launch = 1e3 * sec / std::max( reps, 1 );
+    return CFB_OK;
+}
+
+int cfo_residual_history( const cfo_ctx* c, double* hist, int n, int* count )
+{
+    int m = std::min<int>( n, (int)c->hist.size() );
+    for ( int i = 0; i < m; ++i )
+        hist[i] = c->hist[i];
+    if ( count )
+        *count = (int)c->hist.size();
+    return CFB_OK;
+}
+
+int cfo_get_stats( const cfo_ctx* c, cfb_stats* out )
+{
+    std::memset( out, 0, sizeof( *out ) );
+    out->ms_advect = 1e3 * c->t_phase[0];
+    out->ms_add_inputs = 1e3 * c->t_phase[1];
+    out->ms_build_rhs = 1e3 * c->t_phase[2];
+    out->ms_pcg = 1e3 * c->t_phase[3];
+    out->ms_apply_pressure = 1e3 * c->t_phase[4];
+    out->cg_iterations = c->cg_total;
+    out->steps = c->steps;
+    return CFB_OK;
+}
+int cfo_reset_stats( cfo_ctx* c )
+{
+    for ( double& t : c->t_phase )
+        t = 0;
+    c->cg_total = 0;
+    c->steps = 0;
+    return CFB_OK;
+}
+
+int cfo_num_threads( void )
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// Matrix / preconditioner read-back for the known-answer tests (ghosted layout).
+int cfo_matrix_ptr( cfo_ctx* c, double** A, double** Minv, int* nst )
+{
+    *A = c->A.data();
+    *Minv = c->Mi.data();
+    *nst = c->nst;
+    return CFB_OK;
+}
+
+// Expose the spline weights and a point interpolation for known-answer tests.
+int cfo_spline_weights( int order, double xl, int* s, double* w )
+{
+    if ( order == 1 )
+        spline1( xl, s, w );
+    else if ( order == 3 )
+        spline3( xl, s, w );
+    else
+        return CFB_ERR_INVALID;
+    return CFB_OK;
+}
+int cfo_interpolate( cfo_ctx* c, int field, int order, const double* loc, double* value )
+{
+    Arr* a;
+    int rc = field_arr( *c, field, CFB_CURRENT, &a );
+    if ( rc )
+        return rc;
+    double l[3] = { loc[0], loc[1], c->D == 3 ? loc[2] : 0.0 };
+    *value = order == 1 ? interpolate_field<1>( *c, field_entity( field ), l, *a )
+                        : interpolate_field<3>( *c, field_entity( field ), l, *a );
+    return CFB_OK;
+}
+int cfo_rk3( cfo_ctx* c, const double* x0, double* trace )
+{
+    double a[3] = { x0[0], x0[1], c->D == 3 ? x0[2] : 0.0 }, t[3] = { 0, 0, 0 };
+    rk3( *c, a, c->dt, t );
+    for ( int d = 0; d < c->D; ++d )
+        trace[d] = t[d];
+    return CFB_OK;
+}
+int cfo_coordinates( cfo_ctx* c, int field, const int* idx, double* x )
+{
+    int id[3] = { idx[0], idx[1], c->D == 3 ? idx[2] : 0 };
+    double xx[3] = { 0, 0, 0 };
+    coordinates( *c, field_entity( field ), id, xx );
+    for ( int d = 0; d < c->D; ++d )
+        x[d] = xx[d];
+    return CFB_OK;
+}
+
+} // extern "C"

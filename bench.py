@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the pressure-projection hot path (BASELINE.json).
+
+Metric: Jacobi-PCG iterations per second at 512^3 FP64 per GPU (weak scaling: every rank owns a
+512^3 block of a 3-D block-decomposed box), with the achieved HBM GB/s of the dominant kernel
+(stencil7 + dot) against the measured B200 roofline.  A "step" is one fixed-iteration PCG solve
+(`--iters`, default 100; config 2/3 of BASELINE.json use fixed iteration counts because the
+reference's own tol/max_iter would stop at 2000 < ~2500 needed) on a synthetic,
+decomposition-independent divergence right-hand side that is already resident in HBM.
+
+  python bench.py --gpus N --steps K --warmup W          our arm (one process per GPU under torchrun)
+  python bench.py --impl reference ...                   the CPU restatement of the reference
+                                                         (oracle/, OpenMP) on the box's host cores
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pcg_iterations_per_second"
+UNIT = "iterations/s"
+BYTES_STENCIL = 16  # read p, write q                       
+BYTES_ITER = 88     # stencil 16 + axpy/norms 48 + p-update 24
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s from B200_PROFILING.md (of fallback)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def block_grid(n):
+    """1 -> 1x1x1, 2 -> 1x1x2, 4 -> 1x2x2, 8 -> 2x2x2 (split z, then y, then x)."""
+    px = py = pz = 1
+    dims = [1, 1, 1]
+    k, d = n, 2
+    while k > 1:
+        dims[d] *= 2
+        k //= 2
+        d = (d - 1) % 3
+    px, py, pz = dims
+    assert px * py * pz == n, "gpus must be a power of two"
+    return px, py, pz
+
+
+def make_config(args, rank, world, blocks):
+    from cajitafluids_b200 import default_config
+    n = args.cells
+    if args.scaling == "weak":
+        gcells = tuple(n * b for b in blocks)
+    else:
+        gcells = (n, n, n)
+    cfg = default_config(3, gcells, box=tuple(c / 512.0 for c in gcells))  # h = 1/512 fixed
+    bz, r = divmod(rank, blocks[0] * blocks[1])
+    by, bx = divmod(r, blocks[0])
+    for d, (b, bid) in enumerate(zip(blocks, (bx, by, bz))):
+        cfg.ranks_per_dim[d] = b
+        cfg.block_id[d] = bid
+    cfg.world_rank, cfg.world_size = rank, world
+    cfg.cg_fixed_iters = args.iters
+    cfg.cg_print_level = 0
+    return cfg, gcells
+
+
+def cpu_baseline(args, iters_sample, gcells_1gpu):
+    """The CPU restatement of the reference (oracle/, stored-coefficient matrix, 4-kernel CG, OpenMP)
+    on a bounded sample: `iters_sample` fixed CG iterations of the same 1-GPU workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import psutil
+    from cajitafluids_b200 import config as K, default_config
+    from oracle_api import Oracle
+
+    n = gcells_1gpu[0]
+    need = 23 * (n + 6) ** 3 * 8
+    avail = psutil.virtual_memory().available
+    note = ""
+    while need > 0.6 * avail and n > 64:
+        n //= 2
+        need = 23 * (n + 6) ** 3 * 8
+        note = f" (host RAM too small for the full grid, sampled at {n}^3)"
+    cfg = default_config(3, n, box=n / 512.0)
+    cfg.cg_fixed_iters = iters_sample
+    o = Oracle(cfg)
+    # same synthetic MAC velocity family as the GPU arm (sin/cos product)
+    h = o.cell_size
+    ax = [np.arange(n + 1) * h, (np.arange(n) + 0.5) * h]
+    L = n * h
+    for d, f in enumerate((K.U, K.V, K.W)):
+        g = [np.sin(np.pi * ax[0] / L) if e == d else np.cos(2 * np.pi * ax[1] / L) for e in range(3)]
+        val = g[2][:, None, None] * g[1][None, :, None] * g[0][None, None, :]
+        sl = [slice(None)] * 3
+        sl[2 - d] = 0
+        val[tuple(sl)] = 0.0
+        sl[2 - d] = -1
+        val[tuple(sl)] = 0.0
+        o.set(f, val)
+        del val
+    o.build_rhs()
+    t0 = time.perf_counter()
+    o.pcg_solve()
+    dt = time.perf_counter() - t0
+    cores = o.num_threads()
+    o.close()
+    return {"value": iters_sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{iters_sample} fixed Jacobi-PCG iterations at {n}^3 FP64 on the host cores{note}; "
+                      "CPU restatement of the reference (Kokkos/Cajita unavailable): stored 7-coefficient "
+                      "matrix + M^-1 array, 4 kernels / 3 reductions per iteration, OpenMP",
+            "seconds": dt}, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cells
+    iters_sample = max(2, min(args.iters, 5))
+    t_all = time.perf_counter()
+    vals = []
+    base = None
+    for s in range(args.warmup + args.steps):
+        base, nn = cpu_baseline(args, iters_sample, (n, n, n))
+        if s >= args.warmup:
+            vals.append(base["seconds"])
+        if time.perf_counter() - t_all > 240:  # keep the whole arm within a few minutes
+            break
+    steps_done = max(1, len(vals))
+    total = sum(vals) if vals else base["seconds"]
+    value = iters_sample * steps_done / total
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps_done, "warmup": args.warmup, "ms_per_step": 1e3 * total / steps_done,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"pcg_{n}cubed_fixed_iters_jacobi", "cells_per_gpu": [n, n, n],
+                       "cg_iters_per_step": iters_sample, "note": "bounded sample of the same workload"},
+            "cpu_baseline": {k: v for k, v in base.items() if k != "seconds"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=512, help="cells per side per GPU (weak) / global (strong)")
+    ap.add_argument("--iters", type=int, default=100, help="fixed CG iterations per step")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--timestep-cells", type=int, default=128, help="grid of the extra full-timestep measurement")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from cajitafluids_b200 import Solver, config as K
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    blocks = block_grid(world)
+    cfg, gcells = make_config(args, rank, world, blocks)
+    cfg.device_id = local
+    if world > 1:
+        from cajitafluids_b200.distributed import attach_nccl
+        attach_nccl(cfg, dist)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    s = Solver(cfg)
+    ncell_local = int(np.prod(s.owned_extent(K.QUANTITY)))
+    ncell_global = int(np.prod(gcells))
+    s.fill_synthetic_velocity(0)
+    s.build_rhs()
+    s.set_tuning("time_kernels", 1)
+
+    for _ in range(args.warmup):
+        s.pcg_fixed(args.iters)
+    barrier()
+    s.reset_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ms, resid = s.pcg_fixed(args.iters)  # CUDA events on the library's stream around the whole solve
+        dev_ms += ms
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.summary() if rank == 0 else None
+    st = s.stats()
+    if dist is not None:
+        t = torch.tensor([dev_ms, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall = float(t[0]), float(t[1])
+    total_iters = args.iters * args.steps
+    value = total_iters / (dev_ms * 1e-3)
+
+    # roofline of the dominant kernel, from the per-kernel events recorded inside the timed region
+    peak, peak_src = measured_peak()
+    kt = max(1, st["k_timed_iters"])
+    t_st = st["ms_k_stencil"] / kt
+    ach = ncell_local * BYTES_STENCIL / (t_st * 1e-3) / 1e9 if t_st > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "stencil7_dot_tma", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ncell_local * BYTES_STENCIL,
+                "avg_launch_ms": t_st,
+                "iteration": {"bytes_per_cell": BYTES_ITER,
+                              "achieved_gbs": ncell_local * BYTES_ITER * total_iters / (dev_ms * 1e-3) / 1e9,
+                              "axpy_ms": st["ms_k_axpy"] / kt, "pupdate_ms": st["ms_k_pupdate"] / kt,
+                              "stencil_ms": t_st}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(f"stencil7_dot_{args.cells}")
+        except Exception:
+            pass
+    launches = st["kernel_launches"]
+
+    # e2e: the solver plug-in call with HOST vectors (pinned), H2D of b and D2H of x inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        shp = s.shape(K.RHS)
+        b_host = torch.empty(shp, dtype=torch.float64).pin_memory().numpy()
+        x_host = torch.empty(shp, dtype=torch.float64).pin_memory().numpy()
+        b_host[...] = s.get(K.RHS)
+        s.pcg_solve_host(b_host, x_host)  # warm
+        barrier()
+        t0 = time.perf_counter()
+        e_steps = max(1, min(args.steps, 3))
+        for _ in range(e_steps):
+            _, it, _ = s.pcg_solve_host(b_host, x_host)
+        barrier()
+        e_wall = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_wall = float(t[0])
+        e2e = {"value": args.iters * e_steps / e_wall, "unit": UNIT, "h2d_bytes_per_step": int(b_host.nbytes) * world,
+               "d2h_bytes_per_step": int(x_host.nbytes) * world, "steps": e_steps,
+               "call": "cfb_pcg_solve_host (ReferenceConjugateGradient::solve(b, x) with host vectors)"}
+        del b_host, x_host
+
+    # extra: whole timesteps (advect + inputs + projection) of the default inflow problem, 1 GPU only
+    extra = {"final_residual": resid, "wall_s_timed_region": wall, "cells_local": ncell_local}
+    if world == 1 and args.timestep_cells > 0:
+        s.close()
+        from cajitafluids_b200 import default_config
+        c2 = default_config(3, args.timestep_cells)
+        s2 = Solver(c2)
+        s2.setup()
+        for _ in range(2):
+            s2.step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nst = 5
+        it0 = s2.stats()["cg_iterations"]
+        for _ in range(nst):
+            s2.step()
+        torch.cuda.synchronize()
+        dt_steps = time.perf_counter() - t0
+        extra["timesteps_per_s"] = {"cells": [args.timestep_cells] * 3, "value": nst / dt_steps,
+                                    "cg_iters_per_step": (s2.stats()["cg_iterations"] - it0) / nst,
+                                    "interp_order": 3}
+        s2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_baseline(args, max(2, min(args.iters, 10)), (args.cells,) * 3)
+        cpu.pop("seconds", None)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"pcg_{args.cells}cubed_fixed{args.iters}_jacobi_synthetic_divergence",
+                           "cells_per_gpu": [args.cells] * 3 if args.scaling == "weak" else None,
+                           "global_cells": list(gcells), "blocks": list(blocks), "cg_iters_per_step": args.iters,
+                           "l2": "inputs larger than L2 (each vector %.2f GB)" % (ncell_local * 8 / 1e9),
+                           "timing": "CUDA events on the launching stream around each solve, max over ranks"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "extra": extra}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

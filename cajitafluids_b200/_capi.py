@@ -163,10 +163,13 @@ class Context:
 
     def shape(self, field, region=K.OWNED):
         """numpy shape (z, y, x) of a dense host copy of `region` (z dropped to 1 in 2-D)."""
-        e = list(self.owned_extent(field))
-        if region == K.GHOSTED:
+        if region == K.OWNED:
+            e = self.owned_extent(field)
+        else:
+            # Cajita Ghost index space: owned cells + 2*halo, +1 along the face normal on every block
+            e = list(self.owned_extent(K.QUANTITY))
             for d in range(self.dim):
-                e[d] += 2 * self.halo
+                e[d] += 2 * self.halo + (1 if field in (K.U, K.V, K.W) and field - K.U == d else 0)
         return (e[2], e[1], e[0])
 
     # -- ProblemManager::get as host copies

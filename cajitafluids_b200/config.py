@@ -50,7 +50,7 @@ class Config(C.Structure):
         ("quirk_rk3_stage3_v0", C.c_int32),
         ("device_id", C.c_int32),
         ("use_nccl", C.c_int32),
-        ("nccl_id", C.c_ubyte * NCCL_ID_BYTES),
+        ("nccl_id", C.c_ubyte * (2 * NCCL_ID_BYTES)),
     ]
 
 
@@ -65,6 +65,10 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_int64),
         ("cg_iterations", C.c_int64),
         ("steps", C.c_int64),
+        ("ms_k_axpy", C.c_double),
+        ("ms_k_pupdate", C.c_double),
+        ("ms_k_stencil", C.c_double),
+        ("k_timed_iters", C.c_int64),
     ]
 
 

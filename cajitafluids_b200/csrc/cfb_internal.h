@@ -1,0 +1,181 @@
+// cfb_internal.h — shared declarations of the sm_100a implementation behind include/cfb.h.
+#pragma once
+
+#include "../../include/cfb.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------------
+// Geometry of one rank's block, passed by value to every kernel.
+//
+// Device layout (all fields of a ctx share it):  offset(i,j,k) = origin + k*sz + j*sy + i
+// with (i,j,k) the 0-based OWNED index.  hx = 16 doubles (first owned entity of every row is
+// 128-byte aligned), hy = hz = halo width; rows/planes are allocated for owned + 1 (faces) +
+// 2*halo, so every reference ghost index (local index l <-> owned index l - halo) exists.
+// In 2-D nz = 1 and the z ghost planes stay zero, which makes the 7-point operator with SOLID
+// z walls identical to the reference's 5-point operator (diag 6-2 = 4).
+struct Geo
+{
+    int D;
+    int n[3];     // owned cells
+    int nf[3];    // owned faces along their normal: n[d] + (block touches the high wall)
+    int off[3];   // global offset of owned cell 0
+    int gn[3];    // global cells
+    int h;        // halo cell width
+    int lo_bd[3]; // block touches the low / high physical wall
+    int hi_bd[3];
+    int bt[6];    // boundary types, [d] low, [3 + d] high  (NB: always stride 3 here)
+    long long sy, sz, origin, total; // strides / allocation size in doubles
+    int ay, az;                      // allocated rows / planes
+    double cell, dt, rdx;
+    double ghost_low[3]; // Cajita LocalMesh ghosted low corner of this block
+    double time;
+};
+
+// Pressure operator constants (src/VelocityCorrector.hpp:128,137 + BoundaryConditions.hpp:56-97).
+// diag[c] = 2*D*scale with `scale` subtracted c times (c = number of SOLID walls the cell touches),
+// minv[c] = 1.0 / diag[c]  (src/VelocityCorrector.hpp:178).
+struct OpConst
+{
+    double scale;     // dt / (rho h^2)
+    double neg_scale; // off-diagonal coefficient
+    double diag[8];
+    double minv[8];
+};
+
+// Device-resident CG scalars (one per ctx).  All kernels read/write it; the host polls it.
+#define CFB_HIST_MAX 8192
+struct CgState
+{
+    // global values (after the allreduce when multi-GPU); (rz_new, rr) are adjacent on purpose:
+    // they travel in one 2-element allreduce, pAp in a 1-element one.
+    double rz_old, pAp, rz_new, rr;
+    double bnorm;                   // sqrt(rr) of r0
+    double thresh;                  // absolute threshold in use
+    int iter;                       // completed iterations (kernel-1 executions)
+    int done;                       // 1 once sqrt(rr) <= thresh
+    int fixed;                      // fixed-iteration mode: never set done
+    int pad;
+    unsigned int ticket[4];         // last-block tickets: [0] init/axpy, [1] stencil
+    double hist[CFB_HIST_MAX];
+};
+
+struct InflowConst
+{
+    double lo[3], hi[3], vel[3], quantity, force_dt[3];
+};
+
+#define CFB_MAX_PARTIALS 4096
+#define CFB_KTIMED 64
+
+struct cfb_ctx
+{
+    cfb_config cfg{};
+    Geo g{};
+    OpConst op{};
+    InflowConst inflow{};
+    std::string err;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+
+    // fields: [id][version]; only q,u,v,w have two versions
+    double* fld[4][2] = { { nullptr } };
+    int cur[4] = { 0, 0, 0, 0 };
+    double *lhs = nullptr, *rhs = nullptr, *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr;
+
+    CgState* d_state = nullptr;
+    CgState* h_state = nullptr; // pinned mirror (first bytes only are copied)
+    double* d_partials = nullptr; // [2][CFB_MAX_PARTIALS] scratch for block partial sums
+
+    // stencil TMA descriptor + tiling
+    CUtensorMap tmap_p{};
+    bool tmap_ok = false;
+    int st_variant = 0; // 0 = TMA z-march (default)
+    int st_tx = 64, st_ty = 16, st_stages = 4, st_zc = 64;
+    int poll_every = 0; // 0 = auto
+
+    // stats
+    cudaEvent_t ev[16] = { nullptr };
+    bool ev_pending[8] = { false };
+    bool time_kernels = false;
+    int ktimed = 0;
+    cudaEvent_t kev[CFB_KTIMED][4] = { { nullptr } };
+    cfb_stats stats{};
+    int last_iters = 0;
+    double last_resid = 0;
+    std::vector<double> hist;
+
+    // multi-GPU
+    void* nccl = nullptr; // NcclComm*, see halo.cu
+    double* d_halo_send[6] = { nullptr };
+    double* d_halo_recv[6] = { nullptr };
+    size_t halo_buf_elems = 0;
+    int nbr[6] = { -1, -1, -1, -1, -1, -1 }; // neighbour ranks: [2*d] low, [2*d+1] high
+};
+
+extern std::string g_cfb_error;
+
+int cfb_fail( cfb_ctx* c, int code, const std::string& msg );
+
+#define CFB_CUDA( c, expr )                                                                        \
+    do                                                                                             \
+    {                                                                                              \
+        cudaError_t _e = ( expr );                                                                 \
+        if ( _e != cudaSuccess )                                                                   \
+            return cfb_fail( ( c ), CFB_ERR_CUDA,                                                  \
+                             std::string( #expr ) + ": " + cudaGetErrorString( _e ) + " at " +     \
+                                 __FILE__ + ":" + std::to_string( __LINE__ ) );                    \
+    } while ( 0 )
+
+inline double* field_ptr( cfb_ctx* c, int field, int version )
+{
+    if ( field >= CFB_QUANTITY && field <= CFB_W )
+    {
+        if ( field > c->g.D )
+            return nullptr;
+        int v = version == CFB_CURRENT ? c->cur[field] : 1 - c->cur[field];
+        return c->fld[field][v];
+    }
+    switch ( field )
+    {
+    case CFB_PRESSURE:
+        return c->lhs;
+    case CFB_RHS:
+        return c->rhs;
+    case CFB_CG_R:
+        return c->cg_r;
+    case CFB_CG_P:
+        return c->cg_p;
+    case CFB_CG_Q:
+        return c->cg_q;
+    }
+    return nullptr;
+}
+
+// ---- kernel launchers (each returns the number of kernels it enqueued) -----------------------
+// kernels_fields.cu
+int launch_add_inputs( cfb_ctx* c );
+int launch_advect( cfb_ctx* c );
+int launch_apply_pressure( cfb_ctx* c );
+int launch_fill_synthetic( cfb_ctx* c, int variant, uint64_t seed );
+// kernels_cg.cu
+int launch_divergence( cfb_ctx* c );          // rhs = -div/h ; lhs = 0
+int launch_cg_init( cfb_ctx* c, int fixed );  // x=0, r=b, p=Minv r, rr, rz ; + check kernel
+int launch_cg_axpy( cfb_ctx* c );             // kernel 1 (+ fused kernel-2 reduction)
+int launch_cg_pupdate( cfb_ctx* c );          // convergence bookkeeping + kernel 3
+// kernels_stencil.cu
+int stencil_setup( cfb_ctx* c );              // builds the tensor map for cg_p
+int launch_stencil_dot( cfb_ctx* c );         // kernel 4
+// halo.cu
+int halo_init( cfb_ctx* c );
+void halo_destroy( cfb_ctx* c );
+int halo_exchange_cells( cfb_ctx* c, double* field, int width ); // face-neighbour exchange of a cell array
+int halo_exchange_fields( cfb_ctx* c, int version );             // width-h exchange of q,u,v,w
+int halo_allreduce( cfb_ctx* c, double* dev_vals, int n );

@@ -1,0 +1,422 @@
+// halo.cu — multi-GPU plumbing: one rank == one process == one GPU (like one MPI rank == one Kokkos
+// device in the reference), ghost exchange and CG scalar reductions over NCCL (NVLink 5 / NVSwitch).
+//
+// Replaces:
+//   Cajita::Halo::gather of the advection halo   src/ProblemManager.hpp:173-176,394-403
+//       NodeHaloPattern (26 neighbours in 3-D), width = halo cell width, q,u,v(,w) jointly
+//       -> three axis sweeps (x, then y incl. x ghosts, then z incl. x,y ghosts): 6 messages,
+//          corners and edges arrive transitively; all fields travel in one message per neighbour.
+//   Cajita::Halo::gather of the pressure halo    src/VelocityCorrector.hpp:112-113,236
+//   the CG's per-iteration gather of p (width 1, face neighbours only)
+//       -> one pack kernel for all faces, one ncclGroup of send/recv, one unpack kernel.
+//   MPI_Allreduce of the CG scalars               (Cajita ReferenceConjugateGradient)
+//       -> ncclAllReduce on the device-resident CgState; nothing comes back to the host.
+//
+// NCCL is bound at run time with dlopen("libnccl.so.2"): a single-GPU run has no NCCL dependency and
+// a torch process shares the NCCL it already loaded.  Two communicators are created so that halo
+// traffic (side stream) and scalar reductions (main stream) never share a communicator.
+#include "cfb_internal.h"
+#include "device_geo.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace
+{
+
+struct NcclApi
+{
+    void* handle = nullptr;
+    ncclResult_t ( *GetUniqueId )( ncclUniqueId* ) = nullptr;
+    ncclResult_t ( *CommInitRank )( ncclComm_t*, int, ncclUniqueId, int ) = nullptr;
+    ncclResult_t ( *CommDestroy )( ncclComm_t ) = nullptr;
+    ncclResult_t ( *Send )( const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t ) = nullptr;
+    ncclResult_t ( *Recv )( void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t ) = nullptr;
+    ncclResult_t ( *AllReduce )( const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                                 cudaStream_t ) = nullptr;
+    ncclResult_t ( *GroupStart )() = nullptr;
+    ncclResult_t ( *GroupEnd )() = nullptr;
+    const char* ( *GetErrorString )( ncclResult_t ) = nullptr;
+};
+
+NcclApi g_nccl;
+
+bool nccl_load( std::string& err )
+{
+    if ( g_nccl.handle )
+        return true;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    void* h = nullptr;
+    for ( const char* n : names )
+    {
+        h = dlopen( n, RTLD_NOW | RTLD_GLOBAL );
+        if ( h )
+            break;
+    }
+    if ( !h )
+    {
+        err = std::string( "dlopen(libnccl.so.2) failed: " ) + dlerror();
+        return false;
+    }
+#define BIND( field, sym )                                                                         \
+    g_nccl.field = reinterpret_cast<decltype( g_nccl.field )>( dlsym( h, sym ) );                  \
+    if ( !g_nccl.field )                                                                           \
+    {                                                                                              \
+        err = std::string( "NCCL symbol missing: " ) + sym;                                        \
+        return false;                                                                              \
+    }
+    BIND( GetUniqueId, "ncclGetUniqueId" )
+    BIND( CommInitRank, "ncclCommInitRank" )
+    BIND( CommDestroy, "ncclCommDestroy" )
+    BIND( Send, "ncclSend" )
+    BIND( Recv, "ncclRecv" )
+    BIND( AllReduce, "ncclAllReduce" )
+    BIND( GroupStart, "ncclGroupStart" )
+    BIND( GroupEnd, "ncclGroupEnd" )
+    BIND( GetErrorString, "ncclGetErrorString" )
+#undef BIND
+    g_nccl.handle = h;
+    return true;
+}
+
+struct Comm
+{
+    ncclComm_t halo = nullptr; // send/recv on the side stream
+    ncclComm_t red = nullptr;  // allreduce on the main stream
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+};
+
+#define CFB_NCCL( c, expr )                                                                        \
+    do                                                                                             \
+    {                                                                                              \
+        ncclResult_t _r = ( expr );                                                                \
+        if ( _r != ncclSuccess )                                                                   \
+            return cfb_fail( ( c ), CFB_ERR_NCCL,                                                  \
+                             std::string( #expr ) + ": " + g_nccl.GetErrorString( _r ) );          \
+    } while ( 0 )
+
+// A box of owned-index space [lo, hi) per dim, copied for `nf` fields into / out of a dense buffer.
+struct Box
+{
+    int lo[3], hi[3];
+    __host__ __device__ long long count() const
+    {
+        return (long long)( hi[0] - lo[0] ) * ( hi[1] - lo[1] ) * ( hi[2] - lo[2] );
+    }
+};
+
+struct PackArgs
+{
+    int nbox;        // number of boxes handled by this launch (<= 6)
+    int nf;          // fields per box
+    Box box[6];
+    double* buf[6];  // dense buffer of box b: [field][k][j][i]
+    double* fld[4];  // field base pointers
+};
+
+template <bool PACK>
+__global__ void __launch_bounds__( 256 )
+    pack_kernel( const __grid_constant__ Geo g, const __grid_constant__ PackArgs a )
+{
+    const int b = blockIdx.y;
+    if ( b >= a.nbox )
+        return;
+    const Box& bx = a.box[b];
+    const int ex = bx.hi[0] - bx.lo[0], ey = bx.hi[1] - bx.lo[1];
+    const long long per = bx.count();
+    const long long total = per * a.nf;
+    double* buf = a.buf[b];
+    for ( long long t = blockIdx.x * 256ll + threadIdx.x; t < total; t += (long long)gridDim.x * 256 )
+    {
+        const int f = (int)( t / per );
+        const long long r = t - f * per;
+        const int i = (int)( r % ex ) + bx.lo[0];
+        const int j = (int)( ( r / ex ) % ey ) + bx.lo[1];
+        const int k = (int)( r / ( (long long)ex * ey ) ) + bx.lo[2];
+        double* p = a.fld[f] + geo_off( g, i, j, k );
+        if ( PACK )
+            buf[t] = *p;
+        else
+            *p = buf[t];
+    }
+}
+
+int launch_pack( cfb_ctx* c, const PackArgs& a, bool pack, cudaStream_t st )
+{
+    long long mx = 1;
+    for ( int b = 0; b < a.nbox; ++b )
+        mx = std::max( mx, a.box[b].count() * a.nf );
+    int gx = (int)std::min<long long>( ( mx + 255 ) / 256, (long long)c->sm_count * 8 );
+    dim3 grid( gx, a.nbox );
+    if ( pack )
+        pack_kernel<true><<<grid, 256, 0, st>>>( c->g, a );
+    else
+        pack_kernel<false><<<grid, 256, 0, st>>>( c->g, a );
+    c->stats.kernel_launches += 1;
+    return 1;
+}
+
+inline int rank_of( const cfb_config& cfg, int bx, int by, int bz )
+{
+    return ( bz * cfg.ranks_per_dim[1] + by ) * cfg.ranks_per_dim[0] + bx;
+}
+
+// Exchange along the listed dims: boxes `send_lo/hi` go to the low/high neighbour, `recv_lo/hi` are
+// filled from them.  All transfers of one call form a single NCCL group on stream `st`.
+int exchange( cfb_ctx* c, int nf, double* const fld[4], int ndims, const int dims[3], const Box send_lo[3],
+              const Box send_hi[3], const Box recv_lo[3], const Box recv_hi[3], cudaStream_t st )
+{
+    Comm* cm = static_cast<Comm*>( c->nccl );
+    PackArgs pk{}, up{};
+    pk.nf = up.nf = nf;
+    for ( int f = 0; f < nf; ++f )
+        pk.fld[f] = up.fld[f] = fld[f];
+    struct Xfer
+    {
+        int peer;
+        double *sbuf, *rbuf;
+        size_t scount, rcount;
+    } x[6];
+    int nx = 0;
+    for ( int q = 0; q < ndims; ++q )
+    {
+        const int d = dims[q];
+        for ( int side = 0; side < 2; ++side )
+        {
+            const int peer = c->nbr[2 * d + side];
+            if ( peer < 0 )
+                continue;
+            const Box& sb = side == 0 ? send_lo[q] : send_hi[q];
+            const Box& rb = side == 0 ? recv_lo[q] : recv_hi[q];
+            const int slot = 2 * d + side;
+            if ( (size_t)( sb.count() * nf ) > c->halo_buf_elems || (size_t)( rb.count() * nf ) > c->halo_buf_elems )
+                return cfb_fail( c, CFB_ERR_INVALID, "halo buffer too small" );
+            pk.box[pk.nbox] = sb;
+            pk.buf[pk.nbox++] = c->d_halo_send[slot];
+            up.box[up.nbox] = rb;
+            up.buf[up.nbox++] = c->d_halo_recv[slot];
+            x[nx++] = { peer, c->d_halo_send[slot], c->d_halo_recv[slot], (size_t)( sb.count() * nf ),
+                        (size_t)( rb.count() * nf ) };
+        }
+    }
+    if ( nx == 0 )
+        return CFB_OK;
+    launch_pack( c, pk, true, st );
+    CFB_NCCL( c, g_nccl.GroupStart() );
+    for ( int i = 0; i < nx; ++i )
+    {
+        CFB_NCCL( c, g_nccl.Send( x[i].sbuf, x[i].scount, ncclDouble, x[i].peer, cm->halo, st ) );
+        CFB_NCCL( c, g_nccl.Recv( x[i].rbuf, x[i].rcount, ncclDouble, x[i].peer, cm->halo, st ) );
+    }
+    CFB_NCCL( c, g_nccl.GroupEnd() );
+    launch_pack( c, up, false, st );
+    return CFB_OK;
+}
+
+} // namespace
+
+extern "C" int cfb_nccl_unique_id( unsigned char* id )
+{
+    std::string err;
+    if ( !nccl_load( err ) )
+        return cfb_fail( nullptr, CFB_ERR_NCCL, err );
+    static_assert( sizeof( ncclUniqueId ) == CFB_NCCL_ID_BYTES, "ncclUniqueId size" );
+    for ( int i = 0; i < 2; ++i )
+    {
+        ncclUniqueId u;
+        ncclResult_t r = g_nccl.GetUniqueId( &u );
+        if ( r != ncclSuccess )
+            return cfb_fail( nullptr, CFB_ERR_NCCL, g_nccl.GetErrorString( r ) );
+        std::memcpy( id + i * CFB_NCCL_ID_BYTES, &u, CFB_NCCL_ID_BYTES );
+    }
+    return CFB_OK;
+}
+
+int halo_init( cfb_ctx* c )
+{
+    std::string err;
+    if ( !nccl_load( err ) )
+        return cfb_fail( c, CFB_ERR_NCCL, err );
+    const cfb_config& cfg = c->cfg;
+    const Geo& g = c->g;
+    int nranks = 1;
+    for ( int d = 0; d < g.D; ++d )
+        nranks *= cfg.ranks_per_dim[d];
+    if ( nranks != cfg.world_size )
+        return cfb_fail( c, CFB_ERR_INVALID, "ranks_per_dim does not multiply to world_size" );
+    const int b[3] = { cfg.block_id[0], cfg.block_id[1], g.D == 3 ? cfg.block_id[2] : 0 };
+    if ( rank_of( cfg, b[0], b[1], b[2] ) != cfg.world_rank )
+        return cfb_fail( c, CFB_ERR_INVALID, "world_rank must equal (bz*py + by)*px + bx" );
+    for ( int d = 0; d < g.D; ++d )
+    {
+        int lo[3] = { b[0], b[1], b[2] }, hi[3] = { b[0], b[1], b[2] };
+        lo[d] -= 1;
+        hi[d] += 1;
+        c->nbr[2 * d] = b[d] > 0 ? rank_of( cfg, lo[0], lo[1], lo[2] ) : -1;
+        c->nbr[2 * d + 1] = b[d] < cfg.ranks_per_dim[d] - 1 ? rank_of( cfg, hi[0], hi[1], hi[2] ) : -1;
+    }
+    Comm* cm = new Comm();
+    c->nccl = cm;
+    ncclUniqueId id0, id1;
+    std::memcpy( &id0, cfg.nccl_id, CFB_NCCL_ID_BYTES );
+    std::memcpy( &id1, cfg.nccl_id + CFB_NCCL_ID_BYTES, CFB_NCCL_ID_BYTES );
+    CFB_NCCL( c, g_nccl.CommInitRank( &cm->halo, cfg.world_size, id0, cfg.world_rank ) );
+    CFB_NCCL( c, g_nccl.CommInitRank( &cm->red, cfg.world_size, id1, cfg.world_rank ) );
+    CFB_CUDA( c, cudaEventCreateWithFlags( &cm->ev_ready, cudaEventDisableTiming ) );
+    CFB_CUDA( c, cudaEventCreateWithFlags( &cm->ev_done, cudaEventDisableTiming ) );
+    // buffers: (D+1) fields x (halo+1) layers x the largest ghosted face
+    long long e[3] = { g.n[0] + 1 + 2 * g.h, g.n[1] + 1 + 2 * g.h, g.n[2] + 1 + 2 * g.h };
+    long long face = std::max( e[0] * e[1], std::max( e[0] * e[2], e[1] * e[2] ) );
+    c->halo_buf_elems = (size_t)( face * ( g.h + 1 ) * ( g.D + 1 ) );
+    for ( int s = 0; s < 2 * g.D; ++s )
+    {
+        if ( c->nbr[s] < 0 )
+            continue;
+        CFB_CUDA( c, cudaMalloc( &c->d_halo_send[s], c->halo_buf_elems * sizeof( double ) ) );
+        CFB_CUDA( c, cudaMalloc( &c->d_halo_recv[s], c->halo_buf_elems * sizeof( double ) ) );
+    }
+    // warm both communicators up (connection setup happens on first use)
+    CFB_NCCL( c, g_nccl.AllReduce( &c->d_state->pAp, &c->d_state->pAp, 1, ncclDouble, ncclSum, cm->red, c->stream ) );
+    CFB_NCCL( c, g_nccl.AllReduce( &c->d_state->rr, &c->d_state->rr, 1, ncclDouble, ncclSum, cm->halo, c->comm_stream ) );
+    CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    CFB_CUDA( c, cudaStreamSynchronize( c->comm_stream ) );
+    CFB_CUDA( c, cudaMemsetAsync( c->d_state, 0, sizeof( CgState ), c->stream ) );
+    CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    return CFB_OK;
+}
+
+void halo_destroy( cfb_ctx* c )
+{
+    Comm* cm = static_cast<Comm*>( c->nccl );
+    if ( cm )
+    {
+        if ( cm->halo )
+            g_nccl.CommDestroy( cm->halo );
+        if ( cm->red )
+            g_nccl.CommDestroy( cm->red );
+        if ( cm->ev_ready )
+            cudaEventDestroy( cm->ev_ready );
+        if ( cm->ev_done )
+            cudaEventDestroy( cm->ev_done );
+        delete cm;
+        c->nccl = nullptr;
+    }
+    for ( int s = 0; s < 6; ++s )
+    {
+        if ( c->d_halo_send[s] )
+            cudaFree( c->d_halo_send[s] );
+        if ( c->d_halo_recv[s] )
+            cudaFree( c->d_halo_recv[s] );
+        c->d_halo_send[s] = c->d_halo_recv[s] = nullptr;
+    }
+}
+
+// Width-`w` face-neighbour exchange of one cell array (p of the CG, the pressure before
+// _applyPressure), enqueued on the SIDE stream: halo_cells_begin() forks from the main stream,
+// halo_cells_end() joins.  Between the two the caller may launch work that does not read ghosts.
+int halo_cells_begin( cfb_ctx* c, double* field, int w )
+{
+    Comm* cm = static_cast<Comm*>( c->nccl );
+    const Geo& g = c->g;
+    CFB_CUDA( c, cudaEventRecord( cm->ev_ready, c->stream ) );
+    CFB_CUDA( c, cudaStreamWaitEvent( c->comm_stream, cm->ev_ready, 0 ) );
+    int dims[3] = { 0, 1, 2 };
+    Box slo[3], shi[3], rlo[3], rhi[3];
+    for ( int d = 0; d < g.D; ++d )
+    {
+        Box full;
+        for ( int e = 0; e < 3; ++e )
+        {
+            full.lo[e] = 0;
+            full.hi[e] = g.n[e];
+        }
+        slo[d] = shi[d] = rlo[d] = rhi[d] = full;
+        slo[d].lo[d] = 0;
+        slo[d].hi[d] = w; // my first w layers -> low neighbour's high ghosts
+        shi[d].lo[d] = g.n[d] - w;
+        shi[d].hi[d] = g.n[d];
+        rlo[d].lo[d] = -w;
+        rlo[d].hi[d] = 0;
+        rhi[d].lo[d] = g.n[d];
+        rhi[d].hi[d] = g.n[d] + w;
+    }
+    double* fl[4] = { field, nullptr, nullptr, nullptr };
+    int rc = exchange( c, 1, fl, g.D, dims, slo, shi, rlo, rhi, c->comm_stream );
+    if ( rc )
+        return rc;
+    CFB_CUDA( c, cudaEventRecord( cm->ev_done, c->comm_stream ) );
+    return CFB_OK;
+}
+
+int halo_cells_end( cfb_ctx* c )
+{
+    Comm* cm = static_cast<Comm*>( c->nccl );
+    CFB_CUDA( c, cudaStreamWaitEvent( c->stream, cm->ev_done, 0 ) );
+    return CFB_OK;
+}
+
+int halo_exchange_cells( cfb_ctx* c, double* field, int width )
+{
+    int rc = halo_cells_begin( c, field, width );
+    if ( rc )
+        return rc;
+    return halo_cells_end( c );
+}
+
+// ProblemManager::gather: width-h exchange of q,u,v(,w) including edges and corners, as three axis
+// sweeps on the main stream.  Along the sweep axis d the low ghosts [-h, 0) come from the low
+// neighbour's last h layers and the high ghosts [n, n+h] (h+1 layers: the face on the block
+// boundary is owned by the upper block) from the high neighbour's first h+1 layers; tangentially the
+// sweeps cover owned+1, then the x ghosts, then x and y ghosts.
+int halo_exchange_fields( cfb_ctx* c, int version )
+{
+    const Geo& g = c->g;
+    double* fl[4] = { nullptr, nullptr, nullptr, nullptr };
+    for ( int f = 0; f <= g.D; ++f )
+        fl[f] = field_ptr( c, f, version );
+    for ( int d = 0; d < g.D; ++d )
+    {
+        Box t; // tangential extent of this sweep
+        for ( int e = 0; e < 3; ++e )
+        {
+            if ( e >= g.D )
+            {
+                t.lo[e] = 0;
+                t.hi[e] = 1;
+            }
+            else if ( e < d )
+            {
+                t.lo[e] = -g.h;
+                t.hi[e] = g.n[e] + g.h + 1;
+            }
+            else
+            {
+                t.lo[e] = 0;
+                t.hi[e] = g.n[e] + 1;
+            }
+        }
+        Box slo = t, shi = t, rlo = t, rhi = t;
+        slo.lo[d] = 0;
+        slo.hi[d] = g.h + 1; // -> low neighbour's high ghosts [n, n+h]
+        shi.lo[d] = g.n[d] - g.h;
+        shi.hi[d] = g.n[d]; // -> high neighbour's low ghosts [-h, 0)
+        rlo.lo[d] = -g.h;
+        rlo.hi[d] = 0;
+        rhi.lo[d] = g.n[d];
+        rhi.hi[d] = g.n[d] + g.h + 1;
+        int dims[1] = { d };
+        int rc = exchange( c, g.D + 1, fl, 1, dims, &slo, &shi, &rlo, &rhi, c->stream );
+        if ( rc )
+            return rc;
+    }
+    return CFB_OK;
+}
+
+int halo_allreduce( cfb_ctx* c, double* dev_vals, int n )
+{
+    Comm* cm = static_cast<Comm*>( c->nccl );
+    CFB_NCCL( c, g_nccl.AllReduce( dev_vals, dev_vals, (size_t)n, ncclDouble, ncclSum, cm->red, c->stream ) );
+    return CFB_OK;
+}

@@ -1,0 +1,440 @@
+// kernels_stencil.cu — q = A p fused with sum(p.q): CG kernel 4, the dominant kernel of the path.
+//
+// A is the reference's pressure matrix (src/VelocityCorrector.hpp:116-144 with the boundary fix-up
+// of src/BoundaryConditions.hpp:56-97) applied matrix-free: no coefficient array is stored; the
+// diagonal follows from the number of SOLID walls a cell touches, off-domain neighbours are ghost
+// zeros (physical walls) or the neighbour rank's cells (block boundaries).
+//
+// Design (sm_100a, HBM-bound: 16 algorithmic bytes per cell = read p, write q):
+//   * one CTA owns a TX x TY tile of the x-y plane and marches ZC planes along z (2.5-D blocking):
+//     k-1 / k / k+1 centre values live in registers, the x/y neighbours of plane k come from
+//     shared memory;
+//   * planes are staged into a NS-deep shared-memory ring by TMA (cp.async.bulk.tensor.3d, box
+//     (TX+4) x (TY+2) x 1 with mbarrier complete_tx), issued NS-1 planes ahead by one thread, so
+//     the load path costs no registers and no per-thread address arithmetic; out-of-range box
+//     parts are zero-filled by the TMA unit;
+//   * every thread owns column pairs: 128-bit LDS for the centre / y-neighbours, 128-bit
+//     coalesced STG of q (a warp stores 512 contiguous bytes);
+//   * p.q is accumulated per thread over its z-march, reduced with warp shuffles + one smem pass
+//     per CTA, and finalised deterministically by the last CTA (device_reduce.cuh).
+//   * a second variant (LDG, no shared memory) is kept for A/B measurements via cfb_set_tuning.
+#include "cfb_internal.h"
+#include "device_geo.cuh"
+#include "device_reduce.cuh"
+
+namespace
+{
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32( const void* p )
+{
+    return (uint32_t)__cvta_generic_to_shared( p );
+}
+__device__ __forceinline__ void mbar_init( uint32_t bar, uint32_t count )
+{
+    asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"( bar ), "r"( count ) : "memory" );
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" );
+}
+__device__ __forceinline__ void mbar_expect_tx( uint32_t bar, uint32_t bytes )
+{
+    asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"( bar ), "r"( bytes )
+                  : "memory" );
+}
+__device__ __forceinline__ bool mbar_try_wait( uint32_t bar, uint32_t parity )
+{
+    uint32_t ok;
+    asm volatile( "{\n"
+                  ".reg .pred P1;\n"
+                  "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+                  "selp.u32 %0, 1, 0, P1;\n"
+                  "}"
+                  : "=r"( ok )
+                  : "r"( bar ), "r"( parity )
+                  : "memory" );
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait( uint32_t bar, uint32_t parity )
+{
+    uint32_t spins = 0;
+    while ( !mbar_try_wait( bar, parity ) )
+        if ( ++spins > ( 1u << 22 ) )
+            __trap();
+}
+__device__ __forceinline__ void tma_load_3d( uint32_t dst, const CUtensorMap* map, uint32_t bar, int x,
+                                             int y, int z )
+{
+    asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+                  "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"( dst ),
+                  "l"( map ), "r"( bar ), "r"( x ), "r"( y ), "r"( z )
+                  : "memory" );
+}
+__device__ __forceinline__ void prefetch_tmap( const CUtensorMap* map )
+{
+    asm volatile( "prefetch.tensormap [%0];" ::"l"( map ) : "memory" );
+}
+
+// ---- the 7-point row of A, in the reference's stencil order ---------------------------------
+// {0}, {-x}, {+x}, {-y}, {+y}, {-z}, {+z}; one fused multiply-add per term (bit-identical to the
+// checker's apply_A).
+__device__ __forceinline__ double apply_row( double diag, double ns, double c, double xm, double xp,
+                                             double ym, double yp, double zm, double zp )
+{
+    double a = diag * c;
+    a = fma( ns, xm, a );
+    a = fma( ns, xp, a );
+    a = fma( ns, ym, a );
+    a = fma( ns, yp, a );
+    a = fma( ns, zm, a );
+    a = fma( ns, zp, a );
+    return a;
+}
+
+template <int TX_, int TY_, int NS_>
+struct TileCfg
+{
+    static constexpr int TX = TX_, TY = TY_, NS = NS_;
+    static constexpr int NT = 256;
+    static constexpr int LX = TX / 2;  // threads along x (one column pair each)
+    static constexpr int WY = NT / LX; // thread rows
+    static constexpr int RY = TY / WY; // rows per thread
+    static constexpr int PX = TX + 4;  // smem row pitch in doubles: 2-wide x halo keeps pairs 16-B aligned
+    static constexpr int PY = TY + 2;
+    static constexpr int BOX_BYTES = PX * PY * 8;
+    static constexpr int STAGE_BYTES = ( BOX_BYTES + 127 ) / 128 * 128;
+    static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 128;
+    static_assert( TX % 2 == 0 && NT % LX == 0 && TY % WY == 0 && RY >= 1, "bad tile" );
+};
+
+struct StencilArgs
+{
+    double* q;
+    CgState* S;
+    double* partials;
+    int tiles_x, tiles_y, zc, hx;
+};
+
+template <class C>
+__global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) )
+    stencil7_dot_tma( const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geo g,
+                      const __grid_constant__ OpConst op, const __grid_constant__ StencilArgs a )
+{
+    constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
+    if ( a.S->done )
+        return;
+
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__( 8 ) unsigned long long full_bar[NS];
+
+    const uint32_t smem_base = ( smem_u32( smem_raw ) + 127u ) & ~127u;
+    const double* stage0 =
+        reinterpret_cast<const double*>( smem_raw + ( smem_base - smem_u32( smem_raw ) ) );
+
+    const int tid = threadIdx.x;
+    const int lx = tid % LX, wy = tid / LX;
+
+    // unit -> (tile_x, tile_y, z chunk)
+    const int u = blockIdx.x;
+    const int tx = u % a.tiles_x;
+    const int ty = ( u / a.tiles_x ) % a.tiles_y;
+    const int ch = u / ( a.tiles_x * a.tiles_y );
+    const int x0 = tx * TX, y0 = ty * TY;
+    const int kbeg = ch * a.zc;
+    const int kend = min( kbeg + a.zc, g.n[2] );
+    const int nplanes = kend - kbeg; // planes to compute
+    const int nloads = nplanes + 2;  // planes kbeg-1 .. kend
+
+    // TMA box origin (array coordinates): 2 columns left of the tile, 1 row below, plane kbeg-1
+    const int cx = a.hx + x0 - 2;
+    const int cy = g.h + y0 - 1;
+    const int cz = g.h + kbeg - 1;
+
+    if ( tid == 0 )
+    {
+        prefetch_tmap( &tmap );
+#pragma unroll
+        for ( int s = 0; s < NS; ++s )
+            mbar_init( smem_u32( &full_bar[s] ), 1 );
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if ( tid == 0 )
+    {
+        const int n0 = nloads < NS ? nloads : NS;
+        for ( int l = 0; l < n0; ++l )
+        {
+            const uint32_t bar = smem_u32( &full_bar[l] );
+            mbar_expect_tx( bar, C::BOX_BYTES );
+            tma_load_3d( smem_base + l * C::STAGE_BYTES, &tmap, bar, cx, cy, cz + l );
+        }
+    }
+
+    // per-thread constants: validity and SOLID-wall counts of my cells
+    const int i0 = x0 + 2 * lx; // owned x index of the first cell of my pair
+    const bool vx0 = i0 < g.n[0], vx1 = i0 + 1 < g.n[0];
+    const int wx0 = wall_count( g, 0, i0 + g.off[0] );
+    const int wx1 = wall_count( g, 0, i0 + 1 + g.off[0] );
+    int wyc[RY];
+    bool vy[RY];
+#pragma unroll
+    for ( int r = 0; r < RY; ++r )
+    {
+        const int j = y0 + wy + r * WY;
+        vy[r] = j < g.n[1];
+        wyc[r] = wall_count( g, 1, j + g.off[1] );
+    }
+    const double ns = op.neg_scale;
+
+    double2 zm[RY], cc[RY];
+    mbar_wait( smem_u32( &full_bar[0] ), 0 );
+    mbar_wait( smem_u32( &full_bar[1 % NS] ), ( 1 / NS ) & 1 );
+#pragma unroll
+    for ( int r = 0; r < RY; ++r )
+    {
+        const int row = wy + r * WY + 1;
+        zm[r] = *reinterpret_cast<const double2*>( stage0 + row * PX + 2 * lx + 2 );
+        cc[r] = *reinterpret_cast<const double2*>( stage0 + ( 1 % NS ) * ( C::STAGE_BYTES / 8 ) + row * PX +
+                                                   2 * lx + 2 );
+    }
+
+    // slot 0 (plane kbeg-1) only feeds the zm registers: once every thread has read it, it takes
+    // load NS.  From here on slot (it+1) % NS is released at the end of iteration `it`.
+    __syncthreads();
+    if ( tid == 0 && NS < nloads )
+    {
+        const uint32_t bar = smem_u32( &full_bar[0] );
+        mbar_expect_tx( bar, C::BOX_BYTES );
+        tma_load_3d( smem_base, &tmap, bar, cx, cy, cz + NS );
+    }
+
+    double acc = 0.0;
+    double* qrow = a.q + geo_off( g, i0, y0 + wy, kbeg );
+    for ( int it = 0; it < nplanes; ++it )
+    {
+        const int lc = it + 1, ln = it + 2; // load indices of plane k and plane k+1
+        const int sc = lc % NS, sn = ln % NS;
+        mbar_wait( smem_u32( &full_bar[sn] ), ( ln / NS ) & 1 );
+        const double* P = stage0 + sc * ( C::STAGE_BYTES / 8 );
+        const double* N = stage0 + sn * ( C::STAGE_BYTES / 8 );
+        const int wz = wall_count( g, 2, kbeg + it + g.off[2] );
+#pragma unroll
+        for ( int r = 0; r < RY; ++r )
+        {
+            const int row = wy + r * WY + 1;
+            const double* pc = P + row * PX + 2 * lx + 2;
+            const double2 zp = *reinterpret_cast<const double2*>( N + row * PX + 2 * lx + 2 );
+            const double xl = pc[-1];
+            const double xr = pc[2];
+            const double2 ym = *reinterpret_cast<const double2*>( pc - PX );
+            const double2 yp = *reinterpret_cast<const double2*>( pc + PX );
+            const double2 c = cc[r];
+            const double d0 = op.diag[wx0 + wyc[r] + wz];
+            const double d1 = op.diag[wx1 + wyc[r] + wz];
+            const double a0 = apply_row( d0, ns, c.x, xl, c.y, ym.x, yp.x, zm[r].x, zp.x );
+            const double a1 = apply_row( d1, ns, c.y, c.x, xr, ym.y, yp.y, zm[r].y, zp.y );
+            if ( vy[r] )
+            {
+                double* qp = qrow + (long long)( r * WY ) * g.sy;
+                if ( vx1 )
+                {
+                    *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
+                    acc += c.x * a0;
+                    acc += c.y * a1;
+                }
+                else if ( vx0 )
+                {
+                    *qp = a0;
+                    acc += c.x * a0;
+                }
+            }
+            zm[r] = c;
+            cc[r] = zp;
+        }
+        qrow += g.sz;
+        __syncthreads(); // every thread is done with slot sc -> it can be refilled
+        if ( tid == 0 && lc + NS < nloads )
+        {
+            const uint32_t bar = smem_u32( &full_bar[sc] );
+            mbar_expect_tx( bar, C::BOX_BYTES );
+            tma_load_3d( smem_base + sc * C::STAGE_BYTES, &tmap, bar, cx, cy, cz + lc + NS );
+        }
+    }
+
+    double vals[1] = { acc };
+    if ( block_reduce_finalize<C::NT, 1>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
+    {
+        if ( tid == 0 )
+        {
+            a.S->pAp = vals[0];
+            a.S->rz_old = a.S->rz_new; // kernel "zTr_old = zTr_new" of the CG loop
+        }
+    }
+}
+
+// ---- variant 1: no shared memory, register z-blocking, neighbours through L1/L2 -------------
+// block = 32 x 8 threads, each thread owns one column pair and marches ZC planes.
+__global__ void __launch_bounds__( 256, 4 )
+    stencil7_dot_ldg( const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
+                      const double* __restrict__ p, const __grid_constant__ StencilArgs a )
+{
+    if ( a.S->done )
+        return;
+    const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    const int u = blockIdx.x;
+    const int tx = u % a.tiles_x;
+    const int ty = ( u / a.tiles_x ) % a.tiles_y;
+    const int ch = u / ( a.tiles_x * a.tiles_y );
+    const int i0 = tx * 64 + 2 * lx, j = ty * 8 + wy;
+    const int kbeg = ch * a.zc, kend = min( kbeg + a.zc, g.n[2] );
+    const bool vy = j < g.n[1], vx0 = i0 < g.n[0], vx1 = i0 + 1 < g.n[0];
+    const int wxy0 = wall_count( g, 0, i0 + g.off[0] ) + wall_count( g, 1, j + g.off[1] );
+    const int wxy1 = wall_count( g, 0, i0 + 1 + g.off[0] ) + wall_count( g, 1, j + g.off[1] );
+    const double ns = op.neg_scale;
+    double acc = 0.0;
+    if ( vy && vx0 )
+    {
+        const double* pp = p + geo_off( g, i0, j, kbeg );
+        double* qp = a.q + geo_off( g, i0, j, kbeg );
+        double2 zm = *reinterpret_cast<const double2*>( pp - g.sz );
+        double2 c = *reinterpret_cast<const double2*>( pp );
+        for ( int k = kbeg; k < kend; ++k )
+        {
+            const double2 zp = __ldg( reinterpret_cast<const double2*>( pp + g.sz ) );
+            const double2 ym = __ldg( reinterpret_cast<const double2*>( pp - g.sy ) );
+            const double2 yp = __ldg( reinterpret_cast<const double2*>( pp + g.sy ) );
+            const double xl = __ldg( pp - 1 );
+            const double xr = __ldg( pp + 2 );
+            const int wz = wall_count( g, 2, k + g.off[2] );
+            const double a0 = apply_row( op.diag[wxy0 + wz], ns, c.x, xl, c.y, ym.x, yp.x, zm.x, zp.x );
+            const double a1 = apply_row( op.diag[wxy1 + wz], ns, c.y, c.x, xr, ym.y, yp.y, zm.y, zp.y );
+            if ( vx1 )
+            {
+                *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
+                acc += c.x * a0;
+                acc += c.y * a1;
+            }
+            else
+            {
+                *qp = a0;
+                acc += c.x * a0;
+            }
+            zm = c;
+            c = zp;
+            pp += g.sz;
+            qp += g.sz;
+        }
+    }
+    double vals[1] = { acc };
+    if ( block_reduce_finalize<256, 1>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
+    {
+        if ( threadIdx.x == 0 )
+        {
+            a.S->pAp = vals[0];
+            a.S->rz_old = a.S->rz_new;
+        }
+    }
+}
+
+typedef CUresult ( *PFN_encodeTiled )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                       CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                       CUtensorMapFloatOOBfill );
+
+template <class C>
+int launch_tma( cfb_ctx* c, const StencilArgs& a, int grid )
+{
+    static bool attr_set = false;
+    if ( !attr_set )
+    {
+        cudaFuncSetAttribute( stencil7_dot_tma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        attr_set = true;
+    }
+    stencil7_dot_tma<C><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a );
+    return 1;
+}
+
+} // namespace
+
+// (Re)build the tensor map of cg_p for the current tile shape.
+int stencil_setup( cfb_ctx* c )
+{
+    static PFN_encodeTiled encode = nullptr;
+    if ( !encode )
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres );
+        if ( e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn )
+            return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available" );
+        encode = (PFN_encodeTiled)fn;
+    }
+    const Geo& g = c->g;
+    cuuint64_t gdim[3] = { (cuuint64_t)g.sy, (cuuint64_t)g.ay, (cuuint64_t)g.az };
+    cuuint64_t gstride[2] = { (cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8 };
+    cuuint32_t box[3] = { (cuuint32_t)( c->st_tx + 4 ), (cuuint32_t)( c->st_ty + 2 ), 1 };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    CUresult r = encode( &c->tmap_p, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->cg_p, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+    if ( r != CUDA_SUCCESS )
+        return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string( (int)r ) );
+    c->tmap_ok = true;
+    return CFB_OK;
+}
+
+int launch_stencil_dot( cfb_ctx* c )
+{
+    const Geo& g = c->g;
+    StencilArgs a{};
+    a.q = c->cg_q;
+    a.S = c->d_state;
+    a.partials = c->d_partials;
+    a.hx = 16;
+    const int tx = c->st_variant == 1 ? 64 : c->st_tx;
+    const int ty = c->st_variant == 1 ? 8 : c->st_ty;
+    a.tiles_x = ( g.n[0] + tx - 1 ) / tx;
+    a.tiles_y = ( g.n[1] + ty - 1 ) / ty;
+    int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
+    // keep the number of CTAs (== partial sums) within the scratch buffer
+    while ( (long long)a.tiles_x * a.tiles_y * ( ( g.n[2] + zc - 1 ) / zc ) > CFB_MAX_PARTIALS )
+        zc *= 2;
+    a.zc = zc;
+    const int grid = a.tiles_x * a.tiles_y * ( ( g.n[2] + zc - 1 ) / zc );
+    if ( c->st_variant == 1 )
+    {
+        stencil7_dot_ldg<<<grid, 256, 0, c->stream>>>( g, c->op, c->cg_p, a );
+        return 1;
+    }
+    const int key = c->st_tx * 10000 + c->st_ty * 100 + c->st_stages;
+    switch ( key )
+    {
+    case 641604:
+        return launch_tma<TileCfg<64, 16, 4>>( c, a, grid );
+    case 641606:
+        return launch_tma<TileCfg<64, 16, 6>>( c, a, grid );
+    case 640804:
+        return launch_tma<TileCfg<64, 8, 4>>( c, a, grid );
+    case 643204:
+        return launch_tma<TileCfg<64, 32, 4>>( c, a, grid );
+    case 643203:
+        return launch_tma<TileCfg<64, 32, 3>>( c, a, grid );
+    case 1281604:
+        return launch_tma<TileCfg<128, 16, 4>>( c, a, grid );
+    case 1281603:
+        return launch_tma<TileCfg<128, 16, 3>>( c, a, grid );
+    case 1283203:
+        return launch_tma<TileCfg<128, 32, 3>>( c, a, grid );
+    case 1280804:
+        return launch_tma<TileCfg<128, 8, 4>>( c, a, grid );
+    default:
+        cfb_fail( c, CFB_ERR_INVALID, "unsupported stencil tile configuration" );
+        return 0;
+    }
+}

@@ -18,7 +18,7 @@
  * Array layout (device): every field lives in a padded 3-D box, x (i) fastest:
  *     offset(i,j,k) = (k + hz) * stride_z + (j + hy) * stride_y + (i + hx)
  * with (i,j,k) the 0-based OWNED index of the block, hx = 16 (128-byte aligned
- * first owned entity), hy = hz = halo width (hz = 0, one plane, when dim == 2).
+ * first owned entity), hy = hz = halo width (dim == 2: one owned plane between zero ghost planes).
  * All fields of one ctx share the same strides.  Ghost entities on physical
  * walls are allocated, zero-filled once and never written (reference behaviour:
  * src/ProblemManager.hpp:149-165, tests/tstMesh.cpp:61-68).
@@ -152,7 +152,8 @@ typedef struct cfb_config
     /* device / communicator */
     int32_t device_id;                         /* CUDA ordinal */
     int32_t use_nccl;                          /* 0 when world_size == 1 */
-    unsigned char nccl_id[CFB_NCCL_ID_BYTES];  /* ncclUniqueId from rank 0 (cfb_nccl_unique_id) */
+    /* two ncclUniqueIds from rank 0 (cfb_nccl_unique_id): halo communicator, reduction communicator */
+    unsigned char nccl_id[2 * CFB_NCCL_ID_BYTES];
 } cfb_config;
 
 typedef struct cfb_ctx cfb_ctx;
@@ -170,6 +171,11 @@ typedef struct cfb_stats
     int64_t kernel_launches;  /* our own kernels launched since create / reset */
     int64_t cg_iterations;    /* total CG iterations since create / reset */
     int64_t steps;            /* Solver::step calls */
+    /* per-kernel device time of the CG iterations bracketed with events ("time_kernels" tuning) */
+    double ms_k_axpy;
+    double ms_k_pupdate;
+    double ms_k_stencil;
+    int64_t k_timed_iters;
 } cfb_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------ */
@@ -180,7 +186,8 @@ int cfb_default_config( cfb_config* cfg, int dim );
 /* Split n cells over nb blocks the way Cajita's GlobalGrid does; returns owned count and offset. */
 int cfb_partition( int n, int nb, int block, int* owned, int* offset );
 
-/* rank-0 helper: ncclGetUniqueId into a CFB_NCCL_ID_BYTES buffer. */
+/* rank-0 helper: two ncclGetUniqueId results into a 2 * CFB_NCCL_ID_BYTES buffer; the caller
+ * broadcasts them to all ranks (torch.distributed / MPI_Bcast) and stores them in cfb_config. */
 int cfb_nccl_unique_id( unsigned char* id );
 
 /* Replaces createSolver(...) + Solver ctor (src/Solver.hpp:69-123,283-350):
@@ -207,7 +214,8 @@ int cfb_field_ptr( cfb_ctx* ctx, int field, int version, double** dev_ptr,
                    int64_t* origin, int64_t* stride_y, int64_t* stride_z );
 
 /* Host <-> device copy of a dense x-fastest host array covering `region` of the entity.
- * OWNED: ext from cfb_owned_extent; GHOSTED: ext + 2*halo in each spatial dim. */
+ * OWNED: ext from cfb_owned_extent; GHOSTED: Cajita's Ghost index space = owned CELLS + 2*halo in
+ * each spatial dim, +1 along a face normal on every block (tests/tstMesh.cpp:61-68). */
 int cfb_upload( cfb_ctx* ctx, int field, int version, int region, const double* host );
 int cfb_download( cfb_ctx* ctx, int field, int version, int region, double* host );
 

@@ -1,0 +1,78 @@
+"""Shared helpers for the parity tests: seeded inputs, paired (CUDA, oracle) contexts, norms."""
+import numpy as np
+
+from cajitafluids_b200 import config as K
+
+
+def rel_l2(a, b):
+    """relative L2 difference ||a-b|| / ||b||  (0 when both are zero)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    nb = np.linalg.norm(b.ravel())
+    nd = np.linalg.norm((a - b).ravel())
+    if nb == 0.0:
+        return 0.0 if nd == 0.0 else np.inf
+    return nd / nb
+
+
+def fields_of(dim):
+    return [K.QUANTITY, K.U, K.V] + ([K.W] if dim == 3 else [])
+
+
+def make_cfg(dim, cells, **kw):
+    bt = kw.pop("boundary_type", None)
+    fixed = kw.pop("fixed_iters", 0)
+    tol = kw.pop("tol", None)
+    max_iter = kw.pop("max_iter", None)
+    force = kw.pop("body_force", None)
+    cfg = K.default_config(dim, cells, **kw)
+    if bt is not None:
+        for i, b in enumerate(bt):
+            cfg.boundary_type[i] = b
+    cfg.cg_fixed_iters = fixed
+    if tol is not None:
+        cfg.cg_tolerance = tol
+    if max_iter is not None:
+        cfg.cg_max_iter = max_iter
+    if force is not None:
+        for d, f in enumerate(force):
+            cfg.body_force[d] = f
+    return cfg
+
+
+def smooth_velocity(ctx, rng, amp=1.0):
+    """A smooth, wall-compatible random MAC velocity (owned faces) with |u| <= amp: low-order
+    sin/cos modes with seeded random coefficients.  Returns {field: array[z,y,x]}."""
+    dim = ctx.dim
+    h = ctx.cell_size
+    off = ctx.global_offset()
+    out = {}
+    for d in range(dim):
+        f = K.U + d
+        shp = ctx.shape(f)  # (z, y, x)
+        ext = shp[::-1]
+        coords = []
+        for e in range(dim):
+            g = np.arange(ext[e]) + off[e]
+            coords.append(g * h if e == d else (g + 0.5) * h)
+        grids = np.meshgrid(*coords[::-1], indexing="ij")[::-1]  # x, y, (z) each shaped (z,y,x)/(y,x)
+        val = np.zeros(grids[0].shape)
+        for _ in range(3):
+            k = rng.integers(1, 4, size=dim)
+            ph = rng.uniform(0, 2 * np.pi, size=dim)
+            term = rng.uniform(-1, 1)
+            for e in range(dim):
+                term = term * (np.sin(np.pi * k[e] * grids[e]) if e == d else np.cos(np.pi * k[e] * grids[e] + ph[e]))
+            val = val + term
+        val = amp * val / max(np.abs(val).max(), 1e-30)
+        out[f] = val.reshape(shp)
+    return out
+
+
+def random_cells(ctx, rng, field=K.QUANTITY):
+    return rng.uniform(-1.0, 1.0, size=ctx.shape(field))
+
+
+def set_both(gpu, ora, field, arr, version=K.CURRENT, region=K.OWNED):
+    gpu.set(field, arr, version, region)
+    ora.set(field, arr, version, region)

@@ -26,9 +26,11 @@ def build():
 def load():
     global _lib
     if _lib is None:
-        src = os.path.join(ORACLE_DIR, "cfo_oracle.cpp")
-        if (not os.path.exists(ORACLE_LIB)) or os.path.getmtime(ORACLE_LIB) < os.path.getmtime(src):
-            build()
+        try:
+            build()  # make is a no-op when the .so is newer than cfo_oracle.cpp and include/cfb.h
+        except Exception:
+            if not os.path.exists(ORACLE_LIB):
+                raise
         _lib = Library(ORACLE_LIB, "cfo_")
         d = _lib.dll
         d.cfo_matrix_ptr.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_double)),

@@ -1,0 +1,255 @@
+"""Known-answer tests that pin the CPU oracle (SURVEY.md §8c list).  The reference has no test of
+this path and cannot be built here, so these analytic identities — together with the geometry
+assertions re-expressed in test_oracle_geometry.py — are what the oracle is anchored on.
+"""
+import numpy as np
+import pytest
+
+from cajitafluids_b200 import config as K
+from cajitafluids_b200._capi import CfbError
+from helpers import make_cfg, rel_l2
+from oracle_api import Oracle, spline_weights
+
+H = 3  # halo
+
+
+def box_for(cells):
+    return tuple(c / cells[0] for c in cells)
+
+
+# (1) discrete Neumann eigenvector of the all-SOLID operator -------------------------------------
+@pytest.mark.parametrize("cells,m", [((24, 16, 20), (3, 2, 5)), ((32, 32), (1, 4)), ((17, 9, 11), (0, 3, 1))])
+def test_stencil_eigenvector(cells, m):
+    dim = len(cells)
+    o = Oracle(make_cfg(dim, cells, box=box_for(cells)))
+    ax = [np.cos(np.pi * m[d] * (np.arange(cells[d]) + 0.5) / cells[d]) for d in range(dim)]
+    p = ax[0][None, None, :] * ax[1][None, :, None]
+    if dim == 3:
+        p = p * ax[2][:, None, None]
+    o.set(K.CG_P, p)
+    dot, _ = o.stencil_dot(1)
+    h, dt, _ = o.scalars()
+    scale = dt / (0.1 * h * h)
+    lam = scale * sum(2 - 2 * np.cos(np.pi * m[d] / cells[d]) for d in range(dim))
+    q = o.get(K.CG_Q)
+    assert rel_l2(q, lam * p) < 1e-13
+    assert abs(dot - lam * (p * p).sum()) <= 1e-12 * abs(dot) + 1e-300
+
+
+# (2) null space / FREE wall -----------------------------------------------------------------------
+def test_constant_is_in_the_null_space_with_solid_walls():
+    o = Oracle(make_cfg(3, 12))
+    o.set(K.CG_P, np.ones(o.shape(K.CG_P)))
+    o.stencil_dot(1)
+    assert np.abs(o.get(K.CG_Q)).max() < 1e-9
+
+
+def test_free_wall_is_dirichlet():
+    # one FREE wall (+x): A.1 == scale on that wall layer, 0 elsewhere
+    bt = [K.SOLID] * 6
+    bt[3] = K.FREE
+    o = Oracle(make_cfg(3, 12, boundary_type=bt))
+    o.set(K.CG_P, np.ones(o.shape(K.CG_P)))
+    o.stencil_dot(1)
+    q = o.get(K.CG_Q)
+    h, dt, _ = o.scalars()
+    scale = dt / (0.1 * h * h)
+    assert np.allclose(q[:, :, -1], scale, rtol=1e-12)
+    assert np.abs(q[:, :, :-1]).max() < 1e-9
+
+
+def test_matrix_and_jacobi_entries_2d_reference_values():
+    # src/VelocityCorrector.hpp:137-142,178 + src/BoundaryConditions.hpp:56-97
+    o = Oracle(make_cfg(2, 8))
+    A, Mi = o.matrix()
+    h, dt, _ = o.scalars()
+    s = dt / (0.1 * h * h)
+    interior = A[0, H + 3, H + 3]
+    assert np.allclose(interior, [4 * s, -s, -s, -s, -s])
+    corner = A[0, H, H]
+    assert np.allclose(corner, [2 * s, 0, -s, 0, -s])
+    edge = A[0, H + 7, H + 2]  # top row (gj = 7)
+    assert np.allclose(edge, [3 * s, -s, -s, -s, 0])
+    assert Mi[0, H + 3, H + 3] == 1.0 / interior[0]
+
+
+# (3) CG recovers a manufactured solution -------------------------------------------------------------
+@pytest.mark.parametrize("dim,n", [(2, 24), (3, 12)])
+def test_cg_recovers_manufactured_solution(dim, n):
+    o = Oracle(make_cfg(dim, n, tol=1e-11))
+    rng = np.random.default_rng(0)
+    xs = rng.uniform(-1, 1, size=o.shape(K.PRESSURE))
+    xs -= xs.mean()
+    o.set(K.CG_P, xs)
+    o.stencil_dot(1)
+    b = o.get(K.CG_Q)
+    o.set(K.RHS, b)
+    o.set(K.PRESSURE, np.zeros_like(b))
+    it, res = o.pcg_solve()
+    x = o.get(K.PRESSURE)
+    assert res <= 1e-11
+    assert rel_l2(x - x.mean(), xs) < 1e-8
+
+
+def test_cg_iteration_counts_in_survey_ranges():
+    # SURVEY §6 scratch estimate for the setup() projection of the default inflow
+    for dim, n, expect in ((2, 64, 218), (2, 128, 445), (3, 32, 141)):
+        o = Oracle(make_cfg(dim, n))
+        o.setup()
+        assert abs(o.stats()["cg_iterations"] - expect) <= 2
+
+
+def test_cg_max_iter_throws_like_cajita():
+    o = Oracle(make_cfg(2, 64, max_iter=10))
+    with pytest.raises(CfbError) as e:
+        o.setup()
+    assert e.value.code == K.ERR_NOT_CONVERGED
+
+
+# (4) projection ---------------------------------------------------------------------------------------
+def test_projection_divergence_free_and_walls_zero():
+    o = Oracle(make_cfg(3, 16, quirks=(0, 1), tol=1e-11))
+    rng = np.random.default_rng(1)
+    for f in (K.U, K.V, K.W):
+        o.set(f, rng.uniform(-1, 1, size=o.shape(f)))
+    o.add_inputs()
+    o.correct_velocity()
+    o.build_rhs()
+    assert np.linalg.norm(o.get(K.RHS).ravel()) < 1e-9
+    u, v, w = o.get(K.U), o.get(K.V), o.get(K.W)
+    assert not u[:, :, 0].any() and not u[:, :, -1].any()
+    assert not v[:, 0, :].any() and not v[:, -1, :].any()
+    assert not w[0].any() and not w[-1].any()
+
+
+# (5) B-splines -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order", [1, 3])
+def test_spline_partition_of_unity_and_closed_form(order):
+    for xl in (3.0, 3.25, 7.5, 10.999, 4.000001):
+        s, w = spline_weights(order, xl)
+        assert abs(sum(w) - 1.0) < 1e-15
+        f = xl - int(xl)
+        if order == 1:
+            assert s == [int(xl), int(xl) + 1]
+            assert np.allclose(w, [1 - f, f], atol=1e-16)
+        else:
+            assert s == [int(xl) - 1, int(xl), int(xl) + 1, int(xl) + 2]
+            ref = [(1 - f) ** 3 / 6, (3 * f ** 3 - 6 * f ** 2 + 4) / 6, (-3 * f ** 3 + 3 * f ** 2 + 3 * f + 1) / 6,
+                   f ** 3 / 6]
+            assert np.allclose(w, ref, atol=1e-15)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("order", [1, 3])
+@pytest.mark.parametrize("field", [K.QUANTITY, K.U, K.V])
+def test_sampling_reproduces_linear_fields(dim, order, field):
+    n = 16
+    o = Oracle(make_cfg(dim, n))
+    v = o.view(field)
+    ez, ey, ex = v.shape
+    coef = (0.7, -1.3, 0.4)[:dim]
+    lin = np.zeros(v.shape)
+    for k in range(ez):
+        for j in range(ey):
+            for i in range(ex):
+                x = o.coordinates(field, (i, j, k)[:dim])
+                lin[k, j, i] = 2.0 + sum(c * xx for c, xx in zip(coef, x))
+    v[...] = lin
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        loc = rng.uniform(0.15, 0.85, size=dim)
+        exact = 2.0 + sum(c * xx for c, xx in zip(coef, loc))
+        assert abs(o.interpolate(field, order, loc) - exact) < 1e-13
+
+
+# (6) integer-shift advection -------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_uniform_velocity_one_cell_shift(dim):
+    n = 16
+    cfg = make_cfg(dim, n, interp_order=1, dt=1.0 / n)
+    for d in range(3):
+        cfg.inflow_velocity[d] = 0.0  # no dt clamp, no inflow
+    cfg.inflow_quantity = 0.0
+    o = Oracle(cfg)
+    h, dt, _ = o.scalars()
+    assert dt == h
+    # u == 1 everywhere (also in the ghosts, so the wall layers see the same velocity)
+    o.view(K.U)[...] = 1.0
+    rng = np.random.default_rng(2)
+    q = rng.uniform(0, 1, size=o.shape(K.QUANTITY, K.GHOSTED))
+    o.view(K.QUANTITY)[...] = q
+    x0 = o.coordinates(K.QUANTITY, (8, 8, 8)[:dim])
+    tr = o.rk3(x0)
+    assert abs(tr[0] - (x0[0] - h)) < 1e-15 and all(abs(a - b) < 1e-15 for a, b in zip(tr[1:], x0[1:]))
+    o.time_integrator_step()
+    qn = o.get(K.QUANTITY)
+    sl = (slice(H, H + n),) * 2 if dim == 3 else (slice(0, 1), slice(H, H + n))
+    expect = q[sl[0], sl[1], H - 1:H + n - 1]
+    assert np.allclose(qn, expect, atol=1e-13)
+
+
+# (7) inflow sets -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,faces_i,rows_j", [(128, [26, 27, 28], (58, 69)), (64, [13, 14], (29, 34))])
+def test_inflow_exact_sets_2d(n, faces_i, rows_j):
+    o = Oracle(make_cfg(2, n))
+    o.add_inputs()
+    u = o.get(K.U)[0]
+    jj, ii = np.nonzero(u)
+    assert sorted(set(ii)) == faces_i
+    assert (jj.min(), jj.max()) == rows_j
+    assert (u[jj, ii] == 1.0).all()
+    q = o.get(K.QUANTITY)[0]
+    assert set(np.unique(q)) == {0.0, 3.0}
+    qj, qi = np.nonzero(q)
+    assert (qj.min(), qj.max()) == rows_j
+
+
+# (8) dt clamp -------------------------------------------------------------------------------------------------
+def test_dt_clamp():
+    # src/Solver.hpp:96-106: n = 256, dt = .005, |V| = 1  ->  dt = h = 1/256
+    assert Oracle(make_cfg(2, 256)).dt == 1.0 / 256
+    assert Oracle(make_cfg(2, 128)).dt == 0.005
+    # with gravity the bound includes sqrt(|f| h)
+    o = Oracle(make_cfg(2, 256, gravity=9.8))
+    h = 1.0 / 256
+    assert o.dt == h / (1.0 + np.sqrt(9.8 * h))
+
+
+# (11) quirk regression ---------------------------------------------------------------------------------------
+def test_quirk_q1_applypressure_bc_on_u():
+    """src/VelocityCorrector.hpp:260: with Q1 on, u(., j=0) is zeroed and v on the y walls keeps
+    -+ dt/(rho h) p ; with Q1 off v is zero on the walls."""
+    res = {}
+    for q1 in (1, 0):
+        o = Oracle(make_cfg(2, 32, quirks=(q1, 1)))
+        o.setup()
+        res[q1] = (o.get(K.U)[0], o.get(K.V)[0], o.get(K.PRESSURE)[0], o.scalars())
+    u, v, p, (h, dt, _) = res[1]
+    s = dt / (0.1 * h)
+    assert not u[0, :].any()
+    assert np.allclose(v[0, :], -s * p[0, :], rtol=1e-12) and v[0, :].any()
+    assert np.allclose(v[-1, :], s * p[-1, :], rtol=1e-12)
+    u0, v0, _, _ = res[0]
+    assert u0[0, :].any()
+    assert not v0[0, :].any() and not v0[-1, :].any()
+
+
+def test_quirk_q2_rk3_third_stage():
+    """src/TimeIntegrator.hpp:57-58: x2 = x0 - 3/4 dt v0 (not v1)."""
+    out = {}
+    for q2 in (1, 0):
+        o = Oracle(make_cfg(2, 32, quirks=(0, q2)))
+        v = o.view(K.U)
+        ez, ey, ex = v.shape
+        # u varies with x only: u = 1 + 4x  (so v1 != v0)
+        for i in range(ex):
+            v[:, :, i] = 1.0 + 4.0 * o.coordinates(K.U, (i, 5))[0]
+        out[q2] = o.rk3((0.5, 0.5))[0]
+    x0, dt = 0.5, 0.005
+    u = lambda x: 1.0 + 4.0 * x
+    v0 = u(x0)
+    v1 = u(x0 - 0.5 * dt * v0)
+    for q2, vs in ((1, v0), (0, v1)):
+        v2 = u(x0 - 0.75 * dt * vs)
+        assert abs(out[q2] - (x0 - dt * (2 / 9 * v0 + 3 / 9 * v1 + 4 / 9 * v2))) < 1e-14
+    assert out[0] != out[1]

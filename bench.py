@@ -131,6 +131,7 @@ def cpu_baseline(args, iters_sample, gcells_1gpu):
     cfg = default_config(3, n, box=n / 512.0)
     cfg.cg_fixed_iters = iters_sample
     o = Oracle(cfg)
+    o.set_accumulation(False)  # plain double sums: the reference's arithmetic and cost
     # same synthetic MAC velocity family as the GPU arm (sin/cos product)
     h = o.cell_size
     ax = [np.arange(n + 1) * h, (np.arange(n) + 0.5) * h]

@@ -155,7 +155,7 @@ int enqueue_iteration( cfb_ctx* c )
         halo_exchange_cells( c, c->cg_p, 1 );
     n += launch_stencil_dot( c );
     if ( c->cfg.use_nccl )
-        halo_allreduce( c, &c->d_state->pAp, 1 );
+        cg_global_sum( c, 0 );
     if ( e )
         cudaEventRecord( e[3], c->stream );
     return n;
@@ -190,7 +190,7 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
         halo_exchange_cells( c, c->cg_p, 1 );
     launches += launch_stencil_dot( c );
     if ( c->cfg.use_nccl )
-        halo_allreduce( c, &c->d_state->pAp, 1 );
+        cg_global_sum( c, 0 );
 
     const int batch = poll_batch( c );
     int enq = 0;
@@ -468,9 +468,13 @@ int cfb_create( const cfb_config* cfg, cfb_ctx** out )
     CFB_CUDA( c, alloc0( &c->cg_q ) );
     CFB_CUDA( c, cudaMalloc( &c->d_state, sizeof( CgState ) ) );
     CFB_CUDA( c, cudaMemsetAsync( c->d_state, 0, sizeof( CgState ), c->stream ) );
+    {
+        const int one = 1;
+        CFB_CUDA( c, cudaMemcpyAsync( &c->d_state->world, &one, sizeof( int ), cudaMemcpyHostToDevice, c->stream ) );
+    }
     CFB_CUDA( c, cudaMallocHost( &c->h_state, sizeof( CgState ) ) );
     std::memset( c->h_state, 0, sizeof( CgState ) );
-    CFB_CUDA( c, cudaMalloc( &c->d_partials, 2 * CFB_MAX_PARTIALS * sizeof( double ) ) );
+    CFB_CUDA( c, cudaMalloc( &c->d_partials, 2 * 2 * CFB_MAX_PARTIALS * sizeof( double ) ) );
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
 
     // ProblemManager::initialize with the constant MeshInitFunc (examples/advection.cpp:382-435)
@@ -730,6 +734,8 @@ int cfb_stencil_dot( cfb_ctx* c, int reps, double* dot, double* ms_per_launch )
     for ( int i = 0; i < reps; ++i )
         c->stats.kernel_launches += launch_stencil_dot( c );
     CFB_CUDA( c, cudaEventRecord( c->ev[EV_BENCH1], c->stream ) );
+    if ( c->cfg.use_nccl )
+        cg_global_sum( c, 0 );
     CFB_CUDA( c, cudaMemcpyAsync( c->h_state, c->d_state, STATE_HEAD, cudaMemcpyDeviceToHost, c->stream ) );
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
     int rc = check_async( c, "stencil_dot" );
@@ -799,6 +805,16 @@ int cfb_residual_history( const cfb_ctx* c, double* hist, int n, int* count )
     }
     if ( count )
         *count = total;
+    return CFB_OK;
+}
+
+int cfb_set_cg_params( cfb_ctx* c, double tolerance, int max_iter, int print_level )
+{
+    if ( tolerance < 0 || max_iter < 0 )
+        return cfb_fail( c, CFB_ERR_INVALID, "negative tolerance / max_iter" );
+    c->cfg.cg_tolerance = tolerance;
+    c->cfg.cg_max_iter = max_iter;
+    c->cfg.cg_print_level = print_level;
     return CFB_OK;
 }
 

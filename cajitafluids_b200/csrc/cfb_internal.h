@@ -56,6 +56,10 @@ struct CgState
     // global values (after the allreduce when multi-GPU); (rz_new, rr) are adjacent on purpose:
     // they travel in one 2-element allreduce, pAp in a 1-element one.
     double rz_old, pAp, rz_new, rr;
+    double loc[6];                  // multi-GPU: local double-double sums  pAp | rz_new | rr
+    double gath[64 * 4];            // multi-GPU: all-gathered local sums (<= 64 ranks)
+    int world;                      // number of ranks
+    int pad0;
     double bnorm;                   // sqrt(rr) of r0
     double thresh;                  // absolute threshold in use
     int iter;                       // completed iterations (kernel-1 executions)
@@ -92,7 +96,7 @@ struct cfb_ctx
 
     CgState* d_state = nullptr;
     CgState* h_state = nullptr; // pinned mirror (first bytes only are copied)
-    double* d_partials = nullptr; // [2][CFB_MAX_PARTIALS] scratch for block partial sums
+    double* d_partials = nullptr; // [2 values][CFB_MAX_PARTIALS][hi,lo] scratch for block partial sums
 
     // stencil TMA descriptor + tiling
     CUtensorMap tmap_p{};
@@ -179,3 +183,6 @@ void halo_destroy( cfb_ctx* c );
 int halo_exchange_cells( cfb_ctx* c, double* field, int width ); // face-neighbour exchange of a cell array
 int halo_exchange_fields( cfb_ctx* c, int version );             // width-h exchange of q,u,v,w
 int halo_allreduce( cfb_ctx* c, double* dev_vals, int n );
+int halo_allgather( cfb_ctx* c, const double* dev_send, double* dev_recv, int n_per_rank );
+// kernels_cg.cu: all-gather + exact combine of the local CG sums (which = 0: pAp, 1: rz_new and rr)
+int cg_global_sum( cfb_ctx* c, int which );

@@ -1,56 +1,99 @@
-// device_reduce.cuh — deterministic block reduction + "last block finalises" grid reduction.
+// device_reduce.cuh — order-independent (to the last bit) grid reductions.
 //
-// Every block reduces its threads' values in a fixed tree (warp shuffles, then one warp over the
-// per-warp sums), writes one partial per value, and takes a ticket.  The block that draws the
-// last ticket re-reads all partials in index order and reduces them with the same fixed tree, so
-// for a given launch configuration the result is bit-reproducible run to run (no floating-point
-// atomics anywhere).
+// The CG scalars (r.r, z.r, p.Ap) steer the whole solve; a 1-ulp difference in one of them is
+// amplified by ~1e4-1e5 over a few hundred iterations.  The reference leaves their summation order
+// to Kokkos::parallel_reduce.  Here every thread accumulates the (double-rounded) products in
+// double-double (TwoSum error-free transformation, ~2^-104 relative error), warps/blocks/grid
+// combine double-doubles, and only the final value is rounded to double.  The result is the
+// correctly rounded exact sum of the products — independent of thread count, tile shape, launch
+// configuration or block decomposition — so the CPU checker (which does the same) and any
+// multi-GPU split produce bit-identical alpha/beta.  Cost: 7 FP64 adds per term, invisible in
+// HBM-bound kernels.  No floating-point atomics anywhere.
 #pragma once
 #include <cuda_runtime.h>
 
-__device__ __forceinline__ double warp_sum( double v )
+struct dd_t
+{
+    double hi, lo;
+};
+
+// a += x   (x a plain double)
+__device__ __forceinline__ void dd_acc( dd_t& a, double x )
+{
+    const double s = a.hi + x;
+    const double bb = s - a.hi;
+    const double e = ( a.hi - ( s - bb ) ) + ( x - bb );
+    a.hi = s;
+    a.lo += e;
+}
+
+// a + b, renormalised
+__device__ __forceinline__ dd_t dd_add( dd_t a, dd_t b )
+{
+    const double s = a.hi + b.hi;
+    const double bb = s - a.hi;
+    double e = ( a.hi - ( s - bb ) ) + ( b.hi - bb );
+    e += a.lo + b.lo;
+    dd_t r;
+    r.hi = s + e;
+    r.lo = e - ( r.hi - s );
+    return r;
+}
+
+__device__ __forceinline__ dd_t dd_warp_sum( dd_t v )
 {
 #pragma unroll
     for ( int o = 16; o > 0; o >>= 1 )
-        v += __shfl_down_sync( 0xffffffffu, v, o );
+    {
+        dd_t w;
+        w.hi = __shfl_down_sync( 0xffffffffu, v.hi, o );
+        w.lo = __shfl_down_sync( 0xffffffffu, v.lo, o );
+        v = dd_add( v, w );
+    }
     return v;
 }
 
 // Sum over the block; result valid in thread 0.  NT = blockDim.x (multiple of 32, <= 1024).
 template <int NT>
-__device__ __forceinline__ double block_sum( double v, double* smem /* >= NT/32 doubles */ )
+__device__ __forceinline__ dd_t dd_block_sum( dd_t v, dd_t* smem /* >= NT/32 entries */ )
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    v = warp_sum( v );
+    v = dd_warp_sum( v );
     __syncthreads(); // smem may still be in use by a previous call
     if ( lane == 0 )
         smem[wid] = v;
     __syncthreads();
     if ( wid == 0 )
     {
-        v = lane < NT / 32 ? smem[lane] : 0.0;
-        v = warp_sum( v );
+        if ( lane < NT / 32 )
+            v = smem[lane];
+        else
+            v.hi = v.lo = 0.0;
+        v = dd_warp_sum( v );
     }
     return v;
 }
 
-// Block partials -> global partial arrays (value n at partials[n * stride + block]) -> the last
-// block sums them.  Returns true in every thread of the last block; vals[] then holds the grid
-// totals in thread 0.  The ticket is reset for the next launch.
+// Block partials -> global (value n of block b at partials[(n * stride + b) * 2 + {0,1}]) -> the
+// block that draws the last ticket sums them.  Returns true in every thread of that block; vals[]
+// then holds the grid totals (double-double) in thread 0.  The ticket is reset for the next launch.
 template <int NT, int NV>
-__device__ __forceinline__ bool block_reduce_finalize( double vals[NV], double* partials, int stride,
+__device__ __forceinline__ bool block_reduce_finalize( dd_t vals[NV], double* partials, int stride,
                                                        unsigned int* ticket )
 {
-    __shared__ double s_red[NT / 32];
+    __shared__ dd_t s_red[NT / 32];
     __shared__ bool s_last;
     const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
     const unsigned bid = ( blockIdx.z * gridDim.y + blockIdx.y ) * gridDim.x + blockIdx.x;
 #pragma unroll
     for ( int n = 0; n < NV; ++n )
     {
-        double s = block_sum<NT>( vals[n], s_red );
+        dd_t s = dd_block_sum<NT>( vals[n], s_red );
         if ( threadIdx.x == 0 )
-            partials[n * stride + bid] = s;
+        {
+            partials[( (size_t)n * stride + bid ) * 2 + 0] = s.hi;
+            partials[( (size_t)n * stride + bid ) * 2 + 1] = s.lo;
+        }
     }
     if ( threadIdx.x == 0 )
     {
@@ -65,10 +108,16 @@ __device__ __forceinline__ bool block_reduce_finalize( double vals[NV], double* 
 #pragma unroll
     for ( int n = 0; n < NV; ++n )
     {
-        double s = 0.0;
+        dd_t s;
+        s.hi = s.lo = 0.0;
         for ( unsigned b = threadIdx.x; b < nblocks; b += NT )
-            s += __ldcg( partials + n * stride + b );
-        vals[n] = block_sum<NT>( s, s_red );
+        {
+            dd_t w;
+            w.hi = __ldcg( partials + ( (size_t)n * stride + b ) * 2 + 0 );
+            w.lo = __ldcg( partials + ( (size_t)n * stride + b ) * 2 + 1 );
+            s = dd_add( s, w );
+        }
+        vals[n] = dd_block_sum<NT>( s, s_red );
     }
     if ( threadIdx.x == 0 )
         *ticket = 0u;

@@ -36,6 +36,7 @@ struct NcclApi
     ncclResult_t ( *Recv )( void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t ) = nullptr;
     ncclResult_t ( *AllReduce )( const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                                  cudaStream_t ) = nullptr;
+    ncclResult_t ( *AllGather )( const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t ) = nullptr;
     ncclResult_t ( *GroupStart )() = nullptr;
     ncclResult_t ( *GroupEnd )() = nullptr;
     const char* ( *GetErrorString )( ncclResult_t ) = nullptr;
@@ -73,6 +74,7 @@ bool nccl_load( std::string& err )
     BIND( Send, "ncclSend" )
     BIND( Recv, "ncclRecv" )
     BIND( AllReduce, "ncclAllReduce" )
+    BIND( AllGather, "ncclAllGather" )
     BIND( GroupStart, "ncclGroupStart" )
     BIND( GroupEnd, "ncclGroupEnd" )
     BIND( GetErrorString, "ncclGetErrorString" )
@@ -283,6 +285,9 @@ int halo_init( cfb_ctx* c )
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
     CFB_CUDA( c, cudaStreamSynchronize( c->comm_stream ) );
     CFB_CUDA( c, cudaMemsetAsync( c->d_state, 0, sizeof( CgState ), c->stream ) );
+    if ( cfg.world_size > 64 )
+        return cfb_fail( c, CFB_ERR_INVALID, "at most 64 ranks" );
+    CFB_CUDA( c, cudaMemcpyAsync( &c->d_state->world, &cfg.world_size, sizeof( int ), cudaMemcpyHostToDevice, c->stream ) );
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
     return CFB_OK;
 }
@@ -418,5 +423,12 @@ int halo_allreduce( cfb_ctx* c, double* dev_vals, int n )
 {
     Comm* cm = static_cast<Comm*>( c->nccl );
     CFB_NCCL( c, g_nccl.AllReduce( dev_vals, dev_vals, (size_t)n, ncclDouble, ncclSum, cm->red, c->stream ) );
+    return CFB_OK;
+}
+
+int halo_allgather( cfb_ctx* c, const double* dev_send, double* dev_recv, int n_per_rank )
+{
+    Comm* cm = static_cast<Comm*>( c->nccl );
+    CFB_NCCL( c, g_nccl.AllGather( dev_send, dev_recv, (size_t)n_per_rank, ncclDouble, cm->red, c->stream ) );
     return CFB_OK;
 }

@@ -39,6 +39,45 @@ __device__ __forceinline__ void pair_walls( const Geo& g, int i, int j, int k, i
     c1 = cyz + wall_count( g, 0, i + 1 + g.off[0] );
 }
 
+// Single block: the rounded sums are final.  Multi-GPU: keep the local double-doubles; they are
+// all-gathered and combined exactly (in rank order) by cg_combine_kernel, so the global value is
+// again the correctly rounded exact sum, whatever the decomposition.
+__device__ __forceinline__ void publish_rr_rz( CgState* S, dd_t rr, dd_t rz )
+{
+    if ( S->world > 1 )
+    {
+        S->loc[2] = rz.hi;
+        S->loc[3] = rz.lo;
+        S->loc[4] = rr.hi;
+        S->loc[5] = rr.lo;
+    }
+    else
+    {
+        S->rr = rr.hi + rr.lo;
+        S->rz_new = rz.hi + rz.lo;
+    }
+}
+
+// which == 0: pAp from gath[rank][0..1] ; which == 1: (rz_new, rr) from gath[rank][0..3]
+__global__ void cg_combine_kernel( CgState* S, int which )
+{
+    const int nv = which == 0 ? 1 : 2;
+    dd_t acc[2] = { { 0.0, 0.0 }, { 0.0, 0.0 } };
+    for ( int r = 0; r < S->world; ++r )
+        for ( int v = 0; v < nv; ++v )
+        {
+            dd_t w = { S->gath[( r * nv + v ) * 2], S->gath[( r * nv + v ) * 2 + 1] };
+            acc[v] = dd_add( acc[v], w );
+        }
+    if ( which == 0 )
+        S->pAp = acc[0].hi + acc[0].lo;
+    else
+    {
+        S->rz_new = acc[0].hi + acc[0].lo;
+        S->rr = acc[1].hi + acc[1].lo;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // VelocityCorrector::_buildRHS (src/VelocityCorrector.hpp:204-210) + lhs = 0 (:272)
 template <int D>
@@ -72,7 +111,7 @@ __global__ void __launch_bounds__( NT )
 {
     const unsigned npx = (unsigned)( ( g.n[0] + 1 ) >> 1 );
     const unsigned total = npx * (unsigned)g.n[1] * (unsigned)g.n[2];
-    double rr = 0.0, rz = 0.0;
+    dd_t rr = { 0.0, 0.0 }, rz = { 0.0, 0.0 };
     for ( unsigned t = blockIdx.x * NT + threadIdx.x; t < total; t += gridDim.x * NT )
     {
         int i, j, k, c0, c1;
@@ -87,10 +126,10 @@ __global__ void __launch_bounds__( NT )
             *reinterpret_cast<double2*>( x + o ) = make_double2( 0.0, 0.0 );
             *reinterpret_cast<double2*>( r + o ) = bv;
             *reinterpret_cast<double2*>( p + o ) = make_double2( z0, z1 );
-            rr += bv.x * bv.x;
-            rr += bv.y * bv.y;
-            rz += z0 * bv.x;
-            rz += z1 * bv.y;
+            dd_acc( rr, bv.x * bv.x );
+            dd_acc( rr, bv.y * bv.y );
+            dd_acc( rz, z0 * bv.x );
+            dd_acc( rz, z1 * bv.y );
         }
         else
         {
@@ -99,17 +138,16 @@ __global__ void __launch_bounds__( NT )
             x[o] = 0.0;
             r[o] = bv;
             p[o] = z0;
-            rr += bv * bv;
-            rz += z0 * bv;
+            dd_acc( rr, bv * bv );
+            dd_acc( rz, z0 * bv );
         }
     }
-    double vals[2] = { rr, rz };
+    dd_t vals[2] = { rr, rz };
     if ( block_reduce_finalize<NT, 2>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
     {
         if ( threadIdx.x == 0 )
         {
-            S->rr = vals[0];
-            S->rz_new = vals[1];
+            publish_rr_rz( S, vals[0], vals[1] );
             S->iter = 0;
             S->done = 0;
             S->fixed = fixed;
@@ -140,7 +178,7 @@ __global__ void __launch_bounds__( NT )
     const double nalpha = -alpha;
     const unsigned npx = (unsigned)( ( g.n[0] + 1 ) >> 1 );
     const unsigned total = npx * (unsigned)g.n[1] * (unsigned)g.n[2];
-    double rr = 0.0, rz = 0.0;
+    dd_t rr = { 0.0, 0.0 }, rz = { 0.0, 0.0 };
     for ( unsigned t = blockIdx.x * NT + threadIdx.x; t < total; t += gridDim.x * NT )
     {
         int i, j, k, c0, c1;
@@ -159,10 +197,10 @@ __global__ void __launch_bounds__( NT )
             rv.y = fma( nalpha, qv.y, rv.y );
             *reinterpret_cast<double2*>( x + o ) = xv;
             *reinterpret_cast<double2*>( r + o ) = rv;
-            rr += rv.x * rv.x;
-            rr += rv.y * rv.y;
-            rz += ( op.minv[c0] * rv.x ) * rv.x;
-            rz += ( op.minv[c1] * rv.y ) * rv.y;
+            dd_acc( rr, rv.x * rv.x );
+            dd_acc( rr, rv.y * rv.y );
+            dd_acc( rz, ( op.minv[c0] * rv.x ) * rv.x );
+            dd_acc( rz, ( op.minv[c1] * rv.y ) * rv.y );
         }
         else
         {
@@ -170,18 +208,15 @@ __global__ void __launch_bounds__( NT )
             const double rv = fma( nalpha, q[o], r[o] );
             x[o] = xv;
             r[o] = rv;
-            rr += rv * rv;
-            rz += ( op.minv[c0] * rv ) * rv;
+            dd_acc( rr, rv * rv );
+            dd_acc( rz, ( op.minv[c0] * rv ) * rv );
         }
     }
-    double vals[2] = { rr, rz };
+    dd_t vals[2] = { rr, rz };
     if ( block_reduce_finalize<NT, 2>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
     {
         if ( threadIdx.x == 0 )
-        {
-            S->rr = vals[0];
-            S->rz_new = vals[1];
-        }
+            publish_rr_rz( S, vals[0], vals[1] );
     }
 }
 
@@ -240,6 +275,18 @@ inline int stream_grid( const cfb_ctx* c, long long pairs )
 
 } // namespace
 
+// Multi-GPU: all-gather the local double-double sums and combine them exactly.
+int cg_global_sum( cfb_ctx* c, int which )
+{
+    const int nd = which == 0 ? 2 : 4; // doubles per rank
+    int rc = halo_allgather( c, &c->d_state->loc[which == 0 ? 0 : 2], c->d_state->gath, nd );
+    if ( rc )
+        return rc;
+    cg_combine_kernel<<<1, 1, 0, c->stream>>>( c->d_state, which );
+    c->stats.kernel_launches += 1;
+    return CFB_OK;
+}
+
 int launch_divergence( cfb_ctx* c )
 {
     const Geo& g = c->g;
@@ -266,7 +313,7 @@ int launch_cg_init( cfb_ctx* c, int fixed )
                                                 c->d_partials, fixed );
     int launches = 1;
     if ( c->cfg.use_nccl )
-        halo_allreduce( c, &c->d_state->rz_new, 2 );
+        cg_global_sum( c, 1 );
     cg_check0_kernel<<<1, 1, 0, c->stream>>>( c->d_state, c->cfg.cg_tolerance,
                                               c->cfg.cg_stop_rule == CFB_STOP_REL );
     return launches + 1;
@@ -280,7 +327,7 @@ int launch_cg_axpy( cfb_ctx* c )
     cg_axpy_kernel<<<grid, NT, 0, c->stream>>>( g, c->op, c->cg_p, c->cg_q, c->lhs, c->cg_r, c->d_state,
                                                 c->d_partials );
     if ( c->cfg.use_nccl )
-        halo_allreduce( c, &c->d_state->rz_new, 2 );
+        cg_global_sum( c, 1 );
     return 1;
 }
 

@@ -81,6 +81,20 @@ __device__ __forceinline__ void prefetch_tmap( const CUtensorMap* map )
     asm volatile( "prefetch.tensormap [%0];" ::"l"( map ) : "memory" );
 }
 
+// End of kernel 4: publish p.Ap (see publish_rr_rz in kernels_cg.cu for the multi-GPU path) and
+// perform the CG loop's "zTr_old = zTr_new".
+__device__ __forceinline__ void publish_pAp( CgState* S, dd_t v )
+{
+    if ( S->world > 1 )
+    {
+        S->loc[0] = v.hi;
+        S->loc[1] = v.lo;
+    }
+    else
+        S->pAp = v.hi + v.lo;
+    S->rz_old = S->rz_new;
+}
+
 // ---- the 7-point row of A, in the reference's stencil order ---------------------------------
 // {0}, {-x}, {+x}, {-y}, {+y}, {-z}, {+z}; one fused multiply-add per term (bit-identical to the
 // checker's apply_A).
@@ -214,7 +228,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         tma_load_3d( smem_base, &tmap, bar, cx, cy, cz + NS );
     }
 
-    double acc = 0.0;
+    dd_t acc = { 0.0, 0.0 };
     double* qrow = a.q + geo_off( g, i0, y0 + wy, kbeg );
     for ( int it = 0; it < nplanes; ++it )
     {
@@ -245,13 +259,13 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
                 if ( vx1 )
                 {
                     *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
-                    acc += c.x * a0;
-                    acc += c.y * a1;
+                    dd_acc( acc, c.x * a0 );
+                    dd_acc( acc, c.y * a1 );
                 }
                 else if ( vx0 )
                 {
                     *qp = a0;
-                    acc += c.x * a0;
+                    dd_acc( acc, c.x * a0 );
                 }
             }
             zm[r] = c;
@@ -267,14 +281,11 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         }
     }
 
-    double vals[1] = { acc };
+    dd_t vals[1] = { acc };
     if ( block_reduce_finalize<C::NT, 1>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
     {
         if ( tid == 0 )
-        {
-            a.S->pAp = vals[0];
-            a.S->rz_old = a.S->rz_new; // kernel "zTr_old = zTr_new" of the CG loop
-        }
+            publish_pAp( a.S, vals[0] );
     }
 }
 
@@ -297,7 +308,7 @@ __global__ void __launch_bounds__( 256, 4 )
     const int wxy0 = wall_count( g, 0, i0 + g.off[0] ) + wall_count( g, 1, j + g.off[1] );
     const int wxy1 = wall_count( g, 0, i0 + 1 + g.off[0] ) + wall_count( g, 1, j + g.off[1] );
     const double ns = op.neg_scale;
-    double acc = 0.0;
+    dd_t acc = { 0.0, 0.0 };
     if ( vy && vx0 )
     {
         const double* pp = p + geo_off( g, i0, j, kbeg );
@@ -317,13 +328,13 @@ __global__ void __launch_bounds__( 256, 4 )
             if ( vx1 )
             {
                 *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
-                acc += c.x * a0;
-                acc += c.y * a1;
+                dd_acc( acc, c.x * a0 );
+                dd_acc( acc, c.y * a1 );
             }
             else
             {
                 *qp = a0;
-                acc += c.x * a0;
+                dd_acc( acc, c.x * a0 );
             }
             zm = c;
             c = zp;
@@ -331,14 +342,11 @@ __global__ void __launch_bounds__( 256, 4 )
             qp += g.sz;
         }
     }
-    double vals[1] = { acc };
+    dd_t vals[1] = { acc };
     if ( block_reduce_finalize<256, 1>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
     {
         if ( threadIdx.x == 0 )
-        {
-            a.S->pAp = vals[0];
-            a.S->rz_old = a.S->rz_new;
-        }
+            publish_pAp( a.S, vals[0] );
     }
 }
 

@@ -379,10 +379,22 @@ class B200ConjugateGradient
         if ( s.size() != 1 )
             throw std::runtime_error( "B200ConjugateGradient: only the diagonal (Jacobi) preconditioner is supported" );
     }
-    void setTolerance( double tol ) { _tol = tol; }
-    void setMaxIter( int n ) { _max_iter = n; }
-    void setPrintLevel( int l ) { _print = l; }
-    void setup() {}
+    void setTolerance( double tol )
+    {
+        _tol = tol;
+        push();
+    }
+    void setMaxIter( int n )
+    {
+        _max_iter = n;
+        push();
+    }
+    void setPrintLevel( int l )
+    {
+        _print = l;
+        push();
+    }
+    void setup() { push(); }
     // solve( b, x ) with both vectors resident on the device as the ctx's RHS / PRESSURE fields
     void solve()
     {
@@ -401,6 +413,7 @@ class B200ConjugateGradient
     int printLevel() const { return _print; }
 
   private:
+    void push() { detail::check( cfb_set_cg_params( _h->ctx, _tol, _max_iter, _print ), _h->ctx ); }
     std::shared_ptr<detail::CtxHolder> _h;
     double _tol = 1.0e-6, _resid = 0.0;
     int _max_iter = 2000, _print = 1, _num_iter = 0;
@@ -422,6 +435,24 @@ class VelocityCorrector : public VelocityCorrectorBase
         : _h( std::move( h ) )
         , _pressure_solver( std::move( solver ) )
     {
+        // src/VelocityCorrector.hpp:96-106: stencil, Jacobi preconditioner, tol / max_iter / print
+        const std::size_t D = NumSpaceDim;
+        std::vector<std::array<int, NumSpaceDim>> stencil( 2 * D + 1 );
+        for ( auto& s : stencil )
+            s.fill( 0 );
+        for ( std::size_t d = 0; d < D; ++d )
+        {
+            stencil[1 + 2 * d][d] = -1;
+            stencil[2 + 2 * d][d] = 1;
+        }
+        _pressure_solver->setMatrixStencil( stencil, false );
+        std::vector<std::array<int, NumSpaceDim>> diag_stencil( 1 );
+        diag_stencil[0].fill( 0 );
+        _pressure_solver->setPreconditionerStencil( diag_stencil, false );
+        _pressure_solver->setTolerance( 1.0e-6 );
+        _pressure_solver->setMaxIter( 2000 );
+        _pressure_solver->setPrintLevel( 1 );
+        _pressure_solver->setup();
     }
     void _buildRHS() { detail::check( cfb_build_rhs( _h->ctx ), _h->ctx ); }
     void _applyPressure() { detail::check( cfb_apply_pressure( _h->ctx ), _h->ctx ); }

@@ -266,6 +266,9 @@ int cfb_reset_stats( cfb_ctx* ctx );
 int cfb_residual_history( const cfb_ctx* ctx, double* hist, int n, int* count );
 /* Choose the stencil kernel variant / tiling (tuning hook; 0 = default). */
 int cfb_set_tuning( cfb_ctx* ctx, const char* key, int value );
+/* ReferenceConjugateGradient::setTolerance / setMaxIter / setPrintLevel
+ * (src/VelocityCorrector.hpp:103-105) after construction. */
+int cfb_set_cg_params( cfb_ctx* ctx, double tolerance, int max_iter, int print_level );
 
 int cfb_abi_version( void );
 

@@ -45,6 +45,51 @@ namespace
 
 using clk = std::chrono::steady_clock;
 
+// Accumulator of the global sums (r.r, z.r, p.Ap).  The reference leaves the summation order to
+// Kokkos::parallel_reduce (it changes with backend and thread count, and with it the last bits of
+// alpha/beta, which CG then amplifies by ~1e4-1e5 over a few hundred iterations: measured 1e-11
+// relative in the pressure after 20 steps at 64^3 between 1 and 8 OpenMP threads).  In its default
+// mode the oracle therefore accumulates the (double-rounded) products in double-double (TwoSum),
+// i.e. it returns the correctly rounded EXACT sum, the centre of all admissible orders; the CUDA
+// path does the same, which makes whole runs bit-comparable.  Mode 0 (plain double, the reference's
+// arithmetic) is kept for the CPU-baseline timing.
+struct acc_t
+{
+    double hi = 0.0, lo = 0.0;
+    bool exact = true;
+    acc_t() {}
+    explicit acc_t( bool e ) : exact( e ) {}
+    inline void add( double x )
+    {
+        if ( exact )
+        {
+            const double s = hi + x;
+            const double bb = s - hi;
+            const double e = ( hi - ( s - bb ) ) + ( x - bb );
+            hi = s;
+            lo += e;
+        }
+        else
+            hi += x;
+    }
+    inline void merge( const acc_t& b )
+    {
+        if ( exact )
+        {
+            const double s = hi + b.hi;
+            const double bb = s - hi;
+            double e = ( hi - ( s - bb ) ) + ( b.hi - bb );
+            e += lo + b.lo;
+            hi = s + e;
+            lo = e - ( hi - s );
+        }
+        else
+            hi += b.hi;
+    }
+    inline double value() const { return hi + lo; }
+};
+#pragma omp declare reduction( accsum : acc_t : omp_out.merge( omp_in ) ) initializer( omp_priv = acc_t( omp_orig.exact ) )
+
 // ---------------------------------------------------------------------------------------
 // A ghosted array of one entity type (Cajita::Array with one dof), x fastest.
 // Entity: 0 = Cell, 1 = Face<I>, 2 = Face<J>, 3 = Face<K>.
@@ -114,6 +159,7 @@ struct cfo_ctx
     double t_phase[8] = { 0 };
     long long cg_total = 0;
     long long steps = 0;
+    bool accum_exact = true; // see acc_t
     std::string err;
 };
 
@@ -512,16 +558,17 @@ int cg_solve( cfo_ctx& c )
 
     // r0 = b - A x0 ; rr
     do_gather( c, 1 );
-    double rr = 0.0;
-#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : rr )
+    acc_t rr_acc( c.accum_exact );
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : rr_acc )
     for ( int k = s.lo[2]; k < s.hi[2]; ++k )
         for ( int j = s.lo[1]; j < s.hi[1]; ++j )
             for ( int i = s.lo[0]; i < s.hi[0]; ++i )
             {
                 double r_new = b( i, j, k ) - apply_A( c, x, i, j, k );
                 r( i, j, k ) = r_new;
-                rr += r_new * r_new;
+                rr_acc.add( r_new * r_new );
             }
+    double rr = rr_acc.value();
     do_allreduce( c, &rr, 1 );
     c.resid = std::sqrt( rr );
     if ( c.cfg.cg_stop_rule == CFB_STOP_REL )
@@ -534,8 +581,8 @@ int cg_solve( cfo_ctx& c )
 
     // z0 = M r0 ; p0 = z0 ; zTr
     do_gather( c, 2 );
-    double zTr_old = 0.0;
-#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : zTr_old )
+    acc_t zTr_acc( c.accum_exact );
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : zTr_acc )
     for ( int k = s.lo[2]; k < s.hi[2]; ++k )
         for ( int j = s.lo[1]; j < s.hi[1]; ++j )
             for ( int i = s.lo[0]; i < s.hi[0]; ++i )
@@ -543,22 +590,24 @@ int cg_solve( cfo_ctx& c )
                 double Mr = c.Mi[r.idx( i, j, k )] * r( i, j, k );
                 z( i, j, k ) = Mr;
                 p( i, j, k ) = Mr;
-                zTr_old += Mr * r( i, j, k );
+                zTr_acc.add( Mr * r( i, j, k ) );
             }
+    double zTr_old = zTr_acc.value();
     do_allreduce( c, &zTr_old, 1 );
 
     // q0 = A p0 ; pTAp
     do_gather( c, 3 );
-    double pTAp = 0.0;
-#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : pTAp )
+    acc_t pTAp_acc( c.accum_exact );
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : pTAp_acc )
     for ( int k = s.lo[2]; k < s.hi[2]; ++k )
         for ( int j = s.lo[1]; j < s.hi[1]; ++j )
             for ( int i = s.lo[0]; i < s.hi[0]; ++i )
             {
                 double Ap = apply_A( c, p, i, j, k );
                 q( i, j, k ) = Ap;
-                pTAp += p( i, j, k ) * Ap;
+                pTAp_acc.add( p( i, j, k ) * Ap );
             }
+    double pTAp = pTAp_acc.value();
     do_allreduce( c, &pTAp, 1 );
 
     bool converged = false;
@@ -566,8 +615,8 @@ int cg_solve( cfo_ctx& c )
     {
         // kernel 1: x += alpha p ; r -= alpha q ; rr
         const double alpha = zTr_old / pTAp;
-        rr = 0.0;
-#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : rr )
+        rr_acc = acc_t( c.accum_exact );
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : rr_acc )
         for ( int k = s.lo[2]; k < s.hi[2]; ++k )
             for ( int j = s.lo[1]; j < s.hi[1]; ++j )
                 for ( int i = s.lo[0]; i < s.hi[0]; ++i )
@@ -575,8 +624,9 @@ int cg_solve( cfo_ctx& c )
                     x( i, j, k ) = std::fma( alpha, p( i, j, k ), x( i, j, k ) );
                     double r_new = std::fma( -alpha, q( i, j, k ), r( i, j, k ) );
                     r( i, j, k ) = r_new;
-                    rr += r_new * r_new;
+                    rr_acc.add( r_new * r_new );
                 }
+        rr = rr_acc.value();
         do_allreduce( c, &rr, 1 );
         c.resid = std::sqrt( rr );
         ++c.num_iter;
@@ -591,16 +641,17 @@ int cg_solve( cfo_ctx& c )
 
         // kernel 2: z = M r ; zTr
         do_gather( c, 2 );
-        double zTr_new = 0.0;
-#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : zTr_new )
+        zTr_acc = acc_t( c.accum_exact );
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : zTr_acc )
         for ( int k = s.lo[2]; k < s.hi[2]; ++k )
             for ( int j = s.lo[1]; j < s.hi[1]; ++j )
                 for ( int i = s.lo[0]; i < s.hi[0]; ++i )
                 {
                     double Mr = c.Mi[r.idx( i, j, k )] * r( i, j, k );
                     z( i, j, k ) = Mr;
-                    zTr_new += Mr * r( i, j, k );
+                    zTr_acc.add( Mr * r( i, j, k ) );
                 }
+        double zTr_new = zTr_acc.value();
         do_allreduce( c, &zTr_new, 1 );
 
         // kernel 3: p = z + beta p
@@ -613,16 +664,17 @@ int cg_solve( cfo_ctx& c )
 
         // kernel 4: q = A p ; pTAp
         do_gather( c, 3 );
-        pTAp = 0.0;
-#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : pTAp )
+        pTAp_acc = acc_t( c.accum_exact );
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : pTAp_acc )
         for ( int k = s.lo[2]; k < s.hi[2]; ++k )
             for ( int j = s.lo[1]; j < s.hi[1]; ++j )
                 for ( int i = s.lo[0]; i < s.hi[0]; ++i )
                 {
                     double Ap = apply_A( c, p, i, j, k );
                     q( i, j, k ) = Ap;
-                    pTAp += p( i, j, k ) * Ap;
+                    pTAp_acc.add( p( i, j, k ) * Ap );
                 }
+        pTAp = pTAp_acc.value();
         do_allreduce( c, &pTAp, 1 );
         zTr_old = zTr_new;
     }
@@ -1006,24 +1058,24 @@ int cfo_stencil_dot( cfo_ctx* c, int reps, double* dot, double* ms_per_launch )
     Space s = own_space( *c, 0 );
     const Arr& p = c->cg_p;
     Arr& q = c->cg_q;
-    double pTAp = 0;
+    acc_t pTAp( c->accum_exact );
     auto t0 = clk::now();
     for ( int it = 0; it < reps; ++it )
     {
-        pTAp = 0;
-#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( + : pTAp )
+        pTAp = acc_t( c->accum_exact );
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : pTAp )
         for ( int k = s.lo[2]; k < s.hi[2]; ++k )
             for ( int j = s.lo[1]; j < s.hi[1]; ++j )
                 for ( int i = s.lo[0]; i < s.hi[0]; ++i )
                 {
                     double Ap = apply_A( *c, p, i, j, k );
                     q( i, j, k ) = Ap;
-                    pTAp += p( i, j, k ) * Ap;
+                    pTAp.add( p( i, j, k ) * Ap );
                 }
     }
     double sec = std::chrono::duration<double>( clk::now() - t0 ).count();
     if ( dot )
-        *dot = pTAp;
+        *dot = pTAp.value();
     if ( ms_per_launch )
         *ms_per_launch = 1e3 * sec / std::max( reps, 1 );
     return CFB_OK;
@@ -1057,6 +1109,13 @@ int cfo_reset_stats( cfo_ctx* c )
         t = 0;
     c->cg_total = 0;
     c->steps = 0;
+    return CFB_OK;
+}
+
+// 1 (default): exact double-double sums; 0: plain double sums like the reference (CPU baseline timing)
+int cfo_set_accumulation( cfo_ctx* c, int exact )
+{
+    c->accum_exact = exact != 0;
     return CFB_OK;
 }
 

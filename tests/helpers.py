@@ -76,3 +76,15 @@ def random_cells(ctx, rng, field=K.QUANTITY):
 def set_both(gpu, ora, field, arr, version=K.CURRENT, region=K.OWNED):
     gpu.set(field, arr, version, region)
     ora.set(field, arr, version, region)
+
+
+TOL_FIELD = 1e-10  # north_star bar: fields within 1e-10 relative L2 in FP64
+
+
+def assert_same(a, b, what=""):
+    """The stated bar (1e-10 relative L2) AND the stronger property this implementation has: both
+    sides compute every reduction as a correctly rounded exact sum and every element-wise update
+    with the same rounding sequence, so whole runs are bit-identical."""
+    e = rel_l2(a, b)
+    assert e < TOL_FIELD, f"{what}: rel l2 {e}"
+    assert np.array_equal(a, b), f"{what}: within tolerance (rel l2 {e}) but not bit-identical"

@@ -1,0 +1,146 @@
+"""Multi-GPU parity worker, launched by tests/test_multigpu.py (or by hand) under torchrun:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tests/mgpu_worker.py [--cells 48 40 36] [--steps 4]
+
+Every rank owns one block of the 3-D block decomposition on its own GPU (NCCL halo exchange and
+allreduce inside the C library) and checks its block against the SINGLE-BLOCK CPU oracle run on the
+same global problem: decomposition invariance + parity in one go.
+Exit code 0 on success on every rank.
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from cajitafluids_b200 import Solver, config as K
+from cajitafluids_b200.distributed import attach_nccl, block_grid, decompose
+from helpers import fields_of, make_cfg, rel_l2
+from oracle_api import Oracle
+
+
+def block_slices(gpu, field):
+    """numpy slices (z, y, x) of this rank's owned entities inside the global owned array."""
+    off = gpu.global_offset()
+    ext = gpu.owned_extent(field)
+    return tuple(slice(off[d], off[d] + ext[d]) for d in (2, 1, 0))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cells", type=int, nargs=3, default=[48, 40, 36])
+    ap.add_argument("--steps", type=int, default=4)
+    args = ap.parse_args()
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cells = tuple(args.cells)
+    blocks = block_grid(world)
+    box = tuple(c / cells[0] for c in cells)
+
+    def gcfg(**kw):
+        return make_cfg(3, cells, box=box, **kw)
+
+    def rank_cfg(**kw):
+        c = decompose(gcfg(**kw), rank, world, blocks)
+        c.device_id = local
+        return attach_nccl(c, dist)
+
+    failures = []
+
+    def check(name, ok, detail=""):
+        if not ok:
+            failures.append(f"rank {rank}: {name} {detail}")
+
+    # 1. stencil + dot on a random global p --------------------------------------------------------
+    ora = Oracle(gcfg())
+    gpu = Solver(rank_cfg())
+    rng = np.random.default_rng(77)
+    p = rng.uniform(-1, 1, size=ora.shape(K.CG_P))
+    ora.set(K.CG_P, p)
+    gpu.set(K.CG_P, p[block_slices(gpu, K.CG_P)])
+    dg, _ = gpu.stencil_dot(1)
+    do, _ = ora.stencil_dot(1)
+    qo = ora.get(K.CG_Q)[block_slices(gpu, K.CG_Q)]
+    qg = gpu.get(K.CG_Q)
+    check("stencil q bit-exact", np.array_equal(qg, qo), f"max diff {np.abs(qg - qo).max()}")
+    # each rank's pAp is its local sum until the allreduce; stencil_dot returns the allreduced value
+    check("stencil dot", abs(dg - do) <= 1e-12 * abs(do), f"{dg} vs {do}")
+
+    # 2. width-3 field gather incl. edges/corners -----------------------------------------------------
+    for f in fields_of(3):
+        a = rng.uniform(-1, 1, size=ora.shape(f))
+        ora.set(f, a)
+        gpu.set(f, a[block_slices(gpu, f)])
+    gpu.gather(K.CURRENT)
+    h = 3
+    off = gpu.global_offset()
+    for f in fields_of(3):
+        glob = ora.get(f, region=K.GHOSTED)  # global ghosted array, physical ghosts are zero
+        mine = gpu.get(f, region=K.GHOSTED)
+        ez, ey, ex = mine.shape
+        want = glob[off[2]:off[2] + ez, off[1]:off[1] + ey, off[0]:off[0] + ex]
+        check(f"gather field {f}", np.array_equal(mine, want), f"mismatches {(mine != want).sum()}")
+    gpu.close()
+    ora.close()
+
+    # 3. PCG on a synthetic divergence ------------------------------------------------------------------
+    ora = Oracle(gcfg())
+    gpu = Solver(rank_cfg())
+    for f in fields_of(3)[1:]:
+        a = rng.uniform(-1, 1, size=ora.shape(f))
+        ora.set(f, a)
+        gpu.set(f, a[block_slices(gpu, f)])
+    ora.add_inputs()
+    gpu.add_inputs()
+    ora.build_rhs()
+    gpu.build_rhs()
+    check("rhs bit-exact", np.array_equal(gpu.get(K.RHS), ora.get(K.RHS)[block_slices(gpu, K.RHS)]))
+    ig, rg = gpu.pcg_solve()
+    io, ro = ora.pcg_solve()
+    check("pcg iterations", abs(ig - io) <= 1, f"{ig} vs {io}")
+    if ig == io:
+        e = rel_l2(gpu.get(K.PRESSURE), ora.get(K.PRESSURE)[block_slices(gpu, K.PRESSURE)])
+        check("pcg pressure 1e-10", e < 1e-10, f"rel l2 {e}")
+    gpu.close()
+    ora.close()
+
+    # 4. whole timesteps of the default inflow problem -----------------------------------------------------
+    ora = Oracle(gcfg())
+    gpu = Solver(rank_cfg())
+    ora.setup()
+    gpu.setup()
+    for _ in range(args.steps):
+        ora.step()
+        gpu.step()
+    check("cg iteration total", abs(gpu.stats()["cg_iterations"] - ora.stats()["cg_iterations"]) <= args.steps + 1,
+          f"{gpu.stats()['cg_iterations']} vs {ora.stats()['cg_iterations']}")
+    for f in fields_of(3) + [K.PRESSURE]:
+        e = rel_l2(gpu.get(f), ora.get(f)[block_slices(gpu, f)])
+        # blocks far from the inflow may hold (near-)zero fields: compare against the global norm too
+        gl = np.linalg.norm(ora.get(f).ravel())
+        ea = np.linalg.norm((gpu.get(f) - ora.get(f)[block_slices(gpu, f)]).ravel()) / max(gl, 1e-300)
+        check(f"step field {f}", min(e, ea) < 1e-10, f"rel l2 {e} (vs global norm {ea})")
+    gpu.close()
+    ora.close()
+
+    flag = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(flag)
+    for msg in failures:
+        print("FAIL", msg, flush=True)
+    if rank == 0:
+        print(f"mgpu_worker world={world} blocks={blocks} cells={cells}: "
+              f"{'OK' if int(flag) == 0 else 'FAILED (%d)' % int(flag)}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag) else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,7 @@ def load():
                                     C.POINTER(C.c_int)]
         d.cfo_set_callbacks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         d.cfo_num_threads.restype = C.c_int
+        d.cfo_set_accumulation.argtypes = [C.c_void_p, C.c_int]
     return _lib
 
 
@@ -55,6 +56,10 @@ class Oracle(Context):
     def __init__(self, cfg):
         super().__init__(load(), cfg)
         self._cbs = None
+
+    def set_accumulation(self, exact):
+        """exact=True (default): double-double sums; False: plain double like the reference."""
+        self.lib.dll.cfo_set_accumulation(self.h, 1 if exact else 0)
 
     def num_threads(self):
         return self.lib.dll.cfo_num_threads()

@@ -28,7 +28,12 @@ sys.path.insert(0, ROOT)
 METRIC = "pcg_iterations_per_second"
 UNIT = "iterations/s"
 BYTES_STENCIL = 16  # read p, write q                       
-BYTES_ITER = 88     # stencil 16 + axpy/norms 48 + p-update 24
+# algorithmic bytes per owned cell of one CG iteration / of its dominant kernel, per CG form
+#   0: three kernels  axpy+norms 48 | p-update 24 | stencil7+dot 16            (kernels_cg/stencil.cu)
+#   1: two kernels    r-update+norms 24 | x-update + p-update + stencil7 + dot 48   (kernels_fused.cu)
+BYTES_ITER = {0: 88, 1: 72}
+BYTES_DOMINANT = {0: 16, 1: 48}
+KERNEL_DOMINANT = {0: "stencil7_dot_tma", 1: "cg_fused_kernel (x-update + p-update + stencil7 + p.Ap dot)"}
 
 
 def measured_peak():
@@ -200,7 +205,10 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-timestep", action="store_true")
     ap.add_argument("--timestep-cells", type=int, default=128, help="grid of the extra full-timestep measurement")
+    ap.add_argument("--cg-variant", type=int, default=1, choices=[0, 1], help="1 = two-kernel iteration (72 B/cell)")
+    ap.add_argument("--tune", action="append", default=[], help="key=value passed to cfb_set_tuning")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -237,6 +245,10 @@ def main():
     s.fill_synthetic_velocity(0)
     s.build_rhs()
     s.set_tuning("time_kernels", 1)
+    s.set_tuning("cg_variant", args.cg_variant)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        s.set_tuning(k, int(v))
 
     for _ in range(args.warmup):
         s.pcg_fixed(args.iters)
@@ -259,27 +271,45 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall = float(t[0]), float(t[1])
     total_iters = args.iters * args.steps
-    value = total_iters / (dev_ms * 1e-3)
+    global_its = total_iters / (dev_ms * 1e-3)
+    # whole-job value: one unit = one CG iteration over one cells^3 block.  Weak scaling: every rank
+    # owns such a block, so a global iteration processes `world` units; strong: the global grid is one unit.
+    units = world if args.scaling == "weak" else 1
+    value = global_its * units
 
     # roofline of the dominant kernel, from the per-kernel events recorded inside the timed region
     peak, peak_src = measured_peak()
     kt = max(1, st["k_timed_iters"])
     t_st = st["ms_k_stencil"] / kt
-    ach = ncell_local * BYTES_STENCIL / (t_st * 1e-3) / 1e9 if t_st > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "stencil7_dot_tma", "achieved": ach, "peak": peak, "unit": "GB/s",
+    v = args.cg_variant
+    bdom, biter = BYTES_DOMINANT[v], BYTES_ITER[v]
+    ach = ncell_local * bdom / (t_st * 1e-3) / 1e9 if t_st > 0 else 0.0
+    it_ach = ncell_local * biter * total_iters / (dev_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": KERNEL_DOMINANT[v], "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ncell_local * BYTES_STENCIL,
+                "algorithmic_bytes_per_cell": bdom,
+                "algorithmic_bytes_per_launch": ncell_local * bdom,
                 "avg_launch_ms": t_st,
-                "iteration": {"bytes_per_cell": BYTES_ITER,
-                              "achieved_gbs": ncell_local * BYTES_ITER * total_iters / (dev_ms * 1e-3) / 1e9,
-                              "axpy_ms": st["ms_k_axpy"] / kt, "pupdate_ms": st["ms_k_pupdate"] / kt,
-                              "stencil_ms": t_st}}
+                "iteration": {"form": "two kernels" if v == 1 else "three kernels", "bytes_per_cell": biter,
+                              "achieved_gbs": it_ach, "frac": it_ach / peak}}
+    if v == 1:
+        roofline["iteration"].update({"rupdate_ms": st["ms_k_axpy"] / kt, "fused_ms": t_st})
+    else:
+        roofline["iteration"].update({"axpy_ms": st["ms_k_axpy"] / kt, "pupdate_ms": st["ms_k_pupdate"] / kt,
+                                      "stencil_ms": t_st})
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get(f"stencil7_dot_{args.cells}")
+            roofline["traffic"] = json.load(open(tr)).get(f"cg_variant{v}_dominant_{args.cells}")
         except Exception:
             pass
+    # the plain stencil7 + dot kernel (16 B/cell: CG kernel 4 on its own, used for the first q = A p
+    # of every solve), timed back to back on the same vectors
+    if world == 1:
+        _, st_ms = s.stencil_dot(20)
+        roofline["stencil7_dot_alone"] = {"avg_launch_ms": st_ms, "algorithmic_bytes_per_cell": BYTES_STENCIL,
+                                          "achieved": ncell_local * BYTES_STENCIL / (st_ms * 1e-3) / 1e9,
+                                          "frac": ncell_local * BYTES_STENCIL / (st_ms * 1e-3) / 1e9 / peak}
     launches = st["kernel_launches"]
 
     # e2e: the solver plug-in call with HOST vectors (pinned), H2D of b and D2H of x inside the timed region
@@ -301,13 +331,37 @@ def main():
             t = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_wall = float(t[0])
-        e2e = {"value": args.iters * e_steps / e_wall, "unit": UNIT, "h2d_bytes_per_step": int(b_host.nbytes) * world,
+        e2e = {"value": args.iters * e_steps / e_wall * units, "unit": UNIT, "h2d_bytes_per_step": int(b_host.nbytes) * world,
                "d2h_bytes_per_step": int(x_host.nbytes) * world, "steps": e_steps,
                "call": "cfb_pcg_solve_host (ReferenceConjugateGradient::solve(b, x) with host vectors)"}
         del b_host, x_host
 
     # extra: whole timesteps (advect + inputs + projection) of the default inflow problem, 1 GPU only
-    extra = {"final_residual": resid, "wall_s_timed_region": wall, "cells_local": ncell_local}
+    extra = {"final_residual": resid, "wall_s_timed_region": wall, "cells_local": ncell_local,
+             "global_iterations_per_s": global_its,
+             "value_unit": "CG iterations of one %d^3 block per second, summed over ranks" % args.cells}
+    # whole timesteps (advect + inputs + projection) on the bench grid itself, at every N: the
+    # projection runs the same fixed number of CG iterations as the headline (the reference's own
+    # tol/max_iter cannot converge at 512^3)
+    if not args.no_timestep:
+        s.setup()
+        s.step()
+        barrier()
+        t0 = time.perf_counter()
+        nst = 3
+        for _ in range(nst):
+            s.step()
+        barrier()
+        dt_steps = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt_steps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_steps = float(t[0])
+        st2 = s.stats()
+        extra["timesteps_per_s_bench_grid"] = {
+            "global_cells": list(gcells), "value": nst / dt_steps, "cg_iters_per_step": args.iters,
+            "interp_order": 3, "ms_advect": st2["ms_advect"] / (nst + 1), "note": "projection capped at the "
+            "headline's fixed CG iteration count; wall clock between barriers, max over ranks"}
     if world == 1 and args.timestep_cells > 0:
         s.close()
         from cajitafluids_b200 import default_config

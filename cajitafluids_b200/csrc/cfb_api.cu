@@ -143,6 +143,42 @@ int enqueue_iteration( cfb_ctx* c )
     cudaEvent_t* e = nullptr;
     if ( c->time_kernels && c->ktimed < CFB_KTIMED )
         e = c->kev[c->ktimed++];
+    if ( c->cg_variant == 1 )
+    {
+        // two-kernel form (kernels_fused.cu): e[0..1] phase A, e[2..3] phase B
+        if ( e )
+            cudaEventRecord( e[0], c->stream );
+        n += launch_cg_rupdate( c );
+        if ( e )
+        {
+            cudaEventRecord( e[1], c->stream );
+            cudaEventRecord( e[2], c->stream );
+        }
+        if ( c->cfg.use_nccl )
+        {
+            double* fl[2] = { c->cg_r, c->cg_p };
+            if ( c->overlap_halo && c->n_interior > 0 )
+            {
+                halo_cells_begin( c, fl, 2, 1 );
+                n += launch_cg_fused( c, 1 );
+                halo_cells_end( c );
+                n += launch_cg_fused( c, 2 );
+            }
+            else
+            {
+                halo_cells_begin( c, fl, 2, 1 );
+                halo_cells_end( c );
+                n += launch_cg_fused( c, 0 );
+            }
+            cg_global_sum( c, 0 );
+        }
+        else
+            n += launch_cg_fused( c, 0 );
+        cg_select_p( c, c->pcur ^ 1 ); // phase B wrote the new p into the other buffer
+        if ( e )
+            cudaEventRecord( e[3], c->stream );
+        return n;
+    }
     if ( e )
         cudaEventRecord( e[0], c->stream );
     n += launch_cg_axpy( c );
@@ -185,6 +221,7 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     const int fixed = fixed_iters > 0;
     const int max_it = fixed ? fixed_iters : c->cfg.cg_max_iter;
     long long launches = 0;
+    const int p_start = c->pcur;
     launches += launch_cg_init( c, fixed );
     if ( c->cfg.use_nccl )
         halo_exchange_cells( c, c->cg_p, 1 );
@@ -210,7 +247,9 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
         if ( pending )
         {
             CFB_CUDA( c, cudaEventSynchronize( c->ev[EV_POLL] ) );
-            done = c->h_state->done != 0;
+            const CgState* hs = c->h_state;
+            // two-kernel form: `done` is recorded one phase after the tolerance was met
+            done = hs->done != 0 || ( hs->iter > 0 && std::sqrt( hs->rr ) <= hs->thresh );
             pending = 0;
         }
         if ( !done )
@@ -220,6 +259,8 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
             pending = 1;
         }
     }
+    if ( c->cg_variant == 1 )
+        launches += launch_cg_finish( c );
     CFB_CUDA( c, cudaMemcpyAsync( c->h_state, c->d_state, STATE_HEAD, cudaMemcpyDeviceToHost, c->stream ) );
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
     int rc = check_async( c, "pcg_solve" );
@@ -229,6 +270,13 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     c->stats.kernel_launches += launches;
     c->last_iters = c->h_state->iter;
     c->last_resid = std::sqrt( c->h_state->rr );
+    if ( c->cg_variant == 1 )
+    {
+        // launches enqueued after convergence were no-ops on the device but flipped the host's idea
+        // of the current p buffer: every executed phase B except a converging one wrote a new p
+        const int swaps = c->last_iters - ( ( c->h_state->done && c->last_iters > 0 ) ? 1 : 0 );
+        cg_select_p( c, p_start + swaps );
+    }
     c->stats.cg_iterations += c->last_iters;
     if ( num_iter )
         *num_iter = c->last_iters;
@@ -464,7 +512,9 @@ int cfb_create( const cfb_config* cfg, cfb_ctx** out )
     CFB_CUDA( c, alloc0( &c->lhs ) );
     CFB_CUDA( c, alloc0( &c->rhs ) );
     CFB_CUDA( c, alloc0( &c->cg_r ) );
-    CFB_CUDA( c, alloc0( &c->cg_p ) );
+    CFB_CUDA( c, alloc0( &c->cg_pbuf[0] ) );
+    CFB_CUDA( c, alloc0( &c->cg_pbuf[1] ) );
+    c->cg_p = c->cg_pbuf[0];
     CFB_CUDA( c, alloc0( &c->cg_q ) );
     CFB_CUDA( c, cudaMalloc( &c->d_state, sizeof( CgState ) ) );
     CFB_CUDA( c, cudaMemsetAsync( c->d_state, 0, sizeof( CgState ), c->stream ) );
@@ -503,7 +553,9 @@ int cfb_create( const cfb_config* cfg, cfb_ctx** out )
     }
     else
         c->cfg.use_nccl = 0;
-    return CFB_OK;
+    // two-kernel CG iteration: tensor maps of cg_r / cg_p and the interior/boundary unit list
+    // (needs the neighbour ranks halo_init just set)
+    return fused_setup( c );
 }
 
 int cfb_destroy( cfb_ctx* c )
@@ -518,9 +570,11 @@ int cfb_destroy( cfb_ctx* c )
         for ( int v = 0; v < 2; ++v )
             if ( c->fld[f][v] )
                 cudaFree( c->fld[f][v] );
-    for ( double* p : { c->lhs, c->rhs, c->cg_r, c->cg_p, c->cg_q, c->d_partials } )
+    for ( double* p : { c->lhs, c->rhs, c->cg_r, c->cg_pbuf[0], c->cg_pbuf[1], c->cg_q, c->d_partials } )
         if ( p )
             cudaFree( p );
+    if ( c->d_units )
+        cudaFree( c->d_units );
     if ( c->d_state )
         cudaFree( c->d_state );
     if ( c->h_state )
@@ -833,6 +887,20 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->st_zc = value;
     else if ( k == "poll_every" )
         c->poll_every = value;
+    else if ( k == "cg_variant" )
+        c->cg_variant = value;
+    else if ( k == "fused_tx" )
+        c->fu_tx = value;
+    else if ( k == "fused_ty" )
+        c->fu_ty = value;
+    else if ( k == "fused_stages" )
+        c->fu_stages = value;
+    else if ( k == "fused_zc" )
+        c->fu_zc = value;
+    else if ( k == "rupdate_ctas" )
+        c->ru_ctas = value;
+    else if ( k == "overlap_halo" )
+        c->overlap_halo = value != 0;
     else if ( k == "time_kernels" )
     {
         c->time_kernels = value != 0;
@@ -841,10 +909,21 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
                 for ( auto& e : row )
                     CFB_CUDA( c, cudaEventCreate( &e ) );
     }
+    else if ( k == "fused_auto" )
+        ;
     else
         return cfb_fail( c, CFB_ERR_INVALID, "unknown tuning key: " + k );
     if ( k == "stencil_tx" || k == "stencil_ty" )
         return stencil_setup( c );
+    if ( k == "fused_auto" )
+    {
+        c->fu_auto = value != 0;
+        return fused_setup( c );
+    }
+    if ( k.rfind( "fused_", 0 ) == 0 )
+        c->fu_auto = false;
+    if ( k == "fused_tx" || k == "fused_ty" || k == "fused_zc" )
+        return fused_setup( c );
     return CFB_OK;
 }
 

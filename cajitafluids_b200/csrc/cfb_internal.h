@@ -62,6 +62,7 @@ struct CgState
     int pad0;
     double bnorm;                   // sqrt(rr) of r0
     double thresh;                  // absolute threshold in use
+    double alpha;                   // two-kernel form: alpha of the running iteration (phase A -> B)
     int iter;                       // completed iterations (kernel-1 executions)
     int done;                       // 1 once sqrt(rr) <= thresh
     int fixed;                      // fixed-iteration mode: never set done
@@ -93,6 +94,11 @@ struct cfb_ctx
     double* fld[4][2] = { { nullptr } };
     int cur[4] = { 0, 0, 0, 0 };
     double *lhs = nullptr, *rhs = nullptr, *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr;
+    // the search direction is double-buffered: the two-kernel iteration recomputes the new p on tile
+    // halos from the OLD p of neighbouring tiles, so it cannot be updated in place.  cg_p (and
+    // tmap_p) always name the current buffer cg_pbuf[pcur].
+    double* cg_pbuf[2] = { nullptr, nullptr };
+    int pcur = 0;
 
     CgState* d_state = nullptr;
     CgState* h_state = nullptr; // pinned mirror (first bytes only are copied)
@@ -100,10 +106,22 @@ struct cfb_ctx
 
     // stencil TMA descriptor + tiling
     CUtensorMap tmap_p{};
+    CUtensorMap tmap_pbuf[2] = {}; // stencil-box maps of cg_pbuf[0 / 1]
     bool tmap_ok = false;
     int st_variant = 0; // 0 = TMA z-march (default)
     int st_tx = 64, st_ty = 16, st_stages = 4, st_zc = 64;
     int poll_every = 0; // 0 = auto
+
+    // two-kernel CG iteration (kernels_fused.cu): tensor maps of cg_r / cg_p, tiling, unit list
+    int cg_variant = 1; // 1 = two kernels / 72 B per cell (default), 0 = three kernels / 88 B
+    CUtensorMap tmap_fr{}, tmap_fp[2] = {}; // fused-box maps of cg_r and of cg_pbuf[0 / 1]
+    bool fused_ok = false;
+    bool fu_auto = true; // pick the tiling from the block size; any "fused_*" tuning key turns it off
+    int fu_tx = 64, fu_ty = 16, fu_stages = 3, fu_zc = 64;
+    int* d_units = nullptr; // (tile_x, tile_y, chunk) triples: interior units first, then boundary
+    int n_units = 0, n_interior = 0;
+    int ru_ctas = 3;          // phase A: CTAs per SM of the grid-stride launch
+    bool overlap_halo = true; // multi-GPU: interior units run while the r/p ghosts are in flight
 
     // stats
     cudaEvent_t ev[16] = { nullptr };
@@ -137,6 +155,14 @@ int cfb_fail( cfb_ctx* c, int code, const std::string& msg );
                              std::string( #expr ) + ": " + cudaGetErrorString( _e ) + " at " +     \
                                  __FILE__ + ":" + std::to_string( __LINE__ ) );                    \
     } while ( 0 )
+
+// make cg_pbuf[which] the current search-direction buffer
+inline void cg_select_p( cfb_ctx* c, int which )
+{
+    c->pcur = which & 1;
+    c->cg_p = c->cg_pbuf[c->pcur];
+    c->tmap_p = c->tmap_pbuf[c->pcur];
+}
 
 inline double* field_ptr( cfb_ctx* c, int field, int version )
 {
@@ -177,10 +203,19 @@ int launch_cg_pupdate( cfb_ctx* c );          // convergence bookkeeping + kerne
 // kernels_stencil.cu
 int stencil_setup( cfb_ctx* c );              // builds the tensor map for cg_p
 int launch_stencil_dot( cfb_ctx* c );         // kernel 4
+// kernels_fused.cu
+int fused_setup( cfb_ctx* c );                // tensor maps of cg_r, cg_p + the unit list
+int launch_cg_rupdate( cfb_ctx* c );          // phase A: r -= alpha q, sum r^2, sum r.Minv r
+int launch_cg_fused( cfb_ctx* c, int which ); // phase B: 0 = all units, 1 = interior, 2 = boundary
+int launch_cg_finish( cfb_ctx* c );
 // halo.cu
 int halo_init( cfb_ctx* c );
 void halo_destroy( cfb_ctx* c );
 int halo_exchange_cells( cfb_ctx* c, double* field, int width ); // face-neighbour exchange of a cell array
+// the same for up to two cell arrays in one message per neighbour, split into begin (fork to the side
+// stream) / end (join), so that work not reading ghosts can be launched in between
+int halo_cells_begin( cfb_ctx* c, double* const* fields, int nf, int width );
+int halo_cells_end( cfb_ctx* c );
 int halo_exchange_fields( cfb_ctx* c, int version );             // width-h exchange of q,u,v,w
 int halo_allreduce( cfb_ctx* c, double* dev_vals, int n );
 int halo_allgather( cfb_ctx* c, const double* dev_send, double* dev_recv, int n_per_rank );

@@ -321,7 +321,7 @@ void halo_destroy( cfb_ctx* c )
 // Width-`w` face-neighbour exchange of one cell array (p of the CG, the pressure before
 // _applyPressure), enqueued on the SIDE stream: halo_cells_begin() forks from the main stream,
 // halo_cells_end() joins.  Between the two the caller may launch work that does not read ghosts.
-int halo_cells_begin( cfb_ctx* c, double* field, int w )
+int halo_cells_begin( cfb_ctx* c, double* const* fields, int nf, int w )
 {
     Comm* cm = static_cast<Comm*>( c->nccl );
     const Geo& g = c->g;
@@ -347,8 +347,10 @@ int halo_cells_begin( cfb_ctx* c, double* field, int w )
         rhi[d].lo[d] = g.n[d];
         rhi[d].hi[d] = g.n[d] + w;
     }
-    double* fl[4] = { field, nullptr, nullptr, nullptr };
-    int rc = exchange( c, 1, fl, g.D, dims, slo, shi, rlo, rhi, c->comm_stream );
+    double* fl[4] = { nullptr, nullptr, nullptr, nullptr };
+    for ( int f = 0; f < nf && f < 4; ++f )
+        fl[f] = fields[f];
+    int rc = exchange( c, nf, fl, g.D, dims, slo, shi, rlo, rhi, c->comm_stream );
     if ( rc )
         return rc;
     CFB_CUDA( c, cudaEventRecord( cm->ev_done, c->comm_stream ) );
@@ -364,7 +366,7 @@ int halo_cells_end( cfb_ctx* c )
 
 int halo_exchange_cells( cfb_ctx* c, double* field, int width )
 {
-    int rc = halo_cells_begin( c, field, width );
+    int rc = halo_cells_begin( c, &field, 1, width );
     if ( rc )
         return rc;
     return halo_cells_end( c );

@@ -1,0 +1,747 @@
+// kernels_fused.cu — the two-kernel form of one Jacobi-PCG iteration (72 algorithmic bytes per cell
+// instead of the 88 of the three-kernel form in kernels_cg.cu / kernels_stencil.cu, and instead of
+// the 168 of the reference's stored-coefficient four-kernel form).
+//
+// Same arithmetic, statement by statement, as Cajita::ReferenceConjugateGradient::solve (SURVEY.md
+// §3.3; driven from src/VelocityCorrector.hpp:276), only scheduled differently between the two
+// reduction points an iteration of CG has:
+//
+//   phase A  cg_rupdate   alpha = zr_old / pAp ; r -= alpha q ; sum r^2 ; sum r.M^-1 r
+//                         (24 B/cell: read r, q; write r)
+//   phase B  cg_fused     convergence test ; x += alpha p (the update phase A deferred: p is read
+//                         here anyway) ; beta = zr_new / zr_old ; p = M^-1 r + beta p ; q = A p ;
+//                         sum p.q            (48 B/cell: read r, p, x; write p, x, q)
+//
+// Phase B is the 2.5-D z-marching stencil of kernels_stencil.cu with the p-update moved in front of
+// it: the r and p planes of a (TX+4) x (TY+2) box are staged by TMA into a shared-memory ring, the
+// new p is computed for the tile AND its one-cell x/y halo ring (recomputed, not exchanged between
+// CTAs), kept in a 3-deep shared ring for the x/y neighbours and in registers for the z neighbours.
+// x is streamed with 128-bit LDG/STG, prefetched one plane ahead.  The value of every element is
+// produced by exactly the same expression as in the three-kernel form, so results are bit-identical
+// to it and to the checker.
+//
+// After every phase B x is complete, so a solve may end after any whole iteration.
+#include "cfb_internal.h"
+#include "device_geo.cuh"
+#include "device_reduce.cuh"
+#include "device_tma.cuh"
+
+#include <algorithm>
+
+namespace
+{
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ void pair_decode( const Geo& g, unsigned t, unsigned npx, int& i, int& j, int& k )
+{
+    unsigned row = t / npx;
+    i = 2 * (int)( t - row * npx );
+    k = (int)( row / (unsigned)g.n[1] );
+    j = (int)( row - (unsigned)k * (unsigned)g.n[1] );
+}
+
+__device__ __forceinline__ bool cg_converged( const CgState* S )
+{
+    return !S->fixed && sqrt( S->rr ) <= S->thresh;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase A.  Thread layout: 256 threads = TXP (power of two, 32..256) along x times 256/TXP rows; a
+// block walks over batches of (256/TXP) * RU rows, every thread issuing the 128-bit loads of its RU
+// rows before touching any of them (2 * RU * 16 bytes in flight per thread: this kernel has no
+// reuse at all, it lives on memory-level parallelism), one integer division per RU column pairs.
+constexpr int RU = 4;
+
+__global__ void __launch_bounds__( NT, 3 )
+    cg_rupdate_kernel( const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
+                       const double* __restrict__ q, double* __restrict__ r, CgState* S, double* partials,
+                       int txp_log2 )
+{
+    // `done` is only ever written by this kernel, cg_check0 and cg_finish (never by phase B, whose
+    // late CTAs would otherwise see it mid-launch); phase B of the iteration that met the tolerance
+    // has already applied its x update, so there is nothing left to do.
+    if ( S->done || ( S->iter > 0 && cg_converged( S ) ) )
+    {
+        if ( blockIdx.x == 0 && threadIdx.x == 0 )
+            S->done = 1;
+        return;
+    }
+    const double alpha = S->rz_old / S->pAp;
+    const double nalpha = -alpha;
+    if ( blockIdx.x == 0 && threadIdx.x == 0 )
+        S->alpha = alpha;
+    const int txp = 1 << txp_log2, tyr = NT >> txp_log2;
+    const int lx = threadIdx.x & ( txp - 1 ), ry = threadIdx.x >> txp_log2;
+    const int npx = ( g.n[0] + 1 ) >> 1;
+    const int rows = g.n[1] * g.n[2];
+    const int batch = tyr * RU;
+    const bool odd = g.n[0] & 1;
+    dd_t rr = { 0.0, 0.0 }, rz = { 0.0, 0.0 };
+    for ( int row0 = blockIdx.x * batch; row0 < rows; row0 += gridDim.x * batch )
+    {
+        // rows of this thread: row0 + ry + u * tyr
+        int cyz[RU];
+        long long ro[RU];
+        bool ok[RU];
+#pragma unroll
+        for ( int u = 0; u < RU; ++u )
+        {
+            const int row = row0 + ry + u * tyr;
+            ok[u] = row < rows;
+            const int k = row / g.n[1];
+            const int j = row - k * g.n[1];
+            cyz[u] = wall_count( g, 1, j + g.off[1] ) + wall_count( g, 2, k + g.off[2] );
+            ro[u] = geo_off( g, 0, j, k );
+        }
+        for ( int ip = lx; ip < npx; ip += txp )
+        {
+            const int i = 2 * ip;
+            const bool two = !odd || ip + 1 < npx;
+            double2 qv[RU], rv[RU];
+#pragma unroll
+            for ( int u = 0; u < RU; ++u )
+            {
+                qv[u] = make_double2( 0.0, 0.0 );
+                rv[u] = make_double2( 0.0, 0.0 );
+                if ( ok[u] )
+                {
+                    if ( two )
+                    {
+                        qv[u] = *reinterpret_cast<const double2*>( q + ro[u] + i );
+                        rv[u] = *reinterpret_cast<const double2*>( r + ro[u] + i );
+                    }
+                    else
+                    {
+                        qv[u].x = q[ro[u] + i];
+                        rv[u].x = r[ro[u] + i];
+                    }
+                }
+            }
+            const int wx0 = wall_count( g, 0, i + g.off[0] ), wx1 = wall_count( g, 0, i + 1 + g.off[0] );
+#pragma unroll
+            for ( int u = 0; u < RU; ++u )
+            {
+                if ( !ok[u] )
+                    continue;
+                double2 v = rv[u];
+                v.x = fma( nalpha, qv[u].x, v.x );
+                dd_acc( rr, v.x * v.x );
+                dd_acc( rz, ( op.minv[cyz[u] + wx0] * v.x ) * v.x );
+                if ( two )
+                {
+                    v.y = fma( nalpha, qv[u].y, v.y );
+                    *reinterpret_cast<double2*>( r + ro[u] + i ) = v;
+                    dd_acc( rr, v.y * v.y );
+                    dd_acc( rz, ( op.minv[cyz[u] + wx1] * v.y ) * v.y );
+                }
+                else
+                    r[ro[u] + i] = v.x;
+            }
+        }
+    }
+    dd_t vals[2] = { rr, rz };
+    if ( block_reduce_finalize<NT, 2>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
+    {
+        if ( threadIdx.x == 0 )
+        {
+            if ( S->world > 1 )
+            {
+                S->loc[2] = vals[1].hi;
+                S->loc[3] = vals[1].lo;
+                S->loc[4] = vals[0].hi;
+                S->loc[5] = vals[0].lo;
+            }
+            else
+            {
+                S->rr = vals[0].hi + vals[0].lo;
+                S->rz_new = vals[1].hi + vals[1].lo;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// end of a solve: after any phase B x is up to date; only the `done` flag may be missing when the
+// tolerance was met by the very last iteration enqueued (no phase A followed to record it).
+__global__ void cg_finish_kernel( CgState* S )
+{
+    if ( !S->done && S->iter > 0 && cg_converged( S ) )
+        S->done = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase B
+template <int TX_, int TY_, int NS_>
+struct FusedCfg
+{
+    static constexpr int TX = TX_, TY = TY_, NS = NS_;
+    static constexpr int NT = 256;
+    static constexpr int LX = TX / 2;  // threads along x (one column pair each)
+    static constexpr int WY = NT / LX; // thread rows
+    static constexpr int RY = TY / WY; // rows per thread
+    static constexpr int PX = TX + 4;  // smem row pitch: 2-wide x halo keeps pairs 16-B aligned
+    static constexpr int PY = TY + 2;
+    static constexpr int BOX_BYTES = PX * PY * 8;
+    static constexpr int BOX_PAD = ( BOX_BYTES + 127 ) / 128 * 128;
+    static constexpr int STAGE_BYTES = 2 * BOX_PAD; // r box, p box
+    static constexpr int NPN = 3;                   // new-p planes kept in shared memory
+    static constexpr int SMEM_BYTES = NS * STAGE_BYTES + NPN * BOX_PAD + 128;
+    static constexpr int CTAS = SMEM_BYTES <= 56 * 1024 ? 4 : ( SMEM_BYTES <= 75 * 1024 ? 3 : ( SMEM_BYTES <= 113 * 1024 ? 2 : 1 ) );
+    static_assert( TX % 2 == 0 && NT % LX == 0 && TY % WY == 0 && RY >= 1 && LX % 32 == 0, "bad tile" );
+};
+
+struct FusedArgs
+{
+    double *x, *p, *q; // p: the buffer the NEW search direction is written to
+    const double* p_old;
+    CgState* S;
+    double* partials;
+    const int* units; // optional unit list (tile_x, tile_y, chunk) triples; nullptr = all units in order
+    int tiles_x, tiles_y, zc, hx;
+    int unit_base;   // index of this launch's first unit in the partial-sum scratch
+    int units_total; // units of all launches that make up one phase B (last-block ticket target)
+};
+
+template <class C>
+__global__ void __launch_bounds__( C::NT, C::CTAS )
+    cg_fused_kernel( const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_p,
+                     const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
+                     const __grid_constant__ FusedArgs a )
+{
+    constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
+    constexpr int BOXD = C::BOX_PAD / 8, STAGED = C::STAGE_BYTES / 8;
+    CgState* S = a.S;
+    if ( S->done )
+        return;
+
+    const int tid = threadIdx.x;
+    const int lx = tid % LX, wy = tid / LX;
+
+    // unit -> (tile_x, tile_y, z chunk)
+    int tx, ty, ch;
+    if ( a.units )
+    {
+        tx = a.units[3 * blockIdx.x + 0];
+        ty = a.units[3 * blockIdx.x + 1];
+        ch = a.units[3 * blockIdx.x + 2];
+    }
+    else
+    {
+        const int u = blockIdx.x;
+        tx = u % a.tiles_x;
+        ty = ( u / a.tiles_x ) % a.tiles_y;
+        ch = u / ( a.tiles_x * a.tiles_y );
+    }
+    const int x0 = tx * TX, y0 = ty * TY;
+    const int kbeg = ch * a.zc;
+    const int kend = min( kbeg + a.zc, g.n[2] );
+    const int nplanes = kend - kbeg;
+    const int nloads = nplanes + 2; // planes kbeg-1 .. kend
+
+    const int i0 = x0 + 2 * lx;
+    const bool vx0 = i0 < g.n[0], vx1 = i0 + 1 < g.n[0];
+    bool vy[RY];
+#pragma unroll
+    for ( int r = 0; r < RY; ++r )
+        vy[r] = y0 + wy + r * WY < g.n[1];
+
+    // ---- convergence bookkeeping of the iteration (the reference's test after kernel 1) ----------
+    const double alpha = S->alpha;
+    const double resid = sqrt( S->rr );
+    const bool conv = !S->fixed && resid <= S->thresh;
+    if ( a.unit_base + blockIdx.x == 0 && tid == 0 )
+    {
+        const int it = S->iter;
+        if ( it < CFB_HIST_MAX )
+            S->hist[it] = resid;
+        S->iter = it + 1;
+    }
+    if ( conv )
+    {
+        // x += alpha p of the converged iteration; nothing else (the loop breaks here)
+        for ( int k = kbeg; k < kend; ++k )
+#pragma unroll
+            for ( int r = 0; r < RY; ++r )
+            {
+                if ( !vy[r] || !vx0 )
+                    continue;
+                const long long o = geo_off( g, i0, y0 + wy + r * WY, k );
+                if ( vx1 )
+                {
+                    const double2 pv = *reinterpret_cast<const double2*>( a.p_old + o );
+                    double2 xv = *reinterpret_cast<double2*>( a.x + o );
+                    xv.x = fma( alpha, pv.x, xv.x );
+                    xv.y = fma( alpha, pv.y, xv.y );
+                    *reinterpret_cast<double2*>( a.x + o ) = xv;
+                }
+                else
+                    a.x[o] = fma( alpha, a.p_old[o], a.x[o] );
+            }
+        return;
+    }
+    const double beta = S->rz_new / S->rz_old;
+
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__( 8 ) unsigned long long full_bar[NS];
+    const uint32_t smem_base = ( smem_u32( smem_raw ) + 127u ) & ~127u;
+    double* stage0 = reinterpret_cast<double*>( smem_raw + ( smem_base - smem_u32( smem_raw ) ) );
+    double* pn0 = stage0 + NS * STAGED;
+
+    // TMA box origin (array coordinates): 2 columns left of the tile, 1 row below, plane kbeg-1
+    const int cx = a.hx + x0 - 2;
+    const int cy = g.h + y0 - 1;
+    const int cz = g.h + kbeg - 1;
+
+    auto issue = [&]( int l ) {
+        const int s = l % NS;
+        const uint32_t bar = smem_u32( &full_bar[s] );
+        mbar_expect_tx( bar, 2 * C::BOX_BYTES );
+        tma_load_3d( smem_base + s * C::STAGE_BYTES, &tmap_r, bar, cx, cy, cz + l );
+        tma_load_3d( smem_base + s * C::STAGE_BYTES + C::BOX_PAD, &tmap_p, bar, cx, cy, cz + l );
+    };
+
+    if ( tid == 0 )
+    {
+        prefetch_tmap( &tmap_r );
+        prefetch_tmap( &tmap_p );
+#pragma unroll
+        for ( int s = 0; s < NS; ++s )
+            mbar_init( smem_u32( &full_bar[s] ), 1 );
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if ( tid == 0 )
+    {
+        const int n0 = nloads < NS ? nloads : NS;
+        for ( int l = 0; l < n0; ++l )
+            issue( l );
+    }
+
+    // per-thread constants: SOLID-wall counts of my cells and of my share of the halo ring
+    const int wx0 = wall_count( g, 0, i0 + g.off[0] );
+    const int wx1 = wall_count( g, 0, i0 + 1 + g.off[0] );
+    int wyc[RY];
+#pragma unroll
+    for ( int r = 0; r < RY; ++r )
+        wyc[r] = wall_count( g, 1, y0 + wy + r * WY + g.off[1] );
+    // y halo rows: thread row 0 takes the row below the tile, thread row WY-1 the row above
+    const bool do_yh = ( wy == 0 ) || ( wy == WY - 1 );
+    const int yh_row = ( wy == 0 ) ? 0 : TY + 1;
+    const int yh_w = wall_count( g, 1, y0 + yh_row - 1 + g.off[1] );
+    // x halo columns: 2 * TY single cells, taken by the lanes of one middle warp
+    constexpr int XH_WARP = ( NT / 32 ) / 2;
+    const bool do_xh = ( tid >> 5 ) == XH_WARP;
+    const double ns = op.neg_scale;
+
+    // x of my cells, prefetched one plane ahead
+    double2 xn[RY];
+    double* xrow = a.x + geo_off( g, i0, y0 + wy, kbeg );
+    double* prow = a.p + geo_off( g, i0, y0 + wy, kbeg );
+    double* qrow = a.q + geo_off( g, i0, y0 + wy, kbeg );
+    auto load_x = [&]( const double* xr ) {
+#pragma unroll
+        for ( int r = 0; r < RY; ++r )
+        {
+            xn[r] = make_double2( 0.0, 0.0 );
+            if ( vy[r] )
+            {
+                const double* xp = xr + (long long)( r * WY ) * g.sy;
+                if ( vx1 )
+                    xn[r] = *reinterpret_cast<const double2*>( xp );
+                else if ( vx0 )
+                    xn[r].x = *xp;
+            }
+        }
+    };
+    load_x( xrow );
+
+    // new p of plane-load l for my cells (-> out[]); with `full` also for my share of the halo ring
+    // into the shared new-p plane, and p, x of my cells are written back (plane owned by this chunk).
+    double2 zm[RY], cc[RY], zp[RY];
+    auto new_p = [&]( int l, double2 out[RY], bool full ) {
+        const double* R = stage0 + ( l % NS ) * STAGED;
+        const double* P = R + BOXD;
+        double* PN = pn0 + ( l % C::NPN ) * BOXD;
+        const int wz = wall_count( g, 2, kbeg + l - 1 + g.off[2] );
+        double2 xc[RY];
+        if ( full )
+        {
+#pragma unroll
+            for ( int r = 0; r < RY; ++r )
+                xc[r] = xn[r];
+            if ( l < nplanes ) // next owned plane
+                load_x( xrow + g.sz );
+        }
+#pragma unroll
+        for ( int r = 0; r < RY; ++r )
+        {
+            const int o = ( wy + r * WY + 1 ) * PX + 2 * lx + 2;
+            const double2 rv = *reinterpret_cast<const double2*>( R + o );
+            const double2 pv = *reinterpret_cast<const double2*>( P + o );
+            double2 v;
+            v.x = fma( beta, pv.x, op.minv[wx0 + wyc[r] + wz] * rv.x );
+            v.y = fma( beta, pv.y, op.minv[wx1 + wyc[r] + wz] * rv.y );
+            out[r] = v;
+            if ( full )
+            {
+                *reinterpret_cast<double2*>( PN + o ) = v;
+                if ( vy[r] )
+                {
+                    const long long go = (long long)( r * WY ) * g.sy;
+                    if ( vx1 )
+                    {
+                        *reinterpret_cast<double2*>( prow + go ) = v;
+                        double2 xv = xc[r];
+                        xv.x = fma( alpha, pv.x, xv.x );
+                        xv.y = fma( alpha, pv.y, xv.y );
+                        *reinterpret_cast<double2*>( xrow + go ) = xv;
+                    }
+                    else if ( vx0 )
+                    {
+                        prow[go] = v.x;
+                        xrow[go] = fma( alpha, pv.x, xc[r].x );
+                    }
+                }
+            }
+        }
+        if ( full )
+        {
+            if ( do_yh )
+            {
+                const int o = yh_row * PX + 2 * lx + 2;
+                const double2 rv = *reinterpret_cast<const double2*>( R + o );
+                const double2 pv = *reinterpret_cast<const double2*>( P + o );
+                double2 v;
+                v.x = fma( beta, pv.x, op.minv[wx0 + yh_w + wz] * rv.x );
+                v.y = fma( beta, pv.y, op.minv[wx1 + yh_w + wz] * rv.y );
+                *reinterpret_cast<double2*>( PN + o ) = v;
+            }
+            if ( do_xh )
+            {
+                for ( int it = tid & 31; it < 2 * TY; it += 32 )
+                {
+                    const int side = it / TY, row = it - side * TY; // side 0: column x0-1, 1: x0+TX
+                    const int col = side ? TX + 2 : 1;
+                    const int gi = x0 + ( side ? TX : -1 ) + g.off[0];
+                    const int cw = wall_count( g, 0, gi ) + wall_count( g, 1, y0 + row + g.off[1] ) + wz;
+                    const int o = ( row + 1 ) * PX + col;
+                    PN[o] = fma( beta, P[o], op.minv[cw] * R[o] );
+                }
+            }
+            xrow += g.sz;
+            prow += g.sz;
+        }
+    };
+
+    // prologue: plane kbeg-1 (z neighbour only), plane kbeg (first owned plane)
+    mbar_wait( smem_u32( &full_bar[0] ), 0 );
+    new_p( 0, zm, false );
+    mbar_wait( smem_u32( &full_bar[1 % NS] ), ( 1 / NS ) & 1 );
+    new_p( 1, cc, true );
+    __syncthreads();
+    if ( tid == 0 )
+    {
+        if ( NS < nloads )
+            issue( NS );
+        if ( NS + 1 < nloads && NS > 1 )
+            issue( NS + 1 );
+    }
+
+    dd_t acc = { 0.0, 0.0 };
+    for ( int it = 0; it < nplanes; ++it )
+    {
+        const int l = it + 2; // plane k+1
+        mbar_wait( smem_u32( &full_bar[l % NS] ), ( l / NS ) & 1 );
+        new_p( l, zp, l <= nplanes );
+        // q = A p on plane k = kbeg + it: x/y neighbours from the shared new-p plane of load it+1
+        const double* PN = pn0 + ( ( it + 1 ) % C::NPN ) * BOXD;
+        const int wz = wall_count( g, 2, kbeg + it + g.off[2] );
+#pragma unroll
+        for ( int r = 0; r < RY; ++r )
+        {
+            const double* pc = PN + ( wy + r * WY + 1 ) * PX + 2 * lx + 2;
+            const double xl = pc[-1];
+            const double xr = pc[2];
+            const double2 ym = *reinterpret_cast<const double2*>( pc - PX );
+            const double2 yp = *reinterpret_cast<const double2*>( pc + PX );
+            const double2 c = cc[r];
+            const double d0 = op.diag[wx0 + wyc[r] + wz];
+            const double d1 = op.diag[wx1 + wyc[r] + wz];
+            const double a0 = apply_row( d0, ns, c.x, xl, c.y, ym.x, yp.x, zm[r].x, zp[r].x );
+            const double a1 = apply_row( d1, ns, c.y, c.x, xr, ym.y, yp.y, zm[r].y, zp[r].y );
+            if ( vy[r] )
+            {
+                double* qp = qrow + (long long)( r * WY ) * g.sy;
+                if ( vx1 )
+                {
+                    *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
+                    dd_acc( acc, c.x * a0 );
+                    dd_acc( acc, c.y * a1 );
+                }
+                else if ( vx0 )
+                {
+                    *qp = a0;
+                    dd_acc( acc, c.x * a0 );
+                }
+            }
+            zm[r] = c;
+            cc[r] = zp[r];
+        }
+        qrow += g.sz;
+        __syncthreads(); // stage of load l is consumed, new-p plane of load l is complete
+        if ( tid == 0 && l + NS < nloads )
+            issue( l + NS );
+    }
+
+    // p.Ap: block partials at [unit_base + blockIdx.x], the block drawing the last of
+    // `units_total` tickets finalises (deterministic: double-double sums, order-independent)
+    {
+        __shared__ dd_t s_red[C::NT / 32];
+        __shared__ bool s_last;
+        dd_t s = dd_block_sum<C::NT>( acc, s_red );
+        const unsigned bid = (unsigned)a.unit_base + blockIdx.x;
+        if ( tid == 0 )
+        {
+            a.partials[(size_t)bid * 2 + 0] = s.hi;
+            a.partials[(size_t)bid * 2 + 1] = s.lo;
+            __threadfence();
+            const unsigned t = atomicAdd( &S->ticket[1], 1u );
+            s_last = ( t == (unsigned)a.units_total - 1 );
+        }
+        __syncthreads();
+        if ( !s_last )
+            return;
+        __threadfence();
+        dd_t tot = { 0.0, 0.0 };
+        for ( unsigned b = tid; b < (unsigned)a.units_total; b += C::NT )
+        {
+            dd_t w;
+            w.hi = __ldcg( a.partials + (size_t)b * 2 + 0 );
+            w.lo = __ldcg( a.partials + (size_t)b * 2 + 1 );
+            tot = dd_add( tot, w );
+        }
+        tot = dd_block_sum<C::NT>( tot, s_red );
+        if ( tid == 0 )
+        {
+            S->ticket[1] = 0u;
+            if ( S->world > 1 )
+            {
+                S->loc[0] = tot.hi;
+                S->loc[1] = tot.lo;
+            }
+            else
+                S->pAp = tot.hi + tot.lo;
+            S->rz_old = S->rz_new; // "zTr_old = zTr_new"
+        }
+    }
+}
+
+typedef CUresult ( *PFN_encodeTiled )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                       CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                       CUtensorMapFloatOOBfill );
+
+template <class C>
+int launch_fused_cfg( cfb_ctx* c, const FusedArgs& a, int grid )
+{
+    static bool attr_set = false;
+    if ( !attr_set )
+    {
+        cudaFuncSetAttribute( cg_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        attr_set = true;
+    }
+    cg_fused_kernel<C><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur], c->g, c->op, a );
+    return 1;
+}
+
+int dispatch_fused( cfb_ctx* c, const FusedArgs& a, int grid )
+{
+    const int key = c->fu_tx * 10000 + c->fu_ty * 100 + c->fu_stages;
+    switch ( key )
+    {
+    case 641603:
+        return launch_fused_cfg<FusedCfg<64, 16, 3>>( c, a, grid );
+    case 641604:
+        return launch_fused_cfg<FusedCfg<64, 16, 4>>( c, a, grid );
+    case 640803:
+        return launch_fused_cfg<FusedCfg<64, 8, 3>>( c, a, grid );
+    case 640804:
+        return launch_fused_cfg<FusedCfg<64, 8, 4>>( c, a, grid );
+    case 643202:
+        return launch_fused_cfg<FusedCfg<64, 32, 2>>( c, a, grid );
+    case 643203:
+        return launch_fused_cfg<FusedCfg<64, 32, 3>>( c, a, grid );
+    case 1280803:
+        return launch_fused_cfg<FusedCfg<128, 8, 3>>( c, a, grid );
+    case 1280804:
+        return launch_fused_cfg<FusedCfg<128, 8, 4>>( c, a, grid );
+    case 1281603:
+        return launch_fused_cfg<FusedCfg<128, 16, 3>>( c, a, grid );
+    default:
+        cfb_fail( c, CFB_ERR_INVALID, "unsupported fused tile configuration" );
+        return 0;
+    }
+}
+
+inline int stream_grid( const cfb_ctx* c, long long pairs )
+{
+    long long b = ( pairs + NT - 1 ) / NT;
+    long long cap = (long long)c->sm_count * 8;
+    if ( cap > CFB_MAX_PARTIALS )
+        cap = CFB_MAX_PARTIALS;
+    return (int)( b < 1 ? 1 : ( b > cap ? cap : b ) );
+}
+
+} // namespace
+
+// Tiling of phase B for the current block: tiles in x/y, z chunk, number of units.
+void fused_tiling( const cfb_ctx* c, int& tiles_x, int& tiles_y, int& zc, int& chunks )
+{
+    const Geo& g = c->g;
+    tiles_x = ( g.n[0] + c->fu_tx - 1 ) / c->fu_tx;
+    tiles_y = ( g.n[1] + c->fu_ty - 1 ) / c->fu_ty;
+    zc = c->fu_zc > 0 ? c->fu_zc : g.n[2];
+    while ( (long long)tiles_x * tiles_y * ( ( g.n[2] + zc - 1 ) / zc ) > CFB_MAX_PARTIALS )
+        zc *= 2;
+    chunks = ( g.n[2] + zc - 1 ) / zc;
+}
+
+// (Re)build the tensor maps of cg_r and cg_p for the current fused tile shape.
+int fused_setup( cfb_ctx* c )
+{
+    static PFN_encodeTiled encode = nullptr;
+    if ( !encode )
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres );
+        if ( e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn )
+            return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available" );
+        encode = (PFN_encodeTiled)fn;
+    }
+    const Geo& g = c->g;
+    if ( c->fu_auto )
+    {
+        // measured on B200 (profiles/r1_sweep_fused.log): 128x16 tiles, 3 stages, 64-plane chunks are
+        // the fastest from 256^3 up; smaller blocks need smaller tiles / chunks to fill 148 SMs
+        static const int cand[][4] = { { 128, 16, 3, 64 }, { 64, 16, 3, 32 }, { 64, 16, 3, 16 },
+                                       { 64, 8, 4, 16 },   { 64, 8, 4, 8 },   { 64, 8, 4, 4 } };
+        int pick = 5;
+        for ( int i = 0; i < 6; ++i )
+        {
+            const long long u = (long long)( ( g.n[0] + cand[i][0] - 1 ) / cand[i][0] ) *
+                                ( ( g.n[1] + cand[i][1] - 1 ) / cand[i][1] ) * ( ( g.n[2] + cand[i][3] - 1 ) / cand[i][3] );
+            if ( u >= 120 && u <= CFB_MAX_PARTIALS )
+            {
+                pick = i;
+                break;
+            }
+        }
+        c->fu_tx = cand[pick][0];
+        c->fu_ty = cand[pick][1];
+        c->fu_stages = cand[pick][2];
+        c->fu_zc = cand[pick][3];
+    }
+    cuuint64_t gdim[3] = { (cuuint64_t)g.sy, (cuuint64_t)g.ay, (cuuint64_t)g.az };
+    cuuint64_t gstride[2] = { (cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8 };
+    cuuint32_t box[3] = { (cuuint32_t)( c->fu_tx + 4 ), (cuuint32_t)( c->fu_ty + 2 ), 1 };
+    cuuint32_t estr[3] = { 1, 1, 1 };
+    CUtensorMap* maps[3] = { &c->tmap_fr, &c->tmap_fp[0], &c->tmap_fp[1] };
+    double* base[3] = { c->cg_r, c->cg_pbuf[0], c->cg_pbuf[1] };
+    for ( int m = 0; m < 3; ++m )
+    {
+        CUresult r = encode( maps[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base[m], gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+        if ( r != CUDA_SUCCESS )
+            return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string( (int)r ) );
+    }
+    // unit list: units whose tile touches a face with a neighbour rank (they read exchanged ghosts)
+    // go last, so that everything before them can run while the ghosts are in flight
+    int tiles_x, tiles_y, zc, chunks;
+    fused_tiling( c, tiles_x, tiles_y, zc, chunks );
+    std::vector<int> inner, outer;
+    for ( int ch = 0; ch < chunks; ++ch )
+        for ( int ty = 0; ty < tiles_y; ++ty )
+            for ( int tx = 0; tx < tiles_x; ++tx )
+            {
+                const bool bd = ( tx == 0 && c->nbr[0] >= 0 ) || ( tx == tiles_x - 1 && c->nbr[1] >= 0 ) ||
+                                ( ty == 0 && c->nbr[2] >= 0 ) || ( ty == tiles_y - 1 && c->nbr[3] >= 0 ) ||
+                                ( ch == 0 && c->nbr[4] >= 0 ) || ( ch == chunks - 1 && c->nbr[5] >= 0 );
+                std::vector<int>& v = bd ? outer : inner;
+                v.push_back( tx );
+                v.push_back( ty );
+                v.push_back( ch );
+            }
+    c->n_interior = (int)inner.size() / 3;
+    inner.insert( inner.end(), outer.begin(), outer.end() );
+    c->n_units = (int)inner.size() / 3;
+    if ( c->d_units )
+        cudaFree( c->d_units );
+    c->d_units = nullptr;
+    if ( cudaMalloc( &c->d_units, inner.size() * sizeof( int ) ) != cudaSuccess ||
+         cudaMemcpy( c->d_units, inner.data(), inner.size() * sizeof( int ), cudaMemcpyHostToDevice ) != cudaSuccess )
+        return cfb_fail( c, CFB_ERR_CUDA, "fused unit list upload failed" );
+    c->fused_ok = true;
+    return CFB_OK;
+}
+
+int launch_cg_rupdate( cfb_ctx* c )
+{
+    const Geo& g = c->g;
+    const int npx = ( g.n[0] + 1 ) / 2;
+    int txp_log2 = 5;
+    while ( ( 1 << txp_log2 ) < npx && txp_log2 < 8 )
+        ++txp_log2;
+    const int batch = ( NT >> txp_log2 ) * RU;
+    const long long rows = (long long)g.n[1] * g.n[2];
+    long long grid = ( rows + batch - 1 ) / batch;
+    const long long cap = std::min<long long>( (long long)c->sm_count * c->ru_ctas, CFB_MAX_PARTIALS );
+    if ( grid > cap )
+        grid = cap;
+    cg_rupdate_kernel<<<(int)grid, NT, 0, c->stream>>>( g, c->op, c->cg_q, c->cg_r, c->d_state, c->d_partials,
+                                                       txp_log2 );
+    if ( c->cfg.use_nccl )
+        cg_global_sum( c, 1 );
+    return 1;
+}
+
+int launch_cg_finish( cfb_ctx* c )
+{
+    cg_finish_kernel<<<1, 1, 0, c->stream>>>( c->d_state );
+    return 1;
+}
+
+// phase B over all units (which = 0), or over the device unit list `c->d_units` split into
+// interior units [0, n_interior) (which = 1) and boundary units [n_interior, n_units) (which = 2).
+int launch_cg_fused( cfb_ctx* c, int which )
+{
+    FusedArgs a{};
+    a.x = c->lhs;
+    a.p_old = c->cg_pbuf[c->pcur];
+    a.p = c->cg_pbuf[c->pcur ^ 1];
+    a.q = c->cg_q;
+    a.S = c->d_state;
+    a.partials = c->d_partials;
+    a.hx = 16;
+    int chunks;
+    fused_tiling( c, a.tiles_x, a.tiles_y, a.zc, chunks );
+    const int total = a.tiles_x * a.tiles_y * chunks;
+    a.units_total = total;
+    int grid = total;
+    if ( which != 0 )
+    {
+        if ( !c->d_units || c->n_units != total )
+        {
+            cfb_fail( c, CFB_ERR_INVALID, "fused unit list not built" );
+            return 0;
+        }
+        a.unit_base = which == 1 ? 0 : c->n_interior;
+        grid = which == 1 ? c->n_interior : total - c->n_interior;
+        a.units = c->d_units + 3 * a.unit_base;
+        if ( grid == 0 )
+            return 0;
+    }
+    return dispatch_fused( c, a, grid );
+}

@@ -167,6 +167,72 @@ def test_pcg_solve_parity(dim, cells):
     assert np.array_equal(hg, ho)
 
 
+FUSED_TILINGS = [(64, 16, 3), (64, 16, 4), (64, 8, 3), (64, 8, 4), (64, 32, 2), (64, 32, 3), (128, 8, 3),
+                 (128, 8, 4), (128, 16, 3)]
+
+
+@pytest.mark.parametrize("cells,walls", [((70, 50, 21), "solid"), ((130, 36, 5), "mixed"), ((33, 47), "solid")])
+def test_cg_two_kernel_form_matches_three_kernel_form_and_oracle(cells, walls):
+    """The 72 B/cell two-kernel iteration (kernels_fused.cu) against the 88 B/cell three-kernel one
+    and the oracle: same iteration count, residual history and pressure, bit for bit, for every
+    tiling (several z chunks, ragged tiles)."""
+    dim = len(cells)
+    bt = [K.SOLID] * 6 if walls == "solid" else [K.FREE, K.SOLID, K.SOLID, K.FREE, K.SOLID, K.FREE]
+    cfg = make_cfg(dim, cells, box=box_for(cells), boundary_type=bt)
+    ora = Oracle(cfg)
+    rng = np.random.default_rng(21)
+    vel = None
+    runs = [(0, None)] + [(1, t) for t in FUSED_TILINGS]
+    ref = None
+    for variant, tiling in runs:
+        gpu = Solver(cfg)
+        gpu.set_tuning("cg_variant", variant)
+        if tiling:
+            gpu.set_tuning("fused_stages", tiling[2])
+            gpu.set_tuning("fused_zc", 8)
+            gpu.set_tuning("fused_tx", tiling[0])
+            gpu.set_tuning("fused_ty", tiling[1])
+        if vel is None:
+            vel = smooth_velocity(gpu, rng, amp=1.0)
+            for f, a in vel.items():
+                ora.set(f, a)
+            ora.add_inputs()
+            ora.build_rhs()
+            io, ro = ora.pcg_solve()
+            ref = (io, ro, ora.get(K.PRESSURE), ora.residual_history())
+        for f, a in vel.items():
+            gpu.set(f, a)
+        gpu.add_inputs()
+        gpu.build_rhs()
+        ig, rg = gpu.pcg_solve()
+        assert ig == ref[0], (variant, tiling, ig, ref[0])
+        assert rg == ref[1], (variant, tiling)
+        assert np.array_equal(gpu.get(K.PRESSURE), ref[2]), (variant, tiling)
+        assert np.array_equal(gpu.residual_history(), ref[3]), (variant, tiling)
+        # the vectors the next iteration would use are the same too
+        if variant == 0:
+            keep = {f: gpu.get(f) for f in (K.CG_R,)}
+        else:
+            assert np.array_equal(gpu.get(K.CG_R), keep[K.CG_R]), (variant, tiling)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_cg_fixed_iterations_both_forms(variant):
+    cells = (48, 40, 36)
+    cfg = make_cfg(3, cells, box=box_for(cells), fixed_iters=17)
+    gpu, ora = pair(cfg)
+    gpu.set_tuning("cg_variant", variant)
+    rng = np.random.default_rng(8)
+    b = random_cells(gpu, rng, K.RHS)
+    b -= b.mean()
+    set_both(gpu, ora, K.RHS, b)
+    ig, rg = gpu.pcg_solve()
+    io, ro = ora.pcg_solve()
+    assert ig == io == 17 and rg == ro
+    for f in (K.PRESSURE, K.CG_R, K.CG_P, K.CG_Q):
+        assert np.array_equal(gpu.get(f), ora.get(f)), f
+
+
 def test_pcg_zero_rhs_returns_immediately():
     cfg = make_cfg(3, 16)
     gpu = Solver(cfg)

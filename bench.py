@@ -396,7 +396,11 @@ def main():
                            "cells_per_gpu": [args.cells] * 3 if args.scaling == "weak" else None,
                            "global_cells": list(gcells), "blocks": list(blocks), "cg_iters_per_step": args.iters,
                            "l2": "inputs larger than L2 (each vector %.2f GB)" % (ncell_local * 8 / 1e9),
-                           "timing": "CUDA events on the launching stream around each solve, max over ranks"},
+                           "timing": "CUDA events on the launching stream around each solve, max over ranks",
+                           "cg_form": "two kernels, 72 B/cell" if args.cg_variant == 1 else "three kernels, 88 B/cell",
+                           "exchange": ("none (1 GPU)" if world == 1 else
+                                        "NVLink peer stores (cudaIpc), ghosts + CG sums in one kernel per reduction point"
+                                        if st["peer_mode"] else "NCCL send/recv + all-gather")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "extra": extra}
         print(json.dumps(line), flush=True)

@@ -69,6 +69,7 @@ class Stats(C.Structure):
         ("ms_k_pupdate", C.c_double),
         ("ms_k_stencil", C.c_double),
         ("k_timed_iters", C.c_int64),
+        ("peer_mode", C.c_int64),
     ]
 
 

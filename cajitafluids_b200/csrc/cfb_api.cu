@@ -149,12 +149,22 @@ int enqueue_iteration( cfb_ctx* c )
         if ( e )
             cudaEventRecord( e[0], c->stream );
         n += launch_cg_rupdate( c );
+        const bool peer = c->cfg.use_nccl && c->peer_ok && c->use_peer;
+        if ( peer )
+            peer_exchange( c, 1, true, -1 ); // r ghosts -> neighbours, (rz_new, rr) -> everybody
+        else if ( c->cfg.use_nccl )
+            cg_global_sum( c, 1 );
         if ( e )
         {
             cudaEventRecord( e[1], c->stream );
             cudaEventRecord( e[2], c->stream );
         }
-        if ( c->cfg.use_nccl )
+        if ( peer )
+        {
+            n += launch_cg_fused( c, 0 );
+            peer_exchange( c, 0, false, c->pcur ^ 1 ); // new p ghosts -> neighbours, pAp -> everybody
+        }
+        else if ( c->cfg.use_nccl )
         {
             double* fl[2] = { c->cg_r, c->cg_p };
             if ( c->overlap_halo && c->n_interior > 0 )
@@ -268,6 +278,8 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
         return rc;
     collect_kernel_times( c );
     c->stats.kernel_launches += launches;
+    if ( c->h_state->xerror )
+        return cfb_fail( c, CFB_ERR_NCCL, "peer-memory exchange timed out: a rank never published its CG sums" );
     c->last_iters = c->h_state->iter;
     c->last_resid = std::sqrt( c->h_state->rr );
     if ( c->cg_variant == 1 )
@@ -835,6 +847,7 @@ int cfb_get_stats( const cfb_ctx* c, cfb_stats* out )
     for ( int s = 0; s < PH_COUNT; ++s )
         timer_collect( m, s );
     *out = c->stats;
+    out->peer_mode = ( c->cfg.use_nccl && c->peer_ok && c->use_peer && c->cg_variant == 1 ) ? 1 : 0;
     return CFB_OK;
 }
 int cfb_reset_stats( cfb_ctx* c )
@@ -901,6 +914,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->ru_ctas = value;
     else if ( k == "overlap_halo" )
         c->overlap_halo = value != 0;
+    else if ( k == "peer_halo" )
+        c->use_peer = value != 0;
     else if ( k == "time_kernels" )
     {
         c->time_kernels = value != 0;

@@ -63,6 +63,9 @@ struct CgState
     double bnorm;                   // sqrt(rr) of r0
     double thresh;                  // absolute threshold in use
     double alpha;                   // two-kernel form: alpha of the running iteration (phase A -> B)
+    unsigned long long seq[2];      // peer-memory exchange: publications so far of (pAp | rz_new, rr)
+    int xerror;                     // sticky: a peer never published (timeout)
+    int pad1;
     int iter;                       // completed iterations (kernel-1 executions)
     int done;                       // 1 once sqrt(rr) <= thresh
     int fixed;                      // fixed-iteration mode: never set done
@@ -74,6 +77,15 @@ struct CgState
 struct InflowConst
 {
     double lo[3], hi[3], vel[3], quantity, force_dt[3];
+};
+
+// Mailbox of one rank for the peer-memory reductions: slot [which][writer rank], written by the
+// writer over NVLink (data, system fence, then the sequence number), read locally.
+#define CFB_MAX_PEERS 16
+struct PeerMail
+{
+    double v[2][CFB_MAX_PEERS][4];
+    unsigned long long seq[2][CFB_MAX_PEERS];
 };
 
 #define CFB_MAX_PARTIALS 4096
@@ -121,7 +133,9 @@ struct cfb_ctx
     int* d_units = nullptr; // (tile_x, tile_y, chunk) triples: interior units first, then boundary
     int n_units = 0, n_interior = 0;
     int ru_ctas = 3;          // phase A: CTAs per SM of the grid-stride launch
-    bool overlap_halo = true; // multi-GPU: interior units run while the r/p ghosts are in flight
+    // NCCL path: run interior units while the r/p ghosts are in flight (measured slower than
+    // halo-first at 512^3 per GPU, profiles/r1_bench_n8_*: off by default)
+    bool overlap_halo = false;
 
     // stats
     cudaEvent_t ev[16] = { nullptr };
@@ -140,6 +154,20 @@ struct cfb_ctx
     double* d_halo_recv[6] = { nullptr };
     size_t halo_buf_elems = 0;
     int nbr[6] = { -1, -1, -1, -1, -1, -1 }; // neighbour ranks: [2*d] low, [2*d+1] high
+
+    // NVLink peer memory (cudaIpc): the neighbours' cg_r / cg_pbuf arrays and every rank's mailbox are
+    // mapped into this process, so the per-iteration ghost exchange and the CG reductions are plain
+    // stores into peer HBM from one kernel (halo.cu: cg_xchg_kernel) — no pack/unpack, no NCCL call.
+    bool peer_ok = false;  // mappings established
+    bool use_peer = true;  // use them for the CG iterations ("peer_halo" tuning key)
+    double* peer_r[6] = { nullptr };
+    double* peer_p[2][6] = { { nullptr } };
+    long long peer_origin[6] = { 0 }, peer_sy[6] = { 0 }, peer_sz[6] = { 0 };
+    int peer_n[6][3] = { { 0 } };
+    PeerMail* mail_self = nullptr;
+    PeerMail* mail[CFB_MAX_PEERS] = { nullptr };
+    unsigned int* d_xticket = nullptr;
+    std::vector<void*> ipc_opened;
 };
 
 extern std::string g_cfb_error;
@@ -216,6 +244,10 @@ int halo_exchange_cells( cfb_ctx* c, double* field, int width ); // face-neighbo
 // stream) / end (join), so that work not reading ghosts can be launched in between
 int halo_cells_begin( cfb_ctx* c, double* const* fields, int nf, int width );
 int halo_cells_end( cfb_ctx* c );
+// peer-memory exchange of the two-kernel iteration: store my boundary layers of the given cell arrays
+// (0: cg_r, 1: the p buffer `pbuf`) into the neighbours' ghost layers, publish my local double-double
+// sums (which = 0: pAp, 1: rz_new and rr) to every rank, wait for theirs, combine exactly
+int peer_exchange( cfb_ctx* c, int which, bool push_r, int pbuf );
 int halo_exchange_fields( cfb_ctx* c, int version );             // width-h exchange of q,u,v,w
 int halo_allreduce( cfb_ctx* c, double* dev_vals, int n );
 int halo_allgather( cfb_ctx* c, const double* dev_send, double* dev_recv, int n_per_rank );

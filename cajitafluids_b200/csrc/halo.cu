@@ -17,8 +17,10 @@
 // traffic (side stream) and scalar reductions (main stream) never share a communicator.
 #include "cfb_internal.h"
 #include "device_geo.cuh"
+#include "device_reduce.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -217,6 +219,307 @@ int exchange( cfb_ctx* c, int nf, double* const fld[4], int ndims, const int dim
     return CFB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// NVLink peer-memory path (one kernel per reduction point of the CG iteration).
+//
+//   1. every block copies a share of my boundary layers straight into the neighbours' ghost layers
+//      (their arrays are mapped here through cudaIpc; the stores travel over NVLink / NVSwitch);
+//   2. all threads fence at system scope, the block draws a ticket; the block that draws the last one
+//   3. publishes my local double-double sums and then the sequence number into every rank's mailbox,
+//   4. waits until every rank's sequence number has arrived in MY mailbox (bounded spin), and
+//   5. combines the W double-doubles in rank order: the global value is the correctly rounded exact
+//      sum on every rank, bit for bit the same (see device_reduce.cuh).
+//
+// The two publications per iteration double as the barriers that make the ghost stores safe: a rank
+// enters phase B only after every rank has finished phase A and its ghost stores (and vice versa), and
+// p is double-buffered, so no ghost layer is overwritten while a neighbour may still read it.
+struct XFace
+{
+    const double* src;
+    double* dst;
+    long long dorigin, dsy, dsz;
+    int lo[3], ext[3], shift[3]; // my box (owned index space), peer index = my index - shift
+};
+
+struct XchgArgs
+{
+    int nface;
+    XFace f[12];
+    CgState* S;
+    PeerMail* mail[CFB_MAX_PEERS];
+    unsigned int* ticket;
+    int which, rank, world;
+    long long timeout_cycles;
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64( const unsigned long long* p )
+{
+    unsigned long long v;
+    asm volatile( "ld.volatile.global.u64 %0, [%1];" : "=l"( v ) : "l"( p ) : "memory" );
+    return v;
+}
+
+__global__ void __launch_bounds__( 256 )
+    cg_xchg_kernel( const __grid_constant__ Geo g, const __grid_constant__ XchgArgs a )
+{
+    // 1. ghost stores into the neighbours
+    for ( int fi = 0; fi < a.nface; ++fi )
+    {
+        const XFace& f = a.f[fi];
+        const long long total = (long long)f.ext[0] * f.ext[1] * f.ext[2];
+        for ( long long t = blockIdx.x * 256ll + threadIdx.x; t < total; t += (long long)gridDim.x * 256 )
+        {
+            const int i = (int)( t % f.ext[0] ) + f.lo[0];
+            const int j = (int)( ( t / f.ext[0] ) % f.ext[1] ) + f.lo[1];
+            const int k = (int)( t / ( (long long)f.ext[0] * f.ext[1] ) ) + f.lo[2];
+            const double v = f.src[geo_off( g, i, j, k )];
+            f.dst[f.dorigin + (long long)( k - f.shift[2] ) * f.dsz + (long long)( j - f.shift[1] ) * f.dsy +
+                  ( i - f.shift[0] )] = v;
+        }
+    }
+    // 2. my stores are performed system-wide before the ticket is drawn
+    __threadfence_system();
+    __shared__ bool s_last;
+    __syncthreads();
+    if ( threadIdx.x == 0 )
+    {
+        const unsigned t = atomicAdd( a.ticket, 1u );
+        s_last = ( t == gridDim.x - 1 );
+    }
+    __syncthreads();
+    if ( !s_last )
+        return;
+    __threadfence_system();
+
+    CgState* S = a.S;
+    __shared__ unsigned long long s_seq;
+    if ( threadIdx.x == 0 )
+    {
+        *a.ticket = 0u;
+        s_seq = ++S->seq[a.which];
+    }
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    const int nd = a.which == 0 ? 2 : 4; // doubles published
+    const double* loc = &S->loc[a.which == 0 ? 0 : 2];
+    // 3. publish: data, fence, sequence number (one thread per destination rank)
+    if ( threadIdx.x < a.world )
+    {
+        PeerMail* m = a.mail[threadIdx.x];
+        for ( int q = 0; q < nd; ++q )
+            m->v[a.which][a.rank][q] = loc[q];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>( &m->seq[a.which][a.rank] ) = seq;
+    }
+    // 4. wait for every rank's publication in my mailbox
+    PeerMail* me = a.mail[a.rank];
+    if ( threadIdx.x < a.world && !S->xerror )
+    {
+        const long long t0 = clock64();
+        while ( ld_volatile_u64( &me->seq[a.which][threadIdx.x] ) < seq )
+        {
+            if ( clock64() - t0 > a.timeout_cycles )
+            {
+                S->xerror = 1;
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 5. exact combination in rank order
+    if ( threadIdx.x == 0 )
+    {
+        dd_t acc[2] = { { 0.0, 0.0 }, { 0.0, 0.0 } };
+        const int nv = nd / 2;
+        for ( int r = 0; r < a.world; ++r )
+            for ( int v = 0; v < nv; ++v )
+            {
+                const volatile double* src = &me->v[a.which][r][2 * v];
+                dd_t w = { src[0], src[1] };
+                acc[v] = dd_add( acc[v], w );
+            }
+        if ( a.which == 0 )
+            S->pAp = acc[0].hi + acc[0].lo;
+        else
+        {
+            S->rz_new = acc[0].hi + acc[0].lo;
+            S->rr = acc[1].hi + acc[1].lo;
+        }
+    }
+}
+
+// what every rank tells the others at start-up
+struct PeerInfo
+{
+    cudaIpcMemHandle_t h_r, h_p0, h_p1, h_mail;
+    long long origin, sy, sz;
+    int n[3];
+    int device;
+    int ok;
+};
+
+int peer_setup( cfb_ctx* c )
+{
+    Comm* cm = static_cast<Comm*>( c->nccl );
+    const int W = c->cfg.world_size, me = c->cfg.world_rank;
+    c->peer_ok = false;
+    if ( W > CFB_MAX_PEERS )
+        return CFB_OK;
+    const char* env = std::getenv( "CFB_PEER" );
+    if ( env && env[0] == '0' )
+        return CFB_OK;
+    CFB_CUDA( c, cudaMalloc( &c->mail_self, sizeof( PeerMail ) ) );
+    CFB_CUDA( c, cudaMemset( c->mail_self, 0, sizeof( PeerMail ) ) );
+    CFB_CUDA( c, cudaMalloc( &c->d_xticket, sizeof( unsigned int ) ) );
+    CFB_CUDA( c, cudaMemset( c->d_xticket, 0, sizeof( unsigned int ) ) );
+    PeerInfo mine{};
+    mine.ok = 1;
+    if ( cudaIpcGetMemHandle( &mine.h_r, c->cg_r ) != cudaSuccess ||
+         cudaIpcGetMemHandle( &mine.h_p0, c->cg_pbuf[0] ) != cudaSuccess ||
+         cudaIpcGetMemHandle( &mine.h_p1, c->cg_pbuf[1] ) != cudaSuccess ||
+         cudaIpcGetMemHandle( &mine.h_mail, c->mail_self ) != cudaSuccess )
+    {
+        cudaGetLastError();
+        mine.ok = 0;
+    }
+    mine.origin = c->g.origin;
+    mine.sy = c->g.sy;
+    mine.sz = c->g.sz;
+    for ( int d = 0; d < 3; ++d )
+        mine.n[d] = c->g.n[d];
+    mine.device = c->device;
+    // all-gather the PeerInfo records through NCCL (bytes)
+    PeerInfo* d_all = nullptr;
+    CFB_CUDA( c, cudaMalloc( &d_all, sizeof( PeerInfo ) * ( W + 1 ) ) );
+    CFB_CUDA( c, cudaMemcpy( d_all + W, &mine, sizeof( PeerInfo ), cudaMemcpyHostToDevice ) );
+    CFB_NCCL( c, g_nccl.AllGather( d_all + W, d_all, sizeof( PeerInfo ), ncclChar, cm->red, c->stream ) );
+    CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    std::vector<PeerInfo> all( W );
+    CFB_CUDA( c, cudaMemcpy( all.data(), d_all, sizeof( PeerInfo ) * W, cudaMemcpyDeviceToHost ) );
+    cudaFree( d_all );
+    bool ok = true;
+    for ( int r = 0; r < W; ++r )
+        ok = ok && all[r].ok;
+    auto open = [&]( const cudaIpcMemHandle_t& h, void** out ) -> bool {
+        if ( cudaIpcOpenMemHandle( out, h, cudaIpcMemLazyEnablePeerAccess ) != cudaSuccess )
+        {
+            cudaGetLastError();
+            return false;
+        }
+        c->ipc_opened.push_back( *out );
+        return true;
+    };
+    if ( ok )
+    {
+        for ( int r = 0; r < W && ok; ++r )
+        {
+            if ( r == me )
+                c->mail[r] = c->mail_self;
+            else
+                ok = open( all[r].h_mail, reinterpret_cast<void**>( &c->mail[r] ) );
+        }
+        // a neighbour may appear on several faces (periodic-free block grids: it does not); map once
+        for ( int s = 0; s < 6 && ok; ++s )
+        {
+            const int r = c->nbr[s];
+            if ( r < 0 )
+                continue;
+            ok = open( all[r].h_r, reinterpret_cast<void**>( &c->peer_r[s] ) ) &&
+                 open( all[r].h_p0, reinterpret_cast<void**>( &c->peer_p[0][s] ) ) &&
+                 open( all[r].h_p1, reinterpret_cast<void**>( &c->peer_p[1][s] ) );
+            c->peer_origin[s] = all[r].origin;
+            c->peer_sy[s] = all[r].sy;
+            c->peer_sz[s] = all[r].sz;
+            for ( int d = 0; d < 3; ++d )
+                c->peer_n[s][d] = all[r].n[d];
+        }
+    }
+    // everybody or nobody: agree on the outcome (sum of failures over ranks)
+    double flag = ok ? 0.0 : 1.0, *d_flag = nullptr;
+    CFB_CUDA( c, cudaMalloc( &d_flag, sizeof( double ) ) );
+    CFB_CUDA( c, cudaMemcpy( d_flag, &flag, sizeof( double ), cudaMemcpyHostToDevice ) );
+    CFB_NCCL( c, g_nccl.AllReduce( d_flag, d_flag, 1, ncclDouble, ncclSum, cm->red, c->stream ) );
+    CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    CFB_CUDA( c, cudaMemcpy( &flag, d_flag, sizeof( double ), cudaMemcpyDeviceToHost ) );
+    cudaFree( d_flag );
+    c->peer_ok = flag == 0.0;
+    return CFB_OK;
+}
+
+void peer_destroy( cfb_ctx* c )
+{
+    for ( void* p : c->ipc_opened )
+        cudaIpcCloseMemHandle( p );
+    c->ipc_opened.clear();
+    if ( c->mail_self )
+        cudaFree( c->mail_self );
+    if ( c->d_xticket )
+        cudaFree( c->d_xticket );
+    c->mail_self = nullptr;
+    c->d_xticket = nullptr;
+    c->peer_ok = false;
+}
+
+} // namespace
+
+int peer_exchange( cfb_ctx* c, int which, bool push_r, int pbuf )
+{
+    const Geo& g = c->g;
+    XchgArgs a{};
+    a.S = c->d_state;
+    a.ticket = c->d_xticket;
+    a.which = which;
+    a.rank = c->cfg.world_rank;
+    a.world = c->cfg.world_size;
+    a.timeout_cycles = 4000000000ll; // ~2 s at 1.9 GHz: a dead peer must not hang the GPU
+    for ( int r = 0; r < a.world; ++r )
+        a.mail[r] = c->mail[r];
+    long long cells = 0;
+    for ( int s = 0; s < 2 * g.D; ++s )
+    {
+        if ( c->nbr[s] < 0 )
+            continue;
+        const int d = s / 2, side = s % 2;
+        for ( int fld = 0; fld < 2; ++fld )
+        {
+            if ( ( fld == 0 && !push_r ) || ( fld == 1 && pbuf < 0 ) )
+                continue;
+            XFace& f = a.f[a.nface++];
+            f.src = fld == 0 ? c->cg_r : c->cg_pbuf[pbuf];
+            f.dst = fld == 0 ? c->peer_r[s] : c->peer_p[pbuf][s];
+            f.dorigin = c->peer_origin[s];
+            f.dsy = c->peer_sy[s];
+            f.dsz = c->peer_sz[s];
+            for ( int e = 0; e < 3; ++e )
+            {
+                f.lo[e] = 0;
+                f.ext[e] = g.n[e];
+                f.shift[e] = 0;
+            }
+            f.ext[d] = 1;
+            if ( side == 0 )
+            {
+                f.lo[d] = 0; // my first layer -> the low neighbour's high ghost (index n_peer)
+                f.shift[d] = -c->peer_n[s][d];
+            }
+            else
+            {
+                f.lo[d] = g.n[d] - 1; // my last layer -> the high neighbour's low ghost (index -1)
+                f.shift[d] = g.n[d];
+            }
+            cells += (long long)f.ext[0] * f.ext[1] * f.ext[2];
+        }
+    }
+    int grid = (int)std::min<long long>( std::max<long long>( ( cells + 1023 ) / 1024, 1 ), 2ll * c->sm_count );
+    cg_xchg_kernel<<<grid, 256, 0, c->stream>>>( g, a );
+    c->stats.kernel_launches += 1;
+    return CFB_OK;
+}
+
+namespace
+{
 } // namespace
 
 extern "C" int cfb_nccl_unique_id( unsigned char* id )
@@ -289,11 +592,12 @@ int halo_init( cfb_ctx* c )
         return cfb_fail( c, CFB_ERR_INVALID, "at most 64 ranks" );
     CFB_CUDA( c, cudaMemcpyAsync( &c->d_state->world, &cfg.world_size, sizeof( int ), cudaMemcpyHostToDevice, c->stream ) );
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
-    return CFB_OK;
+    return peer_setup( c );
 }
 
 void halo_destroy( cfb_ctx* c )
 {
+    peer_destroy( c );
     Comm* cm = static_cast<Comm*>( c->nccl );
     if ( cm )
     {

@@ -702,8 +702,6 @@ int launch_cg_rupdate( cfb_ctx* c )
         grid = cap;
     cg_rupdate_kernel<<<(int)grid, NT, 0, c->stream>>>( g, c->op, c->cg_q, c->cg_r, c->d_state, c->d_partials,
                                                        txp_log2 );
-    if ( c->cfg.use_nccl )
-        cg_global_sum( c, 1 );
     return 1;
 }
 

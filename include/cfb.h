@@ -176,6 +176,9 @@ typedef struct cfb_stats
     double ms_k_pupdate;
     double ms_k_stencil;
     int64_t k_timed_iters;
+    /* multi-GPU: 1 = the CG iterations exchange ghosts and sums by direct stores into peer memory over
+     * NVLink (cudaIpc mappings), 0 = NCCL send/recv + all-gather (or single GPU) */
+    int64_t peer_mode;
 } cfb_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------ */

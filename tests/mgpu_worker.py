@@ -100,15 +100,23 @@ def main():
     ora.build_rhs()
     io, ro = ora.pcg_solve()
     po, ho = ora.get(K.PRESSURE), ora.residual_history()
-    modes = [("two-kernel, interior overlapped with the r/p halo", {"cg_variant": 1, "overlap_halo": 1}),
-             ("two-kernel, halo first", {"cg_variant": 1, "overlap_halo": 0}),
-             ("two-kernel, small tiles, several boundary units",
-              {"cg_variant": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
-             ("three-kernel", {"cg_variant": 0})]
+    modes = [("two-kernel, NVLink peer stores (default)", {"cg_variant": 1, "peer_halo": 1}),
+             ("two-kernel, NVLink peer stores, small tiles",
+              {"cg_variant": 1, "peer_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
+             ("two-kernel, NCCL, interior overlapped with the r/p halo",
+              {"cg_variant": 1, "peer_halo": 0, "overlap_halo": 1}),
+             ("two-kernel, NCCL, halo first", {"cg_variant": 1, "peer_halo": 0, "overlap_halo": 0}),
+             ("two-kernel, NCCL, small tiles, several boundary units",
+              {"cg_variant": 1, "peer_halo": 0, "overlap_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64,
+               "fused_ty": 8}),
+             ("three-kernel, NCCL", {"cg_variant": 0})]
     for name, tune in modes:
         gpu = Solver(rank_cfg())
         for k, v in tune.items():
             gpu.set_tuning(k, v)
+        if tune.get("peer_halo") == 1:
+            check(f"peer-memory mode active [{name}]", gpu.stats()["peer_mode"] == 1,
+                  "cudaIpc mapping of the neighbours' arrays failed: NCCL fallback in use")
         for f, a in vel.items():
             gpu.set(f, a[block_slices(gpu, f)])
         gpu.add_inputs()

@@ -910,6 +910,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->fu_stages = value;
     else if ( k == "fused_zc" )
         c->fu_zc = value;
+    else if ( k == "fused_reverse" )
+        c->fu_reverse = value != 0;
     else if ( k == "rupdate_ctas" )
         c->ru_ctas = value;
     else if ( k == "overlap_halo" )
@@ -935,7 +937,7 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->fu_auto = value != 0;
         return fused_setup( c );
     }
-    if ( k.rfind( "fused_", 0 ) == 0 )
+    if ( k.rfind( "fused_", 0 ) == 0 && k != "fused_reverse" )
         c->fu_auto = false;
     if ( k == "fused_tx" || k == "fused_ty" || k == "fused_zc" )
         return fused_setup( c );

@@ -132,6 +132,7 @@ struct cfb_ctx
     int fu_tx = 64, fu_ty = 16, fu_stages = 3, fu_zc = 64;
     int* d_units = nullptr; // (tile_x, tile_y, chunk) triples: interior units first, then boundary
     int n_units = 0, n_interior = 0;
+    bool fu_reverse = false;  // phase B walks the units top-down (L2 reuse between the phases)
     int ru_ctas = 3;          // phase A: CTAs per SM of the grid-stride launch
     // NCCL path: run interior units while the r/p ghosts are in flight (measured slower than
     // halo-first at 512^3 per GPU, profiles/r1_bench_n8_*: off by default)

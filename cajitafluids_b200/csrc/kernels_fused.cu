@@ -199,6 +199,7 @@ struct FusedArgs
     double* partials;
     const int* units; // optional unit list (tile_x, tile_y, chunk) triples; nullptr = all units in order
     int tiles_x, tiles_y, zc, hx;
+    int reverse;     // walk the units from the top of the block down (see launch_cg_fused)
     int unit_base;   // index of this launch's first unit in the partial-sum scratch
     int units_total; // units of all launches that make up one phase B (last-block ticket target)
 };
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     }
     else
     {
-        const int u = blockIdx.x;
+        const int u = a.reverse ? a.units_total - 1 - (int)blockIdx.x : (int)blockIdx.x;
         tx = u % a.tiles_x;
         ty = ( u / a.tiles_x ) % a.tiles_y;
         ch = u / ( a.tiles_x * a.tiles_y );
@@ -623,25 +624,32 @@ int fused_setup( cfb_ctx* c )
     const Geo& g = c->g;
     if ( c->fu_auto )
     {
-        // measured on B200 (profiles/r1_sweep_fused.log): 128x16 tiles, 3 stages, 64-plane chunks are
-        // the fastest from 256^3 up; smaller blocks need smaller tiles / chunks to fill 148 SMs
-        static const int cand[][4] = { { 128, 16, 3, 64 }, { 64, 16, 3, 32 }, { 64, 16, 3, 16 },
-                                       { 64, 8, 4, 16 },   { 64, 8, 4, 8 },   { 64, 8, 4, 4 } };
-        int pick = 5;
-        for ( int i = 0; i < 6; ++i )
+        // Rules distilled from the sweeps in profiles/r1_sweep_fused*.log (64^3 ... 512^3):
+        //  * 128x16 tiles (1 CTA/SM, 3 stages) win from 512 cells along x; below that 64x16 (2 CTAs/SM);
+        //  * 64-plane chunks, halved until there is at least one unit per SM (every chunk re-reads
+        //    two planes, so chunks stay as long as the SM count allows);
+        //  * blocks too small even for that take 64x8 tiles (3 CTAs/SM, 4 stages).
+        auto units_of = [&]( int tx, int ty, int zc ) {
+            return (long long)( ( g.n[0] + tx - 1 ) / tx ) * ( ( g.n[1] + ty - 1 ) / ty ) * ( ( g.n[2] + zc - 1 ) / zc );
+        };
+        int tx = ( g.n[0] >= 512 && g.n[1] >= 64 ) ? 128 : 64, ty = 16, st = 3, zc = 64;
+        while ( units_of( tx, ty, zc ) < c->sm_count && zc > 4 )
+            zc /= 2;
+        if ( units_of( tx, ty, zc ) < c->sm_count )
         {
-            const long long u = (long long)( ( g.n[0] + cand[i][0] - 1 ) / cand[i][0] ) *
-                                ( ( g.n[1] + cand[i][1] - 1 ) / cand[i][1] ) * ( ( g.n[2] + cand[i][3] - 1 ) / cand[i][3] );
-            if ( u >= 120 && u <= CFB_MAX_PARTIALS )
-            {
-                pick = i;
-                break;
-            }
+            tx = 64;
+            ty = 8;
+            st = 4;
+            zc = 64;
+            while ( units_of( tx, ty, zc ) < c->sm_count && zc > 4 )
+                zc /= 2;
         }
-        c->fu_tx = cand[pick][0];
-        c->fu_ty = cand[pick][1];
-        c->fu_stages = cand[pick][2];
-        c->fu_zc = cand[pick][3];
+        while ( units_of( tx, ty, zc ) > CFB_MAX_PARTIALS )
+            zc *= 2;
+        c->fu_tx = tx;
+        c->fu_ty = ty;
+        c->fu_stages = st;
+        c->fu_zc = zc;
     }
     cuuint64_t gdim[3] = { (cuuint64_t)g.sy, (cuuint64_t)g.ay, (cuuint64_t)g.az };
     cuuint64_t gstride[2] = { (cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8 };
@@ -727,6 +735,9 @@ int launch_cg_fused( cfb_ctx* c, int which )
     fused_tiling( c, a.tiles_x, a.tiles_y, a.zc, chunks );
     const int total = a.tiles_x * a.tiles_y * chunks;
     a.units_total = total;
+    // optional top-down walk (phase A sweeps bottom-up and leaves the top of r in the L2); measured
+    // neutral from 64^3 to 512^3 (profiles/r1_sweep_fused2.log), so it is off by default
+    a.reverse = c->fu_reverse ? 1 : 0;
     int grid = total;
     if ( which != 0 )
     {

@@ -24,8 +24,22 @@ for n in sizes:
     s.build_rhs()
     s.set_tuning("time_kernels", 1)
     cells = n ** 3
-    zcs = [32, 64] if n >= 256 else [16, 32]
+    zcs = [29, 37, 64] if n == 256 else ([32, 64] if n > 256 else [8, 10, 16])
     combos = [(0, 0, 0, 0, 0)]
+    # automatic tiling, with and without the top-down walk of phase B
+    for rev in (1, 0):
+        s.set_tuning("cg_variant", 1)
+        s.set_tuning("fused_auto", 1)
+        s.set_tuning("fused_reverse", rev)
+        s.pcg_fixed(5)
+        s.reset_stats()
+        ms, res = s.pcg_fixed(ITERS)
+        st_ = s.stats()
+        kt = max(1, st_["k_timed_iters"])
+        a, c = st_["ms_k_axpy"] / kt, st_["ms_k_stencil"] / kt
+        print(f"n={n} auto tiling reverse={rev}: {ms / ITERS * 1e3:8.1f} us/it {ITERS * 1e3 / ms:7.1f} it/s  "
+              f"iter {cells * 72 * ITERS / ms / 1e6:5.0f} GB/s ({cells * 72 * ITERS / ms / 1e6 / PEAK:.1%})  "
+              f"A {a * 1e3:7.1f} us  B {c * 1e3:7.1f} us  resid {res:.6e}", flush=True)
     # phase A occupancy sweep at the automatic phase-B tiling
     for ctas in (2, 3, 4, 6):
         s.set_tuning("cg_variant", 1)
@@ -39,7 +53,7 @@ for n in sizes:
         print(f"n={n} phase A ctas/SM={ctas}: {a * 1e3:7.1f} us -> {cells * 24 / a / 1e6:5.0f} GB/s "
               f"({cells * 24 / a / 1e6 / PEAK:.1%})   iteration {ms / ITERS * 1e3:8.1f} us", flush=True)
     s.set_tuning("rupdate_ctas", 3)
-    for tx, ty, st in [(64, 16, 3), (64, 32, 3), (128, 8, 3), (128, 16, 3)]:
+    for tx, ty, st in [(64, 16, 3), (64, 8, 4), (128, 16, 3)]:
         for zc in zcs:
             combos.append((1, tx, ty, st, zc))
     for var, tx, ty, st, zc in combos:

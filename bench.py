@@ -206,12 +206,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-timestep", action="store_true")
+    ap.add_argument("--blocks", type=int, nargs=3, default=None, help="block grid bx by bz (default: split z, y, x)")
     ap.add_argument("--timestep-cells", type=int, default=128, help="grid of the extra full-timestep measurement")
     ap.add_argument("--cg-variant", type=int, default=1, choices=[0, 1], help="1 = two-kernel iteration (72 B/cell)")
     ap.add_argument("--tune", action="append", default=[], help="key=value passed to cfb_set_tuning")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+
+    # stdout carries exactly ONE JSON line: everything else that libraries print there (NCCL's version
+    # banner, torch warnings) is sent to stderr at file-descriptor level
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -227,7 +234,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    blocks = block_grid(world)
+    blocks = tuple(args.blocks) if args.blocks else block_grid(world)
+    assert blocks[0] * blocks[1] * blocks[2] == world, "--blocks must multiply to --gpus"
     cfg, gcells = make_config(args, rank, world, blocks)
     cfg.device_id = local
     if world > 1:
@@ -403,7 +411,8 @@ def main():
                                         if st["peer_mode"] else "NCCL send/recv + all-gather")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "extra": extra}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 

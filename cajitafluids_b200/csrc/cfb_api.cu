@@ -149,9 +149,9 @@ int enqueue_iteration( cfb_ctx* c )
         if ( e )
             cudaEventRecord( e[0], c->stream );
         n += launch_cg_rupdate( c );
-        const bool peer = c->cfg.use_nccl && c->peer_ok && c->use_peer;
+        const bool peer = cg_peer_mode( c );
         if ( peer )
-            peer_exchange( c, 1, true, -1 ); // r ghosts -> neighbours, (rz_new, rr) -> everybody
+            peer_exchange( c, 1, true, -1, !peer_xstaged( c ) ); // r faces -> neighbours, (rz_new, rr) -> all
         else if ( c->cfg.use_nccl )
             cg_global_sum( c, 1 );
         if ( e )
@@ -162,7 +162,7 @@ int enqueue_iteration( cfb_ctx* c )
         if ( peer )
         {
             n += launch_cg_fused( c, 0 );
-            peer_exchange( c, 0, false, c->pcur ^ 1 ); // new p ghosts -> neighbours, pAp -> everybody
+            peer_exchange( c, 0, false, c->pcur ^ 1, !peer_xstaged( c ) ); // new p faces, pAp -> all
         }
         else if ( c->cfg.use_nccl )
         {
@@ -232,11 +232,14 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     const int max_it = fixed ? fixed_iters : c->cfg.cg_max_iter;
     long long launches = 0;
     const int p_start = c->pcur;
-    launches += launch_cg_init( c, fixed );
-    if ( c->cfg.use_nccl )
+    const bool peer = cg_peer_mode( c );
+    launches += launch_cg_init( c, fixed ); // peer mode: includes the exchange of p0's faces
+    if ( c->cfg.use_nccl && !peer )
         halo_exchange_cells( c, c->cg_p, 1 );
     launches += launch_stencil_dot( c );
-    if ( c->cfg.use_nccl )
+    if ( peer )
+        peer_exchange( c, 0, false, -1, false );
+    else if ( c->cfg.use_nccl )
         cg_global_sum( c, 0 );
 
     const int batch = poll_batch( c );
@@ -847,7 +850,7 @@ int cfb_get_stats( const cfb_ctx* c, cfb_stats* out )
     for ( int s = 0; s < PH_COUNT; ++s )
         timer_collect( m, s );
     *out = c->stats;
-    out->peer_mode = ( c->cfg.use_nccl && c->peer_ok && c->use_peer && c->cg_variant == 1 ) ? 1 : 0;
+    out->peer_mode = cg_peer_mode( c ) ? 1 : 0;
     return CFB_OK;
 }
 int cfb_reset_stats( cfb_ctx* c )
@@ -918,6 +921,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->overlap_halo = value != 0;
     else if ( k == "peer_halo" )
         c->use_peer = value != 0;
+    else if ( k == "peer_xstage" )
+        c->peer_xstage_reads = value != 0;
     else if ( k == "time_kernels" )
     {
         c->time_kernels = value != 0;

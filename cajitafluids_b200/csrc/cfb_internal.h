@@ -165,6 +165,15 @@ struct cfb_ctx
     double* peer_p[2][6] = { { nullptr } };
     long long peer_origin[6] = { 0 }, peer_sy[6] = { 0 }, peer_sz[6] = { 0 };
     int peer_n[6][3] = { { 0 } };
+    // x faces are strided in memory: they travel packed (contiguous NVLink stores) into the neighbour's
+    // staging area [side][0: r, 1: pbuf 0, 2: pbuf 1][nz * ny] and are scattered into the ghost column
+    // by the receiver (an experiment that let phases A / B store their faces themselves and read the x
+    // ghosts from staging was bit-exact but ~7 % slower: branch exp/peer-inkernel)
+    double* xstage_self = nullptr;
+    // "peer_xstage" tuning key; measured slower than scattering into the ghost columns (x split of 2 x
+    // 512^3: 539 vs 581 it/s): the halo warp waits for the global loads plane by plane
+    bool peer_xstage_reads = false;
+    double* peer_xstage[2] = { nullptr, nullptr };
     PeerMail* mail_self = nullptr;
     PeerMail* mail[CFB_MAX_PEERS] = { nullptr };
     unsigned int* d_xticket = nullptr;
@@ -227,6 +236,17 @@ int launch_fill_synthetic( cfb_ctx* c, int variant, uint64_t seed );
 // kernels_cg.cu
 int launch_divergence( cfb_ctx* c );          // rhs = -div/h ; lhs = 0
 int launch_cg_init( cfb_ctx* c, int fixed );  // x=0, r=b, p=Minv r, rr, rz ; + check kernel
+inline bool cg_peer_mode( const cfb_ctx* c )
+{
+    return c->cfg.use_nccl && c->peer_ok && c->use_peer && c->cg_variant == 1;
+}
+// peer mode with x neighbours and tiles that end exactly on the block: phase B reads its x ghosts
+// straight from the staging areas, so the iterations never scatter them into the ghost columns
+inline bool peer_xstaged( const cfb_ctx* c )
+{
+    return cg_peer_mode( c ) && c->peer_xstage_reads && ( c->nbr[0] >= 0 || c->nbr[1] >= 0 ) &&
+           c->g.n[0] % c->fu_tx == 0;
+}
 int launch_cg_axpy( cfb_ctx* c );             // kernel 1 (+ fused kernel-2 reduction)
 int launch_cg_pupdate( cfb_ctx* c );          // convergence bookkeeping + kernel 3
 // kernels_stencil.cu
@@ -248,7 +268,10 @@ int halo_cells_end( cfb_ctx* c );
 // peer-memory exchange of the two-kernel iteration: store my boundary layers of the given cell arrays
 // (0: cg_r, 1: the p buffer `pbuf`) into the neighbours' ghost layers, publish my local double-double
 // sums (which = 0: pAp, 1: rz_new and rr) to every rank, wait for theirs, combine exactly
-int peer_exchange( cfb_ctx* c, int which, bool push_r, int pbuf );
+// (copy_r / copy_pbuf >= 0: which arrays' faces travel: r, and / or that p buffer; unpack: scatter the
+// received x faces from the staging area into the ghost columns — not needed when phase B reads them
+// from staging, always needed for the plain stencil at the start of a solve)
+int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpack );
 int halo_exchange_fields( cfb_ctx* c, int version );             // width-h exchange of q,u,v,w
 int halo_allreduce( cfb_ctx* c, double* dev_vals, int n );
 int halo_allgather( cfb_ctx* c, const double* dev_send, double* dev_recv, int n_per_rank );

@@ -240,6 +240,7 @@ struct XFace
     double* dst;
     long long dorigin, dsy, dsz;
     int lo[3], ext[3], shift[3]; // my box (owned index space), peer index = my index - shift
+    int packed;                  // 1: dst is a dense staging area, element t of the box goes to dst[t]
 };
 
 struct XchgArgs
@@ -274,8 +275,11 @@ __global__ void __launch_bounds__( 256 )
             const int j = (int)( ( t / f.ext[0] ) % f.ext[1] ) + f.lo[1];
             const int k = (int)( t / ( (long long)f.ext[0] * f.ext[1] ) ) + f.lo[2];
             const double v = f.src[geo_off( g, i, j, k )];
-            f.dst[f.dorigin + (long long)( k - f.shift[2] ) * f.dsz + (long long)( j - f.shift[1] ) * f.dsy +
-                  ( i - f.shift[0] )] = v;
+            if ( f.packed )
+                f.dst[t] = v;
+            else
+                f.dst[f.dorigin + (long long)( k - f.shift[2] ) * f.dsz + (long long)( j - f.shift[1] ) * f.dsy +
+                      ( i - f.shift[0] )] = v;
         }
     }
     // 2. my stores are performed system-wide before the ticket is drawn
@@ -350,10 +354,32 @@ __global__ void __launch_bounds__( 256 )
     }
 }
 
+// staging area -> ghost columns i = -1 / i = n[0] of up to 4 (side, array) pairs
+struct XUnpackArgs
+{
+    int n;
+    const double* src[4];
+    double* dst[4];
+    int col[4];
+};
+
+__global__ void __launch_bounds__( 256 )
+    cg_xunpack_kernel( const __grid_constant__ Geo g, const __grid_constant__ XUnpackArgs a )
+{
+    const long long per = (long long)g.n[1] * g.n[2];
+    for ( long long t = blockIdx.x * 256ll + threadIdx.x; t < per * a.n; t += (long long)gridDim.x * 256 )
+    {
+        const int q = (int)( t / per );
+        const long long e = t - q * per;
+        const int j = (int)( e % g.n[1] ), k = (int)( e / g.n[1] );
+        a.dst[q][geo_off( g, a.col[q], j, k )] = a.src[q][e];
+    }
+}
+
 // what every rank tells the others at start-up
 struct PeerInfo
 {
-    cudaIpcMemHandle_t h_r, h_p0, h_p1, h_mail;
+    cudaIpcMemHandle_t h_r, h_p0, h_p1, h_mail, h_xstage;
     long long origin, sy, sz;
     int n[3];
     int device;
@@ -374,9 +400,13 @@ int peer_setup( cfb_ctx* c )
     CFB_CUDA( c, cudaMemset( c->mail_self, 0, sizeof( PeerMail ) ) );
     CFB_CUDA( c, cudaMalloc( &c->d_xticket, sizeof( unsigned int ) ) );
     CFB_CUDA( c, cudaMemset( c->d_xticket, 0, sizeof( unsigned int ) ) );
+    const size_t xstage_elems = (size_t)4 * c->g.n[1] * c->g.n[2];
+    CFB_CUDA( c, cudaMalloc( &c->xstage_self, xstage_elems * sizeof( double ) ) );
+    CFB_CUDA( c, cudaMemset( c->xstage_self, 0, xstage_elems * sizeof( double ) ) );
     PeerInfo mine{};
     mine.ok = 1;
-    if ( cudaIpcGetMemHandle( &mine.h_r, c->cg_r ) != cudaSuccess ||
+    if ( cudaIpcGetMemHandle( &mine.h_xstage, c->xstage_self ) != cudaSuccess ||
+         cudaIpcGetMemHandle( &mine.h_r, c->cg_r ) != cudaSuccess ||
          cudaIpcGetMemHandle( &mine.h_p0, c->cg_pbuf[0] ) != cudaSuccess ||
          cudaIpcGetMemHandle( &mine.h_p1, c->cg_pbuf[1] ) != cudaSuccess ||
          cudaIpcGetMemHandle( &mine.h_mail, c->mail_self ) != cudaSuccess )
@@ -426,7 +456,9 @@ int peer_setup( cfb_ctx* c )
             const int r = c->nbr[s];
             if ( r < 0 )
                 continue;
-            ok = open( all[r].h_r, reinterpret_cast<void**>( &c->peer_r[s] ) ) &&
+            if ( s < 2 )
+                ok = open( all[r].h_xstage, reinterpret_cast<void**>( &c->peer_xstage[s] ) );
+            ok = ok && open( all[r].h_r, reinterpret_cast<void**>( &c->peer_r[s] ) ) &&
                  open( all[r].h_p0, reinterpret_cast<void**>( &c->peer_p[0][s] ) ) &&
                  open( all[r].h_p1, reinterpret_cast<void**>( &c->peer_p[1][s] ) );
             c->peer_origin[s] = all[r].origin;
@@ -455,6 +487,9 @@ void peer_destroy( cfb_ctx* c )
     c->ipc_opened.clear();
     if ( c->mail_self )
         cudaFree( c->mail_self );
+    if ( c->xstage_self )
+        cudaFree( c->xstage_self );
+    c->xstage_self = nullptr;
     if ( c->d_xticket )
         cudaFree( c->d_xticket );
     c->mail_self = nullptr;
@@ -464,7 +499,13 @@ void peer_destroy( cfb_ctx* c )
 
 } // namespace
 
-int peer_exchange( cfb_ctx* c, int which, bool push_r, int pbuf )
+// staging slot of (side, kind) inside an xstage allocation; kind 0: r, 1: pbuf 0, 2: pbuf 1
+static inline size_t xslot( const Geo& g, int side, int kind )
+{
+    return (size_t)( side * 3 + kind ) * g.n[1] * g.n[2];
+}
+
+int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpack )
 {
     const Geo& g = c->g;
     XchgArgs a{};
@@ -477,6 +518,7 @@ int peer_exchange( cfb_ctx* c, int which, bool push_r, int pbuf )
     for ( int r = 0; r < a.world; ++r )
         a.mail[r] = c->mail[r];
     long long cells = 0;
+    XUnpackArgs u{};
     for ( int s = 0; s < 2 * g.D; ++s )
     {
         if ( c->nbr[s] < 0 )
@@ -484,11 +526,13 @@ int peer_exchange( cfb_ctx* c, int which, bool push_r, int pbuf )
         const int d = s / 2, side = s % 2;
         for ( int fld = 0; fld < 2; ++fld )
         {
-            if ( ( fld == 0 && !push_r ) || ( fld == 1 && pbuf < 0 ) )
+            if ( ( fld == 0 && !copy_r ) || ( fld == 1 && copy_pbuf < 0 ) )
                 continue;
+            const int kind = fld == 0 ? 0 : 1 + copy_pbuf;
+            double* mine = fld == 0 ? c->cg_r : c->cg_pbuf[copy_pbuf];
             XFace& f = a.f[a.nface++];
-            f.src = fld == 0 ? c->cg_r : c->cg_pbuf[pbuf];
-            f.dst = fld == 0 ? c->peer_r[s] : c->peer_p[pbuf][s];
+            f.src = mine;
+            f.dst = fld == 0 ? c->peer_r[s] : c->peer_p[copy_pbuf][s];
             f.dorigin = c->peer_origin[s];
             f.dsy = c->peer_sy[s];
             f.dsz = c->peer_sz[s];
@@ -509,12 +553,33 @@ int peer_exchange( cfb_ctx* c, int which, bool push_r, int pbuf )
                 f.lo[d] = g.n[d] - 1; // my last layer -> the high neighbour's low ghost (index -1)
                 f.shift[d] = g.n[d];
             }
+            if ( d == 0 )
+            {
+                // x faces travel packed into the neighbour's staging slot [its side facing me]; what the
+                // neighbour left in mine is scattered into my ghost column after the barrier
+                f.packed = 1;
+                f.dst = c->peer_xstage[s] + xslot( g, 1 - side, kind );
+                if ( unpack )
+                {
+                    u.src[u.n] = c->xstage_self + xslot( g, side, kind );
+                    u.dst[u.n] = mine;
+                    u.col[u.n] = side == 0 ? -1 : g.n[0];
+                    ++u.n;
+                }
+            }
             cells += (long long)f.ext[0] * f.ext[1] * f.ext[2];
         }
     }
     int grid = (int)std::min<long long>( std::max<long long>( ( cells + 1023 ) / 1024, 1 ), 2ll * c->sm_count );
     cg_xchg_kernel<<<grid, 256, 0, c->stream>>>( g, a );
     c->stats.kernel_launches += 1;
+    if ( u.n > 0 )
+    {
+        const long long tot = (long long)g.n[1] * g.n[2] * u.n;
+        const int ug = (int)std::min<long long>( ( tot + 255 ) / 256, 4ll * c->sm_count );
+        cg_xunpack_kernel<<<ug, 256, 0, c->stream>>>( g, u );
+        c->stats.kernel_launches += 1;
+    }
     return CFB_OK;
 }
 

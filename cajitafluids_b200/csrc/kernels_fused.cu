@@ -200,11 +200,15 @@ struct FusedArgs
     const int* units; // optional unit list (tile_x, tile_y, chunk) triples; nullptr = all units in order
     int tiles_x, tiles_y, zc, hx;
     int reverse;     // walk the units from the top of the block down (see launch_cg_fused)
+    // XS kernels (peer mode, x neighbours): the x ghosts of r and of the old p are read from the dense
+    // staging areas [k * ny + j] the x neighbours fill over NVLink, [0] low side, [1] high side
+    const double* gxr[2];
+    const double* gxp[2];
     int unit_base;   // index of this launch's first unit in the partial-sum scratch
     int units_total; // units of all launches that make up one phase B (last-block ticket target)
 };
 
-template <class C>
+template <class C, bool XS>
 __global__ void __launch_bounds__( C::NT, C::CTAS )
     cg_fused_kernel( const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_p,
                      const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
@@ -427,7 +431,18 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
                     const int gi = x0 + ( side ? TX : -1 ) + g.off[0];
                     const int cw = wall_count( g, 0, gi ) + wall_count( g, 1, y0 + row + g.off[1] ) + wz;
                     const int o = ( row + 1 ) * PX + col;
-                    PN[o] = fma( beta, P[o], op.minv[cw] * R[o] );
+                    double rv = R[o], pv = P[o];
+                    if ( XS )
+                    {
+                        const bool ghost = side ? ( x0 + TX == g.n[0] && a.gxr[1] ) : ( x0 == 0 && a.gxr[0] );
+                        if ( ghost && y0 + row < g.n[1] )
+                        {
+                            const size_t e = (size_t)( kbeg + l - 1 ) * g.n[1] + ( y0 + row );
+                            rv = a.gxr[side][e];
+                            pv = a.gxp[side][e];
+                        }
+                    }
+                    PN[o] = fma( beta, pv, op.minv[cw] * rv );
                 }
             }
             xrow += g.sz;
@@ -549,10 +564,16 @@ int launch_fused_cfg( cfb_ctx* c, const FusedArgs& a, int grid )
     static bool attr_set = false;
     if ( !attr_set )
     {
-        cudaFuncSetAttribute( cg_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
         attr_set = true;
     }
-    cg_fused_kernel<C><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur], c->g, c->op, a );
+    if ( a.gxr[0] || a.gxr[1] )
+        cg_fused_kernel<C, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur], c->g,
+                                                                            c->op, a );
+    else
+        cg_fused_kernel<C, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur], c->g,
+                                                                             c->op, a );
     return 1;
 }
 
@@ -738,6 +759,14 @@ int launch_cg_fused( cfb_ctx* c, int which )
     // optional top-down walk (phase A sweeps bottom-up and leaves the top of r in the L2); measured
     // neutral from 64^3 to 512^3 (profiles/r1_sweep_fused2.log), so it is off by default
     a.reverse = c->fu_reverse ? 1 : 0;
+    if ( peer_xstaged( c ) )
+        for ( int side = 0; side < 2; ++side )
+            if ( c->nbr[side] >= 0 )
+            {
+                const size_t slot = (size_t)c->g.n[1] * c->g.n[2];
+                a.gxr[side] = c->xstage_self + ( side * 3 + 0 ) * slot;
+                a.gxp[side] = c->xstage_self + ( side * 3 + 1 + c->pcur ) * slot;
+            }
     int grid = total;
     if ( which != 0 )
     {

@@ -37,12 +37,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cells", type=int, nargs=3, default=[48, 40, 36])
     ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--blocks", type=int, nargs=3, default=None, help="block grid (default: split z, y, x)")
+    ap.add_argument("--skip-steps", action="store_true", help="only the stencil / gather / PCG sections")
+    ap.add_argument("--quick", action="store_true", help="only the PCG section, three exchange modes")
     args = ap.parse_args()
     rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cells = tuple(args.cells)
-    blocks = block_grid(world)
+    blocks = tuple(args.blocks) if args.blocks else block_grid(world)
+    assert blocks[0] * blocks[1] * blocks[2] == world
     box = tuple(c / cells[0] for c in cells)
 
     def gcfg(**kw):
@@ -59,10 +63,29 @@ def main():
         if not ok:
             failures.append(f"rank {rank}: {name} {detail}")
 
+    rng = np.random.default_rng(77)
+    if not args.quick:
+        sections_1_2(args, rank, gcfg, rank_cfg, rng, check)
+    section_3(args, rank, gcfg, rank_cfg, rng, check)
+    if not (args.quick or args.skip_steps):
+        section_4(args, rank, gcfg, rank_cfg, check)
+
+    flag = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(flag)
+    for msg in failures:
+        print("FAIL", msg, flush=True)
+    if rank == 0:
+        print(f"mgpu_worker world={world} blocks={blocks} cells={cells}: "
+              f"{'OK' if int(flag) == 0 else 'FAILED (%d)' % int(flag)}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) == 0 else 1)
+
+
+def sections_1_2(args, rank, gcfg, rank_cfg, rng, check):
     # 1. stencil + dot on a random global p --------------------------------------------------------
     ora = Oracle(gcfg())
     gpu = Solver(rank_cfg())
-    rng = np.random.default_rng(77)
     p = rng.uniform(-1, 1, size=ora.shape(K.CG_P))
     ora.set(K.CG_P, p)
     gpu.set(K.CG_P, p[block_slices(gpu, K.CG_P)])
@@ -91,6 +114,9 @@ def main():
     gpu.close()
     ora.close()
 
+
+
+def section_3(args, rank, gcfg, rank_cfg, rng, check):
     # 3. PCG on a synthetic divergence: every CG form / halo schedule, bit for bit ----------------------
     ora = Oracle(gcfg())
     vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
@@ -103,6 +129,8 @@ def main():
     modes = [("two-kernel, NVLink peer stores (default)", {"cg_variant": 1, "peer_halo": 1}),
              ("two-kernel, NVLink peer stores, small tiles",
               {"cg_variant": 1, "peer_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
+             ("two-kernel, NVLink peer stores, phase B reads the x ghosts from the staging areas",
+              {"cg_variant": 1, "peer_halo": 1, "peer_xstage": 1}),
              ("two-kernel, NCCL, interior overlapped with the r/p halo",
               {"cg_variant": 1, "peer_halo": 0, "overlap_halo": 1}),
              ("two-kernel, NCCL, halo first", {"cg_variant": 1, "peer_halo": 0, "overlap_halo": 0}),
@@ -110,6 +138,8 @@ def main():
               {"cg_variant": 1, "peer_halo": 0, "overlap_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64,
                "fused_ty": 8}),
              ("three-kernel, NCCL", {"cg_variant": 0})]
+    if args.quick:
+        modes = [modes[0], modes[1], modes[2], modes[4]]
     for name, tune in modes:
         gpu = Solver(rank_cfg())
         for k, v in tune.items():
@@ -134,6 +164,9 @@ def main():
         gpu.close()
     ora.close()
 
+
+
+def section_4(args, rank, gcfg, rank_cfg, check):
     # 4. whole timesteps of the default inflow problem -----------------------------------------------------
     ora = Oracle(gcfg())
     gpu = Solver(rank_cfg())
@@ -152,16 +185,6 @@ def main():
         check(f"step field {f}", min(e, ea) < 1e-10, f"rel l2 {e} (vs global norm {ea})")
     gpu.close()
     ora.close()
-
-    flag = torch.tensor([len(failures)], device="cuda")
-    dist.all_reduce(flag)
-    for msg in failures:
-        print("FAIL", msg, flush=True)
-    if rank == 0:
-        print(f"mgpu_worker world={world} blocks={blocks} cells={cells}: "
-              f"{'OK' if int(flag) == 0 else 'FAILED (%d)' % int(flag)}", flush=True)
-    dist.destroy_process_group()
-    sys.exit(1 if int(flag) else 0)
 
 
 if __name__ == "__main__":

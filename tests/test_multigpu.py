@@ -16,15 +16,28 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_block_decomposed_run_matches_single_block_oracle(world):
+def _run_worker(world, extra, cells=(48, 40, 36)):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world),
-           os.path.join(ROOT, "tests", "mgpu_worker.py"), "--cells", "48", "40", "36", "--steps", "3"]
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), "--cells"] + [str(c) for c in cells] + ["--steps", "3"] + extra
     p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     sys.stdout.write(p.stdout[-4000:])
     sys.stderr.write(p.stderr[-4000:])
     assert p.returncode == 0
     assert "OK" in p.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_block_decomposed_run_matches_single_block_oracle(world):
+    _run_worker(world, [])
+
+
+@pytest.mark.parametrize("blocks", [(2, 1, 1), (1, 2, 1)])
+def test_two_blocks_split_along_x_or_y(blocks):
+    """The default grid splits z first; x splits (strided faces, packed over NVLink) and y splits are
+    otherwise only reached at 8 / 4 GPUs."""
+    # 128 cells along x: the two 64-cell blocks end exactly on a 64-wide tile, which is the case where
+    # phase B reads its x ghosts from the NVLink staging areas instead of the ghost columns
+    _run_worker(2, ["--blocks"] + [str(b) for b in blocks] + ["--quick"], cells=(128, 24, 20))

@@ -6,14 +6,22 @@
 // __graft_entry__.smoke() and as bench.py's cpu_baseline / --impl reference leg.
 // Nothing in cajitafluids_b200/ (the product) links, loads or calls this file.
 //
-// PARITY UNPINNED: the reference cannot be built here (Kokkos, Cabana/Cajita, MPI, Silo
-// absent) and none of its tests touches this path, so this
-// restatement is pinned only by (a) the geometry assertions of tests/tstMesh.cpp and
-// tests/tstProblemManager.cpp re-expressed in tests/test_oracle_geometry.py and (b) the
-// analytic known-answer tests of SURVEY.md §8c.  Third-party arithmetic that is NOT in the
-// reference tree — Cabana (ECP-copa/Cabana, Cajita sub-library, unpinned: `cabana@master`
-// in configs/llnl-lassen/spack.yaml:12, API level ~0.5) — is restated from its published
-// algorithm and marked [Cajita-mem].
+// PARITY STATUS.  The reference cannot be built as shipped (Kokkos, Cabana/Cajita, MPI, Silo absent;
+// SURVEY.md F3) and none of its tests touches this path.  It IS run here, though:
+// `make -C oracle ref` compiles the unmodified reference sources from /root/reference against
+// single-rank stand-ins for those dependencies (oracle/refshim/, see its README) into
+// oracle/_ref/libcfref.so, and tests/test_reference_shim.py holds this file against it BIT FOR BIT
+// (whole 2-D runs, every stage alone on seeded fields, the stored matrix, ghosts, the CG residual
+// history, the solve loop, the error paths); tests/golden/refrun_*.npz are that library's outputs.
+// So everything that lives in the reference tree is PINNED against the reference's own statements.
+// PARITY UNPINNED for the rest: the third-party arithmetic that is NOT in the reference tree —
+// Cabana (ECP-copa/Cabana, Cajita sub-library, unpinned: `cabana@master` in
+// configs/llnl-lassen/spack.yaml:12, API level ~0.5): CG loop, B-splines, G2P, LocalMesh
+// coordinates, index spaces — is restated from its published algorithm, marked [Cajita-mem] here
+// and in the stand-in, and anchored on (a) the reference's geometry assertions (tests/tstMesh.cpp,
+// tests/tstProblemManager.cpp: run unmodified on the stand-in, and re-expressed in
+// tests/test_oracle_geometry.py), (b) the analytic known-answer tests of SURVEY.md §8c and (c) an
+// independent numpy/scipy model (tests/ref2d_numpy.py).  The 3-D extension has no reference at all.
 //
 // The reference is 2-D only.  dim == 2 follows it statement by statement;
 // dim == 3 is the obvious extension, every 3-D choice is marked [3D-ext].

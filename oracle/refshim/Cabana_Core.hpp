@@ -1,0 +1,6 @@
+// Cabana_Core.hpp — forwards to the single-file Cajita stand-in (oracle/refshim/Cajita.hpp).
+// TEST INFRASTRUCTURE ONLY; see oracle/refshim/README.md.
+#ifndef CFREF_SHIM_CABANA_CORE_HPP
+#define CFREF_SHIM_CABANA_CORE_HPP
+#include <Cajita.hpp>
+#endif

@@ -258,8 +258,30 @@ def main():
         k, v = kv.split("=")
         s.set_tuning(k, int(v))
 
-    for _ in range(args.warmup):
-        s.pcg_fixed(args.iters)
+    def all_ranks_ok(ok):
+        if dist is None:
+            return ok
+        t = torch.tensor([0.0 if ok else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0]) == 0.0
+
+    # warm-up; if the NVLink peer-memory exchange fails on ANY rank (a mapping that cannot be used, a
+    # peer that never publishes), all ranks agree to fall back to the NCCL exchange and warm up again
+    fallback = None
+    err = None
+    try:
+        for _ in range(args.warmup):
+            s.pcg_fixed(args.iters)
+    except Exception as e:  # noqa: BLE001
+        err = e
+    if not all_ranks_ok(err is None):
+        if world > 1 and s.stats()["peer_mode"]:
+            fallback = f"peer-memory exchange failed during warm-up ({err}); NCCL send/recv used instead"
+            s.set_tuning("peer_halo", 0)
+            for _ in range(args.warmup):
+                s.pcg_fixed(args.iters)
+        else:
+            raise err if err is not None else RuntimeError("another rank failed during warm-up")
     barrier()
     s.reset_stats()
     sampler = ClockSampler(local)
@@ -408,7 +430,8 @@ def main():
                            "cg_form": "two kernels, 72 B/cell" if args.cg_variant == 1 else "three kernels, 88 B/cell",
                            "exchange": ("none (1 GPU)" if world == 1 else
                                         "NVLink peer stores (cudaIpc), ghosts + CG sums in one kernel per reduction point"
-                                        if st["peer_mode"] else "NCCL send/recv + all-gather")},
+                                        if st["peer_mode"] else "NCCL send/recv + all-gather"),
+                           **({"exchange_fallback": fallback} if fallback else {})},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "extra": extra}
         sys.stdout.flush()

@@ -920,7 +920,12 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     else if ( k == "overlap_halo" )
         c->overlap_halo = value != 0;
     else if ( k == "peer_halo" )
+    {
         c->use_peer = value != 0;
+        // leaving peer mode after a timed-out exchange: clear the sticky error so the NCCL path can run
+        if ( c->d_state )
+            CFB_CUDA( c, cudaMemsetAsync( &c->d_state->xerror, 0, sizeof( int ), c->stream ) );
+    }
     else if ( k == "peer_xstage" )
         c->peer_xstage_reads = value != 0;
     else if ( k == "time_kernels" )

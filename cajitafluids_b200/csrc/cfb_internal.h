@@ -135,7 +135,7 @@ struct cfb_ctx
     bool fu_reverse = false;  // phase B walks the units top-down (L2 reuse between the phases)
     int ru_ctas = 3;          // phase A: CTAs per SM of the grid-stride launch
     // NCCL path: run interior units while the r/p ghosts are in flight (measured slower than
-    // halo-first at 512^3 per GPU, profiles/r1_bench_n8_*: off by default)
+    // halo-first at 2 x 512^3: profiles/r1_bench_n2_nccl_overlap.json vs r1_bench_n2_nccl.json; off)
     bool overlap_halo = false;
 
     // stats

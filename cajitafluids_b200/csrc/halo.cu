@@ -400,7 +400,8 @@ int peer_setup( cfb_ctx* c )
     CFB_CUDA( c, cudaMemset( c->mail_self, 0, sizeof( PeerMail ) ) );
     CFB_CUDA( c, cudaMalloc( &c->d_xticket, sizeof( unsigned int ) ) );
     CFB_CUDA( c, cudaMemset( c->d_xticket, 0, sizeof( unsigned int ) ) );
-    const size_t xstage_elems = (size_t)4 * c->g.n[1] * c->g.n[2];
+    // [2 sides][r, pbuf 0, pbuf 1] slots of ny * nz doubles each (see xslot)
+    const size_t xstage_elems = (size_t)6 * c->g.n[1] * c->g.n[2];
     CFB_CUDA( c, cudaMalloc( &c->xstage_self, xstage_elems * sizeof( double ) ) );
     CFB_CUDA( c, cudaMemset( c->xstage_self, 0, xstage_elems * sizeof( double ) ) );
     PeerInfo mine{};
@@ -514,7 +515,7 @@ int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpac
     a.which = which;
     a.rank = c->cfg.world_rank;
     a.world = c->cfg.world_size;
-    a.timeout_cycles = 4000000000ll; // ~2 s at 1.9 GHz: a dead peer must not hang the GPU
+    a.timeout_cycles = 20000000000ll; // ~10 s at 1.9 GHz: a dead peer must not hang the GPU
     for ( int r = 0; r < a.world; ++r )
         a.mail[r] = c->mail[r];
     long long cells = 0;
@@ -582,10 +583,6 @@ int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpac
     }
     return CFB_OK;
 }
-
-namespace
-{
-} // namespace
 
 extern "C" int cfb_nccl_unique_id( unsigned char* id )
 {

@@ -50,6 +50,7 @@ class Library:
         "get_stats": [C.c_void_p, C.POINTER(K.Stats)],
         "reset_stats": [C.c_void_p],
         "residual_history": [C.c_void_p, _dp, C.c_int, _ip],
+        "output_extract": [C.c_void_p, _dp, _dp, _dp, _dp, _dp],
     }
     # product-only entry points (absent from the checker library)
     _SIG_OPT = {
@@ -63,6 +64,10 @@ class Library:
         "pcg_fixed": [C.c_void_p, C.c_int, _dp, _dp],
         "fill_synthetic_velocity": [C.c_void_p, C.c_int, C.c_uint64],
         "set_tuning": [C.c_void_p, C.c_char_p, C.c_int],
+        "write_output": [C.c_void_p, C.c_char_p, C.c_int],
+        "output_flush": [C.c_void_p],
+        "set_output_dir": [C.c_void_p, C.c_char_p],
+        "write_npy": [C.c_char_p, _dp, C.c_int, C.POINTER(C.c_int64)],
         "abi_version": [],
     }
 
@@ -232,6 +237,30 @@ class Context:
         self._call("pcg_solve_host", b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p),
                    C.byref(it), C.byref(res))
         return x, it.value, res.value
+
+    # -- output stage (SiloWriter::writeFile, src/SiloWriter.hpp:56-197)
+    def output(self):
+        """(quantity[z,y,x], velocity[d,z,y,x] at the cell centres, [nodes_x, nodes_y(, nodes_z)]) of the
+        owned cells: what the reference hands to Silo for this block."""
+        nz, ny, nx = self.shape(K.QUANTITY)
+        q = np.empty((nz, ny, nx))
+        vel = np.empty((self.dim, nz, ny, nx))
+        nodes = [np.empty(n + 1) for n in (nx, ny, nz)[: self.dim]]
+        ptr = [a.ctypes.data_as(_dp) for a in nodes] + [None] * (3 - self.dim)
+        self._call("output_extract", q.ctypes.data_as(_dp), vel.ctypes.data_as(_dp), *ptr)
+        return q, vel, nodes
+
+    def write_output(self, directory, time_step):
+        """siloWrite (src/SiloWriter.hpp:355-417) re-designed: extraction kernel + asynchronous copy now,
+        the files (.npy per variable and block + a .json master on rank 0) at the next write / flush."""
+        self._call("write_output", os.fsencode(directory), int(time_step))
+
+    def output_flush(self):
+        self._call("output_flush")
+
+    def set_output_dir(self, directory):
+        """Makes solve() write at step 0 and every write_freq steps like src/Solver.hpp:156,170-173."""
+        self._call("set_output_dir", os.fsencode(directory) if directory else None)
 
     # -- micro-benchmarks / introspection
     def stencil_dot(self, reps=1):

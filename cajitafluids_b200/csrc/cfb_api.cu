@@ -416,7 +416,6 @@ int cfb_create( const cfb_config* cfg, cfb_ctx** out )
     g.D = D;
     g.h = cfg->halo_cell_width;
     g.cell = cell;
-    g.rdx = 1.0 / cell;
     for ( int d = 0; d < 3; ++d )
     {
         if ( d < D )
@@ -427,9 +426,12 @@ int cfb_create( const cfb_config* cfg, cfb_ctx** out )
             g.hi_bd[d] = cfg->block_id[d] == cfg->ranks_per_dim[d] - 1;
             g.bt[d] = cfg->boundary_type[d];
             g.bt[3 + d] = cfg->boundary_type[D + d];
-            // LocalMesh: own low corner = global low + cell * offset; ghosted low = own low - halo * cell
-            double own_low = cfg->global_bounding_box[d] + cell * g.off[d];
-            g.ghost_low[d] = own_low - g.h * cell;
+            // UniformGlobalMesh: per-dimension cell size; LocalMesh: own low corner = global low +
+            // cell_d * offset; ghosted low = own low - halo * cell_d
+            g.celld[d] = ( cfg->global_bounding_box[3 + d] - cfg->global_bounding_box[d] ) / cfg->global_num_cell[d];
+            g.rdxd[d] = 1.0 / g.celld[d];
+            double own_low = cfg->global_bounding_box[d] + g.celld[d] * g.off[d];
+            g.ghost_low[d] = own_low - g.h * g.celld[d];
         }
         else
         {
@@ -440,6 +442,8 @@ int cfb_create( const cfb_config* cfg, cfb_ctx** out )
             g.lo_bd[d] = g.hi_bd[d] = 1;
             g.bt[d] = g.bt[3 + d] = CFB_SOLID;
             g.ghost_low[d] = 0.0;
+            g.celld[d] = cell;
+            g.rdxd[d] = 1.0 / cell;
         }
         g.nf[d] = g.n[d] + ( ( d < D && g.hi_bd[d] ) ? 1 : 0 );
         if ( g.n[d] < 1 )
@@ -580,6 +584,7 @@ int cfb_destroy( cfb_ctx* c )
     cudaSetDevice( c->device );
     if ( c->stream )
         cudaStreamSynchronize( c->stream );
+    output_destroy( c ); // writes a pending output first
     halo_destroy( c );
     for ( int f = 0; f < 4; ++f )
         for ( int v = 0; v < 2; ++v )
@@ -762,7 +767,19 @@ int cfb_solve( cfb_ctx* c, double t_final, int write_freq, int* steps_taken )
 {
     int t = 0;
     const int num_step = (int)( t_final / c->g.dt ); // src/Solver.hpp:158 (print only)
-    int rc = cfb_setup( c );
+    // _silo->siloWrite before setup and after every write_freq-th step (src/Solver.hpp:156,170-173),
+    // when an output directory has been set (cfb_set_output_dir); both writes of t == 0 go to the same
+    // files, the second replaces the first, as in the reference (DB_CLOBBER)
+    const char* odir = output_solve_dir( c );
+    const std::string out_dir = odir ? odir : "";
+    int rc = CFB_OK;
+    if ( odir && write_freq > 0 )
+    {
+        rc = output_write( c, out_dir.c_str(), t );
+        if ( rc )
+            return rc;
+    }
+    rc = cfb_setup( c );
     if ( rc )
         return rc;
     do
@@ -772,8 +789,17 @@ int cfb_solve( cfb_ctx* c, double t_final, int write_freq, int* steps_taken )
         rc = cfb_step( c );
         if ( rc )
             return rc;
+        if ( odir && write_freq > 0 && 0 == t % write_freq )
+        {
+            rc = output_write( c, out_dir.c_str(), t );
+            if ( rc )
+                return rc;
+        }
         t++;
     } while ( c->g.time < t_final );
+    rc = output_flush( c );
+    if ( rc )
+        return rc;
     if ( steps_taken )
         *steps_taken = t;
     return CFB_OK;

@@ -33,7 +33,10 @@ struct Geo
     int bt[6];    // boundary types, [d] low, [3 + d] high  (NB: always stride 3 here)
     long long sy, sz, origin, total; // strides / allocation size in doubles
     int ay, az;                      // allocated rows / planes
-    double cell, dt, rdx;
+    double cell, dt; // Mesh::cellSize() == cell size of dim 0 (src/Mesh.hpp:119-122): operator scales, dt clamp
+    // Cajita's UniformGlobalMesh keeps one cell size per dimension, (hi_d - lo_d) / n_d; LocalMesh::coordinates
+    // and the spline logical coordinates use it (the Mesh ctor only checks agreement to 10 eps, :56-64)
+    double celld[3], rdxd[3];
     double ghost_low[3]; // Cajita LocalMesh ghosted low corner of this block
     double time;
 };
@@ -90,6 +93,8 @@ struct PeerMail
 
 #define CFB_MAX_PARTIALS 4096
 #define CFB_KTIMED 64
+
+struct OutputStage; // output.cu
 
 struct cfb_ctx
 {
@@ -178,6 +183,9 @@ struct cfb_ctx
     PeerMail* mail[CFB_MAX_PEERS] = { nullptr };
     unsigned int* d_xticket = nullptr;
     std::vector<void*> ipc_opened;
+
+    // output stage (output.cu), created on first use
+    OutputStage* out = nullptr;
 };
 
 extern std::string g_cfb_error;
@@ -257,6 +265,11 @@ int fused_setup( cfb_ctx* c );                // tensor maps of cg_r, cg_p + the
 int launch_cg_rupdate( cfb_ctx* c );          // phase A: r -= alpha q, sum r^2, sum r.Minv r
 int launch_cg_fused( cfb_ctx* c, int which ); // phase B: 0 = all units, 1 = interior, 2 = boundary
 int launch_cg_finish( cfb_ctx* c );
+// output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
+int output_write( cfb_ctx* c, const char* dir, int time_step );
+int output_flush( cfb_ctx* c );
+const char* output_solve_dir( const cfb_ctx* c ); // directory set with cfb_set_output_dir, or nullptr
+void output_destroy( cfb_ctx* c );
 // halo.cu
 int halo_init( cfb_ctx* c );
 void halo_destroy( cfb_ctx* c );

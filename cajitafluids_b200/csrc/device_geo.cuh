@@ -22,7 +22,7 @@ __device__ __forceinline__ void geo_coordinates( const Geo& g, int ent, const in
     for ( int d = 0; d < D; ++d )
     {
         const double l = (double)( idx[d] + g.h );
-        x[d] = ( ent - 1 == d ) ? g.ghost_low[d] + l * g.cell : g.ghost_low[d] + ( l + 0.5 ) * g.cell;
+        x[d] = ( ent - 1 == d ) ? g.ghost_low[d] + l * g.celld[d] : g.ghost_low[d] + ( l + 0.5 ) * g.celld[d];
     }
 }
 
@@ -108,9 +108,9 @@ __device__ __forceinline__ double interp_field( const Geo& g, int ent, const dou
     for ( int d = 0; d < D; ++d )
     {
         // position of local entity 0: coordinates( entity, {0,0,0} )
-        const double low = ( ent - 1 == d ) ? g.ghost_low[d] + 0.0 * g.cell
-                                            : g.ghost_low[d] + ( 0.0 + 0.5 ) * g.cell;
-        const double xl = ( loc[d] - low ) * g.rdx;
+        const double low = ( ent - 1 == d ) ? g.ghost_low[d] + 0.0 * g.celld[d]
+                                            : g.ghost_low[d] + ( 0.0 + 0.5 ) * g.celld[d];
+        const double xl = ( loc[d] - low ) * g.rdxd[d];
         int s0;
         if ( ORDER == 1 )
             spline1( xl, s0, w[d] );

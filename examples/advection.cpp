@@ -42,6 +42,7 @@ struct ClArgs
     double in_vel[3] = { 1.0, 0.0, 0.0 };
     double in_quantity = 3.0;
     std::string dump;
+    std::string out_dir = "data"; // the reference always writes into data/ (src/SiloWriter.hpp:379-384)
 };
 
 const char* short_opts = "n:s:t:i:d:g:p:m:c:x:y:z:w:h:e:q:u:v:D:o:";
@@ -66,6 +67,7 @@ const option long_opts[] = { { "cells", required_argument, nullptr, 'n' },
                              { "input-velocity-z", required_argument, nullptr, 1001 },
                              { "dim", required_argument, nullptr, 'D' },
                              { "dump", required_argument, nullptr, 'o' },
+                             { "output-dir", required_argument, nullptr, 1002 },
                              { "help", no_argument, nullptr, 'j' },
                              { nullptr, 0, nullptr, 0 } };
 
@@ -84,7 +86,10 @@ void usage( const char* prog )
               << "  -x/-y/-z, -w/-h/-e       inflow box corner and extent\n"
               << "  -q, -u, -v               inflow quantity and velocity\n"
               << "  -D, --dim 2|3            space dimension (default 2, like the reference)\n"
-              << "  -o, --dump FILE          write the final q (owned cells, float64) to FILE\n";
+              << "  -o, --dump FILE          write the final q (owned cells, float64) to FILE\n"
+              << "      --output-dir DIR     where the periodic output goes (default data, like the reference;\n"
+              << "                           .npy per variable and block + a .json master per written step;\n"
+              << "                           'none' turns it off)\n";
 }
 
 double positive( const char* what, const char* arg )
@@ -167,6 +172,9 @@ int parse( int argc, char** argv, ClArgs& cl )
             break;
         case 'o':
             cl.dump = optarg;
+            break;
+        case 1002:
+            cl.out_dir = std::strcmp( optarg, "none" ) == 0 ? "" : optarg;
             break;
         case 'j':
             usage( argv[0] );
@@ -268,6 +276,8 @@ int advect( const ClArgs& cl )
 
     auto solver = createSolver<Dim>( cl.device, comm, box, ncell, partitioner, cl.density, initializer, bc, source,
                                      body, cl.delta_t, cl.solver, cl.precon );
+    if ( auto* sv = dynamic_cast<Solver<Dim>*>( solver.get() ) )
+        sv->siloWriter()->setDirectory( cl.out_dir );
     auto t0 = std::chrono::steady_clock::now();
     solver->solve( cl.t_final, cl.write_freq );
     double sec = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();

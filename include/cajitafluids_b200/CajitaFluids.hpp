@@ -18,6 +18,8 @@
 //                                                            setMaxIter, setPrintLevel, solve, ...)
 //   VelocityCorrectorBase / createVelocityCorrector          same        (src/VelocityCorrector.hpp)
 //   TimeIntegrator::step                                     same        (src/TimeIntegrator.hpp:120)
+//   SiloWriter<D,Exec,Mem>::siloWrite                        SiloWriter<D>::siloWrite (src/SiloWriter.hpp:355;
+//                                                            .npy + .json instead of Silo/PMPIO, asynchronous)
 //   SolverBase / Solver<D,...> / createSolver                same        (src/Solver.hpp:41-48,283-350)
 //
 // Errors: the reference throws std::runtime_error / std::logic_error; the shims translate the C
@@ -320,6 +322,8 @@ class ProblemManager
             init_entity( FaceK(), Field::Velocity(), f );
     }
 
+    const std::shared_ptr<detail::CtxHolder>& holder() const { return _h; }
+
   private:
     template <class Entity, class FieldTag, class InitFunctor>
     void init_entity( Entity ent, FieldTag tag, const InitFunctor& f )
@@ -479,6 +483,50 @@ void step( std::shared_ptr<detail::CtxHolder>& h )
 }
 } // namespace TimeIntegrator
 
+// ---- SiloWriter (src/SiloWriter.hpp) -------------------------------------------------------------
+// Same constructor argument and siloWrite signature as the reference's writer.  The extraction (owned q,
+// cell-centred velocity) is one kernel and the copy to the host is asynchronous: siloWrite returns at
+// once, the files of a write appear at the next siloWrite / flush / destruction of the solver.  Silo and
+// PMPIO are not available, so the container is .npy per variable and block + a .json master per step
+// under `directory()` ("data" like src/SiloWriter.hpp:379-384).
+template <std::size_t NumSpaceDim>
+class SiloWriter
+{
+  public:
+    using pm_type = ProblemManager<NumSpaceDim>;
+    explicit SiloWriter( const std::shared_ptr<pm_type>& pm )
+        : _h( pm->holder() )
+    {
+    }
+    explicit SiloWriter( const std::shared_ptr<detail::CtxHolder>& h )
+        : _h( h )
+    {
+    }
+    void setDirectory( const std::string& dir ) { _dir = dir; }
+    const std::string& directory() const { return _dir; }
+    // name ("Mesh"), time and dt are what the reference passes; time and dt are read from the solver state
+    void siloWrite( const char* /*name*/, int time_step, double /*time*/, double /*dt*/ )
+    {
+        detail::check( cfb_write_output( _h->ctx, _dir.c_str(), time_step ), _h->ctx );
+    }
+    void flush() { detail::check( cfb_output_flush( _h->ctx ), _h->ctx ); }
+    // what writeFile hands to Silo, as host arrays (x fastest): quantity[ncell], velocity[D * ncell]
+    void extract( std::vector<double>& quantity, std::vector<double>& velocity )
+    {
+        int ext[3];
+        cfb_owned_extent( _h->ctx, CFB_QUANTITY, ext );
+        const size_t n = (size_t)ext[0] * ext[1] * ext[2];
+        quantity.resize( n );
+        velocity.resize( n * NumSpaceDim );
+        detail::check( cfb_output_extract( _h->ctx, quantity.data(), velocity.data(), nullptr, nullptr, nullptr ),
+                       _h->ctx );
+    }
+
+  private:
+    std::shared_ptr<detail::CtxHolder> _h;
+    std::string _dir = "data";
+};
+
 // ---- Solver (src/Solver.hpp) -----------------------------------------------------------------------
 class SolverBase
 {
@@ -550,16 +598,21 @@ class Solver : public SolverBase
         _pm->initialize( create_functor );
         auto cg = std::make_shared<B200ConjugateGradient>( _h );
         _vc = std::make_shared<VelocityCorrector<NumSpaceDim>>( _h, cg );
+        _silo = std::make_shared<SiloWriter<NumSpaceDim>>( _h ); // src/Solver.hpp:121-122
     }
 
     void setup() override { detail::check( cfb_setup( _h->ctx ), _h->ctx ); }
     void step() override { detail::check( cfb_step( _h->ctx ), _h->ctx ); }
+    // src/Solver.hpp:149-177, _silo->siloWrite before setup and after every write_freq-th step included
+    // (into siloWriter()->directory(), "data" by default; an empty directory name turns the writes off)
     void solve( const double t_final, const int write_freq ) override
     {
         int steps = 0;
+        detail::check( cfb_set_output_dir( _h->ctx, _silo->directory().c_str() ), _h->ctx );
         detail::check( cfb_solve( _h->ctx, t_final, write_freq, &steps ), _h->ctx );
         _steps = steps;
     }
+    const std::shared_ptr<SiloWriter<NumSpaceDim>>& siloWriter() const { return _silo; }
     void _addInputs() { detail::check( cfb_add_inputs( _h->ctx ), _h->ctx ); }
 
     const std::shared_ptr<pm_type>& problemManager() const { return _pm; }
@@ -589,6 +642,7 @@ class Solver : public SolverBase
     bc_type _bc;
     std::shared_ptr<pm_type> _pm;
     std::shared_ptr<VelocityCorrectorBase> _vc;
+    std::shared_ptr<SiloWriter<NumSpaceDim>> _silo;
     int _steps = 0;
 };
 

@@ -253,6 +253,32 @@ int cfb_solve( cfb_ctx* ctx, double t_final, int write_freq, int* steps_taken );
 int cfb_pcg_solve_host( cfb_ctx* ctx, const double* b_host, double* x_host, int* num_iter,
                         double* residual_norm );
 
+/* ---- output stage (the step after the hot path in Solver::solve) ---- */
+
+/* SiloWriter::writeFile (src/SiloWriter.hpp:56-197): what the reference hands to Silo for this block.
+ * One extraction kernel drops the ghosts of q (:136-156) and interpolates the MAC velocity to the cell
+ * centres (Interpolation::interpolateVelocity<D,1> at LocalMesh::coordinates( Cell ), :172-186); the
+ * node coordinates of the owned cells (:109-123) are computed on the host.  Dense x-fastest HOST
+ * arrays: quantity[nz][ny][nx], velocity[D][nz][ny][nx], nodes_d[n_d + 1]; NULL skips an output.
+ * Blocking form (tests, callers that want the arrays). */
+int cfb_output_extract( cfb_ctx* ctx, double* quantity, double* velocity, double* nodes_x, double* nodes_y,
+                        double* nodes_z );
+/* SiloWriter::siloWrite( "Mesh", time_step, time, dt ) (src/SiloWriter.hpp:355-417), asynchronous:
+ * enqueues the extraction kernel behind the work already queued and the device -> pinned-host copy on
+ * an I/O stream, and returns; the files are written at the next cfb_write_output / cfb_output_flush /
+ * cfb_destroy.  Silo and PMPIO are absent, so the container is
+ *     <dir>/raw/CajitaFluidsOutput<rank:05d><step:05d>.{quantity,velocity,nodes_x,nodes_y[,nodes_z]}.npy
+ *     <dir>/CajitaFluids<step:05d>.json      (rank 0: cycle, time, dtime, every block's offset/extent/files;
+ *                                             the role of writeMultiObjects, :292-346)
+ * following the reference's name pattern (:379-384).  dir == NULL or "" means "data" like the reference. */
+int cfb_write_output( cfb_ctx* ctx, const char* dir, int time_step );
+int cfb_output_flush( cfb_ctx* ctx );
+/* Makes cfb_solve write like Solver::solve does (src/Solver.hpp:156,170-173): once before setup and
+ * after every step t with t % write_freq == 0.  NULL / "" turns the writes off (the default). */
+int cfb_set_output_dir( cfb_ctx* ctx, const char* dir );
+/* Host-only helper: a dense little-endian float64 array as a numpy .npy (version 1.0) file, C order. */
+int cfb_write_npy( const char* path, const double* data, int ndim, const int64_t* shape );
+
 /* ---- micro-benchmark / introspection entry points -------------------------------- */
 
 /* q = A p and sum(p*q) on the CG work vectors (fields CFB_CG_P -> CFB_CG_Q), `reps` launches;

@@ -139,7 +139,12 @@ struct cfo_ctx
     int off[3];    // global cell offset of this block
     bool hi_bd[3]; // block touches the high physical boundary in dim d
     bool lo_bd[3];
-    double cell;   // Mesh::cellSize
+    double cell;   // Mesh::cellSize == globalMesh().cellSize( 0 )  (src/Mesh.hpp:119-122)
+    // Cajita's UniformGlobalMesh keeps one cell size PER DIMENSION, (hi_d - lo_d) / n_d [Cajita-mem]
+    // (createUniformGlobalMesh( low, high, num_cell ), src/Mesh.hpp:79-80); the Mesh ctor only checks
+    // that they agree with cellSize( 0 ) to 10 eps (:56-64).  LocalMesh::coordinates and the spline
+    // logical coordinates use these; the operator scales, the dt clamp and the divergence use `cell`.
+    double celld[3];
     double dt;     // clamped
     double time;
     double ghost_low[3]; // LocalMesh ghosted low corner [Cajita-mem]
@@ -228,9 +233,9 @@ inline void coordinates( const cfo_ctx& c, int ent, const int idx[3], double x[3
     for ( int d = 0; d < c.D; ++d )
     {
         if ( ent - 1 == d )
-            x[d] = c.ghost_low[d] + double( idx[d] ) * c.cell;
+            x[d] = c.ghost_low[d] + double( idx[d] ) * c.celld[d];
         else
-            x[d] = c.ghost_low[d] + ( double( idx[d] ) + 0.5 ) * c.cell;
+            x[d] = c.ghost_low[d] + ( double( idx[d] ) + 0.5 ) * c.celld[d];
     }
 }
 
@@ -290,9 +295,9 @@ inline double interpolate_field( const cfo_ctx& c, int ent, const double loc[3],
     const int zero[3] = { 0, 0, 0 };
     double low[3];
     coordinates( c, ent, zero, low );
-    const double rdx = 1.0 / c.cell;
     for ( int d = 0; d < c.D; ++d )
     {
+        const double rdx = 1.0 / c.celld[d]; // evaluateSpline: 1 / local_mesh.cellSize( d ) [Cajita-mem]
         double xl = ( loc[d] - low[d] ) * rdx;
         if ( ORDER == 1 )
             spline1( xl, s[d], w[d] );
@@ -822,8 +827,9 @@ int cfo_create( const cfb_config* cfg, cfo_ctx** out )
             c->bc_max[d] = cfg->global_num_cell[d] - 1; // src/Solver.hpp:109-110
             // LocalMesh [Cajita-mem]: own low corner = global low + cell * global offset;
             // ghosted low corner = own low corner - halo * cell.
-            double own_low = cfg->global_bounding_box[d] + c->cell * c->off[d];
-            c->ghost_low[d] = own_low - c->h * c->cell;
+            c->celld[d] = ( cfg->global_bounding_box[3 + d] - cfg->global_bounding_box[d] ) / cfg->global_num_cell[d];
+            double own_low = cfg->global_bounding_box[d] + c->celld[d] * c->off[d];
+            c->ghost_low[d] = own_low - c->h * c->celld[d];
         }
         else
         {
@@ -832,6 +838,7 @@ int cfo_create( const cfb_config* cfg, cfo_ctx** out )
             c->lo_bd[d] = c->hi_bd[d] = true;
             c->bc_min[d] = c->bc_max[d] = 0;
             c->ghost_low[d] = 0;
+            c->celld[d] = c->cell;
         }
     }
 
@@ -1175,6 +1182,50 @@ int cfo_rk3( cfo_ctx* c, const double* x0, double* trace )
         trace[d] = t[d];
     return CFB_OK;
 }
+// SiloWriter::writeFile  src/SiloWriter.hpp:56-197: what the reference hands to Silo for this block.
+//   :109-123  node coordinates of the owned cells, per dim: coordinates( Node(), {0,..,i,..,0} )[d]
+//             for i = cell_domain.min(d) .. cell_domain.max(d) inclusive (extent + 1 nodes)
+//   :136-156  owned quantity (ghosts dropped)
+//   :172-186  cell-centred velocity: coordinates( Cell(), idx ) -> interpolateVelocity<D,1>
+// No gather precedes it in the reference; the samples that fall on ghost entities carry weight
+// (1 - f) or f with f = 0 up to rounding.  Dense x-fastest outputs: quantity[nz][ny][nx],
+// velocity[D][nz][ny][nx], nodes_d[n_d + 1]; NULL skips an output.
+int cfo_output_extract( cfo_ctx* c, double* quantity, double* velocity, double* nodes_x, double* nodes_y,
+                        double* nodes_z )
+{
+    const Space s = own_space( *c, 0 );
+    const int ex = s.hi[0] - s.lo[0], ey = s.hi[1] - s.lo[1], ez = s.hi[2] - s.lo[2];
+    const size_t ncell = (size_t)ex * ey * ez;
+    double* nodes[3] = { nodes_x, nodes_y, nodes_z };
+    for ( int d = 0; d < c->D; ++d )
+    {
+        if ( !nodes[d] )
+            continue;
+        for ( int i = s.lo[d]; i < s.hi[d] + 1; ++i )
+            nodes[d][i - s.lo[d]] = c->ghost_low[d] + double( i ) * c->celld[d]; // Node: every dim is "normal"
+    }
+    const Arr& q = c->fld[0][c->cur[0]];
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+            {
+                const size_t o = ( (size_t)( k - s.lo[2] ) * ey + ( j - s.lo[1] ) ) * ex + ( i - s.lo[0] );
+                if ( quantity )
+                    quantity[o] = q( i, j, k );
+                if ( velocity )
+                {
+                    const int idx[3] = { i, j, k };
+                    double loc[3] = { 0, 0, 0 }, vel[3] = { 0, 0, 0 };
+                    coordinates( *c, 0, idx, loc );
+                    interpolate_velocity( *c, loc, vel );
+                    for ( int d = 0; d < c->D; ++d )
+                        velocity[(size_t)d * ncell + o] = vel[d];
+                }
+            }
+    return CFB_OK;
+}
+
 int cfo_coordinates( cfo_ctx* c, int field, const int* idx, double* x )
 {
     int id[3] = { idx[0], idx[1], c->D == 3 ? idx[2] : 0 };

@@ -85,6 +85,7 @@ struct Handle
     virtual void ownedSpace( int field, int lo[2], int hi[2] ) = 0;
     virtual void ghostExtent( int field, int ext[2] ) = 0;
     virtual cg_type* cg() = 0;
+    virtual void siloWrite( int time_step ) = 0;
     SolverBase* base = nullptr;
 };
 
@@ -184,6 +185,8 @@ struct HandleT : Handle
             ghostOf( Cell(), ext );
     }
     cg_type* cg() override { return dynamic_cast<cg_type*>( vc->_pressure_solver.get() ); }
+    // the call Solver::solve makes (src/Solver.hpp:156,170-173)
+    void siloWrite( int time_step ) override { s->_silo->siloWrite( strdup( "Mesh" ), time_step, s->_time, s->_dt ); }
 };
 
 } // namespace
@@ -536,6 +539,32 @@ int cfref_silo_last( int* writes, int* cycle, double* time, int dims[2], double*
     put( vcc, s.velocity[1] );
     put( xnodes, s.coords[0] );
     put( ynodes, s.coords[1] );
+    return CFB_OK;
+}
+
+// One SiloWriter::siloWrite of the current state (the call of src/Solver.hpp:170-173), handed back in the
+// shape of cfb_output_extract: quantity[ny][nx], velocity[2][ny][nx], node coordinates per dim.
+int cfref_output_extract( cfref_ctx* c, double* quantity, double* velocity, double* nodes_x, double* nodes_y,
+                          double* /*nodes_z*/ )
+{
+    int rc = guarded( c, [&]() { c->h->siloWrite( (int)c->steps ); } );
+    if ( rc )
+        return rc;
+    const auto& s = cfref::silo_capture();
+    const size_t n = (size_t)s.zone_dims[0] * s.zone_dims[1];
+    if ( s.quantity.size() != n || s.velocity[0].size() != n || s.velocity[1].size() != n )
+        return fail( c, CFB_ERR_INVALID, "silo capture is incomplete" );
+    if ( quantity )
+        std::memcpy( quantity, s.quantity.data(), n * sizeof( double ) );
+    if ( velocity )
+    {
+        std::memcpy( velocity, s.velocity[0].data(), n * sizeof( double ) );
+        std::memcpy( velocity + n, s.velocity[1].data(), n * sizeof( double ) );
+    }
+    if ( nodes_x )
+        std::memcpy( nodes_x, s.coords[0].data(), s.coords[0].size() * sizeof( double ) );
+    if ( nodes_y )
+        std::memcpy( nodes_y, s.coords[1].data(), s.coords[1].size() * sizeof( double ) );
     return CFB_OK;
 }
 

@@ -8,6 +8,9 @@ refrun_cases.py: setup + N steps of Solver<2>, then
     cg_iterations            per pressure solve (setup first)
     resid_last               CG residual history of the last solve
     dt, time, cell           Solver::_dt (clamped), Solver::_time, Mesh::cellSize
+    out_q, out_vel, out_nodes_x/y   what SiloWriter::siloWrite hands to Silo for the final state
+                             (src/SiloWriter.hpp:109-186, captured by the silo.h stand-in): owned quantity,
+                             cell-centred velocity [component, y, x], node coordinates
     exact_*                  the same run with the stand-in CG in the oracle's arithmetic (fused
                              multiply-adds + exactly accumulated dot products): BIT-EXACT fixtures
     plain_*                  the same run in plain double arithmetic (serial sums, no fused
@@ -39,6 +42,8 @@ def run(cfg, steps, exact):
     out["resid_last"] = r.residual_history()
     cell, dt, time = r.scalars()
     out["dt"], out["time"], out["cell"] = dt, time, cell
+    q, vel, nodes = r.output()
+    out["out_q"], out["out_vel"], out["out_nodes_x"], out["out_nodes_y"] = q[0], vel[:, 0], nodes[0], nodes[1]
     r.close()
     return out
 

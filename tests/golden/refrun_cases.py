@@ -17,6 +17,12 @@ def rectangular_48x24():
     return make_cfg(2, (48, 24), box=(1.0, 0.5))
 
 
+def rectangular_40x24_box06():
+    """(hi - lo) / n differs in the last bit between x (1/40) and y (0.6/24): Cajita's per-dimension
+    cell sizes (coordinates, spline logical coordinates) vs Mesh::cellSize() (operator scales)."""
+    return make_cfg(2, (40, 24), box=(1.0, 0.6))
+
+
 def moving_start_n36():
     c = make_cfg(2, 36, body_force=(0.5, -2.0, 0.0))
     c.init_quantity = 0.25
@@ -34,6 +40,7 @@ CASES = {
     "default_n32": (default_n32, 5),
     "gravity_free_walls_n40": (gravity_free_walls_n40, 4),
     "rectangular_48x24": (rectangular_48x24, 4),
+    "rectangular_40x24_box06": (rectangular_40x24_box06, 4),
     "moving_start_n36": (moving_start_n36, 4),
     "default_n64": (default_n64, 3),
 }

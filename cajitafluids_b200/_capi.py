@@ -68,6 +68,7 @@ class Library:
         "output_flush": [C.c_void_p],
         "set_output_dir": [C.c_void_p, C.c_char_p],
         "write_npy": [C.c_char_p, _dp, C.c_int, C.POINTER(C.c_int64)],
+        "set_preconditioner": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double],
         "abi_version": [],
     }
 
@@ -237,6 +238,12 @@ class Context:
         self._call("pcg_solve_host", b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p),
                    C.byref(it), C.byref(res))
         return x, it.value, res.value
+
+    def set_preconditioner(self, kind, nu_pre=2, nu_post=2, nu_coarse=8, omega=0.0):
+        """kind: "jacobi" (the reference's diagonal preconditioner, default) or "mg" (opt-in geometric
+        multigrid V(nu_pre, nu_post) cycle; omega <= 0: default damping)."""
+        k = {"jacobi": K.PRECOND_JACOBI, "mg": K.PRECOND_MG}.get(kind, kind)
+        self._call("set_preconditioner", int(k), int(nu_pre), int(nu_post), int(nu_coarse), C.c_double(omega))
 
     # -- output stage (SiloWriter::writeFile, src/SiloWriter.hpp:56-197)
     def output(self):

@@ -16,6 +16,7 @@ QUANTITY, U, V, W, PRESSURE, RHS, CG_R, CG_P, CG_Q = range(9)
 CURRENT, NEXT = 0, 1
 OWNED, GHOSTED = 0, 1
 STOP_ABS, STOP_REL = 0, 1
+PRECOND_JACOBI, PRECOND_MG = 0, 1
 
 
 class Config(C.Structure):

@@ -164,6 +164,12 @@ struct cfo_ctx
     double resid; // sqrt(sum r^2)
     std::vector<double> hist;
 
+    // opt-in multigrid preconditioner (cfo_set_preconditioner; NOT the reference's: see mg_* below)
+    int precond = 0; // 0 = the reference's diagonal (Jacobi) preconditioner, 1 = geometric multigrid V-cycle
+    int mg_nu1 = 2, mg_nu2 = 2, mg_nuc = 8;
+    double mg_omega = 0.0;
+    struct Mg* mg = nullptr;
+
     // distributed hooks (tests drive halo exchange / allreduce over gloo)
     gather_cb gcb = nullptr;
     allreduce_cb acb = nullptr;
@@ -551,6 +557,216 @@ inline double apply_A( const cfo_ctx& c, const Arr& x, int i, int j, int k )
     return Ax;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Opt-in geometric multigrid preconditioner for the CG (the role HYPRE's PFMG
+// plays in the reference's default path, examples/advection.cpp:186-189, src/VelocityCorrector.hpp:
+// 324-338).  This is NOT a restatement of anything in the reference tree or of HYPRE: it is the
+// CPU statement of the product's own algorithm (cajitafluids_b200/csrc/mg.cu), operation for
+// operation, so that the two can be compared bit for bit.  Parity with the reference is defined
+// only through the solution of the same linear system (same matrix, same stopping test).
+//
+//   z = M^-1 r  :=  one V(nu1, nu2) cycle on A z = r from a zero initial guess
+//   levels      : cell-centred 2:1 coarsening in every dimension while all extents stay even and
+//                 >= 2 after halving; level l uses the SAME 2*D+1-point operator (same boundary
+//                 logic) with scale_l = scale_0 / 4^l (re-discretisation, not Galerkin)
+//   smoother    : damped Jacobi, x += omega D^-1 (b - A x); the first pre-smoothing sweep starts
+//                 from x = 0 and is x = (omega D^-1) b
+//   restriction : mean of the 2^D children of the residual; prolongation: piecewise constant
+//   coarsest    : nuc Jacobi sweeps
+// With nu1 == nu2 the cycle is a symmetric operator (R is a multiple of P^T, the smoother is
+// symmetric), which CG needs.
+struct MgLevel
+{
+    int n[3];
+    int cz;                  // coarsening factor to the next level along z (1 in 2-D)
+    bool slo[3], shi[3];     // the low / high end of dim d is a SOLID physical wall
+    double scale, ns;
+    double diag[8], wminv[8]; // by number of SOLID walls touched: diagonal, omega / diagonal
+    Arr b, x[2];             // ghosted by one layer (ghosts stay zero)
+    int cur = 0;             // x[cur] holds the level's result
+    inline int walls( int i, int j, int k ) const
+    {
+        return ( i == 0 && slo[0] ) + ( i == n[0] - 1 && shi[0] ) + ( j == 0 && slo[1] ) +
+               ( j == n[1] - 1 && shi[1] ) + ( k == 0 && slo[2] ) + ( k == n[2] - 1 && shi[2] );
+    }
+    // the row of apply_A, matrix-free: diag * x, then one fused multiply-add per neighbour in stencil
+    // order (off-domain neighbours are ghost zeros); (i, j, k) are owned indices
+    inline double Ax( const Arr& v, int i, int j, int k ) const
+    {
+        const int I = i + 1, J = j + 1, K = k + 1;
+        double a = diag[walls( i, j, k )] * v( I, J, K );
+        a = std::fma( ns, v( I - 1, J, K ), a );
+        a = std::fma( ns, v( I + 1, J, K ), a );
+        a = std::fma( ns, v( I, J - 1, K ), a );
+        a = std::fma( ns, v( I, J + 1, K ), a );
+        a = std::fma( ns, v( I, J, K - 1 ), a );
+        a = std::fma( ns, v( I, J, K + 1 ), a );
+        return a;
+    }
+};
+
+} // namespace
+
+struct Mg
+{
+    std::vector<MgLevel> lv;
+};
+
+namespace
+{
+
+void mg_build( cfo_ctx& c )
+{
+    delete c.mg;
+    c.mg = new Mg();
+    const int D = c.D;
+    double omega = c.mg_omega > 0.0 ? c.mg_omega : ( D == 3 ? 6.0 / 7.0 : 0.8 );
+    int n[3] = { c.n[0], c.n[1], D == 3 ? c.n[2] : 1 };
+    double scale = c.dt / ( c.cfg.density * c.cell * c.cell ); // src/VelocityCorrector.hpp:128
+    for ( int l = 0; l < 16; ++l )
+    {
+        c.mg->lv.emplace_back();
+        MgLevel& L = c.mg->lv.back();
+        for ( int d = 0; d < 3; ++d )
+        {
+            L.n[d] = n[d];
+            // 2-D: one plane between two SOLID z walls, the same trick as the CUDA kernels (6 - 2 = 4)
+            L.slo[d] = d < D ? ( c.lo_bd[d] && c.cfg.boundary_type[d] == CFB_SOLID ) : true;
+            L.shi[d] = d < D ? ( c.hi_bd[d] && c.cfg.boundary_type[D + d] == CFB_SOLID ) : true;
+        }
+        L.cz = D == 3 ? 2 : 1;
+        L.scale = scale;
+        L.ns = -1.0 * scale;
+        for ( int cnt = 0; cnt < 8; ++cnt )
+        {
+            double dgl = 6.0 * scale; // 2-D: 4 * scale == 6 * scale - scale - scale only up to rounding,
+            if ( D == 2 )             // so follow the reference's own sequence (:137, BoundaryConditions.hpp:56-97)
+            {
+                dgl = 4.0 * scale;
+                for ( int i = 0; i < cnt - 2; ++i )
+                    dgl -= scale;
+            }
+            else
+                for ( int i = 0; i < cnt; ++i )
+                    dgl -= scale;
+            L.diag[cnt] = dgl;
+            L.wminv[cnt] = omega * ( 1.0 / dgl );
+        }
+        const int ext[3] = { n[0] + 2, n[1] + 2, n[2] + 2 };
+        L.b.alloc( ext );
+        L.x[0].alloc( ext );
+        L.x[1].alloc( ext );
+        bool can = true;
+        for ( int d = 0; d < D; ++d )
+            can = can && n[d] % 2 == 0 && n[d] / 2 >= 2;
+        if ( !can )
+            break;
+        for ( int d = 0; d < D; ++d )
+            n[d] /= 2;
+        scale = scale * 0.25;
+    }
+}
+
+inline void mg_smooth0( MgLevel& L )
+{
+    Arr& x = L.x[0];
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int k = 0; k < L.n[2]; ++k )
+        for ( int j = 0; j < L.n[1]; ++j )
+            for ( int i = 0; i < L.n[0]; ++i )
+                x( i + 1, j + 1, k + 1 ) = L.wminv[L.walls( i, j, k )] * L.b( i + 1, j + 1, k + 1 );
+    L.cur = 0;
+}
+
+inline void mg_smooth( MgLevel& L )
+{
+    const Arr& xi = L.x[L.cur];
+    Arr& xo = L.x[1 - L.cur];
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int k = 0; k < L.n[2]; ++k )
+        for ( int j = 0; j < L.n[1]; ++j )
+            for ( int i = 0; i < L.n[0]; ++i )
+            {
+                const double res = L.b( i + 1, j + 1, k + 1 ) - L.Ax( xi, i, j, k );
+                xo( i + 1, j + 1, k + 1 ) = std::fma( L.wminv[L.walls( i, j, k )], res, xi( i + 1, j + 1, k + 1 ) );
+            }
+    L.cur = 1 - L.cur;
+}
+
+// coarse b = mean of the children's residuals, summed pairwise: x pairs, then y, then z
+inline void mg_restrict( const MgLevel& F, MgLevel& C )
+{
+    const Arr& x = F.x[F.cur];
+    auto res = [&]( int i, int j, int k ) { return F.b( i + 1, j + 1, k + 1 ) - F.Ax( x, i, j, k ); };
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int K = 0; K < C.n[2]; ++K )
+        for ( int J = 0; J < C.n[1]; ++J )
+            for ( int I = 0; I < C.n[0]; ++I )
+            {
+                const int i = 2 * I, j = 2 * J, k = F.cz * K;
+                double s = ( res( i, j, k ) + res( i + 1, j, k ) ) + ( res( i, j + 1, k ) + res( i + 1, j + 1, k ) );
+                if ( F.cz == 2 )
+                {
+                    const double t = ( res( i, j, k + 1 ) + res( i + 1, j, k + 1 ) ) +
+                                     ( res( i, j + 1, k + 1 ) + res( i + 1, j + 1, k + 1 ) );
+                    s = ( s + t ) * 0.125;
+                }
+                else
+                    s = s * 0.25;
+                C.b( I + 1, J + 1, K + 1 ) = s;
+            }
+}
+
+inline void mg_prolong( MgLevel& F, const MgLevel& C )
+{
+    Arr& x = F.x[F.cur];
+    const Arr& e = C.x[C.cur];
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int k = 0; k < F.n[2]; ++k )
+        for ( int j = 0; j < F.n[1]; ++j )
+            for ( int i = 0; i < F.n[0]; ++i )
+                x( i + 1, j + 1, k + 1 ) = x( i + 1, j + 1, k + 1 ) + e( i / 2 + 1, j / 2 + 1, k / F.cz + 1 );
+}
+
+void mg_vcycle( cfo_ctx& c, int l )
+{
+    Mg& m = *c.mg;
+    MgLevel& L = m.lv[l];
+    const bool last = l + 1 == (int)m.lv.size();
+    mg_smooth0( L );
+    for ( int s = 1; s < ( last ? c.mg_nuc : c.mg_nu1 ); ++s )
+        mg_smooth( L );
+    if ( last )
+        return;
+    mg_restrict( L, m.lv[l + 1] );
+    mg_vcycle( c, l + 1 );
+    mg_prolong( L, m.lv[l + 1] );
+    for ( int s = 0; s < c.mg_nu2; ++s )
+        mg_smooth( L );
+}
+
+// z = M^-1 r on the owned cells of the ghosted CG arrays
+void mg_apply( cfo_ctx& c, const Arr& r, Arr& z )
+{
+    if ( !c.mg )
+        mg_build( c );
+    MgLevel& L = c.mg->lv[0];
+    const Space s = own_space( c, 0 );
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int k = 0; k < L.n[2]; ++k )
+        for ( int j = 0; j < L.n[1]; ++j )
+            for ( int i = 0; i < L.n[0]; ++i )
+                L.b( i + 1, j + 1, k + 1 ) = r( s.lo[0] + i, s.lo[1] + j, s.lo[2] + k );
+    mg_vcycle( c, 0 );
+    const Arr& x = L.x[L.cur];
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int k = 0; k < L.n[2]; ++k )
+        for ( int j = 0; j < L.n[1]; ++j )
+            for ( int i = 0; i < L.n[0]; ++i )
+                z( s.lo[0] + i, s.lo[1] + j, s.lo[2] + k ) = x( i + 1, j + 1, k + 1 );
+}
+
 // Cajita::ReferenceConjugateGradient::solve( b, x ) [Cajita-mem]  
 // driven from src/VelocityCorrector.hpp:276 with tol 1e-6 / max_iter 2000 (:103-104),
 // diagonal preconditioner (:166-179).  Absolute 2-norm stopping test.
@@ -594,13 +810,16 @@ int cg_solve( cfo_ctx& c )
 
     // z0 = M r0 ; p0 = z0 ; zTr
     do_gather( c, 2 );
+    const bool mgp = c.precond == 1; // opt-in multigrid V-cycle instead of the reference's diagonal M
+    if ( mgp )
+        mg_apply( c, r, z );
     acc_t zTr_acc( c.accum_exact );
 #pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : zTr_acc )
     for ( int k = s.lo[2]; k < s.hi[2]; ++k )
         for ( int j = s.lo[1]; j < s.hi[1]; ++j )
             for ( int i = s.lo[0]; i < s.hi[0]; ++i )
             {
-                double Mr = c.Mi[r.idx( i, j, k )] * r( i, j, k );
+                double Mr = mgp ? z( i, j, k ) : c.Mi[r.idx( i, j, k )] * r( i, j, k );
                 z( i, j, k ) = Mr;
                 p( i, j, k ) = Mr;
                 zTr_acc.add( Mr * r( i, j, k ) );
@@ -654,13 +873,15 @@ int cg_solve( cfo_ctx& c )
 
         // kernel 2: z = M r ; zTr
         do_gather( c, 2 );
+        if ( mgp )
+            mg_apply( c, r, z );
         zTr_acc = acc_t( c.accum_exact );
 #pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : zTr_acc )
         for ( int k = s.lo[2]; k < s.hi[2]; ++k )
             for ( int j = s.lo[1]; j < s.hi[1]; ++j )
                 for ( int i = s.lo[0]; i < s.hi[0]; ++i )
                 {
-                    double Mr = c.Mi[r.idx( i, j, k )] * r( i, j, k );
+                    double Mr = mgp ? z( i, j, k ) : c.Mi[r.idx( i, j, k )] * r( i, j, k );
                     z( i, j, k ) = Mr;
                     zTr_acc.add( Mr * r( i, j, k ) );
                 }
@@ -690,6 +911,37 @@ int cg_solve( cfo_ctx& c )
         pTAp = pTAp_acc.value();
         do_allreduce( c, &pTAp, 1 );
         zTr_old = zTr_new;
+    }
+    // Multigrid preconditioner on the singular (all-SOLID) operator: pin the null-space component of x
+    // to the one the diagonal preconditioner produces.  Jacobi-PCG from x0 = 0 keeps x in
+    // D^-1 range(A), i.e. sum_i d_i x_i = 0 (d = diagonal of A), whereas a V-cycle does not.  The
+    // constant is not arbitrary for the reference's results: quirk Q1 leaks it into v on the y walls
+    // (src/VelocityCorrector.hpp:260).  x -= (sum d_i x_i / sum d_i) restores it.
+    if ( mgp )
+    {
+        bool singular = true;
+        for ( int d = 0; d < c.D; ++d )
+            singular = singular && c.cfg.boundary_type[d] == CFB_SOLID && c.cfg.boundary_type[c.D + d] == CFB_SOLID;
+        if ( singular )
+        {
+            const MgLevel& L = c.mg->lv[0];
+            acc_t dx_acc( c.accum_exact ), d_acc( c.accum_exact );
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : dx_acc, d_acc )
+            for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+                for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                    for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                    {
+                        const double dg = L.diag[L.walls( i - s.lo[0], j - s.lo[1], k - s.lo[2] )];
+                        dx_acc.add( dg * x( i, j, k ) );
+                        d_acc.add( dg );
+                    }
+            const double shift = dx_acc.value() / d_acc.value();
+#pragma omp parallel for collapse( 2 ) schedule( static )
+            for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+                for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+                    for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                        x( i, j, k ) = x( i, j, k ) - shift;
+        }
     }
     c.cg_total += c.num_iter;
     if ( c.cfg.cg_print_level > 0 && c.cfg.world_rank == 0 )
@@ -894,6 +1146,8 @@ int cfo_create( const cfb_config* cfg, cfo_ctx** out )
 
 int cfo_destroy( cfo_ctx* c )
 {
+    if ( c )
+        delete c->mg;
     delete c;
     return CFB_OK;
 }
@@ -1131,6 +1385,33 @@ int cfo_reset_stats( cfo_ctx* c )
 int cfo_set_accumulation( cfo_ctx* c, int exact )
 {
     c->accum_exact = exact != 0;
+    return CFB_OK;
+}
+
+// Opt-in preconditioner of the product (cfb_set_preconditioner): kind 0 = the reference's diagonal,
+// 1 = multigrid V(nu_pre, nu_post) cycle with nu_coarse sweeps on the coarsest level; omega <= 0 picks
+// the default damping (6/7 in 3-D, 0.8 in 2-D).  Single block only.
+int cfo_set_preconditioner( cfo_ctx* c, int kind, int nu_pre, int nu_post, int nu_coarse, double omega )
+{
+    if ( kind != 0 && kind != 1 )
+    {
+        c->err = "unknown preconditioner";
+        return CFB_ERR_INVALID;
+    }
+    if ( kind == 1 && ( c->cfg.world_size > 1 || nu_pre < 1 || nu_post < 0 || nu_coarse < 1 || omega >= 2.0 ) )
+    {
+        c->err = "multigrid preconditioner: single block, nu_pre >= 1, nu_post >= 0, nu_coarse >= 1, omega < 2";
+        return CFB_ERR_INVALID;
+    }
+    c->precond = kind;
+    if ( kind == 1 )
+    {
+        c->mg_nu1 = nu_pre;
+        c->mg_nu2 = nu_post;
+        c->mg_nuc = nu_coarse;
+        c->mg_omega = omega;
+        mg_build( *c );
+    }
     return CFB_OK;
 }
 

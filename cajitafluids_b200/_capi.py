@@ -69,6 +69,7 @@ class Library:
         "set_output_dir": [C.c_void_p, C.c_char_p],
         "write_npy": [C.c_char_p, _dp, C.c_int, C.POINTER(C.c_int64)],
         "set_preconditioner": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double],
+        "mg_apply": [C.c_void_p, _dp, _dp],
         "abi_version": [],
     }
 
@@ -244,6 +245,15 @@ class Context:
         multigrid V(nu_pre, nu_post) cycle; omega <= 0: default damping)."""
         k = {"jacobi": K.PRECOND_JACOBI, "mg": K.PRECOND_MG}.get(kind, kind)
         self._call("set_preconditioner", int(k), int(nu_pre), int(nu_post), int(nu_coarse), C.c_double(omega))
+
+    def mg_apply(self, r):
+        """z = M^-1 r: one multigrid V-cycle on a dense owned-cell array."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        if r.shape != self.shape(K.PRESSURE):
+            raise ValueError(f"shape {r.shape} != {self.shape(K.PRESSURE)}")
+        z = np.empty_like(r)
+        self._call("mg_apply", r.ctypes.data_as(_dp), z.ctypes.data_as(_dp))
+        return z
 
     # -- output stage (SiloWriter::writeFile, src/SiloWriter.hpp:56-197)
     def output(self):

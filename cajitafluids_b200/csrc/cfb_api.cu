@@ -228,6 +228,8 @@ constexpr size_t STATE_HEAD = offsetof( CgState, hist );
 // Jacobi-PCG from x0 = 0 on the current RHS.  `fixed_iters` > 0: exactly that many iterations.
 int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
 {
+    if ( c->precond == CFB_PRECOND_MG )
+        return mg_pcg_solve( c, fixed_iters, num_iter, resid );
     const int fixed = fixed_iters > 0;
     const int max_it = fixed ? fixed_iters : c->cfg.cg_max_iter;
     long long launches = 0;
@@ -585,6 +587,7 @@ int cfb_destroy( cfb_ctx* c )
     if ( c->stream )
         cudaStreamSynchronize( c->stream );
     output_destroy( c ); // writes a pending output first
+    mg_destroy( c );
     halo_destroy( c );
     for ( int f = 0; f < 4; ++f )
         for ( int v = 0; v < 2; ++v )

@@ -95,6 +95,7 @@ struct PeerMail
 #define CFB_KTIMED 64
 
 struct OutputStage; // output.cu
+struct MgStage;     // mg.cu
 
 struct cfb_ctx
 {
@@ -186,6 +187,10 @@ struct cfb_ctx
 
     // output stage (output.cu), created on first use
     OutputStage* out = nullptr;
+
+    // opt-in multigrid preconditioner (mg.cu; cfb_set_preconditioner)
+    int precond = CFB_PRECOND_JACOBI;
+    MgStage* mg = nullptr;
 };
 
 extern std::string g_cfb_error;
@@ -270,6 +275,9 @@ int output_write( cfb_ctx* c, const char* dir, int time_step );
 int output_flush( cfb_ctx* c );
 const char* output_solve_dir( const cfb_ctx* c ); // directory set with cfb_set_output_dir, or nullptr
 void output_destroy( cfb_ctx* c );
+// mg.cu: the CG with z = V-cycle( r ) instead of z = D^-1 r
+int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid );
+void mg_destroy( cfb_ctx* c );
 // halo.cu
 int halo_init( cfb_ctx* c );
 void halo_destroy( cfb_ctx* c );

@@ -1,0 +1,615 @@
+// mg.cu — opt-in geometric multigrid preconditioner for the pressure CG.
+//
+// The reference's default path hands the pressure system to HYPRE (PCG + PFMG,
+// examples/advection.cpp:186-189, src/VelocityCorrector.hpp:324-338); its "Reference" path — the one
+// this library reproduces bit for bit — is Jacobi-PCG, whose iteration count grows like n (292 at
+// 64^3, 582 at 128^3, > 2000 at 512^3).  This file adds what PFMG is there for, behind
+// cfb_set_preconditioner( CFB_PRECOND_MG ): the same CG (same matrix, same absolute stopping test,
+// same exactly-accumulated dot products) with   z = M^-1 r := one V(nu1, nu2) cycle   instead of
+// z = D^-1 r.  It is NOT a restatement of HYPRE; the CPU checker (oracle/cfo_oracle.cpp: mg_*) states
+// the same algorithm operation for operation, so the two agree bit for bit, and the solution agrees
+// with the Jacobi path to the solver tolerance (tests/test_zz_multigrid.py).  Never the default:
+// north_star pins "same preconditioner as the reference" for the parity runs.
+//
+//   levels      : cell-centred 2:1 coarsening while every extent stays even and >= 2 after halving;
+//                 level l re-discretises the same 2*D+1-point operator (same wall logic) with
+//                 scale_l = scale_0 / 4^l
+//   smoother    : damped Jacobi  x += omega D^-1 (b - A x)  (first sweep from x = 0: x = omega D^-1 b),
+//                 ping-pong between two arrays per level
+//   restriction : mean of the 2^D children of the residual (residual fused into the kernel);
+//                 prolongation: piecewise constant, fused with the correction
+//   coarsest    : nuc Jacobi sweeps
+//   null space  : with all walls SOLID the operator is singular; x is shifted at the end so that
+//                 sum_i d_i x_i = 0, the component Jacobi-PCG produces (quirk Q1 of the reference leaks
+//                 that constant into v, src/VelocityCorrector.hpp:260)
+//
+// All kernels here are plain one-thread-per-cell streaming kernels (HBM-bound on the fine level,
+// launch-bound on the coarse ones); q = A p stays the TMA stencil kernel.  Bytes per fine cell and CG
+// iteration with V(2,2): smoother 16 + 3 * 24, residual + restriction 17, prolongation 17, z.r 16,
+// p-update 24, stencil 16, axpy 48 = 226 (+ 1/7 of the cycle for the coarse levels) against 72 for a
+// Jacobi iteration, for ~14 iterations instead of ~2500 at 512^3.
+#include "cfb_internal.h"
+#include "device_geo.cuh"
+#include "device_reduce.cuh"
+#include "device_tma.cuh"
+
+#include <cmath>
+
+namespace
+{
+
+constexpr int NT = 256;
+
+struct MgLevelDev
+{
+    int n[3];
+    int cz;             // coarsening factor to the next level along z (1 in 2-D)
+    int slo[3], shi[3]; // the low / high end of dim d is a SOLID physical wall
+    long long sy, sz, origin;
+    double ns;          // off-diagonal coefficient, -scale_l
+    double diag[8], wminv[8];
+};
+
+struct MgLevelHost
+{
+    MgLevelDev d;
+    double* b = nullptr;
+    double* x[2] = { nullptr, nullptr };
+    int cur = 0;
+    bool owns_b = false;
+    long long cells = 0;
+};
+
+} // namespace
+
+struct MgStage
+{
+    std::vector<MgLevelHost> lv;
+    int nu1 = 2, nu2 = 2, nuc = 8;
+    double omega = 0.0;
+    bool singular = false;
+    cudaEvent_t ev_poll = nullptr;
+};
+
+namespace
+{
+
+__device__ __forceinline__ int mg_walls( const MgLevelDev& L, int i, int j, int k )
+{
+    return ( i == 0 && L.slo[0] ) + ( i == L.n[0] - 1 && L.shi[0] ) + ( j == 0 && L.slo[1] ) +
+           ( j == L.n[1] - 1 && L.shi[1] ) + ( k == 0 && L.slo[2] ) + ( k == L.n[2] - 1 && L.shi[2] );
+}
+
+__device__ __forceinline__ long long mg_off( const MgLevelDev& L, int i, int j, int k )
+{
+    return L.origin + (long long)k * L.sz + (long long)j * L.sy + i;
+}
+
+__device__ __forceinline__ void mg_decode( const MgLevelDev& L, long long t, int& i, int& j, int& k )
+{
+    i = (int)( t % L.n[0] );
+    j = (int)( ( t / L.n[0] ) % L.n[1] );
+    k = (int)( t / ( (long long)L.n[0] * L.n[1] ) );
+}
+
+// (A x)(i,j,k): diag * x, then one fused multiply-add per neighbour in stencil order
+__device__ __forceinline__ double mg_Ax( const MgLevelDev& L, const double* __restrict__ x, long long o, int w )
+{
+    return apply_row( L.diag[w], L.ns, x[o], x[o - 1], x[o + 1], x[o - L.sy], x[o + L.sy], x[o - L.sz],
+                      x[o + L.sz] );
+}
+
+__global__ void __launch_bounds__( NT )
+    mg_smooth0_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b, double* __restrict__ x )
+{
+    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( L, t, i, j, k );
+        const long long o = mg_off( L, i, j, k );
+        x[o] = L.wminv[mg_walls( L, i, j, k )] * b[o];
+    }
+}
+
+__global__ void __launch_bounds__( NT )
+    mg_smooth_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b,
+                      const double* __restrict__ xi, double* __restrict__ xo )
+{
+    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( L, t, i, j, k );
+        const long long o = mg_off( L, i, j, k );
+        const int w = mg_walls( L, i, j, k );
+        const double res = b[o] - mg_Ax( L, xi, o, w );
+        xo[o] = fma( L.wminv[w], res, xi[o] );
+    }
+}
+
+__device__ __forceinline__ double mg_res( const MgLevelDev& F, const double* __restrict__ b,
+                                          const double* __restrict__ x, int i, int j, int k )
+{
+    const long long o = mg_off( F, i, j, k );
+    return b[o] - mg_Ax( F, x, o, mg_walls( F, i, j, k ) );
+}
+
+// coarse b = mean of the children's residuals, summed pairwise: x pairs, then y, then z
+__global__ void __launch_bounds__( NT )
+    mg_restrict_kernel( const __grid_constant__ MgLevelDev F, const __grid_constant__ MgLevelDev C,
+                        const double* __restrict__ bf, const double* __restrict__ xf, double* __restrict__ bc )
+{
+    const long long total = (long long)C.n[0] * C.n[1] * C.n[2];
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int I, J, K;
+        mg_decode( C, t, I, J, K );
+        const int i = 2 * I, j = 2 * J, k = F.cz * K;
+        double s = ( mg_res( F, bf, xf, i, j, k ) + mg_res( F, bf, xf, i + 1, j, k ) ) +
+                   ( mg_res( F, bf, xf, i, j + 1, k ) + mg_res( F, bf, xf, i + 1, j + 1, k ) );
+        if ( F.cz == 2 )
+        {
+            const double u = ( mg_res( F, bf, xf, i, j, k + 1 ) + mg_res( F, bf, xf, i + 1, j, k + 1 ) ) +
+                             ( mg_res( F, bf, xf, i, j + 1, k + 1 ) + mg_res( F, bf, xf, i + 1, j + 1, k + 1 ) );
+            s = ( s + u ) * 0.125;
+        }
+        else
+            s = s * 0.25;
+        bc[mg_off( C, I, J, K )] = s;
+    }
+}
+
+__global__ void __launch_bounds__( NT )
+    mg_prolong_kernel( const __grid_constant__ MgLevelDev F, const __grid_constant__ MgLevelDev C,
+                       double* __restrict__ xf, const double* __restrict__ ec )
+{
+    const long long total = (long long)F.n[0] * F.n[1] * F.n[2];
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( F, t, i, j, k );
+        const long long o = mg_off( F, i, j, k );
+        xf[o] = xf[o] + ec[mg_off( C, i / 2, j / 2, k / F.cz )];
+    }
+}
+
+// ---- the CG around it (Cajita::ReferenceConjugateGradient::solve with a general M^-1) ---------------
+// start of solve: x0 = 0, r0 = b, sum r0^2
+__global__ void __launch_bounds__( NT )
+    mgcg_init_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b, double* __restrict__ x,
+                      double* __restrict__ r, CgState* S, double* partials, int fixed )
+{
+    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+    dd_t rr = { 0.0, 0.0 };
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( L, t, i, j, k );
+        const long long o = mg_off( L, i, j, k );
+        const double bv = b[o];
+        x[o] = 0.0;
+        r[o] = bv;
+        dd_acc( rr, bv * bv );
+    }
+    dd_t vals[1] = { rr };
+    if ( block_reduce_finalize<NT, 1>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
+    {
+        if ( threadIdx.x == 0 )
+        {
+            S->rr = vals[0].hi + vals[0].lo;
+            S->iter = 0;
+            S->done = 0;
+            S->fixed = fixed;
+        }
+    }
+}
+
+__global__ void mgcg_check0_kernel( CgState* S, double tol, int stop_rel )
+{
+    const double bnorm = sqrt( S->rr );
+    S->bnorm = bnorm;
+    S->thresh = stop_rel ? tol * bnorm : tol;
+    if ( !S->fixed && bnorm <= S->thresh )
+        S->done = 1;
+}
+
+// kernel 2's reduction: sum z.r
+__global__ void __launch_bounds__( NT )
+    mgcg_dot_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ z,
+                     const double* __restrict__ r, CgState* S, double* partials )
+{
+    if ( S->done )
+        return;
+    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+    dd_t rz = { 0.0, 0.0 };
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( L, t, i, j, k );
+        const long long o = mg_off( L, i, j, k );
+        dd_acc( rz, z[o] * r[o] );
+    }
+    dd_t vals[1] = { rz };
+    if ( block_reduce_finalize<NT, 1>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
+    {
+        if ( threadIdx.x == 0 )
+            S->rz_new = vals[0].hi + vals[0].lo;
+    }
+}
+
+// kernel 3: p = z + beta p   (first: p0 = z0); the stencil kernel that follows sets rz_old = rz_new
+__global__ void __launch_bounds__( NT )
+    mgcg_pupdate_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ z, double* __restrict__ p,
+                         const CgState* S, int first )
+{
+    if ( S->done )
+        return;
+    const double beta = first ? 0.0 : S->rz_new / S->rz_old;
+    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( L, t, i, j, k );
+        const long long o = mg_off( L, i, j, k );
+        p[o] = first ? z[o] : fma( beta, p[o], z[o] );
+    }
+}
+
+// kernel 1: x += alpha p, r -= alpha q, sum r^2, then the iteration's bookkeeping and stopping test
+__global__ void __launch_bounds__( NT )
+    mgcg_axpy_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ p,
+                      const double* __restrict__ q, double* __restrict__ x, double* __restrict__ r, CgState* S,
+                      double* partials )
+{
+    if ( S->done )
+        return;
+    const double alpha = S->rz_old / S->pAp;
+    const double nalpha = -alpha;
+    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+    dd_t rr = { 0.0, 0.0 };
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( L, t, i, j, k );
+        const long long o = mg_off( L, i, j, k );
+        x[o] = fma( alpha, p[o], x[o] );
+        const double rv = fma( nalpha, q[o], r[o] );
+        r[o] = rv;
+        dd_acc( rr, rv * rv );
+    }
+    dd_t vals[1] = { rr };
+    if ( block_reduce_finalize<NT, 1>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
+    {
+        if ( threadIdx.x == 0 )
+        {
+            const double rrv = vals[0].hi + vals[0].lo;
+            S->rr = rrv;
+            const double resid = sqrt( rrv );
+            const int it = S->iter;
+            if ( it < CFB_HIST_MAX )
+                S->hist[it] = resid;
+            S->iter = it + 1;
+            if ( !S->fixed && resid <= S->thresh )
+                S->done = 1;
+        }
+    }
+}
+
+// null-space pinning: sum d_i x_i and sum d_i -> S->gath[0..1]
+__global__ void __launch_bounds__( NT )
+    mgcg_nullsum_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ x, CgState* S,
+                         double* partials )
+{
+    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+    dd_t dx = { 0.0, 0.0 }, ds = { 0.0, 0.0 };
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( L, t, i, j, k );
+        const double dg = L.diag[mg_walls( L, i, j, k )];
+        dd_acc( dx, dg * x[mg_off( L, i, j, k )] );
+        dd_acc( ds, dg );
+    }
+    dd_t vals[2] = { dx, ds };
+    if ( block_reduce_finalize<NT, 2>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
+    {
+        if ( threadIdx.x == 0 )
+        {
+            S->gath[0] = vals[0].hi + vals[0].lo;
+            S->gath[1] = vals[1].hi + vals[1].lo;
+        }
+    }
+}
+
+__global__ void __launch_bounds__( NT )
+    mgcg_shift_kernel( const __grid_constant__ MgLevelDev L, double* __restrict__ x, const CgState* S )
+{
+    const double shift = S->gath[0] / S->gath[1];
+    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( L, t, i, j, k );
+        const long long o = mg_off( L, i, j, k );
+        x[o] = x[o] - shift;
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+inline int grid_for( const cfb_ctx* c, long long cells )
+{
+    long long b = ( cells + NT - 1 ) / NT;
+    long long cap = (long long)c->sm_count * 8;
+    if ( cap > CFB_MAX_PARTIALS )
+        cap = CFB_MAX_PARTIALS;
+    return (int)( b < 1 ? 1 : ( b > cap ? cap : b ) );
+}
+
+void mg_free( cfb_ctx* c )
+{
+    MgStage* m = c->mg;
+    if ( !m )
+        return;
+    for ( auto& L : m->lv )
+    {
+        if ( L.owns_b && L.b )
+            cudaFree( L.b );
+        for ( double* p : L.x )
+            if ( p )
+                cudaFree( p );
+    }
+    if ( m->ev_poll )
+        cudaEventDestroy( m->ev_poll );
+    delete m;
+    c->mg = nullptr;
+}
+
+int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega )
+{
+    mg_free( c );
+    MgStage* m = new MgStage();
+    c->mg = m;
+    m->nu1 = nu1;
+    m->nu2 = nu2;
+    m->nuc = nuc;
+    const Geo& g = c->g;
+    const int D = g.D;
+    m->omega = omega > 0.0 ? omega : ( D == 3 ? 6.0 / 7.0 : 0.8 );
+    m->singular = true;
+    for ( int d = 0; d < D; ++d )
+        m->singular = m->singular && g.bt[d] == CFB_SOLID && g.bt[3 + d] == CFB_SOLID;
+    CFB_CUDA( c, cudaEventCreateWithFlags( &m->ev_poll, cudaEventDisableTiming ) );
+    int n[3] = { g.n[0], g.n[1], D == 3 ? g.n[2] : 1 };
+    double scale = c->op.scale;
+    for ( int l = 0; l < 16; ++l )
+    {
+        m->lv.emplace_back();
+        MgLevelHost& H = m->lv.back();
+        MgLevelDev& L = H.d;
+        for ( int d = 0; d < 3; ++d )
+        {
+            L.n[d] = n[d];
+            L.slo[d] = d < D ? ( g.lo_bd[d] && g.bt[d] == CFB_SOLID ) : 1;
+            L.shi[d] = d < D ? ( g.hi_bd[d] && g.bt[3 + d] == CFB_SOLID ) : 1;
+        }
+        L.cz = D == 3 ? 2 : 1;
+        L.ns = -1.0 * scale;
+        for ( int cnt = 0; cnt < 8; ++cnt )
+        {
+            // the reference's own sequence (src/VelocityCorrector.hpp:137, BoundaryConditions.hpp:56-97); in
+            // 2-D the two z walls of the single plane are part of the count (see Geo)
+            double dgl;
+            if ( D == 3 )
+            {
+                dgl = 6.0 * scale;
+                for ( int i = 0; i < cnt; ++i )
+                    dgl -= scale;
+            }
+            else
+            {
+                dgl = 4.0 * scale;
+                for ( int i = 0; i < cnt - 2; ++i )
+                    dgl -= scale;
+            }
+            L.diag[cnt] = dgl;
+            L.wminv[cnt] = m->omega * ( 1.0 / dgl );
+        }
+        H.cells = (long long)n[0] * n[1] * n[2];
+        size_t elems;
+        if ( l == 0 )
+        {
+            // the fine level lives in the layout of the CG vectors: b is the residual itself
+            L.sy = g.sy;
+            L.sz = g.sz;
+            L.origin = g.origin;
+            elems = (size_t)g.total;
+            H.b = nullptr; // bound per solve to cg_r
+        }
+        else
+        {
+            L.sy = n[0] + 2;
+            L.sz = L.sy * ( n[1] + 2 );
+            L.origin = L.sz + L.sy + 1;
+            elems = (size_t)L.sz * ( n[2] + 2 );
+            CFB_CUDA( c, cudaMalloc( &H.b, elems * sizeof( double ) ) );
+            CFB_CUDA( c, cudaMemsetAsync( H.b, 0, elems * sizeof( double ), c->stream ) );
+            H.owns_b = true;
+        }
+        for ( int q = 0; q < 2; ++q )
+        {
+            // ghosts are never written: they stay zero, which is what the operator reads off the domain
+            CFB_CUDA( c, cudaMalloc( &H.x[q], elems * sizeof( double ) ) );
+            CFB_CUDA( c, cudaMemsetAsync( H.x[q], 0, elems * sizeof( double ), c->stream ) );
+        }
+        bool can = true;
+        for ( int d = 0; d < D; ++d )
+            can = can && n[d] % 2 == 0 && n[d] / 2 >= 2;
+        if ( !can )
+            break;
+        for ( int d = 0; d < D; ++d )
+            n[d] /= 2;
+        scale = scale * 0.25;
+    }
+    CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    return CFB_OK;
+}
+
+int launch_smooth0( cfb_ctx* c, MgLevelHost& H )
+{
+    mg_smooth0_kernel<<<grid_for( c, H.cells ), NT, 0, c->stream>>>( H.d, H.b, H.x[0] );
+    H.cur = 0;
+    return 1;
+}
+
+int launch_smooth( cfb_ctx* c, MgLevelHost& H )
+{
+    mg_smooth_kernel<<<grid_for( c, H.cells ), NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur] );
+    H.cur = 1 - H.cur;
+    return 1;
+}
+
+int vcycle( cfb_ctx* c, int l )
+{
+    MgStage* m = c->mg;
+    MgLevelHost& H = m->lv[l];
+    const bool last = l + 1 == (int)m->lv.size();
+    int n = launch_smooth0( c, H );
+    for ( int s = 1; s < ( last ? m->nuc : m->nu1 ); ++s )
+        n += launch_smooth( c, H );
+    if ( last )
+        return n;
+    MgLevelHost& C = m->lv[l + 1];
+    mg_restrict_kernel<<<grid_for( c, C.cells ), NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.b );
+    n += 1;
+    n += vcycle( c, l + 1 );
+    mg_prolong_kernel<<<grid_for( c, H.cells ), NT, 0, c->stream>>>( H.d, C.d, H.x[H.cur], C.x[C.cur] );
+    n += 1;
+    for ( int s = 0; s < m->nu2; ++s )
+        n += launch_smooth( c, H );
+    return n;
+}
+
+} // namespace
+
+void mg_destroy( cfb_ctx* c ) { mg_free( c ); }
+
+// Cajita::ReferenceConjugateGradient::solve( b, x ) from x0 = 0 with z = V-cycle( r ).
+int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
+{
+    MgStage* m = c->mg;
+    if ( !m )
+        return cfb_fail( c, CFB_ERR_INVALID, "multigrid preconditioner not set up" );
+    const int fixed = fixed_iters > 0;
+    const int max_it = fixed ? fixed_iters : c->cfg.cg_max_iter;
+    CgState* S = c->d_state;
+    MgLevelHost& F = m->lv[0];
+    F.b = c->cg_r;
+    const MgLevelDev& L = F.d;
+    const int grid = grid_for( c, F.cells );
+    const size_t head = offsetof( CgState, hist );
+    long long launches = 0;
+
+    mgcg_init_kernel<<<grid, NT, 0, c->stream>>>( L, c->rhs, c->lhs, c->cg_r, S, c->d_partials, fixed );
+    mgcg_check0_kernel<<<1, 1, 0, c->stream>>>( S, c->cfg.cg_tolerance, c->cfg.cg_stop_rule == CFB_STOP_REL );
+    launches += 2;
+
+    int enq = 0;
+    bool done = false, pending = false;
+    while ( enq < max_it && !done )
+    {
+        // one iteration: z = M^-1 r ; z.r ; p = z + beta p ; q = A p, p.q ; x, r, r.r, stopping test
+        launches += vcycle( c, 0 );
+        const double* z = F.x[F.cur];
+        mgcg_dot_kernel<<<grid, NT, 0, c->stream>>>( L, z, c->cg_r, S, c->d_partials );
+        mgcg_pupdate_kernel<<<grid, NT, 0, c->stream>>>( L, z, c->cg_p, S, enq == 0 ? 1 : 0 );
+        launches += 2;
+        launches += launch_stencil_dot( c );
+        mgcg_axpy_kernel<<<grid, NT, 0, c->stream>>>( L, c->cg_p, c->cg_q, c->lhs, c->cg_r, S, c->d_partials );
+        launches += 1;
+        ++enq;
+        if ( fixed )
+            continue;
+        // the state after iteration enq - 1 is looked at while iteration enq is already queued
+        if ( pending )
+        {
+            CFB_CUDA( c, cudaEventSynchronize( m->ev_poll ) );
+            done = c->h_state->done != 0;
+            pending = false;
+        }
+        if ( !done )
+        {
+            CFB_CUDA( c, cudaMemcpyAsync( c->h_state, S, head, cudaMemcpyDeviceToHost, c->stream ) );
+            CFB_CUDA( c, cudaEventRecord( m->ev_poll, c->stream ) );
+            pending = true;
+        }
+    }
+    if ( m->singular )
+    {
+        mgcg_nullsum_kernel<<<grid, NT, 0, c->stream>>>( L, c->lhs, S, c->d_partials );
+        mgcg_shift_kernel<<<grid, NT, 0, c->stream>>>( L, c->lhs, S );
+        launches += 2;
+    }
+    CFB_CUDA( c, cudaMemcpyAsync( c->h_state, S, head, cudaMemcpyDeviceToHost, c->stream ) );
+    CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    cudaError_t e = cudaGetLastError();
+    if ( e != cudaSuccess )
+        return cfb_fail( c, CFB_ERR_CUDA, std::string( "mg_pcg_solve: " ) + cudaGetErrorString( e ) );
+    c->stats.kernel_launches += launches;
+    c->last_iters = c->h_state->iter;
+    c->last_resid = std::sqrt( c->h_state->rr );
+    c->stats.cg_iterations += c->last_iters;
+    if ( num_iter )
+        *num_iter = c->last_iters;
+    if ( resid )
+        *resid = c->last_resid;
+    if ( c->cfg.cg_print_level > 0 && c->cfg.world_rank == 0 )
+        std::printf( "Cajita CG Finished in %d iterations, |r|_2 = %g\n", c->last_iters, c->last_resid );
+    if ( !fixed && !c->h_state->done )
+        return cfb_fail( c, CFB_ERR_NOT_CONVERGED, "Cajita CG solver did not converge" );
+    return CFB_OK;
+}
+
+extern "C" int cfb_set_preconditioner( cfb_ctx* c, int kind, int nu_pre, int nu_post, int nu_coarse, double omega )
+{
+    if ( kind != CFB_PRECOND_JACOBI && kind != CFB_PRECOND_MG )
+        return cfb_fail( c, CFB_ERR_INVALID, "unknown preconditioner" );
+    if ( kind == CFB_PRECOND_JACOBI )
+    {
+        c->precond = CFB_PRECOND_JACOBI;
+        return CFB_OK;
+    }
+    if ( c->cfg.world_size > 1 || nu_pre < 1 || nu_post < 0 || nu_coarse < 1 || omega >= 2.0 )
+        return cfb_fail( c, CFB_ERR_INVALID,
+                         "multigrid preconditioner: single block, nu_pre >= 1, nu_post >= 0, nu_coarse >= 1, omega < 2" );
+    int rc = mg_build( c, nu_pre, nu_post, nu_coarse, omega );
+    if ( rc )
+        return rc;
+    c->precond = CFB_PRECOND_MG;
+    return CFB_OK;
+}
+
+// z = M^-1 r for dense owned-cell host arrays: one V-cycle on its own (introspection / tests).
+// Uses the CG work vector r as the fine-level right-hand side.
+extern "C" int cfb_mg_apply( cfb_ctx* c, const double* r_host, double* z_host )
+{
+    MgStage* m = c->mg;
+    if ( c->precond != CFB_PRECOND_MG || !m )
+        return cfb_fail( c, CFB_ERR_INVALID, "multigrid preconditioner not set" );
+    int rc = cfb_upload( c, CFB_CG_R, CFB_CURRENT, CFB_OWNED, r_host );
+    if ( rc )
+        return rc;
+    MgLevelHost& F = m->lv[0];
+    F.b = c->cg_r;
+    c->stats.kernel_launches += vcycle( c, 0 );
+    const Geo& g = c->g;
+    const double* z = F.x[F.cur] + g.origin;
+    cudaMemcpy3DParms p{};
+    p.srcPtr = make_cudaPitchedPtr( const_cast<double*>( z ), (size_t)g.sy * 8, (size_t)g.sy, (size_t)g.ay );
+    p.dstPtr = make_cudaPitchedPtr( z_host, (size_t)g.n[0] * 8, (size_t)g.n[0], (size_t)g.n[1] );
+    p.extent = make_cudaExtent( (size_t)g.n[0] * 8, (size_t)g.n[1], (size_t)g.n[2] );
+    p.kind = cudaMemcpyDeviceToHost;
+    CFB_CUDA( c, cudaMemcpy3DAsync( &p, c->stream ) );
+    CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    return CFB_OK;
+}

@@ -82,7 +82,9 @@ void usage( const char* prog )
               << "  -g, --gravity G          gravity along -y (default 0)\n"
               << "  -p, --driver NAME        b200 (only backend)\n"
               << "  -m, --matrix-solver S    Reference (only solver; HYPRE names are rejected)\n"
-              << "  -c, --preconditioner P   ignored by the Reference solver (Jacobi is built in)\n"
+              << "  -c, --preconditioner P   None/Jacobi/Diagonal: the Reference solver's built-in Jacobi (default);\n"
+              << "                           MG: opt-in geometric multigrid V(2,2) cycle (same system, same\n"
+              << "                           stopping test, O(10) CG iterations instead of O(n))\n"
               << "  -x/-y/-z, -w/-h/-e       inflow box corner and extent\n"
               << "  -q, -u, -v               inflow quantity and velocity\n"
               << "  -D, --dim 2|3            space dimension (default 2, like the reference)\n"

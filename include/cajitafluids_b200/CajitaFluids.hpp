@@ -553,7 +553,8 @@ class Solver : public SolverBase
             const std::string& matrix_solver, const std::string& preconditioner, int device_id = -1 )
         : _bc( bc )
     {
-        (void)preconditioner; // the Reference path always builds its Jacobi preconditioner itself
+        // the Reference path always builds its Jacobi preconditioner itself (the reference ignores the
+        // preconditioner string there); "MG" is this backend's opt-in multigrid V-cycle (cfb_set_preconditioner)
         if ( matrix_solver != "Reference" )
             throw std::runtime_error( "cajitafluids_b200 implements only the 'Reference' matrix solver "
                                       "(HYPRE is out of scope)" );
@@ -596,6 +597,8 @@ class Solver : public SolverBase
         _bc.max = Mesh<NumSpaceDim>( _h ).maxDomainGlobalCellIndex();
         _pm = std::make_shared<pm_type>( _h );
         _pm->initialize( create_functor );
+        if ( preconditioner == "MG" )
+            detail::check( cfb_set_preconditioner( _h->ctx, CFB_PRECOND_MG, 2, 2, 8, 0.0 ), _h->ctx );
         auto cg = std::make_shared<B200ConjugateGradient>( _h );
         _vc = std::make_shared<VelocityCorrector<NumSpaceDim>>( _h, cg );
         _silo = std::make_shared<SiloWriter<NumSpaceDim>>( _h ); // src/Solver.hpp:121-122

@@ -93,6 +93,15 @@ enum
     CFB_STOP_REL = 1 /* sqrt(sum r^2) <= tol * sqrt(sum b^2); extension, never default */
 };
 
+/* Preconditioner of the CG.  The reference's "Reference" solver always uses the diagonal one
+ * (src/VelocityCorrector.hpp:166-179); MG is this library's opt-in extension in the role HYPRE PFMG
+ * plays in the reference's default path (examples/advection.cpp:186-189). */
+enum
+{
+    CFB_PRECOND_JACOBI = 0,
+    CFB_PRECOND_MG = 1
+};
+
 /* Plain-data mirror of everything createSolver(...) receives
  * (src/Solver.hpp:283-293, examples/advection.cpp:438-459). */
 typedef struct cfb_config
@@ -298,6 +307,17 @@ int cfb_set_tuning( cfb_ctx* ctx, const char* key, int value );
 /* ReferenceConjugateGradient::setTolerance / setMaxIter / setPrintLevel
  * (src/VelocityCorrector.hpp:103-105) after construction. */
 int cfb_set_cg_params( cfb_ctx* ctx, double tolerance, int max_iter, int print_level );
+
+/* Choose the CG preconditioner (default CFB_PRECOND_JACOBI == the reference).  CFB_PRECOND_MG: one
+ * geometric multigrid V(nu_pre, nu_post) cycle per CG iteration (damped-Jacobi smoother with damping
+ * `omega`, <= 0 picks 6/7 in 3-D and 0.8 in 2-D; nu_coarse sweeps on the coarsest level; 2:1 cell-centred
+ * coarsening while all extents stay even).  Same matrix, same stopping test, same solution to the
+ * solver tolerance, O(10) iterations instead of O(n).  Single block (world_size == 1) for now. */
+int cfb_set_preconditioner( cfb_ctx* ctx, int kind, int nu_pre, int nu_post, int nu_coarse, double omega );
+
+/* One application of the multigrid preconditioner on its own, z = M^-1 r, for dense owned-cell HOST
+ * arrays (introspection / tests; overwrites the CG work vector r). */
+int cfb_mg_apply( cfb_ctx* ctx, const double* r_host, double* z_host );
 
 int cfb_abi_version( void );
 

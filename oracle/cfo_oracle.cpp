@@ -1415,6 +1415,29 @@ int cfo_set_preconditioner( cfo_ctx* c, int kind, int nu_pre, int nu_post, int n
     return CFB_OK;
 }
 
+// z = M^-1 r for dense owned-cell host arrays: one V-cycle on its own (introspection / tests)
+int cfo_mg_apply( cfo_ctx* c, const double* r_host, double* z_host )
+{
+    if ( c->precond != 1 || !c->mg )
+    {
+        c->err = "multigrid preconditioner not set";
+        return CFB_ERR_INVALID;
+    }
+    const Space s = own_space( *c, 0 );
+    const int ex = s.hi[0] - s.lo[0], ey = s.hi[1] - s.lo[1];
+    Arr &r = c->cg_r, &z = c->cg_z;
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                r( i, j, k ) = r_host[( (size_t)( k - s.lo[2] ) * ey + ( j - s.lo[1] ) ) * ex + ( i - s.lo[0] )];
+    mg_apply( *c, r, z );
+    for ( int k = s.lo[2]; k < s.hi[2]; ++k )
+        for ( int j = s.lo[1]; j < s.hi[1]; ++j )
+            for ( int i = s.lo[0]; i < s.hi[0]; ++i )
+                z_host[( (size_t)( k - s.lo[2] ) * ey + ( j - s.lo[1] ) ) * ex + ( i - s.lo[0] )] = z( i, j, k );
+    return CFB_OK;
+}
+
 int cfo_num_threads( void )
 {
 #ifdef _OPENMP

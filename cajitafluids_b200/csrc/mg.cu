@@ -6,7 +6,7 @@
 // 64^3, 582 at 128^3, > 2000 at 512^3).  This file adds what PFMG is there for, behind
 // cfb_set_preconditioner( CFB_PRECOND_MG ): the same CG (same matrix, same absolute stopping test,
 // same exactly-accumulated dot products) with   z = M^-1 r := one V(nu1, nu2) cycle   instead of
-// z = D^-1 r.  It is NOT a restatement of HYPRE; the CPU checker (oracle/cfo_oracle.cpp: mg_*) states
+// z = D^-1 r.  It is NOT a restatement of HYPRE; the CPU checker (the mg_* functions under oracle/) states
 // the same algorithm operation for operation, so the two agree bit for bit, and the solution agrees
 // with the Jacobi path to the solver tolerance (tests/test_zz_multigrid.py).  Never the default:
 // north_star pins "same preconditioner as the reference" for the parity runs.

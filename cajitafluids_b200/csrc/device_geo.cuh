@@ -157,3 +157,19 @@ __device__ __forceinline__ void interp_velocity( const Geo& g, const double* con
     for ( int d = 0; d < D; ++d )
         out[d] = interp_field<D, 1>( g, 1 + d, vel[1 + d], loc );
 }
+
+// ---- the 7-point row of A, in the reference's stencil order ---------------------------------
+// {0}, {-x}, {+x}, {-y}, {+y}, {-z}, {+z}; one fused multiply-add per term (bit-identical to the
+// checker's apply_A).
+__device__ __forceinline__ double apply_row( double diag, double ns, double c, double xm, double xp,
+                                             double ym, double yp, double zm, double zp )
+{
+    double a = diag * c;
+    a = fma( ns, xm, a );
+    a = fma( ns, xp, a );
+    a = fma( ns, ym, a );
+    a = fma( ns, yp, a );
+    a = fma( ns, zm, a );
+    a = fma( ns, zp, a );
+    return a;
+}

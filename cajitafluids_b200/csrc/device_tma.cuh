@@ -61,19 +61,3 @@ __device__ __forceinline__ void prefetch_tmap( const CUtensorMap* map )
     asm volatile( "prefetch.tensormap [%0];" ::"l"( map ) : "memory" );
 }
 
-// ---- the 7-point row of A, in the reference's stencil order ---------------------------------
-// {0}, {-x}, {+x}, {-y}, {+y}, {-z}, {+z}; one fused multiply-add per term (bit-identical to the
-// checker's apply_A).
-__device__ __forceinline__ double apply_row( double diag, double ns, double c, double xm, double xp,
-                                             double ym, double yp, double zm, double zp )
-{
-    double a = diag * c;
-    a = fma( ns, xm, a );
-    a = fma( ns, xp, a );
-    a = fma( ns, ym, a );
-    a = fma( ns, yp, a );
-    a = fma( ns, zm, a );
-    a = fma( ns, zp, a );
-    return a;
-}
-

@@ -31,7 +31,6 @@
 #include "cfb_internal.h"
 #include "device_geo.cuh"
 #include "device_reduce.cuh"
-#include "device_tma.cuh"
 
 #include <cmath>
 

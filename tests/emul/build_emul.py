@@ -1,0 +1,113 @@
+"""tests/emul/build_emul.py — builds tests/emul/_build/libcfb_emul.so: the product's plain streaming
+kernels and host orchestration compiled as ordinary C++ (see cuda_runtime.h in this directory).
+
+The .cu sources are taken from cajitafluids_b200/csrc as they are; the only rewrite is the launch
+syntax  kernel<<<grid, block, smem, stream>>>( args )  ->  cfb_emul::launch( grid, block, [&]{ kernel( args ); } ).
+"""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "cajitafluids_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libcfb_emul.so")
+SOURCES = ["cfb_api.cu", "kernels_fields.cu", "kernels_cg.cu", "mg.cu", "output.cu"]
+HEADERS = ["cfb_internal.h", "device_geo.cuh"]
+STANDINS = ["cuda_runtime.h", "cuda.h", "device_reduce.cuh", "emul_glue.cpp"]
+
+
+def _match(s, i, open_c, close_c):
+    """index just after the bracket that closes the one at s[i]."""
+    depth = 0
+    while i < len(s):
+        if s[i] == open_c:
+            depth += 1
+        elif s[i] == close_c:
+            depth -= 1
+            if depth == 0:
+                return i + 1
+        i += 1
+    raise ValueError("unbalanced")
+
+
+def _split_top(s):
+    parts, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    parts.append(cur)
+    return [p.strip() for p in parts]
+
+
+def rewrite_launches(src):
+    out, pos = "", 0
+    while True:
+        i = src.find("<<<", pos)
+        if i < 0:
+            return out + src[pos:]
+        # kernel expression: identifier, optionally followed by a template argument list
+        k = i
+        if src[k - 1] == ">":
+            depth, k = 0, k - 1
+            while True:
+                if src[k] == ">":
+                    depth += 1
+                elif src[k] == "<":
+                    depth -= 1
+                    if depth == 0:
+                        break
+                k -= 1
+        m = re.search(r"[A-Za-z_][A-Za-z_0-9:]*$", src[:k])
+        start = m.start()
+        kernel = src[start:i]
+        j = src.find(">>>", i)
+        cfg = _split_top(src[i + 3:j])
+        a0 = src.index("(", j)
+        a1 = _match(src, a0, "(", ")")
+        args = src[a0 + 1:a1 - 1]
+        out += src[pos:start] + (f"cfb_emul::launch( dim3( {cfg[0]} ), dim3( {cfg[1]} ), [&]() {{ {kernel}( {args} ); }} )")
+        pos = a1
+
+
+def build(force=False):
+    os.makedirs(OUT, exist_ok=True)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, f) for f in STANDINS] + \
+           [os.path.join(ROOT, "include", "cfb.h"), os.path.abspath(__file__)]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
+        return LIB
+    cpp = []
+    for f in SOURCES:
+        src = rewrite_launches(open(os.path.join(CSRC, f)).read())
+        dst = os.path.join(OUT, f.replace(".cu", "_emul.cpp"))
+        open(dst, "w").write(src)
+        cpp.append(dst)
+    for f in HEADERS:
+        txt = open(os.path.join(CSRC, f)).read().replace('#include "../../include/cfb.h"',
+                                                         f'#include "{os.path.join(ROOT, "include", "cfb.h")}"')
+        open(os.path.join(OUT, f), "w").write(txt)
+    for f in STANDINS:
+        open(os.path.join(OUT, f), "w").write(open(os.path.join(HERE, f)).read())
+    cpp.append(os.path.join(OUT, "emul_glue.cpp"))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    # -ffp-contract=off: like nvcc -fmad=false, only the explicit fma() calls fuse
+    cmd = [cxx, "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+           "-I", OUT, "-o", LIB] + cpp
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout + p.stderr)
+        raise RuntimeError("emulation build failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True))

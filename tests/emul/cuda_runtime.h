@@ -1,0 +1,180 @@
+// cuda_runtime.h — HOST STAND-IN for the CUDA runtime, used ONLY by tests/emul (see README there).
+//
+// The product's plain streaming kernels (no TMA, no shared memory beyond the reduction helper) are
+// compiled as ordinary C++ and executed one CUDA thread after the other, so that their LOGIC — index
+// arithmetic, statement order, host-side orchestration — can be checked bit for bit against the CPU
+// oracle in a container without a GPU.  This is test infrastructure: nothing under cajitafluids_b200/
+// builds, loads or ships it, and nothing measured ever runs through it.
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+
+#define CFB_HOST_EMUL 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__( ... )
+#define __grid_constant__
+#define __shared__ static
+
+struct uint3
+{
+    unsigned x, y, z;
+};
+struct dim3
+{
+    unsigned x = 1, y = 1, z = 1;
+    dim3() {}
+    dim3( unsigned a, unsigned b = 1, unsigned c = 1 ) : x( a ), y( b ), z( c ) {}
+    dim3( int a ) : x( (unsigned)a ) {}
+    dim3( long long a ) : x( (unsigned)a ) {}
+};
+struct double2
+{
+    double x, y;
+};
+inline double2 make_double2( double a, double b ) { return double2{ a, b }; }
+
+namespace cfb_emul
+{
+extern thread_local uint3 g_threadIdx, g_blockIdx;
+extern thread_local dim3 g_blockDim, g_gridDim;
+// blocks in order; inside a block the threads run one after the other from the LAST to the first, so
+// that thread 0 — the one that finalises block reductions — sees every other thread's contribution
+void launch( dim3 grid, dim3 block, const std::function<void()>& body );
+} // namespace cfb_emul
+#define threadIdx cfb_emul::g_threadIdx
+#define blockIdx cfb_emul::g_blockIdx
+#define blockDim cfb_emul::g_blockDim
+#define gridDim cfb_emul::g_gridDim
+
+template <class T>
+inline T __ldg( const T* p ) { return *p; }
+template <class T>
+inline T __ldcg( const T* p ) { return *p; }
+inline void __syncthreads() {}
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline unsigned atomicAdd( unsigned* p, unsigned v )
+{
+    unsigned o = *p;
+    *p = o + v;
+    return o;
+}
+
+// ---- runtime API (everything is synchronous host memory) ---------------------------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorEmul = 1 };
+typedef struct cfb_emul_stream* cudaStream_t;
+typedef struct cfb_emul_event* cudaEvent_t;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+struct cudaDeviceProp
+{
+    int major = 10, minor = 0, multiProcessorCount = 2;
+};
+struct cudaPitchedPtr
+{
+    void* ptr;
+    size_t pitch, xsize, ysize;
+};
+struct cudaExtent
+{
+    size_t width, height, depth;
+};
+struct cudaMemcpy3DParms
+{
+    cudaPitchedPtr srcPtr{}, dstPtr{};
+    cudaExtent extent{};
+    cudaMemcpyKind kind = cudaMemcpyHostToHost;
+};
+inline cudaPitchedPtr make_cudaPitchedPtr( void* p, size_t pitch, size_t xs, size_t ys ) { return { p, pitch, xs, ys }; }
+inline cudaExtent make_cudaExtent( size_t w, size_t h, size_t d ) { return { w, h, d }; }
+
+inline const char* cudaGetErrorString( cudaError_t ) { return "emulated CUDA error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount( int* n )
+{
+    *n = 1;
+    return cudaSuccess;
+}
+inline cudaError_t cudaGetDeviceProperties( cudaDeviceProp* p, int )
+{
+    *p = cudaDeviceProp();
+    return cudaSuccess;
+}
+inline cudaError_t cudaSetDevice( int ) { return cudaSuccess; }
+template <class T>
+inline cudaError_t cudaMalloc( T** p, size_t bytes )
+{
+    *p = static_cast<T*>( std::malloc( bytes ? bytes : 1 ) );
+    return *p ? cudaSuccess : cudaErrorEmul;
+}
+template <class T>
+inline cudaError_t cudaMallocHost( T** p, size_t bytes ) { return cudaMalloc( p, bytes ); }
+inline cudaError_t cudaFree( void* p )
+{
+    std::free( p );
+    return cudaSuccess;
+}
+inline cudaError_t cudaFreeHost( void* p ) { return cudaFree( p ); }
+inline cudaError_t cudaMemsetAsync( void* p, int v, size_t n, cudaStream_t )
+{
+    std::memset( p, v, n );
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemcpy( void* d, const void* s, size_t n, cudaMemcpyKind )
+{
+    std::memcpy( d, s, n );
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemcpyAsync( void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t )
+{
+    std::memcpy( d, s, n );
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemcpy3DAsync( const cudaMemcpy3DParms* p, cudaStream_t )
+{
+    const char* s = static_cast<const char*>( p->srcPtr.ptr );
+    char* d = static_cast<char*>( p->dstPtr.ptr );
+    for ( size_t z = 0; z < p->extent.depth; ++z )
+        for ( size_t y = 0; y < p->extent.height; ++y )
+            std::memcpy( d + ( z * p->dstPtr.ysize + y ) * p->dstPtr.pitch,
+                         s + ( z * p->srcPtr.ysize + y ) * p->srcPtr.pitch, p->extent.width );
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamCreateWithFlags( cudaStream_t* s, unsigned )
+{
+    *s = reinterpret_cast<cudaStream_t>( std::malloc( 1 ) );
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamDestroy( cudaStream_t s )
+{
+    std::free( s );
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamSynchronize( cudaStream_t ) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent( cudaStream_t, cudaEvent_t, unsigned ) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate( cudaEvent_t* e )
+{
+    *e = reinterpret_cast<cudaEvent_t>( std::malloc( 1 ) );
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventCreateWithFlags( cudaEvent_t* e, unsigned ) { return cudaEventCreate( e ); }
+inline cudaError_t cudaEventDestroy( cudaEvent_t e )
+{
+    std::free( e );
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventRecord( cudaEvent_t, cudaStream_t ) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize( cudaEvent_t ) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime( float* ms, cudaEvent_t, cudaEvent_t )
+{
+    *ms = 0.0f;
+    return cudaSuccess;
+}

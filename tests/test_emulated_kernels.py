@@ -1,0 +1,197 @@
+"""The product's plain streaming kernels and host orchestration, compiled for the HOST (tests/emul:
+`kernel<<<...>>>` becomes a loop over blocks and threads) and held against the CPU oracle bit for bit.
+
+Purpose: check the logic of CUDA code — in particular code written while no GPU was available (the
+output stage, the multigrid preconditioner, the per-dimension cell sizes) — before it reaches a B200.
+Not a fallback and not a measurement path: see tests/emul/README.md.  What is not emulated (TMA stencil,
+fused two-kernel CG form, NVLink / NCCL exchange) is covered by the `-m gpu` tests only.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emul"))
+
+import build_emul  # noqa: E402
+from cajitafluids_b200 import config as K  # noqa: E402
+from cajitafluids_b200._capi import Context, Library  # noqa: E402
+from helpers import fields_of, make_cfg, random_cells, smooth_velocity  # noqa: E402
+from oracle_api import Oracle  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return Library(build_emul.build(), "cfb_")
+
+
+def run(ctx, steps):
+    ctx.setup()
+    its = [ctx.stats()["cg_iterations"]]
+    for _ in range(steps):
+        ctx.step()
+        its.append(ctx.stats()["cg_iterations"])
+    return list(np.diff([0] + its))
+
+
+def same_state(g, o, dim, ghosts=False):
+    for f in fields_of(dim) + [K.PRESSURE, K.RHS]:
+        assert np.array_equal(g.get(f), o.get(f)), f
+    if ghosts:
+        for f in fields_of(dim):
+            for v in (K.CURRENT, K.NEXT):
+                assert np.array_equal(g.get(f, v, K.GHOSTED), o.get(f, v, K.GHOSTED)), (f, v)
+    assert g.scalars() == o.scalars()
+
+
+def same_output(g, o):
+    (qa, va, na), (qb, vb, nb) = g.output(), o.output()
+    assert np.array_equal(qa, qb) and np.array_equal(va, vb)
+    assert all(np.array_equal(x, y) for x, y in zip(na, nb))
+
+
+def box_of(cells):
+    return 1.0 if isinstance(cells, int) else tuple(c / cells[0] for c in cells)
+
+
+STEP_CASES = [
+    (2, 32, {}),
+    (2, 24, dict(interp_order=1)),
+    (2, 40, dict(boundary_type=[K.FREE, K.SOLID, K.SOLID, K.FREE], body_force=(0.0, -9.8, 0.0))),
+    (2, (37, 23), {}),
+    (3, 32, {}),
+    (3, (20, 14, 11), dict(interp_order=1)),
+    (3, 32, dict(boundary_type=[K.SOLID, K.FREE, K.SOLID, K.SOLID, K.SOLID, K.FREE], body_force=(0.0, -5.0, 1.0))),
+    (3, 32, dict(quirks=(True, False))),
+]
+
+
+@pytest.mark.parametrize("dim,cells,kw", STEP_CASES)
+def test_emulated_steps_match_the_oracle_bit_for_bit(emul, dim, cells, kw):
+    cfg = make_cfg(dim, cells, box=box_of(cells), **kw)
+    g, o = Context(emul, cfg), Oracle(cfg)
+    assert run(g, 3) == run(o, 3)
+    same_state(g, o, dim, ghosts=True)
+    assert np.array_equal(g.residual_history(), o.residual_history())
+    same_output(g, o)
+
+
+@pytest.mark.parametrize("cells,box", [((40, 24), (1.0, 0.6)), ((30, 70), (0.3, 0.7)), ((20, 16, 12), (1.0, 0.8, 0.6))])
+def test_emulated_per_dimension_cell_sizes(emul, cells, box):
+    """(hi - lo) / n differs in the last bit between the dimensions: Cajita's LocalMesh uses the
+    per-dimension value for coordinates and spline arguments, Mesh::cellSize() the one of dim 0."""
+    dim = len(cells)
+    cfg = make_cfg(dim, cells, box=box)
+    g, o = Context(emul, cfg), Oracle(cfg)
+    assert run(g, 2) == run(o, 2)
+    same_state(g, o, dim, ghosts=True)
+    same_output(g, o)
+
+
+def test_emulated_stages_on_seeded_fields(emul):
+    for dim, cells in ((2, (29, 18)), (3, (13, 9, 10))):
+        cfg = make_cfg(dim, cells, box=box_of(cells), body_force=(0.3, -0.7, 0.2), fixed_iters=40)
+        g, o = Context(emul, cfg), Oracle(cfg)
+        rng = np.random.default_rng(2)
+        for f, a in smooth_velocity(o, rng, amp=0.9).items():
+            g.set(f, a)
+            o.set(f, a)
+        q = random_cells(o, rng)
+        g.set(K.QUANTITY, q)
+        o.set(K.QUANTITY, q)
+        for stage in ("add_inputs", "time_integrator_step", "build_rhs", "pcg_solve", "apply_pressure"):
+            rg, ro = getattr(g, stage)(), getattr(o, stage)()
+            assert rg == ro, stage
+            same_state(g, o, dim, ghosts=True)
+        same_output(g, o)
+
+
+MG_CASES = [
+    (2, 64, {}), (2, (48, 40), {}), (2, 32, dict(boundary_type=[K.FREE, K.SOLID, K.SOLID, K.SOLID])),
+    (3, 32, {}), (3, (24, 20, 16), {}), (3, 18, {}),
+    (3, 16, dict(boundary_type=[K.SOLID, K.SOLID, K.FREE, K.SOLID, K.SOLID, K.SOLID])),
+]
+
+
+@pytest.mark.parametrize("dim,cells,kw", MG_CASES)
+def test_emulated_multigrid_pcg_matches_the_oracle_bit_for_bit(emul, dim, cells, kw):
+    cfg = make_cfg(dim, cells, box=box_of(cells), **kw)
+    g, o = Context(emul, cfg), Oracle(cfg)
+    g.set_preconditioner("mg")
+    o.set_preconditioner("mg")
+    assert run(g, 2) == run(o, 2)
+    same_state(g, o, dim)
+    assert np.array_equal(g.residual_history(), o.residual_history())
+    assert np.array_equal(g.get(K.CG_R), o.get(K.CG_R))
+
+
+def test_emulated_vcycle_alone_and_parameters(emul):
+    rng = np.random.default_rng(9)
+    for dim, cells in ((2, (32, 16)), (2, (12, 20)), (3, (16, 8, 8)), (3, (12, 20, 8)), (3, (6, 6, 6))):
+        cfg = make_cfg(dim, cells, box=box_of(cells))
+        g, o = Context(emul, cfg), Oracle(cfg)
+        for nu in ((1, 0, 1, 0.0), (1, 1, 2, 0.0), (2, 2, 8, 0.0), (3, 2, 4, 0.7)):
+            g.set_preconditioner("mg", *nu)
+            o.set_preconditioner("mg", *nu)
+            r = rng.standard_normal(o.shape(K.PRESSURE))
+            assert np.array_equal(g.mg_apply(r), o.mg_apply(r)), (cells, nu)
+
+
+def test_emulated_multigrid_fixed_iterations_and_back_to_jacobi(emul):
+    cfg = make_cfg(3, 32, fixed_iters=4)
+    g, o = Context(emul, cfg), Oracle(cfg)
+    for s in (g, o):
+        s.set_preconditioner("mg")
+        s.add_inputs()
+        s.build_rhs()
+    assert g.pcg_solve() == o.pcg_solve()
+    assert np.array_equal(g.get(K.PRESSURE), o.get(K.PRESSURE))
+    for s in (g, o):
+        s.set_preconditioner("jacobi")
+        s.build_rhs()  # lhs = 0 (src/VelocityCorrector.hpp:272): the checker's solve starts from the x it is given
+    assert g.pcg_solve() == o.pcg_solve()
+    assert np.array_equal(g.get(K.PRESSURE), o.get(K.PRESSURE))
+
+
+def test_emulated_solve_writes_at_the_reference_cadence(emul, tmp_path):
+    import json
+    cfg = make_cfg(2, 32)
+    g = Context(emul, cfg)
+    out = str(tmp_path / "data")
+    g.set_output_dir(out)
+    assert g.solve(5 * g.dt * 0.999, 2) == 5
+    masters = sorted(f for f in os.listdir(out) if f.endswith(".json"))
+    assert masters == ["CajitaFluids%05d.json" % t for t in (0, 2, 4)]
+    m = json.load(open(os.path.join(out, masters[-1])))
+    assert m["cycle"] == 4 and m["time"] == g.time and m["dtime"] == g.dt and m["global_num_cell"] == [32, 32]
+    q, vel, nodes = g.output()
+    blk = m["blocks"][0]
+    assert blk["offset"] == [0, 0] and blk["extent"] == [32, 32]
+    assert np.array_equal(np.load(os.path.join(out, blk["quantity"])), q[0])
+    assert np.array_equal(np.load(os.path.join(out, blk["velocity"])), vel[:, 0])
+    base = os.path.join(out, blk["quantity"].replace("quantity.npy", ""))
+    assert np.array_equal(np.load(base + "nodes_x.npy"), nodes[0]) and np.array_equal(np.load(base + "nodes_y.npy"), nodes[1])
+    o = Oracle(cfg)
+    run(o, 3)  # the write of cycle 2 happened after the third step
+    oq, ov, _ = o.output()
+    name2 = os.path.join(out, "raw", "CajitaFluidsOutput%05d%05d." % (0, 2))
+    assert np.array_equal(np.load(name2 + "quantity.npy"), oq[0]) and np.array_equal(np.load(name2 + "velocity.npy"), ov[:, 0])
+
+
+def test_emulated_write_output_is_deferred_until_flush(emul, tmp_path):
+    cfg = make_cfg(3, 32)
+    g = Context(emul, cfg)
+    run(g, 1)
+    out = str(tmp_path / "o")
+    q0, v0, _ = g.output()
+    g.write_output(out, 7)
+    assert not os.path.exists(os.path.join(out, "raw"))
+    g.step()
+    g.output_flush()
+    fq = np.load(os.path.join(out, "raw", "CajitaFluidsOutput%05d%05d.quantity.npy" % (0, 7)))
+    fv = np.load(os.path.join(out, "raw", "CajitaFluidsOutput%05d%05d.velocity.npy" % (0, 7)))
+    assert fq.shape == (32, 32, 32) and fv.shape == (3, 32, 32, 32)
+    assert np.array_equal(fq, q0) and np.array_equal(fv, v0)
+    assert not np.array_equal(g.output()[0], q0)

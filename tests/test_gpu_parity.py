@@ -368,3 +368,21 @@ def test_large_grid_properties_256():
     gpu.stencil_dot(1)
     true_r = b - gpu.get(K.CG_Q)
     assert abs(np.linalg.norm(true_r.ravel()) - res) <= 1e-9 * np.linalg.norm(b.ravel())
+
+
+def test_config1_128cubed_cubic_interp():
+    """BASELINE config 1: 128^3 on one B200, cubic-spline advection + PCG with the reference's tolerance,
+    field by field against the CPU run (shortened to setup + 2 steps, ~1750 CG iterations, to bound the
+    oracle's CPU time)."""
+    cfg = make_cfg(3, 128, interp_order=3)
+    gpu, ora = pair(cfg)
+    gpu.setup()
+    ora.setup()
+    for _ in range(2):
+        gpu.step()
+        ora.step()
+    ig, io = gpu.stats()["cg_iterations"], ora.stats()["cg_iterations"]
+    assert abs(ig - io) <= 3 and ig == io, (ig, io)
+    for f in fields_of(3) + [K.PRESSURE]:
+        assert_same(gpu.get(f), ora.get(f), f"field {f}")
+    assert gpu.time == ora.time

@@ -1,0 +1,32 @@
+#!/bin/bash
+# One gpurun call that (re)establishes the measured state of the repo on a B200:
+#   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
+# Everything lands in gpurun_out/session/.  Order: cheapest and most important first.
+set -u
+O=gpurun_out/session
+mkdir -p "$O"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > "$O/gpu.csv" 2>&1
+
+# 1. the GPU tests, file by file, so that one failing file does not hide the others
+for f in tests/test_capi.py tests/test_golden.py tests/test_golden_refrun.py tests/test_gpu_parity.py \
+         tests/test_zz_output_stage.py tests/test_zz_multigrid.py; do
+    timeout 900 python -m pytest "$f" -m gpu -q -x > "$O/pytest_$(basename "$f" .py).log" 2>&1
+    echo "$f rc=$?" >> "$O/pytest_summary.txt"
+done
+
+# 2. multigrid / output stage numbers (never measured before round 2)
+for n in 128 256 512; do
+    timeout 600 python tools/profile_mg.py $n solve >> "$O/mg_solve.log" 2>&1
+done
+timeout 300 python tools/profile_mg.py 256 output >> "$O/output_stage.log" 2>&1
+timeout 300 python tools/profile_mg.py 512 output >> "$O/output_stage.log" 2>&1
+
+# 3. the headline bench
+timeout 900 python bench.py --steps 5 --warmup 3 > "$O/bench_n1.json" 2> "$O/bench_n1.err"
+
+# 4. launch lists (ncu, serialised; shares only)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$O/launches_mg256.csv" \
+    python tools/profile_mg.py 256 cycle > "$O/ncu_mg.log" 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mg_smooth_kernel|mg_restrict|mg_prolong|output_extract" \
+    -c 8 -o "$O/mg_full" python tools/profile_mg.py 256 cycle >> "$O/ncu_mg.log" 2>&1
+ls -la "$O" > "$O/listing.txt"

@@ -25,9 +25,10 @@
 //
 // All kernels here are plain one-thread-per-cell streaming kernels (HBM-bound on the fine level,
 // launch-bound on the coarse ones); q = A p stays the TMA stencil kernel.  Bytes per fine cell and CG
-// iteration with V(2,2): smoother 16 + 3 * 24, residual + restriction 17, prolongation 17, z.r 16,
-// p-update 24, stencil 16, axpy 48 = 226 (+ 1/7 of the cycle for the coarse levels) against 72 for a
-// Jacobi iteration, for ~14 iterations instead of ~2500 at 512^3.
+// iteration with V(2,2): both pre-smoothing sweeps in one pass 16, residual + restriction 17, prolongation
+// fused with the first post-smoothing sweep 24, second sweep fused with z.r 24, p-update 24, stencil 16,
+// axpy 48 = 169 (+ 1/7 of the 81 of the cycle for the coarse levels) against 72 for a Jacobi iteration,
+// for ~14 iterations instead of ~2500 at 512^3.
 #include "cfb_internal.h"
 #include "device_geo.cuh"
 #include "device_reduce.cuh"
@@ -127,6 +128,60 @@ __global__ void __launch_bounds__( NT )
     }
 }
 
+// The first TWO sweeps from a zero initial guess in one pass (16 instead of 16 + 24 bytes per cell):
+// x1 = (omega D^-1) b is recomputed for the six neighbours from b itself (neighbours off the block are
+// the ghost zeros the unfused sweep would read), then x2 = x1 + omega D^-1 (b - A x1).
+__global__ void __launch_bounds__( NT )
+    mg_smooth02_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b, double* __restrict__ xo )
+{
+    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( L, t, i, j, k );
+        const long long o = mg_off( L, i, j, k );
+        const int w = mg_walls( L, i, j, k );
+        const double bc = b[o];
+        const double xc = L.wminv[w] * bc;
+        const double xm = i > 0 ? L.wminv[mg_walls( L, i - 1, j, k )] * b[o - 1] : 0.0;
+        const double xp = i < L.n[0] - 1 ? L.wminv[mg_walls( L, i + 1, j, k )] * b[o + 1] : 0.0;
+        const double ym = j > 0 ? L.wminv[mg_walls( L, i, j - 1, k )] * b[o - L.sy] : 0.0;
+        const double yp = j < L.n[1] - 1 ? L.wminv[mg_walls( L, i, j + 1, k )] * b[o + L.sy] : 0.0;
+        const double zm = k > 0 ? L.wminv[mg_walls( L, i, j, k - 1 )] * b[o - L.sz] : 0.0;
+        const double zp = k < L.n[2] - 1 ? L.wminv[mg_walls( L, i, j, k + 1 )] * b[o + L.sz] : 0.0;
+        const double res = bc - apply_row( L.diag[w], L.ns, xc, xm, xp, ym, yp, zm, zp );
+        xo[o] = fma( L.wminv[w], res, xc );
+    }
+}
+
+// One smoothing sweep that also accumulates sum xo . b — on the fine level b is the CG residual r and the
+// last sweep's xo is z, so this is the z.r of CG kernel 2 without another pass over z and r.
+__global__ void __launch_bounds__( NT )
+    mg_smooth_dot_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b,
+                          const double* __restrict__ xi, double* __restrict__ xo, CgState* S, double* partials )
+{
+    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+    dd_t rz = { 0.0, 0.0 };
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( L, t, i, j, k );
+        const long long o = mg_off( L, i, j, k );
+        const int w = mg_walls( L, i, j, k );
+        const double bv = b[o];
+        const double res = bv - mg_Ax( L, xi, o, w );
+        const double z = fma( L.wminv[w], res, xi[o] );
+        xo[o] = z;
+        dd_acc( rz, z * bv );
+    }
+    dd_t vals[1] = { rz };
+    if ( block_reduce_finalize<NT, 1>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
+    {
+        if ( threadIdx.x == 0 )
+            S->rz_new = vals[0].hi + vals[0].lo;
+    }
+}
+
 __device__ __forceinline__ double mg_res( const MgLevelDev& F, const double* __restrict__ b,
                                           const double* __restrict__ x, int i, int j, int k )
 {
@@ -170,6 +225,50 @@ __global__ void __launch_bounds__( NT )
         mg_decode( F, t, i, j, k );
         const long long o = mg_off( F, i, j, k );
         xf[o] = xf[o] + ec[mg_off( C, i / 2, j / 2, k / F.cz )];
+    }
+}
+
+// Prolongation + correction + the first post-smoothing sweep in one pass (24 instead of 17 + 24 bytes per
+// cell): x' = x + P e is formed on the fly for the cell and its six neighbours (neighbours off the block:
+// the ghost zeros of x', which the separate prolongation never writes), then xo = x' + omega D^-1 (b - A x').
+// DOT: also sum xo . b (see mg_smooth_dot_kernel), for cycles whose only post-smoothing sweep this is.
+template <bool DOT>
+__global__ void __launch_bounds__( NT )
+    mg_prolong_smooth_kernel( const __grid_constant__ MgLevelDev F, const __grid_constant__ MgLevelDev C,
+                              const double* __restrict__ b, const double* __restrict__ xi,
+                              const double* __restrict__ ec, double* __restrict__ xo, CgState* S, double* partials )
+{
+    const long long total = (long long)F.n[0] * F.n[1] * F.n[2];
+    dd_t rz = { 0.0, 0.0 };
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        int i, j, k;
+        mg_decode( F, t, i, j, k );
+        const long long o = mg_off( F, i, j, k );
+        const int w = mg_walls( F, i, j, k );
+        const int I = i / 2, J = j / 2, K = k / F.cz;
+        const double xc = xi[o] + ec[mg_off( C, I, J, K )];
+        const double xm = i > 0 ? xi[o - 1] + ec[mg_off( C, ( i - 1 ) / 2, J, K )] : 0.0;
+        const double xp = i < F.n[0] - 1 ? xi[o + 1] + ec[mg_off( C, ( i + 1 ) / 2, J, K )] : 0.0;
+        const double ym = j > 0 ? xi[o - F.sy] + ec[mg_off( C, I, ( j - 1 ) / 2, K )] : 0.0;
+        const double yp = j < F.n[1] - 1 ? xi[o + F.sy] + ec[mg_off( C, I, ( j + 1 ) / 2, K )] : 0.0;
+        const double zm = k > 0 ? xi[o - F.sz] + ec[mg_off( C, I, J, ( k - 1 ) / F.cz )] : 0.0;
+        const double zp = k < F.n[2] - 1 ? xi[o + F.sz] + ec[mg_off( C, I, J, ( k + 1 ) / F.cz )] : 0.0;
+        const double bv = b[o];
+        const double res = bv - apply_row( F.diag[w], F.ns, xc, xm, xp, ym, yp, zm, zp );
+        const double z = fma( F.wminv[w], res, xc );
+        xo[o] = z;
+        if ( DOT )
+            dd_acc( rz, z * bv );
+    }
+    if ( DOT )
+    {
+        dd_t vals[1] = { rz };
+        if ( block_reduce_finalize<NT, 1>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
+        {
+            if ( threadIdx.x == 0 )
+                S->rz_new = vals[0].hi + vals[0].lo;
+        }
     }
 }
 
@@ -454,38 +553,75 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega )
     return CFB_OK;
 }
 
-int launch_smooth0( cfb_ctx* c, MgLevelHost& H )
+// the first `sweeps` (>= 1) smoothing sweeps of a level from a zero initial guess
+int launch_presmooth( cfb_ctx* c, MgLevelHost& H, int sweeps )
 {
-    mg_smooth0_kernel<<<grid_for( c, H.cells ), NT, 0, c->stream>>>( H.d, H.b, H.x[0] );
-    H.cur = 0;
-    return 1;
+    const int grid = grid_for( c, H.cells );
+    int n = 1, done;
+    if ( sweeps >= 2 )
+    {
+        mg_smooth02_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[1] );
+        H.cur = 1; // where the unfused pair of sweeps leaves its result
+        done = 2;
+    }
+    else
+    {
+        mg_smooth0_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[0] );
+        H.cur = 0;
+        done = 1;
+    }
+    for ( ; done < sweeps; ++done, ++n )
+    {
+        mg_smooth_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur] );
+        H.cur = 1 - H.cur;
+    }
+    return n;
 }
 
-int launch_smooth( cfb_ctx* c, MgLevelHost& H )
-{
-    mg_smooth_kernel<<<grid_for( c, H.cells ), NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur] );
-    H.cur = 1 - H.cur;
-    return 1;
-}
-
-int vcycle( cfb_ctx* c, int l )
+// One V-cycle on level l.  `dot` (fine level only, from the CG): the sweep that produces the level's
+// result also accumulates sum z.r into S->rz_new; returns through *dotted whether it did (it cannot
+// when there is no post-smoothing sweep).
+int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted )
 {
     MgStage* m = c->mg;
     MgLevelHost& H = m->lv[l];
     const bool last = l + 1 == (int)m->lv.size();
-    int n = launch_smooth0( c, H );
-    for ( int s = 1; s < ( last ? m->nuc : m->nu1 ); ++s )
-        n += launch_smooth( c, H );
+    const int grid = grid_for( c, H.cells );
+    if ( dotted )
+        *dotted = false;
+    int n = launch_presmooth( c, H, last ? m->nuc : m->nu1 );
     if ( last )
         return n;
     MgLevelHost& C = m->lv[l + 1];
     mg_restrict_kernel<<<grid_for( c, C.cells ), NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.b );
     n += 1;
-    n += vcycle( c, l + 1 );
-    mg_prolong_kernel<<<grid_for( c, H.cells ), NT, 0, c->stream>>>( H.d, C.d, H.x[H.cur], C.x[C.cur] );
+    n += vcycle( c, l + 1, false, nullptr );
+    if ( m->nu2 == 0 )
+    {
+        mg_prolong_kernel<<<grid, NT, 0, c->stream>>>( H.d, C.d, H.x[H.cur], C.x[C.cur] );
+        return n + 1;
+    }
+    const bool dot_here = dot && m->nu2 == 1;
+    if ( dot_here )
+        mg_prolong_smooth_kernel<true><<<grid, NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.x[C.cur],
+                                                                   H.x[1 - H.cur], c->d_state, c->d_partials );
+    else
+        mg_prolong_smooth_kernel<false><<<grid, NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.x[C.cur],
+                                                                    H.x[1 - H.cur], c->d_state, c->d_partials );
+    H.cur = 1 - H.cur;
     n += 1;
-    for ( int s = 0; s < m->nu2; ++s )
-        n += launch_smooth( c, H );
+    for ( int s = 1; s < m->nu2; ++s )
+    {
+        if ( dot && s == m->nu2 - 1 )
+            mg_smooth_dot_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur], c->d_state,
+                                                             c->d_partials );
+        else
+            mg_smooth_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur] );
+        H.cur = 1 - H.cur;
+        n += 1;
+    }
+    if ( dotted )
+        *dotted = dot;
     return n;
 }
 
@@ -518,11 +654,16 @@ int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     while ( enq < max_it && !done )
     {
         // one iteration: z = M^-1 r ; z.r ; p = z + beta p ; q = A p, p.q ; x, r, r.r, stopping test
-        launches += vcycle( c, 0 );
+        bool dotted = false;
+        launches += vcycle( c, 0, true, &dotted );
         const double* z = F.x[F.cur];
-        mgcg_dot_kernel<<<grid, NT, 0, c->stream>>>( L, z, c->cg_r, S, c->d_partials );
+        if ( !dotted ) // no post-smoothing sweep to fuse z.r into
+        {
+            mgcg_dot_kernel<<<grid, NT, 0, c->stream>>>( L, z, c->cg_r, S, c->d_partials );
+            launches += 1;
+        }
         mgcg_pupdate_kernel<<<grid, NT, 0, c->stream>>>( L, z, c->cg_p, S, enq == 0 ? 1 : 0 );
-        launches += 2;
+        launches += 1;
         launches += launch_stencil_dot( c );
         mgcg_axpy_kernel<<<grid, NT, 0, c->stream>>>( L, c->cg_p, c->cg_q, c->lhs, c->cg_r, S, c->d_partials );
         launches += 1;
@@ -600,7 +741,7 @@ extern "C" int cfb_mg_apply( cfb_ctx* c, const double* r_host, double* z_host )
         return rc;
     MgLevelHost& F = m->lv[0];
     F.b = c->cg_r;
-    c->stats.kernel_launches += vcycle( c, 0 );
+    c->stats.kernel_launches += vcycle( c, 0, false, nullptr );
     const Geo& g = c->g;
     const double* z = F.x[F.cur] + g.origin;
     cudaMemcpy3DParms p{};

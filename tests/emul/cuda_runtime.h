@@ -128,6 +128,11 @@ inline cudaError_t cudaMemsetAsync( void* p, int v, size_t n, cudaStream_t )
     std::memset( p, v, n );
     return cudaSuccess;
 }
+inline cudaError_t cudaMemset( void* p, int v, size_t n )
+{
+    std::memset( p, v, n );
+    return cudaSuccess;
+}
 inline cudaError_t cudaMemcpy( void* d, const void* s, size_t n, cudaMemcpyKind )
 {
     std::memcpy( d, s, n );
@@ -148,6 +153,17 @@ inline cudaError_t cudaMemcpy3DAsync( const cudaMemcpy3DParms* p, cudaStream_t )
                          s + ( z * p->srcPtr.ysize + y ) * p->srcPtr.pitch, p->extent.width );
     return cudaSuccess;
 }
+// no peer memory in the emulation: the NVLink exchange path reports "not available"
+struct cudaIpcMemHandle_t
+{
+    char reserved[64];
+};
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle( cudaIpcMemHandle_t*, void* ) { return cudaErrorEmul; }
+inline cudaError_t cudaIpcOpenMemHandle( void**, cudaIpcMemHandle_t, unsigned ) { return cudaErrorEmul; }
+inline cudaError_t cudaIpcCloseMemHandle( void* ) { return cudaSuccess; }
+inline long long clock64() { return 0; }
+
 inline cudaError_t cudaStreamCreateWithFlags( cudaStream_t* s, unsigned )
 {
     *s = reinterpret_cast<cudaStream_t>( std::malloc( 1 ) );

@@ -35,7 +35,7 @@ inline dd_t dd_add( dd_t a, dd_t b )
 template <int NT, int NV>
 inline bool block_reduce_finalize( dd_t vals[NV], double* partials, int stride, unsigned int* ticket )
 {
-    static dd_t acc[NV];
+    static thread_local dd_t acc[NV]; // ranks of a multi-rank emulation are threads
     const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
     const unsigned bid = ( blockIdx.z * gridDim.y + blockIdx.y ) * gridDim.x + blockIdx.x;
     if ( threadIdx.x == blockDim.x - 1 ) // first thread of the block to run

@@ -3,7 +3,8 @@
 //   * q = A p, sum p.q  (the TMA stencil kernel, verified on the GPU)  -> a plain loop with the same row
 //     arithmetic (apply_row) and the same exactly-accumulated dot product
 //   * the two-kernel fused CG form  -> not available: the emulated context runs the three-kernel form
-//   * multi-GPU                     -> not available: halo_init fails
+//   * multi-GPU: halo.cu itself is compiled; NCCL is the in-process stand-in of nccl_emul.cpp (ranks are
+//     threads), the NVLink peer-memory path reports "not available" (cudaIpc stand-ins fail)
 #include "cfb_internal.h"
 #include "device_geo.cuh"
 #include "device_reduce.cuh"
@@ -61,7 +62,14 @@ int launch_stencil_dot( cfb_ctx* c )
                 q[o] = a;
                 dd_acc( acc, p[o] * a );
             }
-    S->pAp = acc.hi + acc.lo;
+    // publish_pAp of kernels_stencil.cu: several blocks keep the local double-double for the exact combine
+    if ( S->world > 1 )
+    {
+        S->loc[0] = acc.hi;
+        S->loc[1] = acc.lo;
+    }
+    else
+        S->pAp = acc.hi + acc.lo;
     S->rz_old = S->rz_new;
     return 1;
 }
@@ -75,14 +83,3 @@ int fused_setup( cfb_ctx* c )
 int launch_cg_rupdate( cfb_ctx* c ) { return cfb_fail( c, CFB_ERR_INVALID, "emul: fused CG form unavailable" ), 0; }
 int launch_cg_fused( cfb_ctx* c, int ) { return cfb_fail( c, CFB_ERR_INVALID, "emul: fused CG form unavailable" ), 0; }
 int launch_cg_finish( cfb_ctx* ) { return 0; }
-
-int halo_init( cfb_ctx* c ) { return cfb_fail( c, CFB_ERR_NCCL, "emul: single block only" ); }
-void halo_destroy( cfb_ctx* ) {}
-int halo_exchange_cells( cfb_ctx*, double*, int ) { return CFB_OK; }
-int halo_cells_begin( cfb_ctx*, double* const*, int, int ) { return CFB_OK; }
-int halo_cells_end( cfb_ctx* ) { return CFB_OK; }
-int peer_exchange( cfb_ctx*, int, bool, int, bool ) { return CFB_OK; }
-int halo_exchange_fields( cfb_ctx*, int ) { return CFB_OK; }
-int halo_allreduce( cfb_ctx*, double*, int ) { return CFB_OK; }
-int halo_allgather( cfb_ctx*, const double*, double*, int ) { return CFB_OK; }
-extern "C" int cfb_nccl_unique_id( unsigned char* ) { return cfb_fail( nullptr, CFB_ERR_NCCL, "emul: no NCCL" ); }

@@ -1,0 +1,126 @@
+"""Several ranks of the host-emulated library (tests/emul) in one process: the block decomposition, the
+three-sweep field halo, the NCCL-path CG (three-kernel form, all-gathered exact sums), the pressure halo
+and the output stage's gather, held against the SINGLE-BLOCK oracle bit for bit — on the block grids of
+1, 2, 4 and 8 GPUs (1x1x2, 1x2x2, 2x2x2) and on x / y splits.
+
+Covers the host logic of cajitafluids_b200/csrc/halo.cu (boxes, neighbours, message sizes, sweep order)
+that the GPU tests could only exercise on two GPUs so far.  Not covered here: the NVLink peer-memory
+exchange and the fused two-kernel CG form (GPU tests only).  See tests/emul/README.md.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emul"))
+
+import build_emul  # noqa: E402
+from cajitafluids_b200 import config as K  # noqa: E402
+from cajitafluids_b200._capi import Library  # noqa: E402
+from helpers import fields_of, make_cfg  # noqa: E402
+from multirank import block_slices, run_ranks  # noqa: E402
+from oracle_api import Oracle  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return Library(build_emul.build(), "cfb_")
+
+
+GRIDS = [(2, None), (4, None), (8, None), (2, (2, 1, 1)), (2, (1, 2, 1)), (4, (2, 2, 1)), (3, (3, 1, 1)), (6, (1, 3, 2))]
+
+
+def cfg3(cells=(24, 20, 18), **kw):
+    return make_cfg(3, cells, box=tuple(c / cells[0] for c in cells), **kw)
+
+
+@pytest.mark.parametrize("world,blocks", GRIDS)
+def test_field_gather_fills_every_ghost_including_edges_and_corners(emul, world, blocks):
+    cfg = cfg3()
+    ora = Oracle(cfg)
+    rng = np.random.default_rng(3)
+    glob = {}
+    for f in fields_of(3):
+        a = rng.uniform(-1, 1, size=ora.shape(f))
+        ora.set(f, a)
+        glob[f] = (a, ora.get(f, region=K.GHOSTED))  # physical ghosts are zero
+
+    def body(ctx, rank):
+        for f in fields_of(3):
+            ctx.set(f, glob[f][0][block_slices(ctx, f)])
+        ctx.gather(K.CURRENT)
+        off = ctx.global_offset()
+        bad = []
+        for f in fields_of(3):
+            mine = ctx.get(f, region=K.GHOSTED)
+            ez, ey, ex = mine.shape
+            want = glob[f][1][off[2]:off[2] + ez, off[1]:off[1] + ey, off[0]:off[0] + ex]
+            if not np.array_equal(mine, want):
+                bad.append((f, int((mine != want).sum())))
+        return bad
+
+    assert run_ranks(emul, cfg, world, body, blocks) == [[]] * world
+
+
+@pytest.mark.parametrize("world,blocks", GRIDS)
+def test_decomposed_pcg_is_bit_identical_to_the_single_block_oracle(emul, world, blocks):
+    cfg = cfg3()
+    ora = Oracle(cfg)
+    rng = np.random.default_rng(77)
+    vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
+    for f, a in vel.items():
+        ora.set(f, a)
+    ora.add_inputs()
+    ora.build_rhs()
+    io, ro = ora.pcg_solve()
+    po, bo, ho = ora.get(K.PRESSURE), ora.get(K.RHS), ora.residual_history()
+
+    def body(ctx, rank):
+        for f, a in vel.items():
+            ctx.set(f, a[block_slices(ctx, f)])
+        ctx.add_inputs()
+        ctx.build_rhs()
+        ok_rhs = np.array_equal(ctx.get(K.RHS), bo[block_slices(ctx, K.RHS)])
+        ig, rg = ctx.pcg_solve()
+        ok_p = np.array_equal(ctx.get(K.PRESSURE), po[block_slices(ctx, K.PRESSURE)])
+        return ok_rhs, ig, rg, ok_p, np.array_equal(ctx.residual_history(), ho)
+
+    for res in run_ranks(emul, cfg, world, body, blocks):
+        assert res == (True, io, ro, True, True), res
+
+
+@pytest.mark.parametrize("world,blocks", [(2, None), (4, None), (8, None), (4, (2, 2, 1))])
+def test_decomposed_steps_and_output_match_the_single_block_oracle(emul, world, blocks):
+    cfg = cfg3(cells=(32, 24, 16), body_force=(0.0, -3.0, 0.5))
+    ora = Oracle(cfg)
+    ora.setup()
+    want0 = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
+    for _ in range(2):
+        ora.step()
+    want = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
+    oq, ov, _ = ora.output()
+    its = ora.stats()["cg_iterations"]
+
+    gl = {f: max(np.linalg.norm(want[f].ravel()), 1e-300) for f in want}
+
+    def body(ctx, rank):
+        # Block-local LocalMesh coordinates (own low corner + local index * cell, like every rank of the
+        # reference computes them) differ from the single block's in the last bit, so advected fields agree
+        # to rounding, not bit for bit; everything before the first advection does (asserted below).
+        ctx.setup()
+        exact = [f for f in want0 if not np.array_equal(ctx.get(f), want0[f][block_slices(ctx, f)])]
+        for _ in range(2):
+            ctx.step()
+        err = {f: float(np.linalg.norm((ctx.get(f) - want[f][block_slices(ctx, f)]).ravel()) / gl[f]) for f in want}
+        q, v, _ = ctx.output()
+        sl = block_slices(ctx, K.QUANTITY)
+        err["out_q"] = float(np.abs(q - oq[sl]).max())
+        err["out_vel"] = float(np.abs(v - ov[(slice(None),) + sl]).max())
+        return exact, err, ctx.stats()["cg_iterations"], ctx.time
+
+    for exact, err, it, t in run_ranks(emul, cfg, world, body, blocks):
+        assert exact == []
+        assert max(err.values()) < 1e-12, err
+        assert abs(it - its) <= 3 and t == ora.time

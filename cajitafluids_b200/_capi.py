@@ -70,15 +70,17 @@ class Library:
         "write_npy": [C.c_char_p, _dp, C.c_int, C.POINTER(C.c_int64)],
         "set_preconditioner": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double],
         "mg_apply": [C.c_void_p, _dp, _dp],
+        "set_mg_max_levels": [C.c_void_p, C.c_int],
+        "mg_num_levels": [C.c_void_p, _ip],
         "abi_version": [],
     }
 
-    def __init__(self, path, prefix):
+    def __init__(self, path, prefix, mode=C.RTLD_GLOBAL):
         if not os.path.exists(path):
             raise FileNotFoundError(
                 f"{path} is missing: build it first (python -c 'import __graft_entry__ as g; g.build()')")
         self.path, self.prefix = path, prefix
-        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self.dll = C.CDLL(path, mode=mode)
         self.fn = {}
         for table, required in ((self._SIG, True), (self._SIG_OPT, False)):
             for name, args in table.items():
@@ -245,6 +247,14 @@ class Context:
         multigrid V(nu_pre, nu_post) cycle; omega <= 0: default damping)."""
         k = {"jacobi": K.PRECOND_JACOBI, "mg": K.PRECOND_MG}.get(kind, kind)
         self._call("set_preconditioner", int(k), int(nu_pre), int(nu_post), int(nu_coarse), C.c_double(omega))
+
+    def set_mg_max_levels(self, n):
+        self._call("set_mg_max_levels", int(n))
+
+    def mg_num_levels(self):
+        n = C.c_int()
+        self._call("mg_num_levels", C.byref(n))
+        return n.value
 
     def mg_apply(self, r):
         """z = M^-1 r: one multigrid V-cycle on a dense owned-cell array."""

@@ -190,6 +190,7 @@ struct cfb_ctx
 
     // opt-in multigrid preconditioner (mg.cu; cfb_set_preconditioner)
     int precond = CFB_PRECOND_JACOBI;
+    int mg_max_levels = 0; // 0 = as many as the block allows
     MgStage* mg = nullptr;
 };
 
@@ -294,6 +295,7 @@ int halo_cells_end( cfb_ctx* c );
 // from staging, always needed for the plain stencil at the start of a solve)
 int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpack );
 int halo_exchange_fields( cfb_ctx* c, int version );             // width-h exchange of q,u,v,w
+int halo_sendrecv_slots( cfb_ctx* c, const size_t counts[6], cudaStream_t st ); // d_halo_send/recv[s] <-> nbr[s]
 int halo_allreduce( cfb_ctx* c, double* dev_vals, int n );
 int halo_allgather( cfb_ctx* c, const double* dev_send, double* dev_recv, int n_per_rank );
 // kernels_cg.cu: all-gather + exact combine of the local CG sums (which = 0: pAp, 1: rz_new and rr)

@@ -787,6 +787,26 @@ int halo_exchange_fields( cfb_ctx* c, int version )
     return CFB_OK;
 }
 
+// One grouped exchange of the per-neighbour buffers: d_halo_send[s] (counts[s] doubles) goes to the neighbour on
+// face s, d_halo_recv[s] is filled by it; used by callers that pack / unpack with their own kernels (the
+// multigrid levels of mg.cu, whose arrays do not have the layout of the CG vectors).
+int halo_sendrecv_slots( cfb_ctx* c, const size_t counts[6], cudaStream_t st )
+{
+    Comm* cm = static_cast<Comm*>( c->nccl );
+    CFB_NCCL( c, g_nccl.GroupStart() );
+    for ( int s = 0; s < 6; ++s )
+    {
+        if ( c->nbr[s] < 0 || counts[s] == 0 )
+            continue;
+        if ( counts[s] > c->halo_buf_elems )
+            return cfb_fail( c, CFB_ERR_INVALID, "halo buffer too small" );
+        CFB_NCCL( c, g_nccl.Send( c->d_halo_send[s], counts[s], ncclDouble, c->nbr[s], cm->halo, st ) );
+        CFB_NCCL( c, g_nccl.Recv( c->d_halo_recv[s], counts[s], ncclDouble, c->nbr[s], cm->halo, st ) );
+    }
+    CFB_NCCL( c, g_nccl.GroupEnd() );
+    return CFB_OK;
+}
+
 int halo_allreduce( cfb_ctx* c, double* dev_vals, int n )
 {
     Comm* cm = static_cast<Comm*>( c->nccl );

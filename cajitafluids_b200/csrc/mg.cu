@@ -19,6 +19,12 @@
 //   restriction : mean of the 2^D children of the residual (residual fused into the kernel);
 //                 prolongation: piecewise constant, fused with the correction
 //   coarsest    : nuc Jacobi sweeps
+//   several GPUs: the SAME global cycle, block-decomposed like the CG (not a block-local preconditioner: that
+//                 loses the coarse space across blocks, 49 instead of 12 iterations at 64^3 on 2x2x2 blocks);
+//                 every level is coarsened block by block (identical block extents required), ghost layers
+//                 are refreshed before each operator application by a one-layer face exchange (pack kernel,
+//                 one grouped NCCL send/recv, unpack kernel), sums are all-gathered and combined exactly, so
+//                 iteration counts and results do not depend on the decomposition
 //   null space  : with all walls SOLID the operator is singular; x is shifted at the end so that
 //                 sum_i d_i x_i = 0, the component Jacobi-PCG produces (quirk Q1 of the reference leaks
 //                 that constant into v, src/VelocityCorrector.hpp:260)
@@ -45,6 +51,8 @@ struct MgLevelDev
     int n[3];
     int cz;             // coarsening factor to the next level along z (1 in 2-D)
     int slo[3], shi[3]; // the low / high end of dim d is a SOLID physical wall
+    int nlo[3], nhi[3]; // a neighbouring block continues the grid there: the ghost layer holds its values
+                        // after an exchange (otherwise ghosts are the zeros the operator reads off the domain)
     long long sy, sz, origin;
     double ns;          // off-diagonal coefficient, -scale_l
     double diag[8], wminv[8];
@@ -66,6 +74,7 @@ struct MgStage
 {
     std::vector<MgLevelHost> lv;
     int nu1 = 2, nu2 = 2, nuc = 8;
+    int max_levels = 0; // 0 = as many as the block allows
     double omega = 0.0;
     bool singular = false;
     cudaEvent_t ev_poll = nullptr;
@@ -91,6 +100,9 @@ __device__ __forceinline__ void mg_decode( const MgLevelDev& L, long long t, int
     j = (int)( ( t / L.n[0] ) % L.n[1] );
     k = (int)( t / ( (long long)L.n[0] * L.n[1] ) );
 }
+
+// coarse index of fine index i (floor division, so that the ghost index -1 maps to the coarse ghost -1)
+__device__ __forceinline__ int mg_parent( int i, int f ) { return f == 1 ? i : ( ( i + 2 ) >> 1 ) - 1; }
 
 // (A x)(i,j,k): diag * x, then one fused multiply-add per neighbour in stencil order
 __device__ __forceinline__ double mg_Ax( const MgLevelDev& L, const double* __restrict__ x, long long o, int w )
@@ -143,15 +155,32 @@ __global__ void __launch_bounds__( NT )
         const int w = mg_walls( L, i, j, k );
         const double bc = b[o];
         const double xc = L.wminv[w] * bc;
-        const double xm = i > 0 ? L.wminv[mg_walls( L, i - 1, j, k )] * b[o - 1] : 0.0;
-        const double xp = i < L.n[0] - 1 ? L.wminv[mg_walls( L, i + 1, j, k )] * b[o + 1] : 0.0;
-        const double ym = j > 0 ? L.wminv[mg_walls( L, i, j - 1, k )] * b[o - L.sy] : 0.0;
-        const double yp = j < L.n[1] - 1 ? L.wminv[mg_walls( L, i, j + 1, k )] * b[o + L.sy] : 0.0;
-        const double zm = k > 0 ? L.wminv[mg_walls( L, i, j, k - 1 )] * b[o - L.sz] : 0.0;
-        const double zp = k < L.n[2] - 1 ? L.wminv[mg_walls( L, i, j, k + 1 )] * b[o + L.sz] : 0.0;
+        // a neighbour across a block interface is a ghost entry of b (exchanged by the caller); its wall
+        // count is that of an interior cell along the interface normal, which mg_walls returns for -1 / n
+        const double xm = ( i > 0 || L.nlo[0] ) ? L.wminv[mg_walls( L, i - 1, j, k )] * b[o - 1] : 0.0;
+        const double xp = ( i < L.n[0] - 1 || L.nhi[0] ) ? L.wminv[mg_walls( L, i + 1, j, k )] * b[o + 1] : 0.0;
+        const double ym = ( j > 0 || L.nlo[1] ) ? L.wminv[mg_walls( L, i, j - 1, k )] * b[o - L.sy] : 0.0;
+        const double yp = ( j < L.n[1] - 1 || L.nhi[1] ) ? L.wminv[mg_walls( L, i, j + 1, k )] * b[o + L.sy] : 0.0;
+        const double zm = ( k > 0 || L.nlo[2] ) ? L.wminv[mg_walls( L, i, j, k - 1 )] * b[o - L.sz] : 0.0;
+        const double zp = ( k < L.n[2] - 1 || L.nhi[2] ) ? L.wminv[mg_walls( L, i, j, k + 1 )] * b[o + L.sz] : 0.0;
         const double res = bc - apply_row( L.diag[w], L.ns, xc, xm, xp, ym, yp, zm, zp );
         xo[o] = fma( L.wminv[w], res, xc );
     }
+}
+
+// End of a reduction.  One block: the rounded sum is final.  Several blocks (ranks): keep the local
+// double-double in S->loc[0..1]; the host all-gathers them and mgcg_combine_kernel adds them exactly in
+// rank order, so the global value is again the correctly rounded exact sum, whatever the decomposition.
+__device__ __forceinline__ bool mg_publish( CgState* S, dd_t v, int slot, double* direct )
+{
+    if ( S->world > 1 )
+    {
+        S->loc[2 * slot] = v.hi;
+        S->loc[2 * slot + 1] = v.lo;
+        return false;
+    }
+    *direct = v.hi + v.lo;
+    return true;
 }
 
 // One smoothing sweep that also accumulates sum xo . b — on the fine level b is the CG residual r and the
@@ -178,7 +207,7 @@ __global__ void __launch_bounds__( NT )
     if ( block_reduce_finalize<NT, 1>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
     {
         if ( threadIdx.x == 0 )
-            S->rz_new = vals[0].hi + vals[0].lo;
+            mg_publish( S, vals[0], 0, &S->rz_new );
     }
 }
 
@@ -248,12 +277,13 @@ __global__ void __launch_bounds__( NT )
         const int w = mg_walls( F, i, j, k );
         const int I = i / 2, J = j / 2, K = k / F.cz;
         const double xc = xi[o] + ec[mg_off( C, I, J, K )];
-        const double xm = i > 0 ? xi[o - 1] + ec[mg_off( C, ( i - 1 ) / 2, J, K )] : 0.0;
-        const double xp = i < F.n[0] - 1 ? xi[o + 1] + ec[mg_off( C, ( i + 1 ) / 2, J, K )] : 0.0;
-        const double ym = j > 0 ? xi[o - F.sy] + ec[mg_off( C, I, ( j - 1 ) / 2, K )] : 0.0;
-        const double yp = j < F.n[1] - 1 ? xi[o + F.sy] + ec[mg_off( C, I, ( j + 1 ) / 2, K )] : 0.0;
-        const double zm = k > 0 ? xi[o - F.sz] + ec[mg_off( C, I, J, ( k - 1 ) / F.cz )] : 0.0;
-        const double zp = k < F.n[2] - 1 ? xi[o + F.sz] + ec[mg_off( C, I, J, ( k + 1 ) / F.cz )] : 0.0;
+        // across a block interface: the ghost entries of x and of the coarse correction (both exchanged)
+        const double xm = ( i > 0 || F.nlo[0] ) ? xi[o - 1] + ec[mg_off( C, mg_parent( i - 1, 2 ), J, K )] : 0.0;
+        const double xp = ( i < F.n[0] - 1 || F.nhi[0] ) ? xi[o + 1] + ec[mg_off( C, mg_parent( i + 1, 2 ), J, K )] : 0.0;
+        const double ym = ( j > 0 || F.nlo[1] ) ? xi[o - F.sy] + ec[mg_off( C, I, mg_parent( j - 1, 2 ), K )] : 0.0;
+        const double yp = ( j < F.n[1] - 1 || F.nhi[1] ) ? xi[o + F.sy] + ec[mg_off( C, I, mg_parent( j + 1, 2 ), K )] : 0.0;
+        const double zm = ( k > 0 || F.nlo[2] ) ? xi[o - F.sz] + ec[mg_off( C, I, J, mg_parent( k - 1, F.cz ) )] : 0.0;
+        const double zp = ( k < F.n[2] - 1 || F.nhi[2] ) ? xi[o + F.sz] + ec[mg_off( C, I, J, mg_parent( k + 1, F.cz ) )] : 0.0;
         const double bv = b[o];
         const double res = bv - apply_row( F.diag[w], F.ns, xc, xm, xp, ym, yp, zm, zp );
         const double z = fma( F.wminv[w], res, xc );
@@ -267,7 +297,7 @@ __global__ void __launch_bounds__( NT )
         if ( block_reduce_finalize<NT, 1>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
         {
             if ( threadIdx.x == 0 )
-                S->rz_new = vals[0].hi + vals[0].lo;
+                mg_publish( S, vals[0], 0, &S->rz_new );
         }
     }
 }
@@ -295,7 +325,7 @@ __global__ void __launch_bounds__( NT )
     {
         if ( threadIdx.x == 0 )
         {
-            S->rr = vals[0].hi + vals[0].lo;
+            mg_publish( S, vals[0], 0, &S->rr );
             S->iter = 0;
             S->done = 0;
             S->fixed = fixed;
@@ -332,7 +362,7 @@ __global__ void __launch_bounds__( NT )
     if ( block_reduce_finalize<NT, 1>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
     {
         if ( threadIdx.x == 0 )
-            S->rz_new = vals[0].hi + vals[0].lo;
+            mg_publish( S, vals[0], 0, &S->rz_new );
     }
 }
 
@@ -352,6 +382,18 @@ __global__ void __launch_bounds__( NT )
         const long long o = mg_off( L, i, j, k );
         p[o] = first ? z[o] : fma( beta, p[o], z[o] );
     }
+}
+
+// after kernel 1's sum r^2 is known globally: history, iteration count, stopping test
+__device__ __forceinline__ void mgcg_bookkeeping( CgState* S )
+{
+    const double resid = sqrt( S->rr );
+    const int it = S->iter;
+    if ( it < CFB_HIST_MAX )
+        S->hist[it] = resid;
+    S->iter = it + 1;
+    if ( !S->fixed && resid <= S->thresh )
+        S->done = 1;
 }
 
 // kernel 1: x += alpha p, r -= alpha q, sum r^2, then the iteration's bookkeeping and stopping test
@@ -379,22 +421,12 @@ __global__ void __launch_bounds__( NT )
     dd_t vals[1] = { rr };
     if ( block_reduce_finalize<NT, 1>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
     {
-        if ( threadIdx.x == 0 )
-        {
-            const double rrv = vals[0].hi + vals[0].lo;
-            S->rr = rrv;
-            const double resid = sqrt( rrv );
-            const int it = S->iter;
-            if ( it < CFB_HIST_MAX )
-                S->hist[it] = resid;
-            S->iter = it + 1;
-            if ( !S->fixed && resid <= S->thresh )
-                S->done = 1;
-        }
+        if ( threadIdx.x == 0 && mg_publish( S, vals[0], 0, &S->rr ) )
+            mgcg_bookkeeping( S );
     }
 }
 
-// null-space pinning: sum d_i x_i and sum d_i -> S->gath[0..1]
+// null-space pinning: sum d_i x_i and sum d_i -> S->loc[4..5]
 __global__ void __launch_bounds__( NT )
     mgcg_nullsum_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ x, CgState* S,
                          double* partials )
@@ -414,8 +446,8 @@ __global__ void __launch_bounds__( NT )
     {
         if ( threadIdx.x == 0 )
         {
-            S->gath[0] = vals[0].hi + vals[0].lo;
-            S->gath[1] = vals[1].hi + vals[1].lo;
+            mg_publish( S, vals[0], 0, &S->loc[4] );
+            mg_publish( S, vals[1], 1, &S->loc[5] );
         }
     }
 }
@@ -423,7 +455,7 @@ __global__ void __launch_bounds__( NT )
 __global__ void __launch_bounds__( NT )
     mgcg_shift_kernel( const __grid_constant__ MgLevelDev L, double* __restrict__ x, const CgState* S )
 {
-    const double shift = S->gath[0] / S->gath[1];
+    const double shift = S->loc[4] / S->loc[5];
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
     {
@@ -431,6 +463,73 @@ __global__ void __launch_bounds__( NT )
         mg_decode( L, t, i, j, k );
         const long long o = mg_off( L, i, j, k );
         x[o] = x[o] - shift;
+    }
+}
+
+// Several blocks: exact combination, in rank order, of the all-gathered local double-doubles (S->gath,
+// nv values per rank).  what: 0 = r0.r0 of the start, 1 = z.r, 2 = r.r of an iteration (+ bookkeeping),
+// 3 = the two null-space sums.
+__global__ void mgcg_combine_kernel( CgState* S, int what )
+{
+    if ( what != 0 && what != 3 && S->done )
+        return;
+    const int nv = what == 3 ? 2 : 1;
+    dd_t acc[2] = { { 0.0, 0.0 }, { 0.0, 0.0 } };
+    for ( int r = 0; r < S->world; ++r )
+        for ( int v = 0; v < nv; ++v )
+        {
+            dd_t w = { S->gath[( r * nv + v ) * 2], S->gath[( r * nv + v ) * 2 + 1] };
+            acc[v] = dd_add( acc[v], w );
+        }
+    const double v0 = acc[0].hi + acc[0].lo;
+    if ( what == 0 )
+        S->rr = v0;
+    else if ( what == 1 )
+        S->rz_new = v0;
+    else if ( what == 2 )
+    {
+        S->rr = v0;
+        mgcg_bookkeeping( S );
+    }
+    else
+    {
+        S->loc[4] = v0;
+        S->loc[5] = acc[1].hi + acc[1].lo;
+    }
+}
+
+// One-layer face exchange of a level array: PACK copies my boundary layers into the send buffers, !PACK
+// scatters the received layers into my ghost layers.  blockIdx.y = face.
+struct MgFaces
+{
+    int nface;
+    int dim[6], src[6], dst[6]; // normal direction; owned index of the layer sent; ghost index filled
+    double* buf[6];
+};
+
+template <bool PACK>
+__global__ void __launch_bounds__( NT )
+    mg_face_kernel( const __grid_constant__ MgLevelDev L, const __grid_constant__ MgFaces a, double* __restrict__ arr )
+{
+    const int f = blockIdx.y;
+    if ( f >= a.nface )
+        return;
+    const int d = a.dim[f];
+    const int e0 = d == 0 ? L.n[1] : L.n[0];               // fastest tangential extent
+    const int e1 = d == 2 ? L.n[1] : L.n[2];               // slowest tangential extent
+    const long long total = (long long)e0 * e1;
+    const int fix = PACK ? a.src[f] : a.dst[f];
+    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    {
+        const int u = (int)( t % e0 ), v = (int)( t / e0 );
+        const int i = d == 0 ? fix : u;
+        const int j = d == 0 ? u : ( d == 1 ? fix : v );
+        const int k = d == 2 ? fix : v;
+        const long long o = mg_off( L, i, j, k );
+        if ( PACK )
+            a.buf[f][t] = arr[o];
+        else
+            arr[o] = a.buf[f][t];
     }
 }
 
@@ -463,11 +562,12 @@ void mg_free( cfb_ctx* c )
     c->mg = nullptr;
 }
 
-int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega )
+int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega, int max_levels )
 {
     mg_free( c );
     MgStage* m = new MgStage();
     c->mg = m;
+    m->max_levels = max_levels;
     m->nu1 = nu1;
     m->nu2 = nu2;
     m->nuc = nuc;
@@ -490,6 +590,8 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega )
             L.n[d] = n[d];
             L.slo[d] = d < D ? ( g.lo_bd[d] && g.bt[d] == CFB_SOLID ) : 1;
             L.shi[d] = d < D ? ( g.hi_bd[d] && g.bt[3 + d] == CFB_SOLID ) : 1;
+            L.nlo[d] = ( d < D && c->cfg.use_nccl && c->nbr[2 * d] >= 0 ) ? 1 : 0;
+            L.nhi[d] = ( d < D && c->cfg.use_nccl && c->nbr[2 * d + 1] >= 0 ) ? 1 : 0;
         }
         L.cz = D == 3 ? 2 : 1;
         L.ns = -1.0 * scale;
@@ -540,7 +642,8 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega )
             CFB_CUDA( c, cudaMalloc( &H.x[q], elems * sizeof( double ) ) );
             CFB_CUDA( c, cudaMemsetAsync( H.x[q], 0, elems * sizeof( double ), c->stream ) );
         }
-        bool can = true;
+        // every block has the same extents here (cfb_set_preconditioner checks), so all ranks stop together
+        bool can = m->max_levels <= 0 || l + 1 < m->max_levels;
         for ( int d = 0; d < D; ++d )
             can = can && n[d] % 2 == 0 && n[d] / 2 >= 2;
         if ( !can )
@@ -553,13 +656,74 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega )
     return CFB_OK;
 }
 
+// Several blocks: refresh the one-cell ghost layers of a level array from the face neighbours (pack kernel,
+// one grouped NCCL send/recv, unpack kernel; 7-point operator and cell-local transfers: faces only).
+int mg_exchange( cfb_ctx* c, MgLevelHost& H, double* arr, int* launches )
+{
+    if ( !c->cfg.use_nccl )
+        return CFB_OK;
+    const MgLevelDev& L = H.d;
+    MgFaces pk{}, up{};
+    size_t counts[6] = { 0, 0, 0, 0, 0, 0 };
+    long long mx = 1;
+    for ( int s = 0; s < 6; ++s )
+    {
+        if ( c->nbr[s] < 0 )
+            continue;
+        const int d = s / 2, side = s % 2;
+        const long long cnt = (long long)L.n[0] * L.n[1] * L.n[2] / L.n[d];
+        counts[s] = (size_t)cnt;
+        mx = cnt > mx ? cnt : mx;
+        pk.dim[pk.nface] = up.dim[up.nface] = d;
+        pk.src[pk.nface] = side == 0 ? 0 : L.n[d] - 1; // my first layer -> low neighbour, my last -> high
+        up.dst[up.nface] = side == 0 ? -1 : L.n[d];    // its last layer -> my low ghost, its first -> my high
+        pk.buf[pk.nface++] = c->d_halo_send[s];
+        up.buf[up.nface++] = c->d_halo_recv[s];
+    }
+    if ( pk.nface == 0 )
+        return CFB_OK;
+    long long bx = ( mx + NT - 1 ) / NT;
+    const long long cap = (long long)c->sm_count * 4;
+    dim3 grid( (unsigned)( bx > cap ? cap : bx ), (unsigned)pk.nface );
+    mg_face_kernel<true><<<grid, NT, 0, c->stream>>>( L, pk, arr );
+    int rc = halo_sendrecv_slots( c, counts, c->stream );
+    if ( rc )
+        return rc;
+    mg_face_kernel<false><<<grid, NT, 0, c->stream>>>( L, up, arr );
+    *launches += 2;
+    return CFB_OK;
+}
+
+// Several blocks: all-gather the local double-doubles left in S->loc by the last reduction and combine
+// them exactly (see mgcg_combine_kernel for `what`).
+int mg_global_sum( cfb_ctx* c, int what, int* launches )
+{
+    if ( !c->cfg.use_nccl )
+        return CFB_OK;
+    int rc = halo_allgather( c, &c->d_state->loc[0], c->d_state->gath, what == 3 ? 4 : 2 );
+    if ( rc )
+        return rc;
+    mgcg_combine_kernel<<<1, 1, 0, c->stream>>>( c->d_state, what );
+    *launches += 1;
+    return CFB_OK;
+}
+
+#define MG_TRY( expr )                                                                             \
+    do                                                                                             \
+    {                                                                                              \
+        int _rc = ( expr );                                                                        \
+        if ( _rc )                                                                                 \
+            return _rc;                                                                            \
+    } while ( 0 )
+
 // the first `sweeps` (>= 1) smoothing sweeps of a level from a zero initial guess
-int launch_presmooth( cfb_ctx* c, MgLevelHost& H, int sweeps )
+int launch_presmooth( cfb_ctx* c, MgLevelHost& H, int sweeps, int* n )
 {
     const int grid = grid_for( c, H.cells );
-    int n = 1, done;
+    int done;
     if ( sweeps >= 2 )
     {
+        MG_TRY( mg_exchange( c, H, H.b, n ) ); // the fused pair reads b of the six neighbours
         mg_smooth02_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[1] );
         H.cur = 1; // where the unfused pair of sweeps leaves its result
         done = 2;
@@ -570,18 +734,21 @@ int launch_presmooth( cfb_ctx* c, MgLevelHost& H, int sweeps )
         H.cur = 0;
         done = 1;
     }
-    for ( ; done < sweeps; ++done, ++n )
+    *n += 1;
+    for ( ; done < sweeps; ++done )
     {
+        MG_TRY( mg_exchange( c, H, H.x[H.cur], n ) );
         mg_smooth_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur] );
         H.cur = 1 - H.cur;
+        *n += 1;
     }
-    return n;
+    return CFB_OK;
 }
 
-// One V-cycle on level l.  `dot` (fine level only, from the CG): the sweep that produces the level's
-// result also accumulates sum z.r into S->rz_new; returns through *dotted whether it did (it cannot
-// when there is no post-smoothing sweep).
-int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted )
+// One V-cycle on level l; *n counts the launches.  `dot` (fine level only, from the CG): the sweep that
+// produces the level's result also accumulates sum z.r; *dotted tells whether it did (it cannot when there
+// is no post-smoothing sweep).
+int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
 {
     MgStage* m = c->mg;
     MgLevelHost& H = m->lv[l];
@@ -589,18 +756,22 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted )
     const int grid = grid_for( c, H.cells );
     if ( dotted )
         *dotted = false;
-    int n = launch_presmooth( c, H, last ? m->nuc : m->nu1 );
+    MG_TRY( launch_presmooth( c, H, last ? m->nuc : m->nu1, n ) );
     if ( last )
-        return n;
+        return CFB_OK;
     MgLevelHost& C = m->lv[l + 1];
+    MG_TRY( mg_exchange( c, H, H.x[H.cur], n ) ); // the residual reads x of the six neighbours
     mg_restrict_kernel<<<grid_for( c, C.cells ), NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.b );
-    n += 1;
-    n += vcycle( c, l + 1, false, nullptr );
+    *n += 1;
+    MG_TRY( vcycle( c, l + 1, false, nullptr, n ) );
     if ( m->nu2 == 0 )
     {
         mg_prolong_kernel<<<grid, NT, 0, c->stream>>>( H.d, C.d, H.x[H.cur], C.x[C.cur] );
-        return n + 1;
+        *n += 1;
+        return CFB_OK;
     }
+    // x[cur] still has the ghosts exchanged for the restriction; the coarse correction needs its own
+    MG_TRY( mg_exchange( c, C, C.x[C.cur], n ) );
     const bool dot_here = dot && m->nu2 == 1;
     if ( dot_here )
         mg_prolong_smooth_kernel<true><<<grid, NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.x[C.cur],
@@ -609,20 +780,21 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted )
         mg_prolong_smooth_kernel<false><<<grid, NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.x[C.cur],
                                                                     H.x[1 - H.cur], c->d_state, c->d_partials );
     H.cur = 1 - H.cur;
-    n += 1;
+    *n += 1;
     for ( int s = 1; s < m->nu2; ++s )
     {
+        MG_TRY( mg_exchange( c, H, H.x[H.cur], n ) );
         if ( dot && s == m->nu2 - 1 )
             mg_smooth_dot_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur], c->d_state,
                                                              c->d_partials );
         else
             mg_smooth_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur] );
         H.cur = 1 - H.cur;
-        n += 1;
+        *n += 1;
     }
     if ( dotted )
         *dotted = dot;
-    return n;
+    return CFB_OK;
 }
 
 } // namespace
@@ -645,7 +817,9 @@ int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     const size_t head = offsetof( CgState, hist );
     long long launches = 0;
 
+    int nl = 0; // launches counted by the helpers
     mgcg_init_kernel<<<grid, NT, 0, c->stream>>>( L, c->rhs, c->lhs, c->cg_r, S, c->d_partials, fixed );
+    MG_TRY( mg_global_sum( c, 0, &nl ) );
     mgcg_check0_kernel<<<1, 1, 0, c->stream>>>( S, c->cfg.cg_tolerance, c->cfg.cg_stop_rule == CFB_STOP_REL );
     launches += 2;
 
@@ -655,18 +829,24 @@ int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     {
         // one iteration: z = M^-1 r ; z.r ; p = z + beta p ; q = A p, p.q ; x, r, r.r, stopping test
         bool dotted = false;
-        launches += vcycle( c, 0, true, &dotted );
+        MG_TRY( vcycle( c, 0, true, &dotted, &nl ) );
         const double* z = F.x[F.cur];
         if ( !dotted ) // no post-smoothing sweep to fuse z.r into
         {
             mgcg_dot_kernel<<<grid, NT, 0, c->stream>>>( L, z, c->cg_r, S, c->d_partials );
             launches += 1;
         }
+        MG_TRY( mg_global_sum( c, 1, &nl ) );
         mgcg_pupdate_kernel<<<grid, NT, 0, c->stream>>>( L, z, c->cg_p, S, enq == 0 ? 1 : 0 );
         launches += 1;
+        if ( c->cfg.use_nccl )
+            MG_TRY( halo_exchange_cells( c, c->cg_p, 1 ) );
         launches += launch_stencil_dot( c );
+        if ( c->cfg.use_nccl )
+            MG_TRY( cg_global_sum( c, 0 ) );
         mgcg_axpy_kernel<<<grid, NT, 0, c->stream>>>( L, c->cg_p, c->cg_q, c->lhs, c->cg_r, S, c->d_partials );
         launches += 1;
+        MG_TRY( mg_global_sum( c, 2, &nl ) );
         ++enq;
         if ( fixed )
             continue;
@@ -687,6 +867,7 @@ int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     if ( m->singular )
     {
         mgcg_nullsum_kernel<<<grid, NT, 0, c->stream>>>( L, c->lhs, S, c->d_partials );
+        MG_TRY( mg_global_sum( c, 3, &nl ) );
         mgcg_shift_kernel<<<grid, NT, 0, c->stream>>>( L, c->lhs, S );
         launches += 2;
     }
@@ -695,7 +876,7 @@ int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     cudaError_t e = cudaGetLastError();
     if ( e != cudaSuccess )
         return cfb_fail( c, CFB_ERR_CUDA, std::string( "mg_pcg_solve: " ) + cudaGetErrorString( e ) );
-    c->stats.kernel_launches += launches;
+    c->stats.kernel_launches += launches + nl;
     c->last_iters = c->h_state->iter;
     c->last_resid = std::sqrt( c->h_state->rr );
     c->stats.cg_iterations += c->last_iters;
@@ -719,13 +900,32 @@ extern "C" int cfb_set_preconditioner( cfb_ctx* c, int kind, int nu_pre, int nu_
         c->precond = CFB_PRECOND_JACOBI;
         return CFB_OK;
     }
-    if ( c->cfg.world_size > 1 || nu_pre < 1 || nu_post < 0 || nu_coarse < 1 || omega >= 2.0 )
+    if ( nu_pre < 1 || nu_post < 0 || nu_coarse < 1 || omega >= 2.0 )
         return cfb_fail( c, CFB_ERR_INVALID,
-                         "multigrid preconditioner: single block, nu_pre >= 1, nu_post >= 0, nu_coarse >= 1, omega < 2" );
-    int rc = mg_build( c, nu_pre, nu_post, nu_coarse, omega );
+                         "multigrid preconditioner: nu_pre >= 1, nu_post >= 0, nu_coarse >= 1, omega < 2" );
+    // several blocks: the levels are coarsened block by block, which needs identical block extents
+    for ( int d = 0; d < c->g.D; ++d )
+        if ( c->cfg.global_num_cell[d] % c->cfg.ranks_per_dim[d] != 0 )
+            return cfb_fail( c, CFB_ERR_INVALID,
+                             "multigrid preconditioner: the cells of every dimension must divide evenly among the blocks" );
+    int rc = mg_build( c, nu_pre, nu_post, nu_coarse, omega, c->mg_max_levels );
     if ( rc )
         return rc;
     c->precond = CFB_PRECOND_MG;
+    return CFB_OK;
+}
+
+extern "C" int cfb_set_mg_max_levels( cfb_ctx* c, int max_levels )
+{
+    c->mg_max_levels = max_levels;
+    if ( c->precond == CFB_PRECOND_MG && c->mg )
+        return mg_build( c, c->mg->nu1, c->mg->nu2, c->mg->nuc, c->mg->omega, max_levels );
+    return CFB_OK;
+}
+
+extern "C" int cfb_mg_num_levels( cfb_ctx* c, int* levels )
+{
+    *levels = c->mg ? (int)c->mg->lv.size() : 0;
     return CFB_OK;
 }
 
@@ -741,7 +941,11 @@ extern "C" int cfb_mg_apply( cfb_ctx* c, const double* r_host, double* z_host )
         return rc;
     MgLevelHost& F = m->lv[0];
     F.b = c->cg_r;
-    c->stats.kernel_launches += vcycle( c, 0, false, nullptr );
+    int nl = 0;
+    rc = vcycle( c, 0, false, nullptr, &nl );
+    if ( rc )
+        return rc;
+    c->stats.kernel_launches += nl;
     const Geo& g = c->g;
     const double* z = F.x[F.cur] + g.origin;
     cudaMemcpy3DParms p{};

@@ -312,9 +312,15 @@ int cfb_set_cg_params( cfb_ctx* ctx, double tolerance, int max_iter, int print_l
  * geometric multigrid V(nu_pre, nu_post) cycle per CG iteration (damped-Jacobi smoother with damping
  * `omega`, <= 0 picks 6/7 in 3-D and 0.8 in 2-D; nu_coarse sweeps on the coarsest level; 2:1 cell-centred
  * coarsening while all extents stay even).  Same matrix, same stopping test, same solution to the
- * solver tolerance, O(10) iterations instead of O(n).  Single block (world_size == 1) for now. */
+ * solver tolerance, O(10) iterations instead of O(n).  With several blocks the same global cycle runs
+ * block-decomposed (one-layer face exchange per operator application; the cells of every dimension must
+ * divide evenly among the blocks), so iteration counts and results do not depend on the decomposition. */
 int cfb_set_preconditioner( cfb_ctx* ctx, int kind, int nu_pre, int nu_post, int nu_coarse, double omega );
 
+/* Cap on the number of multigrid levels (0 = as many as the grid allows: coarsening goes on while every
+ * block's extents stay even and >= 2 after halving) and the depth in use. */
+int cfb_set_mg_max_levels( cfb_ctx* ctx, int max_levels );
+int cfb_mg_num_levels( cfb_ctx* ctx, int* levels );
 /* One application of the multigrid preconditioner on its own, z = M^-1 r, for dense owned-cell HOST
  * arrays (introspection / tests; overwrites the CG work vector r). */
 int cfb_mg_apply( cfb_ctx* ctx, const double* r_host, double* z_host );

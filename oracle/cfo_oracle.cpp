@@ -167,6 +167,7 @@ struct cfo_ctx
     // opt-in multigrid preconditioner (cfo_set_preconditioner; NOT the reference's: see mg_* below)
     int precond = 0; // 0 = the reference's diagonal (Jacobi) preconditioner, 1 = geometric multigrid V-cycle
     int mg_nu1 = 2, mg_nu2 = 2, mg_nuc = 8;
+    int mg_max_levels = 0; // 0 = as many as the grid allows
     double mg_omega = 0.0;
     struct Mg* mg = nullptr;
 
@@ -657,7 +658,7 @@ void mg_build( cfo_ctx& c )
         L.b.alloc( ext );
         L.x[0].alloc( ext );
         L.x[1].alloc( ext );
-        bool can = true;
+        bool can = c.mg_max_levels <= 0 || l + 1 < c.mg_max_levels;
         for ( int d = 0; d < D; ++d )
             can = can && n[d] % 2 == 0 && n[d] / 2 >= 2;
         if ( !can )
@@ -1412,6 +1413,21 @@ int cfo_set_preconditioner( cfo_ctx* c, int kind, int nu_pre, int nu_post, int n
         c->mg_omega = omega;
         mg_build( *c );
     }
+    return CFB_OK;
+}
+
+// Cap on the number of multigrid levels (0 = as many as the grid allows).  A block-decomposed run of the
+// product coarsens while every BLOCK stays even; the single-block checker is given the same depth.
+int cfo_set_mg_max_levels( cfo_ctx* c, int max_levels )
+{
+    c->mg_max_levels = max_levels;
+    if ( c->precond == 1 )
+        mg_build( *c );
+    return CFB_OK;
+}
+int cfo_mg_num_levels( cfo_ctx* c, int* levels )
+{
+    *levels = c->mg ? (int)c->mg->lv.size() : 0;
     return CFB_OK;
 }
 

@@ -105,6 +105,8 @@ def build(force=False):
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     # -ffp-contract=off: like nvcc -fmad=false, only the explicit fma() calls fuse
     cmd = [cxx, "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-pthread",
+           # the real library may be loaded in the same process (RTLD_GLOBAL): bind our own symbols to ourselves
+           "-Wl,-Bsymbolic",
            "-Ddlopen=cfb_emul_dlopen", "-Ddlsym=cfb_emul_dlsym", "-Ddlerror=cfb_emul_dlerror",
            "-I", OUT, "-o", LIB] + cpp
     p = subprocess.run(cmd, capture_output=True, text=True)

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--blocks", type=int, nargs=3, default=None, help="block grid (default: split z, y, x)")
     ap.add_argument("--skip-steps", action="store_true", help="only the stencil / gather / PCG sections")
     ap.add_argument("--quick", action="store_true", help="only the PCG section, three exchange modes")
+    ap.add_argument("--mg", action="store_true", help="only the multigrid-preconditioner section")
     args = ap.parse_args()
     rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
     torch.cuda.set_device(local)
@@ -64,11 +65,14 @@ def main():
             failures.append(f"rank {rank}: {name} {detail}")
 
     rng = np.random.default_rng(77)
-    if not args.quick:
-        sections_1_2(args, rank, gcfg, rank_cfg, rng, check)
-    section_3(args, rank, gcfg, rank_cfg, rng, check)
-    if not (args.quick or args.skip_steps):
-        section_4(args, rank, gcfg, rank_cfg, check)
+    if args.mg:
+        section_5(args, rank, blocks, gcfg, rank_cfg, rng, check)
+    else:
+        if not args.quick:
+            sections_1_2(args, rank, gcfg, rank_cfg, rng, check)
+        section_3(args, rank, gcfg, rank_cfg, rng, check)
+        if not (args.quick or args.skip_steps):
+            section_4(args, rank, gcfg, rank_cfg, check)
 
     flag = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(flag)
@@ -183,6 +187,46 @@ def section_4(args, rank, gcfg, rank_cfg, check):
         gl = np.linalg.norm(ora.get(f).ravel())
         ea = np.linalg.norm((gpu.get(f) - ora.get(f)[block_slices(gpu, f)]).ravel()) / max(gl, 1e-300)
         check(f"step field {f}", min(e, ea) < 1e-10, f"rel l2 {e} (vs global norm {ea})")
+    gpu.close()
+    ora.close()
+
+
+def section_5(args, rank, blocks, gcfg, rank_cfg, rng, check):
+    # 5. opt-in multigrid preconditioner: the same global V-cycle, block-decomposed --------------------------
+    n = [c // b for c, b in zip(args.cells, blocks)]
+    levels = 1
+    while all(e % 2 == 0 and e // 2 >= 2 for e in n):
+        n = [e // 2 for e in n]
+        levels += 1
+    ora = Oracle(gcfg())
+    ora.set_mg_max_levels(levels)  # the blocks stop coarsening when a BLOCK extent becomes odd
+    ora.set_preconditioner("mg")
+    r = rng.standard_normal(ora.shape(K.PRESSURE))
+    z = ora.mg_apply(r)
+    vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
+    for f, a in vel.items():
+        ora.set(f, a)
+    ora.add_inputs()
+    ora.build_rhs()
+    io, ro = ora.pcg_solve()
+    po, ho = ora.get(K.PRESSURE), ora.residual_history()
+    gpu = Solver(rank_cfg())
+    gpu.set_preconditioner("mg")
+    check("mg levels", gpu.mg_num_levels() == levels, f"{gpu.mg_num_levels()} vs {levels}")
+    sl = block_slices(gpu, K.PRESSURE)
+    zg = gpu.mg_apply(r[sl])
+    check("V-cycle 1e-13", rel_l2(zg, z[sl]) < 1e-13, f"rel l2 {rel_l2(zg, z[sl])}")
+    check("V-cycle bit-exact", np.array_equal(zg, z[sl]))
+    for f, a in vel.items():
+        gpu.set(f, a[block_slices(gpu, f)])
+    gpu.add_inputs()
+    gpu.build_rhs()
+    ig, rg = gpu.pcg_solve()
+    check("mg-pcg iterations", abs(ig - io) <= 1, f"{ig} vs {io}")
+    e = rel_l2(gpu.get(K.PRESSURE), po[sl])
+    check("mg-pcg pressure 1e-10", e < 1e-10, f"rel l2 {e}")
+    check("mg-pcg pressure bit-exact", np.array_equal(gpu.get(K.PRESSURE), po[sl]))
+    check("mg-pcg residual history bit-exact", np.array_equal(gpu.residual_history(), ho))
     gpu.close()
     ora.close()
 

@@ -45,6 +45,8 @@ def load():
         d.cfo_set_callbacks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         d.cfo_num_threads.restype = C.c_int
         d.cfo_set_accumulation.argtypes = [C.c_void_p, C.c_int]
+        d.cfo_set_mg_max_levels.argtypes = [C.c_void_p, C.c_int]
+        d.cfo_mg_num_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     return _lib
 
 

@@ -24,7 +24,8 @@ from oracle_api import Oracle  # noqa: E402
 
 @pytest.fixture(scope="module")
 def emul():
-    return Library(build_emul.build(), "cfb_")
+    import ctypes
+    return Library(build_emul.build(), "cfb_", mode=ctypes.RTLD_LOCAL)
 
 
 def run(ctx, steps):

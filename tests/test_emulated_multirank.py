@@ -26,7 +26,8 @@ from oracle_api import Oracle  # noqa: E402
 
 @pytest.fixture(scope="module")
 def emul():
-    return Library(build_emul.build(), "cfb_")
+    import ctypes
+    return Library(build_emul.build(), "cfb_", mode=ctypes.RTLD_LOCAL)
 
 
 GRIDS = [(2, None), (4, None), (8, None), (2, (2, 1, 1)), (2, (1, 2, 1)), (4, (2, 2, 1)), (3, (3, 1, 1)), (6, (1, 3, 2))]
@@ -124,3 +125,109 @@ def test_decomposed_steps_and_output_match_the_single_block_oracle(emul, world, 
         assert exact == []
         assert max(err.values()) < 1e-12, err
         assert abs(it - its) <= 3 and t == ora.time
+
+
+# ---- the opt-in multigrid preconditioner, block-decomposed (the same global cycle on every decomposition) ----
+MG_GRIDS = [(2, None, (32, 32, 32)), (4, None, (32, 32, 32)), (8, None, (32, 32, 32)), (2, (2, 1, 1), (32, 24, 16)),
+            (4, (2, 2, 1), (32, 24, 16)), (3, (1, 3, 1), (16, 24, 8)), (8, None, (16, 16, 16))]
+
+
+def mg_levels_of(cells, blocks):
+    """depth of the block-wise coarsening: while every block extent is even and >= 2 after halving"""
+    n = [c // b for c, b in zip(cells, blocks)]
+    lv = 1
+    while all(e % 2 == 0 and e // 2 >= 2 for e in n):
+        n = [e // 2 for e in n]
+        lv += 1
+    return lv
+
+
+@pytest.mark.parametrize("world,blocks,cells", MG_GRIDS)
+@pytest.mark.parametrize("nu", [(2, 2, 8), (1, 1, 3), (3, 0, 2)])
+def test_decomposed_vcycle_is_bit_identical_to_the_single_block_oracle(emul, world, blocks, cells, nu):
+    from cajitafluids_b200.distributed import block_grid
+    cfg = cfg3(cells=cells)
+    bl = blocks or block_grid(world, 3)
+    ora = Oracle(cfg)
+    ora.set_mg_max_levels(mg_levels_of(cells, bl))
+    ora.set_preconditioner("mg", *nu)
+    r = np.random.default_rng(4).standard_normal(ora.shape(K.PRESSURE))
+    z = ora.mg_apply(r)
+
+    def body(ctx, rank):
+        ctx.set_preconditioner("mg", *nu)
+        sl = block_slices(ctx, K.PRESSURE)
+        return ctx.mg_num_levels(), np.array_equal(ctx.mg_apply(r[sl]), z[sl])
+
+    assert run_ranks(emul, cfg, world, body, blocks) == [(ora.mg_num_levels(), True)] * world
+
+
+@pytest.mark.parametrize("world,blocks,cells", MG_GRIDS)
+def test_decomposed_mg_pcg_is_bit_identical_to_the_single_block_oracle(emul, world, blocks, cells):
+    from cajitafluids_b200.distributed import block_grid
+    cfg = cfg3(cells=cells)
+    bl = blocks or block_grid(world, 3)
+    ora = Oracle(cfg)
+    ora.set_mg_max_levels(mg_levels_of(cells, bl))
+    ora.set_preconditioner("mg")
+    rng = np.random.default_rng(77)
+    vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
+    for f, a in vel.items():
+        ora.set(f, a)
+    ora.add_inputs()
+    ora.build_rhs()
+    io, ro = ora.pcg_solve()
+    po, ho = ora.get(K.PRESSURE), ora.residual_history()
+    assert io < 40
+
+    def body(ctx, rank):
+        ctx.set_preconditioner("mg")
+        for f, a in vel.items():
+            ctx.set(f, a[block_slices(ctx, f)])
+        ctx.add_inputs()
+        ctx.build_rhs()
+        ig, rg = ctx.pcg_solve()
+        return ig, rg, np.array_equal(ctx.get(K.PRESSURE), po[block_slices(ctx, K.PRESSURE)]), \
+            np.array_equal(ctx.residual_history(), ho)
+
+    for res in run_ranks(emul, cfg, world, body, blocks):
+        assert res == (io, ro, True, True), res
+
+
+def test_decomposed_mg_steps_match_the_single_block_oracle(emul):
+    cells = (32, 32, 32)
+    cfg = cfg3(cells=cells)
+    ora = Oracle(cfg)
+    ora.set_mg_max_levels(mg_levels_of(cells, (2, 2, 2)))
+    ora.set_preconditioner("mg")
+    ora.setup()
+    want0 = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
+    ora.step()
+    want = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
+    gl = {f: max(np.linalg.norm(want[f].ravel()), 1e-300) for f in want}
+    its = ora.stats()["cg_iterations"]
+
+    def body(ctx, rank):
+        ctx.set_preconditioner("mg")
+        ctx.setup()
+        exact = [f for f in want0 if not np.array_equal(ctx.get(f), want0[f][block_slices(ctx, f)])]
+        ctx.step()
+        err = {f: float(np.linalg.norm((ctx.get(f) - want[f][block_slices(ctx, f)]).ravel()) / gl[f]) for f in want}
+        return exact, err, ctx.stats()["cg_iterations"]
+
+    for exact, err, it in run_ranks(emul, cfg, 8, body):
+        assert exact == [] and max(err.values()) < 1e-12 and abs(it - its) <= 1, (exact, err, it, its)
+
+
+def test_mg_needs_evenly_divided_blocks(emul):
+    from cajitafluids_b200 import CfbError
+    cfg = cfg3(cells=(30, 20, 18))  # 30 cells over 4 blocks
+
+    def body(ctx, rank):
+        try:
+            ctx.set_preconditioner("mg")
+        except CfbError as e:
+            return "divide evenly" in str(e)
+        return False
+
+    assert run_ranks(emul, cfg, 4, body, (4, 1, 1)) == [True] * 4

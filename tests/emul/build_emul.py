@@ -16,6 +16,8 @@ OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libcfb_emul.so")
 SOURCES = ["cfb_api.cu", "kernels_fields.cu", "kernels_cg.cu", "mg.cu", "output.cu", "halo.cu"]
 HEADERS = ["cfb_internal.h", "device_geo.cuh"]
+# kernels whose threads meet at __syncthreads() for real: one fiber per CUDA thread
+COOP_KERNELS = {"cg_xchg_kernel"}
 STANDINS = ["cuda_runtime.h", "cuda.h", "nccl.h", "device_reduce.cuh", "emul_glue.cpp", "nccl_emul.cpp"]
 
 
@@ -75,7 +77,8 @@ def rewrite_launches(src):
         a0 = src.index("(", j)
         a1 = _match(src, a0, "(", ")")
         args = src[a0 + 1:a1 - 1]
-        out += src[pos:start] + (f"cfb_emul::launch( dim3( {cfg[0]} ), dim3( {cfg[1]} ), [&]() {{ {kernel}( {args} ); }} )")
+        fn = "launch_coop" if kernel.strip() in COOP_KERNELS else "launch"
+        out += src[pos:start] + (f"cfb_emul::{fn}( dim3( {cfg[0]} ), dim3( {cfg[1]} ), [&]() {{ {kernel}( {args} ); }} )")
         pos = a1
 
 

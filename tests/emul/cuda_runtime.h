@@ -20,7 +20,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__( ... )
 #define __grid_constant__
-#define __shared__ static
+#define __shared__ static thread_local /* one block at a time per rank thread; fibers share it */
 
 struct uint3
 {
@@ -47,6 +47,12 @@ extern thread_local dim3 g_blockDim, g_gridDim;
 // blocks in order; inside a block the threads run one after the other from the LAST to the first, so
 // that thread 0 — the one that finalises block reductions — sees every other thread's contribution
 void launch( dim3 grid, dim3 block, const std::function<void()>& body );
+// cooperative form for kernels whose threads really meet at __syncthreads() (the peer-memory exchange
+// kernel): every CUDA thread of a block is a fiber (ucontext); a fiber that reaches __syncthreads() yields,
+// and all live fibers of the block pass the barrier together.  Blocks run in order.
+void launch_coop( dim3 grid, dim3 block, const std::function<void()>& body );
+void sync_threads(); // no-op outside launch_coop
+long long clock_ns();
 } // namespace cfb_emul
 #define threadIdx cfb_emul::g_threadIdx
 #define blockIdx cfb_emul::g_blockIdx
@@ -57,9 +63,9 @@ template <class T>
 inline T __ldg( const T* p ) { return *p; }
 template <class T>
 inline T __ldcg( const T* p ) { return *p; }
-inline void __syncthreads() {}
-inline void __threadfence() {}
-inline void __threadfence_system() {}
+inline void __syncthreads() { cfb_emul::sync_threads(); }
+inline void __threadfence() { __atomic_thread_fence( __ATOMIC_SEQ_CST ); }
+inline void __threadfence_system() { __atomic_thread_fence( __ATOMIC_SEQ_CST ); }
 inline unsigned atomicAdd( unsigned* p, unsigned v )
 {
     unsigned o = *p;
@@ -153,16 +159,25 @@ inline cudaError_t cudaMemcpy3DAsync( const cudaMemcpy3DParms* p, cudaStream_t )
                          s + ( z * p->srcPtr.ysize + y ) * p->srcPtr.pitch, p->extent.width );
     return cudaSuccess;
 }
-// no peer memory in the emulation: the NVLink exchange path reports "not available"
+// "peer memory": the ranks of an emulated run are threads of one process, so a handle is the pointer itself
 struct cudaIpcMemHandle_t
 {
     char reserved[64];
 };
 enum { cudaIpcMemLazyEnablePeerAccess = 1 };
-inline cudaError_t cudaIpcGetMemHandle( cudaIpcMemHandle_t*, void* ) { return cudaErrorEmul; }
-inline cudaError_t cudaIpcOpenMemHandle( void**, cudaIpcMemHandle_t, unsigned ) { return cudaErrorEmul; }
+inline cudaError_t cudaIpcGetMemHandle( cudaIpcMemHandle_t* h, void* p )
+{
+    std::memset( h, 0, sizeof( *h ) );
+    std::memcpy( h->reserved, &p, sizeof( p ) );
+    return cudaSuccess;
+}
+inline cudaError_t cudaIpcOpenMemHandle( void** out, cudaIpcMemHandle_t h, unsigned )
+{
+    std::memcpy( out, h.reserved, sizeof( *out ) );
+    return cudaSuccess;
+}
 inline cudaError_t cudaIpcCloseMemHandle( void* ) { return cudaSuccess; }
-inline long long clock64() { return 0; }
+inline long long clock64() { return cfb_emul::clock_ns(); }
 
 inline cudaError_t cudaStreamCreateWithFlags( cudaStream_t* s, unsigned )
 {

@@ -2,12 +2,16 @@
 // library that cannot be emulated (TMA / mbarrier kernels, NCCL / peer-memory exchange).
 //   * q = A p, sum p.q  (the TMA stencil kernel, verified on the GPU)  -> a plain loop with the same row
 //     arithmetic (apply_row) and the same exactly-accumulated dot product
-//   * the two-kernel fused CG form  -> not available: the emulated context runs the three-kernel form
+//   * the two-kernel fused CG form  -> plain loops with the kernels' semantics (phase A, phase B, finish)
 //   * multi-GPU: halo.cu itself is compiled; NCCL is the in-process stand-in of nccl_emul.cpp (ranks are
 //     threads), the NVLink peer-memory path reports "not available" (cudaIpc stand-ins fail)
 #include "cfb_internal.h"
 #include "device_geo.cuh"
 #include "device_reduce.cuh"
+
+#include <chrono>
+#include <ucontext.h>
+#include <vector>
 
 namespace cfb_emul
 {
@@ -31,6 +35,92 @@ void launch( dim3 grid, dim3 block, const std::function<void()>& body )
                             body();
                         }
             }
+}
+
+long long clock_ns()
+{
+    return std::chrono::duration_cast<std::chrono::nanoseconds>( std::chrono::steady_clock::now().time_since_epoch() )
+        .count();
+}
+
+// ---- cooperative launch: one fiber per CUDA thread -------------------------------------------------
+namespace
+{
+struct Fiber
+{
+    ucontext_t ctx;
+    std::vector<char> stack;
+    bool finished = false;
+};
+struct Coop
+{
+    bool active = false;
+    ucontext_t sched;
+    std::vector<Fiber> fibers;
+    int current = -1;
+    const std::function<void()>* body = nullptr;
+};
+thread_local Coop t_coop;
+
+void fiber_entry()
+{
+    Coop& c = t_coop;
+    ( *c.body )();
+    c.fibers[c.current].finished = true;
+    swapcontext( &c.fibers[c.current].ctx, &c.sched );
+}
+} // namespace
+
+void sync_threads()
+{
+    Coop& c = t_coop;
+    if ( !c.active )
+        return; // sequential launch: kernels that get here do not depend on the barrier
+    swapcontext( &c.fibers[c.current].ctx, &c.sched ); // yield; resumed when every live fiber has arrived
+}
+
+void launch_coop( dim3 grid, dim3 block, const std::function<void()>& body )
+{
+    Coop& c = t_coop;
+    const unsigned nt = block.x; // 1-D blocks only
+    g_gridDim = grid;
+    g_blockDim = block;
+    c.body = &body;
+    if ( c.fibers.size() < nt )
+        c.fibers.resize( nt );
+    for ( unsigned bx = 0; bx < grid.x; ++bx )
+    {
+        g_blockIdx = uint3{ bx, 0, 0 };
+        for ( unsigned t = 0; t < nt; ++t )
+        {
+            Fiber& f = c.fibers[t];
+            if ( f.stack.empty() )
+                f.stack.resize( 256 * 1024 );
+            f.finished = false;
+            getcontext( &f.ctx );
+            f.ctx.uc_stack.ss_sp = f.stack.data();
+            f.ctx.uc_stack.ss_size = f.stack.size();
+            f.ctx.uc_link = nullptr;
+            makecontext( &f.ctx, fiber_entry, 0 );
+        }
+        c.active = true;
+        unsigned live = nt;
+        while ( live > 0 )
+        {
+            // one pass = every live fiber runs up to its next barrier (or to its end), in thread order
+            for ( unsigned t = 0; t < nt; ++t )
+            {
+                if ( c.fibers[t].finished )
+                    continue;
+                c.current = (int)t;
+                g_threadIdx = uint3{ t, 0, 0 };
+                swapcontext( &c.sched, &c.fibers[t].ctx );
+                if ( c.fibers[t].finished )
+                    --live;
+            }
+        }
+        c.active = false;
+    }
 }
 } // namespace cfb_emul
 
@@ -74,12 +164,143 @@ int launch_stencil_dot( cfb_ctx* c )
     return 1;
 }
 
+// ---- the two-kernel CG form (kernels_fused.cu: TMA, not emulable) as plain loops -------------------------
+// Same semantics, statement for statement, as cg_rupdate_kernel / cg_fused_kernel / cg_finish_kernel, so that
+// the host orchestration around them (p double-buffering, done / finish logic, polling, and above all the
+// NVLink peer-memory exchange, whose kernel IS the product's) runs on the CPU.
 int fused_setup( cfb_ctx* c )
 {
-    c->cg_variant = 0; // three-kernel CG form: the fused TMA kernels cannot be emulated
-    c->fused_ok = false;
+    c->fused_ok = true;
     return CFB_OK;
 }
-int launch_cg_rupdate( cfb_ctx* c ) { return cfb_fail( c, CFB_ERR_INVALID, "emul: fused CG form unavailable" ), 0; }
-int launch_cg_fused( cfb_ctx* c, int ) { return cfb_fail( c, CFB_ERR_INVALID, "emul: fused CG form unavailable" ), 0; }
-int launch_cg_finish( cfb_ctx* ) { return 0; }
+
+namespace
+{
+inline bool cg_converged( const CgState* S ) { return !S->fixed && std::sqrt( S->rr ) <= S->thresh; }
+inline int walls_at( const Geo& g, int i, int j, int k )
+{
+    return wall_count( g, 0, i + g.off[0] ) + wall_count( g, 1, j + g.off[1] ) + wall_count( g, 2, k + g.off[2] );
+}
+} // namespace
+
+// phase A: alpha = zr_old / pAp ; r -= alpha q ; sum r^2 ; sum r.M^-1 r
+int launch_cg_rupdate( cfb_ctx* c )
+{
+    const Geo& g = c->g;
+    const OpConst& op = c->op;
+    CgState* S = c->d_state;
+    if ( S->done || ( S->iter > 0 && cg_converged( S ) ) )
+    {
+        S->done = 1;
+        return 1;
+    }
+    const double alpha = S->rz_old / S->pAp, nalpha = -alpha;
+    S->alpha = alpha;
+    dd_t rr{ 0.0, 0.0 }, rz{ 0.0, 0.0 };
+    double* r = c->cg_r;
+    const double* q = c->cg_q;
+    for ( int k = 0; k < g.n[2]; ++k )
+        for ( int j = 0; j < g.n[1]; ++j )
+            for ( int i = 0; i < g.n[0]; ++i )
+            {
+                const long long o = geo_off( g, i, j, k );
+                const double v = fma( nalpha, q[o], r[o] );
+                r[o] = v;
+                dd_acc( rr, v * v );
+                dd_acc( rz, ( op.minv[walls_at( g, i, j, k )] * v ) * v );
+            }
+    if ( S->world > 1 )
+    {
+        S->loc[2] = rz.hi;
+        S->loc[3] = rz.lo;
+        S->loc[4] = rr.hi;
+        S->loc[5] = rr.lo;
+    }
+    else
+    {
+        S->rr = rr.hi + rr.lo;
+        S->rz_new = rz.hi + rz.lo;
+    }
+    return 1;
+}
+
+int launch_cg_finish( cfb_ctx* c )
+{
+    CgState* S = c->d_state;
+    if ( !S->done && S->iter > 0 && cg_converged( S ) )
+        S->done = 1;
+    return 1;
+}
+
+// phase B: convergence test ; x += alpha p ; beta ; p_new = M^-1 r + beta p (also on the one-cell ghost ring,
+// recomputed from the ghosts of r and of the old p, never stored there) ; q = A p_new ; sum p.q
+// which: 0 = all units, 1 = "interior" (everything here), 2 = "boundary" (nothing left)
+int launch_cg_fused( cfb_ctx* c, int which )
+{
+    if ( which == 2 )
+        return 0;
+    const Geo& g = c->g;
+    const OpConst& op = c->op;
+    CgState* S = c->d_state;
+    if ( S->done )
+        return 1;
+    double* x = c->lhs;
+    const double* p_old = c->cg_pbuf[c->pcur];
+    double* p_new = c->cg_pbuf[c->pcur ^ 1];
+    const double* r = c->cg_r;
+    double* q = c->cg_q;
+    const double alpha = S->alpha;
+    const double resid = std::sqrt( S->rr );
+    const bool conv = !S->fixed && resid <= S->thresh;
+    {
+        const int it = S->iter;
+        if ( it < CFB_HIST_MAX )
+            S->hist[it] = resid;
+        S->iter = it + 1;
+    }
+    if ( conv )
+    {
+        for ( int k = 0; k < g.n[2]; ++k )
+            for ( int j = 0; j < g.n[1]; ++j )
+                for ( int i = 0; i < g.n[0]; ++i )
+                {
+                    const long long o = geo_off( g, i, j, k );
+                    x[o] = fma( alpha, p_old[o], x[o] );
+                }
+        return 1;
+    }
+    const double beta = S->rz_new / S->rz_old;
+    std::vector<double> pn( (size_t)g.total, 0.0 );
+    for ( int k = -1; k <= g.n[2]; ++k )
+        for ( int j = -1; j <= g.n[1]; ++j )
+            for ( int i = -1; i <= g.n[0]; ++i )
+            {
+                const int out = ( i < 0 || i >= g.n[0] ) + ( j < 0 || j >= g.n[1] ) + ( k < 0 || k >= g.n[2] );
+                if ( out > 1 )
+                    continue; // edges and corners are never read by the 7-point operator
+                const long long o = geo_off( g, i, j, k );
+                pn[o] = fma( beta, p_old[o], op.minv[walls_at( g, i, j, k )] * r[o] );
+            }
+    dd_t acc{ 0.0, 0.0 };
+    for ( int k = 0; k < g.n[2]; ++k )
+        for ( int j = 0; j < g.n[1]; ++j )
+            for ( int i = 0; i < g.n[0]; ++i )
+            {
+                const long long o = geo_off( g, i, j, k );
+                x[o] = fma( alpha, p_old[o], x[o] );
+                p_new[o] = pn[o];
+                const double a = apply_row( op.diag[walls_at( g, i, j, k )], op.neg_scale, pn[o], pn[o - 1], pn[o + 1],
+                                            pn[o - g.sy], pn[o + g.sy], pn[o - g.sz], pn[o + g.sz] );
+                q[o] = a;
+                dd_acc( acc, pn[o] * a );
+            }
+    if ( S->world > 1 )
+    {
+        S->loc[0] = acc.hi;
+        S->loc[1] = acc.lo;
+    }
+    else
+        S->pAp = acc.hi + acc.lo;
+    S->rz_old = S->rz_new;
+    return 1;
+}

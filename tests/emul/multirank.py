@@ -9,10 +9,12 @@ from cajitafluids_b200._capi import Context
 from cajitafluids_b200.distributed import block_grid, decompose
 
 
-def run_ranks(lib, global_cfg, world, fn, blocks=None, timeout=300):
+def run_ranks(lib, global_cfg, world, fn, blocks=None, timeout=300, peer=False):
     """fn(ctx, rank) -> result, on `world` rank threads; returns the list of results (raises the first
     exception of any rank)."""
-    os.environ["CFB_PEER"] = "0"  # no peer memory in the emulation
+    # peer=True: the NVLink peer-memory exchange of the CG iterations (the ranks share one address space, the
+    # cudaIpc stand-ins hand out plain pointers, the exchange kernel runs with one fiber per CUDA thread)
+    os.environ["CFB_PEER"] = "1" if peer else "0"
     blocks = blocks or block_grid(world, global_cfg.dim)
     ids = (C.c_ubyte * (2 * K.NCCL_ID_BYTES))()
     lib.check(lib.fn["nccl_unique_id"](ids))

@@ -231,3 +231,57 @@ def test_mg_needs_evenly_divided_blocks(emul):
         return False
 
     assert run_ranks(emul, cfg, 4, body, (4, 1, 1)) == [True] * 4
+
+
+# ---- the default multi-GPU path of the CG iterations: NVLink peer-memory exchange (halo.cu: peer_setup,
+# peer_exchange, cg_xchg_kernel, cg_xunpack_kernel are the product's; phases A / B are the plain-loop stand-ins)
+@pytest.mark.parametrize("world,blocks", GRIDS)
+def test_peer_memory_exchange_pcg_is_bit_identical_to_the_single_block_oracle(emul, world, blocks):
+    cfg = cfg3()
+    ora = Oracle(cfg)
+    rng = np.random.default_rng(78)
+    vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
+    for f, a in vel.items():
+        ora.set(f, a)
+    ora.add_inputs()
+    ora.build_rhs()
+    io, ro = ora.pcg_solve()
+    po, ho = ora.get(K.PRESSURE), ora.residual_history()
+
+    def body(ctx, rank):
+        peer = ctx.stats()["peer_mode"]
+        for f, a in vel.items():
+            ctx.set(f, a[block_slices(ctx, f)])
+        out = []
+        for _ in range(2):  # twice: sequence numbers and p buffers carry over from solve to solve
+            ctx.add_inputs()
+            ctx.build_rhs()
+            ig, rg = ctx.pcg_solve()
+            out.append((ig, rg, np.array_equal(ctx.get(K.PRESSURE), po[block_slices(ctx, K.PRESSURE)]),
+                        np.array_equal(ctx.residual_history(), ho)))
+        return peer, out
+
+    for peer, out in run_ranks(emul, cfg, world, body, blocks, peer=True):
+        assert peer == 1
+        assert out == [(io, ro, True, True)] * 2, out
+
+
+@pytest.mark.parametrize("world,blocks", [(2, None), (8, None), (4, (2, 2, 1))])
+def test_peer_memory_exchange_steps_and_fixed_iterations(emul, world, blocks):
+    cfg = cfg3(cells=(32, 24, 16), fixed_iters=25)
+    ora = Oracle(cfg)
+    ora.setup()
+    want0 = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
+    ora.step()
+    want = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
+    gl = {f: max(np.linalg.norm(want[f].ravel()), 1e-300) for f in want}
+
+    def body(ctx, rank):
+        ctx.setup()
+        exact = [f for f in want0 if not np.array_equal(ctx.get(f), want0[f][block_slices(ctx, f)])]
+        ctx.step()
+        err = {f: float(np.linalg.norm((ctx.get(f) - want[f][block_slices(ctx, f)]).ravel()) / gl[f]) for f in want}
+        return ctx.stats()["peer_mode"], exact, err
+
+    for peer, exact, err in run_ranks(emul, cfg, world, body, blocks, peer=True):
+        assert peer == 1 and exact == [] and max(err.values()) < 1e-12, (peer, exact, err)

@@ -440,6 +440,25 @@ def main():
             tts["note"] = ("one pressure solve of the default inflow problem at %d^3 to sqrt(sum r^2) <= 1e-6, "
                            "wall clock incl. convergence polling; mg = opt-in V(2,2) cycle, never the default" % args.cells)
             extra["projection_time_to_solution"] = tts
+            # the same whole timesteps as extra.timesteps_per_s (reference tol / max_iter), with the opt-in
+            # multigrid preconditioner
+            if args.timestep_cells > 0:
+                s4 = Solver(default_config(3, args.timestep_cells))
+                s4.set_preconditioner("mg")
+                s4.setup()
+                for _ in range(2):
+                    s4.step()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                it0 = s4.stats()["cg_iterations"]
+                for _ in range(5):
+                    s4.step()
+                torch.cuda.synchronize()
+                dt4 = time.perf_counter() - t0
+                extra["timesteps_per_s_mg"] = {"cells": [args.timestep_cells] * 3, "value": 5 / dt4,
+                                               "cg_iters_per_step": (s4.stats()["cg_iterations"] - it0) / 5,
+                                               "interp_order": 3, "preconditioner": "opt-in multigrid V(2,2)"}
+                s4.close()
         except Exception as e:  # noqa: BLE001
             extra["projection_time_to_solution"] = {"error": repr(e)[:300]}
 

@@ -196,3 +196,28 @@ def test_emulated_write_output_is_deferred_until_flush(emul, tmp_path):
     assert fq.shape == (32, 32, 32) and fv.shape == (3, 32, 32, 32)
     assert np.array_equal(fq, q0) and np.array_equal(fv, v0)
     assert not np.array_equal(g.output()[0], q0)
+
+
+def test_emulated_bench_entry_points(emul):
+    """The calls bench.py makes: synthetic right-hand side, fixed-count solves (both CG forms), the solver
+    plug-in call with host vectors, the stand-alone stencil."""
+    cfg = make_cfg(3, (24, 20, 16), box=(1.0, 20 / 24, 16 / 24), fixed_iters=12)
+    g, o = Context(emul, cfg), Oracle(cfg)
+    g.fill_synthetic_velocity(0)
+    for f in fields_of(3)[1:]:
+        o.set(f, g.get(f))
+    g.build_rhs()
+    o.build_rhs()
+    b = o.get(K.RHS)
+    assert np.array_equal(g.get(K.RHS), b) and np.abs(b).max() > 0
+    io, ro = o.pcg_solve()
+    po = o.get(K.PRESSURE)
+    for variant in (1, 0):
+        g.set_tuning("cg_variant", variant)
+        ms, rg = g.pcg_fixed(12)
+        assert rg == ro and np.array_equal(g.get(K.PRESSURE), po), variant
+    x, it, res = g.pcg_solve_host(b)
+    assert it == io and res == ro and np.array_equal(x, po)
+    dg, _ = g.stencil_dot(2)
+    do, _ = o.stencil_dot(1)
+    assert np.array_equal(g.get(K.CG_Q), o.get(K.CG_Q)) and abs(dg - do) <= 1e-13 * abs(do)

@@ -285,3 +285,29 @@ def test_peer_memory_exchange_steps_and_fixed_iterations(emul, world, blocks):
 
     for peer, exact, err in run_ranks(emul, cfg, world, body, blocks, peer=True):
         assert peer == 1 and exact == [] and max(err.values()) < 1e-12, (peer, exact, err)
+
+
+@pytest.mark.parametrize("world,blocks,peer", [(2, (1, 2, 1), False), (4, (2, 2, 1), False), (2, (2, 1, 1), True),
+                                               (4, (2, 2, 1), True), (3, (3, 1, 1), True)])
+def test_two_dimensional_block_decomposition(emul, world, blocks, peer):
+    """The reference's own dimensionality, several blocks (quirks Q1 / Q2 on): projection bit for bit, steps to
+    rounding (block-local coordinates)."""
+    cfg = make_cfg(2, (48, 36), box=(1.0, 0.75))
+    ora = Oracle(cfg)
+    ora.setup()
+    want0 = {f: ora.get(f) for f in fields_of(2) + [K.PRESSURE]}
+    for _ in range(2):
+        ora.step()
+    want = {f: ora.get(f) for f in fields_of(2) + [K.PRESSURE]}
+    gl = {f: max(np.linalg.norm(want[f].ravel()), 1e-300) for f in want}
+
+    def body(ctx, rank):
+        ctx.setup()
+        exact = [f for f in want0 if not np.array_equal(ctx.get(f), want0[f][block_slices(ctx, f)])]
+        for _ in range(2):
+            ctx.step()
+        err = {f: float(np.linalg.norm((ctx.get(f) - want[f][block_slices(ctx, f)]).ravel()) / gl[f]) for f in want}
+        return ctx.stats()["peer_mode"], exact, err
+
+    for pm, exact, err in run_ranks(emul, cfg, world, body, blocks, peer=peer):
+        assert pm == (1 if peer else 0) and exact == [] and max(err.values()) < 1e-12, (pm, exact, err)

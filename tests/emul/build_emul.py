@@ -14,11 +14,13 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "cajitafluids_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libcfb_emul.so")
+LIB_TMA = os.path.join(OUT, "libcfb_emul_tma.so")  # the TMA kernels themselves instead of plain-loop stand-ins
+TMA_SOURCES = ["kernels_stencil.cu", "kernels_fused.cu"]
 SOURCES = ["cfb_api.cu", "kernels_fields.cu", "kernels_cg.cu", "mg.cu", "output.cu", "halo.cu"]
 HEADERS = ["cfb_internal.h", "device_geo.cuh"]
 # kernels whose threads meet at __syncthreads() for real: one fiber per CUDA thread
-COOP_KERNELS = {"cg_xchg_kernel"}
-STANDINS = ["cuda_runtime.h", "cuda.h", "nccl.h", "device_reduce.cuh", "emul_glue.cpp", "nccl_emul.cpp"]
+COOP_KERNELS = {"cg_xchg_kernel", "stencil7_dot_tma", "cg_fused_kernel"}
+STANDINS = ["cuda_runtime.h", "cuda.h", "nccl.h", "device_reduce.cuh", "device_tma.cuh", "emul_glue.cpp", "nccl_emul.cpp"]
 
 
 def _match(s, i, open_c, close_c):
@@ -77,23 +79,30 @@ def rewrite_launches(src):
         a0 = src.index("(", j)
         a1 = _match(src, a0, "(", ")")
         args = src[a0 + 1:a1 - 1]
-        fn = "launch_coop" if kernel.strip() in COOP_KERNELS else "launch"
+        fn = "launch_coop" if kernel.strip().split("<")[0] in COOP_KERNELS else "launch"
         out += src[pos:start] + (f"cfb_emul::{fn}( dim3( {cfg[0]} ), dim3( {cfg[1]} ), [&]() {{ {kernel}( {args} ); }} )")
         pos = a1
 
 
-def build(force=False):
+def build(force=False, tma=False):
+    """tma=False: libcfb_emul.so, the TMA kernels replaced by plain-loop stand-ins (fast);
+    tma=True: libcfb_emul_tma.so, kernels_stencil.cu / kernels_fused.cu themselves, one fiber per CUDA thread."""
     os.makedirs(OUT, exist_ok=True)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, f) for f in STANDINS] + \
+    lib = LIB_TMA if tma else LIB
+    sources = SOURCES + (TMA_SOURCES if tma else [])
+    deps = [os.path.join(CSRC, f) for f in sources + HEADERS] + [os.path.join(HERE, f) for f in STANDINS] + \
            [os.path.join(ROOT, "include", "cfb.h"), os.path.abspath(__file__)]
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
-        return LIB
+    if not force and os.path.exists(lib) and all(os.path.getmtime(lib) >= os.path.getmtime(d) for d in deps):
+        return lib
     cpp = []
-    for f in SOURCES:
+    for f in sources:
         src = rewrite_launches(open(os.path.join(CSRC, f)).read())
         # the one piece of inline PTX outside the TMA kernels: a volatile 64-bit load
         src = src.replace('asm volatile( "ld.volatile.global.u64 %0, [%1];" : "=l"( v ) : "l"( p ) : "memory" );',
                           "v = *reinterpret_cast<const volatile unsigned long long*>( p );")
+        # dynamic shared memory: a thread-local buffer of the rank thread
+        src = src.replace("extern __shared__ unsigned char smem_raw[];",
+                          "unsigned char* const smem_raw = cfb_emul::dyn_smem();")
         dst = os.path.join(OUT, f.replace(".cu", "_emul.cpp"))
         open(dst, "w").write(src)
         cpp.append(dst)
@@ -110,14 +119,15 @@ def build(force=False):
     cmd = [cxx, "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-pthread",
            # the real library may be loaded in the same process (RTLD_GLOBAL): bind our own symbols to ourselves
            "-Wl,-Bsymbolic",
-           "-Ddlopen=cfb_emul_dlopen", "-Ddlsym=cfb_emul_dlsym", "-Ddlerror=cfb_emul_dlerror",
-           "-I", OUT, "-o", LIB] + cpp
+           "-Ddlopen=cfb_emul_dlopen", "-Ddlsym=cfb_emul_dlsym", "-Ddlerror=cfb_emul_dlerror"] + \
+          (["-DCFB_EMUL_REAL_TMA"] if tma else []) + ["-I", OUT, "-o", lib] + cpp
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         sys.stderr.write(p.stdout + p.stderr)
         raise RuntimeError("emulation build failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     print(build(force=True))
+    print(build(force=True, tma=True))

@@ -21,6 +21,7 @@
 #define __launch_bounds__( ... )
 #define __grid_constant__
 #define __shared__ static thread_local /* one block at a time per rank thread; fibers share it */
+#define __align__( n ) __attribute__( ( aligned( n ) ) )
 
 struct uint3
 {
@@ -52,7 +53,14 @@ void launch( dim3 grid, dim3 block, const std::function<void()>& body );
 // and all live fibers of the block pass the barrier together.  Blocks run in order.
 void launch_coop( dim3 grid, dim3 block, const std::function<void()>& body );
 void sync_threads(); // no-op outside launch_coop
+bool coop_active();
 long long clock_ns();
+// "shared memory" of the emulated block: thread-local storage of the rank thread.  Addresses in the
+// shared window are 32-bit offsets from a thread-local anchor (all shared objects of a kernel — the static
+// thread_local arrays that __shared__ turns into and the dynamic buffer — live in one TLS block).
+unsigned char* dyn_smem();
+uint32_t smem_addr( const void* p );
+void* smem_ptr( uint32_t a );
 } // namespace cfb_emul
 #define threadIdx cfb_emul::g_threadIdx
 #define blockIdx cfb_emul::g_blockIdx
@@ -63,6 +71,8 @@ template <class T>
 inline T __ldg( const T* p ) { return *p; }
 template <class T>
 inline T __ldcg( const T* p ) { return *p; }
+inline int min( int a, int b ) { return a < b ? a : b; }
+inline int max( int a, int b ) { return a > b ? a : b; }
 inline void __syncthreads() { cfb_emul::sync_threads(); }
 inline void __threadfence() { __atomic_thread_fence( __ATOMIC_SEQ_CST ); }
 inline void __threadfence_system() { __atomic_thread_fence( __ATOMIC_SEQ_CST ); }
@@ -102,6 +112,13 @@ struct cudaMemcpy3DParms
 inline cudaPitchedPtr make_cudaPitchedPtr( void* p, size_t pitch, size_t xs, size_t ys ) { return { p, pitch, xs, ys }; }
 inline cudaExtent make_cudaExtent( size_t w, size_t h, size_t d ) { return { w, h, d }; }
 
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+enum { cudaEnableDefault = 0 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+cudaError_t cudaGetDriverEntryPoint( const char* name, void** fn, unsigned long long flags,
+                                     cudaDriverEntryPointQueryResult* res );
+template <class F>
+inline cudaError_t cudaFuncSetAttribute( F, cudaFuncAttribute, int ) { return cudaSuccess; }
 inline const char* cudaGetErrorString( cudaError_t ) { return "emulated CUDA error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount( int* n )

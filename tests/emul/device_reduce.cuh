@@ -32,12 +32,59 @@ inline dd_t dd_add( dd_t a, dd_t b )
     return r;
 }
 
+// Sum over the block, cooperative launches only (one fiber per CUDA thread, real barriers): between two
+// barriers the fibers run one after the other, so a shared running sum is race-free.  Valid in every thread.
+template <int NT>
+inline dd_t dd_block_sum( dd_t v, dd_t* /*smem*/ )
+{
+    static thread_local dd_t acc;
+    __syncthreads(); // a previous call's result has been read by everybody
+    if ( threadIdx.x == 0 )
+        acc = dd_t{ 0.0, 0.0 };
+    __syncthreads();
+    acc = dd_add( acc, v );
+    __syncthreads();
+    return acc;
+}
+
 template <int NT, int NV>
 inline bool block_reduce_finalize( dd_t vals[NV], double* partials, int stride, unsigned int* ticket )
 {
-    static thread_local dd_t acc[NV]; // ranks of a multi-rank emulation are threads
     const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
     const unsigned bid = ( blockIdx.z * gridDim.y + blockIdx.y ) * gridDim.x + blockIdx.x;
+    if ( cfb_emul::coop_active() )
+    {
+        // the product's structure: block sums, partials, ticket, the last block adds the partials
+        static thread_local bool s_last;
+        for ( int n = 0; n < NV; ++n )
+        {
+            const dd_t s = dd_block_sum<NT>( vals[n], nullptr );
+            if ( threadIdx.x == 0 )
+            {
+                partials[( (size_t)n * stride + bid ) * 2 + 0] = s.hi;
+                partials[( (size_t)n * stride + bid ) * 2 + 1] = s.lo;
+            }
+        }
+        if ( threadIdx.x == 0 )
+            s_last = atomicAdd( ticket, 1u ) == nblocks - 1;
+        __syncthreads();
+        if ( !s_last )
+            return false;
+        if ( threadIdx.x == 0 )
+        {
+            for ( int n = 0; n < NV; ++n )
+            {
+                dd_t s{ 0.0, 0.0 };
+                for ( unsigned b = 0; b < nblocks; ++b )
+                    s = dd_add( s, dd_t{ partials[( (size_t)n * stride + b ) * 2 + 0], partials[( (size_t)n * stride + b ) * 2 + 1] } );
+                vals[n] = s;
+            }
+            *ticket = 0u;
+        }
+        return true;
+    }
+    // sequential launches: thread 0 of a block runs last
+    static thread_local dd_t acc[NV];
     if ( threadIdx.x == blockDim.x - 1 ) // first thread of the block to run
         for ( int n = 0; n < NV; ++n )
             acc[n] = dd_t{ 0.0, 0.0 };

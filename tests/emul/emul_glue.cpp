@@ -71,6 +71,20 @@ void fiber_entry()
 }
 } // namespace
 
+bool coop_active() { return t_coop.active; }
+
+namespace
+{
+thread_local char t_smem_anchor;
+thread_local __attribute__( ( aligned( 128 ) ) ) unsigned char t_dyn_smem[232 * 1024];
+} // namespace
+unsigned char* dyn_smem() { return t_dyn_smem; }
+uint32_t smem_addr( const void* p )
+{
+    return (uint32_t)( reinterpret_cast<uintptr_t>( p ) - reinterpret_cast<uintptr_t>( &t_smem_anchor ) );
+}
+void* smem_ptr( uint32_t a ) { return &t_smem_anchor + (int32_t)a; }
+
 void sync_threads()
 {
     Coop& c = t_coop;
@@ -124,6 +138,41 @@ void launch_coop( dim3 grid, dim3 block, const std::function<void()>& body )
 }
 } // namespace cfb_emul
 
+// cuTensorMapEncodeTiled as far as the product uses it: 3-D float64 tiles, no interleave / swizzle
+static CUresult emul_encode_tiled( CUtensorMap* m, CUtensorMapDataType, cuuint32_t rank, void* base,
+                                   const cuuint64_t* gdim, const cuuint64_t* gstride, const cuuint32_t* box,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill )
+{
+    if ( rank != 3 || ( reinterpret_cast<uintptr_t>( base ) & 15 ) || ( gstride[0] & 15 ) || ( gstride[1] & 15 ) ||
+         box[0] > 256 || box[1] > 256 || box[2] > 256 || ( box[0] * 8 ) % 16 != 0 )
+        return CUDA_ERROR_INVALID_VALUE; // the constraints the real encoder enforces
+    m->base = base;
+    for ( int d = 0; d < 3; ++d )
+    {
+        m->dim[d] = gdim[d];
+        m->box[d] = box[d];
+    }
+    m->stride[0] = gstride[0];
+    m->stride[1] = gstride[1];
+    return CUDA_SUCCESS;
+}
+cudaError_t cudaGetDriverEntryPoint( const char* name, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* res )
+{
+    if ( std::string( name ) == "cuTensorMapEncodeTiled" )
+    {
+        *fn = reinterpret_cast<void*>( emul_encode_tiled );
+        *res = cudaDriverEntryPointSuccess;
+    }
+    else
+    {
+        *fn = nullptr;
+        *res = cudaDriverEntryPointSymbolNotFound;
+    }
+    return cudaSuccess;
+}
+
+#ifndef CFB_EMUL_REAL_TMA
 int stencil_setup( cfb_ctx* c )
 {
     c->tmap_ok = true;
@@ -304,3 +353,4 @@ int launch_cg_fused( cfb_ctx* c, int which )
     S->rz_old = S->rz_new;
     return 1;
 }
+#endif // !CFB_EMUL_REAL_TMA

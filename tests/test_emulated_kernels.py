@@ -22,10 +22,14 @@ from helpers import fields_of, make_cfg, random_cells, smooth_velocity  # noqa: 
 from oracle_api import Oracle  # noqa: E402
 
 
-@pytest.fixture(scope="module")
-def emul():
+# "loops": the TMA kernels (stencil, phase B of the two-kernel CG form) are plain-loop stand-ins;
+# "tma": they are the product's kernels themselves (TMA loads as synchronous copies, one fiber per CUDA thread)
+@pytest.fixture(scope="module", params=["loops", "tma"])
+def emul(request):
     import ctypes
-    return Library(build_emul.build(), "cfb_", mode=ctypes.RTLD_LOCAL)
+    lib = Library(build_emul.build(tma=request.param == "tma"), "cfb_", mode=ctypes.RTLD_LOCAL)
+    lib.tma = request.param == "tma"  # fibers make these runs ~20x slower: the tests shorten themselves
+    return lib
 
 
 def run(ctx, steps):
@@ -73,7 +77,8 @@ STEP_CASES = [
 def test_emulated_steps_match_the_oracle_bit_for_bit(emul, dim, cells, kw):
     cfg = make_cfg(dim, cells, box=box_of(cells), **kw)
     g, o = Context(emul, cfg), Oracle(cfg)
-    assert run(g, 3) == run(o, 3)
+    steps = 1 if emul.tma else 3
+    assert run(g, steps) == run(o, steps)
     same_state(g, o, dim, ghosts=True)
     assert np.array_equal(g.residual_history(), o.residual_history())
     same_output(g, o)
@@ -86,7 +91,8 @@ def test_emulated_per_dimension_cell_sizes(emul, cells, box):
     dim = len(cells)
     cfg = make_cfg(dim, cells, box=box)
     g, o = Context(emul, cfg), Oracle(cfg)
-    assert run(g, 2) == run(o, 2)
+    steps = 1 if emul.tma else 2
+    assert run(g, steps) == run(o, steps)
     same_state(g, o, dim, ghosts=True)
     same_output(g, o)
 
@@ -122,7 +128,8 @@ def test_emulated_multigrid_pcg_matches_the_oracle_bit_for_bit(emul, dim, cells,
     g, o = Context(emul, cfg), Oracle(cfg)
     g.set_preconditioner("mg")
     o.set_preconditioner("mg")
-    assert run(g, 2) == run(o, 2)
+    steps = 1 if emul.tma else 2
+    assert run(g, steps) == run(o, steps)
     same_state(g, o, dim)
     assert np.array_equal(g.residual_history(), o.residual_history())
     assert np.array_equal(g.get(K.CG_R), o.get(K.CG_R))
@@ -158,6 +165,8 @@ def test_emulated_multigrid_fixed_iterations_and_back_to_jacobi(emul):
 
 def test_emulated_solve_writes_at_the_reference_cadence(emul, tmp_path):
     import json
+    if emul.tma:
+        pytest.skip("output path: nothing TMA-specific")
     cfg = make_cfg(2, 32)
     g = Context(emul, cfg)
     out = str(tmp_path / "data")
@@ -182,6 +191,8 @@ def test_emulated_solve_writes_at_the_reference_cadence(emul, tmp_path):
 
 
 def test_emulated_write_output_is_deferred_until_flush(emul, tmp_path):
+    if emul.tma:
+        pytest.skip("output path: nothing TMA-specific")
     cfg = make_cfg(3, 32)
     g = Context(emul, cfg)
     run(g, 1)
@@ -221,3 +232,40 @@ def test_emulated_bench_entry_points(emul):
     dg, _ = g.stencil_dot(2)
     do, _ = o.stencil_dot(1)
     assert np.array_equal(g.get(K.CG_Q), o.get(K.CG_Q)) and abs(dg - do) <= 1e-13 * abs(do)
+
+
+def test_emulated_tma_tile_configurations(emul):
+    """Every tile shape / stage count / z chunk the launchers can dispatch, for the stencil and for phase B of
+    the two-kernel form, incl. ragged tiles, against the oracle (TMA kernels themselves: "tma" library only)."""
+    if not emul.tma:
+        pytest.skip("the plain-loop stand-ins have no tiles")
+    cells = (70, 37, 9)
+    cfg = make_cfg(3, cells, box=box_of(cells), fixed_iters=3,
+                   boundary_type=[K.SOLID, K.FREE, K.SOLID, K.SOLID, K.SOLID, K.FREE])
+    o = Oracle(cfg)
+    rng = np.random.default_rng(12)
+    vel = smooth_velocity(o, rng)
+    for f, a in vel.items():
+        o.set(f, a)
+    o.build_rhs()
+    ro = o.pcg_solve()
+    po = o.get(K.PRESSURE)
+    g = Context(emul, cfg)
+    for f, a in vel.items():
+        g.set(f, a)
+    stencil = [(64, 16, 4), (64, 16, 6), (64, 8, 4), (64, 32, 4), (64, 32, 3), (128, 16, 4), (128, 16, 3), (128, 32, 3),
+               (128, 8, 4)]
+    fused = [(64, 16, 3, 64), (64, 8, 4, 4), (128, 16, 3, 2), (64, 16, 3, 1), (128, 8, 4, 64)]
+    for tx, ty, st in stencil:
+        for k, v in (("cg_variant", 0), ("stencil_stages", st), ("stencil_ty", ty), ("stencil_tx", tx), ("stencil_zc", 4)):
+            g.set_tuning(k, v)
+        g.build_rhs()
+        assert g.pcg_solve() == ro and np.array_equal(g.get(K.PRESSURE), po), (tx, ty, st)
+    g.set_tuning("cg_variant", 1)
+    for tx, ty, st, zc in fused:
+        for k, v in (("fused_stages", st), ("fused_ty", ty), ("fused_tx", tx), ("fused_zc", zc)):
+            g.set_tuning(k, v)
+        for rev in (0, 1):
+            g.set_tuning("fused_reverse", rev)
+            g.build_rhs()
+            assert g.pcg_solve() == ro and np.array_equal(g.get(K.PRESSURE), po), (tx, ty, st, zc, rev)

@@ -31,9 +31,11 @@ BYTES_STENCIL = 16  # read p, write q                       
 # algorithmic bytes per owned cell of one CG iteration / of its dominant kernel, per CG form
 #   0: three kernels  axpy+norms 48 | p-update 24 | stencil7+dot 16            (kernels_cg/stencil.cu)
 #   1: two kernels    r-update+norms 24 | x-update + p-update + stencil7 + dot 48   (kernels_fused.cu)
-BYTES_ITER = {0: 88, 1: 72}
-BYTES_DOMINANT = {0: 16, 1: 48}
-KERNEL_DOMINANT = {0: "stencil7_dot_tma", 1: "cg_fused_kernel (x-update + p-update + stencil7 + p.Ap dot)"}
+#   2: two kernels    stencil7 recomputed + r-update+norms 24 | x-update + p-update + stencil7 + dot, q not stored 40
+BYTES_ITER = {0: 88, 1: 72, 2: 64}
+BYTES_DOMINANT = {0: 16, 1: 48, 2: 40}
+KERNEL_DOMINANT = {0: "stencil7_dot_tma", 1: "cg_fused_kernel (x-update + p-update + stencil7 + p.Ap dot)",
+                   2: "cg_fused_kernel (x-update + p-update + stencil7 + p.Ap dot, q not stored)"}
 
 
 def measured_peak():
@@ -208,7 +210,8 @@ def main():
     ap.add_argument("--no-timestep", action="store_true")
     ap.add_argument("--blocks", type=int, nargs=3, default=None, help="block grid bx by bz (default: split z, y, x)")
     ap.add_argument("--timestep-cells", type=int, default=128, help="grid of the extra full-timestep measurement")
-    ap.add_argument("--cg-variant", type=int, default=1, choices=[0, 1], help="1 = two-kernel iteration (72 B/cell)")
+    ap.add_argument("--cg-variant", type=int, default=1, choices=[0, 1, 2],
+                    help="1 = two-kernel iteration (72 B/cell, default), 0 = three kernels (88 B), 2 = two kernels without a stored q (64 B)")
     ap.add_argument("--tune", action="append", default=[], help="key=value passed to cfb_set_tuning")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -320,9 +323,9 @@ def main():
                 "algorithmic_bytes_per_cell": bdom,
                 "algorithmic_bytes_per_launch": ncell_local * bdom,
                 "avg_launch_ms": t_st,
-                "iteration": {"form": "two kernels" if v == 1 else "three kernels", "bytes_per_cell": biter,
+                "iteration": {"form": "two kernels" if v >= 1 else "three kernels", "bytes_per_cell": biter,
                               "achieved_gbs": it_ach, "frac": it_ach / peak}}
-    if v == 1:
+    if v >= 1:
         roofline["iteration"].update({"rupdate_ms": st["ms_k_axpy"] / kt, "fused_ms": t_st})
     else:
         roofline["iteration"].update({"axpy_ms": st["ms_k_axpy"] / kt, "pupdate_ms": st["ms_k_pupdate"] / kt,
@@ -476,7 +479,8 @@ def main():
                            "global_cells": list(gcells), "blocks": list(blocks), "cg_iters_per_step": args.iters,
                            "l2": "inputs larger than L2 (each vector %.2f GB)" % (ncell_local * 8 / 1e9),
                            "timing": "CUDA events on the launching stream around each solve, max over ranks",
-                           "cg_form": "two kernels, 72 B/cell" if args.cg_variant == 1 else "three kernels, 88 B/cell",
+                           "cg_form": {0: "three kernels, 88 B/cell", 1: "two kernels, 72 B/cell",
+                                       2: "two kernels, q not stored, 64 B/cell"}[args.cg_variant],
                            "exchange": ("none (1 GPU)" if world == 1 else
                                         "NVLink peer stores (cudaIpc), ghosts + CG sums in one kernel per reduction point"
                                         if st["peer_mode"] else "NCCL send/recv + all-gather"),

@@ -143,13 +143,22 @@ int enqueue_iteration( cfb_ctx* c )
     cudaEvent_t* e = nullptr;
     if ( c->time_kernels && c->ktimed < CFB_KTIMED )
         e = c->kev[c->ktimed++];
-    if ( c->cg_variant == 1 )
+    if ( c->cg_variant >= 1 )
     {
-        // two-kernel form (kernels_fused.cu): e[0..1] phase A, e[2..3] phase B
+        // two-kernel forms (kernels_fused.cu): e[0..1] phase A, e[2..3] phase B.  Variant 2 (64 B/cell) does
+        // not store q: its phase A' recomputes A p from the search direction, whose ghosts the peer exchange
+        // after phase B has delivered (NCCL path: one more exchange, phase B recomputes its ring itself)
+        const bool peer = cg_peer_mode( c );
         if ( e )
             cudaEventRecord( e[0], c->stream );
-        n += launch_cg_rupdate( c );
-        const bool peer = cg_peer_mode( c );
+        if ( c->cg_variant == 2 )
+        {
+            if ( c->cfg.use_nccl && !peer )
+                halo_exchange_cells( c, c->cg_p, 1 );
+            n += launch_stencil_rupdate( c );
+        }
+        else
+            n += launch_cg_rupdate( c );
         if ( peer )
             peer_exchange( c, 1, true, -1, !peer_xstaged( c ) ); // r faces -> neighbours, (rz_new, rr) -> all
         else if ( c->cfg.use_nccl )
@@ -274,7 +283,7 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
             pending = 1;
         }
     }
-    if ( c->cg_variant == 1 )
+    if ( c->cg_variant >= 1 )
         launches += launch_cg_finish( c );
     CFB_CUDA( c, cudaMemcpyAsync( c->h_state, c->d_state, STATE_HEAD, cudaMemcpyDeviceToHost, c->stream ) );
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
@@ -287,7 +296,7 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
         return cfb_fail( c, CFB_ERR_NCCL, "peer-memory exchange timed out: a rank never published its CG sums" );
     c->last_iters = c->h_state->iter;
     c->last_resid = std::sqrt( c->h_state->rr );
-    if ( c->cg_variant == 1 )
+    if ( c->cg_variant >= 1 )
     {
         // launches enqueued after convergence were no-ops on the device but flipped the host's idea
         // of the current p buffer: every executed phase B except a converging one wrote a new p

@@ -131,7 +131,9 @@ struct cfb_ctx
     int poll_every = 0; // 0 = auto
 
     // two-kernel CG iteration (kernels_fused.cu): tensor maps of cg_r / cg_p, tiling, unit list
-    int cg_variant = 1; // 1 = two kernels / 72 B per cell (default), 0 = three kernels / 88 B
+    // 1 = two kernels / 72 B per cell (default), 0 = three kernels / 88 B, 2 = two kernels / 64 B: q is
+    // never stored, phase A' recomputes A p (kernels_stencil.cu MODE 1); not yet measured on a B200
+    int cg_variant = 1;
     CUtensorMap tmap_fr{}, tmap_fp[2] = {}; // fused-box maps of cg_r and of cg_pbuf[0 / 1]
     bool fused_ok = false;
     bool fu_auto = true; // pick the tiling from the block size; any "fused_*" tuning key turns it off
@@ -252,13 +254,14 @@ int launch_divergence( cfb_ctx* c );          // rhs = -div/h ; lhs = 0
 int launch_cg_init( cfb_ctx* c, int fixed );  // x=0, r=b, p=Minv r, rr, rz ; + check kernel
 inline bool cg_peer_mode( const cfb_ctx* c )
 {
-    return c->cfg.use_nccl && c->peer_ok && c->use_peer && c->cg_variant == 1;
+    return c->cfg.use_nccl && c->peer_ok && c->use_peer && c->cg_variant >= 1;
 }
 // peer mode with x neighbours and tiles that end exactly on the block: phase B reads its x ghosts
 // straight from the staging areas, so the iterations never scatter them into the ghost columns
 inline bool peer_xstaged( const cfb_ctx* c )
 {
-    return cg_peer_mode( c ) && c->peer_xstage_reads && ( c->nbr[0] >= 0 || c->nbr[1] >= 0 ) &&
+    // (not with cg_variant 2: its phase A' reads the x ghosts of p from the ghost columns through TMA)
+    return cg_peer_mode( c ) && c->peer_xstage_reads && c->cg_variant == 1 && ( c->nbr[0] >= 0 || c->nbr[1] >= 0 ) &&
            c->g.n[0] % c->fu_tx == 0;
 }
 int launch_cg_axpy( cfb_ctx* c );             // kernel 1 (+ fused kernel-2 reduction)
@@ -266,6 +269,7 @@ int launch_cg_pupdate( cfb_ctx* c );          // convergence bookkeeping + kerne
 // kernels_stencil.cu
 int stencil_setup( cfb_ctx* c );              // builds the tensor map for cg_p
 int launch_stencil_dot( cfb_ctx* c );         // kernel 4
+int launch_stencil_rupdate( cfb_ctx* c );     // cg_variant 2, phase A': r -= alpha (A p) without a stored q
 // kernels_fused.cu
 int fused_setup( cfb_ctx* c );                // tensor maps of cg_r, cg_p + the unit list
 int launch_cg_rupdate( cfb_ctx* c );          // phase A: r -= alpha q, sum r^2, sum r.Minv r

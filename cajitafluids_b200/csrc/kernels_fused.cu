@@ -204,6 +204,7 @@ struct FusedArgs
     // staging areas [k * ny + j] the x neighbours fill over NVLink, [0] low side, [1] high side
     const double* gxr[2];
     const double* gxp[2];
+    int store_q;     // 0: the 64-byte iteration (cg_variant 2) recomputes q = A p in its phase A' and never reads it
     int unit_base;   // index of this launch's first unit in the partial-sum scratch
     int units_total; // units of all launches that make up one phase B (last-block ticket target)
 };
@@ -491,13 +492,15 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
                 double* qp = qrow + (long long)( r * WY ) * g.sy;
                 if ( vx1 )
                 {
-                    *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
+                    if ( a.store_q )
+                        *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
                     dd_acc( acc, c.x * a0 );
                     dd_acc( acc, c.y * a1 );
                 }
                 else if ( vx0 )
                 {
-                    *qp = a0;
+                    if ( a.store_q )
+                        *qp = a0;
                     dd_acc( acc, c.x * a0 );
                 }
             }
@@ -759,6 +762,7 @@ int launch_cg_fused( cfb_ctx* c, int which )
     // optional top-down walk (phase A sweeps bottom-up and leaves the top of r in the L2); measured
     // neutral from 64^3 to 512^3 (profiles/r1_sweep_fused2.log), so it is off by default
     a.reverse = c->fu_reverse ? 1 : 0;
+    a.store_q = c->cg_variant == 2 ? 0 : 1;
     if ( peer_xstaged( c ) )
         for ( int side = 0; side < 2; ++side )
             if ( c->nbr[side] >= 0 )

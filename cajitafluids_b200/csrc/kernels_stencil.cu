@@ -58,20 +58,46 @@ struct TileCfg
 
 struct StencilArgs
 {
+    double* r; // MODE 1 only
     double* q;
     CgState* S;
     double* partials;
     int tiles_x, tiles_y, zc, hx;
 };
 
-template <class C>
+// MODE 0: q = A p, sum p.q (CG kernel 4).
+// MODE 1: phase A' of the 64-byte iteration (cg_variant 2): the same march over p, but q = A p is consumed
+//         on the spot instead of being stored: alpha = zr_old / pAp ; r -= alpha (A p) ; sum r^2 ; sum r.M^-1 r
+//         (reads p through TMA and r with 128-bit loads, writes r: 24 B/cell, and phase B no longer writes q).
+//         Statement for statement cg_rupdate_kernel with q recomputed by the same row expression that
+//         produced it, hence bit-identical.
+template <class C, int MODE>
 __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) )
     stencil7_dot_tma( const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geo g,
                       const __grid_constant__ OpConst op, const __grid_constant__ StencilArgs a )
 {
     constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
-    if ( a.S->done )
-        return;
+    double nalpha = 0.0;
+    if ( MODE == 0 )
+    {
+        if ( a.S->done )
+            return;
+    }
+    else
+    {
+        // as in cg_rupdate_kernel: `done` is only ever written here, by cg_check0 and by cg_finish
+        CgState* S = a.S;
+        if ( S->done || ( S->iter > 0 && !S->fixed && sqrt( S->rr ) <= S->thresh ) )
+        {
+            if ( blockIdx.x == 0 && threadIdx.x == 0 )
+                S->done = 1;
+            return;
+        }
+        const double alpha = S->rz_old / S->pAp;
+        nalpha = -alpha;
+        if ( blockIdx.x == 0 && threadIdx.x == 0 )
+            S->alpha = alpha;
+    }
 
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__( 8 ) unsigned long long full_bar[NS];
@@ -157,8 +183,8 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         tma_load_3d( smem_base, &tmap, bar, cx, cy, cz + NS );
     }
 
-    dd_t acc = { 0.0, 0.0 };
-    double* qrow = a.q + geo_off( g, i0, y0 + wy, kbeg );
+    dd_t acc = { 0.0, 0.0 }, acc2 = { 0.0, 0.0 }; // MODE 0: p.q | MODE 1: r.r, r.M^-1 r
+    double* qrow = ( MODE == 0 ? a.q : a.r ) + geo_off( g, i0, y0 + wy, kbeg );
     for ( int it = 0; it < nplanes; ++it )
     {
         const int lc = it + 1, ln = it + 2; // load indices of plane k and plane k+1
@@ -185,16 +211,42 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
             if ( vy[r] )
             {
                 double* qp = qrow + (long long)( r * WY ) * g.sy;
-                if ( vx1 )
+                if ( MODE == 0 )
                 {
-                    *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
-                    dd_acc( acc, c.x * a0 );
-                    dd_acc( acc, c.y * a1 );
+                    if ( vx1 )
+                    {
+                        *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
+                        dd_acc( acc, c.x * a0 );
+                        dd_acc( acc, c.y * a1 );
+                    }
+                    else if ( vx0 )
+                    {
+                        *qp = a0;
+                        dd_acc( acc, c.x * a0 );
+                    }
                 }
-                else if ( vx0 )
+                else
                 {
-                    *qp = a0;
-                    dd_acc( acc, c.x * a0 );
+                    // kernel 1's residual update + kernel 2's reduction (z = M^-1 r is never stored)
+                    const int w0 = wx0 + wyc[r] + wz, w1 = wx1 + wyc[r] + wz;
+                    if ( vx1 )
+                    {
+                        double2 rv = *reinterpret_cast<const double2*>( qp );
+                        rv.x = fma( nalpha, a0, rv.x );
+                        rv.y = fma( nalpha, a1, rv.y );
+                        *reinterpret_cast<double2*>( qp ) = rv;
+                        dd_acc( acc, rv.x * rv.x );
+                        dd_acc( acc2, ( op.minv[w0] * rv.x ) * rv.x );
+                        dd_acc( acc, rv.y * rv.y );
+                        dd_acc( acc2, ( op.minv[w1] * rv.y ) * rv.y );
+                    }
+                    else if ( vx0 )
+                    {
+                        const double rv = fma( nalpha, a0, *qp );
+                        *qp = rv;
+                        dd_acc( acc, rv * rv );
+                        dd_acc( acc2, ( op.minv[w0] * rv ) * rv );
+                    }
                 }
             }
             zm[r] = c;
@@ -210,11 +262,38 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         }
     }
 
-    dd_t vals[1] = { acc };
-    if ( block_reduce_finalize<C::NT, 1>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
+    if ( MODE == 0 )
     {
-        if ( tid == 0 )
-            publish_pAp( a.S, vals[0] );
+        dd_t vals[1] = { acc };
+        if ( block_reduce_finalize<C::NT, 1>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
+        {
+            if ( tid == 0 )
+                publish_pAp( a.S, vals[0] );
+        }
+    }
+    else
+    {
+        dd_t vals[2] = { acc, acc2 };
+        if ( block_reduce_finalize<C::NT, 2>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
+        {
+            if ( tid == 0 )
+            {
+                // publish_rr_rz of kernels_cg.cu
+                CgState* S = a.S;
+                if ( S->world > 1 )
+                {
+                    S->loc[2] = vals[1].hi;
+                    S->loc[3] = vals[1].lo;
+                    S->loc[4] = vals[0].hi;
+                    S->loc[5] = vals[0].lo;
+                }
+                else
+                {
+                    S->rr = vals[0].hi + vals[0].lo;
+                    S->rz_new = vals[1].hi + vals[1].lo;
+                }
+            }
+        }
     }
 }
 
@@ -284,17 +363,22 @@ typedef CUresult ( *PFN_encodeTiled )( CUtensorMap*, CUtensorMapDataType, cuuint
                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                        CUtensorMapFloatOOBfill );
 
-template <class C>
-int launch_tma( cfb_ctx* c, const StencilArgs& a, int grid )
+template <class C, int MODE>
+int launch_tma_mode( cfb_ctx* c, const StencilArgs& a, int grid )
 {
     static bool attr_set = false;
     if ( !attr_set )
     {
-        cudaFuncSetAttribute( stencil7_dot_tma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
         attr_set = true;
     }
-    stencil7_dot_tma<C><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a );
+    stencil7_dot_tma<C, MODE><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a );
     return 1;
+}
+template <class C>
+int launch_tma( cfb_ctx* c, const StencilArgs& a, int grid, int mode )
+{
+    return mode == 0 ? launch_tma_mode<C, 0>( c, a, grid ) : launch_tma_mode<C, 1>( c, a, grid );
 }
 
 } // namespace
@@ -330,10 +414,11 @@ int stencil_setup( cfb_ctx* c )
     return CFB_OK;
 }
 
-int launch_stencil_dot( cfb_ctx* c )
+static int launch_stencil( cfb_ctx* c, int mode )
 {
     const Geo& g = c->g;
     StencilArgs a{};
+    a.r = c->cg_r;
     a.q = c->cg_q;
     a.S = c->d_state;
     a.partials = c->d_partials;
@@ -350,6 +435,11 @@ int launch_stencil_dot( cfb_ctx* c )
     const int grid = a.tiles_x * a.tiles_y * ( ( g.n[2] + zc - 1 ) / zc );
     if ( c->st_variant == 1 )
     {
+        if ( mode != 0 )
+        {
+            cfb_fail( c, CFB_ERR_INVALID, "the LDG stencil variant has no phase A' form" );
+            return 0;
+        }
         stencil7_dot_ldg<<<grid, 256, 0, c->stream>>>( g, c->op, c->cg_p, a );
         return 1;
     }
@@ -357,25 +447,30 @@ int launch_stencil_dot( cfb_ctx* c )
     switch ( key )
     {
     case 641604:
-        return launch_tma<TileCfg<64, 16, 4>>( c, a, grid );
+        return launch_tma<TileCfg<64, 16, 4>>( c, a, grid, mode );
     case 641606:
-        return launch_tma<TileCfg<64, 16, 6>>( c, a, grid );
+        return launch_tma<TileCfg<64, 16, 6>>( c, a, grid, mode );
     case 640804:
-        return launch_tma<TileCfg<64, 8, 4>>( c, a, grid );
+        return launch_tma<TileCfg<64, 8, 4>>( c, a, grid, mode );
     case 643204:
-        return launch_tma<TileCfg<64, 32, 4>>( c, a, grid );
+        return launch_tma<TileCfg<64, 32, 4>>( c, a, grid, mode );
     case 643203:
-        return launch_tma<TileCfg<64, 32, 3>>( c, a, grid );
+        return launch_tma<TileCfg<64, 32, 3>>( c, a, grid, mode );
     case 1281604:
-        return launch_tma<TileCfg<128, 16, 4>>( c, a, grid );
+        return launch_tma<TileCfg<128, 16, 4>>( c, a, grid, mode );
     case 1281603:
-        return launch_tma<TileCfg<128, 16, 3>>( c, a, grid );
+        return launch_tma<TileCfg<128, 16, 3>>( c, a, grid, mode );
     case 1283203:
-        return launch_tma<TileCfg<128, 32, 3>>( c, a, grid );
+        return launch_tma<TileCfg<128, 32, 3>>( c, a, grid, mode );
     case 1280804:
-        return launch_tma<TileCfg<128, 8, 4>>( c, a, grid );
+        return launch_tma<TileCfg<128, 8, 4>>( c, a, grid, mode );
     default:
         cfb_fail( c, CFB_ERR_INVALID, "unsupported stencil tile configuration" );
         return 0;
     }
 }
+
+int launch_stencil_dot( cfb_ctx* c ) { return launch_stencil( c, 0 ); }
+
+// phase A' of the 64-byte iteration (cg_variant 2): r -= alpha (A p) with q recomputed, sum r^2, sum r.M^-1 r
+int launch_stencil_rupdate( cfb_ctx* c ) { return launch_stencil( c, 1 ); }

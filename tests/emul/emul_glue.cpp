@@ -273,6 +273,50 @@ int launch_cg_rupdate( cfb_ctx* c )
     return 1;
 }
 
+// phase A' of the 64-byte iteration (kernels_stencil.cu MODE 1): q = A p recomputed, never stored
+int launch_stencil_rupdate( cfb_ctx* c )
+{
+    const Geo& g = c->g;
+    const OpConst& op = c->op;
+    CgState* S = c->d_state;
+    if ( S->done || ( S->iter > 0 && cg_converged( S ) ) )
+    {
+        S->done = 1;
+        return 1;
+    }
+    const double alpha = S->rz_old / S->pAp, nalpha = -alpha;
+    S->alpha = alpha;
+    dd_t rr{ 0.0, 0.0 }, rz{ 0.0, 0.0 };
+    double* r = c->cg_r;
+    const double* p = c->cg_p;
+    for ( int k = 0; k < g.n[2]; ++k )
+        for ( int j = 0; j < g.n[1]; ++j )
+            for ( int i = 0; i < g.n[0]; ++i )
+            {
+                const long long o = geo_off( g, i, j, k );
+                const int w = walls_at( g, i, j, k );
+                const double a = apply_row( op.diag[w], op.neg_scale, p[o], p[o - 1], p[o + 1], p[o - g.sy], p[o + g.sy],
+                                            p[o - g.sz], p[o + g.sz] );
+                const double v = fma( nalpha, a, r[o] );
+                r[o] = v;
+                dd_acc( rr, v * v );
+                dd_acc( rz, ( op.minv[w] * v ) * v );
+            }
+    if ( S->world > 1 )
+    {
+        S->loc[2] = rz.hi;
+        S->loc[3] = rz.lo;
+        S->loc[4] = rr.hi;
+        S->loc[5] = rr.lo;
+    }
+    else
+    {
+        S->rr = rr.hi + rr.lo;
+        S->rz_new = rz.hi + rz.lo;
+    }
+    return 1;
+}
+
 int launch_cg_finish( cfb_ctx* c )
 {
     CgState* S = c->d_state;
@@ -340,7 +384,8 @@ int launch_cg_fused( cfb_ctx* c, int which )
                 p_new[o] = pn[o];
                 const double a = apply_row( op.diag[walls_at( g, i, j, k )], op.neg_scale, pn[o], pn[o - 1], pn[o + 1],
                                             pn[o - g.sy], pn[o + g.sy], pn[o - g.sz], pn[o + g.sz] );
-                q[o] = a;
+                if ( c->cg_variant != 2 )
+                    q[o] = a;
                 dd_acc( acc, pn[o] * a );
             }
     if ( S->world > 1 )

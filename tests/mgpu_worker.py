@@ -141,7 +141,9 @@ def section_3(args, rank, gcfg, rank_cfg, rng, check):
              ("two-kernel, NCCL, small tiles, several boundary units",
               {"cg_variant": 1, "peer_halo": 0, "overlap_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64,
                "fused_ty": 8}),
-             ("three-kernel, NCCL", {"cg_variant": 0})]
+             ("three-kernel, NCCL", {"cg_variant": 0}),
+             ("two-kernel without a stored q (64 B/cell), NVLink peer stores", {"cg_variant": 2, "peer_halo": 1}),
+             ("two-kernel without a stored q (64 B/cell), NCCL", {"cg_variant": 2, "peer_halo": 0})]
     if args.quick:
         modes = [modes[0], modes[1], modes[2], modes[4]]
     for name, tune in modes:

@@ -269,3 +269,38 @@ def test_emulated_tma_tile_configurations(emul):
             g.set_tuning("fused_reverse", rev)
             g.build_rhs()
             assert g.pcg_solve() == ro and np.array_equal(g.get(K.PRESSURE), po), (tx, ty, st, zc, rev)
+
+
+@pytest.mark.parametrize("dim,cells,kw", [(3, (70, 50, 21), {}), (2, (33, 47), {}), (3, (130, 36, 5), dict(
+    boundary_type=[K.SOLID, K.FREE, K.SOLID, K.SOLID, K.SOLID, K.FREE])), (3, 32, {})])
+def test_emulated_64_byte_iteration_matches_the_oracle(emul, dim, cells, kw):
+    """cg_variant 2: q is never stored, phase A' recomputes A p (kernels_stencil.cu MODE 1), phase B skips the
+    q store.  Same values as the other forms, bit for bit; q keeps what the start of the solve left in it."""
+    cfg = make_cfg(dim, cells, box=box_of(cells), **kw)
+    g, o = Context(emul, cfg), Oracle(cfg)
+    g.set_tuning("cg_variant", 2)
+    if cells == 32:
+        if emul.tma:
+            pytest.skip("covered by the fixed-iteration cases")
+        assert run(g, 1) == run(o, 1)
+        same_state(g, o, dim)
+        assert np.array_equal(g.residual_history(), o.residual_history())
+        return
+    rng = np.random.default_rng(6)
+    for f, a in smooth_velocity(o, rng).items():
+        g.set(f, a)
+        o.set(f, a)
+    for fixed in ((7,) if emul.tma else (0, 7)):
+        for s in (g, o):
+            s.cfg.cg_fixed_iters = fixed
+        g2, o2 = Context(emul, g.cfg), Oracle(o.cfg)
+        g2.set_tuning("cg_variant", 2)
+        for f in fields_of(dim)[1:]:
+            g2.set(f, o.get(f))
+            o2.set(f, o.get(f))
+        for s in (g2, o2):
+            s.add_inputs()
+            s.build_rhs()
+        assert g2.pcg_solve() == o2.pcg_solve()
+        assert np.array_equal(g2.get(K.PRESSURE), o2.get(K.PRESSURE)) and np.array_equal(g2.get(K.CG_R), o2.get(K.CG_R))
+        assert np.array_equal(g2.residual_history(), o2.residual_history())

@@ -318,3 +318,33 @@ def test_two_dimensional_block_decomposition(emul, world, blocks, peer):
 
     for pm, exact, err in run_ranks(emul, cfg, world, body, blocks, peer=peer):
         assert pm == (1 if peer else 0) and exact == [] and max(err.values()) < 1e-12, (pm, exact, err)
+
+
+@pytest.mark.parametrize("world,blocks,peer", [(8, None, True), (8, None, False), (4, (2, 2, 1), True), (2, (2, 1, 1), True),
+                                               (2, (1, 2, 1), False), (6, (1, 3, 2), True)])
+def test_64_byte_iteration_block_decomposed(emul, world, blocks, peer):
+    """cg_variant 2 on several blocks: phase A' reads the ghosts of the search direction that the exchange after
+    phase B delivered (peer path) / that one more exchange delivers (NCCL path)."""
+    cfg = cfg3(fixed_iters=15) if emul.tma else cfg3()
+    ora = Oracle(cfg)
+    rng = np.random.default_rng(79)
+    vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
+    for f, a in vel.items():
+        ora.set(f, a)
+    ora.add_inputs()
+    ora.build_rhs()
+    io, ro = ora.pcg_solve()
+    po, ho = ora.get(K.PRESSURE), ora.residual_history()
+
+    def body(ctx, rank):
+        ctx.set_tuning("cg_variant", 2)
+        for f, a in vel.items():
+            ctx.set(f, a[block_slices(ctx, f)])
+        ctx.add_inputs()
+        ctx.build_rhs()
+        ig, rg = ctx.pcg_solve()
+        return ctx.stats()["peer_mode"], ig, rg, np.array_equal(ctx.get(K.PRESSURE), po[block_slices(ctx, K.PRESSURE)]), \
+            np.array_equal(ctx.residual_history(), ho)
+
+    for res in run_ranks(emul, cfg, world, body, blocks, peer=peer):
+        assert res == (1 if peer else 0, io, ro, True, True), res

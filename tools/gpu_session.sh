@@ -24,6 +24,14 @@ timeout 300 python tools/profile_mg.py 512 output >> "$O/output_stage.log" 2>&1
 # 3. the headline bench
 timeout 900 python bench.py --steps 5 --warmup 3 > "$O/bench_n1.json" 2> "$O/bench_n1.err"
 
+# 3b. the 64-byte iteration (cg_variant 2), never measured before round 2
+timeout 600 python bench.py --steps 5 --warmup 3 --cg-variant 2 --no-cpu-baseline --no-e2e --no-timestep \
+    > "$O/bench_n1_variant2.json" 2> "$O/bench_n1_variant2.err"
+for zc in 16 32 64; do
+    timeout 300 python bench.py --steps 3 --warmup 3 --cg-variant 2 --no-cpu-baseline --no-e2e --no-timestep \
+        --tune stencil_zc=$zc >> "$O/bench_n1_variant2_sweep.json" 2>> "$O/bench_n1_variant2.err"
+done
+
 # 4. launch lists (ncu, serialised; shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$O/launches_mg256.csv" \
     python tools/profile_mg.py 256 cycle > "$O/ncu_mg.log" 2>&1

@@ -304,3 +304,22 @@ def test_emulated_64_byte_iteration_matches_the_oracle(emul, dim, cells, kw):
         assert g2.pcg_solve() == o2.pcg_solve()
         assert np.array_equal(g2.get(K.PRESSURE), o2.get(K.PRESSURE)) and np.array_equal(g2.get(K.CG_R), o2.get(K.CG_R))
         assert np.array_equal(g2.residual_history(), o2.residual_history())
+
+
+def test_emulated_bench_tiling_is_what_runs_at_512(emul):
+    """A slab with the x / y extents of the benchmark grid takes the tiling rules' 128 x 16 x 3 phase-B tiles and
+    the 64 x 16 x 4 stencil tiles: the configuration every headline number was measured with."""
+    if not emul.tma:
+        pytest.skip("the plain-loop stand-ins have no tiles")
+    cells = (512, 64, 6)
+    cfg = make_cfg(3, cells, box=box_of(cells), fixed_iters=3)
+    g, o = Context(emul, cfg), Oracle(cfg)
+    g.fill_synthetic_velocity(1, 99)
+    for f in fields_of(3)[1:]:
+        o.set(f, g.get(f))
+    for variant in (1, 2):
+        g.set_tuning("cg_variant", variant)
+        for s in (g, o):
+            s.build_rhs()
+        assert g.pcg_solve() == o.pcg_solve(), variant
+        assert np.array_equal(g.get(K.PRESSURE), o.get(K.PRESSURE)), variant

@@ -348,3 +348,44 @@ def test_64_byte_iteration_block_decomposed(emul, world, blocks, peer):
 
     for res in run_ranks(emul, cfg, world, body, blocks, peer=peer):
         assert res == (1 if peer else 0, io, ro, True, True), res
+
+
+MODES = [("peer, small tiles", True, {"fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
+         ("peer, phase B reads the x ghosts from the staging areas", True, {"peer_xstage": 1}),
+         ("NCCL, interior overlapped with the r/p halo", False, {"overlap_halo": 1}),
+         ("NCCL, overlap, small tiles, several boundary units", False,
+          {"overlap_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
+         ("three-kernel, NCCL", False, {"cg_variant": 0})]
+
+
+@pytest.mark.parametrize("name,peer,tune", MODES, ids=[m[0] for m in MODES])
+@pytest.mark.parametrize("world,blocks,cells", [(8, None, (24, 20, 18)), (2, (2, 1, 1), (128, 24, 20))])
+def test_every_exchange_schedule_of_the_cg_iterations(emul, world, blocks, cells, name, peer, tune):
+    """The tuning modes the multi-GPU worker runs on real GPUs (tests/mgpu_worker.py section 3), on 2x2x2 blocks
+    and on an x split whose blocks end exactly on a 64-wide tile (the staging-read variant's case)."""
+    if not emul.tma:
+        pytest.skip("unit lists and staging reads exist in the TMA kernels only")
+    cfg = cfg3(cells=cells, fixed_iters=12)
+    ora = Oracle(cfg)
+    rng = np.random.default_rng(80)
+    vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
+    for f, a in vel.items():
+        ora.set(f, a)
+    ora.add_inputs()
+    ora.build_rhs()
+    io, ro = ora.pcg_solve()
+    po = ora.get(K.PRESSURE)
+
+    def body(ctx, rank):
+        for k, v in tune.items():
+            ctx.set_tuning(k, v)
+        for f, a in vel.items():
+            ctx.set(f, a[block_slices(ctx, f)])
+        ctx.add_inputs()
+        ctx.build_rhs()
+        ig, rg = ctx.pcg_solve()
+        return ctx.stats()["peer_mode"], ig, rg, np.array_equal(ctx.get(K.PRESSURE), po[block_slices(ctx, K.PRESSURE)])
+
+    want_peer = 1 if peer and tune.get("cg_variant", 1) >= 1 else 0
+    for res in run_ranks(emul, cfg, world, body, blocks, peer=peer):
+        assert res == (want_peer, io, ro, True), (name, res)

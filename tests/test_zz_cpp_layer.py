@@ -89,3 +89,41 @@ def test_cpp_driver_multigrid_flag_and_errors(driver, tmp_path):
     p = subprocess.run([driver, "-n", "32", "-t", "0.01", "-m", "PCG"], cwd=tmp_path, capture_output=True, text=True,
                        timeout=60)
     assert p.returncode != 0 and "Reference" in (p.stdout + p.stderr)
+
+
+def build_shim_tests(lib, out_dir):
+    exe = os.path.join(str(out_dir), "tst_shims")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "tst_shims.cpp"), "-o", exe, lib,
+                           "-Wl,-rpath," + os.path.dirname(lib), "-ldl", "-lpthread"])
+    return exe
+
+
+def test_reference_unit_tests_re_expressed_on_the_cpp_shims(tmp_path):
+    """tests/cpp/tst_shims.cpp: the reference's tstMesh / tstProblemManager / (the intent of) tstBoundaryConditions
+    and the three plug-in seams of INTEGRATION.md, on the host-emulated library."""
+    exe = build_shim_tests(build_emul.build(), tmp_path)
+    p = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "all shim tests passed" in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_cpp_shims_and_driver_on_the_gpu(tmp_path):
+    """The same C++ programs against the CUDA library."""
+    from cajitafluids_b200._capi import LIB_PATH
+    exe = build_shim_tests(LIB_PATH, tmp_path)
+    p = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "all shim tests passed" in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]
+    drv = os.path.join(ROOT, "examples", "advection_b200")
+    if not os.path.exists(drv):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
+    q = str(tmp_path / "q.bin")
+    p = subprocess.run([drv, "-n", "32", "-t", "0.02", "-D", "2", "-o", q], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    its = [int(m) for m in re.findall(r"Finished in (\d+) iterations", p.stdout)]
+    assert its == [105, 117, 119, 119, 118]  # the reference's own CLI prints the same (checked on the CPU above)
+    o = Oracle(make_cfg(2, 32))
+    o.solve(0.02, 0)
+    assert np.array_equal(np.fromfile(q).reshape(o.shape(K.QUANTITY)), o.get(K.QUANTITY))

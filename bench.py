@@ -469,6 +469,25 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_baseline(args, max(2, min(args.iters, 10)), (args.cells,) * 3)
         cpu.pop("seconds", None)
+        # the same whole timesteps as extra.timesteps_per_s (default inflow problem, reference tol / max_iter,
+        # cubic interpolation) on the host cores: setup, then ONE timed step (bounded: ~600 CG iterations at 128^3)
+        if args.timestep_cells > 0:
+            try:
+                from cajitafluids_b200 import default_config
+                from oracle_api import Oracle
+                o = Oracle(default_config(3, args.timestep_cells))
+                o.set_accumulation(False)  # plain double sums: the reference's arithmetic and cost
+                o.setup()
+                t0 = time.perf_counter()
+                it0 = o.stats()["cg_iterations"]
+                o.step()
+                dt_cpu = time.perf_counter() - t0
+                cpu["timesteps_per_s"] = {"cells": [args.timestep_cells] * 3, "value": 1.0 / dt_cpu,
+                                          "cg_iters_per_step": o.stats()["cg_iterations"] - it0, "interp_order": 3,
+                                          "sample": "one whole timestep after setup"}
+                o.close()
+            except Exception as e:  # noqa: BLE001
+                cpu["timesteps_per_s"] = {"error": repr(e)[:200]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

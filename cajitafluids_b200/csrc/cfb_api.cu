@@ -964,6 +964,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         if ( c->d_state )
             CFB_CUDA( c, cudaMemsetAsync( &c->d_state->xerror, 0, sizeof( int ), c->stream ) );
     }
+    else if ( k == "mg_graph" )
+        return mg_set_graph( c, value != 0 );
     else if ( k == "peer_xstage" )
         c->peer_xstage_reads = value != 0;
     else if ( k == "time_kernels" )

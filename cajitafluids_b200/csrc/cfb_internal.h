@@ -193,6 +193,7 @@ struct cfb_ctx
     // opt-in multigrid preconditioner (mg.cu; cfb_set_preconditioner)
     int precond = CFB_PRECOND_JACOBI;
     int mg_max_levels = 0; // 0 = as many as the block allows
+    bool mg_graph = false; // "mg_graph" tuning key: replay the V-cycle as a CUDA graph (one block)
     MgStage* mg = nullptr;
 };
 
@@ -283,6 +284,7 @@ void output_destroy( cfb_ctx* c );
 // mg.cu: the CG with z = V-cycle( r ) instead of z = D^-1 r
 int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid );
 void mg_destroy( cfb_ctx* c );
+int mg_set_graph( cfb_ctx* c, bool on );
 // halo.cu
 int halo_init( cfb_ctx* c );
 void halo_destroy( cfb_ctx* c );

@@ -78,6 +78,14 @@ struct MgStage
     double omega = 0.0;
     bool singular = false;
     cudaEvent_t ev_poll = nullptr;
+    // "mg_graph" tuning key (one block only): the ~60 launches of a V-cycle replayed as one CUDA graph.  All
+    // pointers, the ping-pong sequence and the launch shapes of a cycle are the same every time, so the graph
+    // is captured once per form ([0] plain cycle, [1] with the fused z.r of the CG) and reused.
+    bool use_graph = false;
+    cudaGraphExec_t graph[2] = { nullptr, nullptr };
+    int graph_launches[2] = { 0, 0 };
+    bool graph_dotted[2] = { false, false };
+    int graph_cur0[2] = { 0, 0 }; // where the fine level's result ends up
 };
 
 namespace
@@ -558,6 +566,9 @@ void mg_free( cfb_ctx* c )
     }
     if ( m->ev_poll )
         cudaEventDestroy( m->ev_poll );
+    for ( cudaGraphExec_t g : m->graph )
+        if ( g )
+            cudaGraphExecDestroy( g );
     delete m;
     c->mg = nullptr;
 }
@@ -568,6 +579,7 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega, int max_level
     MgStage* m = new MgStage();
     c->mg = m;
     m->max_levels = max_levels;
+    m->use_graph = c->mg_graph;
     m->nu1 = nu1;
     m->nu2 = nu2;
     m->nuc = nuc;
@@ -797,9 +809,53 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
     return CFB_OK;
 }
 
+// The fine-level cycle as the callers use it: plain launches, or (mg_graph, one block) the captured graph.
+int run_cycle( cfb_ctx* c, bool dot, bool* dotted, int* n )
+{
+    MgStage* m = c->mg;
+    if ( !m->use_graph || c->cfg.use_nccl )
+        return vcycle( c, 0, dot, dotted, n );
+    const int f = dot ? 1 : 0;
+    if ( !m->graph[f] )
+    {
+        cudaGraph_t g = nullptr;
+        int launches = 0;
+        bool d = false;
+        CFB_CUDA( c, cudaStreamBeginCapture( c->stream, cudaStreamCaptureModeThreadLocal ) );
+        int rc = vcycle( c, 0, dot, &d, &launches );
+        cudaError_t e = cudaStreamEndCapture( c->stream, &g );
+        if ( rc )
+            return rc;
+        if ( e != cudaSuccess || !g )
+            return cfb_fail( c, CFB_ERR_CUDA, std::string( "V-cycle graph capture failed: " ) + cudaGetErrorString( e ) );
+        e = cudaGraphInstantiate( &m->graph[f], g, 0 );
+        cudaGraphDestroy( g );
+        if ( e != cudaSuccess )
+            return cfb_fail( c, CFB_ERR_CUDA, std::string( "cudaGraphInstantiate: " ) + cudaGetErrorString( e ) );
+        m->graph_launches[f] = launches;
+        m->graph_dotted[f] = d;
+        m->graph_cur0[f] = m->lv[0].cur;
+    }
+    CFB_CUDA( c, cudaGraphLaunch( m->graph[f], c->stream ) );
+    m->lv[0].cur = m->graph_cur0[f];
+    if ( dotted )
+        *dotted = m->graph_dotted[f];
+    *n += m->graph_launches[f];
+    return CFB_OK;
+}
+
 } // namespace
 
 void mg_destroy( cfb_ctx* c ) { mg_free( c ); }
+
+// "mg_graph" tuning key
+int mg_set_graph( cfb_ctx* c, bool on )
+{
+    if ( c->mg )
+        c->mg->use_graph = on;
+    c->mg_graph = on;
+    return CFB_OK;
+}
 
 // Cajita::ReferenceConjugateGradient::solve( b, x ) from x0 = 0 with z = V-cycle( r ).
 int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
@@ -829,7 +885,7 @@ int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     {
         // one iteration: z = M^-1 r ; z.r ; p = z + beta p ; q = A p, p.q ; x, r, r.r, stopping test
         bool dotted = false;
-        MG_TRY( vcycle( c, 0, true, &dotted, &nl ) );
+        MG_TRY( run_cycle( c, true, &dotted, &nl ) );
         const double* z = F.x[F.cur];
         if ( !dotted ) // no post-smoothing sweep to fuse z.r into
         {
@@ -942,7 +998,7 @@ extern "C" int cfb_mg_apply( cfb_ctx* c, const double* r_host, double* z_host )
     MgLevelHost& F = m->lv[0];
     F.b = c->cg_r;
     int nl = 0;
-    rc = vcycle( c, 0, false, nullptr, &nl );
+    rc = run_cycle( c, false, nullptr, &nl );
     if ( rc )
         return rc;
     c->stats.kernel_launches += nl;

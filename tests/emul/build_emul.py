@@ -2,7 +2,8 @@
 kernels and host orchestration compiled as ordinary C++ (see cuda_runtime.h in this directory).
 
 The .cu sources are taken from cajitafluids_b200/csrc as they are; the only rewrite is the launch
-syntax  kernel<<<grid, block, smem, stream>>>( args )  ->  cfb_emul::launch( grid, block, [&]{ kernel( args ); } ).
+syntax  kernel<<<grid, block, smem, stream>>>( args )  ->  cfb_emul::launch( grid, block, [=]{ kernel( args ); } )
+(arguments captured by value, as a real launch copies them: recorded launches can be replayed as a graph).
 """
 import os
 import re
@@ -80,7 +81,7 @@ def rewrite_launches(src):
         a1 = _match(src, a0, "(", ")")
         args = src[a0 + 1:a1 - 1]
         fn = "launch_coop" if kernel.strip().split("<")[0] in COOP_KERNELS else "launch"
-        out += src[pos:start] + (f"cfb_emul::{fn}( dim3( {cfg[0]} ), dim3( {cfg[1]} ), [&]() {{ {kernel}( {args} ); }} )")
+        out += src[pos:start] + (f"cfb_emul::{fn}( dim3( {cfg[0]} ), dim3( {cfg[1]} ), [=]() {{ {kernel}( {args} ); }} )")
         pos = a1
 
 

@@ -207,6 +207,17 @@ inline cudaError_t cudaStreamDestroy( cudaStream_t s )
     return cudaSuccess;
 }
 inline cudaError_t cudaStreamSynchronize( cudaStream_t ) { return cudaSuccess; }
+// CUDA graphs, kernel nodes only: while a capture is open the emulated launches are recorded (arguments by
+// value, as a real launch copies them) instead of executed; cudaGraphLaunch replays them.
+typedef struct cfb_emul_graph* cudaGraph_t;
+typedef struct cfb_emul_graph* cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1 };
+cudaError_t cudaStreamBeginCapture( cudaStream_t, cudaStreamCaptureMode );
+cudaError_t cudaStreamEndCapture( cudaStream_t, cudaGraph_t* );
+cudaError_t cudaGraphInstantiate( cudaGraphExec_t*, cudaGraph_t, unsigned long long );
+cudaError_t cudaGraphLaunch( cudaGraphExec_t, cudaStream_t );
+cudaError_t cudaGraphDestroy( cudaGraph_t );
+cudaError_t cudaGraphExecDestroy( cudaGraphExec_t );
 inline cudaError_t cudaStreamWaitEvent( cudaStream_t, cudaEvent_t, unsigned ) { return cudaSuccess; }
 inline cudaError_t cudaEventCreate( cudaEvent_t* e )
 {

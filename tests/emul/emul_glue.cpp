@@ -18,8 +18,25 @@ namespace cfb_emul
 thread_local uint3 g_threadIdx{ 0, 0, 0 }, g_blockIdx{ 0, 0, 0 };
 thread_local dim3 g_blockDim, g_gridDim;
 
+namespace
+{
+struct GraphNode
+{
+    dim3 grid, block;
+    std::function<void()> body;
+    bool coop;
+};
+thread_local bool t_capturing = false;
+thread_local std::vector<GraphNode> t_nodes;
+} // namespace
+
 void launch( dim3 grid, dim3 block, const std::function<void()>& body )
 {
+    if ( t_capturing )
+    {
+        t_nodes.push_back( { grid, block, body, false } );
+        return;
+    }
     g_gridDim = grid;
     g_blockDim = block;
     for ( unsigned bz = 0; bz < grid.z; ++bz )
@@ -95,6 +112,11 @@ void sync_threads()
 
 void launch_coop( dim3 grid, dim3 block, const std::function<void()>& body )
 {
+    if ( t_capturing )
+    {
+        t_nodes.push_back( { grid, block, body, true } );
+        return;
+    }
     Coop& c = t_coop;
     const unsigned nt = block.x; // 1-D blocks only
     g_gridDim = grid;
@@ -137,6 +159,54 @@ void launch_coop( dim3 grid, dim3 block, const std::function<void()>& body )
     }
 }
 } // namespace cfb_emul
+
+struct cfb_emul_graph
+{
+    std::vector<cfb_emul::GraphNode> nodes;
+};
+cudaError_t cudaStreamBeginCapture( cudaStream_t, cudaStreamCaptureMode )
+{
+    if ( cfb_emul::t_capturing )
+        return cudaErrorEmul;
+    cfb_emul::t_nodes.clear();
+    cfb_emul::t_capturing = true;
+    return cudaSuccess;
+}
+cudaError_t cudaStreamEndCapture( cudaStream_t, cudaGraph_t* g )
+{
+    if ( !cfb_emul::t_capturing )
+        return cudaErrorEmul;
+    cfb_emul::t_capturing = false;
+    *g = new cfb_emul_graph{ cfb_emul::t_nodes };
+    cfb_emul::t_nodes.clear();
+    return cudaSuccess;
+}
+cudaError_t cudaGraphInstantiate( cudaGraphExec_t* e, cudaGraph_t g, unsigned long long )
+{
+    *e = new cfb_emul_graph{ g->nodes };
+    return cudaSuccess;
+}
+cudaError_t cudaGraphLaunch( cudaGraphExec_t e, cudaStream_t )
+{
+    for ( const auto& n : e->nodes )
+    {
+        if ( n.coop )
+            cfb_emul::launch_coop( n.grid, n.block, n.body );
+        else
+            cfb_emul::launch( n.grid, n.block, n.body );
+    }
+    return cudaSuccess;
+}
+cudaError_t cudaGraphDestroy( cudaGraph_t g )
+{
+    delete g;
+    return cudaSuccess;
+}
+cudaError_t cudaGraphExecDestroy( cudaGraphExec_t e )
+{
+    delete e;
+    return cudaSuccess;
+}
 
 // cuTensorMapEncodeTiled as far as the product uses it: 3-D float64 tiles, no interleave / swizzle
 static CUresult emul_encode_tiled( CUtensorMap* m, CUtensorMapDataType, cuuint32_t rank, void* base,

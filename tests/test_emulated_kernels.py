@@ -323,3 +323,30 @@ def test_emulated_bench_tiling_is_what_runs_at_512(emul):
             s.build_rhs()
         assert g.pcg_solve() == o.pcg_solve(), variant
         assert np.array_equal(g.get(K.PRESSURE), o.get(K.PRESSURE)), variant
+
+
+@pytest.mark.parametrize("dim,cells,nu", [(3, 32, (2, 2, 8)), (2, (48, 40), (1, 1, 3)), (3, (24, 20, 16), (3, 0, 2))])
+def test_emulated_multigrid_cycle_replayed_as_a_graph(emul, dim, cells, nu):
+    """"mg_graph": the V-cycle's launches are captured once per form and replayed (the emulation records the
+    launches with their arguments by value and replays them, like a CUDA graph of kernel nodes)."""
+    if emul.tma:
+        pytest.skip("nothing TMA-specific")
+    cfg = make_cfg(dim, cells, box=box_of(cells))
+    g, o = Context(emul, cfg), Oracle(cfg)
+    g.set_tuning("mg_graph", 1)
+    for s in (g, o):
+        s.set_preconditioner("mg", *nu)
+    launches0 = g.stats()["kernel_launches"]
+    assert run(g, 2) == run(o, 2)
+    same_state(g, o, dim)
+    assert np.array_equal(g.residual_history(), o.residual_history())
+    r = np.random.default_rng(1).standard_normal(o.shape(K.PRESSURE))
+    for _ in range(2):
+        assert np.array_equal(g.mg_apply(r), o.mg_apply(r))
+    # the launch accounting does not depend on how the cycle is issued
+    g2 = Context(emul, cfg)
+    g2.set_preconditioner("mg", *nu)
+    run(g2, 2)
+    g2.mg_apply(r)
+    g2.mg_apply(r)
+    assert g.stats()["kernel_launches"] - launches0 == g2.stats()["kernel_launches"]

@@ -207,6 +207,31 @@ def test_cuda_mg_fixed_iterations_and_back_to_jacobi():
 
 
 @pytest.mark.gpu
+def test_cuda_mg_cycle_replayed_as_a_cuda_graph():
+    """"mg_graph" tuning key: same results, one graph launch per V-cycle instead of ~60 kernel launches."""
+    import time
+    from cajitafluids_b200 import Solver
+    cfg = make_cfg(3, 64)
+    o = Oracle(cfg)
+    o.set_preconditioner("mg")
+    io = run(o, 2)
+    t = {}
+    for graph in (0, 1):
+        g = Solver(cfg)
+        g.set_tuning("mg_graph", graph)
+        g.set_preconditioner("mg")
+        t0 = time.perf_counter()
+        assert list(run(g, 2)) == list(io)
+        t[graph] = time.perf_counter() - t0
+        for f in ALL(3):
+            assert np.array_equal(g.get(f), o.get(f)), (graph, f)
+        r = np.random.default_rng(1).standard_normal(o.shape(K.PRESSURE))
+        assert np.array_equal(g.mg_apply(r), o.mg_apply(r))
+        g.close()
+    print("64^3, setup + 2 steps with MG: plain launches %.4f s, graph %.4f s" % (t[0], t[1]))
+
+
+@pytest.mark.gpu
 def test_cuda_mg_beats_jacobi_at_128_cubed():
     """Time to solution of one projection at 128^3 with the reference's tolerance: the number that the
     preconditioner is there for (reported; required to be at least 1.5x better — at this size the V-cycle's ~60

@@ -32,8 +32,10 @@ def problem(kind, **kw):
 
 
 if mode == "solve":
-    for kind in ("jacobi", "mg"):
-        s = problem(kind)
+    for kind in ("jacobi", "mg", "mg+graph"):
+        s = problem(kind.split("+")[0])
+        if kind.endswith("graph"):
+            s.set_tuning("mg_graph", 1)
         s.pcg_solve()
         s.reset_stats()
         t0 = time.perf_counter()

@@ -424,14 +424,16 @@ def main():
         try:
             from cajitafluids_b200 import default_config
             tts = {}
-            for kind in ("jacobi", "mg", "mg_graph"):
+            for kind in ("jacobi", "mg", "mg_graph", "mg_graph_coarse"):
                 try:
                     c3 = default_config(3, args.cells, box=args.cells / 512.0)
                     c3.cg_max_iter = 20000
                     c3.cg_print_level = 0
                     s3 = Solver(c3)
-                    if kind == "mg_graph":  # the V-cycle's ~60 launches replayed as one CUDA graph
+                    if "graph" in kind:  # the V-cycle's ~60 launches replayed as one CUDA graph
                         s3.set_tuning("mg_graph", 1)
+                    if "coarse" in kind:  # levels <= 16^3 down and back up in one single-CTA kernel
+                        s3.set_tuning("mg_coarse_kernel", 1)
                     s3.set_preconditioner("jacobi" if kind == "jacobi" else "mg")
                     s3.add_inputs()
                     s3.build_rhs()

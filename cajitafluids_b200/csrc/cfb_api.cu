@@ -966,6 +966,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     }
     else if ( k == "mg_graph" )
         return mg_set_graph( c, value != 0 );
+    else if ( k == "mg_coarse_kernel" )
+        return mg_set_coarse_kernel( c, value != 0 );
     else if ( k == "peer_xstage" )
         c->peer_xstage_reads = value != 0;
     else if ( k == "time_kernels" )

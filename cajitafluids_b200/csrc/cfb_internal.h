@@ -194,6 +194,7 @@ struct cfb_ctx
     int precond = CFB_PRECOND_JACOBI;
     int mg_max_levels = 0; // 0 = as many as the block allows
     bool mg_graph = false; // "mg_graph" tuning key: replay the V-cycle as a CUDA graph (one block)
+    bool mg_coarse = false; // "mg_coarse_kernel" tuning key: the coarse end of the cycle in one single-CTA kernel
     MgStage* mg = nullptr;
 };
 
@@ -285,6 +286,7 @@ void output_destroy( cfb_ctx* c );
 int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid );
 void mg_destroy( cfb_ctx* c );
 int mg_set_graph( cfb_ctx* c, bool on );
+int mg_set_coarse_kernel( cfb_ctx* c, bool on );
 // halo.cu
 int halo_init( cfb_ctx* c );
 void halo_destroy( cfb_ctx* c );

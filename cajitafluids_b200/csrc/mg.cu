@@ -81,6 +81,9 @@ struct MgStage
     // "mg_graph" tuning key (one block only): the ~60 launches of a V-cycle replayed as one CUDA graph.  All
     // pointers, the ping-pong sequence and the launch shapes of a cycle are the same every time, so the graph
     // is captured once per form ([0] plain cycle, [1] with the fused z.r of the CG) and reused.
+    // "mg_coarse_kernel" tuning key (one block only): levels [coarse_start, last] run in one single-CTA kernel
+    bool use_coarse = false;
+    int coarse_start = -1;
     bool use_graph = false;
     cudaGraphExec_t graph[2] = { nullptr, nullptr };
     int graph_launches[2] = { 0, 0 };
@@ -119,17 +122,64 @@ __device__ __forceinline__ double mg_Ax( const MgLevelDev& L, const double* __re
                       x[o + L.sz] );
 }
 
+// ---- the element-wise operations of the cycle, one cell each (shared by the grid-wide kernels below and by
+// the single-CTA kernel that runs the coarse end of the cycle) ------------------------------------------
+__device__ __forceinline__ void cell_smooth0( const MgLevelDev& L, const double* __restrict__ b,
+                                              double* __restrict__ x, long long t )
+{
+    int i, j, k;
+    mg_decode( L, t, i, j, k );
+    const long long o = mg_off( L, i, j, k );
+    x[o] = L.wminv[mg_walls( L, i, j, k )] * b[o];
+}
+
+__device__ __forceinline__ double cell_smooth( const MgLevelDev& L, const double* __restrict__ b,
+                                               const double* __restrict__ xi, double* __restrict__ xo, long long t,
+                                               double* bv_out = nullptr )
+{
+    int i, j, k;
+    mg_decode( L, t, i, j, k );
+    const long long o = mg_off( L, i, j, k );
+    const int w = mg_walls( L, i, j, k );
+    const double bv = b[o];
+    const double res = bv - mg_Ax( L, xi, o, w );
+    const double z = fma( L.wminv[w], res, xi[o] );
+    xo[o] = z;
+    if ( bv_out )
+        *bv_out = bv;
+    return z;
+}
+
+// The first TWO sweeps from a zero initial guess in one pass (16 instead of 16 + 24 bytes per cell):
+// x1 = (omega D^-1) b is recomputed for the six neighbours from b itself (neighbours off the block are
+// the ghost zeros the unfused sweep would read), then x2 = x1 + omega D^-1 (b - A x1).
+__device__ __forceinline__ void cell_smooth02( const MgLevelDev& L, const double* __restrict__ b,
+                                               double* __restrict__ xo, long long t )
+{
+    int i, j, k;
+    mg_decode( L, t, i, j, k );
+    const long long o = mg_off( L, i, j, k );
+    const int w = mg_walls( L, i, j, k );
+    const double bc = b[o];
+    const double xc = L.wminv[w] * bc;
+    // a neighbour across a block interface is a ghost entry of b (exchanged by the caller); its wall
+    // count is that of an interior cell along the interface normal, which mg_walls returns for -1 / n
+    const double xm = ( i > 0 || L.nlo[0] ) ? L.wminv[mg_walls( L, i - 1, j, k )] * b[o - 1] : 0.0;
+    const double xp = ( i < L.n[0] - 1 || L.nhi[0] ) ? L.wminv[mg_walls( L, i + 1, j, k )] * b[o + 1] : 0.0;
+    const double ym = ( j > 0 || L.nlo[1] ) ? L.wminv[mg_walls( L, i, j - 1, k )] * b[o - L.sy] : 0.0;
+    const double yp = ( j < L.n[1] - 1 || L.nhi[1] ) ? L.wminv[mg_walls( L, i, j + 1, k )] * b[o + L.sy] : 0.0;
+    const double zm = ( k > 0 || L.nlo[2] ) ? L.wminv[mg_walls( L, i, j, k - 1 )] * b[o - L.sz] : 0.0;
+    const double zp = ( k < L.n[2] - 1 || L.nhi[2] ) ? L.wminv[mg_walls( L, i, j, k + 1 )] * b[o + L.sz] : 0.0;
+    const double res = bc - apply_row( L.diag[w], L.ns, xc, xm, xp, ym, yp, zm, zp );
+    xo[o] = fma( L.wminv[w], res, xc );
+}
+
 __global__ void __launch_bounds__( NT )
     mg_smooth0_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b, double* __restrict__ x )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-    {
-        int i, j, k;
-        mg_decode( L, t, i, j, k );
-        const long long o = mg_off( L, i, j, k );
-        x[o] = L.wminv[mg_walls( L, i, j, k )] * b[o];
-    }
+        cell_smooth0( L, b, x, t );
 }
 
 __global__ void __launch_bounds__( NT )
@@ -138,42 +188,15 @@ __global__ void __launch_bounds__( NT )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-    {
-        int i, j, k;
-        mg_decode( L, t, i, j, k );
-        const long long o = mg_off( L, i, j, k );
-        const int w = mg_walls( L, i, j, k );
-        const double res = b[o] - mg_Ax( L, xi, o, w );
-        xo[o] = fma( L.wminv[w], res, xi[o] );
-    }
+        cell_smooth( L, b, xi, xo, t );
 }
 
-// The first TWO sweeps from a zero initial guess in one pass (16 instead of 16 + 24 bytes per cell):
-// x1 = (omega D^-1) b is recomputed for the six neighbours from b itself (neighbours off the block are
-// the ghost zeros the unfused sweep would read), then x2 = x1 + omega D^-1 (b - A x1).
 __global__ void __launch_bounds__( NT )
     mg_smooth02_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b, double* __restrict__ xo )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-    {
-        int i, j, k;
-        mg_decode( L, t, i, j, k );
-        const long long o = mg_off( L, i, j, k );
-        const int w = mg_walls( L, i, j, k );
-        const double bc = b[o];
-        const double xc = L.wminv[w] * bc;
-        // a neighbour across a block interface is a ghost entry of b (exchanged by the caller); its wall
-        // count is that of an interior cell along the interface normal, which mg_walls returns for -1 / n
-        const double xm = ( i > 0 || L.nlo[0] ) ? L.wminv[mg_walls( L, i - 1, j, k )] * b[o - 1] : 0.0;
-        const double xp = ( i < L.n[0] - 1 || L.nhi[0] ) ? L.wminv[mg_walls( L, i + 1, j, k )] * b[o + 1] : 0.0;
-        const double ym = ( j > 0 || L.nlo[1] ) ? L.wminv[mg_walls( L, i, j - 1, k )] * b[o - L.sy] : 0.0;
-        const double yp = ( j < L.n[1] - 1 || L.nhi[1] ) ? L.wminv[mg_walls( L, i, j + 1, k )] * b[o + L.sy] : 0.0;
-        const double zm = ( k > 0 || L.nlo[2] ) ? L.wminv[mg_walls( L, i, j, k - 1 )] * b[o - L.sz] : 0.0;
-        const double zp = ( k < L.n[2] - 1 || L.nhi[2] ) ? L.wminv[mg_walls( L, i, j, k + 1 )] * b[o + L.sz] : 0.0;
-        const double res = bc - apply_row( L.diag[w], L.ns, xc, xm, xp, ym, yp, zm, zp );
-        xo[o] = fma( L.wminv[w], res, xc );
-    }
+        cell_smooth02( L, b, xo, t );
 }
 
 // End of a reduction.  One block: the rounded sum is final.  Several blocks (ranks): keep the local
@@ -201,14 +224,8 @@ __global__ void __launch_bounds__( NT )
     dd_t rz = { 0.0, 0.0 };
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
     {
-        int i, j, k;
-        mg_decode( L, t, i, j, k );
-        const long long o = mg_off( L, i, j, k );
-        const int w = mg_walls( L, i, j, k );
-        const double bv = b[o];
-        const double res = bv - mg_Ax( L, xi, o, w );
-        const double z = fma( L.wminv[w], res, xi[o] );
-        xo[o] = z;
+        double bv;
+        const double z = cell_smooth( L, b, xi, xo, t, &bv );
         dd_acc( rz, z * bv );
     }
     dd_t vals[1] = { rz };
@@ -227,28 +244,71 @@ __device__ __forceinline__ double mg_res( const MgLevelDev& F, const double* __r
 }
 
 // coarse b = mean of the children's residuals, summed pairwise: x pairs, then y, then z
+__device__ __forceinline__ void cell_restrict( const MgLevelDev& F, const MgLevelDev& C, const double* __restrict__ bf,
+                                               const double* __restrict__ xf, double* __restrict__ bc, long long t )
+{
+    int I, J, K;
+    mg_decode( C, t, I, J, K );
+    const int i = 2 * I, j = 2 * J, k = F.cz * K;
+    double s = ( mg_res( F, bf, xf, i, j, k ) + mg_res( F, bf, xf, i + 1, j, k ) ) +
+               ( mg_res( F, bf, xf, i, j + 1, k ) + mg_res( F, bf, xf, i + 1, j + 1, k ) );
+    if ( F.cz == 2 )
+    {
+        const double u = ( mg_res( F, bf, xf, i, j, k + 1 ) + mg_res( F, bf, xf, i + 1, j, k + 1 ) ) +
+                         ( mg_res( F, bf, xf, i, j + 1, k + 1 ) + mg_res( F, bf, xf, i + 1, j + 1, k + 1 ) );
+        s = ( s + u ) * 0.125;
+    }
+    else
+        s = s * 0.25;
+    bc[mg_off( C, I, J, K )] = s;
+}
+
+__device__ __forceinline__ void cell_prolong( const MgLevelDev& F, const MgLevelDev& C, double* __restrict__ xf,
+                                              const double* __restrict__ ec, long long t )
+{
+    int i, j, k;
+    mg_decode( F, t, i, j, k );
+    const long long o = mg_off( F, i, j, k );
+    xf[o] = xf[o] + ec[mg_off( C, i / 2, j / 2, k / F.cz )];
+}
+
+// Prolongation + correction + the first post-smoothing sweep in one pass (24 instead of 17 + 24 bytes per
+// cell): x' = x + P e is formed on the fly for the cell and its six neighbours (neighbours off the block:
+// the ghost zeros of x', which the separate prolongation never writes), then xo = x' + omega D^-1 (b - A x').
+__device__ __forceinline__ double cell_prolong_smooth( const MgLevelDev& F, const MgLevelDev& C,
+                                                       const double* __restrict__ b, const double* __restrict__ xi,
+                                                       const double* __restrict__ ec, double* __restrict__ xo,
+                                                       long long t, double* bv_out = nullptr )
+{
+    int i, j, k;
+    mg_decode( F, t, i, j, k );
+    const long long o = mg_off( F, i, j, k );
+    const int w = mg_walls( F, i, j, k );
+    const int I = i / 2, J = j / 2, K = k / F.cz;
+    const double xc = xi[o] + ec[mg_off( C, I, J, K )];
+    // across a block interface: the ghost entries of x and of the coarse correction (both exchanged)
+    const double xm = ( i > 0 || F.nlo[0] ) ? xi[o - 1] + ec[mg_off( C, mg_parent( i - 1, 2 ), J, K )] : 0.0;
+    const double xp = ( i < F.n[0] - 1 || F.nhi[0] ) ? xi[o + 1] + ec[mg_off( C, mg_parent( i + 1, 2 ), J, K )] : 0.0;
+    const double ym = ( j > 0 || F.nlo[1] ) ? xi[o - F.sy] + ec[mg_off( C, I, mg_parent( j - 1, 2 ), K )] : 0.0;
+    const double yp = ( j < F.n[1] - 1 || F.nhi[1] ) ? xi[o + F.sy] + ec[mg_off( C, I, mg_parent( j + 1, 2 ), K )] : 0.0;
+    const double zm = ( k > 0 || F.nlo[2] ) ? xi[o - F.sz] + ec[mg_off( C, I, J, mg_parent( k - 1, F.cz ) )] : 0.0;
+    const double zp = ( k < F.n[2] - 1 || F.nhi[2] ) ? xi[o + F.sz] + ec[mg_off( C, I, J, mg_parent( k + 1, F.cz ) )] : 0.0;
+    const double bv = b[o];
+    const double res = bv - apply_row( F.diag[w], F.ns, xc, xm, xp, ym, yp, zm, zp );
+    const double z = fma( F.wminv[w], res, xc );
+    xo[o] = z;
+    if ( bv_out )
+        *bv_out = bv;
+    return z;
+}
+
 __global__ void __launch_bounds__( NT )
     mg_restrict_kernel( const __grid_constant__ MgLevelDev F, const __grid_constant__ MgLevelDev C,
                         const double* __restrict__ bf, const double* __restrict__ xf, double* __restrict__ bc )
 {
     const long long total = (long long)C.n[0] * C.n[1] * C.n[2];
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-    {
-        int I, J, K;
-        mg_decode( C, t, I, J, K );
-        const int i = 2 * I, j = 2 * J, k = F.cz * K;
-        double s = ( mg_res( F, bf, xf, i, j, k ) + mg_res( F, bf, xf, i + 1, j, k ) ) +
-                   ( mg_res( F, bf, xf, i, j + 1, k ) + mg_res( F, bf, xf, i + 1, j + 1, k ) );
-        if ( F.cz == 2 )
-        {
-            const double u = ( mg_res( F, bf, xf, i, j, k + 1 ) + mg_res( F, bf, xf, i + 1, j, k + 1 ) ) +
-                             ( mg_res( F, bf, xf, i, j + 1, k + 1 ) + mg_res( F, bf, xf, i + 1, j + 1, k + 1 ) );
-            s = ( s + u ) * 0.125;
-        }
-        else
-            s = s * 0.25;
-        bc[mg_off( C, I, J, K )] = s;
-    }
+        cell_restrict( F, C, bf, xf, bc, t );
 }
 
 __global__ void __launch_bounds__( NT )
@@ -257,17 +317,9 @@ __global__ void __launch_bounds__( NT )
 {
     const long long total = (long long)F.n[0] * F.n[1] * F.n[2];
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-    {
-        int i, j, k;
-        mg_decode( F, t, i, j, k );
-        const long long o = mg_off( F, i, j, k );
-        xf[o] = xf[o] + ec[mg_off( C, i / 2, j / 2, k / F.cz )];
-    }
+        cell_prolong( F, C, xf, ec, t );
 }
 
-// Prolongation + correction + the first post-smoothing sweep in one pass (24 instead of 17 + 24 bytes per
-// cell): x' = x + P e is formed on the fly for the cell and its six neighbours (neighbours off the block:
-// the ghost zeros of x', which the separate prolongation never writes), then xo = x' + omega D^-1 (b - A x').
 // DOT: also sum xo . b (see mg_smooth_dot_kernel), for cycles whose only post-smoothing sweep this is.
 template <bool DOT>
 __global__ void __launch_bounds__( NT )
@@ -279,23 +331,8 @@ __global__ void __launch_bounds__( NT )
     dd_t rz = { 0.0, 0.0 };
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
     {
-        int i, j, k;
-        mg_decode( F, t, i, j, k );
-        const long long o = mg_off( F, i, j, k );
-        const int w = mg_walls( F, i, j, k );
-        const int I = i / 2, J = j / 2, K = k / F.cz;
-        const double xc = xi[o] + ec[mg_off( C, I, J, K )];
-        // across a block interface: the ghost entries of x and of the coarse correction (both exchanged)
-        const double xm = ( i > 0 || F.nlo[0] ) ? xi[o - 1] + ec[mg_off( C, mg_parent( i - 1, 2 ), J, K )] : 0.0;
-        const double xp = ( i < F.n[0] - 1 || F.nhi[0] ) ? xi[o + 1] + ec[mg_off( C, mg_parent( i + 1, 2 ), J, K )] : 0.0;
-        const double ym = ( j > 0 || F.nlo[1] ) ? xi[o - F.sy] + ec[mg_off( C, I, mg_parent( j - 1, 2 ), K )] : 0.0;
-        const double yp = ( j < F.n[1] - 1 || F.nhi[1] ) ? xi[o + F.sy] + ec[mg_off( C, I, mg_parent( j + 1, 2 ), K )] : 0.0;
-        const double zm = ( k > 0 || F.nlo[2] ) ? xi[o - F.sz] + ec[mg_off( C, I, J, mg_parent( k - 1, F.cz ) )] : 0.0;
-        const double zp = ( k < F.n[2] - 1 || F.nhi[2] ) ? xi[o + F.sz] + ec[mg_off( C, I, J, mg_parent( k + 1, F.cz ) )] : 0.0;
-        const double bv = b[o];
-        const double res = bv - apply_row( F.diag[w], F.ns, xc, xm, xp, ym, yp, zm, zp );
-        const double z = fma( F.wminv[w], res, xc );
-        xo[o] = z;
+        double bv;
+        const double z = cell_prolong_smooth( F, C, b, xi, ec, xo, t, &bv );
         if ( DOT )
             dd_acc( rz, z * bv );
     }
@@ -307,6 +344,99 @@ __global__ void __launch_bounds__( NT )
             if ( threadIdx.x == 0 )
                 mg_publish( S, vals[0], 0, &S->rz_new );
         }
+    }
+}
+
+// ---- the coarse end of the cycle in ONE kernel ------------------------------------------------------------
+// From the first level with at most MG_COARSE_CELLS cells down to the coarsest and back up, a single CTA runs
+// every sweep / transfer with a block barrier in between ("mg_coarse_kernel" tuning key; one block only).  The
+// arrays of these levels (<= 3 x 46 KB each, smaller below) live in the L2; what is saved is ~30 of the ~60
+// launches of a cycle, which is what bounds the cycle on grids up to ~128^3.  Same element-wise operations in
+// the same order as the launch-per-operation form: bit-identical.
+#define MG_COARSE_CELLS 4096
+#define MG_COARSE_LEVELS 8
+struct MgCoarseArgs
+{
+    int nlev, nu1, nu2, nuc;
+    MgLevelDev lv[MG_COARSE_LEVELS];
+    double* b[MG_COARSE_LEVELS];
+    double* x[MG_COARSE_LEVELS][2];
+};
+
+__global__ void __launch_bounds__( NT )
+    mg_coarse_cycle_kernel( const __grid_constant__ MgCoarseArgs a )
+{
+    __shared__ int cur[MG_COARSE_LEVELS];
+    const int tid = threadIdx.x;
+    // down: pre-smoothing (the coarsest level: its nuc sweeps), residual + restriction
+    for ( int l = 0; l < a.nlev; ++l )
+    {
+        const MgLevelDev& L = a.lv[l];
+        const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+        const int sweeps = l == a.nlev - 1 ? a.nuc : a.nu1;
+        int c, done;
+        if ( sweeps >= 2 )
+        {
+            for ( long long t = tid; t < total; t += NT )
+                cell_smooth02( L, a.b[l], a.x[l][1], t );
+            c = 1;
+            done = 2;
+        }
+        else
+        {
+            for ( long long t = tid; t < total; t += NT )
+                cell_smooth0( L, a.b[l], a.x[l][0], t );
+            c = 0;
+            done = 1;
+        }
+        __syncthreads();
+        for ( ; done < sweeps; ++done )
+        {
+            for ( long long t = tid; t < total; t += NT )
+                cell_smooth( L, a.b[l], a.x[l][c], a.x[l][1 - c], t );
+            c = 1 - c;
+            __syncthreads();
+        }
+        if ( tid == 0 )
+            cur[l] = c;
+        if ( l + 1 < a.nlev )
+        {
+            const MgLevelDev& C = a.lv[l + 1];
+            const long long ctotal = (long long)C.n[0] * C.n[1] * C.n[2];
+            for ( long long t = tid; t < ctotal; t += NT )
+                cell_restrict( L, C, a.b[l], a.x[l][c], a.b[l + 1], t );
+        }
+        __syncthreads();
+    }
+    // up: prolongation + correction (+ first post-smoothing sweep), remaining post-smoothing sweeps
+    for ( int l = a.nlev - 2; l >= 0; --l )
+    {
+        const MgLevelDev& L = a.lv[l];
+        const MgLevelDev& C = a.lv[l + 1];
+        const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+        int c = cur[l];
+        const double* ec = a.x[l + 1][cur[l + 1]];
+        if ( a.nu2 == 0 )
+        {
+            for ( long long t = tid; t < total; t += NT )
+                cell_prolong( L, C, a.x[l][c], ec, t );
+            __syncthreads();
+            continue;
+        }
+        for ( long long t = tid; t < total; t += NT )
+            cell_prolong_smooth( L, C, a.b[l], a.x[l][c], ec, a.x[l][1 - c], t );
+        c = 1 - c;
+        __syncthreads();
+        for ( int s2 = 1; s2 < a.nu2; ++s2 )
+        {
+            for ( long long t = tid; t < total; t += NT )
+                cell_smooth( L, a.b[l], a.x[l][c], a.x[l][1 - c], t );
+            c = 1 - c;
+            __syncthreads();
+        }
+        if ( tid == 0 )
+            cur[l] = c;
+        __syncthreads();
     }
 }
 
@@ -580,6 +710,7 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega, int max_level
     c->mg = m;
     m->max_levels = max_levels;
     m->use_graph = c->mg_graph;
+    m->use_coarse = c->mg_coarse;
     m->nu1 = nu1;
     m->nu2 = nu2;
     m->nuc = nuc;
@@ -665,6 +796,13 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega, int max_level
         scale = scale * 0.25;
     }
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    m->coarse_start = -1;
+    for ( int l = 0; l < (int)m->lv.size(); ++l )
+        if ( m->lv[l].cells <= MG_COARSE_CELLS && (int)m->lv.size() - l <= MG_COARSE_LEVELS )
+        {
+            m->coarse_start = l;
+            break;
+        }
     return CFB_OK;
 }
 
@@ -768,6 +906,33 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
     const int grid = grid_for( c, H.cells );
     if ( dotted )
         *dotted = false;
+    if ( m->use_coarse && !c->cfg.use_nccl && l == m->coarse_start )
+    {
+        // the rest of the cycle, down to the coarsest level and back up to this one, in one single-CTA kernel
+        MgCoarseArgs a{};
+        a.nlev = (int)m->lv.size() - l;
+        a.nu1 = m->nu1;
+        a.nu2 = m->nu2;
+        a.nuc = m->nuc;
+        for ( int q = 0; q < a.nlev; ++q )
+        {
+            MgLevelHost& Q = m->lv[l + q];
+            a.lv[q] = Q.d;
+            a.b[q] = Q.b;
+            a.x[q][0] = Q.x[0];
+            a.x[q][1] = Q.x[1];
+        }
+        mg_coarse_cycle_kernel<<<1, NT, 0, c->stream>>>( a );
+        *n += 1;
+        // where the kernel leaves this level's result: the same ping-pong sequence as the launches below
+        const int sweeps = last ? m->nuc : m->nu1;
+        int cur = sweeps >= 2 ? 1 : 0;
+        cur ^= ( sweeps - ( sweeps >= 2 ? 2 : 1 ) ) & 1;
+        if ( !last )
+            cur ^= m->nu2 & 1;
+        H.cur = cur;
+        return CFB_OK;
+    }
     MG_TRY( launch_presmooth( c, H, last ? m->nuc : m->nu1, n ) );
     if ( last )
         return CFB_OK;
@@ -848,12 +1013,27 @@ int run_cycle( cfb_ctx* c, bool dot, bool* dotted, int* n )
 
 void mg_destroy( cfb_ctx* c ) { mg_free( c ); }
 
-// "mg_graph" tuning key
+// "mg_graph" / "mg_coarse_kernel" tuning keys
 int mg_set_graph( cfb_ctx* c, bool on )
 {
     if ( c->mg )
         c->mg->use_graph = on;
     c->mg_graph = on;
+    return CFB_OK;
+}
+int mg_set_coarse_kernel( cfb_ctx* c, bool on )
+{
+    if ( c->mg )
+    {
+        c->mg->use_coarse = on;
+        for ( cudaGraphExec_t& g : c->mg->graph ) // a captured cycle has the other form baked in
+            if ( g )
+            {
+                cudaGraphExecDestroy( g );
+                g = nullptr;
+            }
+    }
+    c->mg_coarse = on;
     return CFB_OK;
 }
 

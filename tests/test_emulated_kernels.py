@@ -350,3 +350,46 @@ def test_emulated_multigrid_cycle_replayed_as_a_graph(emul, dim, cells, nu):
     g2.mg_apply(r)
     g2.mg_apply(r)
     assert g.stats()["kernel_launches"] - launches0 == g2.stats()["kernel_launches"]
+
+
+@pytest.mark.parametrize("dim,cells,nu", [(3, 32, (2, 2, 8)), (3, 64, (2, 2, 8)), (2, (48, 40), (1, 1, 3)), (3, (24, 20, 16), (3, 0, 2)),
+                                          (3, 16, (2, 1, 1)), (2, 128, (1, 2, 5)), (3, (12, 20, 8), (2, 2, 4))])
+def test_emulated_multigrid_coarse_end_in_one_kernel(emul, dim, cells, nu):
+    """"mg_coarse_kernel": from the first level with <= 4096 cells down and back up in a single-CTA kernel with
+    block barriers (fibers in the emulation): the same operations in the same order, bit for bit; also together
+    with the graph replay of the whole cycle."""
+    if emul.tma:
+        pytest.skip("nothing TMA-specific")
+    cfg = make_cfg(dim, cells, box=box_of(cells), fixed_iters=6)
+    o = Oracle(cfg)
+    o.set_preconditioner("mg", *nu)
+    vel = smooth_velocity(o, np.random.default_rng(8))
+    for f, a in vel.items():
+        o.set(f, a)
+    o.add_inputs()
+    o.build_rhs()
+    ro = o.pcg_solve()
+    po = o.get(K.PRESSURE)
+    r = np.random.default_rng(2).standard_normal(o.shape(K.PRESSURE))
+    zo = o.mg_apply(r)
+    for graph in (0, 1):
+        g = Context(emul, cfg)
+        g.set_tuning("mg_coarse_kernel", 1)
+        g.set_tuning("mg_graph", graph)
+        g.set_preconditioner("mg", *nu)
+        for f, a in vel.items():
+            g.set(f, a)
+        g.add_inputs()
+        g.build_rhs()
+        n0 = g.stats()["kernel_launches"]
+        assert g.pcg_solve() == ro
+        n_coarse = g.stats()["kernel_launches"] - n0
+        assert np.array_equal(g.get(K.PRESSURE), po)
+        assert np.array_equal(g.mg_apply(r), zo)
+        assert np.array_equal(g.mg_apply(r), zo)
+        # fewer launches than the launch-per-operation form
+        g.set_tuning("mg_coarse_kernel", 0)
+        g.build_rhs()
+        n0 = g.stats()["kernel_launches"]
+        assert g.pcg_solve() == ro and np.array_equal(g.get(K.PRESSURE), po)
+        assert n_coarse < g.stats()["kernel_launches"] - n0

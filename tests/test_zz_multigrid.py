@@ -216,19 +216,20 @@ def test_cuda_mg_cycle_replayed_as_a_cuda_graph():
     o.set_preconditioner("mg")
     io = run(o, 2)
     t = {}
-    for graph in (0, 1):
+    for graph, coarse in ((0, 0), (1, 0), (0, 1), (1, 1)):
         g = Solver(cfg)
         g.set_tuning("mg_graph", graph)
+        g.set_tuning("mg_coarse_kernel", coarse)  # levels <= 16^3 down and back up in one single-CTA kernel
         g.set_preconditioner("mg")
         t0 = time.perf_counter()
-        assert list(run(g, 2)) == list(io)
-        t[graph] = time.perf_counter() - t0
+        assert list(run(g, 2)) == list(io), (graph, coarse)
+        t[(graph, coarse)] = time.perf_counter() - t0
         for f in ALL(3):
-            assert np.array_equal(g.get(f), o.get(f)), (graph, f)
+            assert np.array_equal(g.get(f), o.get(f)), (graph, coarse, f)
         r = np.random.default_rng(1).standard_normal(o.shape(K.PRESSURE))
-        assert np.array_equal(g.mg_apply(r), o.mg_apply(r))
+        assert np.array_equal(g.mg_apply(r), o.mg_apply(r)), (graph, coarse)
         g.close()
-    print("64^3, setup + 2 steps with MG: plain launches %.4f s, graph %.4f s" % (t[0], t[1]))
+    print("64^3, setup + 2 steps with MG, seconds by (graph, coarse kernel):", t)
 
 
 @pytest.mark.gpu

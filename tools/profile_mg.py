@@ -32,10 +32,12 @@ def problem(kind, **kw):
 
 
 if mode == "solve":
-    for kind in ("jacobi", "mg", "mg+graph"):
+    for kind in ("jacobi", "mg", "mg+graph", "mg+coarse", "mg+graph+coarse"):
         s = problem(kind.split("+")[0])
-        if kind.endswith("graph"):
+        if "graph" in kind:
             s.set_tuning("mg_graph", 1)
+        if "coarse" in kind:
+            s.set_tuning("mg_coarse_kernel", 1)
         s.pcg_solve()
         s.reset_stats()
         t0 = time.perf_counter()

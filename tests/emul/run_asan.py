@@ -21,7 +21,8 @@ def build():
     import build_emul
     build_emul.build(force=True)
     out = build_emul.OUT
-    cpp = [os.path.join(out, f) for f in sorted(os.listdir(out)) if f.endswith(".cpp")]
+    cpp = [os.path.join(out, f.replace(".cu", "_emul.cpp")) for f in build_emul.SOURCES] + \
+          [os.path.join(out, "emul_glue.cpp"), os.path.join(out, "nccl_emul.cpp")]
     lib = os.path.join(out, "libcfb_emul_asan.so")
     cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer",
            "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-pthread", "-Wl,-Bsymbolic",

@@ -185,10 +185,32 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
 
     dd_t acc = { 0.0, 0.0 }, acc2 = { 0.0, 0.0 }; // MODE 0: p.q | MODE 1: r.r, r.M^-1 r
     double* qrow = ( MODE == 0 ? a.q : a.r ) + geo_off( g, i0, y0 + wy, kbeg );
+    // MODE 1: r is streamed with 128-bit loads one plane ahead of its use (the loads of plane k + 1 are in
+    // flight while plane k waits for its TMA stage and is computed), like x in phase B
+    double2 rcur[RY], rnxt[RY];
+    auto load_r = [&]( double2* dst, const double* row0 ) {
+#pragma unroll
+        for ( int r = 0; r < RY; ++r )
+        {
+            dst[r] = make_double2( 0.0, 0.0 );
+            if ( vy[r] )
+            {
+                const double* rp = row0 + (long long)( r * WY ) * g.sy;
+                if ( vx1 )
+                    dst[r] = *reinterpret_cast<const double2*>( rp );
+                else if ( vx0 )
+                    dst[r].x = *rp;
+            }
+        }
+    };
+    if ( MODE == 1 && nplanes > 0 )
+        load_r( rcur, qrow );
     for ( int it = 0; it < nplanes; ++it )
     {
         const int lc = it + 1, ln = it + 2; // load indices of plane k and plane k+1
         const int sc = lc % NS, sn = ln % NS;
+        if ( MODE == 1 && it + 1 < nplanes )
+            load_r( rnxt, qrow + g.sz );
         mbar_wait( smem_u32( &full_bar[sn] ), ( ln / NS ) & 1 );
         const double* P = stage0 + sc * ( C::STAGE_BYTES / 8 );
         const double* N = stage0 + sn * ( C::STAGE_BYTES / 8 );
@@ -231,7 +253,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
                     const int w0 = wx0 + wyc[r] + wz, w1 = wx1 + wyc[r] + wz;
                     if ( vx1 )
                     {
-                        double2 rv = *reinterpret_cast<const double2*>( qp );
+                        double2 rv = rcur[r];
                         rv.x = fma( nalpha, a0, rv.x );
                         rv.y = fma( nalpha, a1, rv.y );
                         *reinterpret_cast<double2*>( qp ) = rv;
@@ -242,7 +264,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
                     }
                     else if ( vx0 )
                     {
-                        const double rv = fma( nalpha, a0, *qp );
+                        const double rv = fma( nalpha, a0, rcur[r].x );
                         *qp = rv;
                         dd_acc( acc, rv * rv );
                         dd_acc( acc2, ( op.minv[w0] * rv ) * rv );
@@ -251,6 +273,8 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
             }
             zm[r] = c;
             cc[r] = zp;
+            if ( MODE == 1 )
+                rcur[r] = rnxt[r];
         }
         qrow += g.sz;
         __syncthreads(); // every thread is done with slot sc -> it can be refilled

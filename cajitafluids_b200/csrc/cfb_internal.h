@@ -89,6 +89,9 @@ struct PeerMail
 {
     double v[2][CFB_MAX_PEERS][4];
     unsigned long long seq[2][CFB_MAX_PEERS];
+    // multigrid ghost exchanges (mg.cu): slot [writer rank] = number of exchanges whose stores that rank has
+    // completed into my arrays
+    unsigned long long mseq[CFB_MAX_PEERS];
 };
 
 #define CFB_MAX_PARTIALS 4096
@@ -304,6 +307,10 @@ int halo_cells_end( cfb_ctx* c );
 int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpack );
 int halo_exchange_fields( cfb_ctx* c, int version );             // width-h exchange of q,u,v,w
 int halo_sendrecv_slots( cfb_ctx* c, const size_t counts[6], cudaStream_t st ); // d_halo_send/recv[s] <-> nbr[s]
+// NVLink peer memory for further arrays: every rank passes its `count` device allocations (same count, same
+// order on all ranks); on success mapped[s * count + a] is the face-s neighbour's array a in this process
+// (nullptr where there is no neighbour) and *ok is true on every rank, otherwise *ok is false on every rank.
+int peer_map_arrays( cfb_ctx* c, int count, double* const* mine, std::vector<double*>& mapped, bool* ok );
 int halo_allreduce( cfb_ctx* c, double* dev_vals, int n );
 int halo_allgather( cfb_ctx* c, const double* dev_send, double* dev_recv, int n_per_rank );
 // kernels_cg.cu: all-gather + exact combine of the local CG sums (which = 0: pAp, 1: rz_new and rr)

@@ -787,6 +787,74 @@ int halo_exchange_fields( cfb_ctx* c, int version )
     return CFB_OK;
 }
 
+int peer_map_arrays( cfb_ctx* c, int count, double* const* mine, std::vector<double*>& mapped, bool* ok_out )
+{
+    Comm* cm = static_cast<Comm*>( c->nccl );
+    const int W = c->cfg.world_size, me = c->cfg.world_rank;
+    *ok_out = false;
+    mapped.assign( (size_t)6 * count, nullptr );
+    if ( !cm || count < 1 )
+        return CFB_OK;
+    // [flag][count handles] per rank, all-gathered as bytes
+    const size_t rec = sizeof( cudaIpcMemHandle_t ) * count + 64;
+    std::vector<char> mine_rec( rec, 0 );
+    int good = c->peer_ok ? 1 : 0; // no peer mailboxes, no peer exchanges
+    for ( int a = 0; a < count && good; ++a )
+        if ( cudaIpcGetMemHandle( reinterpret_cast<cudaIpcMemHandle_t*>( mine_rec.data() + 64 ) + a, mine[a] ) != cudaSuccess )
+        {
+            cudaGetLastError();
+            good = 0;
+        }
+    std::memcpy( mine_rec.data(), &good, sizeof( int ) );
+    char* d_all = nullptr;
+    CFB_CUDA( c, cudaMalloc( &d_all, rec * ( W + 1 ) ) );
+    CFB_CUDA( c, cudaMemcpy( d_all + rec * W, mine_rec.data(), rec, cudaMemcpyHostToDevice ) );
+    CFB_NCCL( c, g_nccl.AllGather( d_all + rec * W, d_all, rec, ncclChar, cm->red, c->stream ) );
+    CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    std::vector<char> all( rec * W );
+    CFB_CUDA( c, cudaMemcpy( all.data(), d_all, rec * W, cudaMemcpyDeviceToHost ) );
+    cudaFree( d_all );
+    bool ok = true;
+    for ( int r = 0; r < W; ++r )
+    {
+        int g = 0;
+        std::memcpy( &g, all.data() + rec * r, sizeof( int ) );
+        ok = ok && g != 0;
+    }
+    if ( ok )
+        for ( int s = 0; s < 6 && ok; ++s )
+        {
+            const int r = c->nbr[s];
+            if ( r < 0 || r == me )
+                continue;
+            const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>( all.data() + rec * r + 64 );
+            for ( int a = 0; a < count && ok; ++a )
+            {
+                void* p = nullptr;
+                if ( cudaIpcOpenMemHandle( &p, h[a], cudaIpcMemLazyEnablePeerAccess ) != cudaSuccess )
+                {
+                    cudaGetLastError();
+                    ok = false;
+                    break;
+                }
+                c->ipc_opened.push_back( p );
+                mapped[(size_t)s * count + a] = static_cast<double*>( p );
+            }
+        }
+    // everybody or nobody
+    double flag = ok ? 0.0 : 1.0, *d_flag = nullptr;
+    CFB_CUDA( c, cudaMalloc( &d_flag, sizeof( double ) ) );
+    CFB_CUDA( c, cudaMemcpy( d_flag, &flag, sizeof( double ), cudaMemcpyHostToDevice ) );
+    CFB_NCCL( c, g_nccl.AllReduce( d_flag, d_flag, 1, ncclDouble, ncclSum, cm->red, c->stream ) );
+    CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    CFB_CUDA( c, cudaMemcpy( &flag, d_flag, sizeof( double ), cudaMemcpyDeviceToHost ) );
+    cudaFree( d_flag );
+    *ok_out = flag == 0.0;
+    if ( !*ok_out )
+        mapped.assign( (size_t)6 * count, nullptr );
+    return CFB_OK;
+}
+
 // One grouped exchange of the per-neighbour buffers: d_halo_send[s] (counts[s] doubles) goes to the neighbour on
 // face s, d_halo_recv[s] is filled by it; used by callers that pack / unpack with their own kernels (the
 // multigrid levels of mg.cu, whose arrays do not have the layout of the CG vectors).

@@ -39,6 +39,7 @@
 #include "device_geo.cuh"
 #include "device_reduce.cuh"
 
+#include <algorithm>
 #include <cmath>
 
 namespace
@@ -81,6 +82,14 @@ struct MgStage
     // "mg_graph" tuning key (one block only): the ~60 launches of a V-cycle replayed as one CUDA graph.  All
     // pointers, the ping-pong sequence and the launch shapes of a cycle are the same every time, so the graph
     // is captured once per form ([0] plain cycle, [1] with the fused z.r of the CG) and reused.
+    // several blocks with NVLink peer memory: the neighbours' level arrays mapped into this process, so that a
+    // ghost exchange is ONE kernel that stores my boundary layers into their ghost layers and meets them at a
+    // flag barrier (mg_xchg_kernel) instead of pack kernel + NCCL send/recv + unpack kernel
+    bool peer = false;
+    std::vector<double*> own_arrays;  // what was exported, in the order all ranks use
+    std::vector<double*> peer_arrays; // [face s][array a] -> peer_arrays[s * own_arrays.size() + a]
+    unsigned long long xseq = 0;      // exchanges so far (the same on every rank)
+    const double* last_xchg = nullptr; // the array of the previous exchange
     // "mg_coarse_kernel" tuning key (one block only): levels [coarse_start, last] run in one single-CTA kernel
     bool use_coarse = false;
     int coarse_start = -1;
@@ -671,6 +680,76 @@ __global__ void __launch_bounds__( NT )
     }
 }
 
+// The same exchange over NVLink peer memory, one kernel: (1) my boundary layers go straight into the
+// neighbours' ghost layers (same level geometry on every rank); (2) system-scope fence, ticket; the last block
+// (3) tells every neighbour "my stores of exchange #seq are done" in its mailbox and (4) waits until every
+// neighbour has said the same in mine (bounded spin).  The protocol of cg_xchg_kernel (halo.cu), between face
+// neighbours only.  Consecutive exchanges never target the same array, so a neighbour that is still reading the
+// ghosts of the previous exchange is never overwritten: it cannot be more than one exchange behind.
+struct MgXchg
+{
+    int nface;
+    int dim[6], src[6], dst[6];
+    double* peer[6];                    // the neighbour's copy of the array being exchanged
+    unsigned long long* tell[6];        // &mail[neighbour]->mseq[me]
+    const unsigned long long* hear[6];  // &mail_self->mseq[neighbour]
+    unsigned long long seq;
+    unsigned int* ticket;
+    CgState* S;
+    long long timeout_cycles;
+};
+
+__device__ __forceinline__ unsigned long long mg_ld_volatile_u64( const unsigned long long* p )
+{
+    return *reinterpret_cast<const volatile unsigned long long*>( p );
+}
+
+__global__ void __launch_bounds__( NT )
+    mg_xchg_kernel( const __grid_constant__ MgLevelDev L, const __grid_constant__ MgXchg a, const double* arr )
+{
+    for ( int f = 0; f < a.nface; ++f )
+    {
+        const int d = a.dim[f];
+        const int e0 = d == 0 ? L.n[1] : L.n[0];
+        const int e1 = d == 2 ? L.n[1] : L.n[2];
+        const long long total = (long long)e0 * e1;
+        double* dst = a.peer[f];
+        for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+        {
+            const int u = (int)( t % e0 ), v = (int)( t / e0 );
+            const int i = d == 0 ? a.src[f] : u, j = d == 0 ? u : ( d == 1 ? a.src[f] : v ), k = d == 2 ? a.src[f] : v;
+            const int I = d == 0 ? a.dst[f] : i, J = d == 1 ? a.dst[f] : j, K = d == 2 ? a.dst[f] : k;
+            dst[mg_off( L, I, J, K )] = arr[mg_off( L, i, j, k )];
+        }
+    }
+    __threadfence_system();
+    __shared__ bool s_last;
+    __syncthreads();
+    if ( threadIdx.x == 0 )
+        s_last = atomicAdd( a.ticket, 1u ) == gridDim.x - 1;
+    __syncthreads();
+    if ( !s_last )
+        return;
+    __threadfence_system();
+    if ( threadIdx.x == 0 )
+        *a.ticket = 0u;
+    if ( threadIdx.x < a.nface )
+    {
+        *reinterpret_cast<volatile unsigned long long*>( a.tell[threadIdx.x] ) = a.seq;
+        if ( !a.S->xerror )
+        {
+            const long long t0 = clock64();
+            while ( mg_ld_volatile_u64( a.hear[threadIdx.x] ) < a.seq )
+                if ( clock64() - t0 > a.timeout_cycles )
+                {
+                    a.S->xerror = 1;
+                    break;
+                }
+        }
+    }
+    __threadfence_system();
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 inline int grid_for( const cfb_ctx* c, long long cells )
 {
@@ -686,6 +765,23 @@ void mg_free( cfb_ctx* c )
     MgStage* m = c->mg;
     if ( !m )
         return;
+    if ( m->peer )
+    {
+        // close my mappings of the neighbours' arrays; nobody frees before everybody has closed (a collective:
+        // every rank rebuilds / destroys its preconditioner at the same point)
+        cudaStreamSynchronize( c->stream );
+        for ( double* p : m->peer_arrays )
+            if ( p )
+            {
+                cudaIpcCloseMemHandle( p );
+                for ( void*& q : c->ipc_opened )
+                    if ( q == p )
+                        q = nullptr;
+            }
+        c->ipc_opened.erase( std::remove( c->ipc_opened.begin(), c->ipc_opened.end(), nullptr ), c->ipc_opened.end() );
+        halo_allreduce( c, &c->d_state->gath[0], 1 );
+        cudaStreamSynchronize( c->stream );
+    }
     for ( auto& L : m->lv )
     {
         if ( L.owns_b && L.b )
@@ -796,6 +892,20 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega, int max_level
         scale = scale * 0.25;
     }
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    if ( c->cfg.use_nccl && c->peer_ok && c->use_peer )
+    {
+        // level 0: the two x arrays (its right-hand side is cg_r, mapped since start-up); below: b and both x
+        for ( size_t l = 0; l < m->lv.size(); ++l )
+        {
+            if ( l > 0 )
+                m->own_arrays.push_back( m->lv[l].b );
+            m->own_arrays.push_back( m->lv[l].x[0] );
+            m->own_arrays.push_back( m->lv[l].x[1] );
+        }
+        int rc = peer_map_arrays( c, (int)m->own_arrays.size(), m->own_arrays.data(), m->peer_arrays, &m->peer );
+        if ( rc )
+            return rc;
+    }
     m->coarse_start = -1;
     for ( int l = 0; l < (int)m->lv.size(); ++l )
         if ( m->lv[l].cells <= MG_COARSE_CELLS && (int)m->lv.size() - l <= MG_COARSE_LEVELS )
@@ -832,6 +942,47 @@ int mg_exchange( cfb_ctx* c, MgLevelHost& H, double* arr, int* launches )
     }
     if ( pk.nface == 0 )
         return CFB_OK;
+    // Two exchanges in a row on the same array (only V(nu1, 0) cycles with a one-sweep coarsest level do that)
+    // would let a fast rank overwrite ghosts a neighbour is still reading: those go through NCCL, whose
+    // receives are ordered behind the neighbour's own stream.
+    const bool repeat = c->mg->last_xchg == arr;
+    c->mg->last_xchg = arr;
+    if ( c->mg->peer && c->use_peer && !repeat )
+    {
+        MgStage* m = c->mg;
+        // which exported array is this?  (level 0's right-hand side is cg_r: the start-up mapping)
+        int idx = -1;
+        for ( size_t a = 0; a < m->own_arrays.size(); ++a )
+            if ( m->own_arrays[a] == arr )
+                idx = (int)a;
+        if ( idx < 0 && arr != c->cg_r )
+            return cfb_fail( c, CFB_ERR_INVALID, "multigrid exchange of an array that was not exported" );
+        MgXchg x{};
+        int f = 0;
+        for ( int s = 0; s < 6; ++s )
+        {
+            if ( c->nbr[s] < 0 )
+                continue;
+            const int d = s / 2, side = s % 2;
+            x.dim[f] = d;
+            x.src[f] = side == 0 ? 0 : L.n[d] - 1; // my first layer -> the low neighbour's high ghost
+            x.dst[f] = side == 0 ? L.n[d] : -1;    // (index n there), my last -> the high neighbour's low ghost
+            x.peer[f] = idx >= 0 ? m->peer_arrays[(size_t)s * m->own_arrays.size() + idx] : c->peer_r[s];
+            x.tell[f] = &c->mail[c->nbr[s]]->mseq[c->cfg.world_rank];
+            x.hear[f] = &c->mail_self->mseq[c->nbr[s]];
+            ++f;
+        }
+        x.nface = f;
+        x.seq = ++m->xseq;
+        x.ticket = c->d_xticket;
+        x.S = c->d_state;
+        x.timeout_cycles = 20000000000ll;
+        long long gx = ( mx + 4 * NT - 1 ) / ( 4 * NT );
+        const long long gcap = 2ll * c->sm_count;
+        mg_xchg_kernel<<<(int)( gx < 1 ? 1 : ( gx > gcap ? gcap : gx ) ), NT, 0, c->stream>>>( L, x, arr );
+        *launches += 1;
+        return CFB_OK;
+    }
     long long bx = ( mx + NT - 1 ) / NT;
     const long long cap = (long long)c->sm_count * 4;
     dim3 grid( (unsigned)( bx > cap ? cap : bx ), (unsigned)pk.nface );
@@ -1113,6 +1264,8 @@ int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     if ( e != cudaSuccess )
         return cfb_fail( c, CFB_ERR_CUDA, std::string( "mg_pcg_solve: " ) + cudaGetErrorString( e ) );
     c->stats.kernel_launches += launches + nl;
+    if ( c->h_state->xerror )
+        return cfb_fail( c, CFB_ERR_NCCL, "peer-memory exchange timed out: a neighbour never finished its ghost stores" );
     c->last_iters = c->h_state->iter;
     c->last_resid = std::sqrt( c->h_state->rr );
     c->stats.cg_iterations += c->last_iters;

@@ -14,7 +14,11 @@
 //   levels      : cell-centred 2:1 coarsening while every extent stays even and >= 2 after halving;
 //                 level l re-discretises the same 2*D+1-point operator (same wall logic) with
 //                 scale_l = scale_0 / 4^l
-//   smoother    : damped Jacobi  x += omega D^-1 (b - A x)  (first sweep from x = 0: x = omega D^-1 b),
+//   smoother    : damped Jacobi  x += omega D^-1 (b - A x)  (first sweep from x = 0: x = omega D^-1 b), one
+//                 omega per sweep: by default the reciprocals of the Chebyshev nodes of [0.4, 2] in 3-D with
+//                 2..4 sweeps (0.566, 1.577 for V(2,2): 8 / 8 / 9 instead of 11 / 12 / 14 iterations at
+//                 32^3 / 64^3 / 128^3 for nothing), reversed after the coarse correction; 6/7 (3-D, one sweep),
+//                 0.8 (2-D) otherwise,
 //                 ping-pong between two arrays per level
 //   restriction : mean of the 2^D children of the residual (residual fused into the kernel);
 //                 prolongation: piecewise constant, fused with the correction
@@ -34,7 +38,7 @@
 // iteration with V(2,2): both pre-smoothing sweeps in one pass 16, residual + restriction 17, prolongation
 // fused with the first post-smoothing sweep 24, second sweep fused with z.r 24, p-update 24, stencil 16,
 // axpy 48 = 169 (+ 1/7 of the 81 of the cycle for the coarse levels) against 72 for a Jacobi iteration,
-// for ~14 iterations instead of ~2500 at 512^3.
+// for ~10 iterations instead of ~2500 at 512^3.
 #include "cfb_internal.h"
 #include "device_geo.cuh"
 #include "device_reduce.cuh"
@@ -56,7 +60,7 @@ struct MgLevelDev
                         // after an exchange (otherwise ghosts are the zeros the operator reads off the domain)
     long long sy, sz, origin;
     double ns;          // off-diagonal coefficient, -scale_l
-    double diag[8], wminv[8];
+    double diag[8], minv[8]; // by number of SOLID walls touched: diagonal, 1 / diagonal
 };
 
 struct MgLevelHost
@@ -76,7 +80,9 @@ struct MgStage
     std::vector<MgLevelHost> lv;
     int nu1 = 2, nu2 = 2, nuc = 8;
     int max_levels = 0; // 0 = as many as the block allows
-    double omega = 0.0;
+    double omega = 0.0;               // the caller's argument (<= 0: default schedule)
+    std::vector<double> wpre, wpost;  // damping of every pre- / post-smoothing sweep
+    double wc = 0.0;                  // damping on the coarsest level
     bool singular = false;
     cudaEvent_t ev_poll = nullptr;
     // "mg_graph" tuning key (one block only): the ~60 launches of a V-cycle replayed as one CUDA graph.  All
@@ -133,16 +139,16 @@ __device__ __forceinline__ double mg_Ax( const MgLevelDev& L, const double* __re
 
 // ---- the element-wise operations of the cycle, one cell each (shared by the grid-wide kernels below and by
 // the single-CTA kernel that runs the coarse end of the cycle) ------------------------------------------
-__device__ __forceinline__ void cell_smooth0( const MgLevelDev& L, const double* __restrict__ b,
+__device__ __forceinline__ void cell_smooth0( const MgLevelDev& L, double omega, const double* __restrict__ b,
                                               double* __restrict__ x, long long t )
 {
     int i, j, k;
     mg_decode( L, t, i, j, k );
     const long long o = mg_off( L, i, j, k );
-    x[o] = L.wminv[mg_walls( L, i, j, k )] * b[o];
+    x[o] = ( omega * L.minv[mg_walls( L, i, j, k )] ) * b[o];
 }
 
-__device__ __forceinline__ double cell_smooth( const MgLevelDev& L, const double* __restrict__ b,
+__device__ __forceinline__ double cell_smooth( const MgLevelDev& L, double omega, const double* __restrict__ b,
                                                const double* __restrict__ xi, double* __restrict__ xo, long long t,
                                                double* bv_out = nullptr )
 {
@@ -152,7 +158,7 @@ __device__ __forceinline__ double cell_smooth( const MgLevelDev& L, const double
     const int w = mg_walls( L, i, j, k );
     const double bv = b[o];
     const double res = bv - mg_Ax( L, xi, o, w );
-    const double z = fma( L.wminv[w], res, xi[o] );
+    const double z = fma( omega * L.minv[w], res, xi[o] );
     xo[o] = z;
     if ( bv_out )
         *bv_out = bv;
@@ -162,50 +168,52 @@ __device__ __forceinline__ double cell_smooth( const MgLevelDev& L, const double
 // The first TWO sweeps from a zero initial guess in one pass (16 instead of 16 + 24 bytes per cell):
 // x1 = (omega D^-1) b is recomputed for the six neighbours from b itself (neighbours off the block are
 // the ghost zeros the unfused sweep would read), then x2 = x1 + omega D^-1 (b - A x1).
-__device__ __forceinline__ void cell_smooth02( const MgLevelDev& L, const double* __restrict__ b,
-                                               double* __restrict__ xo, long long t )
+__device__ __forceinline__ void cell_smooth02( const MgLevelDev& L, double omega1, double omega2,
+                                               const double* __restrict__ b, double* __restrict__ xo, long long t )
 {
     int i, j, k;
     mg_decode( L, t, i, j, k );
     const long long o = mg_off( L, i, j, k );
     const int w = mg_walls( L, i, j, k );
     const double bc = b[o];
-    const double xc = L.wminv[w] * bc;
+    const double xc = ( omega1 * L.minv[w] ) * bc;
     // a neighbour across a block interface is a ghost entry of b (exchanged by the caller); its wall
     // count is that of an interior cell along the interface normal, which mg_walls returns for -1 / n
-    const double xm = ( i > 0 || L.nlo[0] ) ? L.wminv[mg_walls( L, i - 1, j, k )] * b[o - 1] : 0.0;
-    const double xp = ( i < L.n[0] - 1 || L.nhi[0] ) ? L.wminv[mg_walls( L, i + 1, j, k )] * b[o + 1] : 0.0;
-    const double ym = ( j > 0 || L.nlo[1] ) ? L.wminv[mg_walls( L, i, j - 1, k )] * b[o - L.sy] : 0.0;
-    const double yp = ( j < L.n[1] - 1 || L.nhi[1] ) ? L.wminv[mg_walls( L, i, j + 1, k )] * b[o + L.sy] : 0.0;
-    const double zm = ( k > 0 || L.nlo[2] ) ? L.wminv[mg_walls( L, i, j, k - 1 )] * b[o - L.sz] : 0.0;
-    const double zp = ( k < L.n[2] - 1 || L.nhi[2] ) ? L.wminv[mg_walls( L, i, j, k + 1 )] * b[o + L.sz] : 0.0;
+    const double xm = ( i > 0 || L.nlo[0] ) ? ( omega1 * L.minv[mg_walls( L, i - 1, j, k )] ) * b[o - 1] : 0.0;
+    const double xp = ( i < L.n[0] - 1 || L.nhi[0] ) ? ( omega1 * L.minv[mg_walls( L, i + 1, j, k )] ) * b[o + 1] : 0.0;
+    const double ym = ( j > 0 || L.nlo[1] ) ? ( omega1 * L.minv[mg_walls( L, i, j - 1, k )] ) * b[o - L.sy] : 0.0;
+    const double yp = ( j < L.n[1] - 1 || L.nhi[1] ) ? ( omega1 * L.minv[mg_walls( L, i, j + 1, k )] ) * b[o + L.sy] : 0.0;
+    const double zm = ( k > 0 || L.nlo[2] ) ? ( omega1 * L.minv[mg_walls( L, i, j, k - 1 )] ) * b[o - L.sz] : 0.0;
+    const double zp = ( k < L.n[2] - 1 || L.nhi[2] ) ? ( omega1 * L.minv[mg_walls( L, i, j, k + 1 )] ) * b[o + L.sz] : 0.0;
     const double res = bc - apply_row( L.diag[w], L.ns, xc, xm, xp, ym, yp, zm, zp );
-    xo[o] = fma( L.wminv[w], res, xc );
+    xo[o] = fma( omega2 * L.minv[w], res, xc );
 }
 
 __global__ void __launch_bounds__( NT )
-    mg_smooth0_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b, double* __restrict__ x )
+    mg_smooth0_kernel( const __grid_constant__ MgLevelDev L, double omega, const double* __restrict__ b,
+                       double* __restrict__ x )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-        cell_smooth0( L, b, x, t );
+        cell_smooth0( L, omega, b, x, t );
 }
 
 __global__ void __launch_bounds__( NT )
-    mg_smooth_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b,
+    mg_smooth_kernel( const __grid_constant__ MgLevelDev L, double omega, const double* __restrict__ b,
                       const double* __restrict__ xi, double* __restrict__ xo )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-        cell_smooth( L, b, xi, xo, t );
+        cell_smooth( L, omega, b, xi, xo, t );
 }
 
 __global__ void __launch_bounds__( NT )
-    mg_smooth02_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b, double* __restrict__ xo )
+    mg_smooth02_kernel( const __grid_constant__ MgLevelDev L, double omega1, double omega2,
+                        const double* __restrict__ b, double* __restrict__ xo )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-        cell_smooth02( L, b, xo, t );
+        cell_smooth02( L, omega1, omega2, b, xo, t );
 }
 
 // End of a reduction.  One block: the rounded sum is final.  Several blocks (ranks): keep the local
@@ -226,7 +234,7 @@ __device__ __forceinline__ bool mg_publish( CgState* S, dd_t v, int slot, double
 // One smoothing sweep that also accumulates sum xo . b — on the fine level b is the CG residual r and the
 // last sweep's xo is z, so this is the z.r of CG kernel 2 without another pass over z and r.
 __global__ void __launch_bounds__( NT )
-    mg_smooth_dot_kernel( const __grid_constant__ MgLevelDev L, const double* __restrict__ b,
+    mg_smooth_dot_kernel( const __grid_constant__ MgLevelDev L, double omega, const double* __restrict__ b,
                           const double* __restrict__ xi, double* __restrict__ xo, CgState* S, double* partials )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__( NT )
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
     {
         double bv;
-        const double z = cell_smooth( L, b, xi, xo, t, &bv );
+        const double z = cell_smooth( L, omega, b, xi, xo, t, &bv );
         dd_acc( rz, z * bv );
     }
     dd_t vals[1] = { rz };
@@ -284,7 +292,7 @@ __device__ __forceinline__ void cell_prolong( const MgLevelDev& F, const MgLevel
 // Prolongation + correction + the first post-smoothing sweep in one pass (24 instead of 17 + 24 bytes per
 // cell): x' = x + P e is formed on the fly for the cell and its six neighbours (neighbours off the block:
 // the ghost zeros of x', which the separate prolongation never writes), then xo = x' + omega D^-1 (b - A x').
-__device__ __forceinline__ double cell_prolong_smooth( const MgLevelDev& F, const MgLevelDev& C,
+__device__ __forceinline__ double cell_prolong_smooth( const MgLevelDev& F, const MgLevelDev& C, double omega,
                                                        const double* __restrict__ b, const double* __restrict__ xi,
                                                        const double* __restrict__ ec, double* __restrict__ xo,
                                                        long long t, double* bv_out = nullptr )
@@ -304,7 +312,7 @@ __device__ __forceinline__ double cell_prolong_smooth( const MgLevelDev& F, cons
     const double zp = ( k < F.n[2] - 1 || F.nhi[2] ) ? xi[o + F.sz] + ec[mg_off( C, I, J, mg_parent( k + 1, F.cz ) )] : 0.0;
     const double bv = b[o];
     const double res = bv - apply_row( F.diag[w], F.ns, xc, xm, xp, ym, yp, zm, zp );
-    const double z = fma( F.wminv[w], res, xc );
+    const double z = fma( omega * F.minv[w], res, xc );
     xo[o] = z;
     if ( bv_out )
         *bv_out = bv;
@@ -332,7 +340,7 @@ __global__ void __launch_bounds__( NT )
 // DOT: also sum xo . b (see mg_smooth_dot_kernel), for cycles whose only post-smoothing sweep this is.
 template <bool DOT>
 __global__ void __launch_bounds__( NT )
-    mg_prolong_smooth_kernel( const __grid_constant__ MgLevelDev F, const __grid_constant__ MgLevelDev C,
+    mg_prolong_smooth_kernel( const __grid_constant__ MgLevelDev F, const __grid_constant__ MgLevelDev C, double omega,
                               const double* __restrict__ b, const double* __restrict__ xi,
                               const double* __restrict__ ec, double* __restrict__ xo, CgState* S, double* partials )
 {
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__( NT )
     for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
     {
         double bv;
-        const double z = cell_prolong_smooth( F, C, b, xi, ec, xo, t, &bv );
+        const double z = cell_prolong_smooth( F, C, omega, b, xi, ec, xo, t, &bv );
         if ( DOT )
             dd_acc( rz, z * bv );
     }
@@ -367,6 +375,7 @@ __global__ void __launch_bounds__( NT )
 struct MgCoarseArgs
 {
     int nlev, nu1, nu2, nuc;
+    double wpre[8], wpost[8], wc; // damping per sweep (nu1, nu2 <= 8 here)
     MgLevelDev lv[MG_COARSE_LEVELS];
     double* b[MG_COARSE_LEVELS];
     double* x[MG_COARSE_LEVELS][2];
@@ -382,19 +391,20 @@ __global__ void __launch_bounds__( NT )
     {
         const MgLevelDev& L = a.lv[l];
         const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
-        const int sweeps = l == a.nlev - 1 ? a.nuc : a.nu1;
+        const bool coarsest = l == a.nlev - 1;
+        const int sweeps = coarsest ? a.nuc : a.nu1;
         int c, done;
         if ( sweeps >= 2 )
         {
             for ( long long t = tid; t < total; t += NT )
-                cell_smooth02( L, a.b[l], a.x[l][1], t );
+                cell_smooth02( L, coarsest ? a.wc : a.wpre[0], coarsest ? a.wc : a.wpre[1], a.b[l], a.x[l][1], t );
             c = 1;
             done = 2;
         }
         else
         {
             for ( long long t = tid; t < total; t += NT )
-                cell_smooth0( L, a.b[l], a.x[l][0], t );
+                cell_smooth0( L, coarsest ? a.wc : a.wpre[0], a.b[l], a.x[l][0], t );
             c = 0;
             done = 1;
         }
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__( NT )
         for ( ; done < sweeps; ++done )
         {
             for ( long long t = tid; t < total; t += NT )
-                cell_smooth( L, a.b[l], a.x[l][c], a.x[l][1 - c], t );
+                cell_smooth( L, coarsest ? a.wc : a.wpre[done], a.b[l], a.x[l][c], a.x[l][1 - c], t );
             c = 1 - c;
             __syncthreads();
         }
@@ -433,13 +443,13 @@ __global__ void __launch_bounds__( NT )
             continue;
         }
         for ( long long t = tid; t < total; t += NT )
-            cell_prolong_smooth( L, C, a.b[l], a.x[l][c], ec, a.x[l][1 - c], t );
+            cell_prolong_smooth( L, C, a.wpost[0], a.b[l], a.x[l][c], ec, a.x[l][1 - c], t );
         c = 1 - c;
         __syncthreads();
         for ( int s2 = 1; s2 < a.nu2; ++s2 )
         {
             for ( long long t = tid; t < total; t += NT )
-                cell_smooth( L, a.b[l], a.x[l][c], a.x[l][1 - c], t );
+                cell_smooth( L, a.wpost[s2], a.b[l], a.x[l][c], a.x[l][1 - c], t );
             c = 1 - c;
             __syncthreads();
         }
@@ -812,7 +822,28 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega, int max_level
     m->nuc = nuc;
     const Geo& g = c->g;
     const int D = g.D;
-    m->omega = omega > 0.0 ? omega : ( D == 3 ? 6.0 / 7.0 : 0.8 );
+    m->omega = omega;
+    {
+        // damping per sweep; literals so that every implementation uses the same bits:
+        // 1 / ( 1.2 + 0.8 cos( (2k - 1) pi / (2 nu) ) ), k = 1..nu
+        static const double cheb[5][4] = { { 0, 0, 0, 0 },
+                                           { 0, 0, 0, 0 },
+                                           { 0.5663522991524661, 1.576504843704677, 0, 0 },
+                                           { 0.5283121635129678, 0.8333333333333334, 1.9716878364870327, 0 },
+                                           { 0.515702196925985, 0.6639459287266942, 1.118751870515935, 2.169685110214365 } };
+        const double fixed = omega > 0.0 ? omega : ( D == 3 ? 6.0 / 7.0 : 0.8 );
+        m->wc = fixed;
+        auto fill = [&]( std::vector<double>& w, int nu, bool reverse ) {
+            w.assign( nu > 0 ? nu : 0, fixed );
+            // only for the symmetric cycle (nu1 == nu2): the big per-sweep factors are harmless as a product,
+            // not one by one, and CG needs M symmetric positive definite
+            if ( omega <= 0.0 && D == 3 && nu >= 2 && nu <= 4 && nu1 == nu2 )
+                for ( int q = 0; q < nu; ++q )
+                    w[q] = cheb[nu][reverse ? nu - 1 - q : q];
+        };
+        fill( m->wpre, nu1, false );
+        fill( m->wpost, nu2, true );
+    }
     m->singular = true;
     for ( int d = 0; d < D; ++d )
         m->singular = m->singular && g.bt[d] == CFB_SOLID && g.bt[3 + d] == CFB_SOLID;
@@ -852,7 +883,7 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega, int max_level
                     dgl -= scale;
             }
             L.diag[cnt] = dgl;
-            L.wminv[cnt] = m->omega * ( 1.0 / dgl );
+            L.minv[cnt] = 1.0 / dgl;
         }
         H.cells = (long long)n[0] * n[1] * n[2];
         size_t elems;
@@ -1017,21 +1048,23 @@ int mg_global_sum( cfb_ctx* c, int what, int* launches )
             return _rc;                                                                            \
     } while ( 0 )
 
-// the first `sweeps` (>= 1) smoothing sweeps of a level from a zero initial guess
-int launch_presmooth( cfb_ctx* c, MgLevelHost& H, int sweeps, int* n )
+// the first `sweeps` (>= 1) smoothing sweeps of a level from a zero initial guess; w[s] = damping of sweep s
+// (nullptr: the coarsest level's fixed damping)
+int launch_presmooth( cfb_ctx* c, MgLevelHost& H, int sweeps, const double* w, int* n )
 {
     const int grid = grid_for( c, H.cells );
+    const double wc = c->mg->wc;
     int done;
     if ( sweeps >= 2 )
     {
         MG_TRY( mg_exchange( c, H, H.b, n ) ); // the fused pair reads b of the six neighbours
-        mg_smooth02_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[1] );
+        mg_smooth02_kernel<<<grid, NT, 0, c->stream>>>( H.d, w ? w[0] : wc, w ? w[1] : wc, H.b, H.x[1] );
         H.cur = 1; // where the unfused pair of sweeps leaves its result
         done = 2;
     }
     else
     {
-        mg_smooth0_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[0] );
+        mg_smooth0_kernel<<<grid, NT, 0, c->stream>>>( H.d, w ? w[0] : wc, H.b, H.x[0] );
         H.cur = 0;
         done = 1;
     }
@@ -1039,7 +1072,7 @@ int launch_presmooth( cfb_ctx* c, MgLevelHost& H, int sweeps, int* n )
     for ( ; done < sweeps; ++done )
     {
         MG_TRY( mg_exchange( c, H, H.x[H.cur], n ) );
-        mg_smooth_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur] );
+        mg_smooth_kernel<<<grid, NT, 0, c->stream>>>( H.d, w ? w[done] : wc, H.b, H.x[H.cur], H.x[1 - H.cur] );
         H.cur = 1 - H.cur;
         *n += 1;
     }
@@ -1057,7 +1090,7 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
     const int grid = grid_for( c, H.cells );
     if ( dotted )
         *dotted = false;
-    if ( m->use_coarse && !c->cfg.use_nccl && l == m->coarse_start )
+    if ( m->use_coarse && !c->cfg.use_nccl && l == m->coarse_start && m->nu1 <= 8 && m->nu2 <= 8 )
     {
         // the rest of the cycle, down to the coarsest level and back up to this one, in one single-CTA kernel
         MgCoarseArgs a{};
@@ -1065,6 +1098,11 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
         a.nu1 = m->nu1;
         a.nu2 = m->nu2;
         a.nuc = m->nuc;
+        a.wc = m->wc;
+        for ( int q = 0; q < m->nu1; ++q )
+            a.wpre[q] = m->wpre[q];
+        for ( int q = 0; q < m->nu2; ++q )
+            a.wpost[q] = m->wpost[q];
         for ( int q = 0; q < a.nlev; ++q )
         {
             MgLevelHost& Q = m->lv[l + q];
@@ -1084,7 +1122,7 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
         H.cur = cur;
         return CFB_OK;
     }
-    MG_TRY( launch_presmooth( c, H, last ? m->nuc : m->nu1, n ) );
+    MG_TRY( launch_presmooth( c, H, last ? m->nuc : m->nu1, last ? nullptr : m->wpre.data(), n ) );
     if ( last )
         return CFB_OK;
     MgLevelHost& C = m->lv[l + 1];
@@ -1102,10 +1140,10 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
     MG_TRY( mg_exchange( c, C, C.x[C.cur], n ) );
     const bool dot_here = dot && m->nu2 == 1;
     if ( dot_here )
-        mg_prolong_smooth_kernel<true><<<grid, NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.x[C.cur],
+        mg_prolong_smooth_kernel<true><<<grid, NT, 0, c->stream>>>( H.d, C.d, m->wpost[0], H.b, H.x[H.cur], C.x[C.cur],
                                                                    H.x[1 - H.cur], c->d_state, c->d_partials );
     else
-        mg_prolong_smooth_kernel<false><<<grid, NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.x[C.cur],
+        mg_prolong_smooth_kernel<false><<<grid, NT, 0, c->stream>>>( H.d, C.d, m->wpost[0], H.b, H.x[H.cur], C.x[C.cur],
                                                                     H.x[1 - H.cur], c->d_state, c->d_partials );
     H.cur = 1 - H.cur;
     *n += 1;
@@ -1113,10 +1151,10 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
     {
         MG_TRY( mg_exchange( c, H, H.x[H.cur], n ) );
         if ( dot && s == m->nu2 - 1 )
-            mg_smooth_dot_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur], c->d_state,
+            mg_smooth_dot_kernel<<<grid, NT, 0, c->stream>>>( H.d, m->wpost[s], H.b, H.x[H.cur], H.x[1 - H.cur], c->d_state,
                                                              c->d_partials );
         else
-            mg_smooth_kernel<<<grid, NT, 0, c->stream>>>( H.d, H.b, H.x[H.cur], H.x[1 - H.cur] );
+            mg_smooth_kernel<<<grid, NT, 0, c->stream>>>( H.d, m->wpost[s], H.b, H.x[H.cur], H.x[1 - H.cur] );
         H.cur = 1 - H.cur;
         *n += 1;
     }

@@ -310,8 +310,9 @@ int cfb_set_cg_params( cfb_ctx* ctx, double tolerance, int max_iter, int print_l
 
 /* Choose the CG preconditioner (default CFB_PRECOND_JACOBI == the reference).  CFB_PRECOND_MG: one
  * geometric multigrid V(nu_pre, nu_post) cycle per CG iteration (damped-Jacobi smoother with damping
- * `omega`, <= 0 picks 6/7 in 3-D and 0.8 in 2-D; nu_coarse sweeps on the coarsest level; 2:1 cell-centred
- * coarsening while all extents stay even).  Same matrix, same stopping test, same solution to the
+ * `omega`; <= 0 picks the default: in 3-D with 2..4 sweeps per side one damping per sweep, the reciprocals
+ * of the Chebyshev nodes of [0.4, 2], else 6/7 in 3-D and 0.8 in 2-D; nu_coarse sweeps on the coarsest
+ * level; 2:1 cell-centred coarsening while all extents stay even).  Same matrix, same stopping test, same solution to the
  * solver tolerance, O(10) iterations instead of O(n).  With several blocks the same global cycle runs
  * block-decomposed (one-layer face exchange per operator application; the cells of every dimension must
  * divide evenly among the blocks), so iteration counts and results do not depend on the decomposition. */

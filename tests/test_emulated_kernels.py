@@ -75,6 +75,8 @@ STEP_CASES = [
 
 @pytest.mark.parametrize("dim,cells,kw", STEP_CASES)
 def test_emulated_steps_match_the_oracle_bit_for_bit(emul, dim, cells, kw):
+    if emul.tma and (cells == 32 and kw):
+        pytest.skip("tma runs the default 3-D case and the ragged ones")
     cfg = make_cfg(dim, cells, box=box_of(cells), **kw)
     g, o = Context(emul, cfg), Oracle(cfg)
     steps = 1 if emul.tma else 3

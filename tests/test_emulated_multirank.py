@@ -413,3 +413,36 @@ def test_every_exchange_schedule_of_the_cg_iterations(emul, world, blocks, cells
     want_peer = 1 if peer and tune.get("cg_variant", 1) >= 1 else 0
     for res in run_ranks(emul, cfg, world, body, blocks, peer=peer):
         assert res == (want_peer, io, ro, True), (name, res)
+
+
+def test_decomposed_solve_writes_one_file_set_per_block_and_one_master(emul, tmp_path):
+    """siloWrite on several ranks: every block writes its own arrays, rank 0 the master naming all of them
+    (writeMultiObjects, src/SiloWriter.hpp:292-346); stitched together they are the single-block output."""
+    import json
+    if emul.tma:
+        pytest.skip("output path: nothing TMA-specific")
+    cells = (32, 24, 16)
+    cfg = cfg3(cells=cells)
+    out = str(tmp_path / "data")
+    ora = Oracle(cfg)
+    steps = ora.solve(3 * ora.dt * 0.999, 0)
+    oq, ov, _ = ora.output()
+
+    def body(ctx, rank):
+        ctx.set_output_dir(out)
+        n = ctx.solve(3 * ctx.dt * 0.999, 2)
+        return n, ctx.global_offset(), ctx.owned_extent(K.QUANTITY)
+
+    res = run_ranks(emul, cfg, 4, body, (2, 2, 1))
+    assert [r[0] for r in res] == [steps] * 4
+    m = json.load(open(os.path.join(out, "CajitaFluids%05d.json" % 2)))
+    assert m["cycle"] == 2 and m["global_num_cell"] == list(cells) and len(m["blocks"]) == 4
+    q = np.full(oq.shape, np.nan)
+    v = np.full(ov.shape, np.nan)
+    for blk, (_, off, ext) in zip(m["blocks"], res):
+        assert blk["offset"] == list(off) and blk["extent"] == list(ext)
+        sl = tuple(slice(off[d], off[d] + ext[d]) for d in (2, 1, 0))
+        q[sl] = np.load(os.path.join(out, blk["quantity"]))
+        v[(slice(None),) + sl] = np.load(os.path.join(out, blk["velocity"]))
+    # written after step index 2 = the final state; advected fields agree to rounding across decompositions
+    assert np.abs(q - oq).max() < 1e-12 and np.abs(v - ov).max() < 1e-12

@@ -395,3 +395,15 @@ def test_emulated_multigrid_coarse_end_in_one_kernel(emul, dim, cells, nu):
         n0 = g.stats()["kernel_launches"]
         assert g.pcg_solve() == ro and np.array_equal(g.get(K.PRESSURE), po)
         assert n_coarse < g.stats()["kernel_launches"] - n0
+
+
+def test_emulated_randomized_cases_against_the_oracle(emul):
+    """A short seeded run of tests/emul/fuzz.py (random dimension, ragged sizes, walls, forces, quirks, CG form,
+    preconditioner and its options); `python tests/emul/fuzz.py loops|tma SEED N` runs as many as wanted."""
+    import fuzz
+    bad = []
+    for seed in range(9000, 9002 if emul.tma else 9008):
+        ok, desc = fuzz.one_case(emul, "tma" if emul.tma else "loops", seed)
+        if not ok:
+            bad.append(desc)
+    assert not bad, bad

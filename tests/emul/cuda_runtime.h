@@ -55,6 +55,7 @@ void launch_coop( dim3 grid, dim3 block, const std::function<void()>& body );
 void sync_threads(); // no-op outside launch_coop
 bool coop_active();
 long long clock_ns();
+long long clock_ns_real();
 // "shared memory" of the emulated block: thread-local storage of the rank thread.  Addresses in the
 // shared window are 32-bit offsets from a thread-local anchor (all shared objects of a kernel — the static
 // thread_local arrays that __shared__ turns into and the dynamic buffer — live in one TLS block).
@@ -219,21 +220,30 @@ cudaError_t cudaGraphLaunch( cudaGraphExec_t, cudaStream_t );
 cudaError_t cudaGraphDestroy( cudaGraph_t );
 cudaError_t cudaGraphExecDestroy( cudaGraphExec_t );
 inline cudaError_t cudaStreamWaitEvent( cudaStream_t, cudaEvent_t, unsigned ) { return cudaSuccess; }
+// events carry the host time of their record, so that the library's CUDA-event timers return something
+struct cfb_emul_event
+{
+    long long ns;
+};
 inline cudaError_t cudaEventCreate( cudaEvent_t* e )
 {
-    *e = reinterpret_cast<cudaEvent_t>( std::malloc( 1 ) );
+    *e = new cfb_emul_event{ 0 };
     return cudaSuccess;
 }
 inline cudaError_t cudaEventCreateWithFlags( cudaEvent_t* e, unsigned ) { return cudaEventCreate( e ); }
 inline cudaError_t cudaEventDestroy( cudaEvent_t e )
 {
-    std::free( e );
+    delete e;
     return cudaSuccess;
 }
-inline cudaError_t cudaEventRecord( cudaEvent_t, cudaStream_t ) { return cudaSuccess; }
-inline cudaError_t cudaEventSynchronize( cudaEvent_t ) { return cudaSuccess; }
-inline cudaError_t cudaEventElapsedTime( float* ms, cudaEvent_t, cudaEvent_t )
+inline cudaError_t cudaEventRecord( cudaEvent_t e, cudaStream_t )
 {
-    *ms = 0.0f;
+    e->ns = cfb_emul::clock_ns_real();
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventSynchronize( cudaEvent_t ) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime( float* ms, cudaEvent_t a, cudaEvent_t b )
+{
+    *ms = (float)( ( b->ns - a->ns ) * 1.0e-6 );
     return cudaSuccess;
 }

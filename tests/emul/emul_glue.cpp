@@ -55,6 +55,11 @@ void launch( dim3 grid, dim3 block, const std::function<void()>& body )
             }
 }
 
+long long clock_ns_real()
+{
+    return std::chrono::duration_cast<std::chrono::nanoseconds>( std::chrono::steady_clock::now().time_since_epoch() ).count();
+}
+
 // clock64() of the emulation: only the bounded spins of the peer-memory kernels call it, once per look at a
 // flag another rank thread has to set — so it also gives the processor away (the ranks may outnumber the
 // cores) and it runs 8x slow, which stretches the kernels' ~10 s timeouts to minutes on a loaded machine

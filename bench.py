@@ -426,6 +426,8 @@ def main():
                    "--cells", str(args.cells), "--iters", str(args.iters), "--cg-variant", "2", "--no-cpu-baseline",
                    "--no-e2e", "--no-timestep", "--no-probe"]
             p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+            if p.returncode != 0 or not p.stdout.strip():
+                raise RuntimeError("child exit %d: %s" % (p.returncode, p.stderr.strip()[-200:]))
             child = json.loads(p.stdout.strip().splitlines()[-1])
             extra["cg_variant2"] = {
                 "value": child["value"], "unit": UNIT, "ms_per_step": child["ms_per_step"],

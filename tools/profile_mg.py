@@ -20,7 +20,7 @@ mode = sys.argv[2] if len(sys.argv) > 2 else "solve"
 
 
 def problem(kind, **kw):
-    cfg = default_config(3, n, box=n / 512.0)
+    cfg = default_config(3, n)  # unit box: the default inflow lies inside it at every n
     cfg.cg_max_iter = 20000
     for k, v in kw.items():
         setattr(cfg, k, v)

@@ -964,6 +964,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         if ( c->d_state )
             CFB_CUDA( c, cudaMemsetAsync( &c->d_state->xerror, 0, sizeof( int ), c->stream ) );
     }
+    else if ( k == "flat_2d" )
+        c->flat_2d = value != 0;
     else if ( k == "mg_graph" )
         return mg_set_graph( c, value != 0 );
     else if ( k == "mg_coarse_kernel" )

@@ -132,6 +132,9 @@ struct cfb_ctx
     int st_variant = 0; // 0 = TMA z-march (default)
     int st_tx = 64, st_ty = 16, st_stages = 4, st_zc = 64;
     int poll_every = 0; // 0 = auto
+    // "flat_2d" tuning key: two-dimensional runs skip the loads of the two zero ghost planes in the TMA kernels
+    // (FLAT instantiations); off until it has run on a B200
+    bool flat_2d = false;
 
     // two-kernel CG iteration (kernels_fused.cu): tensor maps of cg_r / cg_p, tiling, unit list
     // 1 = two kernels / 72 B per cell (default), 0 = three kernels / 88 B, 2 = two kernels / 64 B: q is

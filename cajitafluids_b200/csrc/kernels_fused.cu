@@ -209,7 +209,10 @@ struct FusedArgs
     int units_total; // units of all launches that make up one phase B (last-block ticket target)
 };
 
-template <class C, bool XS>
+// FLAT: two-dimensional runs (one owned plane between two zero ghost planes, see Geo): the z neighbours are
+// zero by construction, so the two ghost planes are neither loaded nor recomputed — the 2-D traffic of r and p
+// drops from three planes to the one that exists.  A template flag: the 3-D instantiations are untouched.
+template <class C, bool XS, bool FLAT>
 __global__ void __launch_bounds__( C::NT, C::CTAS )
     cg_fused_kernel( const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_p,
                      const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
@@ -319,9 +322,14 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     __syncthreads();
     if ( tid == 0 )
     {
-        const int n0 = nloads < NS ? nloads : NS;
-        for ( int l = 0; l < n0; ++l )
-            issue( l );
+        if ( FLAT )
+            issue( 1 ); // the one plane there is
+        else
+        {
+            const int n0 = nloads < NS ? nloads : NS;
+            for ( int l = 0; l < n0; ++l )
+                issue( l );
+        }
     }
 
     // per-thread constants: SOLID-wall counts of my cells and of my share of the halo ring
@@ -452,12 +460,21 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     };
 
     // prologue: plane kbeg-1 (z neighbour only), plane kbeg (first owned plane)
-    mbar_wait( smem_u32( &full_bar[0] ), 0 );
-    new_p( 0, zm, false );
+    if ( FLAT )
+    {
+#pragma unroll
+        for ( int r = 0; r < RY; ++r )
+            zm[r] = make_double2( 0.0, 0.0 ); // new p of the ghost plane: fma( beta, 0, minv * 0 )
+    }
+    else
+    {
+        mbar_wait( smem_u32( &full_bar[0] ), 0 );
+        new_p( 0, zm, false );
+    }
     mbar_wait( smem_u32( &full_bar[1 % NS] ), ( 1 / NS ) & 1 );
     new_p( 1, cc, true );
     __syncthreads();
-    if ( tid == 0 )
+    if ( tid == 0 && !FLAT )
     {
         if ( NS < nloads )
             issue( NS );
@@ -469,8 +486,17 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     for ( int it = 0; it < nplanes; ++it )
     {
         const int l = it + 2; // plane k+1
-        mbar_wait( smem_u32( &full_bar[l % NS] ), ( l / NS ) & 1 );
-        new_p( l, zp, l <= nplanes );
+        if ( FLAT )
+        {
+#pragma unroll
+            for ( int r = 0; r < RY; ++r )
+                zp[r] = make_double2( 0.0, 0.0 );
+        }
+        else
+        {
+            mbar_wait( smem_u32( &full_bar[l % NS] ), ( l / NS ) & 1 );
+            new_p( l, zp, l <= nplanes );
+        }
         // q = A p on plane k = kbeg + it: x/y neighbours from the shared new-p plane of load it+1
         const double* PN = pn0 + ( ( it + 1 ) % C::NPN ) * BOXD;
         const int wz = wall_count( g, 2, kbeg + it + g.off[2] );
@@ -509,7 +535,7 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
         }
         qrow += g.sz;
         __syncthreads(); // stage of load l is consumed, new-p plane of load l is complete
-        if ( tid == 0 && l + NS < nloads )
+        if ( tid == 0 && !FLAT && l + NS < nloads )
             issue( l + NS );
     }
 
@@ -567,16 +593,26 @@ int launch_fused_cfg( cfb_ctx* c, const FusedArgs& a, int grid )
     static bool attr_set = false;
     if ( !attr_set )
     {
-        cudaFuncSetAttribute( cg_fused_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
-        cudaFuncSetAttribute( cg_fused_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
         attr_set = true;
     }
-    if ( a.gxr[0] || a.gxr[1] )
-        cg_fused_kernel<C, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur], c->g,
-                                                                            c->op, a );
+    const bool xs = a.gxr[0] || a.gxr[1];
+    const bool flat = c->g.D == 2 && c->flat_2d; // one owned plane between two zero ghost planes
+    if ( xs && flat )
+        cg_fused_kernel<C, true, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+                                                                                  c->g, c->op, a );
+    else if ( xs )
+        cg_fused_kernel<C, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+                                                                                   c->g, c->op, a );
+    else if ( flat )
+        cg_fused_kernel<C, false, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+                                                                                   c->g, c->op, a );
     else
-        cg_fused_kernel<C, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur], c->g,
-                                                                             c->op, a );
+        cg_fused_kernel<C, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+                                                                                    c->g, c->op, a );
     return 1;
 }
 

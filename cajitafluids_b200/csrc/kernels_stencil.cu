@@ -71,7 +71,9 @@ struct StencilArgs
 //         (reads p through TMA and r with 128-bit loads, writes r: 24 B/cell, and phase B no longer writes q).
 //         Statement for statement cg_rupdate_kernel with q recomputed by the same row expression that
 //         produced it, hence bit-identical.
-template <class C, int MODE>
+// FLAT: two-dimensional runs (one owned plane between two zero ghost planes): the z neighbours are zero by
+// construction and their planes are not loaded.  A template flag: the 3-D instantiations are untouched.
+template <class C, int MODE, bool FLAT>
 __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) )
     stencil7_dot_tma( const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geo g,
                       const __grid_constant__ OpConst op, const __grid_constant__ StencilArgs a )
@@ -137,11 +139,11 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     if ( tid == 0 )
     {
         const int n0 = nloads < NS ? nloads : NS;
-        for ( int l = 0; l < n0; ++l )
+        for ( int l = FLAT ? 1 : 0; l < ( FLAT ? 2 : n0 ); ++l )
         {
-            const uint32_t bar = smem_u32( &full_bar[l] );
+            const uint32_t bar = smem_u32( &full_bar[l % NS] );
             mbar_expect_tx( bar, C::BOX_BYTES );
-            tma_load_3d( smem_base + l * C::STAGE_BYTES, &tmap, bar, cx, cy, cz + l );
+            tma_load_3d( smem_base + ( l % NS ) * C::STAGE_BYTES, &tmap, bar, cx, cy, cz + l );
         }
     }
 
@@ -162,13 +164,14 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     const double ns = op.neg_scale;
 
     double2 zm[RY], cc[RY];
-    mbar_wait( smem_u32( &full_bar[0] ), 0 );
+    if ( !FLAT )
+        mbar_wait( smem_u32( &full_bar[0] ), 0 );
     mbar_wait( smem_u32( &full_bar[1 % NS] ), ( 1 / NS ) & 1 );
 #pragma unroll
     for ( int r = 0; r < RY; ++r )
     {
         const int row = wy + r * WY + 1;
-        zm[r] = *reinterpret_cast<const double2*>( stage0 + row * PX + 2 * lx + 2 );
+        zm[r] = FLAT ? make_double2( 0.0, 0.0 ) : *reinterpret_cast<const double2*>( stage0 + row * PX + 2 * lx + 2 );
         cc[r] = *reinterpret_cast<const double2*>( stage0 + ( 1 % NS ) * ( C::STAGE_BYTES / 8 ) + row * PX +
                                                    2 * lx + 2 );
     }
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     // slot 0 (plane kbeg-1) only feeds the zm registers: once every thread has read it, it takes
     // load NS.  From here on slot (it+1) % NS is released at the end of iteration `it`.
     __syncthreads();
-    if ( tid == 0 && NS < nloads )
+    if ( tid == 0 && !FLAT && NS < nloads )
     {
         const uint32_t bar = smem_u32( &full_bar[0] );
         mbar_expect_tx( bar, C::BOX_BYTES );
@@ -211,7 +214,8 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         const int sc = lc % NS, sn = ln % NS;
         if ( MODE == 1 && it + 1 < nplanes )
             load_r( rnxt, qrow + g.sz );
-        mbar_wait( smem_u32( &full_bar[sn] ), ( ln / NS ) & 1 );
+        if ( !FLAT )
+            mbar_wait( smem_u32( &full_bar[sn] ), ( ln / NS ) & 1 );
         const double* P = stage0 + sc * ( C::STAGE_BYTES / 8 );
         const double* N = stage0 + sn * ( C::STAGE_BYTES / 8 );
         const int wz = wall_count( g, 2, kbeg + it + g.off[2] );
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         {
             const int row = wy + r * WY + 1;
             const double* pc = P + row * PX + 2 * lx + 2;
-            const double2 zp = *reinterpret_cast<const double2*>( N + row * PX + 2 * lx + 2 );
+            const double2 zp = FLAT ? make_double2( 0.0, 0.0 ) : *reinterpret_cast<const double2*>( N + row * PX + 2 * lx + 2 );
             const double xl = pc[-1];
             const double xr = pc[2];
             const double2 ym = *reinterpret_cast<const double2*>( pc - PX );
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         }
         qrow += g.sz;
         __syncthreads(); // every thread is done with slot sc -> it can be refilled
-        if ( tid == 0 && lc + NS < nloads )
+        if ( tid == 0 && !FLAT && lc + NS < nloads )
         {
             const uint32_t bar = smem_u32( &full_bar[sc] );
             mbar_expect_tx( bar, C::BOX_BYTES );
@@ -393,10 +397,14 @@ int launch_tma_mode( cfb_ctx* c, const StencilArgs& a, int grid )
     static bool attr_set = false;
     if ( !attr_set )
     {
-        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
         attr_set = true;
     }
-    stencil7_dot_tma<C, MODE><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a );
+    if ( c->g.D == 2 && c->flat_2d )
+        stencil7_dot_tma<C, MODE, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a );
+    else
+        stencil7_dot_tma<C, MODE, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a );
     return 1;
 }
 template <class C>

@@ -302,7 +302,16 @@ int cfb_get_stats( const cfb_ctx* ctx, cfb_stats* out );
 int cfb_reset_stats( cfb_ctx* ctx );
 /* CG residual history of the last solve (sqrt(sum r^2) after each iteration), up to n entries. */
 int cfb_residual_history( const cfb_ctx* ctx, double* hist, int n, int* count );
-/* Choose the stencil kernel variant / tiling (tuning hook; 0 = default). */
+/* Tuning hook (never changes results; unknown keys return CFB_ERR_INVALID).  Keys:
+ *   cg_variant 1|0|2      CG iteration form: two kernels 72 B/cell (default), three kernels 88 B, two kernels 64 B
+ *   stencil_variant, stencil_tx, stencil_ty, stencil_stages, stencil_zc      tiling of the stencil7 + dot kernel
+ *   fused_auto, fused_tx, fused_ty, fused_stages, fused_zc, fused_reverse, rupdate_ctas   tiling of the two-kernel form
+ *   flat_2d 0|1           2-D runs: do not load the two zero ghost planes in the TMA kernels (default 0)
+ *   poll_every n          convergence polling interval in iterations (0 = auto)
+ *   peer_halo 0|1         ghost exchange over NVLink peer memory (default when available) or NCCL send/recv
+ *   overlap_halo, peer_xstage      exchange schedules (see csrc/halo.cu)
+ *   mg_graph, mg_coarse_kernel     multigrid V-cycle as a CUDA graph / coarse levels in one kernel (one block)
+ *   time_kernels 0|1      record CUDA events around each CG kernel (cfb_stats.ms_k_*) */
 int cfb_set_tuning( cfb_ctx* ctx, const char* key, int value );
 /* ReferenceConjugateGradient::setTolerance / setMaxIter / setPrintLevel
  * (src/VelocityCorrector.hpp:103-105) after construction. */

@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > "
 
 # 1. the GPU tests, file by file, so that one failing file does not hide the others
 for f in tests/test_capi.py tests/test_golden.py tests/test_golden_refrun.py tests/test_gpu_parity.py \
-         tests/test_zz_output_stage.py tests/test_zz_multigrid.py; do
+         tests/test_zz_output_stage.py tests/test_zz_multigrid.py tests/test_zz_cpp_layer.py tests/test_zzz_flat2d.py; do
     timeout 900 python -m pytest "$f" -m gpu -q -x > "$O/pytest_$(basename "$f" .py).log" 2>&1
     echo "$f rc=$?" >> "$O/pytest_summary.txt"
 done
@@ -31,6 +31,9 @@ for zc in 16 32 64; do
     timeout 300 python bench.py --steps 3 --warmup 3 --cg-variant 2 --no-cpu-baseline --no-e2e --no-timestep \
         --tune stencil_zc=$zc >> "$O/bench_n1_variant2_sweep.json" 2>> "$O/bench_n1_variant2.err"
 done
+
+# 3c. two-dimensional runs with / without the ghost-plane loads (flat_2d), never measured before round 2
+timeout 300 python tools/profile_2d.py 8192 50 > "$O/flat2d.json" 2> "$O/flat2d.err"
 
 # 4. launch lists (ncu, serialised; shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$O/launches_mg256.csv" \

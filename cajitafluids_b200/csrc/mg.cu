@@ -33,7 +33,7 @@
 //                 sum_i d_i x_i = 0, the component Jacobi-PCG produces (quirk Q1 of the reference leaks
 //                 that constant into v, src/VelocityCorrector.hpp:260)
 //
-// All kernels here are plain one-thread-per-cell streaming kernels (HBM-bound on the fine level,
+// All kernels here are plain one-thread-per-cell streaming kernels (grid-stride walks with MgCursor; HBM-bound on the fine level,
 // launch-bound on the coarse ones); q = A p stays the TMA stencil kernel.  Bytes per fine cell and CG
 // iteration with V(2,2): both pre-smoothing sweeps in one pass 16, residual + restriction 17, prolongation
 // fused with the first post-smoothing sweep 24, second sweep fused with z.r 24, p-update 24, stencil 16,
@@ -120,12 +120,56 @@ __device__ __forceinline__ long long mg_off( const MgLevelDev& L, int i, int j, 
     return L.origin + (long long)k * L.sz + (long long)j * L.sy + i;
 }
 
-__device__ __forceinline__ void mg_decode( const MgLevelDev& L, long long t, int& i, int& j, int& k )
+// v -> (i, j, k) of a level with x extent n0 and y extent n1: two divisions, 32-bit whenever v fits
+__device__ __forceinline__ void mg_split( long long v, int n0, int n1, int& i, int& j, int& k )
 {
-    i = (int)( t % L.n[0] );
-    j = (int)( ( t / L.n[0] ) % L.n[1] );
-    k = (int)( t / ( (long long)L.n[0] * L.n[1] ) );
+    if ( v < 0x7fffffffll )
+    {
+        const unsigned u = (unsigned)v, r = u / (unsigned)n0;
+        i = (int)( u - r * (unsigned)n0 );
+        k = (int)( r / (unsigned)n1 );
+        j = (int)( r - (unsigned)k * (unsigned)n1 );
+    }
+    else
+    {
+        const long long r = v / n0;
+        i = (int)( v - r * n0 );
+        k = (int)( r / n1 );
+        j = (int)( r - (long long)k * n1 );
+    }
 }
+
+// A thread's walk over the cells t = first, first + stride, ... < total of a level (x fastest) with (i, j, k)
+// carried along: the divisions are done once per thread — for the start and, if the thread has a second cell at
+// all, for the stride — and every further cell costs adds and compares.  (A 64-bit division per cell and
+// coordinate is ~100 instructions: more issue slots than the 16-24 bytes of a fine-level cell take from HBM.)
+struct MgCursor
+{
+    long long t, stride;
+    int i, j, k, di, dj, dk, n0, n1;
+    __device__ __forceinline__ MgCursor( const MgLevelDev& L, long long first, long long stride_, long long total )
+        : t( first ), stride( stride_ ), di( 0 ), dj( 0 ), dk( 0 ), n0( L.n[0] ), n1( L.n[1] )
+    {
+        mg_split( first, n0, n1, i, j, k );
+        if ( first + stride_ < total )
+            mg_split( stride_, n0, n1, di, dj, dk );
+    }
+    __device__ __forceinline__ void next()
+    {
+        t += stride;
+        i += di;
+        int c = i >= n0 ? 1 : 0;
+        i -= c ? n0 : 0;
+        j += dj + c;
+        c = j >= n1 ? 1 : 0;
+        j -= c ? n1 : 0;
+        k += dk + c;
+    }
+};
+// all cells of a level, by the threads of the grid / of one CTA
+#define MG_GRID_CELLS( cu, L, total )                                                                              \
+    for ( MgCursor cu( L, blockIdx.x * (long long)NT + threadIdx.x, (long long)gridDim.x * NT, total ); cu.t < total; cu.next() )
+#define MG_CTA_CELLS( cu, L, total ) for ( MgCursor cu( L, tid, NT, total ); cu.t < total; cu.next() )
 
 // coarse index of fine index i (floor division, so that the ghost index -1 maps to the coarse ghost -1)
 __device__ __forceinline__ int mg_parent( int i, int f ) { return f == 1 ? i : ( ( i + 2 ) >> 1 ) - 1; }
@@ -140,20 +184,18 @@ __device__ __forceinline__ double mg_Ax( const MgLevelDev& L, const double* __re
 // ---- the element-wise operations of the cycle, one cell each (shared by the grid-wide kernels below and by
 // the single-CTA kernel that runs the coarse end of the cycle) ------------------------------------------
 __device__ __forceinline__ void cell_smooth0( const MgLevelDev& L, double omega, const double* __restrict__ b,
-                                              double* __restrict__ x, long long t )
+                                              double* __restrict__ x, const MgCursor& cu )
 {
-    int i, j, k;
-    mg_decode( L, t, i, j, k );
+    const int i = cu.i, j = cu.j, k = cu.k;
     const long long o = mg_off( L, i, j, k );
     x[o] = ( omega * L.minv[mg_walls( L, i, j, k )] ) * b[o];
 }
 
 __device__ __forceinline__ double cell_smooth( const MgLevelDev& L, double omega, const double* __restrict__ b,
-                                               const double* __restrict__ xi, double* __restrict__ xo, long long t,
+                                               const double* __restrict__ xi, double* __restrict__ xo, const MgCursor& cu,
                                                double* bv_out = nullptr )
 {
-    int i, j, k;
-    mg_decode( L, t, i, j, k );
+    const int i = cu.i, j = cu.j, k = cu.k;
     const long long o = mg_off( L, i, j, k );
     const int w = mg_walls( L, i, j, k );
     const double bv = b[o];
@@ -169,10 +211,9 @@ __device__ __forceinline__ double cell_smooth( const MgLevelDev& L, double omega
 // x1 = (omega D^-1) b is recomputed for the six neighbours from b itself (neighbours off the block are
 // the ghost zeros the unfused sweep would read), then x2 = x1 + omega D^-1 (b - A x1).
 __device__ __forceinline__ void cell_smooth02( const MgLevelDev& L, double omega1, double omega2,
-                                               const double* __restrict__ b, double* __restrict__ xo, long long t )
+                                               const double* __restrict__ b, double* __restrict__ xo, const MgCursor& cu )
 {
-    int i, j, k;
-    mg_decode( L, t, i, j, k );
+    const int i = cu.i, j = cu.j, k = cu.k;
     const long long o = mg_off( L, i, j, k );
     const int w = mg_walls( L, i, j, k );
     const double bc = b[o];
@@ -194,8 +235,8 @@ __global__ void __launch_bounds__( NT )
                        double* __restrict__ x )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-        cell_smooth0( L, omega, b, x, t );
+    MG_GRID_CELLS( cu, L, total )
+        cell_smooth0( L, omega, b, x, cu );
 }
 
 __global__ void __launch_bounds__( NT )
@@ -203,8 +244,8 @@ __global__ void __launch_bounds__( NT )
                       const double* __restrict__ xi, double* __restrict__ xo )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-        cell_smooth( L, omega, b, xi, xo, t );
+    MG_GRID_CELLS( cu, L, total )
+        cell_smooth( L, omega, b, xi, xo, cu );
 }
 
 __global__ void __launch_bounds__( NT )
@@ -212,8 +253,8 @@ __global__ void __launch_bounds__( NT )
                         const double* __restrict__ b, double* __restrict__ xo )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-        cell_smooth02( L, omega1, omega2, b, xo, t );
+    MG_GRID_CELLS( cu, L, total )
+        cell_smooth02( L, omega1, omega2, b, xo, cu );
 }
 
 // End of a reduction.  One block: the rounded sum is final.  Several blocks (ranks): keep the local
@@ -239,10 +280,10 @@ __global__ void __launch_bounds__( NT )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     dd_t rz = { 0.0, 0.0 };
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    MG_GRID_CELLS( cu, L, total )
     {
         double bv;
-        const double z = cell_smooth( L, omega, b, xi, xo, t, &bv );
+        const double z = cell_smooth( L, omega, b, xi, xo, cu, &bv );
         dd_acc( rz, z * bv );
     }
     dd_t vals[1] = { rz };
@@ -262,10 +303,9 @@ __device__ __forceinline__ double mg_res( const MgLevelDev& F, const double* __r
 
 // coarse b = mean of the children's residuals, summed pairwise: x pairs, then y, then z
 __device__ __forceinline__ void cell_restrict( const MgLevelDev& F, const MgLevelDev& C, const double* __restrict__ bf,
-                                               const double* __restrict__ xf, double* __restrict__ bc, long long t )
+                                               const double* __restrict__ xf, double* __restrict__ bc, const MgCursor& cu )
 {
-    int I, J, K;
-    mg_decode( C, t, I, J, K );
+    const int I = cu.i, J = cu.j, K = cu.k;
     const int i = 2 * I, j = 2 * J, k = F.cz * K;
     double s = ( mg_res( F, bf, xf, i, j, k ) + mg_res( F, bf, xf, i + 1, j, k ) ) +
                ( mg_res( F, bf, xf, i, j + 1, k ) + mg_res( F, bf, xf, i + 1, j + 1, k ) );
@@ -281,10 +321,9 @@ __device__ __forceinline__ void cell_restrict( const MgLevelDev& F, const MgLeve
 }
 
 __device__ __forceinline__ void cell_prolong( const MgLevelDev& F, const MgLevelDev& C, double* __restrict__ xf,
-                                              const double* __restrict__ ec, long long t )
+                                              const double* __restrict__ ec, const MgCursor& cu )
 {
-    int i, j, k;
-    mg_decode( F, t, i, j, k );
+    const int i = cu.i, j = cu.j, k = cu.k;
     const long long o = mg_off( F, i, j, k );
     xf[o] = xf[o] + ec[mg_off( C, i / 2, j / 2, k / F.cz )];
 }
@@ -295,10 +334,9 @@ __device__ __forceinline__ void cell_prolong( const MgLevelDev& F, const MgLevel
 __device__ __forceinline__ double cell_prolong_smooth( const MgLevelDev& F, const MgLevelDev& C, double omega,
                                                        const double* __restrict__ b, const double* __restrict__ xi,
                                                        const double* __restrict__ ec, double* __restrict__ xo,
-                                                       long long t, double* bv_out = nullptr )
+                                                       const MgCursor& cu, double* bv_out = nullptr )
 {
-    int i, j, k;
-    mg_decode( F, t, i, j, k );
+    const int i = cu.i, j = cu.j, k = cu.k;
     const long long o = mg_off( F, i, j, k );
     const int w = mg_walls( F, i, j, k );
     const int I = i / 2, J = j / 2, K = k / F.cz;
@@ -324,8 +362,8 @@ __global__ void __launch_bounds__( NT )
                         const double* __restrict__ bf, const double* __restrict__ xf, double* __restrict__ bc )
 {
     const long long total = (long long)C.n[0] * C.n[1] * C.n[2];
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-        cell_restrict( F, C, bf, xf, bc, t );
+    MG_GRID_CELLS( cu, C, total )
+        cell_restrict( F, C, bf, xf, bc, cu );
 }
 
 __global__ void __launch_bounds__( NT )
@@ -333,8 +371,8 @@ __global__ void __launch_bounds__( NT )
                        double* __restrict__ xf, const double* __restrict__ ec )
 {
     const long long total = (long long)F.n[0] * F.n[1] * F.n[2];
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
-        cell_prolong( F, C, xf, ec, t );
+    MG_GRID_CELLS( cu, F, total )
+        cell_prolong( F, C, xf, ec, cu );
 }
 
 // DOT: also sum xo . b (see mg_smooth_dot_kernel), for cycles whose only post-smoothing sweep this is.
@@ -346,10 +384,10 @@ __global__ void __launch_bounds__( NT )
 {
     const long long total = (long long)F.n[0] * F.n[1] * F.n[2];
     dd_t rz = { 0.0, 0.0 };
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    MG_GRID_CELLS( cu, F, total )
     {
         double bv;
-        const double z = cell_prolong_smooth( F, C, omega, b, xi, ec, xo, t, &bv );
+        const double z = cell_prolong_smooth( F, C, omega, b, xi, ec, xo, cu, &bv );
         if ( DOT )
             dd_acc( rz, z * bv );
     }
@@ -396,23 +434,23 @@ __global__ void __launch_bounds__( NT )
         int c, done;
         if ( sweeps >= 2 )
         {
-            for ( long long t = tid; t < total; t += NT )
-                cell_smooth02( L, coarsest ? a.wc : a.wpre[0], coarsest ? a.wc : a.wpre[1], a.b[l], a.x[l][1], t );
+            MG_CTA_CELLS( cu, L, total )
+                cell_smooth02( L, coarsest ? a.wc : a.wpre[0], coarsest ? a.wc : a.wpre[1], a.b[l], a.x[l][1], cu );
             c = 1;
             done = 2;
         }
         else
         {
-            for ( long long t = tid; t < total; t += NT )
-                cell_smooth0( L, coarsest ? a.wc : a.wpre[0], a.b[l], a.x[l][0], t );
+            MG_CTA_CELLS( cu, L, total )
+                cell_smooth0( L, coarsest ? a.wc : a.wpre[0], a.b[l], a.x[l][0], cu );
             c = 0;
             done = 1;
         }
         __syncthreads();
         for ( ; done < sweeps; ++done )
         {
-            for ( long long t = tid; t < total; t += NT )
-                cell_smooth( L, coarsest ? a.wc : a.wpre[done], a.b[l], a.x[l][c], a.x[l][1 - c], t );
+            MG_CTA_CELLS( cu, L, total )
+                cell_smooth( L, coarsest ? a.wc : a.wpre[done], a.b[l], a.x[l][c], a.x[l][1 - c], cu );
             c = 1 - c;
             __syncthreads();
         }
@@ -422,8 +460,8 @@ __global__ void __launch_bounds__( NT )
         {
             const MgLevelDev& C = a.lv[l + 1];
             const long long ctotal = (long long)C.n[0] * C.n[1] * C.n[2];
-            for ( long long t = tid; t < ctotal; t += NT )
-                cell_restrict( L, C, a.b[l], a.x[l][c], a.b[l + 1], t );
+            MG_CTA_CELLS( cu, C, ctotal )
+                cell_restrict( L, C, a.b[l], a.x[l][c], a.b[l + 1], cu );
         }
         __syncthreads();
     }
@@ -437,19 +475,19 @@ __global__ void __launch_bounds__( NT )
         const double* ec = a.x[l + 1][cur[l + 1]];
         if ( a.nu2 == 0 )
         {
-            for ( long long t = tid; t < total; t += NT )
-                cell_prolong( L, C, a.x[l][c], ec, t );
+            MG_CTA_CELLS( cu, L, total )
+                cell_prolong( L, C, a.x[l][c], ec, cu );
             __syncthreads();
             continue;
         }
-        for ( long long t = tid; t < total; t += NT )
-            cell_prolong_smooth( L, C, a.wpost[0], a.b[l], a.x[l][c], ec, a.x[l][1 - c], t );
+        MG_CTA_CELLS( cu, L, total )
+            cell_prolong_smooth( L, C, a.wpost[0], a.b[l], a.x[l][c], ec, a.x[l][1 - c], cu );
         c = 1 - c;
         __syncthreads();
         for ( int s2 = 1; s2 < a.nu2; ++s2 )
         {
-            for ( long long t = tid; t < total; t += NT )
-                cell_smooth( L, a.wpost[s2], a.b[l], a.x[l][c], a.x[l][1 - c], t );
+            MG_CTA_CELLS( cu, L, total )
+                cell_smooth( L, a.wpost[s2], a.b[l], a.x[l][c], a.x[l][1 - c], cu );
             c = 1 - c;
             __syncthreads();
         }
@@ -467,10 +505,9 @@ __global__ void __launch_bounds__( NT )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     dd_t rr = { 0.0, 0.0 };
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    MG_GRID_CELLS( cu, L, total )
     {
-        int i, j, k;
-        mg_decode( L, t, i, j, k );
+        const int i = cu.i, j = cu.j, k = cu.k;
         const long long o = mg_off( L, i, j, k );
         const double bv = b[o];
         x[o] = 0.0;
@@ -508,10 +545,9 @@ __global__ void __launch_bounds__( NT )
         return;
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     dd_t rz = { 0.0, 0.0 };
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    MG_GRID_CELLS( cu, L, total )
     {
-        int i, j, k;
-        mg_decode( L, t, i, j, k );
+        const int i = cu.i, j = cu.j, k = cu.k;
         const long long o = mg_off( L, i, j, k );
         dd_acc( rz, z[o] * r[o] );
     }
@@ -532,10 +568,9 @@ __global__ void __launch_bounds__( NT )
         return;
     const double beta = first ? 0.0 : S->rz_new / S->rz_old;
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    MG_GRID_CELLS( cu, L, total )
     {
-        int i, j, k;
-        mg_decode( L, t, i, j, k );
+        const int i = cu.i, j = cu.j, k = cu.k;
         const long long o = mg_off( L, i, j, k );
         p[o] = first ? z[o] : fma( beta, p[o], z[o] );
     }
@@ -565,10 +600,9 @@ __global__ void __launch_bounds__( NT )
     const double nalpha = -alpha;
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     dd_t rr = { 0.0, 0.0 };
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    MG_GRID_CELLS( cu, L, total )
     {
-        int i, j, k;
-        mg_decode( L, t, i, j, k );
+        const int i = cu.i, j = cu.j, k = cu.k;
         const long long o = mg_off( L, i, j, k );
         x[o] = fma( alpha, p[o], x[o] );
         const double rv = fma( nalpha, q[o], r[o] );
@@ -590,10 +624,9 @@ __global__ void __launch_bounds__( NT )
 {
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
     dd_t dx = { 0.0, 0.0 }, ds = { 0.0, 0.0 };
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    MG_GRID_CELLS( cu, L, total )
     {
-        int i, j, k;
-        mg_decode( L, t, i, j, k );
+        const int i = cu.i, j = cu.j, k = cu.k;
         const double dg = L.diag[mg_walls( L, i, j, k )];
         dd_acc( dx, dg * x[mg_off( L, i, j, k )] );
         dd_acc( ds, dg );
@@ -614,10 +647,9 @@ __global__ void __launch_bounds__( NT )
 {
     const double shift = S->loc[4] / S->loc[5];
     const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
-    for ( long long t = blockIdx.x * (long long)NT + threadIdx.x; t < total; t += (long long)gridDim.x * NT )
+    MG_GRID_CELLS( cu, L, total )
     {
-        int i, j, k;
-        mg_decode( L, t, i, j, k );
+        const int i = cu.i, j = cu.j, k = cu.k;
         const long long o = mg_off( L, i, j, k );
         x[o] = x[o] - shift;
     }

@@ -40,9 +40,10 @@ def make_cfg(dim, cells, **kw):
     return cfg
 
 
-def smooth_velocity(ctx, rng, amp=1.0):
-    """A smooth, wall-compatible random MAC velocity (owned faces) with |u| <= amp: low-order
-    sin/cos modes with seeded random coefficients.  Returns {field: array[z,y,x]}."""
+def smooth_velocity(ctx, rng, amp=1.0, extent=None):
+    """A smooth random MAC velocity (owned faces) with |u| <= amp: low-order sin/cos modes with seeded random
+    coefficients, wall-compatible (zero normal component on the walls) on the unit box — or on a box with
+    edge lengths `extent` and its low corner at the origin when that is given.  Returns {field: array[z,y,x]}."""
     dim = ctx.dim
     h = ctx.cell_size
     off = ctx.global_offset()
@@ -54,7 +55,7 @@ def smooth_velocity(ctx, rng, amp=1.0):
         coords = []
         for e in range(dim):
             g = np.arange(ext[e]) + off[e]
-            coords.append(g * h if e == d else (g + 0.5) * h)
+            coords.append((g * h if e == d else (g + 0.5) * h) / (1.0 if extent is None else extent[e]))
         grids = np.meshgrid(*coords[::-1], indexing="ij")[::-1]  # x, y, (z) each shaped (z,y,x)/(y,x)
         val = np.zeros(grids[0].shape)
         for _ in range(3):

@@ -966,6 +966,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     }
     else if ( k == "flat_2d" )
         c->flat_2d = value != 0;
+    else if ( k == "advect_tile" )
+        c->advect_tile = value != 0;
     else if ( k == "mg_graph" )
         return mg_set_graph( c, value != 0 );
     else if ( k == "mg_coarse_kernel" )

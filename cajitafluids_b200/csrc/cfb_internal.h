@@ -135,6 +135,8 @@ struct cfb_ctx
     // "flat_2d" tuning key: two-dimensional runs skip the loads of the two zero ghost planes in the TMA kernels
     // (FLAT instantiations); off until it has run on a B200
     bool flat_2d = false;
+    // "advect_tile" tuning key: 32 x 2 x 2 entity tiles per block in the advection kernel instead of rows
+    bool advect_tile = false;
 
     // two-kernel CG iteration (kernels_fused.cu): tensor maps of cg_r / cg_p, tiling, unit list
     // 1 = two kernels / 72 B per cell (default), 0 = three kernels / 88 B, 2 = two kernels / 64 B: q is

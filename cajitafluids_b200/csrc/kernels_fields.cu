@@ -80,7 +80,11 @@ struct AdvectArgs
     double* next[4];
 };
 
-template <int D, int ORDER>
+// TILED ("advect_tile" tuning key, off until measured): a block owns a 32 x 2 x 2 (3-D) / 32 x 4 (2-D) tile of
+// entities instead of 128 consecutive ones of a row, so that the 4^D-point neighbourhoods of its threads overlap
+// in y and z as well as in x (fewer distinct rows pulled from the L2 per output).  Only the thread -> entity map
+// changes: the same values.
+template <int D, int ORDER, bool TILED>
 __global__ void __launch_bounds__( 128 )
     advect_kernel( const __grid_constant__ Geo g, const __grid_constant__ AdvectArgs a, int quirk_v0 )
 {
@@ -88,16 +92,33 @@ __global__ void __launch_bounds__( 128 )
     const int ex = ent == 1 ? g.nf[0] : g.n[0];
     const int ey = ent == 2 ? g.nf[1] : g.n[1];
     const int ez = D == 3 ? ( ent == 3 ? g.nf[2] : g.n[2] ) : 1;
-    const long long total = (long long)ex * ey * ez;
     const double* fc = a.cur[ent];
     double* fn = a.next[ent];
     const double dt = g.dt;
-    for ( long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-          t += (long long)gridDim.x * blockDim.x )
+    constexpr int TY = D == 3 ? 2 : 4, TZ = D == 3 ? 2 : 1;
+    const int nbx = ( ex + 31 ) / 32, nby = ( ey + TY - 1 ) / TY, nbz = ( ez + TZ - 1 ) / TZ;
+    // work items: entities (flat) or tiles; a tiled block handles one tile per round
+    const long long total = TILED ? (long long)nbx * nby * nbz : (long long)ex * ey * ez;
+    for ( long long t = TILED ? (long long)blockIdx.x : blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+          t += TILED ? (long long)gridDim.x : (long long)gridDim.x * blockDim.x )
     {
-        const int i = (int)( t % ex );
-        const int j = (int)( ( t / ex ) % ey );
-        const int k = (int)( t / ( (long long)ex * ey ) );
+        int i, j, k;
+        if ( TILED )
+        {
+            const int bx = (int)( t % nbx ), by = (int)( ( t / nbx ) % nby ), bz = (int)( t / ( (long long)nbx * nby ) );
+            const int tid = threadIdx.x;
+            i = bx * 32 + ( tid & 31 );
+            j = by * TY + ( ( tid >> 5 ) % TY );
+            k = bz * TZ + ( tid >> 5 ) / TY;
+            if ( i >= ex || j >= ey || k >= ez )
+                continue;
+        }
+        else
+        {
+            i = (int)( t % ex );
+            j = (int)( ( t / ex ) % ey );
+            k = (int)( t / ( (long long)ex * ey ) );
+        }
         const int idx[3] = { i, j, k };
         double x0[3], v0[3], x1[3], v1[3], x2[3], v2[3], trace[3];
         // 1. location of the entity            src/TimeIntegrator.hpp:105
@@ -273,17 +294,34 @@ int launch_advect( cfb_ctx* c )
         a.next[e] = field_ptr( c, e, CFB_NEXT );
     }
     long long total = (long long)( g.n[0] + 1 ) * ( g.n[1] + 1 ) * ( g.D == 3 ? g.n[2] + 1 : 1 );
-    dim3 grid( grid_for( total, 128, c->sm_count ), g.D + 1 );
     const int qv0 = c->cfg.quirk_rk3_stage3_v0;
     const int order = c->cfg.field_interp_order;
+    if ( c->advect_tile )
+    {
+        // one block per 128-entity tile (the largest entity extents: faces)
+        const long long tiles = (long long)( ( g.n[0] + 1 + 31 ) / 32 ) * ( ( g.n[1] + 1 + ( g.D == 3 ? 1 : 3 ) ) / ( g.D == 3 ? 2 : 4 ) ) *
+                                ( g.D == 3 ? ( g.n[2] + 1 + 1 ) / 2 : 1 );
+        const long long cap = (long long)c->sm_count * 64;
+        dim3 grid( (unsigned)( tiles < cap ? tiles : cap ), g.D + 1 );
+        if ( g.D == 2 && order == 1 )
+            advect_kernel<2, 1, true><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
+        else if ( g.D == 2 )
+            advect_kernel<2, 3, true><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
+        else if ( order == 1 )
+            advect_kernel<3, 1, true><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
+        else
+            advect_kernel<3, 3, true><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
+        return 1;
+    }
+    dim3 grid( grid_for( total, 128, c->sm_count ), g.D + 1 );
     if ( g.D == 2 && order == 1 )
-        advect_kernel<2, 1><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
+        advect_kernel<2, 1, false><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
     else if ( g.D == 2 )
-        advect_kernel<2, 3><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
+        advect_kernel<2, 3, false><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
     else if ( order == 1 )
-        advect_kernel<3, 1><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
+        advect_kernel<3, 1, false><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
     else
-        advect_kernel<3, 3><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
+        advect_kernel<3, 3, false><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
     return 1;
 }
 

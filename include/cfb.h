@@ -307,6 +307,7 @@ int cfb_residual_history( const cfb_ctx* ctx, double* hist, int n, int* count );
  *   stencil_variant, stencil_tx, stencil_ty, stencil_stages, stencil_zc      tiling of the stencil7 + dot kernel
  *   fused_auto, fused_tx, fused_ty, fused_stages, fused_zc, fused_reverse, rupdate_ctas   tiling of the two-kernel form
  *   flat_2d 0|1           2-D runs: do not load the two zero ghost planes in the TMA kernels (default 0)
+ *   advect_tile 0|1       advection kernel: 32 x 2 x 2 entity tiles per block instead of rows (default 0)
  *   poll_every n          convergence polling interval in iterations (0 = auto)
  *   peer_halo 0|1         ghost exchange over NVLink peer memory (default when available) or NCCL send/recv
  *   overlap_halo, peer_xstage      exchange schedules (see csrc/halo.cu)

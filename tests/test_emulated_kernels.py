@@ -432,3 +432,18 @@ def test_emulated_two_dimensional_runs_without_the_ghost_plane_loads(emul, cells
     g2.set_tuning("flat_2d", 1)
     assert run(g2, 1) == run(o2, 1)
     same_state(g2, o2, 2)
+
+
+@pytest.mark.parametrize("dim,cells,kw", [(2, (37, 23), {}), (2, 24, dict(interp_order=1)), (3, (33, 14, 11), {}),
+                                          (3, (20, 14, 11), dict(interp_order=1)),
+                                          (3, 32, dict(boundary_type=[K.SOLID, K.FREE, K.SOLID, K.SOLID, K.SOLID, K.FREE]))])
+def test_emulated_advection_in_entity_tiles(emul, dim, cells, kw):
+    """"advect_tile": a block of the advection kernel owns a 32 x 2 x 2 (32 x 4 in 2-D) tile of entities instead of
+    128 consecutive ones; only the thread -> entity map changes, ragged edges included."""
+    if emul.tma:
+        pytest.skip("no TMA kernel involved")
+    cfg = make_cfg(dim, cells, box=box_of(cells), **kw)
+    g, o = Context(emul, cfg), Oracle(cfg)
+    g.set_tuning("advect_tile", 1)
+    assert run(g, 2) == run(o, 2)
+    same_state(g, o, dim, ghosts=True)

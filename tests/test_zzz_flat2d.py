@@ -51,3 +51,22 @@ def test_cuda_two_dimensional_steps_without_the_ghost_plane_loads():
     for f in fields_of(2) + [K.PRESSURE]:
         assert np.array_equal(g.get(f), o.get(f)), f
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,cells,kw", [(2, (150, 90), {}), (3, (70, 33, 21), {}), (3, 48, dict(interp_order=1))])
+def test_cuda_advection_in_entity_tiles(dim, cells, kw):
+    """"advect_tile" tuning key (32 x 2 x 2 entity tiles per block in the advection kernel): the same values."""
+    from cajitafluids_b200 import Solver
+    box = 1.0 if isinstance(cells, int) else box_of(cells)
+    cfg = make_cfg(dim, cells, box=box, **kw)
+    g, o = Solver(cfg), Oracle(cfg)
+    g.set_tuning("advect_tile", 1)
+    for s in (g, o):
+        s.setup()
+        for _ in range(3):
+            s.step()
+    assert g.stats()["cg_iterations"] == o.stats()["cg_iterations"]
+    for f in fields_of(dim) + [K.PRESSURE]:
+        assert np.array_equal(g.get(f), o.get(f)), f
+    g.close()

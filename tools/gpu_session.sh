@@ -35,6 +35,9 @@ done
 # 3c. two-dimensional runs with / without the ghost-plane loads (flat_2d), never measured before round 2
 timeout 300 python tools/profile_2d.py 8192 50 > "$O/flat2d.json" 2> "$O/flat2d.err"
 
+# 3d. advection kernel, rows vs entity tiles (advect_tile), never measured before round 2
+timeout 300 python tools/profile_advect.py 512 3 > "$O/advect_tile.json" 2> "$O/advect_tile.err"
+
 # 4. launch lists (ncu, serialised; shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$O/launches_mg256.csv" \
     python tools/profile_mg.py 256 cycle > "$O/ncu_mg.log" 2>&1

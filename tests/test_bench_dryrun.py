@@ -69,6 +69,10 @@ def test_bench_line_carries_the_contract_keys():
     # would not see the emulation shim); the same entry point is run here directly
     assert "projection_time_to_solution" not in x
     x.update(run_bench(["--side", "mg", "--cells", "32", "--timestep-cells", "32"]))
+    x.update(run_bench(["--side", "probes", "--cells", "32"]))
+    assert x["advect_tile_probe"]["tile0_ms"] > 0 and x["advect_tile_probe"]["tile1_ms"] > 0
+    fl = x["flat_2d_probe"]
+    assert fl["flat0_variant1"]["residual"] == fl["flat1_variant1"]["residual"] == fl["flat1_variant2"]["residual"]
     tts = x["projection_time_to_solution"]
     for kind in ("jacobi", "mg", "mg_graph", "mg_graph_coarse"):
         assert "cg_iterations" in tts[kind], tts[kind]

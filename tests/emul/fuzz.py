@@ -5,6 +5,7 @@
 Every case draws dimension, (ragged or power-of-two) cell counts, wall types, body force, interpolation order,
 quirk switches, fixed / converged solves, the CG form (three kernels / two kernels / 64-byte), the preconditioner
 (Jacobi, multigrid with random sweep counts, with and without the single-CTA coarse kernel and the graph replay),
+the flat_2d and advect_tile options,
 seeded fields, then runs setup + one step on both sides and compares every field, the iteration count, the output
 stage — and the error code if a solve does not converge.
 """
@@ -49,6 +50,12 @@ def one_case(lib, which, seed):
     cfg = make_cfg(dim, cells, box=box, **kw)
     g, o = Context(lib, cfg), Oracle(cfg)
     g.set_tuning("cg_variant", variant)
+    # later options draw from their own stream, so that the cases of earlier runs stay what they were
+    rng2 = np.random.default_rng(seed + 1000003)
+    flat, tile = int(rng2.integers(2)), int(rng2.integers(2))
+    g.set_tuning("flat_2d", flat)
+    g.set_tuning("advect_tile", tile)
+    desc += f" flat_2d={flat} advect_tile={tile}"
     if prec == "mg":
         om = 0.0 if nu[0] == nu[1] else 0.7  # unsymmetric cycles: a damping that keeps CG going
         g.set_preconditioner("mg", *nu, om)

@@ -1,0 +1,64 @@
+"""Size-independent properties at the benchmark's full size (512^3, BASELINE.json's metric configuration): the
+oracle does not finish there in seconds, so the checks are the ones the domain offers — an eigenvector of the
+7-point operator, its constant null space, the CG recurrence residual against the true residual b - A x, and the
+three CG forms (88 / 72 / 64 B per cell: src/VelocityCorrector.hpp:124-143 + Cajita's ReferenceConjugateGradient)
+agreeing bit for bit with one another.  (Sorts last: ~15 GB of device memory, a few GB of host arrays.)"""
+import os
+
+import numpy as np
+import pytest
+
+from cajitafluids_b200 import config as K
+from helpers import make_cfg, rel_l2
+
+N = int(os.environ.get("CFB_FULL_N", "512"))
+
+
+@pytest.mark.gpu
+def test_operator_and_cg_properties_at_full_size():
+    from cajitafluids_b200 import Solver
+    n = N
+    cfg = make_cfg(3, n, fixed_iters=40)
+    gpu = Solver(cfg)
+    ax = np.cos(np.pi * 2 * (np.arange(n) + 0.5) / n)
+    p = ax[:, None, None] * ax[None, :, None] * ax[None, None, :]
+    gpu.set(K.CG_P, p)
+    gpu.stencil_dot(1)
+    h, dt, _ = gpu.scalars()
+    lam = dt / (cfg.density * h * h) * 3 * (2 - 2 * np.cos(np.pi * 2 / n))
+    assert rel_l2(gpu.get(K.CG_Q), lam * p) < 1e-12
+    p.fill(1.0)
+    gpu.set(K.CG_P, p)
+    gpu.stencil_dot(1)
+    assert np.abs(gpu.get(K.CG_Q)).max() < 1e-9 * dt / (cfg.density * h * h)
+    del p
+    gpu.fill_synthetic_velocity(0)
+    gpu.build_rhs()
+    b = gpu.get(K.RHS)
+    it, res = gpu.pcg_solve()
+    assert it == 40
+    gpu.set(K.CG_P, gpu.get(K.PRESSURE))
+    gpu.stencil_dot(1)
+    true_r = b - gpu.get(K.CG_Q)
+    assert abs(np.linalg.norm(true_r.ravel()) - res) <= 1e-9 * np.linalg.norm(b.ravel())
+    gpu.close()
+
+
+@pytest.mark.gpu
+def test_the_three_cg_forms_agree_bit_for_bit_at_full_size():
+    from cajitafluids_b200 import Solver
+    gpu = Solver(make_cfg(3, N, fixed_iters=30))
+    gpu.fill_synthetic_velocity(0)
+    gpu.build_rhs()
+    ref = None
+    for variant in (1, 0, 2):
+        gpu.set_tuning("cg_variant", variant)
+        it, res = gpu.pcg_solve()
+        x, hist = gpu.get(K.PRESSURE), gpu.residual_history()
+        assert it == 30 and len(hist) == 30
+        if ref is None:
+            ref = (res, x, hist)
+        else:
+            assert res == ref[0] and np.array_equal(hist, ref[2]), variant
+            assert np.array_equal(x, ref[1]), variant
+    gpu.close()

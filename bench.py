@@ -476,11 +476,18 @@ def main():
 
     # e2e: the solver plug-in call with HOST vectors (pinned), H2D of b and D2H of x inside the timed region
     e2e = None
+    rhs_norm = None
     if not args.no_e2e:
         shp = s.shape(K.RHS)
         b_host = torch.empty(shp, dtype=torch.float64).pin_memory().numpy()
         x_host = torch.empty(shp, dtype=torch.float64).pin_memory().numpy()
         b_host[...] = s.get(K.RHS)
+        bsq = float(np.vdot(b_host.ravel(), b_host.ravel()))  # |b|^2 of this block (report |b| and the final |r|)
+        if dist is not None:
+            t = torch.tensor([bsq], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            bsq = float(t[0])
+        rhs_norm = bsq ** 0.5
         s.pcg_solve_host(b_host, x_host)  # warm
         barrier()
         t0 = time.perf_counter()
@@ -499,7 +506,7 @@ def main():
         del b_host, x_host
 
     # extra: whole timesteps (advect + inputs + projection) of the default inflow problem, 1 GPU only
-    extra = {"final_residual": resid, "wall_s_timed_region": wall, "cells_local": ncell_local,
+    extra = {"final_residual": resid, "rhs_norm": rhs_norm, "wall_s_timed_region": wall, "cells_local": ncell_local,
              "global_iterations_per_s": global_its,
              "value_unit": "CG iterations of one %d^3 block per second, summed over ranks" % args.cells}
     # whole timesteps (advect + inputs + projection) on the bench grid itself, at every N: the

@@ -288,7 +288,7 @@ int launch_advect( cfb_ctx* c )
 {
     const Geo& g = c->g;
     AdvectArgs a{};
-    for ( int e = 0; e <= g.D; ++e )
+    for ( int e = 0; e <= g.D && e < 4; ++e ) // (D <= 3; the second bound is for the compiler's range analysis)
     {
         a.cur[e] = field_ptr( c, e, CFB_CURRENT );
         a.next[e] = field_ptr( c, e, CFB_NEXT );

@@ -33,14 +33,6 @@ namespace
 
 constexpr int NT = 256;
 
-__device__ __forceinline__ void pair_decode( const Geo& g, unsigned t, unsigned npx, int& i, int& j, int& k )
-{
-    unsigned row = t / npx;
-    i = 2 * (int)( t - row * npx );
-    k = (int)( row / (unsigned)g.n[1] );
-    j = (int)( row - (unsigned)k * (unsigned)g.n[1] );
-}
-
 __device__ __forceinline__ bool cg_converged( const CgState* S )
 {
     return !S->fixed && sqrt( S->rr ) <= S->thresh;
@@ -643,15 +635,6 @@ int dispatch_fused( cfb_ctx* c, const FusedArgs& a, int grid )
         cfb_fail( c, CFB_ERR_INVALID, "unsupported fused tile configuration" );
         return 0;
     }
-}
-
-inline int stream_grid( const cfb_ctx* c, long long pairs )
-{
-    long long b = ( pairs + NT - 1 ) / NT;
-    long long cap = (long long)c->sm_count * 8;
-    if ( cap > CFB_MAX_PARTIALS )
-        cap = CFB_MAX_PARTIALS;
-    return (int)( b < 1 ? 1 : ( b > cap ? cap : b ) );
 }
 
 } // namespace

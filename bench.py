@@ -552,6 +552,35 @@ def main():
                                     "interp_order": 3}
         s2.close()
 
+    # extra: BASELINE.json configs[2] — 256^3 PCG-only, fixed 200 iterations, synthetic divergence right-hand side,
+    # HBM GB/s against the roofline (same kernels and CG form as the headline; one vector = 134 MB ~ the L2 size)
+    if world == 1 and not args.no_timestep:
+        try:
+            from cajitafluids_b200 import default_config
+            n2 = max(16, args.cells // 2)
+            c5 = default_config(3, n2, box=n2 / 512.0)
+            c5.cg_fixed_iters = 200
+            c5.cg_print_level = 0
+            s5 = Solver(c5)
+            s5.set_tuning("cg_variant", args.cg_variant)
+            s5.fill_synthetic_velocity(0)
+            s5.build_rhs()
+            for _ in range(3):
+                s5.pcg_fixed(200)
+            ms5 = 0.0
+            for _ in range(3):
+                m, r5 = s5.pcg_fixed(200)
+                ms5 += m
+            gbs5 = n2 ** 3 * BYTES_ITER[args.cg_variant] * 600 / (ms5 * 1e-3) / 1e9
+            extra["config2_pcg_only"] = {"cells": [n2] * 3, "cg_iters_per_step": 200, "steps": 3,
+                                         "iterations_per_s": 600 / (ms5 * 1e-3), "achieved_gbs": gbs5,
+                                         "frac_of_peak": gbs5 / peak, "bytes_per_cell": BYTES_ITER[args.cg_variant],
+                                         "final_residual": r5,
+                                         "note": "at 256^3 a vector (134 MB) is about the size of the L2: not an HBM-only number"}
+            s5.close()
+        except Exception as e:  # noqa: BLE001
+            extra["config2_pcg_only"] = {"error": repr(e)[:300]}
+
     # extra: the same workload with the 64-byte CG form (cg_variant 2: q never stored), measured in a CHILD
     # process — it was written after the round's GPU budget was spent and is not the default yet; a failure
     # there cannot touch this process.  Same fixed iteration count, so its final residual must equal ours bit for bit.

@@ -65,6 +65,8 @@ def test_bench_line_carries_the_contract_keys():
     assert d["gpu_launches"] > 0
     x = d["extra"]
     assert x["cells_local"] == 32 ** 3 and "timesteps_per_s_bench_grid" in x and x["timesteps_per_s"]["cells"] == [32, 32, 32]
+    assert x["config2_pcg_only"]["cells"] == [16, 16, 16] and x["config2_pcg_only"]["iterations_per_s"] > 0
+    assert x["rhs_norm"] > 0
     # the multigrid side measurements run in a child process of the real bench (skipped by --no-probe: a child
     # would not see the emulation shim); the same entry point is run here directly
     assert "projection_time_to_solution" not in x

@@ -530,7 +530,8 @@ def main():
         extra["timesteps_per_s_bench_grid"] = {
             "global_cells": list(gcells), "value": nst / dt_steps, "cg_iters_per_step": args.iters,
             "interp_order": 3, "ms_advect": st2["ms_advect"] / (nst + 1), "note": "projection capped at the "
-            "headline's fixed CG iteration count; wall clock between barriers, max over ranks"}
+            "headline's fixed CG iteration count; wall clock between barriers, max over ranks; inflow source on, "
+            "body-force term applied with g = 0 (the default problem; same kernel work as BASELINE configs[4])"}
     if world == 1 and args.timestep_cells > 0:
         s.close()
         from cajitafluids_b200 import default_config

@@ -43,4 +43,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python tools/profile_mg.py 256 cycle > "$O/ncu_mg.log" 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mg_smooth_kernel|mg_restrict|mg_prolong|output_extract" \
     -c 8 -o "$O/mg_full" python tools/profile_mg.py 256 cycle >> "$O/ncu_mg.log" 2>&1
+# 5. the 64-byte iteration under ncu: launch list, then the full set for its two kernels
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file "$O/launches_variant2_512.csv" \
+    python tools/profile_target.py 512 20 2 > "$O/ncu_variant2.log" 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"stencil7_dot_tma|cg_fused_kernel" -s 4 -c 6 \
+    -o "$O/variant2_full" python tools/profile_target.py 512 6 2 >> "$O/ncu_variant2.log" 2>&1
 ls -la "$O" > "$O/listing.txt"

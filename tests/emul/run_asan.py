@@ -50,6 +50,7 @@ def workload(lib_path):
         box = 1.0 if isinstance(cells, int) else tuple(c / cells[0] for c in cells)
         g = Context(lib, make_cfg(dim, cells, box=box))
         g.set_preconditioner(prec)
+        g.set_tuning("advect_tile", 1 if prec == "jacobi" else 0)  # entity tiles: ragged edges of the tile grid
         run(g, 2)
         g.output()
         if prec == "mg":

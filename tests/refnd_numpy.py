@@ -232,6 +232,12 @@ class RefND:
         self.correct_velocity()
         self.time += self.dt
 
+    def output(self):
+        """what SiloWriter hands to Silo (src/SiloWriter.hpp:136-197): the owned quantity and the velocity interpolated
+        (order 1) to the cell centres, as [(k,) j, i] arrays"""
+        x = [np.broadcast_to(c, self.n) for c in self.coords(None, self.own_grid(None))]
+        return self.owned("q"), [np.ascontiguousarray(self.sample(d, self.vel[d], x, 1).T) for d in range(self.D)]
+
     def owned(self, name):
         """owned entities as [(k,) j, i] like the C ABI's dense host arrays"""
         ent = {"q": None, "u": 0, "v": 1, "w": 2, "p": None}[name]

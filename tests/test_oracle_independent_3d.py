@@ -94,3 +94,23 @@ def test_3d_matrix_apply_against_assembled_sparse_matrix():
     o.stencil_dot(1)
     want = (m.A @ p.T.ravel()).reshape(cells).T     # the model is [i, j, k]
     assert rel_l2(o.get(K.CG_Q), want) < 1e-14
+
+
+def test_3d_output_stage_against_the_model():
+    """src/SiloWriter.hpp:136-197 extended to 3-D: owned quantity + velocity interpolated to the cell centres."""
+    cells = (32, 24, 16)
+    o = Oracle(make_cfg(3, cells, box=tuple(c / cells[0] for c in cells)))
+    m = RefND(cells, quirk_q1=False)
+    o.setup()
+    m.setup()
+    for _ in range(2):
+        o.step()
+        m.step()
+    q, vel, nodes = o.output()
+    mq, mvel = m.output()
+    assert rel_l2(q, mq) < 1e-9
+    vel = np.asarray(vel).reshape((3,) + cells[::-1])
+    for d in range(3):
+        assert rel_l2(vel[d], mvel[d]) < 1e-9, d
+    for d in range(3):
+        assert np.allclose(nodes[d], np.arange(cells[d] + 1) / cells[0], rtol=0, atol=1e-15)

@@ -168,7 +168,9 @@ int enqueue_iteration( cfb_ctx* c )
             cudaEventRecord( e[1], c->stream );
             cudaEventRecord( e[2], c->stream );
         }
-        if ( peer )
+        if ( peer && c->peer_fused )
+            n += launch_cg_fused_peer( c ); // the same, exchange inside the kernel
+        else if ( peer )
         {
             n += launch_cg_fused( c, 0 );
             peer_exchange( c, 0, false, c->pcur ^ 1, !peer_xstaged( c ) ); // new p faces, pAp -> all
@@ -968,6 +970,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->flat_2d = value != 0;
     else if ( k == "advect_tile" )
         c->advect_tile = value != 0;
+    else if ( k == "peer_fused" )
+        c->peer_fused = value != 0;
     else if ( k == "mg_graph" )
         return mg_set_graph( c, value != 0 );
     else if ( k == "mg_coarse_kernel" )

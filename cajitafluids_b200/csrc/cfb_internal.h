@@ -137,6 +137,9 @@ struct cfb_ctx
     bool flat_2d = false;
     // "advect_tile" tuning key: 32 x 2 x 2 entity tiles per block in the advection kernel instead of rows
     bool advect_tile = false;
+    // "peer_fused" tuning key (several blocks, NVLink peer memory): phase B stores its block-face cells into the
+    // neighbours' ghost layers itself and its last block runs the mailbox exchange — no exchange kernel after it
+    bool peer_fused = false;
 
     // two-kernel CG iteration (kernels_fused.cu): tensor maps of cg_r / cg_p, tiling, unit list
     // 1 = two kernels / 72 B per cell (default), 0 = three kernels / 88 B, 2 = two kernels / 64 B: q is
@@ -284,6 +287,7 @@ int launch_stencil_rupdate( cfb_ctx* c );     // cg_variant 2, phase A': r -= al
 int fused_setup( cfb_ctx* c );                // tensor maps of cg_r, cg_p + the unit list
 int launch_cg_rupdate( cfb_ctx* c );          // phase A: r -= alpha q, sum r^2, sum r.Minv r
 int launch_cg_fused( cfb_ctx* c, int which ); // phase B: 0 = all units, 1 = interior, 2 = boundary
+int launch_cg_fused_peer( cfb_ctx* c );        // phase B + its ghost / reduction exchange in one kernel (peer_fused)
 int launch_cg_finish( cfb_ctx* c );
 // output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
 int output_write( cfb_ctx* c, const char* dir, int time_step );

@@ -201,14 +201,70 @@ struct FusedArgs
     int units_total; // units of all launches that make up one phase B (last-block ticket target)
 };
 
+// ---- phase B with the ghost exchange and the reduction exchange inside ("peer_fused" tuning key) -----------
+// Several blocks over NVLink peer memory.  Instead of phase B followed by the exchange kernel (halo.cu:
+// cg_xchg_kernel), the boundary tiles store the cells of the new search direction that lie on a block face
+// straight into the neighbour's ghost layer as they are computed — the transfer overlaps the z-march tile by
+// tile — and the block that draws the last ticket (the one that already closes the p.Ap reduction) publishes
+// the local double-double into every rank's mailbox, waits for everybody's and combines them: steps 3-5 of the
+// exchange kernel, same mailboxes, same sequence numbers, hence the same barrier semantics (a rank leaves phase
+// B only when every rank's ghost stores of this phase are done; p is double-buffered, so nobody still reads the
+// ghost layers written here).  One launch less per iteration.
+struct PeerFace
+{
+    double* dst;                 // the neighbour's copy of the array the new p is written to
+    long long dorigin, dsy, dsz; // its layout
+    int lo[3], ext[3], shift[3]; // my box (owned index space); peer index = my index - shift
+};
+
+struct PeerFusedArgs
+{
+    int nface;
+    PeerFace f[6];
+    PeerMail* mail[CFB_MAX_PEERS];
+    int rank, world;
+    long long timeout_cycles;
+};
+
+struct NoPeerArgs
+{
+};
+
+template <bool PF>
+struct PeerSel
+{
+    typedef NoPeerArgs type;
+};
+template <>
+struct PeerSel<true>
+{
+    typedef PeerFusedArgs type;
+};
+
+__device__ __forceinline__ void peer_store_cell( const PeerFusedArgs& pf, unsigned fmask, int i, int j, int k, double v )
+{
+#pragma unroll
+    for ( int f = 0; f < 6; ++f )
+    {
+        if ( !( ( fmask >> f ) & 1u ) )
+            continue;
+        const PeerFace& F = pf.f[f];
+        if ( i >= F.lo[0] && i < F.lo[0] + F.ext[0] && j >= F.lo[1] && j < F.lo[1] + F.ext[1] && k >= F.lo[2] &&
+             k < F.lo[2] + F.ext[2] )
+            F.dst[F.dorigin + (long long)( k - F.shift[2] ) * F.dsz + (long long)( j - F.shift[1] ) * F.dsy +
+                  ( i - F.shift[0] )] = v;
+    }
+}
+
 // FLAT: two-dimensional runs (one owned plane between two zero ghost planes, see Geo): the z neighbours are
 // zero by construction, so the two ghost planes are neither loaded nor recomputed — the 2-D traffic of r and p
 // drops from three planes to the one that exists.  A template flag: the 3-D instantiations are untouched.
-template <class C, bool XS, bool FLAT>
+// PF: the exchange inside (see PeerFusedArgs); a template flag, the other instantiations are untouched.
+template <class C, bool XS, bool FLAT, bool PF>
 __global__ void __launch_bounds__( C::NT, C::CTAS )
     cg_fused_kernel( const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_p,
                      const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
-                     const __grid_constant__ FusedArgs a )
+                     const __grid_constant__ FusedArgs a, const __grid_constant__ typename PeerSel<PF>::type pf )
 {
     constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
     constexpr int BOXD = C::BOX_PAD / 8, STAGED = C::STAGE_BYTES / 8;
@@ -239,6 +295,19 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     const int kend = min( kbeg + a.zc, g.n[2] );
     const int nplanes = kend - kbeg;
     const int nloads = nplanes + 2; // planes kbeg-1 .. kend
+
+    // PF: which block faces does this unit touch?  (uniform over the CTA; 0 for the interior units)
+    unsigned fmask = 0u;
+    if constexpr ( PF )
+    {
+        for ( int f = 0; f < pf.nface; ++f )
+        {
+            const PeerFace& F = pf.f[f];
+            if ( x0 < F.lo[0] + F.ext[0] && x0 + TX > F.lo[0] && y0 < F.lo[1] + F.ext[1] && y0 + TY > F.lo[1] &&
+                 kbeg < F.lo[2] + F.ext[2] && kend > F.lo[2] )
+                fmask |= 1u << f;
+        }
+    }
 
     const int i0 = x0 + 2 * lx;
     const bool vx0 = i0 < g.n[0], vx1 = i0 + 1 < g.n[0];
@@ -408,6 +477,17 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
                         prow[go] = v.x;
                         xrow[go] = fma( alpha, pv.x, xc[r].x );
                     }
+                    if constexpr ( PF )
+                    {
+                        if ( fmask )
+                        {
+                            const int j = y0 + wy + r * WY, k = kbeg + l - 1;
+                            if ( vx0 )
+                                peer_store_cell( pf, fmask, i0, j, k, v.x );
+                            if ( vx1 )
+                                peer_store_cell( pf, fmask, i0 + 1, j, k, v.y );
+                        }
+                    }
                 }
             }
         }
@@ -536,6 +616,13 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     {
         __shared__ dd_t s_red[C::NT / 32];
         __shared__ bool s_last;
+        if constexpr ( PF )
+        {
+            // my ghost stores are performed system-wide before the ticket is drawn (the barrier inside the block
+            // sum stands between this fence and thread 0's ticket)
+            if ( fmask )
+                __threadfence_system();
+        }
         dd_t s = dd_block_sum<C::NT>( acc, s_red );
         const unsigned bid = (unsigned)a.unit_base + blockIdx.x;
         if ( tid == 0 )
@@ -571,6 +658,49 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
                 S->pAp = tot.hi + tot.lo;
             S->rz_old = S->rz_new; // "zTr_old = zTr_new"
         }
+        if constexpr ( PF )
+        {
+            // steps 3-5 of cg_xchg_kernel (halo.cu) for reduction point 0: publish (data, fence, sequence number),
+            // wait for every rank's publication in my mailbox (bounded), combine exactly in rank order
+            __shared__ unsigned long long s_seq;
+            __threadfence_system();
+            if ( tid == 0 )
+                s_seq = ++S->seq[0];
+            __syncthreads(); // also: S->loc[0..1] of thread 0 is visible to the publishing threads
+            const unsigned long long seq = s_seq;
+            if ( tid < pf.world )
+            {
+                PeerMail* m = pf.mail[tid];
+                m->v[0][pf.rank][0] = S->loc[0];
+                m->v[0][pf.rank][1] = S->loc[1];
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned long long*>( &m->seq[0][pf.rank] ) = seq;
+            }
+            PeerMail* me = pf.mail[pf.rank];
+            if ( tid < pf.world && !S->xerror )
+            {
+                const long long t0 = clock64();
+                while ( *reinterpret_cast<const volatile unsigned long long*>( &me->seq[0][tid] ) < seq )
+                    if ( clock64() - t0 > pf.timeout_cycles )
+                    {
+                        S->xerror = 1;
+                        break;
+                    }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if ( tid == 0 )
+            {
+                dd_t sum = { 0.0, 0.0 };
+                for ( int r = 0; r < pf.world; ++r )
+                {
+                    const volatile double* src = &me->v[0][r][0];
+                    dd_t w = { src[0], src[1] };
+                    sum = dd_add( sum, w );
+                }
+                S->pAp = sum.hi + sum.lo;
+            }
+        }
     }
 }
 
@@ -580,57 +710,62 @@ typedef CUresult ( *PFN_encodeTiled )( CUtensorMap*, CUtensorMapDataType, cuuint
                                        CUtensorMapFloatOOBfill );
 
 template <class C>
-int launch_fused_cfg( cfb_ctx* c, const FusedArgs& a, int grid )
+int launch_fused_cfg( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedArgs* pf )
 {
     static bool attr_set = false;
     if ( !attr_set )
     {
-        cudaFuncSetAttribute( cg_fused_kernel<C, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
-        cudaFuncSetAttribute( cg_fused_kernel<C, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
-        cudaFuncSetAttribute( cg_fused_kernel<C, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
-        cudaFuncSetAttribute( cg_fused_kernel<C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( cg_fused_kernel<C, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
         attr_set = true;
     }
     const bool xs = a.gxr[0] || a.gxr[1];
     const bool flat = c->g.D == 2 && c->flat_2d; // one owned plane between two zero ghost planes
-    if ( xs && flat )
-        cg_fused_kernel<C, true, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
-                                                                                  c->g, c->op, a );
+    const NoPeerArgs none{};
+    if ( pf ) // (launch_cg_fused_peer has made sure that neither xs nor flat applies)
+        cg_fused_kernel<C, false, false, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+                                                                                          c->g, c->op, a, *pf );
+    else if ( xs && flat )
+        cg_fused_kernel<C, true, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+                                                                                         c->g, c->op, a, none );
     else if ( xs )
-        cg_fused_kernel<C, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
-                                                                                   c->g, c->op, a );
+        cg_fused_kernel<C, true, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+                                                                                          c->g, c->op, a, none );
     else if ( flat )
-        cg_fused_kernel<C, false, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
-                                                                                   c->g, c->op, a );
+        cg_fused_kernel<C, false, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+                                                                                          c->g, c->op, a, none );
     else
-        cg_fused_kernel<C, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
-                                                                                    c->g, c->op, a );
+        cg_fused_kernel<C, false, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+                                                                                           c->g, c->op, a, none );
     return 1;
 }
 
-int dispatch_fused( cfb_ctx* c, const FusedArgs& a, int grid )
+int dispatch_fused( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedArgs* pf = nullptr )
 {
     const int key = c->fu_tx * 10000 + c->fu_ty * 100 + c->fu_stages;
     switch ( key )
     {
     case 641603:
-        return launch_fused_cfg<FusedCfg<64, 16, 3>>( c, a, grid );
+        return launch_fused_cfg<FusedCfg<64, 16, 3>>( c, a, grid, pf );
     case 641604:
-        return launch_fused_cfg<FusedCfg<64, 16, 4>>( c, a, grid );
+        return launch_fused_cfg<FusedCfg<64, 16, 4>>( c, a, grid, pf );
     case 640803:
-        return launch_fused_cfg<FusedCfg<64, 8, 3>>( c, a, grid );
+        return launch_fused_cfg<FusedCfg<64, 8, 3>>( c, a, grid, pf );
     case 640804:
-        return launch_fused_cfg<FusedCfg<64, 8, 4>>( c, a, grid );
+        return launch_fused_cfg<FusedCfg<64, 8, 4>>( c, a, grid, pf );
     case 643202:
-        return launch_fused_cfg<FusedCfg<64, 32, 2>>( c, a, grid );
+        return launch_fused_cfg<FusedCfg<64, 32, 2>>( c, a, grid, pf );
     case 643203:
-        return launch_fused_cfg<FusedCfg<64, 32, 3>>( c, a, grid );
+        return launch_fused_cfg<FusedCfg<64, 32, 3>>( c, a, grid, pf );
     case 1280803:
-        return launch_fused_cfg<FusedCfg<128, 8, 3>>( c, a, grid );
+        return launch_fused_cfg<FusedCfg<128, 8, 3>>( c, a, grid, pf );
     case 1280804:
-        return launch_fused_cfg<FusedCfg<128, 8, 4>>( c, a, grid );
+        return launch_fused_cfg<FusedCfg<128, 8, 4>>( c, a, grid, pf );
     case 1281603:
-        return launch_fused_cfg<FusedCfg<128, 16, 3>>( c, a, grid );
+        return launch_fused_cfg<FusedCfg<128, 16, 3>>( c, a, grid, pf );
     default:
         cfb_fail( c, CFB_ERR_INVALID, "unsupported fused tile configuration" );
         return 0;
@@ -805,4 +940,68 @@ int launch_cg_fused( cfb_ctx* c, int which )
             return 0;
     }
     return dispatch_fused( c, a, grid );
+}
+
+// Phase B over all units with the exchange inside (PeerFusedArgs): replaces
+//   launch_cg_fused( c, 0 ); peer_exchange( c, 0, false, c->pcur ^ 1, ... );
+// Falls back to exactly that pair when the fused form does not apply (x ghosts read from the staging areas,
+// two-dimensional runs without the ghost-plane loads).
+int launch_cg_fused_peer( cfb_ctx* c )
+{
+    const Geo& g = c->g;
+    if ( peer_xstaged( c ) || ( g.D == 2 && c->flat_2d ) )
+    {
+        const int n = launch_cg_fused( c, 0 );
+        peer_exchange( c, 0, false, c->pcur ^ 1, !peer_xstaged( c ) );
+        return n;
+    }
+    FusedArgs a{};
+    a.x = c->lhs;
+    a.p_old = c->cg_pbuf[c->pcur];
+    a.p = c->cg_pbuf[c->pcur ^ 1];
+    a.q = c->cg_q;
+    a.S = c->d_state;
+    a.partials = c->d_partials;
+    a.hx = 16;
+    int chunks;
+    fused_tiling( c, a.tiles_x, a.tiles_y, a.zc, chunks );
+    const int total = a.tiles_x * a.tiles_y * chunks;
+    a.units_total = total;
+    a.reverse = c->fu_reverse ? 1 : 0;
+    a.store_q = c->cg_variant == 2 ? 0 : 1;
+    PeerFusedArgs pf{};
+    pf.rank = c->cfg.world_rank;
+    pf.world = c->cfg.world_size;
+    pf.timeout_cycles = 20000000000ll; // ~10 s at 1.9 GHz: a dead peer must not hang the GPU
+    for ( int r = 0; r < pf.world; ++r )
+        pf.mail[r] = c->mail[r];
+    for ( int s = 0; s < 2 * g.D; ++s )
+    {
+        if ( c->nbr[s] < 0 )
+            continue;
+        const int d = s / 2, side = s % 2;
+        PeerFace& f = pf.f[pf.nface++];
+        f.dst = c->peer_p[c->pcur ^ 1][s];
+        f.dorigin = c->peer_origin[s];
+        f.dsy = c->peer_sy[s];
+        f.dsz = c->peer_sz[s];
+        for ( int e = 0; e < 3; ++e )
+        {
+            f.lo[e] = 0;
+            f.ext[e] = g.n[e];
+            f.shift[e] = 0;
+        }
+        f.ext[d] = 1;
+        if ( side == 0 )
+        {
+            f.lo[d] = 0; // my first layer -> the low neighbour's high ghost (index n_peer)
+            f.shift[d] = -c->peer_n[s][d];
+        }
+        else
+        {
+            f.lo[d] = g.n[d] - 1; // my last layer -> the high neighbour's low ghost (index -1)
+            f.shift[d] = g.n[d];
+        }
+    }
+    return dispatch_fused( c, a, total, &pf );
 }

@@ -311,6 +311,7 @@ int cfb_residual_history( const cfb_ctx* ctx, double* hist, int n, int* count );
  *   poll_every n          convergence polling interval in iterations (0 = auto)
  *   peer_halo 0|1         ghost exchange over NVLink peer memory (default when available) or NCCL send/recv
  *   overlap_halo, peer_xstage      exchange schedules (see csrc/halo.cu)
+ *   peer_fused 0|1        phase B of the CG iteration does its ghost / reduction exchange itself (default 0)
  *   mg_graph, mg_coarse_kernel     multigrid V-cycle as a CUDA graph / coarse levels in one kernel (one block)
  *   time_kernels 0|1      record CUDA events around each CG kernel (cfb_stats.ms_k_*) */
 int cfb_set_tuning( cfb_ctx* ctx, const char* key, int value );

@@ -478,4 +478,11 @@ int launch_cg_fused( cfb_ctx* c, int which )
     S->rz_old = S->rz_new;
     return 1;
 }
+// "peer_fused" with the plain-loop stand-ins: the unfused pair it replaces
+int launch_cg_fused_peer( cfb_ctx* c )
+{
+    const int n = launch_cg_fused( c, 0 );
+    peer_exchange( c, 0, false, c->pcur ^ 1, !peer_xstaged( c ) );
+    return n;
+}
 #endif // !CFB_EMUL_REAL_TMA

@@ -376,6 +376,10 @@ def test_64_byte_iteration_block_decomposed(emul, world, blocks, peer):
 
 MODES = [("peer, small tiles", True, {"fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
          ("peer, phase B reads the x ghosts from the staging areas", True, {"peer_xstage": 1}),
+         ("peer, exchange inside phase B", True, {"peer_fused": 1}),
+         ("peer, exchange inside phase B, small tiles", True,
+          {"peer_fused": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
+         ("peer, exchange inside phase B, 64-byte iteration", True, {"peer_fused": 1, "cg_variant": 2}),
          ("NCCL, interior overlapped with the r/p halo", False, {"overlap_halo": 1}),
          ("NCCL, overlap, small tiles, several boundary units", False,
           {"overlap_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
@@ -446,3 +450,43 @@ def test_decomposed_solve_writes_one_file_set_per_block_and_one_master(emul, tmp
         v[(slice(None),) + sl] = np.load(os.path.join(out, blk["velocity"]))
     # written after step index 2 = the final state; advected fields agree to rounding across decompositions
     assert np.abs(q - oq).max() < 1e-12 and np.abs(v - ov).max() < 1e-12
+
+
+GRIDS_FUSED = [(2, None), (2, (2, 1, 1)), (2, (1, 2, 1)), (3, (1, 1, 3)), (4, None), (4, (2, 2, 1)), (6, (1, 3, 2)), (8, None)]
+
+
+@pytest.mark.parametrize("world,blocks", GRIDS_FUSED)
+def test_exchange_inside_phase_b_on_every_block_grid(emul, world, blocks):
+    """"peer_fused": the boundary tiles of phase B store their block-face cells of the new search direction straight
+    into the neighbours' ghost layers and the last block of the kernel runs the mailbox exchange of p.Ap — no exchange
+    kernel after phase B.  Converged and repeated solves (sequence numbers and p buffers carry over), uneven blocks."""
+    if not emul.tma:
+        pytest.skip("the exchange lives in the TMA kernel (the plain-loop stand-in runs the unfused pair)")
+    cfg = cfg3(cells=(23, 20, 21))
+    ora = Oracle(cfg)
+    rng = np.random.default_rng(81)
+    vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
+    for f, a in vel.items():
+        ora.set(f, a)
+    ora.add_inputs()
+    ora.build_rhs()
+    io, ro = ora.pcg_solve()
+    po, ho = ora.get(K.PRESSURE), ora.residual_history()
+
+    def body(ctx, rank):
+        ctx.set_tuning("peer_fused", 1)
+        for f, a in vel.items():
+            ctx.set(f, a[block_slices(ctx, f)])
+        out = []
+        for _ in range(2):
+            ctx.add_inputs()
+            ctx.build_rhs()
+            l0 = ctx.stats()["kernel_launches"]
+            ig, rg = ctx.pcg_solve()
+            out.append((ig, rg, np.array_equal(ctx.get(K.PRESSURE), po[block_slices(ctx, K.PRESSURE)]),
+                        np.array_equal(ctx.residual_history(), ho)))
+        return ctx.stats()["peer_mode"], out
+
+    for peer, out in run_ranks(emul, cfg, world, body, blocks, peer=True):
+        assert peer == 1
+        assert out == [(io, ro, True, True)] * 2, out

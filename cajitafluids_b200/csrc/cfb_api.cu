@@ -151,15 +151,20 @@ int enqueue_iteration( cfb_ctx* c )
         const bool peer = cg_peer_mode( c );
         if ( e )
             cudaEventRecord( e[0], c->stream );
+        const bool fusedA = peer && c->peer_fused && c->cg_variant == 1; // exchange inside phase A
         if ( c->cg_variant == 2 )
         {
             if ( c->cfg.use_nccl && !peer )
                 halo_exchange_cells( c, c->cg_p, 1 );
             n += launch_stencil_rupdate( c );
         }
+        else if ( fusedA )
+            n += launch_cg_rupdate_peer( c );
         else
             n += launch_cg_rupdate( c );
-        if ( peer )
+        if ( fusedA )
+            ;
+        else if ( peer )
             peer_exchange( c, 1, true, -1, !peer_xstaged( c ) ); // r faces -> neighbours, (rz_new, rr) -> all
         else if ( c->cfg.use_nccl )
             cg_global_sum( c, 1 );

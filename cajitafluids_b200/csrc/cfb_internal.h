@@ -288,6 +288,7 @@ int fused_setup( cfb_ctx* c );                // tensor maps of cg_r, cg_p + the
 int launch_cg_rupdate( cfb_ctx* c );          // phase A: r -= alpha q, sum r^2, sum r.Minv r
 int launch_cg_fused( cfb_ctx* c, int which ); // phase B: 0 = all units, 1 = interior, 2 = boundary
 int launch_cg_fused_peer( cfb_ctx* c );        // phase B + its ghost / reduction exchange in one kernel (peer_fused)
+int launch_cg_rupdate_peer( cfb_ctx* c );      // phase A + its ghost / reduction exchange in one kernel (peer_fused)
 int launch_cg_finish( cfb_ctx* c );
 // output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
 int output_write( cfb_ctx* c, const char* dir, int time_step );

@@ -38,6 +38,114 @@ __device__ __forceinline__ bool cg_converged( const CgState* S )
     return !S->fixed && sqrt( S->rr ) <= S->thresh;
 }
 
+// ---- the two kernels of an iteration with their ghost / reduction exchange inside ("peer_fused" tuning key) ----
+// Several blocks over NVLink peer memory.  Instead of phase B followed by the exchange kernel (halo.cu:
+// cg_xchg_kernel), the boundary tiles store the cells of the new search direction that lie on a block face
+// straight into the neighbour's ghost layer as they are computed — the transfer overlaps the z-march tile by
+// tile — and the block that draws the last ticket (the one that already closes the p.Ap reduction) publishes
+// the local double-double into every rank's mailbox, waits for everybody's and combines them: steps 3-5 of the
+// exchange kernel, same mailboxes, same sequence numbers, hence the same barrier semantics (a rank leaves phase
+// B only when every rank's ghost stores of this phase are done; p is double-buffered, so nobody still reads the
+// ghost layers written here).  Phase A (cg_rupdate_kernel<true>) does the same with the faces of r and the
+// (r.z, r.r) pair; r is single-buffered, and safe for the same reason: a rank enters phase A only when every
+// rank has left phase B, the last reader of the old ghost layers of r.  No exchange launch in the iteration.
+struct PeerFace
+{
+    double* dst;                 // the neighbour's copy of the array the new p is written to
+    long long dorigin, dsy, dsz; // its layout
+    int lo[3], ext[3], shift[3]; // my box (owned index space); peer index = my index - shift
+};
+
+struct PeerFusedArgs
+{
+    int nface;
+    PeerFace f[6];
+    PeerMail* mail[CFB_MAX_PEERS];
+    int rank, world;
+    long long timeout_cycles;
+};
+
+struct NoPeerArgs
+{
+};
+
+template <bool PF>
+struct PeerSel
+{
+    typedef NoPeerArgs type;
+};
+template <>
+struct PeerSel<true>
+{
+    typedef PeerFusedArgs type;
+};
+
+__device__ __forceinline__ void peer_store_cell( const PeerFusedArgs& pf, unsigned fmask, int i, int j, int k, double v )
+{
+#pragma unroll
+    for ( int f = 0; f < 6; ++f )
+    {
+        if ( !( ( fmask >> f ) & 1u ) )
+            continue;
+        const PeerFace& F = pf.f[f];
+        if ( i >= F.lo[0] && i < F.lo[0] + F.ext[0] && j >= F.lo[1] && j < F.lo[1] + F.ext[1] && k >= F.lo[2] &&
+             k < F.lo[2] + F.ext[2] )
+            F.dst[F.dorigin + (long long)( k - F.shift[2] ) * F.dsz + (long long)( j - F.shift[1] ) * F.dsy +
+                  ( i - F.shift[0] )] = v;
+    }
+}
+
+// Steps 3-5 of cg_xchg_kernel (halo.cu), run by all threads of the block that drew the last ticket of a kernel:
+// publish S->loc[first .. first + nd) into slot [which][my rank] of every rank's mailbox (data, system fence,
+// sequence number), wait for every rank's publication in mine (bounded), and hand back the exact sums in rank
+// order: out[v] = sum over ranks of the v-th double-double (thread 0 only).
+template <int NV>
+__device__ __forceinline__ void peer_mail_exchange( CgState* S, const PeerFusedArgs& pf, int which, int first, dd_t out[NV] )
+{
+    __shared__ unsigned long long s_seq;
+    const int tid = threadIdx.x;
+    __threadfence_system();
+    if ( tid == 0 )
+        s_seq = ++S->seq[which];
+    __syncthreads(); // also: what thread 0 left in S->loc is visible to the publishing threads
+    const unsigned long long seq = s_seq;
+    if ( tid < pf.world )
+    {
+        PeerMail* m = pf.mail[tid];
+        for ( int q = 0; q < 2 * NV; ++q )
+            m->v[which][pf.rank][q] = S->loc[first + q];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>( &m->seq[which][pf.rank] ) = seq;
+    }
+    PeerMail* me = pf.mail[pf.rank];
+    if ( tid < pf.world && !S->xerror )
+    {
+        const long long t0 = clock64();
+        while ( *reinterpret_cast<const volatile unsigned long long*>( &me->seq[which][tid] ) < seq )
+            if ( clock64() - t0 > pf.timeout_cycles )
+            {
+                S->xerror = 1;
+                break;
+            }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ( tid == 0 )
+    {
+        for ( int v = 0; v < NV; ++v )
+        {
+            dd_t sum = { 0.0, 0.0 };
+            for ( int r = 0; r < pf.world; ++r )
+            {
+                const volatile double* src = &me->v[which][r][2 * v];
+                dd_t w = { src[0], src[1] };
+                sum = dd_add( sum, w );
+            }
+            out[v] = sum;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // phase A.  Thread layout: 256 threads = TXP (power of two, 32..256) along x times 256/TXP rows; a
 // block walks over batches of (256/TXP) * RU rows, every thread issuing the 128-bit loads of its RU
@@ -45,10 +153,11 @@ __device__ __forceinline__ bool cg_converged( const CgState* S )
 // reuse at all, it lives on memory-level parallelism), one integer division per RU column pairs.
 constexpr int RU = 4;
 
+template <bool PF>
 __global__ void __launch_bounds__( NT, 3 )
     cg_rupdate_kernel( const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
                        const double* __restrict__ q, double* __restrict__ r, CgState* S, double* partials,
-                       int txp_log2 )
+                       int txp_log2, const __grid_constant__ typename PeerSel<PF>::type pf )
 {
     // `done` is only ever written by this kernel, cg_check0 and cg_finish (never by phase B, whose
     // late CTAs would otherwise see it mid-launch); phase B of the iteration that met the tolerance
@@ -70,12 +179,15 @@ __global__ void __launch_bounds__( NT, 3 )
     const int batch = tyr * RU;
     const bool odd = g.n[0] & 1;
     dd_t rr = { 0.0, 0.0 }, rz = { 0.0, 0.0 };
+    bool stored = false; // PF: this thread has written into a neighbour's ghost layer
     for ( int row0 = blockIdx.x * batch; row0 < rows; row0 += gridDim.x * batch )
     {
         // rows of this thread: row0 + ry + u * tyr
         int cyz[RU];
         long long ro[RU];
         bool ok[RU];
+        int rj[RU], rk[RU];     // PF: the row's (j, k)
+        unsigned rmask[RU];     // PF: faces whose (j, k) range holds the row
 #pragma unroll
         for ( int u = 0; u < RU; ++u )
         {
@@ -85,6 +197,18 @@ __global__ void __launch_bounds__( NT, 3 )
             const int j = row - k * g.n[1];
             cyz[u] = wall_count( g, 1, j + g.off[1] ) + wall_count( g, 2, k + g.off[2] );
             ro[u] = geo_off( g, 0, j, k );
+            if constexpr ( PF )
+            {
+                rj[u] = j;
+                rk[u] = k;
+                rmask[u] = 0u;
+                for ( int f = 0; f < pf.nface; ++f )
+                {
+                    const PeerFace& F = pf.f[f];
+                    if ( j >= F.lo[1] && j < F.lo[1] + F.ext[1] && k >= F.lo[2] && k < F.lo[2] + F.ext[2] )
+                        rmask[u] |= 1u << f;
+                }
+            }
         }
         for ( int ip = lx; ip < npx; ip += txp )
         {
@@ -129,8 +253,25 @@ __global__ void __launch_bounds__( NT, 3 )
                 }
                 else
                     r[ro[u] + i] = v.x;
+                if constexpr ( PF )
+                {
+                    if ( rmask[u] )
+                    {
+                        peer_store_cell( pf, rmask[u], i, rj[u], rk[u], v.x );
+                        if ( two )
+                            peer_store_cell( pf, rmask[u], i + 1, rj[u], rk[u], v.y );
+                        stored = true;
+                    }
+                }
             }
         }
+    }
+    if constexpr ( PF )
+    {
+        // my ghost stores are performed system-wide before the block's ticket is drawn (the barriers inside the
+        // block reduction stand between this fence and thread 0's ticket)
+        if ( stored )
+            __threadfence_system();
     }
     dd_t vals[2] = { rr, rz };
     if ( block_reduce_finalize<NT, 2>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
@@ -148,6 +289,16 @@ __global__ void __launch_bounds__( NT, 3 )
             {
                 S->rr = vals[0].hi + vals[0].lo;
                 S->rz_new = vals[1].hi + vals[1].lo;
+            }
+        }
+        if constexpr ( PF )
+        {
+            dd_t sum[2]; // reduction point 1: (r.z, r.r) from S->loc[2..5]
+            peer_mail_exchange<2>( S, pf, 1, 2, sum );
+            if ( threadIdx.x == 0 )
+            {
+                S->rz_new = sum[0].hi + sum[0].lo;
+                S->rr = sum[1].hi + sum[1].lo;
             }
         }
     }
@@ -200,61 +351,6 @@ struct FusedArgs
     int unit_base;   // index of this launch's first unit in the partial-sum scratch
     int units_total; // units of all launches that make up one phase B (last-block ticket target)
 };
-
-// ---- phase B with the ghost exchange and the reduction exchange inside ("peer_fused" tuning key) -----------
-// Several blocks over NVLink peer memory.  Instead of phase B followed by the exchange kernel (halo.cu:
-// cg_xchg_kernel), the boundary tiles store the cells of the new search direction that lie on a block face
-// straight into the neighbour's ghost layer as they are computed — the transfer overlaps the z-march tile by
-// tile — and the block that draws the last ticket (the one that already closes the p.Ap reduction) publishes
-// the local double-double into every rank's mailbox, waits for everybody's and combines them: steps 3-5 of the
-// exchange kernel, same mailboxes, same sequence numbers, hence the same barrier semantics (a rank leaves phase
-// B only when every rank's ghost stores of this phase are done; p is double-buffered, so nobody still reads the
-// ghost layers written here).  One launch less per iteration.
-struct PeerFace
-{
-    double* dst;                 // the neighbour's copy of the array the new p is written to
-    long long dorigin, dsy, dsz; // its layout
-    int lo[3], ext[3], shift[3]; // my box (owned index space); peer index = my index - shift
-};
-
-struct PeerFusedArgs
-{
-    int nface;
-    PeerFace f[6];
-    PeerMail* mail[CFB_MAX_PEERS];
-    int rank, world;
-    long long timeout_cycles;
-};
-
-struct NoPeerArgs
-{
-};
-
-template <bool PF>
-struct PeerSel
-{
-    typedef NoPeerArgs type;
-};
-template <>
-struct PeerSel<true>
-{
-    typedef PeerFusedArgs type;
-};
-
-__device__ __forceinline__ void peer_store_cell( const PeerFusedArgs& pf, unsigned fmask, int i, int j, int k, double v )
-{
-#pragma unroll
-    for ( int f = 0; f < 6; ++f )
-    {
-        if ( !( ( fmask >> f ) & 1u ) )
-            continue;
-        const PeerFace& F = pf.f[f];
-        if ( i >= F.lo[0] && i < F.lo[0] + F.ext[0] && j >= F.lo[1] && j < F.lo[1] + F.ext[1] && k >= F.lo[2] &&
-             k < F.lo[2] + F.ext[2] )
-            F.dst[F.dorigin + (long long)( k - F.shift[2] ) * F.dsz + (long long)( j - F.shift[1] ) * F.dsy +
-                  ( i - F.shift[0] )] = v;
-    }
-}
 
 // FLAT: two-dimensional runs (one owned plane between two zero ghost planes, see Geo): the z neighbours are
 // zero by construction, so the two ghost planes are neither loaded nor recomputed — the 2-D traffic of r and p
@@ -660,46 +756,10 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
         }
         if constexpr ( PF )
         {
-            // steps 3-5 of cg_xchg_kernel (halo.cu) for reduction point 0: publish (data, fence, sequence number),
-            // wait for every rank's publication in my mailbox (bounded), combine exactly in rank order
-            __shared__ unsigned long long s_seq;
-            __threadfence_system();
+            dd_t sum[1];
+            peer_mail_exchange<1>( S, pf, 0, 0, sum );
             if ( tid == 0 )
-                s_seq = ++S->seq[0];
-            __syncthreads(); // also: S->loc[0..1] of thread 0 is visible to the publishing threads
-            const unsigned long long seq = s_seq;
-            if ( tid < pf.world )
-            {
-                PeerMail* m = pf.mail[tid];
-                m->v[0][pf.rank][0] = S->loc[0];
-                m->v[0][pf.rank][1] = S->loc[1];
-                __threadfence_system();
-                *reinterpret_cast<volatile unsigned long long*>( &m->seq[0][pf.rank] ) = seq;
-            }
-            PeerMail* me = pf.mail[pf.rank];
-            if ( tid < pf.world && !S->xerror )
-            {
-                const long long t0 = clock64();
-                while ( *reinterpret_cast<const volatile unsigned long long*>( &me->seq[0][tid] ) < seq )
-                    if ( clock64() - t0 > pf.timeout_cycles )
-                    {
-                        S->xerror = 1;
-                        break;
-                    }
-            }
-            __threadfence_system();
-            __syncthreads();
-            if ( tid == 0 )
-            {
-                dd_t sum = { 0.0, 0.0 };
-                for ( int r = 0; r < pf.world; ++r )
-                {
-                    const volatile double* src = &me->v[0][r][0];
-                    dd_t w = { src[0], src[1] };
-                    sum = dd_add( sum, w );
-                }
-                S->pAp = sum.hi + sum.lo;
-            }
+                S->pAp = sum[0].hi + sum[0].lo;
         }
     }
 }
@@ -873,7 +933,7 @@ int fused_setup( cfb_ctx* c )
     return CFB_OK;
 }
 
-int launch_cg_rupdate( cfb_ctx* c )
+static int launch_rupdate_impl( cfb_ctx* c, const PeerFusedArgs* pf )
 {
     const Geo& g = c->g;
     const int npx = ( g.n[0] + 1 ) / 2;
@@ -886,9 +946,68 @@ int launch_cg_rupdate( cfb_ctx* c )
     const long long cap = std::min<long long>( (long long)c->sm_count * c->ru_ctas, CFB_MAX_PARTIALS );
     if ( grid > cap )
         grid = cap;
-    cg_rupdate_kernel<<<(int)grid, NT, 0, c->stream>>>( g, c->op, c->cg_q, c->cg_r, c->d_state, c->d_partials,
-                                                       txp_log2 );
+    if ( pf )
+        cg_rupdate_kernel<true><<<(int)grid, NT, 0, c->stream>>>( g, c->op, c->cg_q, c->cg_r, c->d_state, c->d_partials,
+                                                                 txp_log2, *pf );
+    else
+        cg_rupdate_kernel<false><<<(int)grid, NT, 0, c->stream>>>( g, c->op, c->cg_q, c->cg_r, c->d_state,
+                                                                  c->d_partials, txp_log2, NoPeerArgs{} );
     return 1;
+}
+
+int launch_cg_rupdate( cfb_ctx* c ) { return launch_rupdate_impl( c, nullptr ); }
+
+// the faces of block `c` towards its neighbours, as destinations of `array` (one of the neighbours' mapped copies)
+static void peer_faces( cfb_ctx* c, PeerFusedArgs& pf, double* const dst_of_side[6] )
+{
+    const Geo& g = c->g;
+    pf.rank = c->cfg.world_rank;
+    pf.world = c->cfg.world_size;
+    pf.timeout_cycles = 20000000000ll; // ~10 s at 1.9 GHz: a dead peer must not hang the GPU
+    for ( int r = 0; r < pf.world; ++r )
+        pf.mail[r] = c->mail[r];
+    for ( int s = 0; s < 2 * g.D; ++s )
+    {
+        if ( c->nbr[s] < 0 )
+            continue;
+        const int d = s / 2, side = s % 2;
+        PeerFace& f = pf.f[pf.nface++];
+        f.dst = dst_of_side[s];
+        f.dorigin = c->peer_origin[s];
+        f.dsy = c->peer_sy[s];
+        f.dsz = c->peer_sz[s];
+        for ( int e = 0; e < 3; ++e )
+        {
+            f.lo[e] = 0;
+            f.ext[e] = g.n[e];
+            f.shift[e] = 0;
+        }
+        f.ext[d] = 1;
+        if ( side == 0 )
+        {
+            f.lo[d] = 0; // my first layer -> the low neighbour's high ghost (index n_peer)
+            f.shift[d] = -c->peer_n[s][d];
+        }
+        else
+        {
+            f.lo[d] = g.n[d] - 1; // my last layer -> the high neighbour's low ghost (index -1)
+            f.shift[d] = g.n[d];
+        }
+    }
+}
+
+// Phase A with the exchange inside: replaces  launch_cg_rupdate( c ); peer_exchange( c, 1, true, -1, ... );
+int launch_cg_rupdate_peer( cfb_ctx* c )
+{
+    if ( peer_xstaged( c ) )
+    {
+        const int n = launch_cg_rupdate( c );
+        peer_exchange( c, 1, true, -1, false );
+        return n;
+    }
+    PeerFusedArgs pf{};
+    peer_faces( c, pf, c->peer_r );
+    return launch_rupdate_impl( c, &pf );
 }
 
 int launch_cg_finish( cfb_ctx* c )
@@ -970,38 +1089,6 @@ int launch_cg_fused_peer( cfb_ctx* c )
     a.reverse = c->fu_reverse ? 1 : 0;
     a.store_q = c->cg_variant == 2 ? 0 : 1;
     PeerFusedArgs pf{};
-    pf.rank = c->cfg.world_rank;
-    pf.world = c->cfg.world_size;
-    pf.timeout_cycles = 20000000000ll; // ~10 s at 1.9 GHz: a dead peer must not hang the GPU
-    for ( int r = 0; r < pf.world; ++r )
-        pf.mail[r] = c->mail[r];
-    for ( int s = 0; s < 2 * g.D; ++s )
-    {
-        if ( c->nbr[s] < 0 )
-            continue;
-        const int d = s / 2, side = s % 2;
-        PeerFace& f = pf.f[pf.nface++];
-        f.dst = c->peer_p[c->pcur ^ 1][s];
-        f.dorigin = c->peer_origin[s];
-        f.dsy = c->peer_sy[s];
-        f.dsz = c->peer_sz[s];
-        for ( int e = 0; e < 3; ++e )
-        {
-            f.lo[e] = 0;
-            f.ext[e] = g.n[e];
-            f.shift[e] = 0;
-        }
-        f.ext[d] = 1;
-        if ( side == 0 )
-        {
-            f.lo[d] = 0; // my first layer -> the low neighbour's high ghost (index n_peer)
-            f.shift[d] = -c->peer_n[s][d];
-        }
-        else
-        {
-            f.lo[d] = g.n[d] - 1; // my last layer -> the high neighbour's low ghost (index -1)
-            f.shift[d] = g.n[d];
-        }
-    }
+    peer_faces( c, pf, c->peer_p[c->pcur ^ 1] );
     return dispatch_fused( c, a, total, &pf );
 }

@@ -20,7 +20,8 @@ TMA_SOURCES = ["kernels_stencil.cu", "kernels_fused.cu"]
 SOURCES = ["cfb_api.cu", "kernels_fields.cu", "kernels_cg.cu", "mg.cu", "output.cu", "halo.cu"]
 HEADERS = ["cfb_internal.h", "device_geo.cuh"]
 # kernels whose threads meet at __syncthreads() for real: one fiber per CUDA thread
-COOP_KERNELS = {"cg_xchg_kernel", "stencil7_dot_tma", "cg_fused_kernel", "mg_coarse_cycle_kernel", "mg_xchg_kernel"}
+COOP_KERNELS = {"cg_xchg_kernel", "stencil7_dot_tma", "cg_fused_kernel", "cg_rupdate_kernel", "mg_coarse_cycle_kernel",
+                "mg_xchg_kernel"}
 STANDINS = ["cuda_runtime.h", "cuda.h", "nccl.h", "device_reduce.cuh", "device_tma.cuh", "emul_glue.cpp", "nccl_emul.cpp"]
 
 

@@ -474,19 +474,47 @@ def test_exchange_inside_phase_b_on_every_block_grid(emul, world, blocks):
     po, ho = ora.get(K.PRESSURE), ora.residual_history()
 
     def body(ctx, rank):
-        ctx.set_tuning("peer_fused", 1)
         for f, a in vel.items():
             ctx.set(f, a[block_slices(ctx, f)])
-        out = []
-        for _ in range(2):
+        out, launches = [], []
+        for fused in (1, 0, 1):  # the two forms share the mailboxes and their sequence numbers
+            ctx.set_tuning("peer_fused", fused)
             ctx.add_inputs()
             ctx.build_rhs()
             l0 = ctx.stats()["kernel_launches"]
             ig, rg = ctx.pcg_solve()
+            launches.append(ctx.stats()["kernel_launches"] - l0)
             out.append((ig, rg, np.array_equal(ctx.get(K.PRESSURE), po[block_slices(ctx, K.PRESSURE)]),
                         np.array_equal(ctx.residual_history(), ho)))
-        return ctx.stats()["peer_mode"], out
+        return ctx.stats()["peer_mode"], out, launches
 
-    for peer, out in run_ranks(emul, cfg, world, body, blocks, peer=True):
+    for peer, out, launches in run_ranks(emul, cfg, world, body, blocks, peer=True):
         assert peer == 1
-        assert out == [(io, ro, True, True)] * 2, out
+        assert out == [(io, ro, True, True)] * 3, out
+        # two exchange launches (and the x-unpack launches) less per iteration
+        assert launches[0] == launches[2] and launches[1] >= launches[0] + 2 * io - 4, launches
+
+
+def test_exchange_inside_the_kernels_whole_steps(emul):
+    """(same bar as test_peer_memory_exchange_steps_and_fixed_iterations: the projection of the setup bit for bit,
+    a whole step to 1e-12 of the global norm)"""
+    if not emul.tma:
+        pytest.skip("the exchange lives in the TMA kernels")
+    cfg = cfg3(cells=(32, 24, 16), fixed_iters=20)
+    ora = Oracle(cfg)
+    ora.setup()
+    want0 = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
+    ora.step()
+    want = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
+    gl = {f: max(np.linalg.norm(want[f].ravel()), 1e-300) for f in want}
+
+    def body(ctx, rank):
+        ctx.set_tuning("peer_fused", 1)
+        ctx.setup()
+        exact = [f for f in want0 if not np.array_equal(ctx.get(f), want0[f][block_slices(ctx, f)])]
+        ctx.step()
+        err = {f: float(np.linalg.norm((ctx.get(f) - want[f][block_slices(ctx, f)]).ravel()) / gl[f]) for f in want}
+        return exact, err
+
+    for exact, err in run_ranks(emul, cfg, 8, body, None, peer=True):
+        assert exact == [] and max(err.values()) < 1e-12, (exact, err)

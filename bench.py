@@ -632,6 +632,38 @@ def main():
         except Exception as e:  # noqa: BLE001
             extra["advect_tile_probe"] = {"error": repr(e)[:300]}
 
+    # extra (several GPUs, NVLink peer memory): the same workload with the ghost / reduction exchanges inside the two
+    # kernels of the iteration ("peer_fused": no exchange launch) — written after the round's GPU budget was spent and
+    # not the default; measured last, so that nothing above depends on it; every rank agrees on the outcome.
+    if world > 1 and st["peer_mode"] and not fallback and args.cg_variant == 1 and not args.no_probe and not args.tune:
+        try:
+            err, ms_f, r_f, r_ref = None, 0.0, None, None
+            try:
+                _, r_ref = s.pcg_fixed(args.iters)  # the default form on the right-hand side as it is now
+                s.set_tuning("peer_fused", 1)
+                for _ in range(2):
+                    s.pcg_fixed(args.iters)
+                for _ in range(3):
+                    m, r_f = s.pcg_fixed(args.iters)
+                    ms_f += m
+            except Exception as e:  # noqa: BLE001
+                err = e
+            try:
+                s.set_tuning("peer_fused", 0)
+            except Exception:  # noqa: BLE001
+                pass
+            if all_ranks_ok(err is None):
+                t = torch.tensor([ms_f], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                extra["peer_fused"] = {"value": units * 3 * args.iters / (float(t[0]) * 1e-3), "unit": UNIT, "steps": 3,
+                                       "final_residual": r_f, "same_residual_as_default_form": r_f == r_ref,
+                                       "note": "exchange inside phase A and phase B (no exchange kernel), 3 steps; "
+                                               "not the headline form until it has been profiled"}
+            else:
+                extra["peer_fused"] = {"error": repr(err)[:300] if err is not None else "another rank failed"}
+        except Exception as e:  # noqa: BLE001
+            extra["peer_fused"] = {"error": repr(e)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_baseline(args, max(2, min(args.iters, 10)), (args.cells,) * 3)

@@ -22,6 +22,13 @@ timeout 600 $RUN --master-port 29613 bench.py --gpus $N --steps 5 --warmup 3 --s
 # 3. the 64-byte iteration on N GPUs
 timeout 600 $RUN --master-port 29614 bench.py --gpus $N --steps 5 --warmup 3 --cg-variant 2 --no-e2e --no-timestep \
     > "$O/bench_weak_peer_variant2.json" 2> "$O/bench_weak_peer_variant2.err"
+# 3b. ghost / reduction exchange inside the two kernels of the iteration (peer_fused), weak and strong
+timeout 600 $RUN --master-port 29616 bench.py --gpus $N --steps 5 --warmup 3 --tune peer_fused=1 --no-e2e --no-timestep \
+    > "$O/bench_weak_peer_fused.json" 2> "$O/bench_weak_peer_fused.err"
+timeout 600 $RUN --master-port 29617 bench.py --gpus $N --steps 5 --warmup 3 --scaling strong --cells 256 --tune peer_fused=1 \
+    --no-e2e --no-timestep > "$O/bench_strong256_peer_fused.json" 2> "$O/bench_strong256_peer_fused.err"
+timeout 600 $RUN --master-port 29618 bench.py --gpus $N --steps 5 --warmup 3 --scaling strong --cells 256 \
+    --no-e2e --no-timestep > "$O/bench_strong256_peer.json" 2> "$O/bench_strong256_peer.err"
 # 4. the multigrid preconditioner at scale: Jacobi vs MG, peer vs NCCL ghost exchanges
 timeout 900 $RUN --master-port 29615 tools/profile_mg_multi.py 512 > "$O/mg_multi.log" 2>&1
 ls -la "$O" > "$O/listing.txt"

@@ -29,6 +29,8 @@ timeout 600 $RUN --master-port 29617 bench.py --gpus $N --steps 5 --warmup 3 --s
     --no-e2e --no-timestep > "$O/bench_strong256_peer_fused.json" 2> "$O/bench_strong256_peer_fused.err"
 timeout 600 $RUN --master-port 29618 bench.py --gpus $N --steps 5 --warmup 3 --scaling strong --cells 256 \
     --no-e2e --no-timestep > "$O/bench_strong256_peer.json" 2> "$O/bench_strong256_peer.err"
+timeout 600 $RUN --master-port 29619 bench.py --gpus $N --steps 5 --warmup 3 --scaling strong --tune peer_fused=1 \
+    --no-e2e --no-timestep > "$O/bench_strong_peer_fused.json" 2> "$O/bench_strong_peer_fused.err"
 # 4. the multigrid preconditioner at scale: Jacobi vs MG, peer vs NCCL ghost exchanges
 timeout 900 $RUN --master-port 29615 tools/profile_mg_multi.py 512 > "$O/mg_multi.log" 2>&1
 ls -la "$O" > "$O/listing.txt"

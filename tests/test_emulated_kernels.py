@@ -426,8 +426,8 @@ def test_emulated_two_dimensional_runs_without_the_ghost_plane_loads(emul, cells
             s.build_rhs()
         assert g.pcg_solve() == o.pcg_solve(), variant
         assert np.array_equal(g.get(K.PRESSURE), o.get(K.PRESSURE)) and np.array_equal(g.get(K.CG_R), o.get(K.CG_R)), variant
-    if cells[0] > 200:
-        return  # (the reference's 2000 iterations do not converge there, and fibers are slow)
+    if cells != (64, 64):
+        return  # (whole runs on one case: fibers are slow)
     g2, o2 = Context(emul, make_cfg(2, cells, box=box_of(cells), **kw)), Oracle(make_cfg(2, cells, box=box_of(cells), **kw))
     g2.set_tuning("flat_2d", 1)
     assert run(g2, 1) == run(o2, 1)

@@ -452,17 +452,18 @@ def test_decomposed_solve_writes_one_file_set_per_block_and_one_master(emul, tmp
     assert np.abs(q - oq).max() < 1e-12 and np.abs(v - ov).max() < 1e-12
 
 
-GRIDS_FUSED = [(2, None), (2, (2, 1, 1)), (2, (1, 2, 1)), (3, (1, 1, 3)), (4, None), (4, (2, 2, 1)), (6, (1, 3, 2)), (8, None)]
+# (world, blocks, fixed iterations: 0 = to convergence, once — fibers are slow)
+GRIDS_FUSED = [(2, None, 0), (2, (2, 1, 1), 14), (2, (1, 2, 1), 14), (4, (2, 2, 1), 14), (6, (1, 3, 2), 14), (8, None, 14)]
 
 
-@pytest.mark.parametrize("world,blocks", GRIDS_FUSED)
-def test_exchange_inside_phase_b_on_every_block_grid(emul, world, blocks):
+@pytest.mark.parametrize("world,blocks,fixed", GRIDS_FUSED)
+def test_exchange_inside_the_kernels_on_every_block_grid(emul, world, blocks, fixed):
     """"peer_fused": the boundary tiles of phase B store their block-face cells of the new search direction straight
     into the neighbours' ghost layers and the last block of the kernel runs the mailbox exchange of p.Ap — no exchange
     kernel after phase B.  Converged and repeated solves (sequence numbers and p buffers carry over), uneven blocks."""
     if not emul.tma:
         pytest.skip("the exchange lives in the TMA kernel (the plain-loop stand-in runs the unfused pair)")
-    cfg = cfg3(cells=(23, 20, 21))
+    cfg = cfg3(cells=(23, 20, 21), fixed_iters=fixed)
     ora = Oracle(cfg)
     rng = np.random.default_rng(81)
     vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}

@@ -151,12 +151,12 @@ int enqueue_iteration( cfb_ctx* c )
         const bool peer = cg_peer_mode( c );
         if ( e )
             cudaEventRecord( e[0], c->stream );
-        const bool fusedA = peer && c->peer_fused && c->cg_variant == 1; // exchange inside phase A
+        const bool fusedA = peer && c->peer_fused; // exchange inside phase A / A'
         if ( c->cg_variant == 2 )
         {
             if ( c->cfg.use_nccl && !peer )
                 halo_exchange_cells( c, c->cg_p, 1 );
-            n += launch_stencil_rupdate( c );
+            n += fusedA ? launch_stencil_rupdate_peer( c ) : launch_stencil_rupdate( c );
         }
         else if ( fusedA )
             n += launch_cg_rupdate_peer( c );

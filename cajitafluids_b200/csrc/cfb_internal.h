@@ -289,6 +289,7 @@ int launch_cg_rupdate( cfb_ctx* c );          // phase A: r -= alpha q, sum r^2,
 int launch_cg_fused( cfb_ctx* c, int which ); // phase B: 0 = all units, 1 = interior, 2 = boundary
 int launch_cg_fused_peer( cfb_ctx* c );        // phase B + its ghost / reduction exchange in one kernel (peer_fused)
 int launch_cg_rupdate_peer( cfb_ctx* c );      // phase A + its ghost / reduction exchange in one kernel (peer_fused)
+int launch_stencil_rupdate_peer( cfb_ctx* c ); // phase A' of the 64-byte iteration, the same
 int launch_cg_finish( cfb_ctx* c );
 // output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
 int output_write( cfb_ctx* c, const char* dir, int time_step );

@@ -22,6 +22,7 @@
 #include "device_geo.cuh"
 #include "device_reduce.cuh"
 #include "device_tma.cuh"
+#include "device_peer.cuh"
 
 namespace
 {
@@ -73,10 +74,13 @@ struct StencilArgs
 //         produced it, hence bit-identical.
 // FLAT: two-dimensional runs (one owned plane between two zero ghost planes): the z neighbours are zero by
 // construction and their planes are not loaded.  A template flag: the 3-D instantiations are untouched.
-template <class C, int MODE, bool FLAT>
+// PF (MODE 1 only, "peer_fused"): the faces of the new r go into the neighbours' ghost layers from here and the
+// last block runs the mailbox exchange of (r.z, r.r) — device_peer.cuh; no exchange kernel after phase A'.
+template <class C, int MODE, bool FLAT, bool PF>
 __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) )
     stencil7_dot_tma( const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geo g,
-                      const __grid_constant__ OpConst op, const __grid_constant__ StencilArgs a )
+                      const __grid_constant__ OpConst op, const __grid_constant__ StencilArgs a,
+                      const __grid_constant__ typename PeerSel<PF>::type pf )
 {
     constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
     double nalpha = 0.0;
@@ -121,6 +125,18 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     const int kend = min( kbeg + a.zc, g.n[2] );
     const int nplanes = kend - kbeg; // planes to compute
     const int nloads = nplanes + 2;  // planes kbeg-1 .. kend
+    // PF: which block faces does this unit touch?  (uniform over the CTA; 0 for the interior units)
+    unsigned fmask = 0u;
+    if constexpr ( PF )
+    {
+        for ( int f = 0; f < pf.nface; ++f )
+        {
+            const PeerFace& F = pf.f[f];
+            if ( x0 < F.lo[0] + F.ext[0] && x0 + TX > F.lo[0] && y0 < F.lo[1] + F.ext[1] && y0 + TY > F.lo[1] &&
+                 kbeg < F.lo[2] + F.ext[2] && kend > F.lo[2] )
+                fmask |= 1u << f;
+        }
+    }
 
     // TMA box origin (array coordinates): 2 columns left of the tile, 1 row below, plane kbeg-1
     const int cx = a.hx + x0 - 2;
@@ -273,6 +289,17 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
                         dd_acc( acc, rv * rv );
                         dd_acc( acc2, ( op.minv[w0] * rv ) * rv );
                     }
+                    if constexpr ( PF )
+                    {
+                        if ( fmask )
+                        {
+                            const int j = y0 + wy + r * WY, k = kbeg + it;
+                            if ( vx0 )
+                                peer_store_cell( pf, fmask, i0, j, k, fma( nalpha, a0, rcur[r].x ) );
+                            if ( vx1 )
+                                peer_store_cell( pf, fmask, i0 + 1, j, k, fma( nalpha, a1, rcur[r].y ) );
+                        }
+                    }
                 }
             }
             zm[r] = c;
@@ -301,6 +328,12 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     }
     else
     {
+        if constexpr ( PF )
+        {
+            // my ghost stores are performed system-wide before the block's ticket is drawn
+            if ( fmask )
+                __threadfence_system();
+        }
         dd_t vals[2] = { acc, acc2 };
         if ( block_reduce_finalize<C::NT, 2>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
         {
@@ -319,6 +352,16 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
                 {
                     S->rr = vals[0].hi + vals[0].lo;
                     S->rz_new = vals[1].hi + vals[1].lo;
+                }
+            }
+            if constexpr ( PF )
+            {
+                dd_t sum[2]; // reduction point 1: (r.z, r.r) from S->loc[2..5]
+                peer_mail_exchange<2>( a.S, pf, 1, 2, sum );
+                if ( tid == 0 )
+                {
+                    a.S->rz_new = sum[0].hi + sum[0].lo;
+                    a.S->rr = sum[1].hi + sum[1].lo;
                 }
             }
         }
@@ -392,25 +435,30 @@ typedef CUresult ( *PFN_encodeTiled )( CUtensorMap*, CUtensorMapDataType, cuuint
                                        CUtensorMapFloatOOBfill );
 
 template <class C, int MODE>
-int launch_tma_mode( cfb_ctx* c, const StencilArgs& a, int grid )
+int launch_tma_mode( cfb_ctx* c, const StencilArgs& a, int grid, const PeerFusedArgs* pf )
 {
     static bool attr_set = false;
     if ( !attr_set )
     {
-        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
-        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        if ( MODE == 1 )
+            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
         attr_set = true;
     }
-    if ( c->g.D == 2 && c->flat_2d )
-        stencil7_dot_tma<C, MODE, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a );
+    const NoPeerArgs none{};
+    if ( MODE == 1 && pf ) // (launch_stencil_rupdate_peer has made sure that flat does not apply)
+        stencil7_dot_tma<C, 1, false, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a, *pf );
+    else if ( c->g.D == 2 && c->flat_2d )
+        stencil7_dot_tma<C, MODE, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a, none );
     else
-        stencil7_dot_tma<C, MODE, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a );
+        stencil7_dot_tma<C, MODE, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a, none );
     return 1;
 }
 template <class C>
-int launch_tma( cfb_ctx* c, const StencilArgs& a, int grid, int mode )
+int launch_tma( cfb_ctx* c, const StencilArgs& a, int grid, int mode, const PeerFusedArgs* pf )
 {
-    return mode == 0 ? launch_tma_mode<C, 0>( c, a, grid ) : launch_tma_mode<C, 1>( c, a, grid );
+    return mode == 0 ? launch_tma_mode<C, 0>( c, a, grid, nullptr ) : launch_tma_mode<C, 1>( c, a, grid, pf );
 }
 
 } // namespace
@@ -446,7 +494,7 @@ int stencil_setup( cfb_ctx* c )
     return CFB_OK;
 }
 
-static int launch_stencil( cfb_ctx* c, int mode )
+static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullptr )
 {
     const Geo& g = c->g;
     StencilArgs a{};
@@ -479,23 +527,23 @@ static int launch_stencil( cfb_ctx* c, int mode )
     switch ( key )
     {
     case 641604:
-        return launch_tma<TileCfg<64, 16, 4>>( c, a, grid, mode );
+        return launch_tma<TileCfg<64, 16, 4>>( c, a, grid, mode, pf );
     case 641606:
-        return launch_tma<TileCfg<64, 16, 6>>( c, a, grid, mode );
+        return launch_tma<TileCfg<64, 16, 6>>( c, a, grid, mode, pf );
     case 640804:
-        return launch_tma<TileCfg<64, 8, 4>>( c, a, grid, mode );
+        return launch_tma<TileCfg<64, 8, 4>>( c, a, grid, mode, pf );
     case 643204:
-        return launch_tma<TileCfg<64, 32, 4>>( c, a, grid, mode );
+        return launch_tma<TileCfg<64, 32, 4>>( c, a, grid, mode, pf );
     case 643203:
-        return launch_tma<TileCfg<64, 32, 3>>( c, a, grid, mode );
+        return launch_tma<TileCfg<64, 32, 3>>( c, a, grid, mode, pf );
     case 1281604:
-        return launch_tma<TileCfg<128, 16, 4>>( c, a, grid, mode );
+        return launch_tma<TileCfg<128, 16, 4>>( c, a, grid, mode, pf );
     case 1281603:
-        return launch_tma<TileCfg<128, 16, 3>>( c, a, grid, mode );
+        return launch_tma<TileCfg<128, 16, 3>>( c, a, grid, mode, pf );
     case 1283203:
-        return launch_tma<TileCfg<128, 32, 3>>( c, a, grid, mode );
+        return launch_tma<TileCfg<128, 32, 3>>( c, a, grid, mode, pf );
     case 1280804:
-        return launch_tma<TileCfg<128, 8, 4>>( c, a, grid, mode );
+        return launch_tma<TileCfg<128, 8, 4>>( c, a, grid, mode, pf );
     default:
         cfb_fail( c, CFB_ERR_INVALID, "unsupported stencil tile configuration" );
         return 0;
@@ -506,3 +554,18 @@ int launch_stencil_dot( cfb_ctx* c ) { return launch_stencil( c, 0 ); }
 
 // phase A' of the 64-byte iteration (cg_variant 2): r -= alpha (A p) with q recomputed, sum r^2, sum r.M^-1 r
 int launch_stencil_rupdate( cfb_ctx* c ) { return launch_stencil( c, 1 ); }
+
+// the same with the ghost exchange of r and the (r.z, r.r) exchange inside: replaces
+//   launch_stencil_rupdate( c ); peer_exchange( c, 1, true, -1, ... );
+int launch_stencil_rupdate_peer( cfb_ctx* c )
+{
+    if ( peer_xstaged( c ) || ( c->g.D == 2 && c->flat_2d ) || c->st_variant == 1 )
+    {
+        const int n = launch_stencil_rupdate( c );
+        peer_exchange( c, 1, true, -1, !peer_xstaged( c ) );
+        return n;
+    }
+    PeerFusedArgs pf{};
+    peer_faces( c, pf, c->peer_r );
+    return launch_stencil( c, 1, &pf );
+}

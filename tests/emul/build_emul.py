@@ -18,7 +18,7 @@ LIB = os.path.join(OUT, "libcfb_emul.so")
 LIB_TMA = os.path.join(OUT, "libcfb_emul_tma.so")  # the TMA kernels themselves instead of plain-loop stand-ins
 TMA_SOURCES = ["kernels_stencil.cu", "kernels_fused.cu"]
 SOURCES = ["cfb_api.cu", "kernels_fields.cu", "kernels_cg.cu", "mg.cu", "output.cu", "halo.cu"]
-HEADERS = ["cfb_internal.h", "device_geo.cuh"]
+HEADERS = ["cfb_internal.h", "device_geo.cuh", "device_peer.cuh"]
 # kernels whose threads meet at __syncthreads() for real: one fiber per CUDA thread
 COOP_KERNELS = {"cg_xchg_kernel", "stencil7_dot_tma", "cg_fused_kernel", "cg_rupdate_kernel", "mg_coarse_cycle_kernel",
                 "mg_xchg_kernel"}

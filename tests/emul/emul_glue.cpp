@@ -491,4 +491,10 @@ int launch_cg_rupdate_peer( cfb_ctx* c )
     peer_exchange( c, 1, true, -1, !peer_xstaged( c ) );
     return n;
 }
+int launch_stencil_rupdate_peer( cfb_ctx* c )
+{
+    const int n = launch_stencil_rupdate( c );
+    peer_exchange( c, 1, true, -1, !peer_xstaged( c ) );
+    return n;
+}
 #endif // !CFB_EMUL_REAL_TMA

@@ -146,7 +146,7 @@ def section_3(args, rank, gcfg, rank_cfg, rng, check):
              ("two-kernel without a stored q (64 B/cell), NCCL", {"cg_variant": 2, "peer_halo": 0}),
              # written after the round's GPU budget was spent; last, so that everything above is checked first
              ("two-kernel, NVLink peer stores, exchange inside the kernels", {"cg_variant": 1, "peer_halo": 1, "peer_fused": 1}),
-             ("two-kernel without a stored q, exchange inside phase B", {"cg_variant": 2, "peer_halo": 1, "peer_fused": 1})]
+             ("two-kernel without a stored q, exchange inside the kernels", {"cg_variant": 2, "peer_halo": 1, "peer_fused": 1})]
     if args.quick:
         modes = [modes[0], modes[1], modes[2], modes[4]]
     for name, tune in modes:

@@ -379,7 +379,7 @@ MODES = [("peer, small tiles", True, {"fused_stages": 4, "fused_zc": 4, "fused_t
          ("peer, exchange inside phase B", True, {"peer_fused": 1}),
          ("peer, exchange inside phase B, small tiles", True,
           {"peer_fused": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
-         ("peer, exchange inside phase B, 64-byte iteration", True, {"peer_fused": 1, "cg_variant": 2}),
+         ("peer, exchange inside the kernels, 64-byte iteration", True, {"peer_fused": 1, "cg_variant": 2}),
          ("NCCL, interior overlapped with the r/p halo", False, {"overlap_halo": 1}),
          ("NCCL, overlap, small tiles, several boundary units", False,
           {"overlap_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),

@@ -20,7 +20,9 @@ TMA_SOURCES = ["kernels_stencil.cu", "kernels_fused.cu"]
 SOURCES = ["cfb_api.cu", "kernels_fields.cu", "kernels_cg.cu", "mg.cu", "output.cu", "halo.cu"]
 HEADERS = ["cfb_internal.h", "device_geo.cuh", "device_peer.cuh"]
 # kernels whose threads meet at __syncthreads() for real: one fiber per CUDA thread
-COOP_KERNELS = {"cg_xchg_kernel", "stencil7_dot_tma", "cg_fused_kernel", "cg_rupdate_kernel", "mg_coarse_cycle_kernel",
+# (a name with its template arguments selects that instantiation only: phase A meets at barriers only when it
+# runs the mailbox exchange itself)
+COOP_KERNELS = {"cg_xchg_kernel", "stencil7_dot_tma", "cg_fused_kernel", "cg_rupdate_kernel<true>", "mg_coarse_cycle_kernel",
                 "mg_xchg_kernel"}
 STANDINS = ["cuda_runtime.h", "cuda.h", "nccl.h", "device_reduce.cuh", "device_tma.cuh", "emul_glue.cpp", "nccl_emul.cpp"]
 
@@ -81,7 +83,7 @@ def rewrite_launches(src):
         a0 = src.index("(", j)
         a1 = _match(src, a0, "(", ")")
         args = src[a0 + 1:a1 - 1]
-        fn = "launch_coop" if kernel.strip().split("<")[0] in COOP_KERNELS else "launch"
+        fn = "launch_coop" if kernel.strip().split("<")[0] in COOP_KERNELS or kernel.strip() in COOP_KERNELS else "launch"
         out += src[pos:start] + (f"cfb_emul::{fn}( dim3( {cfg[0]} ), dim3( {cfg[1]} ), [=]() {{ {kernel}( {args} ); }} )")
         pos = a1
 

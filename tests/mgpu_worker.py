@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--skip-steps", action="store_true", help="only the stencil / gather / PCG sections")
     ap.add_argument("--quick", action="store_true", help="only the PCG section, three exchange modes")
     ap.add_argument("--mg", action="store_true", help="only the multigrid-preconditioner section")
+    ap.add_argument("--fused", action="store_true", help="only the PCG section, exchange inside the kernels (peer_fused)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
     torch.cuda.set_device(local)
@@ -67,6 +68,8 @@ def main():
     rng = np.random.default_rng(77)
     if args.mg:
         section_5(args, rank, blocks, gcfg, rank_cfg, rng, check)
+    elif args.fused:
+        section_3(args, rank, gcfg, rank_cfg, rng, check)
     else:
         if not args.quick:
             sections_1_2(args, rank, gcfg, rank_cfg, rng, check)
@@ -143,12 +146,19 @@ def section_3(args, rank, gcfg, rank_cfg, rng, check):
                "fused_ty": 8}),
              ("three-kernel, NCCL", {"cg_variant": 0}),
              ("two-kernel without a stored q (64 B/cell), NVLink peer stores", {"cg_variant": 2, "peer_halo": 1}),
-             ("two-kernel without a stored q (64 B/cell), NCCL", {"cg_variant": 2, "peer_halo": 0}),
-             # written after the round's GPU budget was spent; last, so that everything above is checked first
-             ("two-kernel, NVLink peer stores, exchange inside the kernels", {"cg_variant": 1, "peer_halo": 1, "peer_fused": 1}),
-             ("two-kernel without a stored q, exchange inside the kernels", {"cg_variant": 2, "peer_halo": 1, "peer_fused": 1})]
+             ("two-kernel without a stored q (64 B/cell), NCCL", {"cg_variant": 2, "peer_halo": 0})]
     if args.quick:
         modes = [modes[0], modes[1], modes[2], modes[4]]
+    if args.fused:
+        # written after the round's GPU budget was spent: run by tests/test_zzz_multigpu_late.py only
+        modes = [modes[0],
+                 ("two-kernel, NVLink peer stores, exchange inside the kernels",
+                  {"cg_variant": 1, "peer_halo": 1, "peer_fused": 1}),
+                 ("exchange inside the kernels, small tiles",
+                  {"cg_variant": 1, "peer_halo": 1, "peer_fused": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64,
+                   "fused_ty": 8}),
+                 ("two-kernel without a stored q, exchange inside the kernels",
+                  {"cg_variant": 2, "peer_halo": 1, "peer_fused": 1})]
     for name, tune in modes:
         gpu = Solver(rank_cfg())
         for k, v in tune.items():

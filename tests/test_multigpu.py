@@ -41,11 +41,3 @@ def test_two_blocks_split_along_x_or_y(blocks):
     # 128 cells along x: the two 64-cell blocks end exactly on a 64-wide tile, which is the case where
     # phase B reads its x ghosts from the NVLink staging areas instead of the ghost columns
     _run_worker(2, ["--blocks"] + [str(b) for b in blocks] + ["--quick"], cells=(128, 24, 20))
-
-
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_block_decomposed_multigrid_matches_single_block_oracle(world):
-    """The opt-in multigrid preconditioner runs the same global V-cycle on every decomposition (one-layer
-    face exchange per operator application): V-cycle and MG-PCG bit for bit against the single-block oracle.
-    (Checked on the CPU by tests/test_emulated_multirank.py; first GPU run pending.)"""
-    _run_worker(world, ["--mg"], cells=(64, 32, 32))

@@ -12,6 +12,8 @@ RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-add
 # 1. parity on N GPUs: every exchange schedule, field halo, whole steps, the block-decomposed multigrid
 timeout 1200 python -m pytest tests/test_multigpu.py -m gpu -q -x -k "$N or two_blocks" > "$O/pytest_multigpu.log" 2>&1
 echo "pytest rc=$?" >> "$O/summary.txt"
+timeout 1200 python -m pytest tests/test_zzz_multigpu_late.py -m gpu -q -k "$N" > "$O/pytest_multigpu_late.log" 2>&1
+echo "pytest (late) rc=$?" >> "$O/summary.txt"
 
 # 2. the headline bench, weak scaling (default: NVLink peer-memory exchange), then the NCCL path, then strong scaling
 timeout 600 $RUN --master-port 29611 bench.py --gpus $N --steps 5 --warmup 3 > "$O/bench_weak_peer.json" 2> "$O/bench_weak_peer.err"

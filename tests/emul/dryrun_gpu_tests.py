@@ -11,6 +11,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("CFB_FULL_N", "48")  # the full-size tests at a size the emulation finishes
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.exit(pytest.main([os.path.join(ROOT, "tests"), "-q", "-m", "gpu", "-p", "no:cacheprovider", "--deselect",
                       "tests/test_zz_cpp_layer.py::test_cpp_shims_and_driver_on_the_gpu"] + sys.argv[1:]))

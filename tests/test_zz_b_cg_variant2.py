@@ -1,0 +1,71 @@
+"""The 64-byte CG iteration (`cg_variant` 2: q = A p is never stored; phase A' — the TMA stencil kernel in a second
+mode — recomputes it while it updates r, src/VelocityCorrector.hpp:124-143 + Cajita's ReferenceConjugateGradient) on
+the GPU against the other forms and the oracle, bit for bit.  CPU: tests/test_emulated_kernels.py (the kernels
+themselves on the host).  (Sorts late: written after this round's GPU budget was spent.)"""
+import numpy as np
+import pytest
+
+from cajitafluids_b200 import config as K
+from helpers import fields_of, make_cfg, rel_l2, smooth_velocity
+from oracle_api import Oracle
+
+ALL = lambda dim: fields_of(dim) + [K.PRESSURE]  # noqa: E731
+
+
+def run(ctx, steps):
+    ctx.setup()
+    its = [ctx.stats()["cg_iterations"]]
+    for _ in range(steps):
+        ctx.step()
+        its.append(ctx.stats()["cg_iterations"])
+    return np.diff([0] + its)
+
+
+# ---------------------------------------------------------------------------------------------
+# cg_variant 2 (64 B/cell: q never stored, phase A' recomputes A p) — written after the round's GPU budget was
+# spent, bit-exact against the oracle in the host emulation (TMA kernels themselves); first GPU run here
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells,walls", [((70, 50, 21), "solid"), ((130, 36, 5), "mixed"), ((33, 47), "solid"),
+                                         ((64, 64, 64), "solid")])
+def test_cuda_64_byte_iteration_matches_the_other_forms_and_the_oracle(cells, walls):
+    from cajitafluids_b200 import Solver
+    dim = len(cells)
+    bt = None
+    if walls == "mixed":
+        bt = [K.SOLID, K.FREE, K.SOLID, K.SOLID, K.SOLID, K.FREE]
+    box = tuple(c / cells[0] for c in cells)
+    for fixed in (0, 9):
+        cfg = make_cfg(dim, cells, box=box, fixed_iters=fixed, **(dict(boundary_type=bt) if bt else {}))
+        o = Oracle(cfg)
+        rng = np.random.default_rng(6)
+        vel = smooth_velocity(o, rng)
+        for f, a in vel.items():
+            o.set(f, a)
+        o.add_inputs()
+        o.build_rhs()
+        ro = o.pcg_solve()
+        for variant in (2, 1):
+            g = Solver(cfg)
+            g.set_tuning("cg_variant", variant)
+            for f, a in vel.items():
+                g.set(f, a)
+            g.add_inputs()
+            g.build_rhs()
+            rg = g.pcg_solve()
+            assert abs(rg[0] - ro[0]) <= 1, (variant, rg, ro)
+            assert rel_l2(g.get(K.PRESSURE), o.get(K.PRESSURE)) < 1e-10, variant
+            assert rg == ro and np.array_equal(g.get(K.PRESSURE), o.get(K.PRESSURE)), (variant, rg, ro)
+            assert np.array_equal(g.residual_history(), o.residual_history())
+            g.close()
+
+
+@pytest.mark.gpu
+def test_cuda_64_byte_iteration_whole_steps():
+    from cajitafluids_b200 import Solver
+    for dim, n in ((2, 64), (3, 48)):
+        cfg = make_cfg(dim, n)
+        g, o = Solver(cfg), Oracle(cfg)
+        g.set_tuning("cg_variant", 2)
+        assert list(run(g, 3)) == list(run(o, 3))
+        for f in ALL(dim):
+            assert np.array_equal(g.get(f), o.get(f)), f

@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > "
 
 # 1. the GPU tests, file by file, so that one failing file does not hide the others
 for f in tests/test_capi.py tests/test_golden.py tests/test_golden_refrun.py tests/test_gpu_parity.py \
-         tests/test_zz_output_stage.py tests/test_zz_multigrid.py tests/test_zz_cpp_layer.py tests/test_zzy_full_size.py tests/test_zzz_late_options.py; do
+         tests/test_zz_a_output_stage.py tests/test_zz_b_cg_variant2.py tests/test_zz_multigrid.py tests/test_zz_cpp_layer.py tests/test_zzy_full_size.py tests/test_zzz_late_options.py; do
     timeout 900 python -m pytest "$f" -m gpu -q -x > "$O/pytest_$(basename "$f" .py).log" 2>&1
     echo "$f rc=$?" >> "$O/pytest_summary.txt"
 done

@@ -18,6 +18,26 @@ int cfb_fail( cfb_ctx* c, int code, const std::string& msg )
     return code;
 }
 
+int ensure_partials( cfb_ctx* c, long long units )
+{
+    if ( units > CFB_MAX_UNITS )
+        return cfb_fail( c, CFB_ERR_INVALID,
+                         "tiling yields " + std::to_string( units ) + " units in one launch (limit " +
+                             std::to_string( (long long)CFB_MAX_UNITS ) + "): choose larger tiles" );
+    const int need = (int)std::max<long long>( units, CFB_MAX_PARTIALS );
+    if ( c->d_partials && need <= c->partials_cap )
+        return CFB_OK;
+    if ( c->stream )
+        CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
+    if ( c->d_partials )
+        cudaFree( c->d_partials );
+    c->d_partials = nullptr;
+    c->partials_cap = 0;
+    CFB_CUDA( c, cudaMalloc( &c->d_partials, (size_t)2 * 2 * need * sizeof( double ) ) );
+    c->partials_cap = need;
+    return CFB_OK;
+}
+
 namespace
 {
 
@@ -155,7 +175,7 @@ int enqueue_iteration( cfb_ctx* c )
         if ( c->cg_variant == 2 )
         {
             if ( c->cfg.use_nccl && !peer )
-                halo_exchange_cells( c, c->cg_p, 1 );
+                note_rc( c, halo_exchange_cells( c, c->cg_p, 1 ) );
             n += fusedA ? launch_stencil_rupdate_peer( c ) : launch_stencil_rupdate( c );
         }
         else if ( fusedA )
@@ -165,9 +185,9 @@ int enqueue_iteration( cfb_ctx* c )
         if ( fusedA )
             ;
         else if ( peer )
-            peer_exchange( c, 1, true, -1, !peer_xstaged( c ) ); // r faces -> neighbours, (rz_new, rr) -> all
+            note_rc( c, peer_exchange( c, 1, true, -1, !peer_xstaged( c ) ) ); // r faces -> neighbours, (rz_new, rr) -> all
         else if ( c->cfg.use_nccl )
-            cg_global_sum( c, 1 );
+            note_rc( c, cg_global_sum( c, 1 ) );
         if ( e )
         {
             cudaEventRecord( e[1], c->stream );
@@ -178,25 +198,25 @@ int enqueue_iteration( cfb_ctx* c )
         else if ( peer )
         {
             n += launch_cg_fused( c, 0 );
-            peer_exchange( c, 0, false, c->pcur ^ 1, !peer_xstaged( c ) ); // new p faces, pAp -> all
+            note_rc( c, peer_exchange( c, 0, false, c->pcur ^ 1, !peer_xstaged( c ) ) ); // new p faces, pAp -> all
         }
         else if ( c->cfg.use_nccl )
         {
             double* fl[2] = { c->cg_r, c->cg_p };
             if ( c->overlap_halo && c->n_interior > 0 )
             {
-                halo_cells_begin( c, fl, 2, 1 );
+                note_rc( c, halo_cells_begin( c, fl, 2, 1 ) );
                 n += launch_cg_fused( c, 1 );
-                halo_cells_end( c );
+                note_rc( c, halo_cells_end( c ) );
                 n += launch_cg_fused( c, 2 );
             }
             else
             {
-                halo_cells_begin( c, fl, 2, 1 );
-                halo_cells_end( c );
+                note_rc( c, halo_cells_begin( c, fl, 2, 1 ) );
+                note_rc( c, halo_cells_end( c ) );
                 n += launch_cg_fused( c, 0 );
             }
-            cg_global_sum( c, 0 );
+            note_rc( c, cg_global_sum( c, 0 ) );
         }
         else
             n += launch_cg_fused( c, 0 );
@@ -214,10 +234,10 @@ int enqueue_iteration( cfb_ctx* c )
     if ( e )
         cudaEventRecord( e[2], c->stream );
     if ( c->cfg.use_nccl )
-        halo_exchange_cells( c, c->cg_p, 1 );
+        note_rc( c, halo_exchange_cells( c, c->cg_p, 1 ) );
     n += launch_stencil_dot( c );
     if ( c->cfg.use_nccl )
-        cg_global_sum( c, 0 );
+        note_rc( c, cg_global_sum( c, 0 ) );
     if ( e )
         cudaEventRecord( e[3], c->stream );
     return n;
@@ -249,17 +269,28 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     const int fixed = fixed_iters > 0;
     const int max_it = fixed ? fixed_iters : c->cfg.cg_max_iter;
     long long launches = 0;
+    c->sticky_rc = 0;
     const int p_start = c->pcur;
     const bool peer = cg_peer_mode( c );
     launches += launch_cg_init( c, fixed ); // peer mode: includes the exchange of p0's faces
     if ( c->cfg.use_nccl && !peer )
-        halo_exchange_cells( c, c->cg_p, 1 );
+        note_rc( c, halo_exchange_cells( c, c->cg_p, 1 ) );
     launches += launch_stencil_dot( c );
     if ( peer )
-        peer_exchange( c, 0, false, -1, false );
+        note_rc( c, peer_exchange( c, 0, false, -1, false ) );
     else if ( c->cfg.use_nccl )
-        cg_global_sum( c, 0 );
+        note_rc( c, cg_global_sum( c, 0 ) );
 
+    // a launcher refused its configuration or an exchange call failed: nothing (more) is enqueued, the
+    // error goes back to the caller instead of a wrong x with CFB_OK
+    auto bail = [&]() -> int {
+        const int rc = take_sticky_rc( c );
+        cudaStreamSynchronize( c->stream );
+        c->ktimed = 0;
+        return rc;
+    };
+    if ( c->sticky_rc )
+        return bail();
     const int batch = poll_batch( c );
     int enq = 0;
     bool done = false;
@@ -270,8 +301,10 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     while ( enq < max_it && !done )
     {
         int b = std::min( batch, max_it - enq );
-        for ( int i = 0; i < b; ++i )
+        for ( int i = 0; i < b && !c->sticky_rc; ++i )
             launches += enqueue_iteration( c );
+        if ( c->sticky_rc )
+            return bail();
         enq += b;
         if ( fixed )
             continue;
@@ -561,7 +594,11 @@ int cfb_create( const cfb_config* cfg, cfb_ctx** out )
     }
     CFB_CUDA( c, cudaMallocHost( &c->h_state, sizeof( CgState ) ) );
     std::memset( c->h_state, 0, sizeof( CgState ) );
-    CFB_CUDA( c, cudaMalloc( &c->d_partials, 2 * 2 * CFB_MAX_PARTIALS * sizeof( double ) ) );
+    {
+        const int rc = ensure_partials( c, CFB_MAX_PARTIALS );
+        if ( rc )
+            return rc;
+    }
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
 
     // ProblemManager::initialize with the constant MeshInitFunc (examples/advection.cpp:382-435)
@@ -839,20 +876,24 @@ int cfb_stencil_dot( cfb_ctx* c, int reps, double* dot, double* ms_per_launch )
 {
     if ( reps < 1 )
         reps = 1;
+    c->sticky_rc = 0;
     // make sure a previous converged solve does not turn the launches into no-ops
     CFB_CUDA( c, cudaMemsetAsync( &c->d_state->done, 0, sizeof( int ), c->stream ) );
     if ( c->cfg.use_nccl )
-        halo_exchange_cells( c, c->cg_p, 1 );
+        note_rc( c, halo_exchange_cells( c, c->cg_p, 1 ) );
     c->stats.kernel_launches += launch_stencil_dot( c ); // warm-up, untimed
     CFB_CUDA( c, cudaEventRecord( c->ev[EV_BENCH0], c->stream ) );
     for ( int i = 0; i < reps; ++i )
         c->stats.kernel_launches += launch_stencil_dot( c );
     CFB_CUDA( c, cudaEventRecord( c->ev[EV_BENCH1], c->stream ) );
     if ( c->cfg.use_nccl )
-        cg_global_sum( c, 0 );
+        note_rc( c, cg_global_sum( c, 0 ) );
     CFB_CUDA( c, cudaMemcpyAsync( c->h_state, c->d_state, STATE_HEAD, cudaMemcpyDeviceToHost, c->stream ) );
     CFB_CUDA( c, cudaStreamSynchronize( c->stream ) );
-    int rc = check_async( c, "stencil_dot" );
+    int rc = take_sticky_rc( c );
+    if ( rc )
+        return rc;
+    rc = check_async( c, "stencil_dot" );
     if ( rc )
         return rc;
     float ms = 0;
@@ -936,12 +977,47 @@ int cfb_set_cg_params( cfb_ctx* c, double tolerance, int max_iter, int print_lev
 int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
 {
     std::string k = key ? key : "";
+    // range of every integer key (switches take any value: non-zero is on).  Tile shapes are set one key at a
+    // time, so a combination nobody instantiated is refused where it is used: fused_setup for the extents, the
+    // launch for the (tx, ty, stages) triple — pcg_solve / cfb_stencil_dot then return CFB_ERR_INVALID.
+    struct Range
+    {
+        const char* key;
+        int lo, hi;
+    };
+    static const Range ranges[] = { { "stencil_variant", 0, 1 }, { "stencil_tx", 64, 128 }, { "stencil_ty", 8, 32 },
+                                    { "stencil_stages", 3, 6 },  { "stencil_zc", 0, 1 << 20 }, { "poll_every", 0, 1 << 20 },
+                                    { "cg_variant", 0, 2 },      { "fused_tx", 64, 128 },   { "fused_ty", 8, 32 },
+                                    { "fused_stages", 2, 4 },    { "fused_zc", 0, 1 << 20 }, { "rupdate_ctas", 1, 8 } };
+    for ( const Range& r : ranges )
+        if ( k == r.key && ( value < r.lo || value > r.hi ) )
+            return cfb_fail( c, CFB_ERR_INVALID,
+                             "tuning key " + k + ": value " + std::to_string( value ) + " outside [" +
+                                 std::to_string( r.lo ) + ", " + std::to_string( r.hi ) + "]" );
+    // a set-up that fails puts the previous value back
+    auto set_checked = [&]( int& field, int ( *setup )( cfb_ctx* ) ) -> int {
+        const int old = field;
+        const bool old_auto = c->fu_auto;
+        field = value;
+        if ( setup == fused_setup )
+            c->fu_auto = false;
+        const int rc = setup( c );
+        if ( rc )
+        {
+            const std::string msg = c->err;
+            field = old;
+            c->fu_auto = old_auto;
+            setup( c );
+            return cfb_fail( c, rc, msg );
+        }
+        return CFB_OK;
+    };
     if ( k == "stencil_variant" )
         c->st_variant = value;
     else if ( k == "stencil_tx" )
-        c->st_tx = value;
+        return set_checked( c->st_tx, stencil_setup );
     else if ( k == "stencil_ty" )
-        c->st_ty = value;
+        return set_checked( c->st_ty, stencil_setup );
     else if ( k == "stencil_stages" )
         c->st_stages = value;
     else if ( k == "stencil_zc" )
@@ -951,13 +1027,16 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     else if ( k == "cg_variant" )
         c->cg_variant = value;
     else if ( k == "fused_tx" )
-        c->fu_tx = value;
+        return set_checked( c->fu_tx, fused_setup );
     else if ( k == "fused_ty" )
-        c->fu_ty = value;
+        return set_checked( c->fu_ty, fused_setup );
     else if ( k == "fused_stages" )
+    {
         c->fu_stages = value;
+        c->fu_auto = false;
+    }
     else if ( k == "fused_zc" )
-        c->fu_zc = value;
+        return set_checked( c->fu_zc, fused_setup );
     else if ( k == "fused_reverse" )
         c->fu_reverse = value != 0;
     else if ( k == "rupdate_ctas" )
@@ -992,20 +1071,16 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
                     CFB_CUDA( c, cudaEventCreate( &e ) );
     }
     else if ( k == "fused_auto" )
-        ;
+    {
+        const bool old = c->fu_auto;
+        c->fu_auto = value != 0;
+        const int rc = fused_setup( c );
+        if ( rc )
+            c->fu_auto = old;
+        return rc;
+    }
     else
         return cfb_fail( c, CFB_ERR_INVALID, "unknown tuning key: " + k );
-    if ( k == "stencil_tx" || k == "stencil_ty" )
-        return stencil_setup( c );
-    if ( k == "fused_auto" )
-    {
-        c->fu_auto = value != 0;
-        return fused_setup( c );
-    }
-    if ( k.rfind( "fused_", 0 ) == 0 && k != "fused_reverse" )
-        c->fu_auto = false;
-    if ( k == "fused_tx" || k == "fused_ty" || k == "fused_zc" )
-        return fused_setup( c );
     return CFB_OK;
 }
 

@@ -94,7 +94,10 @@ struct PeerMail
     unsigned long long mseq[CFB_MAX_PEERS];
 };
 
+// Minimum capacity (entries per value) of the block-partial scratch; the grid-stride kernels never launch more
+// blocks than this.  The tiled kernels (one block per unit) grow the scratch to their unit count: ensure_partials.
 #define CFB_MAX_PARTIALS 4096
+#define CFB_MAX_UNITS ( 1 << 22 ) // more tiles than this in one launch is refused (CFB_ERR_INVALID)
 #define CFB_KTIMED 64
 
 struct OutputStage; // output.cu
@@ -123,7 +126,11 @@ struct cfb_ctx
 
     CgState* d_state = nullptr;
     CgState* h_state = nullptr; // pinned mirror (first bytes only are copied)
-    double* d_partials = nullptr; // [2 values][CFB_MAX_PARTIALS][hi,lo] scratch for block partial sums
+    double* d_partials = nullptr; // [2 values][partials_cap][hi,lo] scratch for block partial sums
+    int partials_cap = 0;         // >= CFB_MAX_PARTIALS; value n of block b at [( n * stride + b ) * 2], stride <= cap
+    // first error raised while enqueuing work (a launcher refusing a configuration, a failed exchange call): the
+    // launchers return launch counts, so the code travels here and pcg_solve / the C entry points hand it out
+    int sticky_rc = 0;
 
     // stencil TMA descriptor + tiling
     CUtensorMap tmap_p{};
@@ -212,6 +219,21 @@ struct cfb_ctx
 extern std::string g_cfb_error;
 
 int cfb_fail( cfb_ctx* c, int code, const std::string& msg );
+// remember the first non-zero status of a call whose return value cannot travel (see cfb_ctx::sticky_rc)
+inline int note_rc( cfb_ctx* c, int rc )
+{
+    if ( rc && !c->sticky_rc )
+        c->sticky_rc = rc;
+    return rc;
+}
+inline int take_sticky_rc( cfb_ctx* c )
+{
+    const int rc = c->sticky_rc;
+    c->sticky_rc = 0;
+    return rc;
+}
+// make room for `units` block partials per value (host-synchronising when it has to grow; set-up time only)
+int ensure_partials( cfb_ctx* c, long long units );
 
 #define CFB_CUDA( c, expr )                                                                        \
     do                                                                                             \

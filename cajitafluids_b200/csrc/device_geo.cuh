@@ -97,13 +97,18 @@ __device__ __forceinline__ void spline3( double xl, int& s0, double w[4] )
 // Interpolation::interpolateField<D, ORDER, Entity>  src/Interpolation.hpp:30-41.
 // Stencil indices are clamped into the ghosted allocation (the reference does not clamp: leaving
 // the halo is undefined behaviour there; parity is defined for CFL <= 1 only).
+// Fast path (the normal case, CFL <= 1): no stencil index is clamped, so the (ORDER+1)^D samples sit at
+// base + a + b * sy + c * sz — one 64-bit offset per row instead of a clamp and a full index computation per
+// sample (the kernel is instruction-issue bound: profiles/r2_advect_*).  Same loads, same products, same
+// summation order as the clamped path, hence the same bits.
 template <int D, int ORDER>
 __device__ __forceinline__ double interp_field( const Geo& g, int ent, const double* __restrict__ f,
                                                 const double loc[3] )
 {
     constexpr int NK = ORDER + 1;
-    int s[3][NK];
+    int s0[3] = { 0, 0, 0 };
     double w[3][NK];
+    bool inside = true;
 #pragma unroll
     for ( int d = 0; d < D; ++d )
     {
@@ -111,21 +116,65 @@ __device__ __forceinline__ double interp_field( const Geo& g, int ent, const dou
         const double low = ( ent - 1 == d ) ? g.ghost_low[d] + 0.0 * g.celld[d]
                                             : g.ghost_low[d] + ( 0.0 + 0.5 ) * g.celld[d];
         const double xl = ( loc[d] - low ) * g.rdxd[d];
-        int s0;
         if ( ORDER == 1 )
-            spline1( xl, s0, w[d] );
+            spline1( xl, s0[d], w[d] );
         else
-            spline3( xl, s0, w[d] );
+            spline3( xl, s0[d], w[d] );
+        const int emax = g.n[d] + 2 * g.h + ( ent - 1 == d ? 1 : 0 ) - 1;
+        inside = inside && s0[d] >= 0 && s0[d] + NK - 1 <= emax;
+    }
+    double value = 0.0;
+    if ( inside )
+    {
+        // local ghosted index -> owned index: - halo.  One pointer per (b, c) row of the stencil box, the samples
+        // of a row at immediate offsets from it.
+        const double* base = f + geo_off( g, s0[0] - g.h, s0[1] - g.h, D == 3 ? s0[2] - g.h : 0 );
+        const int rsy = (int)g.sy, rsz = (int)g.sz; // row / plane strides fit 32 bits (asserted in cfb_create)
+        if ( D == 2 )
+        {
+            const double* row[NK];
+#pragma unroll
+            for ( int b = 0; b < NK; ++b )
+                row[b] = base + (unsigned)( b * rsy );
+#pragma unroll
+            for ( int a = 0; a < NK; ++a )
+#pragma unroll
+                for ( int b = 0; b < NK; ++b )
+                    value += __ldg( row[b] + a ) * w[0][a] * w[1][b];
+        }
+        else
+        {
+            const double* row[NK][NK];
+#pragma unroll
+            for ( int b = 0; b < NK; ++b )
+#pragma unroll
+                for ( int c = 0; c < NK; ++c )
+                    row[b][c] = base + (unsigned)( c * rsz + b * rsy );
+#pragma unroll
+            for ( int a = 0; a < NK; ++a )
+#pragma unroll
+                for ( int b = 0; b < NK; ++b )
+#pragma unroll
+                    for ( int c = 0; c < NK; ++c )
+                        value += __ldg( row[b][c] + a ) * w[0][a] * w[1][b] * w[2][c];
+        }
+        return value;
+    }
+    // Stencil indices clamped into the ghosted allocation (the reference does not clamp: leaving the halo is
+    // undefined behaviour there; parity is defined for CFL <= 1 only).
+    int s[3][NK];
+#pragma unroll
+    for ( int d = 0; d < D; ++d )
+    {
         const int emax = g.n[d] + 2 * g.h + ( ent - 1 == d ? 1 : 0 ) - 1;
 #pragma unroll
         for ( int a = 0; a < NK; ++a )
         {
-            int si = s0 + a;
+            int si = s0[d] + a;
             si = si < 0 ? 0 : ( si > emax ? emax : si );
-            s[d][a] = si - g.h; // local ghosted index -> owned index
+            s[d][a] = si - g.h;
         }
     }
-    double value = 0.0;
     if ( D == 2 )
     {
 #pragma unroll

@@ -313,9 +313,9 @@ int launch_cg_init( cfb_ctx* c, int fixed )
                                                 c->d_partials, fixed );
     int launches = 1;
     if ( cg_peer_mode( c ) )
-        peer_exchange( c, 1, false, c->pcur, true ); // sums + the faces of p0 (x: staging AND ghost columns)
+        note_rc( c, peer_exchange( c, 1, false, c->pcur, true ) ); // sums + the faces of p0 (x: staging AND ghost columns)
     else if ( c->cfg.use_nccl )
-        cg_global_sum( c, 1 );
+        note_rc( c, cg_global_sum( c, 1 ) );
     cg_check0_kernel<<<1, 1, 0, c->stream>>>( c->d_state, c->cfg.cg_tolerance,
                                               c->cfg.cg_stop_rule == CFB_STOP_REL );
     return launches + 1;
@@ -329,7 +329,7 @@ int launch_cg_axpy( cfb_ctx* c )
     cg_axpy_kernel<<<grid, NT, 0, c->stream>>>( g, c->op, c->cg_p, c->cg_q, c->lhs, c->cg_r, c->d_state,
                                                 c->d_partials );
     if ( c->cfg.use_nccl )
-        cg_global_sum( c, 1 );
+        note_rc( c, cg_global_sum( c, 1 ) );
     return 1;
 }
 

@@ -720,7 +720,7 @@ int dispatch_fused( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedArg
     case 1281603:
         return launch_fused_cfg<FusedCfg<128, 16, 3>>( c, a, grid, pf );
     default:
-        cfb_fail( c, CFB_ERR_INVALID, "unsupported fused tile configuration" );
+        note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "unsupported fused tile configuration" ) );
         return 0;
     }
 }
@@ -734,8 +734,6 @@ void fused_tiling( const cfb_ctx* c, int& tiles_x, int& tiles_y, int& zc, int& c
     tiles_x = ( g.n[0] + c->fu_tx - 1 ) / c->fu_tx;
     tiles_y = ( g.n[1] + c->fu_ty - 1 ) / c->fu_ty;
     zc = c->fu_zc > 0 ? c->fu_zc : g.n[2];
-    while ( (long long)tiles_x * tiles_y * ( ( g.n[2] + zc - 1 ) / zc ) > CFB_MAX_PARTIALS )
-        zc *= 2;
     chunks = ( g.n[2] + zc - 1 ) / zc;
 }
 
@@ -753,6 +751,8 @@ int fused_setup( cfb_ctx* c )
         encode = (PFN_encodeTiled)fn;
     }
     const Geo& g = c->g;
+    if ( !c->fu_auto && ( c->fu_tx < 2 || c->fu_ty < 1 || c->fu_zc < 0 ) )
+        return cfb_fail( c, CFB_ERR_INVALID, "fused tile extents must be positive" );
     if ( c->fu_auto )
     {
         // Rules distilled from the sweeps in profiles/r1_sweep_fused*.log (64^3 ... 512^3):
@@ -775,7 +775,9 @@ int fused_setup( cfb_ctx* c )
             while ( units_of( tx, ty, zc ) < c->sm_count && zc > 4 )
                 zc /= 2;
         }
-        while ( units_of( tx, ty, zc ) > CFB_MAX_PARTIALS )
+        // very many units (large blocks): longer chunks re-read fewer planes; bounded — a large cross-section
+        // alone can exceed any unit budget (two-dimensional grids), the partial-sum scratch follows the unit count
+        while ( units_of( tx, ty, zc ) > CFB_MAX_PARTIALS && zc < g.n[2] )
             zc *= 2;
         c->fu_tx = tx;
         c->fu_ty = ty;
@@ -800,6 +802,11 @@ int fused_setup( cfb_ctx* c )
     // go last, so that everything before them can run while the ghosts are in flight
     int tiles_x, tiles_y, zc, chunks;
     fused_tiling( c, tiles_x, tiles_y, zc, chunks );
+    {
+        const int rc = ensure_partials( c, (long long)tiles_x * tiles_y * chunks );
+        if ( rc )
+            return rc;
+    }
     std::vector<int> inner, outer;
     for ( int ch = 0; ch < chunks; ++ch )
         for ( int ty = 0; ty < tiles_y; ++ty )
@@ -903,7 +910,7 @@ int launch_cg_fused( cfb_ctx* c, int which )
     {
         if ( !c->d_units || c->n_units != total )
         {
-            cfb_fail( c, CFB_ERR_INVALID, "fused unit list not built" );
+            note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "fused unit list not built" ) );
             return 0;
         }
         a.unit_base = which == 1 ? 0 : c->n_interior;

@@ -64,6 +64,7 @@ struct StencilArgs
     CgState* S;
     double* partials;
     int tiles_x, tiles_y, zc, hx;
+    int pstride; // entries per value in the partial-sum scratch (cfb_ctx::partials_cap)
 };
 
 // MODE 0: q = A p, sum p.q (CG kernel 4).
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     if ( MODE == 0 )
     {
         dd_t vals[1] = { acc };
-        if ( block_reduce_finalize<C::NT, 1>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
+        if ( block_reduce_finalize<C::NT, 1>( vals, a.partials, a.pstride, &a.S->ticket[1] ) )
         {
             if ( tid == 0 )
                 publish_pAp( a.S, vals[0] );
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
                 __threadfence_system();
         }
         dd_t vals[2] = { acc, acc2 };
-        if ( block_reduce_finalize<C::NT, 2>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
+        if ( block_reduce_finalize<C::NT, 2>( vals, a.partials, a.pstride, &a.S->ticket[1] ) )
         {
             if ( tid == 0 )
             {
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__( 256, 4 )
         }
     }
     dd_t vals[1] = { acc };
-    if ( block_reduce_finalize<256, 1>( vals, a.partials, CFB_MAX_PARTIALS, &a.S->ticket[1] ) )
+    if ( block_reduce_finalize<256, 1>( vals, a.partials, a.pstride, &a.S->ticket[1] ) )
     {
         if ( threadIdx.x == 0 )
             publish_pAp( a.S, vals[0] );
@@ -501,23 +502,31 @@ static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullp
     a.r = c->cg_r;
     a.q = c->cg_q;
     a.S = c->d_state;
-    a.partials = c->d_partials;
     a.hx = 16;
     const int tx = c->st_variant == 1 ? 64 : c->st_tx;
     const int ty = c->st_variant == 1 ? 8 : c->st_ty;
+    if ( tx < 2 || ty < 1 )
+    {
+        note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "unsupported stencil tile configuration" ) );
+        return 0;
+    }
     a.tiles_x = ( g.n[0] + tx - 1 ) / tx;
     a.tiles_y = ( g.n[1] + ty - 1 ) / ty;
-    int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
-    // keep the number of CTAs (== partial sums) within the scratch buffer
-    while ( (long long)a.tiles_x * a.tiles_y * ( ( g.n[2] + zc - 1 ) / zc ) > CFB_MAX_PARTIALS )
-        zc *= 2;
+    const int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
     a.zc = zc;
-    const int grid = a.tiles_x * a.tiles_y * ( ( g.n[2] + zc - 1 ) / zc );
+    // one block per unit, one partial sum per block: the scratch follows the unit count (large cross-sections,
+    // e.g. two-dimensional grids beyond 2048^2, have more than CFB_MAX_PARTIALS tiles in a single plane)
+    const long long units = (long long)a.tiles_x * a.tiles_y * ( ( g.n[2] + zc - 1 ) / zc );
+    if ( note_rc( c, ensure_partials( c, units ) ) )
+        return 0;
+    a.partials = c->d_partials;
+    a.pstride = c->partials_cap;
+    const int grid = (int)units;
     if ( c->st_variant == 1 )
     {
         if ( mode != 0 )
         {
-            cfb_fail( c, CFB_ERR_INVALID, "the LDG stencil variant has no phase A' form" );
+            note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "the LDG stencil variant has no phase A' form" ) );
             return 0;
         }
         stencil7_dot_ldg<<<grid, 256, 0, c->stream>>>( g, c->op, c->cg_p, a );
@@ -545,7 +554,7 @@ static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullp
     case 1280804:
         return launch_tma<TileCfg<128, 8, 4>>( c, a, grid, mode, pf );
     default:
-        cfb_fail( c, CFB_ERR_INVALID, "unsupported stencil tile configuration" );
+        note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "unsupported stencil tile configuration" ) );
         return 0;
     }
 }

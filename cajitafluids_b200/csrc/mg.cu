@@ -1275,6 +1275,7 @@ int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     long long launches = 0;
 
     int nl = 0; // launches counted by the helpers
+    c->sticky_rc = 0;
     mgcg_init_kernel<<<grid, NT, 0, c->stream>>>( L, c->rhs, c->lhs, c->cg_r, S, c->d_partials, fixed );
     MG_TRY( mg_global_sum( c, 0, &nl ) );
     mgcg_check0_kernel<<<1, 1, 0, c->stream>>>( S, c->cfg.cg_tolerance, c->cfg.cg_stop_rule == CFB_STOP_REL );
@@ -1299,6 +1300,11 @@ int mg_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
         if ( c->cfg.use_nccl )
             MG_TRY( halo_exchange_cells( c, c->cg_p, 1 ) );
         launches += launch_stencil_dot( c );
+        if ( c->sticky_rc ) // the stencil launcher refused its tile configuration
+        {
+            cudaStreamSynchronize( c->stream );
+            return take_sticky_rc( c );
+        }
         if ( c->cfg.use_nccl )
             MG_TRY( cg_global_sum( c, 0 ) );
         mgcg_axpy_kernel<<<grid, NT, 0, c->stream>>>( L, c->cg_p, c->cg_q, c->lhs, c->cg_r, S, c->d_partials );

@@ -15,6 +15,16 @@ def rel_l2(a, b):
     return nd / nb
 
 
+def eigen_tol(n, dim=3):
+    """Bound on the relative L2 error of A p against lambda p for the smoothest non-constant Neumann eigenvector
+    p = prod cos(2 pi (g + 1/2) / n) of the (2 dim + 1)-point operator in double arithmetic.  The row sum
+    diag * p - sum of neighbours cancels to lambda / diag = dim (2 - 2 cos(2 pi / n)) / (2 dim) ~ (2 pi / n)^2 / 2
+    of its terms, so the rounding error relative to the result grows like n^2 (4.6e-13 at 256^3, 2.6e-12 at 512^3
+    measured): a fixed bound is wrong at full size.  8 eps (2 dim) / (dim (2 - 2 cos(2 pi / n))), i.e. 2.4e-11 at
+    n = 512 — checked against plain numpy in tests/test_oracle_kat.py::test_eigenvector_bound_scales_with_n."""
+    return 8.0 * np.finfo(np.float64).eps * (2 * dim) / (dim * (2.0 - 2.0 * np.cos(2.0 * np.pi / n)))
+
+
 def fields_of(dim):
     return [K.QUANTITY, K.U, K.V] + ([K.W] if dim == 3 else [])
 

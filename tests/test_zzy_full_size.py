@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from cajitafluids_b200 import config as K
-from helpers import make_cfg, rel_l2
+from helpers import make_cfg, rel_l2, eigen_tol
 
 N = int(os.environ.get("CFB_FULL_N", "512"))
 
@@ -26,7 +26,7 @@ def test_operator_and_cg_properties_at_full_size():
     gpu.stencil_dot(1)
     h, dt, _ = gpu.scalars()
     lam = dt / (cfg.density * h * h) * 3 * (2 - 2 * np.cos(np.pi * 2 / n))
-    assert rel_l2(gpu.get(K.CG_Q), lam * p) < 1e-12
+    assert rel_l2(gpu.get(K.CG_Q), lam * p) < eigen_tol(n)
     p.fill(1.0)
     gpu.set(K.CG_P, p)
     gpu.stencil_dot(1)

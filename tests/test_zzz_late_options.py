@@ -70,3 +70,66 @@ def test_cuda_advection_in_entity_tiles(dim, cells, kw):
     for f in fields_of(dim) + [K.PRESSURE]:
         assert np.array_equal(g.get(f), o.get(f)), f
     g.close()
+
+
+@pytest.mark.gpu
+def test_two_dimensional_grids_with_more_tiles_than_the_minimum_scratch():
+    """Round-1 host crash (SIGFPE in the tiling loops once one x-y plane had more than 4096 tiles: any 2-D grid
+    beyond ~2048^2, the reference's own dimensionality — src/Solver.hpp:50-55).  4096 x 2304: 32 x 144 tiles of
+    128 x 16 (phase B), 64 x 144 of 64 x 16 (plain stencil, phase A'), every CG form, with and without the
+    ghost-plane loads, against the oracle bit for bit."""
+    from cajitafluids_b200 import Solver
+    cells = (4096, 2304)
+    cfg = make_cfg(2, cells, box=box_of(cells), fixed_iters=6)
+    g, o = Solver(cfg), Oracle(cfg)
+    for s in (g, o):
+        s.add_inputs()
+    ref = None
+    for flat in (0, 1):
+        g.set_tuning("flat_2d", flat)
+        for variant in (1, 2, 0):
+            g.set_tuning("cg_variant", variant)
+            g.build_rhs()
+            res = g.pcg_solve()
+            if ref is None:
+                o.build_rhs()
+                ref = (o.pcg_solve(), o.get(K.PRESSURE))
+            assert res == ref[0], (flat, variant)
+            assert np.array_equal(g.get(K.PRESSURE), ref[1]), (flat, variant)
+    g.close()
+    o.close()
+
+
+@pytest.mark.gpu
+def test_two_dimensional_8192_squared():
+    """The probe size of bench.py (8192^2 = the cell count of 406^3): 64 x 512 = 32768 units in one plane.  The
+    three CG forms and the FLAT instantiations agree with one another bit for bit, the operator has its
+    eigenvector (size-independent checks: the oracle's 23 ghosted arrays would take 12 GB of host memory)."""
+    from cajitafluids_b200 import Solver
+    from helpers import eigen_tol, rel_l2
+    n = 8192
+    cfg = make_cfg(2, n, fixed_iters=20)
+    g = Solver(cfg)
+    ax = np.cos(np.pi * 2 * (np.arange(n) + 0.5) / n)
+    p = ax[:, None] * ax[None, :]
+    g.set(K.CG_P, p.reshape(g.shape(K.CG_P)))
+    g.stencil_dot(1)
+    h, dt, _ = g.scalars()
+    lam = dt / (cfg.density * h * h) * 2 * (2 - 2 * np.cos(np.pi * 2 / n))
+    assert rel_l2(g.get(K.CG_Q).reshape(n, n), lam * p) < eigen_tol(n, 2)
+    del p
+    g.fill_synthetic_velocity(0)
+    ref = None
+    for flat in (0, 1):
+        g.set_tuning("flat_2d", flat)
+        for variant in (1, 2, 0):
+            g.set_tuning("cg_variant", variant)
+            g.build_rhs()
+            it, res = g.pcg_solve()
+            x = g.get(K.PRESSURE)
+            assert it == 20 and np.isfinite(res) and res > 0
+            if ref is None:
+                ref = (res, x)
+            else:
+                assert res == ref[0] and np.array_equal(x, ref[1]), (flat, variant)
+    g.close()

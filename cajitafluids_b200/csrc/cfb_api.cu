@@ -101,6 +101,11 @@ void timer_stop( cfb_ctx* c, int slot )
     c->ev_pending[slot] = true;
 }
 
+int check_cuda( cfb_ctx* c, cudaError_t e )
+{
+    return e == cudaSuccess ? CFB_OK : cfb_fail( c, CFB_ERR_CUDA, cudaGetErrorString( e ) );
+}
+
 int check_async( cfb_ctx* c, const char* what )
 {
     cudaError_t e = cudaGetLastError();
@@ -171,6 +176,37 @@ int enqueue_iteration( cfb_ctx* c )
         const bool peer = cg_peer_mode( c );
         if ( e )
             cudaEventRecord( e[0], c->stream );
+        if ( peer_overlapped( c ) )
+        {
+            // Overlapped exchange.  Main stream: phase A (its last block runs the (r.z, r.r) mailboxes) ->
+            // interior units of phase B -> [ghosts have landed] -> boundary units (their last block runs the p.Ap
+            // mailboxes).  Side stream: the faces of r under the interior units, the faces of the new search
+            // direction under the next phase A and interior units.
+            // Nobody overwrites a ghost layer that may still be read.  A rank stores its r faces after its own
+            // phase A, which it enters only behind the p.Ap mailboxes of the previous iteration, i.e. after every
+            // rank's boundary units — the readers of the old r ghosts — are done.  It stores the faces of the new
+            // search direction after its boundary units, hence behind the (r.z, r.r) mailboxes of this iteration,
+            // i.e. after every rank's boundary units of the previous iteration — the last readers of that
+            // buffer's ghosts (the direction is double-buffered).  The x staging slots (one for r, one per
+            // direction buffer) follow the same argument: the receiver scatters a slot before its boundary units.
+            n += launch_cg_rupdate_mail( c );
+            note_rc( c, check_cuda( c, cudaEventRecord( c->ev_phase[0], c->stream ) ) );
+            if ( e )
+            {
+                cudaEventRecord( e[1], c->stream );
+                cudaEventRecord( e[2], c->stream );
+            }
+            note_rc( c, peer_faces_async( c, 0, -1, c->ev_phase[0] ) );
+            n += launch_cg_fused( c, 1 );
+            note_rc( c, peer_faces_join( c ) );
+            n += launch_cg_fused_mail( c, 2 );
+            note_rc( c, check_cuda( c, cudaEventRecord( c->ev_phase[1], c->stream ) ) );
+            note_rc( c, peer_faces_async( c, 1, c->pcur ^ 1, c->ev_phase[1] ) );
+            cg_select_p( c, c->pcur ^ 1 );
+            if ( e )
+                cudaEventRecord( e[3], c->stream );
+            return n;
+        }
         const bool fusedA = peer && c->peer_fused; // exchange inside phase A / A'
         if ( c->cg_variant == 2 )
         {
@@ -285,6 +321,7 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     // error goes back to the caller instead of a wrong x with CFB_OK
     auto bail = [&]() -> int {
         const int rc = take_sticky_rc( c );
+        peer_faces_join( c );
         cudaStreamSynchronize( c->stream );
         c->ktimed = 0;
         return rc;
@@ -323,6 +360,7 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
             pending = 1;
         }
     }
+    note_rc( c, peer_faces_join( c ) ); // overlapped exchange: the side stream's last transfers
     if ( c->cg_variant >= 1 )
         launches += launch_cg_finish( c );
     CFB_CUDA( c, cudaMemcpyAsync( c->h_state, c->d_state, STATE_HEAD, cudaMemcpyDeviceToHost, c->stream ) );
@@ -565,7 +603,12 @@ int cfb_create( const cfb_config* cfg, cfb_ctx** out )
     s.quantity = cfg->inflow_quantity;
 
     CFB_CUDA( c, cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) );
-    CFB_CUDA( c, cudaStreamCreateWithFlags( &c->comm_stream, cudaStreamNonBlocking ) );
+    {
+        // the side stream carries the exchanges that run under compute kernels: its blocks go first
+        int lo_prio = 0, hi_prio = 0;
+        CFB_CUDA( c, cudaDeviceGetStreamPriorityRange( &lo_prio, &hi_prio ) );
+        CFB_CUDA( c, cudaStreamCreateWithPriority( &c->comm_stream, cudaStreamNonBlocking, hi_prio ) );
+    }
     for ( auto& e : c->ev )
         CFB_CUDA( c, cudaEventCreate( &e ) );
 
@@ -656,6 +699,9 @@ int cfb_destroy( cfb_ctx* c )
     if ( c->h_state )
         cudaFreeHost( c->h_state );
     for ( auto& e : c->ev )
+        if ( e )
+            cudaEventDestroy( e );
+    for ( cudaEvent_t e : { c->ev_phase[0], c->ev_phase[1], c->ev_ghost } )
         if ( e )
             cudaEventDestroy( e );
     for ( auto& row : c->kev )
@@ -1056,6 +1102,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->advect_tile = value != 0;
     else if ( k == "peer_fused" )
         c->peer_fused = value != 0;
+    else if ( k == "peer_overlap" )
+        c->peer_overlap = value != 0;
     else if ( k == "mg_graph" )
         return mg_set_graph( c, value != 0 );
     else if ( k == "mg_coarse_kernel" )

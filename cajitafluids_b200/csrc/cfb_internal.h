@@ -67,6 +67,7 @@ struct CgState
     double thresh;                  // absolute threshold in use
     double alpha;                   // two-kernel form: alpha of the running iteration (phase A -> B)
     unsigned long long seq[2];      // peer-memory exchange: publications so far of (pAp | rz_new, rr)
+    unsigned long long fseq[2];     // overlapped exchange: face transfers completed so far of (r | the search direction)
     int xerror;                     // sticky: a peer never published (timeout)
     int pad1;
     int iter;                       // completed iterations (kernel-1 executions)
@@ -89,6 +90,9 @@ struct PeerMail
 {
     double v[2][CFB_MAX_PEERS][4];
     unsigned long long seq[2][CFB_MAX_PEERS];
+    // overlapped exchange (halo.cu: cg_face_kernel): slot [0: r, 1: search direction][my face the writer sits on] =
+    // number of face transfers of that kind the neighbour has completed into my ghost layers / staging areas
+    unsigned long long fseq[2][6];
     // multigrid ghost exchanges (mg.cu): slot [writer rank] = number of exchanges whose stores that rank has
     // completed into my arrays
     unsigned long long mseq[CFB_MAX_PEERS];
@@ -147,6 +151,13 @@ struct cfb_ctx
     // "peer_fused" tuning key (several blocks, NVLink peer memory): phase B stores its block-face cells into the
     // neighbours' ghost layers itself and its last block runs the mailbox exchange — no exchange kernel after it
     bool peer_fused = false;
+    // "peer_overlap" tuning key (several blocks, NVLink peer memory, two-kernel form): the reduction of each phase
+    // runs in the last block of the compute kernel (mailboxes), the faces travel on the side stream under the
+    // interior units of phase B (r) and under the next phase A (search direction); boundary units run last
+    bool peer_overlap = false;
+    cudaEvent_t ev_phase[2] = { nullptr, nullptr }; // main stream: phase A / phase B of the running iteration done
+    cudaEvent_t ev_ghost = nullptr;                 // side stream: every face transfer enqueued so far has landed
+    bool side_busy = false;                         // face transfers enqueued since the last join
 
     // two-kernel CG iteration (kernels_fused.cu): tensor maps of cg_r / cg_p, tiling, unit list
     // 1 = two kernels / 72 B per cell (default), 0 = three kernels / 88 B, 2 = two kernels / 64 B: q is
@@ -291,6 +302,15 @@ inline bool cg_peer_mode( const cfb_ctx* c )
 {
     return c->cfg.use_nccl && c->peer_ok && c->use_peer && c->cg_variant >= 1;
 }
+// peer mode with the exchange taken off the critical path (cfb_api.cu: enqueue_iteration); the 72-byte form only
+// (phase A' of the 64-byte form reads the ghosts of the search direction), not with the staging-area reads or the
+// two-dimensional FLAT kernels (no mailbox instantiation of those)
+inline bool peer_xstaged( const cfb_ctx* c );
+inline bool peer_overlapped( const cfb_ctx* c )
+{
+    return cg_peer_mode( c ) && c->peer_overlap && c->cg_variant == 1 && !c->peer_fused && !c->peer_xstage_reads &&
+           !( c->g.D == 2 && c->flat_2d );
+}
 // peer mode with x neighbours and tiles that end exactly on the block: phase B reads its x ghosts
 // straight from the staging areas, so the iterations never scatter them into the ghost columns
 inline bool peer_xstaged( const cfb_ctx* c )
@@ -310,6 +330,8 @@ int fused_setup( cfb_ctx* c );                // tensor maps of cg_r, cg_p + the
 int launch_cg_rupdate( cfb_ctx* c );          // phase A: r -= alpha q, sum r^2, sum r.Minv r
 int launch_cg_fused( cfb_ctx* c, int which ); // phase B: 0 = all units, 1 = interior, 2 = boundary
 int launch_cg_fused_peer( cfb_ctx* c );        // phase B + its ghost / reduction exchange in one kernel (peer_fused)
+int launch_cg_rupdate_mail( cfb_ctx* c );      // phase A, its last block runs the mailbox reduction (peer_overlap)
+int launch_cg_fused_mail( cfb_ctx* c, int which ); // phase B units (1 interior / 2 boundary), the same (peer_overlap)
 int launch_cg_rupdate_peer( cfb_ctx* c );      // phase A + its ghost / reduction exchange in one kernel (peer_fused)
 int launch_stencil_rupdate_peer( cfb_ctx* c ); // phase A' of the 64-byte iteration, the same
 int launch_cg_finish( cfb_ctx* c );
@@ -338,6 +360,12 @@ int halo_cells_end( cfb_ctx* c );
 // received x faces from the staging area into the ghost columns — not needed when phase B reads them
 // from staging, always needed for the plain stencil at the start of a solve)
 int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpack );
+// overlapped exchange: on the side stream, once `after` (an event of the main stream) has happened, store my
+// boundary layers of cg_r (kind 0) or of search-direction buffer `pbuf` (kind 1) into the neighbours' ghost
+// layers, tell each neighbour, wait until each neighbour has told me, scatter the x faces I received; then record
+// c->ev_ghost.  No reduction here: the compute kernels' last blocks run the mailboxes (device_peer.cuh).
+int peer_faces_async( cfb_ctx* c, int kind, int pbuf, cudaEvent_t after );
+int peer_faces_join( cfb_ctx* c ); // main stream waits for everything peer_faces_async has enqueued
 int halo_exchange_fields( cfb_ctx* c, int version );             // width-h exchange of q,u,v,w
 int halo_sendrecv_slots( cfb_ctx* c, const size_t counts[6], cudaStream_t st ); // d_halo_send/recv[s] <-> nbr[s]
 // NVLink peer memory for further arrays: every rank passes its `count` device allocations (same count, same

@@ -115,6 +115,18 @@ __device__ __forceinline__ void peer_mail_exchange( CgState* S, const PeerFusedA
     }
 }
 
+// no faces: the kernel only runs the mailbox reduction in its last block ("peer_overlap": the faces travel on the
+// side stream, halo.cu: cg_face_kernel)
+inline void peer_mail_only( cfb_ctx* c, PeerFusedArgs& pf )
+{
+    pf.nface = 0;
+    pf.rank = c->cfg.world_rank;
+    pf.world = c->cfg.world_size;
+    pf.timeout_cycles = 20000000000ll; // ~10 s at 1.9 GHz: a dead peer must not hang the GPU
+    for ( int r = 0; r < pf.world; ++r )
+        pf.mail[r] = c->mail[r];
+}
+
 // the faces of block `c` towards its neighbours, as destinations of `array` (one of the neighbours' mapped copies)
 inline void peer_faces( cfb_ctx* c, PeerFusedArgs& pf, double* const dst_of_side[6] )
 {

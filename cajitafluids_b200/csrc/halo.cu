@@ -376,6 +376,89 @@ __global__ void __launch_bounds__( 256 )
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Overlapped exchange ("peer_overlap"): the ghost stores of cg_xchg_kernel without its reduction, run on the side
+// stream while the main stream computes cells that do not read ghosts.
+//   1. every block stores a share of my boundary layers into the neighbours' ghost layers / x staging areas;
+//   2. system fence, ticket; the block that draws the last one
+//   3. tells every face neighbour "transfer number n of this kind has landed" (its mailbox, slot of the face I sit on),
+//   4. waits until every face neighbour has told me the same (bounded spin).
+// What follows on the side stream (the x scatter, the event the boundary units wait for) therefore sees complete
+// ghost layers.  Why nobody overwrites a layer that is still being read: cfb_api.cu, enqueue_iteration.
+struct FaceArgs
+{
+    int nface;
+    XFace f[6];
+    PeerMail* nbr_mail[6]; // mailbox of the neighbour behind face i of this launch
+    int nbr_slot[6];       // ... and the slot I write there: the neighbour's face that looks at me
+    int my_slot[6];        // the slot of my own mailbox that neighbour writes
+    PeerMail* mail_self;
+    CgState* S;
+    unsigned int* ticket;
+    int kind;
+    long long timeout_cycles;
+};
+
+__global__ void __launch_bounds__( 256 )
+    cg_face_kernel( const __grid_constant__ Geo g, const __grid_constant__ FaceArgs a )
+{
+    for ( int fi = 0; fi < a.nface; ++fi )
+    {
+        const XFace& f = a.f[fi];
+        const long long total = (long long)f.ext[0] * f.ext[1] * f.ext[2];
+        for ( long long t = blockIdx.x * 256ll + threadIdx.x; t < total; t += (long long)gridDim.x * 256 )
+        {
+            const int i = (int)( t % f.ext[0] ) + f.lo[0];
+            const int j = (int)( ( t / f.ext[0] ) % f.ext[1] ) + f.lo[1];
+            const int k = (int)( t / ( (long long)f.ext[0] * f.ext[1] ) ) + f.lo[2];
+            const double v = f.src[geo_off( g, i, j, k )];
+            if ( f.packed )
+                f.dst[t] = v;
+            else
+                f.dst[f.dorigin + (long long)( k - f.shift[2] ) * f.dsz + (long long)( j - f.shift[1] ) * f.dsy +
+                      ( i - f.shift[0] )] = v;
+        }
+    }
+    __threadfence_system();
+    __shared__ bool s_last;
+    __syncthreads();
+    if ( threadIdx.x == 0 )
+    {
+        const unsigned t = atomicAdd( a.ticket, 1u );
+        s_last = ( t == gridDim.x - 1 );
+    }
+    __syncthreads();
+    if ( !s_last )
+        return;
+    __threadfence_system();
+    CgState* S = a.S;
+    __shared__ unsigned long long s_seq;
+    if ( threadIdx.x == 0 )
+    {
+        *a.ticket = 0u;
+        s_seq = ++S->fseq[a.kind];
+    }
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    if ( threadIdx.x < a.nface )
+    {
+        *reinterpret_cast<volatile unsigned long long*>( &a.nbr_mail[threadIdx.x]->fseq[a.kind][a.nbr_slot[threadIdx.x]] ) = seq;
+        if ( !S->xerror )
+        {
+            const long long t0 = clock64();
+            while ( ld_volatile_u64( &a.mail_self->fseq[a.kind][a.my_slot[threadIdx.x]] ) < seq )
+            {
+                if ( clock64() - t0 > a.timeout_cycles )
+                {
+                    S->xerror = 1;
+                    break;
+                }
+            }
+        }
+    }
+    __threadfence_system();
+}
+
 // what every rank tells the others at start-up
 struct PeerInfo
 {
@@ -398,8 +481,9 @@ int peer_setup( cfb_ctx* c )
         return CFB_OK;
     CFB_CUDA( c, cudaMalloc( &c->mail_self, sizeof( PeerMail ) ) );
     CFB_CUDA( c, cudaMemset( c->mail_self, 0, sizeof( PeerMail ) ) );
-    CFB_CUDA( c, cudaMalloc( &c->d_xticket, sizeof( unsigned int ) ) );
-    CFB_CUDA( c, cudaMemset( c->d_xticket, 0, sizeof( unsigned int ) ) );
+    // [0]: cg_xchg_kernel (main stream), [1]: cg_face_kernel (side stream)
+    CFB_CUDA( c, cudaMalloc( &c->d_xticket, 2 * sizeof( unsigned int ) ) );
+    CFB_CUDA( c, cudaMemset( c->d_xticket, 0, 2 * sizeof( unsigned int ) ) );
     // [2 sides][r, pbuf 0, pbuf 1] slots of ny * nz doubles each (see xslot)
     const size_t xstage_elems = (size_t)6 * c->g.n[1] * c->g.n[2];
     CFB_CUDA( c, cudaMalloc( &c->xstage_self, xstage_elems * sizeof( double ) ) );
@@ -478,6 +562,12 @@ int peer_setup( cfb_ctx* c )
     CFB_CUDA( c, cudaMemcpy( &flag, d_flag, sizeof( double ), cudaMemcpyDeviceToHost ) );
     cudaFree( d_flag );
     c->peer_ok = flag == 0.0;
+    if ( c->peer_ok && !c->ev_ghost ) // events of the overlapped exchange (cfb_api.cu: enqueue_iteration)
+    {
+        CFB_CUDA( c, cudaEventCreateWithFlags( &c->ev_ghost, cudaEventDisableTiming ) );
+        CFB_CUDA( c, cudaEventCreateWithFlags( &c->ev_phase[0], cudaEventDisableTiming ) );
+        CFB_CUDA( c, cudaEventCreateWithFlags( &c->ev_phase[1], cudaEventDisableTiming ) );
+    }
     return CFB_OK;
 }
 
@@ -581,6 +671,88 @@ int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpac
         cg_xunpack_kernel<<<ug, 256, 0, c->stream>>>( g, u );
         c->stats.kernel_launches += 1;
     }
+    return CFB_OK;
+}
+
+int peer_faces_async( cfb_ctx* c, int kind, int pbuf, cudaEvent_t after )
+{
+    const Geo& g = c->g;
+    FaceArgs a{};
+    a.S = c->d_state;
+    a.ticket = c->d_xticket + 1;
+    a.kind = kind;
+    a.mail_self = c->mail_self;
+    a.timeout_cycles = 20000000000ll; // ~10 s at 1.9 GHz: a dead peer must not hang the GPU
+    double* mine = kind == 0 ? c->cg_r : c->cg_pbuf[pbuf];
+    const int stage_kind = kind == 0 ? 0 : 1 + pbuf;
+    long long cells = 0;
+    XUnpackArgs u{};
+    for ( int s = 0; s < 2 * g.D; ++s )
+    {
+        if ( c->nbr[s] < 0 )
+            continue;
+        const int d = s / 2, side = s % 2;
+        const int i = a.nface++;
+        a.nbr_mail[i] = c->mail[c->nbr[s]];
+        a.nbr_slot[i] = s ^ 1;
+        a.my_slot[i] = s;
+        XFace& f = a.f[i];
+        f.src = mine;
+        f.dst = kind == 0 ? c->peer_r[s] : c->peer_p[pbuf][s];
+        f.dorigin = c->peer_origin[s];
+        f.dsy = c->peer_sy[s];
+        f.dsz = c->peer_sz[s];
+        for ( int e = 0; e < 3; ++e )
+        {
+            f.lo[e] = 0;
+            f.ext[e] = g.n[e];
+            f.shift[e] = 0;
+        }
+        f.ext[d] = 1;
+        if ( side == 0 )
+        {
+            f.lo[d] = 0; // my first layer -> the low neighbour's high ghost (index n_peer)
+            f.shift[d] = -c->peer_n[s][d];
+        }
+        else
+        {
+            f.lo[d] = g.n[d] - 1; // my last layer -> the high neighbour's low ghost (index -1)
+            f.shift[d] = g.n[d];
+        }
+        if ( d == 0 )
+        {
+            // x faces travel packed (see peer_exchange) and are scattered by the receiver behind the flag wait
+            f.packed = 1;
+            f.dst = c->peer_xstage[s] + xslot( g, 1 - side, stage_kind );
+            u.src[u.n] = c->xstage_self + xslot( g, side, stage_kind );
+            u.dst[u.n] = mine;
+            u.col[u.n] = side == 0 ? -1 : g.n[0];
+            ++u.n;
+        }
+        cells += (long long)f.ext[0] * f.ext[1] * f.ext[2];
+    }
+    CFB_CUDA( c, cudaStreamWaitEvent( c->comm_stream, after, 0 ) );
+    const int grid = (int)std::min<long long>( std::max<long long>( ( cells + 1023 ) / 1024, 1 ), 2ll * c->sm_count );
+    cg_face_kernel<<<grid, 256, 0, c->comm_stream>>>( g, a );
+    c->stats.kernel_launches += 1;
+    if ( u.n > 0 )
+    {
+        const long long tot = (long long)g.n[1] * g.n[2] * u.n;
+        const int ug = (int)std::min<long long>( ( tot + 255 ) / 256, 4ll * c->sm_count );
+        cg_xunpack_kernel<<<ug, 256, 0, c->comm_stream>>>( g, u );
+        c->stats.kernel_launches += 1;
+    }
+    CFB_CUDA( c, cudaEventRecord( c->ev_ghost, c->comm_stream ) );
+    c->side_busy = true;
+    return CFB_OK;
+}
+
+int peer_faces_join( cfb_ctx* c )
+{
+    if ( !c->side_busy )
+        return CFB_OK;
+    CFB_CUDA( c, cudaStreamWaitEvent( c->stream, c->ev_ghost, 0 ) );
+    c->side_busy = false;
     return CFB_OK;
 }
 

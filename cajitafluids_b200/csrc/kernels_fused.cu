@@ -871,6 +871,14 @@ int launch_cg_rupdate_peer( cfb_ctx* c )
     return launch_rupdate_impl( c, &pf );
 }
 
+// Phase A whose last block runs the mailbox reduction of (r.z, r.r); no faces ("peer_overlap")
+int launch_cg_rupdate_mail( cfb_ctx* c )
+{
+    PeerFusedArgs pf{};
+    peer_mail_only( c, pf );
+    return launch_rupdate_impl( c, &pf );
+}
+
 int launch_cg_finish( cfb_ctx* c )
 {
     cg_finish_kernel<<<1, 1, 0, c->stream>>>( c->d_state );
@@ -879,7 +887,7 @@ int launch_cg_finish( cfb_ctx* c )
 
 // phase B over all units (which = 0), or over the device unit list `c->d_units` split into
 // interior units [0, n_interior) (which = 1) and boundary units [n_interior, n_units) (which = 2).
-int launch_cg_fused( cfb_ctx* c, int which )
+static int launch_cg_fused_impl( cfb_ctx* c, int which, const PeerFusedArgs* pf )
 {
     FusedArgs a{};
     a.x = c->lhs;
@@ -919,7 +927,19 @@ int launch_cg_fused( cfb_ctx* c, int which )
         if ( grid == 0 )
             return 0;
     }
-    return dispatch_fused( c, a, grid );
+    return dispatch_fused( c, a, grid, pf );
+}
+
+int launch_cg_fused( cfb_ctx* c, int which ) { return launch_cg_fused_impl( c, which, nullptr ); }
+
+// Phase B units whose last block (the one that draws the last of ALL the phase's tickets, i.e. a block of the
+// launch that comes last) runs the mailbox reduction of p.Ap; no faces ("peer_overlap").  Interior units read
+// no ghosts and are launched plain; the caller launches the boundary units through here.
+int launch_cg_fused_mail( cfb_ctx* c, int which )
+{
+    PeerFusedArgs pf{};
+    peer_mail_only( c, pf );
+    return launch_cg_fused_impl( c, which, &pf );
 }
 
 // Phase B over all units with the exchange inside (PeerFusedArgs): replaces

@@ -1493,6 +1493,22 @@ int cfo_num_threads( void )
 #endif
 }
 
+// Number of OpenMP threads for everything that follows (n < 1: all the cores the process may run on).  The
+// benchmark's CPU arm calls it: a launcher such as torchrun exports OMP_NUM_THREADS=1, which would time this
+// restatement of the reference on a single core.
+int cfo_set_num_threads( int n )
+{
+#ifdef _OPENMP
+    if ( n < 1 )
+        n = omp_get_num_procs();
+    omp_set_num_threads( n );
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 // Matrix / preconditioner read-back for the known-answer tests (ghosted layout).
 int cfo_matrix_ptr( cfo_ctx* c, double** A, double** Minv, int* nst )
 {

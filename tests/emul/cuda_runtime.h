@@ -202,6 +202,16 @@ inline cudaError_t cudaStreamCreateWithFlags( cudaStream_t* s, unsigned )
     *s = reinterpret_cast<cudaStream_t>( std::malloc( 1 ) );
     return cudaSuccess;
 }
+inline cudaError_t cudaDeviceGetStreamPriorityRange( int* lo, int* hi )
+{
+    *lo = 0;
+    *hi = -1;
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamCreateWithPriority( cudaStream_t* s, unsigned flags, int )
+{
+    return cudaStreamCreateWithFlags( s, flags );
+}
 inline cudaError_t cudaStreamDestroy( cudaStream_t s )
 {
     std::free( s );

@@ -408,9 +408,11 @@ int launch_cg_finish( cfb_ctx* c )
 // phase B: convergence test ; x += alpha p ; beta ; p_new = M^-1 r + beta p (also on the one-cell ghost ring,
 // recomputed from the ghosts of r and of the old p, never stored there) ; q = A p_new ; sum p.q
 // which: 0 = all units, 1 = "interior" (everything here), 2 = "boundary" (nothing left)
+// (overlapped exchange: the ghosts arrive between the two launches, so there "interior" is nothing and the
+// boundary launch, launch_cg_fused_mail below, does everything)
 int launch_cg_fused( cfb_ctx* c, int which )
 {
-    if ( which == 2 )
+    if ( which == 2 || ( which == 1 && peer_overlapped( c ) ) )
         return 0;
     const Geo& g = c->g;
     const OpConst& op = c->op;
@@ -477,6 +479,21 @@ int launch_cg_fused( cfb_ctx* c, int which )
         S->pAp = acc.hi + acc.lo;
     S->rz_old = S->rz_new;
     return 1;
+}
+// "peer_overlap" with the plain-loop stand-ins: the kernel followed by the reduction-only exchange its last block runs
+int launch_cg_rupdate_mail( cfb_ctx* c )
+{
+    const int n = launch_cg_rupdate( c );
+    peer_exchange( c, 1, false, -1, false );
+    return n;
+}
+int launch_cg_fused_mail( cfb_ctx* c, int which )
+{
+    if ( which != 2 )
+        return 0;
+    const int n = launch_cg_fused( c, 0 );
+    peer_exchange( c, 0, false, -1, false );
+    return n;
 }
 // "peer_fused" with the plain-loop stand-ins: the unfused pair it replaces
 int launch_cg_fused_peer( cfb_ctx* c )

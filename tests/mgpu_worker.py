@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="only the PCG section, three exchange modes")
     ap.add_argument("--mg", action="store_true", help="only the multigrid-preconditioner section")
     ap.add_argument("--fused", action="store_true", help="only the PCG section, exchange inside the kernels (peer_fused)")
+    ap.add_argument("--overlap", action="store_true",
+                    help="the PCG section and whole steps with the overlapped exchange (peer_overlap) on and off")
     args = ap.parse_args()
     rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
     torch.cuda.set_device(local)
@@ -70,6 +72,10 @@ def main():
         section_5(args, rank, blocks, gcfg, rank_cfg, rng, check)
     elif args.fused:
         section_3(args, rank, gcfg, rank_cfg, rng, check)
+    elif args.overlap:
+        section_3(args, rank, gcfg, rank_cfg, rng, check)
+        for on in (1, 0):
+            section_4(args, rank, gcfg, rank_cfg, check, tune={"peer_overlap": on})
     else:
         if not args.quick:
             sections_1_2(args, rank, gcfg, rank_cfg, rng, check)
@@ -159,6 +165,15 @@ def section_3(args, rank, gcfg, rank_cfg, rng, check):
                    "fused_ty": 8}),
                  ("two-kernel without a stored q, exchange inside the kernels",
                   {"cg_variant": 2, "peer_halo": 1, "peer_fused": 1})]
+    if args.overlap:
+        modes = [("overlapped exchange (faces on the side stream, reductions in the kernels' last blocks)",
+                  {"cg_variant": 1, "peer_halo": 1, "peer_overlap": 1}),
+                 ("overlapped exchange, small tiles",
+                  {"cg_variant": 1, "peer_halo": 1, "peer_overlap": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64,
+                   "fused_ty": 8}),
+                 ("exchange kernel after each phase", {"cg_variant": 1, "peer_halo": 1, "peer_overlap": 0}),
+                 ("overlapped exchange requested, 64-byte form (falls back to the exchange kernel)",
+                  {"cg_variant": 2, "peer_halo": 1, "peer_overlap": 1})]
     for name, tune in modes:
         gpu = Solver(rank_cfg())
         for k, v in tune.items():
@@ -185,10 +200,12 @@ def section_3(args, rank, gcfg, rank_cfg, rng, check):
 
 
 
-def section_4(args, rank, gcfg, rank_cfg, check):
+def section_4(args, rank, gcfg, rank_cfg, check, tune=None):
     # 4. whole timesteps of the default inflow problem -----------------------------------------------------
     ora = Oracle(gcfg())
     gpu = Solver(rank_cfg())
+    for k, v in (tune or {}).items():
+        gpu.set_tuning(k, v)
     ora.setup()
     gpu.setup()
     for _ in range(args.steps):
@@ -201,7 +218,7 @@ def section_4(args, rank, gcfg, rank_cfg, check):
         # blocks far from the inflow may hold (near-)zero fields: compare against the global norm too
         gl = np.linalg.norm(ora.get(f).ravel())
         ea = np.linalg.norm((gpu.get(f) - ora.get(f)[block_slices(gpu, f)]).ravel()) / max(gl, 1e-300)
-        check(f"step field {f}", min(e, ea) < 1e-10, f"rel l2 {e} (vs global norm {ea})")
+        check(f"step field {f} {tune or ''}", min(e, ea) < 1e-10, f"rel l2 {e} (vs global norm {ea})")
     gpu.close()
     ora.close()
 

@@ -44,10 +44,18 @@ def load():
                                     C.POINTER(C.c_int)]
         d.cfo_set_callbacks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         d.cfo_num_threads.restype = C.c_int
+        d.cfo_set_num_threads.argtypes = [C.c_int]
+        d.cfo_set_num_threads.restype = C.c_int
         d.cfo_set_accumulation.argtypes = [C.c_void_p, C.c_int]
         d.cfo_set_mg_max_levels.argtypes = [C.c_void_p, C.c_int]
         d.cfo_mg_num_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     return _lib
+
+
+def set_num_threads(n=0):
+    """OpenMP threads of the oracle from here on (0: every core the process may run on, whatever
+    OMP_NUM_THREADS a launcher exported); returns the count in use."""
+    return load().dll.cfo_set_num_threads(int(n))
 
 
 GATHER_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int)

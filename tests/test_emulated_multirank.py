@@ -380,6 +380,10 @@ MODES = [("peer, small tiles", True, {"fused_stages": 4, "fused_zc": 4, "fused_t
          ("peer, exchange inside phase B, small tiles", True,
           {"peer_fused": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
          ("peer, exchange inside the kernels, 64-byte iteration", True, {"peer_fused": 1, "cg_variant": 2}),
+         ("peer, faces on the side stream under interior work, reductions in the kernels' last blocks", True,
+          {"peer_overlap": 1}),
+         ("peer, overlapped exchange, small tiles", True,
+          {"peer_overlap": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
          ("NCCL, interior overlapped with the r/p halo", False, {"overlap_halo": 1}),
          ("NCCL, overlap, small tiles, several boundary units", False,
           {"overlap_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
@@ -454,6 +458,67 @@ def test_decomposed_solve_writes_one_file_set_per_block_and_one_master(emul, tmp
 
 # (world, blocks, fixed iterations: 0 = to convergence, once — fibers are slow)
 GRIDS_FUSED = [(2, None, 0), (2, (2, 1, 1), 14), (2, (1, 2, 1), 14), (4, (2, 2, 1), 14), (6, (1, 3, 2), 14), (8, None, 14)]
+
+
+@pytest.mark.parametrize("world,blocks,fixed", GRIDS_FUSED)
+def test_overlapped_exchange_on_every_block_grid(emul, world, blocks, fixed):
+    """"peer_overlap": the reduction of each phase in the last block of its compute kernel (mailboxes), the faces on
+    the side stream (cg_face_kernel: neighbour-to-neighbour arrival flags), boundary units of phase B last.  Converged
+    and repeated solves, switching between the schedules from solve to solve (mailbox and face sequence numbers,
+    p buffers carry over), x / y / z / uneven splits."""
+    if not emul.tma:
+        pytest.skip("unit lists exist in the TMA kernels only")
+    cfg = cfg3(cells=(23, 20, 21), fixed_iters=fixed)
+    ora = Oracle(cfg)
+    rng = np.random.default_rng(83)
+    vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
+    for f, a in vel.items():
+        ora.set(f, a)
+    ora.add_inputs()
+    ora.build_rhs()
+    io, ro = ora.pcg_solve()
+    po, ho = ora.get(K.PRESSURE), ora.residual_history()
+
+    def body(ctx, rank):
+        for f, a in vel.items():
+            ctx.set(f, a[block_slices(ctx, f)])
+        out = []
+        for overlap in (1, 0, 1, 1):
+            ctx.set_tuning("peer_overlap", overlap)
+            ctx.add_inputs()
+            ctx.build_rhs()
+            ig, rg = ctx.pcg_solve()
+            out.append((ig, rg, np.array_equal(ctx.get(K.PRESSURE), po[block_slices(ctx, K.PRESSURE)]),
+                        np.array_equal(ctx.residual_history(), ho)))
+        return ctx.stats()["peer_mode"], out
+
+    for peer, out in run_ranks(emul, cfg, world, body, blocks, peer=True):
+        assert peer == 1
+        assert out == [(io, ro, True, True)] * 4, out
+
+
+def test_overlapped_exchange_whole_steps(emul):
+    """(same bar as test_peer_memory_exchange_steps_and_fixed_iterations)"""
+    if not emul.tma:
+        pytest.skip("unit lists exist in the TMA kernels only")
+    cfg = cfg3(cells=(32, 24, 16), fixed_iters=20)
+    ora = Oracle(cfg)
+    ora.setup()
+    want0 = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
+    ora.step()
+    want = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
+    gl = {f: max(np.linalg.norm(want[f].ravel()), 1e-300) for f in want}
+
+    def body(ctx, rank):
+        ctx.set_tuning("peer_overlap", 1)
+        ctx.setup()
+        exact = [f for f in want0 if not np.array_equal(ctx.get(f), want0[f][block_slices(ctx, f)])]
+        ctx.step()
+        err = {f: float(np.linalg.norm((ctx.get(f) - want[f][block_slices(ctx, f)]).ravel()) / gl[f]) for f in want}
+        return exact, err
+
+    for exact, err in run_ranks(emul, cfg, 8, body, None, peer=True):
+        assert exact == [] and max(err.values()) < 1e-12, (exact, err)
 
 
 @pytest.mark.parametrize("world,blocks,fixed", GRIDS_FUSED)

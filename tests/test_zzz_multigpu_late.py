@@ -24,3 +24,13 @@ def test_exchange_inside_the_kernels_matches_single_block_oracle(world, blocks):
     iteration.  Every CG form, bit for bit against the single-block oracle."""
     extra = ["--fused"] + (["--blocks"] + [str(b) for b in blocks] if blocks else [])
     _run_worker(world, extra, cells=(128, 24, 20) if blocks == (2, 1, 1) else (48, 40, 36))
+
+
+@pytest.mark.parametrize("world,blocks", [(2, None), (2, (2, 1, 1)), (2, (1, 2, 1)), (4, None), (8, None)])
+def test_overlapped_exchange_matches_single_block_oracle(world, blocks):
+    """`peer_overlap`: the faces travel on the side stream under the interior units of phase B (r) and under the next
+    phase A (search direction), the reductions run in the last blocks of the two compute kernels, boundary units
+    last.  PCG bit for bit and whole steps against the single-block oracle, with the schedule on and off.
+    (tests/test_emulated_multirank.py::test_overlapped_exchange_on_every_block_grid on the CPU.)"""
+    extra = ["--overlap"] + (["--blocks"] + [str(b) for b in blocks] if blocks else [])
+    _run_worker(world, extra, cells=(128, 24, 20) if blocks == (2, 1, 1) else (48, 40, 36))

@@ -32,6 +32,8 @@ BYTES_STENCIL = 16  # read p, write q                       
 #   0: three kernels  axpy+norms 48 | p-update 24 | stencil7+dot 16            (kernels_cg/stencil.cu)
 #   1: two kernels    r-update+norms 24 | x-update + p-update + stencil7 + dot 48   (kernels_fused.cu)
 #   2: two kernels    stencil7 recomputed + r-update+norms 24 | x-update + p-update + stencil7 + dot, q not stored 40
+# the exchange schedule of the CG iterations the library picks on several GPUs (cfb_internal.h: peer_overlap)
+DEFAULT_PEER_OVERLAP = False
 BYTES_ITER = {0: 88, 1: 72, 2: 64}
 BYTES_DOMINANT = {0: 16, 1: 48, 2: 40}
 KERNEL_DOMINANT = {0: "stencil7_dot_tma", 1: "cg_fused_kernel (x-update + p-update + stencil7 + p.Ap dot)",
@@ -99,71 +101,124 @@ def block_grid(n):
     return px, py, pz
 
 
-def make_config(args, rank, world, blocks):
+def make_config(args, rank, world, blocks, scaling=None, cells=None, gravity=0.0, iters=None):
     from cajitafluids_b200 import default_config
-    n = args.cells
-    if args.scaling == "weak":
+    n = cells or args.cells
+    if (scaling or args.scaling) == "weak":
         gcells = tuple(n * b for b in blocks)
     else:
         gcells = (n, n, n)
-    cfg = default_config(3, gcells, box=tuple(c / 512.0 for c in gcells))  # h = 1/512 fixed
+    # h = 1/512 fixed; gravity g: body force (0, -g, 0) as examples/advection.cpp:452
+    cfg = default_config(3, gcells, box=tuple(c / 512.0 for c in gcells), gravity=gravity)
     bz, r = divmod(rank, blocks[0] * blocks[1])
     by, bx = divmod(r, blocks[0])
     for d, (b, bid) in enumerate(zip(blocks, (bx, by, bz))):
         cfg.ranks_per_dim[d] = b
         cfg.block_id[d] = bid
     cfg.world_rank, cfg.world_size = rank, world
-    cfg.cg_fixed_iters = args.iters
+    cfg.cg_fixed_iters = args.iters if iters is None else iters
     cfg.cg_print_level = 0
     return cfg, gcells
 
 
-def cpu_baseline(args, iters_sample, gcells_1gpu):
-    """The CPU restatement of the reference (oracle/, stored-coefficient matrix, 4-kernel CG, OpenMP)
-    on a bounded sample: `iters_sample` fixed CG iterations of the same 1-GPU workload."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import numpy as np
-    import psutil
-    from cajitafluids_b200 import config as K, default_config
-    from oracle_api import Oracle
+def workload_name(args):
+    return f"pcg_{args.cells}cubed_fixed{args.iters}_jacobi_synthetic_divergence"
 
-    n = gcells_1gpu[0]
-    need = 23 * (n + 6) ** 3 * 8
-    avail = psutil.virtual_memory().available
-    note = ""
-    while need > 0.6 * avail and n > 64:
-        n //= 2
+
+class CpuArm:
+    """The CPU restatement of the reference (oracle/: stored-coefficient matrix, 4-kernel / 3-reduction CG, OpenMP)
+    on the same 1-GPU workload, with every host core whatever OMP_NUM_THREADS the launcher exported (torchrun sets
+    it to 1).  One context for the whole arm; a timed step is a solve of `iters_sample` fixed iterations and is
+    normalised per iteration: the per-solve set-up (cg_init and the first A p, which the GPU arm amortises over its
+    100 iterations per step) is measured with one-iteration solves and taken out."""
+
+    def __init__(self, cells):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import numpy as np
+        import psutil
+        import oracle_api
+        from cajitafluids_b200 import config as K, default_config
+
+        self.cores = oracle_api.set_num_threads(0)
+        n = cells
         need = 23 * (n + 6) ** 3 * 8
-        note = f" (host RAM too small for the full grid, sampled at {n}^3)"
-    cfg = default_config(3, n, box=n / 512.0)
-    cfg.cg_fixed_iters = iters_sample
-    o = Oracle(cfg)
-    o.set_accumulation(False)  # plain double sums: the reference's arithmetic and cost
-    # same synthetic MAC velocity family as the GPU arm (sin/cos product, SURVEY §8d)
-    h = o.cell_size
-    ax = [np.arange(n + 1) * h, (np.arange(n) + 0.5) * h]
-    L = n * h
-    for d, f in enumerate((K.U, K.V, K.W)):
-        g = [np.sin(np.pi * ax[0] / L) if e == d else np.cos(2 * np.pi * ax[1] / L) for e in range(3)]
-        val = g[2][:, None, None] * g[1][None, :, None] * g[0][None, None, :]
-        sl = [slice(None)] * 3
-        sl[2 - d] = 0
-        val[tuple(sl)] = 0.0
-        sl[2 - d] = -1
-        val[tuple(sl)] = 0.0
-        o.set(f, val)
-        del val
-    o.build_rhs()
-    t0 = time.perf_counter()
-    o.pcg_solve()
-    dt = time.perf_counter() - t0
-    cores = o.num_threads()
-    o.close()
-    return {"value": iters_sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{iters_sample} fixed Jacobi-PCG iterations at {n}^3 FP64 on the host cores{note}; "
-                      "CPU restatement of the reference (Kokkos/Cajita unavailable): stored 7-coefficient "
-                      "matrix + M^-1 array, 4 kernels / 3 reductions per iteration, OpenMP",
-            "seconds": dt}, n
+        avail = psutil.virtual_memory().available
+        self.note = ""
+        while need > 0.6 * avail and n > 64:
+            n //= 2
+            need = 23 * (n + 6) ** 3 * 8
+            self.note = f" (host RAM too small for the full grid, sampled at {n}^3)"
+        self.n = n
+        cfg = default_config(3, n, box=n / 512.0)
+        cfg.cg_fixed_iters = 1
+        o = oracle_api.Oracle(cfg)
+        o.set_accumulation(False)  # plain double sums: the reference's arithmetic and cost
+        # same synthetic MAC velocity family as the GPU arm (sin/cos product, SURVEY 8d)
+        h = o.cell_size
+        ax = [np.arange(n + 1) * h, (np.arange(n) + 0.5) * h]
+        L = n * h
+        for d, f in enumerate((K.U, K.V, K.W)):
+            g = [np.sin(np.pi * ax[0] / L) if e == d else np.cos(2 * np.pi * ax[1] / L) for e in range(3)]
+            val = g[2][:, None, None] * g[1][None, :, None] * g[0][None, None, :]
+            sl = [slice(None)] * 3
+            sl[2 - d] = 0
+            val[tuple(sl)] = 0.0
+            sl[2 - d] = -1
+            val[tuple(sl)] = 0.0
+            o.set(f, val)
+            del val
+        o.build_rhs()
+        self.o = o
+
+    def solve(self, iters):
+        self.o.set_fixed_iters(iters)
+        self.o.build_rhs()  # (also resets the pressure: the checker's solve starts from the lhs it finds)
+        t0 = time.perf_counter()
+        self.o.pcg_solve()
+        return time.perf_counter() - t0
+
+    def measure(self, iters_sample, steps, warmup, budget_s):
+        """-> dict(t_iter, t_setup, step_seconds[], iters_sample, steps).  Stops adding steps when `budget_s` is
+        used up (never below one timed step)."""
+        t_all = time.perf_counter()
+        t1 = min(self.solve(1) for _ in range(2))
+        probe = self.solve(2)
+        t_it0 = max(probe - t1, 1e-6)
+        # a step must leave room for all K + W of them inside the budget
+        left = budget_s - (time.perf_counter() - t_all)
+        fit = int((left / max(1, steps + warmup) - t1) / t_it0)
+        iters_sample = max(2, min(iters_sample, fit))
+        for _ in range(warmup):
+            self.solve(iters_sample)
+        secs = []
+        for _ in range(steps):
+            secs.append(self.solve(iters_sample))
+            if time.perf_counter() - t_all > budget_s and secs:
+                break
+        t_iter = [(t - t1) / (iters_sample - 1) for t in secs]
+        mean_it = sum(t_iter) / len(t_iter)
+        return {"t_iter": mean_it, "t_setup": max(t1 - mean_it, 0.0), "step_seconds": secs,
+                "iters_sample": iters_sample, "steps": len(secs)}
+
+    def describe(self, m):
+        return (f"{m['steps']} solves of {m['iters_sample']} fixed Jacobi-PCG iterations at {self.n}^3 FP64 on "
+                f"{self.cores} host cores{self.note}, per-iteration rate with the per-solve set-up "
+                f"({m['t_setup']:.2f} s: cg_init + first A p, from one-iteration solves) taken out; CPU restatement of "
+                "the reference (Kokkos/Cajita unavailable): stored 7-coefficient matrix + M^-1 array, 4 kernels / "
+                "3 reductions per iteration, OpenMP")
+
+    def close(self):
+        self.o.close()
+
+
+def cpu_baseline(args):
+    """bounded sample for the main arm's line (N = 1 only)."""
+    arm = CpuArm(args.cells)
+    m = arm.measure(10, 2, 0, 40.0)
+    out = {"value": 1.0 / m["t_iter"], "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.describe(m),
+           "value_with_setup": m["iters_sample"] * m["steps"] / sum(m["step_seconds"])}
+    arm.close()
+    return out
 
 
 def run_reference(args):
@@ -171,28 +226,30 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.cells
-    iters_sample = max(2, min(args.iters, 5))
-    t_all = time.perf_counter()
-    vals = []
-    base = None
-    for s in range(args.warmup + args.steps):
-        base, nn = cpu_baseline(args, iters_sample, (n, n, n))
-        if s >= args.warmup:
-            vals.append(base["seconds"])
-        if time.perf_counter() - t_all > 240:  # keep the whole arm within a few minutes
-            break
-    steps_done = max(1, len(vals))
-    total = sum(vals) if vals else base["seconds"]
-    value = iters_sample * steps_done / total
-    base["value"] = value
+    arm = CpuArm(n)
+    # the whole arm (K + W steps) within a few minutes: ~150 s of timed solves plus the set-up of the context
+    m = arm.measure(min(args.iters, 20), args.steps, args.warmup, 150.0)
+    value = 1.0 / m["t_iter"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    base = {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.describe(m)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps_done, "warmup": args.warmup, "ms_per_step": 1e3 * total / steps_done,
+            "steps": m["steps"], "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(m["step_seconds"]) / m["steps"],
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"pcg_{n}cubed_fixed_iters_jacobi", "cells_per_gpu": [n, n, n],
-                       "cg_iters_per_step": iters_sample, "note": "bounded sample of the same workload"},
-            "cpu_baseline": {k: v for k, v in base.items() if k != "seconds"},
+            "config": {"workload": workload_name(args), "cells_per_gpu": [n, n, n] if args.scaling == "weak" else None,
+                       "cg_iters_per_step": args.iters,
+                       "cg_iters_timed_per_step": m["iters_sample"],
+                       "normalisation": "iterations/s = 1 / per-iteration time; a step of this arm is a bounded sample "
+                                        "of the workload's step (fewer iterations of the same solve), its per-solve "
+                                        "set-up taken out",
+                       "unit_of_work": "one CG iteration over one %d^3 block; the host cores work on one block at a "
+                                       "time, so this figure does not depend on the number of GPUs of the other arm "
+                                       "(whose value sums block-iterations over ranks)" % n,
+                       "launched_world_size": world},
+            "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    arm.close()
     print(json.dumps(line), flush=True)
 
 
@@ -263,18 +320,15 @@ def mg_side_measurements(args):
     os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
-def side_probes(args):
-    """`--side probes` (child process of the main arm): the opt-in kernel options that were written after the
-    round's GPU budget was spent, timed so that the next round starts from numbers — the advection kernel with
-    rows vs entity tiles ("advect_tile") on the bench grid, and two-dimensional fixed-iteration solves with and
-    without the ghost-plane loads ("flat_2d").  Prints one JSON object with the keys to merge into `extra`."""
+def probe_advect(args):
+    """`--side advect` (child process of the main arm): the advection kernel with rows vs entity tiles
+    ("advect_tile") on the bench grid.  Prints one JSON object with the keys to merge into `extra`."""
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
     import torch
     from cajitafluids_b200 import Solver, default_config
     torch.cuda.set_device(0)
-    out = {}
     adv = {}
     for tile in (0, 1):
         try:
@@ -293,7 +347,19 @@ def side_probes(args):
         except Exception as e:  # noqa: BLE001
             adv["tile%d_error" % tile] = repr(e)[:200]
     adv["note"] = "advection kernel (q, u, v, w in one launch) at %d^3, rows (tile0) vs 32x2x2 entity tiles (tile1)" % args.cells
-    out["advect_tile_probe"] = adv
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps({"advect_tile_probe": adv}) + "\n").encode())
+
+
+def probe_flat2d(args):
+    """`--side flat2d` (child process of the main arm): two-dimensional fixed-iteration solves (the reference's own
+    dimensionality) with and without the ghost-plane loads ("flat_2d"), both two-kernel CG forms."""
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    from cajitafluids_b200 import Solver, default_config
+    torch.cuda.set_device(0)
     n2 = args.cells * 16 if args.cells >= 64 else args.cells  # 8192^2 for the 512^3 bench
     flat = {"cells": [n2, n2], "iters": 50}
     for fl in (0, 1):
@@ -314,9 +380,161 @@ def side_probes(args):
                 s.close()
             except Exception as e:  # noqa: BLE001
                 flat[key] = {"error": repr(e)[:200]}
-    out["flat_2d_probe"] = flat
     sys.stdout.flush()
-    os.write(json_fd, (json.dumps(out) + "\n").encode())
+    os.write(json_fd, (json.dumps({"flat_2d_probe": flat}) + "\n").encode())
+
+
+def run_child(extra, key, argv, timeout):
+    """a side measurement in a child process with a time limit; a failure is reported under ITS OWN key."""
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, capture_output=True, text=True, timeout=timeout)
+        if p.returncode != 0 or not p.stdout.strip():
+            raise RuntimeError("child exit %d: %s" % (p.returncode, p.stderr.strip()[-300:]))
+        extra.update(json.loads(p.stdout.strip().splitlines()[-1]))
+    except Exception as e:  # noqa: BLE001
+        extra[key] = {"error": repr(e)[:400]}
+
+
+def multi_gpu_extras(args, s, extra, dist, torch, np, rank, world, local, blocks, units, resid, fallback, barrier,
+                     all_ranks_ok):
+    """Several GPUs, measured in the same run so that the driver's scaling runs record them at every N:
+    extra.exchange_schedules  the headline workload with each exchange schedule of the CG iterations;
+    extra.strong_scaling      BASELINE configs[3]: the 1-GPU grid (cells^3 GLOBAL) block-decomposed over the N GPUs;
+    extra.decomposition_parity  a small block-decomposed run (solve + 3 whole steps, 96^3 global) against the
+                              single-block CPU oracle on rank 0: the analogue of the reference's only distributed
+                              test (tests/tstProblemManager.cpp:61-98), for the peer path and the NCCL path."""
+    from cajitafluids_b200 import Solver, config as K
+    from cajitafluids_b200.distributed import attach_nccl
+
+    def timed(solver, steps=3, warm=2):
+        err, ms_sum, res = None, 0.0, None
+        try:
+            for _ in range(warm):
+                solver.pcg_fixed(args.iters)
+            for _ in range(steps):
+                m, res = solver.pcg_fixed(args.iters)
+                ms_sum += m
+        except Exception as e:  # noqa: BLE001
+            err = e
+        if not all_ranks_ok(err is None):
+            return {"error": repr(err)[:300] if err is not None else "another rank failed"}
+        t = torch.tensor([ms_sum], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"iterations_per_s": steps * args.iters / (float(t[0]) * 1e-3), "final_residual": res, "steps": steps}
+
+    # 1. exchange schedules on the headline workload (same right-hand side: equal residuals bit for bit)
+    sched = {}
+    if s.stats()["peer_mode"] and not fallback:
+        for name, tune in (("peer_exchange_kernel_after_each_phase", {"peer_overlap": 0}),
+                           ("peer_overlapped", {"peer_overlap": 1}),
+                           ("nccl_sendrecv_allgather", {"peer_halo": 0})):
+            try:
+                for k, v in tune.items():
+                    s.set_tuning(k, v)
+                r = timed(s)
+                if "iterations_per_s" in r:
+                    r = {"value": r["iterations_per_s"] * units, "unit": UNIT,
+                         "same_residual_as_headline": r["final_residual"] == resid, "steps": r["steps"]}
+                sched[name] = r
+            except Exception as e:  # noqa: BLE001
+                sched[name] = {"error": repr(e)[:300]}
+        s.set_tuning("peer_halo", 1)
+        s.set_tuning("peer_overlap", int(DEFAULT_PEER_OVERLAP))
+        extra["exchange_schedules"] = sched
+
+    # 2. strong scaling (BASELINE configs[3]): cells^3 global over all ranks
+    if args.scaling == "weak":
+        try:
+            cfg_s, g_s = make_config(args, rank, world, blocks, scaling="strong")
+            cfg_s.device_id = local
+            attach_nccl(cfg_s, dist)
+            ss = Solver(cfg_s)
+            ss.fill_synthetic_velocity(0)
+            ss.build_rhs()
+            r = timed(ss, steps=5, warm=3)
+            if "iterations_per_s" in r:
+                r.update({"global_cells": list(g_s), "blocks": list(blocks), "cg_iters_per_step": args.iters,
+                          "cells_local": int(np.prod(ss.owned_extent(K.QUANTITY))), "peer_mode": ss.stats()["peer_mode"],
+                          "peer_overlap": ss.stats()["peer_overlap"],
+                          "note": "global CG iterations/s of the fixed %d^3 problem on %d GPUs; divide by the N = 1 "
+                                  "headline value for the speed-up" % (args.cells, world)})
+            extra["strong_scaling"] = r
+            ss.close()
+        except Exception as e:  # noqa: BLE001
+            extra["strong_scaling"] = {"error": repr(e)[:300]}
+
+    # 3. decomposition parity against the single-block oracle
+    try:
+        extra["decomposition_parity"] = decomposition_parity(dist, torch, np, rank, world, local, blocks)
+    except Exception as e:  # noqa: BLE001
+        extra["decomposition_parity"] = {"error": repr(e)[:300]}
+
+
+def decomposition_parity(dist, torch, np, rank, world, local, blocks, n=96, steps=3):
+    from cajitafluids_b200 import Solver, config as K, default_config
+    from cajitafluids_b200.distributed import attach_nccl, decompose
+    gcfg = default_config(3, n)  # the default inflow problem, reference tol / max_iter
+    fields = [K.QUANTITY, K.U, K.V, K.W, K.PRESSURE]
+    # rank 0: the single-block oracle, every host core; its fields and iteration counts go to every rank
+    shapes = {f: ((n + 1 if f == K.W else n), (n + 1 if f == K.V else n), (n + 1 if f == K.U else n)) for f in fields}
+    ref = {f: torch.empty(shapes[f], dtype=torch.float64, device="cuda") for f in fields}
+    its = torch.zeros(steps + 1, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_api
+        oracle_api.set_num_threads(0)
+        o = oracle_api.Oracle(gcfg)
+        o.setup()
+        cnt = [o.stats()["cg_iterations"]]
+        for _ in range(steps):
+            o.step()
+            cnt.append(o.stats()["cg_iterations"])
+        for f in fields:
+            ref[f].copy_(torch.from_numpy(np.ascontiguousarray(o.get(f))))
+        its.copy_(torch.tensor(np.diff([0] + cnt), dtype=torch.float64))
+        o.close()
+    for f in fields:
+        dist.broadcast(ref[f], src=0)
+    dist.broadcast(its, src=0)
+    want_its = [int(v) for v in its.tolist()]
+    out = {"global_cells": [n] * 3, "blocks": list(blocks), "steps": steps, "oracle_cg_iterations": want_its,
+           "checker": "single-block CPU oracle on rank 0 (oracle/, exact sums)"}
+    for name, tune in (("peer", {}), ("nccl", {"peer_halo": 0})):
+        cfg = decompose(gcfg, rank, world, blocks)
+        cfg.device_id = local
+        attach_nccl(cfg, dist)
+        g = Solver(cfg)
+        for k, v in tune.items():
+            g.set_tuning(k, v)
+        g.setup()
+        cnt = [g.stats()["cg_iterations"]]
+        for _ in range(steps):
+            g.step()
+            cnt.append(g.stats()["cg_iterations"])
+        got_its = [int(v) for v in np.diff([0] + cnt)]
+        off = g.global_offset()
+        num = torch.zeros(len(fields), dtype=torch.float64, device="cuda")
+        den = torch.zeros(len(fields), dtype=torch.float64, device="cuda")
+        same = torch.ones(1, dtype=torch.float64, device="cuda")
+        for i, f in enumerate(fields):
+            mine = g.get(f)
+            ext = mine.shape
+            want = ref[f][off[2]:off[2] + ext[0], off[1]:off[1] + ext[1], off[0]:off[0] + ext[2]].cpu().numpy()
+            num[i] = float(((mine - want) ** 2).sum())
+            den[i] = float((want ** 2).sum())
+            if not np.array_equal(mine, want):
+                same[0] = 0.0
+        dist.all_reduce(num)
+        dist.all_reduce(den)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        rel = [float((a / b) ** 0.5) if b > 0 else (0.0 if a == 0 else float("inf")) for a, b in zip(num.tolist(), den.tolist())]
+        out[name] = {"peer_mode": g.stats()["peer_mode"], "peer_overlap": g.stats()["peer_overlap"],
+                     "cg_iterations": got_its, "iters_equal": got_its == want_its,
+                     "iters_within_1": all(abs(a - b) <= 1 for a, b in zip(got_its, want_its)),
+                     "max_rel_l2": max(rel), "rel_l2": dict(zip(["q", "u", "v", "w", "p"], rel)),
+                     "bit_identical": bool(float(same[0]) == 1.0)}
+        g.close()
+    return out
 
 
 def main():
@@ -337,14 +555,16 @@ def main():
                     help="1 = two-kernel iteration (72 B/cell, default), 0 = three kernels (88 B), 2 = two kernels without a stored q (64 B)")
     ap.add_argument("--tune", action="append", default=[], help="key=value passed to cfb_set_tuning")
     ap.add_argument("--no-probe", action="store_true", help="skip the side measurement of the 64-byte CG form")
-    ap.add_argument("--side", default=None, choices=["mg", "probes"], help=argparse.SUPPRESS)
+    ap.add_argument("--side", default=None, choices=["mg", "advect", "flat2d"], help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.side == "mg":
         return mg_side_measurements(args)
-    if args.side == "probes":
-        return side_probes(args)
+    if args.side == "advect":
+        return probe_advect(args)
+    if args.side == "flat2d":
+        return probe_flat2d(args)
 
     # stdout carries exactly ONE JSON line: everything else that libraries print there (NCCL's version
     # banner, torch warnings) is sent to stderr at file-descriptor level
@@ -454,6 +674,20 @@ def main():
                 "avg_launch_ms": t_st,
                 "iteration": {"form": "two kernels" if v >= 1 else "three kernels", "bytes_per_cell": biter,
                               "achieved_gbs": it_ach, "frac": it_ach / peak}}
+    if world > 1:
+        # several GPUs: the events bracket each phase INCLUDING the exchange that follows its compute kernel; the
+        # exposed exchange time is bracketed separately, so the kernel-only figure is stated next to it
+        xa, xb = st["ms_k_exch_a"] / kt, st["ms_k_exch_b"] / kt
+        k_only = max(t_st - xb, 1e-9)
+        roofline.update({"avg_launch_ms": k_only, "achieved": ncell_local * bdom / (k_only * 1e-3) / 1e9,
+                         "frac": ncell_local * bdom / (k_only * 1e-3) / 1e9 / peak,
+                         "exchange": {"schedule": "overlapped: faces on the side stream, reductions in the compute "
+                                                  "kernels' last blocks (their barrier wait is inside the kernel times)"
+                                      if st["peer_overlap"] else
+                                      ("one exchange kernel after each phase (NVLink peer stores + mailbox reduction)"
+                                       if st["peer_mode"] else "NCCL send/recv before phase B, all-gather after each phase"),
+                                      "exposed_after_phase_a_ms": xa, "exposed_after_phase_b_ms": xb,
+                                      "phase_a_kernel_ms": st["ms_k_axpy"] / kt - xa, "phase_b_kernel_ms": k_only}})
     if v >= 1:
         roofline["iteration"].update({"rupdate_ms": st["ms_k_axpy"] / kt, "fused_ms": t_st})
     else:
@@ -463,6 +697,9 @@ def main():
     if os.path.exists(tr):
         try:
             roofline["traffic"] = json.load(open(tr)).get(f"cg_variant{v}_dominant_{args.cells}")
+            roofline["traffic_source"] = ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                          "ncu --set full capture of this kernel at this size (a committed constant, "
+                                          "not measured in this run)")
         except Exception:
             pass
     # the plain stencil7 + dot kernel (16 B/cell: CG kernel 4 on its own, used for the first q = A p
@@ -512,28 +749,54 @@ def main():
     # whole timesteps (advect + inputs + projection) on the bench grid itself, at every N: the
     # projection runs the same fixed number of CG iterations as the headline (the reference's own
     # tol/max_iter cannot converge at 512^3)
+    if world > 1 and not args.no_probe and not args.tune:
+        multi_gpu_extras(args, s, extra, dist, torch, np, rank, world, local, blocks, units, resid, fallback, barrier,
+                         all_ranks_ok)
     if not args.no_timestep:
-        s.setup()
-        s.step()
-        barrier()
-        t0 = time.perf_counter()
-        nst = 3
-        for _ in range(nst):
-            s.step()
-        barrier()
-        dt_steps = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt_steps], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt_steps = float(t[0])
-        st2 = s.stats()
-        extra["timesteps_per_s_bench_grid"] = {
-            "global_cells": list(gcells), "value": nst / dt_steps, "cg_iters_per_step": args.iters,
-            "interp_order": 3, "ms_advect": st2["ms_advect"] / (nst + 1), "note": "projection capped at the "
-            "headline's fixed CG iteration count; wall clock between barriers, max over ranks; inflow source on, "
-            "body-force term applied with g = 0 (the default problem; same kernel work as BASELINE configs[4])"}
-    if world == 1 and args.timestep_cells > 0:
+        # BASELINE configs[4]: full timestep (advection + inputs + projection) with inflow source AND body force
+        # (g = 9.8: src/BodyForce.hpp:43-60; the dt clamp then includes sqrt(g h), src/Solver.hpp:96-106), weak
+        # scaled like the headline.  A context of its own: the force and the clamped dt are fixed at creation.
         s.close()
+        s = None
+        try:
+            cfg_t, _ = make_config(args, rank, world, blocks, gravity=9.8)
+            cfg_t.device_id = local
+            if world > 1:
+                from cajitafluids_b200.distributed import attach_nccl
+                attach_nccl(cfg_t, dist)
+            st_ = Solver(cfg_t)
+            st_.set_tuning("cg_variant", args.cg_variant)
+            st_.setup()
+            st_.step()
+            barrier()
+            st_.reset_stats()
+            t0 = time.perf_counter()
+            nst = 3
+            for _ in range(nst):
+                st_.step()
+            barrier()
+            dt_steps = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dt_steps], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt_steps = float(t[0])
+            st2 = st_.stats()
+            extra["timesteps_per_s_bench_grid"] = {
+                "global_cells": list(gcells), "value": nst / dt_steps, "cg_iters_per_step": args.iters,
+                "interp_order": 3, "gravity": 9.8, "dt": st_.dt, "ms_advect": st2["ms_advect"] / nst,
+                "ms_add_inputs": st2["ms_add_inputs"] / nst, "ms_build_rhs": st2["ms_build_rhs"] / nst,
+                "ms_pcg": st2["ms_pcg"] / nst, "ms_apply_pressure": st2["ms_apply_pressure"] / nst,
+                "note": "BASELINE configs[4]: inflow source and body force (0, -9.8, 0) on, dt clamped to "
+                        "h / (|v_in| + sqrt(g h)); projection capped at the headline's fixed CG iteration count (the "
+                        "reference's tol / max_iter cannot converge at this size, SURVEY F5); wall clock between "
+                        "barriers, max over ranks"}
+            st_.close()
+        except Exception as e:  # noqa: BLE001
+            extra["timesteps_per_s_bench_grid"] = {"error": repr(e)[:300]}
+    if world == 1 and args.timestep_cells > 0:
+        if s is not None:
+            s.close()
+            s = None
         from cajitafluids_b200 import default_config
         c2 = default_config(3, args.timestep_cells)
         s2 = Solver(c2)
@@ -609,71 +872,23 @@ def main():
     # kernels were written after the round's GPU budget was spent, and neither a failure nor a hang there may
     # cost the headline line.
     if world == 1 and not args.no_timestep and not args.no_probe:
-        try:
-            s.close()
-        except Exception:  # noqa: BLE001
-            pass
-        try:
-            cmd = [sys.executable, os.path.abspath(__file__), "--side", "mg", "--cells", str(args.cells),
-                   "--timestep-cells", str(args.timestep_cells)]
-            p = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
-            if p.returncode != 0 or not p.stdout.strip():
-                raise RuntimeError("child exit %d: %s" % (p.returncode, p.stderr.strip()[-200:]))
-            extra.update(json.loads(p.stdout.strip().splitlines()[-1]))
-        except Exception as e:  # noqa: BLE001
-            extra["projection_time_to_solution"] = {"error": repr(e)[:300]}
-        # opt-in kernel options written after the GPU budget was spent (side_probes), same arrangement
-        try:
-            cmd = [sys.executable, os.path.abspath(__file__), "--side", "probes", "--cells", str(args.cells)]
-            p = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
-            if p.returncode != 0 or not p.stdout.strip():
-                raise RuntimeError("child exit %d: %s" % (p.returncode, p.stderr.strip()[-200:]))
-            extra.update(json.loads(p.stdout.strip().splitlines()[-1]))
-        except Exception as e:  # noqa: BLE001
-            extra["advect_tile_probe"] = {"error": repr(e)[:300]}
-
-    # extra (several GPUs, NVLink peer memory): the same workload with the ghost / reduction exchanges inside the two
-    # kernels of the iteration ("peer_fused": no exchange launch) — written after the round's GPU budget was spent and
-    # not the default; measured last, so that nothing above depends on it; every rank agrees on the outcome.
-    if world > 1 and st["peer_mode"] and not fallback and args.cg_variant == 1 and not args.no_probe and not args.tune:
-        try:
-            err, ms_f, r_f, r_ref = None, 0.0, None, None
-            try:
-                _, r_ref = s.pcg_fixed(args.iters)  # the default form on the right-hand side as it is now
-                s.set_tuning("peer_fused", 1)
-                for _ in range(2):
-                    s.pcg_fixed(args.iters)
-                for _ in range(3):
-                    m, r_f = s.pcg_fixed(args.iters)
-                    ms_f += m
-            except Exception as e:  # noqa: BLE001
-                err = e
-            try:
-                s.set_tuning("peer_fused", 0)
-            except Exception:  # noqa: BLE001
-                pass
-            if all_ranks_ok(err is None):
-                t = torch.tensor([ms_f], dtype=torch.float64, device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                extra["peer_fused"] = {"value": units * 3 * args.iters / (float(t[0]) * 1e-3), "unit": UNIT, "steps": 3,
-                                       "final_residual": r_f, "same_residual_as_default_form": r_f == r_ref,
-                                       "note": "exchange inside phase A and phase B (no exchange kernel), 3 steps; "
-                                               "not the headline form until it has been profiled"}
-            else:
-                extra["peer_fused"] = {"error": repr(err)[:300] if err is not None else "another rank failed"}
-        except Exception as e:  # noqa: BLE001
-            extra["peer_fused"] = {"error": repr(e)[:300]}
+        run_child(extra, "projection_time_to_solution",
+                  ["--side", "mg", "--cells", str(args.cells), "--timestep-cells", str(args.timestep_cells)], 240)
+        # opt-in kernel options, each in its own child and under its own key
+        run_child(extra, "advect_tile_probe", ["--side", "advect", "--cells", str(args.cells)], 120)
+        run_child(extra, "flat_2d_probe", ["--side", "flat2d", "--cells", str(args.cells)], 180)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_baseline(args, max(2, min(args.iters, 10)), (args.cells,) * 3)
-        cpu.pop("seconds", None)
+        cpu = cpu_baseline(args)
         # the same whole timesteps as extra.timesteps_per_s (default inflow problem, reference tol / max_iter,
         # cubic interpolation) on the host cores: setup, then ONE timed step (bounded: ~600 CG iterations at 128^3)
         if args.timestep_cells > 0:
             try:
                 from cajitafluids_b200 import default_config
                 from oracle_api import Oracle
+                import oracle_api
+                oracle_api.set_num_threads(0)
                 o = Oracle(default_config(3, args.timestep_cells))
                 o.set_accumulation(False)  # plain double sums: the reference's arithmetic and cost
                 o.setup()
@@ -692,7 +907,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"pcg_{args.cells}cubed_fixed{args.iters}_jacobi_synthetic_divergence",
+                "config": {"workload": workload_name(args),
                            "cells_per_gpu": [args.cells] * 3 if args.scaling == "weak" else None,
                            "global_cells": list(gcells), "blocks": list(blocks), "cg_iters_per_step": args.iters,
                            "l2": "inputs larger than L2 (each vector %.2f GB)" % (ncell_local * 8 / 1e9),
@@ -700,6 +915,8 @@ def main():
                            "cg_form": {0: "three kernels, 88 B/cell", 1: "two kernels, 72 B/cell",
                                        2: "two kernels, q not stored, 64 B/cell"}[args.cg_variant],
                            "exchange": ("none (1 GPU)" if world == 1 else
+                                        "NVLink peer stores (cudaIpc): faces on the side stream under interior work, CG "
+                                        "sums through mailboxes in the compute kernels' last blocks" if st["peer_overlap"] else
                                         "NVLink peer stores (cudaIpc), ghosts + CG sums in one kernel per reduction point"
                                         if st["peer_mode"] else "NCCL send/recv + all-gather"),
                            **({"exchange_fallback": fallback} if fallback else {})},

@@ -71,6 +71,9 @@ class Stats(C.Structure):
         ("ms_k_stencil", C.c_double),
         ("k_timed_iters", C.c_int64),
         ("peer_mode", C.c_int64),
+        ("ms_k_exch_a", C.c_double),
+        ("ms_k_exch_b", C.c_double),
+        ("peer_overlap", C.c_int64),
     ]
 
 

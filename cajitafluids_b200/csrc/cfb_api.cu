@@ -193,6 +193,7 @@ int enqueue_iteration( cfb_ctx* c )
             note_rc( c, check_cuda( c, cudaEventRecord( c->ev_phase[0], c->stream ) ) );
             if ( e )
             {
+                cudaEventRecord( e[4], c->stream );
                 cudaEventRecord( e[1], c->stream );
                 cudaEventRecord( e[2], c->stream );
             }
@@ -204,7 +205,10 @@ int enqueue_iteration( cfb_ctx* c )
             note_rc( c, peer_faces_async( c, 1, c->pcur ^ 1, c->ev_phase[1] ) );
             cg_select_p( c, c->pcur ^ 1 );
             if ( e )
+            {
+                cudaEventRecord( e[5], c->stream );
                 cudaEventRecord( e[3], c->stream );
+            }
             return n;
         }
         const bool fusedA = peer && c->peer_fused; // exchange inside phase A / A'
@@ -218,6 +222,8 @@ int enqueue_iteration( cfb_ctx* c )
             n += launch_cg_rupdate_peer( c );
         else
             n += launch_cg_rupdate( c );
+        if ( e )
+            cudaEventRecord( e[4], c->stream );
         if ( fusedA )
             ;
         else if ( peer )
@@ -234,6 +240,8 @@ int enqueue_iteration( cfb_ctx* c )
         else if ( peer )
         {
             n += launch_cg_fused( c, 0 );
+            if ( e )
+                cudaEventRecord( e[5], c->stream );
             note_rc( c, peer_exchange( c, 0, false, c->pcur ^ 1, !peer_xstaged( c ) ) ); // new p faces, pAp -> all
         }
         else if ( c->cfg.use_nccl )
@@ -252,26 +260,37 @@ int enqueue_iteration( cfb_ctx* c )
                 note_rc( c, halo_cells_end( c ) );
                 n += launch_cg_fused( c, 0 );
             }
+            if ( e )
+                cudaEventRecord( e[5], c->stream );
             note_rc( c, cg_global_sum( c, 0 ) );
         }
         else
             n += launch_cg_fused( c, 0 );
         cg_select_p( c, c->pcur ^ 1 ); // phase B wrote the new p into the other buffer
         if ( e )
+        {
+            if ( !( peer || c->cfg.use_nccl ) || ( peer && c->peer_fused ) )
+                cudaEventRecord( e[5], c->stream );
             cudaEventRecord( e[3], c->stream );
+        }
         return n;
     }
     if ( e )
         cudaEventRecord( e[0], c->stream );
     n += launch_cg_axpy( c );
     if ( e )
+    {
+        cudaEventRecord( e[4], c->stream );
         cudaEventRecord( e[1], c->stream );
+    }
     n += launch_cg_pupdate( c );
     if ( e )
         cudaEventRecord( e[2], c->stream );
     if ( c->cfg.use_nccl )
         note_rc( c, halo_exchange_cells( c, c->cg_p, 1 ) );
     n += launch_stencil_dot( c );
+    if ( e )
+        cudaEventRecord( e[5], c->stream );
     if ( c->cfg.use_nccl )
         note_rc( c, cg_global_sum( c, 0 ) );
     if ( e )
@@ -290,6 +309,12 @@ void collect_kernel_times( cfb_ctx* c )
         c->stats.ms_k_axpy += a;
         c->stats.ms_k_pupdate += b;
         c->stats.ms_k_stencil += d;
+        float xa = 0, xb = 0;
+        if ( cudaEventElapsedTime( &xa, c->kev[i][4], c->kev[i][1] ) == cudaSuccess )
+            c->stats.ms_k_exch_a += xa;
+        if ( cudaEventElapsedTime( &xb, c->kev[i][5], c->kev[i][3] ) == cudaSuccess )
+            c->stats.ms_k_exch_b += xb;
+        cudaGetLastError();
         c->stats.k_timed_iters++;
     }
     c->ktimed = 0;
@@ -983,6 +1008,7 @@ int cfb_get_stats( const cfb_ctx* c, cfb_stats* out )
         timer_collect( m, s );
     *out = c->stats;
     out->peer_mode = cg_peer_mode( c ) ? 1 : 0;
+    out->peer_overlap = peer_overlapped( c ) ? 1 : 0;
     return CFB_OK;
 }
 int cfb_reset_stats( cfb_ctx* c )

@@ -180,7 +180,7 @@ struct cfb_ctx
     bool ev_pending[8] = { false };
     bool time_kernels = false;
     int ktimed = 0;
-    cudaEvent_t kev[CFB_KTIMED][4] = { { nullptr } };
+    cudaEvent_t kev[CFB_KTIMED][6] = { { nullptr } }; // A start, A end, B start, B end | A kernel end, B kernel end
     cfb_stats stats{};
     int last_iters = 0;
     double last_resid = 0;

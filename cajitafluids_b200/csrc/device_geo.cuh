@@ -121,7 +121,10 @@ __device__ __forceinline__ double interp_field( const Geo& g, int ent, const dou
         else
             spline3( xl, s0[d], w[d] );
         const int emax = g.n[d] + 2 * g.h + ( ent - 1 == d ? 1 : 0 ) - 1;
-        inside = inside && s0[d] >= 0 && s0[d] + NK - 1 <= emax;
+        // 0 <= s0 and s0 + NK - 1 <= emax, written so that no garbage index (the int conversion of a NaN or of a
+        // huge coordinate, and s0 = int - 1 wrapping around) can pass: such points take the clamped path
+        const int hi = emax - ( NK - 1 );
+        inside = inside && hi >= 0 && (unsigned)s0[d] <= (unsigned)hi;
     }
     double value = 0.0;
     if ( inside )

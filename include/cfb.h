@@ -188,6 +188,13 @@ typedef struct cfb_stats
     /* multi-GPU: 1 = the CG iterations exchange ghosts and sums by direct stores into peer memory over
      * NVLink (cudaIpc mappings), 0 = NCCL send/recv + all-gather (or single GPU) */
     int64_t peer_mode;
+    /* several GPUs, same bracketing: time on the main stream between the end of the phase-A / phase-B compute
+     * kernel and the end of the exchange that follows it (ghost stores + global sums); 0 when the exchange runs
+     * inside / beside the compute kernels ("peer_overlap") — ms_k_axpy and ms_k_stencil include these */
+    double ms_k_exch_a;
+    double ms_k_exch_b;
+    /* 1 = overlapped exchange schedule in use for the CG iterations (see the "peer_overlap" tuning key) */
+    int64_t peer_overlap;
 } cfb_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------ */

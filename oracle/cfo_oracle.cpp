@@ -1493,6 +1493,14 @@ int cfo_num_threads( void )
 #endif
 }
 
+// Fixed-iteration mode of the following solves (0: back to the stopping test); the benchmark's CPU arm times solves
+// of two lengths on one context to separate the per-solve set-up from the per-iteration cost.
+int cfo_set_fixed_iters( cfo_ctx* c, int iters )
+{
+    c->cfg.cg_fixed_iters = iters > 0 ? iters : 0;
+    return CFB_OK;
+}
+
 // Number of OpenMP threads for everything that follows (n < 1: all the cores the process may run on).  The
 // benchmark's CPU arm calls it: a launcher such as torchrun exports OMP_NUM_THREADS=1, which would time this
 // restatement of the reference on a single core.

@@ -67,11 +67,15 @@ def test_bench_line_carries_the_contract_keys():
     assert x["cells_local"] == 32 ** 3 and "timesteps_per_s_bench_grid" in x and x["timesteps_per_s"]["cells"] == [32, 32, 32]
     assert x["config2_pcg_only"]["cells"] == [16, 16, 16] and x["config2_pcg_only"]["iterations_per_s"] > 0
     assert x["rhs_norm"] > 0
+    ts = x["timesteps_per_s_bench_grid"]  # BASELINE configs[4]: body force on, dt clamp includes sqrt(g h)
+    assert ts["gravity"] == 9.8 and ts["value"] > 0 and ts["dt"] < 1.0 / 512 and ts["ms_advect"] > 0
+    assert "value_with_setup" in c and c["value_with_setup"] <= c["value"] * 1.05
     # the multigrid side measurements run in a child process of the real bench (skipped by --no-probe: a child
     # would not see the emulation shim); the same entry point is run here directly
     assert "projection_time_to_solution" not in x
     x.update(run_bench(["--side", "mg", "--cells", "32", "--timestep-cells", "32"]))
-    x.update(run_bench(["--side", "probes", "--cells", "32"]))
+    x.update(run_bench(["--side", "advect", "--cells", "32"]))
+    x.update(run_bench(["--side", "flat2d", "--cells", "32"]))
     assert x["advect_tile_probe"]["tile0_ms"] > 0 and x["advect_tile_probe"]["tile1_ms"] > 0
     fl = x["flat_2d_probe"]
     assert fl["flat0_variant1"]["residual"] == fl["flat1_variant1"]["residual"] == fl["flat1_variant2"]["residual"]
@@ -102,3 +106,17 @@ def test_bench_other_cg_forms_and_reference_arm():
     assert r["impl"] == "reference" and r["metric"] == "pcg_iterations_per_second" and r["value"] > 0
     assert r["e2e"] == {"value": r["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert r["cpu_baseline"]["kind"] == "port" and r["cpu_baseline"]["value"] == r["value"]
+    # same workload label as the main arm, the honoured step count, every host core whatever the launcher exported
+    assert r["config"]["workload"] == d2["config"]["workload"].replace("fixed6", "fixed4") and r["steps"] == 1
+    assert r["config"]["cg_iters_per_step"] == 4 and 2 <= r["config"]["cg_iters_timed_per_step"] <= 4
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--cells", "32",
+                        "--iters", "4", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600,
+                       cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    r2 = json.loads(p.stdout.strip().splitlines()[-1])
+    assert r2["steps"] == 2 and r2["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and r2["n_gpus"] == 2
+    env["RANK"] = "1"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--cells", "32"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0 and not p.stdout.strip()  # the other ranks exit 0 without work

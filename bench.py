@@ -34,10 +34,11 @@ BYTES_STENCIL = 16  # read p, write q                       
 #   2: two kernels    stencil7 recomputed + r-update+norms 24 | x-update + p-update + stencil7 + dot, q not stored 40
 # the exchange schedule of the CG iterations the library picks on several GPUs (cfb_internal.h: peer_overlap)
 DEFAULT_PEER_OVERLAP = False
-BYTES_ITER = {0: 88, 1: 72, 2: 64}
-BYTES_DOMINANT = {0: 16, 1: 48, 2: 40}
+BYTES_ITER = {0: 88, 1: 72, 2: 64, 3: 88}
+BYTES_DOMINANT = {0: 16, 1: 48, 2: 40, 3: 16}
 KERNEL_DOMINANT = {0: "stencil7_dot_tma", 1: "cg_fused_kernel (x-update + p-update + stencil7 + p.Ap dot)",
-                   2: "cg_fused_kernel (x-update + p-update + stencil7 + p.Ap dot, q not stored)"}
+                   2: "cg_fused_kernel (x-update + p-update + stencil7 + p.Ap dot, q not stored)",
+                   3: "stencil7_dot_tma MODE 2 (u = M^-1 r, w = A u, three sums) of the single-reduction form"}
 
 
 def measured_peak():
@@ -551,7 +552,7 @@ def main():
     ap.add_argument("--no-timestep", action="store_true")
     ap.add_argument("--blocks", type=int, nargs=3, default=None, help="block grid bx by bz (default: split z, y, x)")
     ap.add_argument("--timestep-cells", type=int, default=128, help="grid of the extra full-timestep measurement")
-    ap.add_argument("--cg-variant", type=int, default=1, choices=[0, 1, 2],
+    ap.add_argument("--cg-variant", type=int, default=1, choices=[0, 1, 2, 3],
                     help="1 = two-kernel iteration (72 B/cell, default), 0 = three kernels (88 B), 2 = two kernels without a stored q (64 B)")
     ap.add_argument("--tune", action="append", default=[], help="key=value passed to cfb_set_tuning")
     ap.add_argument("--no-probe", action="store_true", help="skip the side measurement of the 64-byte CG form")
@@ -688,7 +689,9 @@ def main():
                                        if st["peer_mode"] else "NCCL send/recv before phase B, all-gather after each phase"),
                                       "exposed_after_phase_a_ms": xa, "exposed_after_phase_b_ms": xb,
                                       "phase_a_kernel_ms": st["ms_k_axpy"] / kt - xa, "phase_b_kernel_ms": k_only}})
-    if v >= 1:
+    if v == 3:
+        roofline["iteration"].update({"update_ms": st["ms_k_axpy"] / kt, "stencil_ms": t_st})
+    elif v >= 1:
         roofline["iteration"].update({"rupdate_ms": st["ms_k_axpy"] / kt, "fused_ms": t_st})
     else:
         roofline["iteration"].update({"axpy_ms": st["ms_k_axpy"] / kt, "pupdate_ms": st["ms_k_pupdate"] / kt,
@@ -913,7 +916,8 @@ def main():
                            "l2": "inputs larger than L2 (each vector %.2f GB)" % (ncell_local * 8 / 1e9),
                            "timing": "CUDA events on the launching stream around each solve, max over ranks",
                            "cg_form": {0: "three kernels, 88 B/cell", 1: "two kernels, 72 B/cell",
-                                       2: "two kernels, q not stored, 64 B/cell"}[args.cg_variant],
+                                       2: "two kernels, q not stored, 64 B/cell",
+                                       3: "single-reduction (Chronopoulos-Gear), two kernels, 88 B/cell, opt-in"}[args.cg_variant],
                            "exchange": ("none (1 GPU)" if world == 1 else
                                         "NVLink peer stores (cudaIpc): faces on the side stream under interior work, CG "
                                         "sums through mailboxes in the compute kernels' last blocks" if st["peer_overlap"] else

@@ -33,7 +33,7 @@ int ensure_partials( cfb_ctx* c, long long units )
         cudaFree( c->d_partials );
     c->d_partials = nullptr;
     c->partials_cap = 0;
-    CFB_CUDA( c, cudaMalloc( &c->d_partials, (size_t)2 * 2 * need * sizeof( double ) ) );
+    CFB_CUDA( c, cudaMalloc( &c->d_partials, (size_t)3 * 2 * need * sizeof( double ) ) ); // <= 3 values per block
     c->partials_cap = need;
     return CFB_OK;
 }
@@ -327,6 +327,8 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
 {
     if ( c->precond == CFB_PRECOND_MG )
         return mg_pcg_solve( c, fixed_iters, num_iter, resid );
+    if ( c->cg_variant == 3 )
+        return cg1_pcg_solve( c, fixed_iters, num_iter, resid ); // opt-in single-reduction form (kernels_cg1.cu)
     const int fixed = fixed_iters > 0;
     const int max_it = fixed ? fixed_iters : c->cfg.cg_max_iter;
     long long launches = 0;
@@ -1059,7 +1061,7 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     };
     static const Range ranges[] = { { "stencil_variant", 0, 1 }, { "stencil_tx", 64, 128 }, { "stencil_ty", 8, 32 },
                                     { "stencil_stages", 3, 6 },  { "stencil_zc", 0, 1 << 20 }, { "poll_every", 0, 1 << 20 },
-                                    { "cg_variant", 0, 2 },      { "fused_tx", 64, 128 },   { "fused_ty", 8, 32 },
+                                    { "cg_variant", 0, 3 },      { "fused_tx", 64, 128 },   { "fused_ty", 8, 32 },
                                     { "fused_stages", 2, 4 },    { "fused_zc", 0, 1 << 20 }, { "rupdate_ctas", 1, 8 } };
     for ( const Range& r : ranges )
         if ( k == r.key && ( value < r.lo || value > r.hi ) )

@@ -60,12 +60,13 @@ struct CgState
     // they travel in one 2-element allreduce, pAp in a 1-element one.
     double rz_old, pAp, rz_new, rr;
     double loc[6];                  // multi-GPU: local double-double sums  pAp | rz_new | rr
-    double gath[64 * 4];            // multi-GPU: all-gathered local sums (<= 64 ranks)
+    double gath[64 * 6];            // multi-GPU: all-gathered local sums (<= 64 ranks, <= 3 double-doubles each)
     int world;                      // number of ranks
     int pad0;
     double bnorm;                   // sqrt(rr) of r0
     double thresh;                  // absolute threshold in use
     double alpha;                   // two-kernel form: alpha of the running iteration (phase A -> B)
+    double beta;                    // single-reduction form (cg_variant 3): beta of the running iteration
     unsigned long long seq[2];      // peer-memory exchange: publications so far of (pAp | rz_new, rr)
     unsigned long long fseq[2];     // overlapped exchange: face transfers completed so far of (r | the search direction)
     int xerror;                     // sticky: a peer never published (timeout)
@@ -88,7 +89,7 @@ struct InflowConst
 #define CFB_MAX_PEERS 16
 struct PeerMail
 {
-    double v[2][CFB_MAX_PEERS][4];
+    double v[2][CFB_MAX_PEERS][6]; // <= 3 double-doubles per publication
     unsigned long long seq[2][CFB_MAX_PEERS];
     // overlapped exchange (halo.cu: cg_face_kernel): slot [0: r, 1: search direction][my face the writer sits on] =
     // number of face transfers of that kind the neighbour has completed into my ghost layers / staging areas
@@ -130,7 +131,7 @@ struct cfb_ctx
 
     CgState* d_state = nullptr;
     CgState* h_state = nullptr; // pinned mirror (first bytes only are copied)
-    double* d_partials = nullptr; // [2 values][partials_cap][hi,lo] scratch for block partial sums
+    double* d_partials = nullptr; // [3 values][partials_cap][hi,lo] scratch for block partial sums
     int partials_cap = 0;         // >= CFB_MAX_PARTIALS; value n of block b at [( n * stride + b ) * 2], stride <= cap
     // first error raised while enqueuing work (a launcher refusing a configuration, a failed exchange call): the
     // launchers return launch counts, so the code travels here and pcg_solve / the C entry points hand it out
@@ -139,6 +140,7 @@ struct cfb_ctx
     // stencil TMA descriptor + tiling
     CUtensorMap tmap_p{};
     CUtensorMap tmap_pbuf[2] = {}; // stencil-box maps of cg_pbuf[0 / 1]
+    CUtensorMap tmap_sr{};         // stencil-box map of cg_r (single-reduction form: the stencil runs on M^-1 r)
     bool tmap_ok = false;
     int st_variant = 0; // 0 = TMA z-march (default)
     int st_tx = 64, st_ty = 16, st_stages = 4, st_zc = 64;
@@ -161,7 +163,9 @@ struct cfb_ctx
 
     // two-kernel CG iteration (kernels_fused.cu): tensor maps of cg_r / cg_p, tiling, unit list
     // 1 = two kernels / 72 B per cell (default), 0 = three kernels / 88 B, 2 = two kernels / 64 B: q is
-    // never stored, phase A' recomputes A p (kernels_stencil.cu MODE 1); not yet measured on a B200
+    // never stored, phase A' recomputes A p (kernels_stencil.cu MODE 1); 3 = single-reduction (Chronopoulos-Gear)
+    // form, opt-in: two kernels / 88 B per cell, ONE reduction point and one ghost exchange per iteration
+    // (kernels_cg1.cu; iteration counts within +-1 of the other forms, which are bit-identical to one another)
     int cg_variant = 1;
     CUtensorMap tmap_fr{}, tmap_fp[2] = {}; // fused-box maps of cg_r and of cg_pbuf[0 / 1]
     bool fused_ok = false;
@@ -325,6 +329,12 @@ int launch_cg_pupdate( cfb_ctx* c );          // convergence bookkeeping + kerne
 int stencil_setup( cfb_ctx* c );              // builds the tensor map for cg_p
 int launch_stencil_dot( cfb_ctx* c );         // kernel 4
 int launch_stencil_rupdate( cfb_ctx* c );     // cg_variant 2, phase A': r -= alpha (A p) without a stored q
+// cg_variant 3: w = A M^-1 r with the three sums of the iteration (init: the launch that starts a solve); mail: the
+// last block runs the mailbox reduction (NVLink peer path)
+int launch_cg1_stencil( cfb_ctx* c, int init, bool mail );
+// kernels_cg1.cu: p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s
+int launch_cg1_update( cfb_ctx* c );
+int cg1_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid );
 // kernels_fused.cu
 int fused_setup( cfb_ctx* c );                // tensor maps of cg_r, cg_p + the unit list
 int launch_cg_rupdate( cfb_ctx* c );          // phase A: r -= alpha q, sum r^2, sum r.Minv r

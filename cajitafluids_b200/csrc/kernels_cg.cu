@@ -16,6 +16,7 @@
 #include "cfb_internal.h"
 #include "device_geo.cuh"
 #include "device_reduce.cuh"
+#include "device_cg1.cuh"
 
 namespace
 {
@@ -58,11 +59,13 @@ __device__ __forceinline__ void publish_rr_rz( CgState* S, dd_t rr, dd_t rz )
     }
 }
 
-// which == 0: pAp from gath[rank][0..1] ; which == 1: (rz_new, rr) from gath[rank][0..3]
+// which == 0: pAp from gath[rank][0..1] ; which == 1: (rz_new, rr) from gath[rank][0..3] ;
+// which == 2 / 3: (r.r, r.u, w.u) of the single-reduction form from gath[rank][0..5], then its scalar step (3: the
+// launch that starts a solve)
 __global__ void cg_combine_kernel( CgState* S, int which )
 {
-    const int nv = which == 0 ? 1 : 2;
-    dd_t acc[2] = { { 0.0, 0.0 }, { 0.0, 0.0 } };
+    const int nv = which == 0 ? 1 : ( which == 1 ? 2 : 3 );
+    dd_t acc[3] = { { 0.0, 0.0 }, { 0.0, 0.0 }, { 0.0, 0.0 } };
     for ( int r = 0; r < S->world; ++r )
         for ( int v = 0; v < nv; ++v )
         {
@@ -71,11 +74,13 @@ __global__ void cg_combine_kernel( CgState* S, int which )
         }
     if ( which == 0 )
         S->pAp = acc[0].hi + acc[0].lo;
-    else
+    else if ( which == 1 )
     {
         S->rz_new = acc[0].hi + acc[0].lo;
         S->rr = acc[1].hi + acc[1].lo;
     }
+    else if ( !S->done ) // (a stencil launch behind convergence did nothing: no scalar step either)
+        cg1_finish( S, acc[0].hi + acc[0].lo, acc[1].hi + acc[1].lo, acc[2].hi + acc[2].lo, which == 3 );
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -278,8 +283,8 @@ inline int stream_grid( const cfb_ctx* c, long long pairs )
 // Multi-GPU: all-gather the local double-double sums and combine them exactly.
 int cg_global_sum( cfb_ctx* c, int which )
 {
-    const int nd = which == 0 ? 2 : 4; // doubles per rank
-    int rc = halo_allgather( c, &c->d_state->loc[which == 0 ? 0 : 2], c->d_state->gath, nd );
+    const int nd = which == 0 ? 2 : ( which == 1 ? 4 : 6 ); // doubles per rank
+    int rc = halo_allgather( c, &c->d_state->loc[which == 1 ? 2 : 0], c->d_state->gath, nd );
     if ( rc )
         return rc;
     cg_combine_kernel<<<1, 1, 0, c->stream>>>( c->d_state, which );

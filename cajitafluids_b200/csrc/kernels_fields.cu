@@ -72,23 +72,28 @@ __global__ void __launch_bounds__( 256 )
 }
 
 // ---------------------------------------------------------------------------------------------
-// TimeIntegrator::advect for one entity.  blockIdx.y selects the entity (0 = Cell/q, 1.. = faces),
-// so the whole TimeIntegrator::step advection is one launch.
+// TimeIntegrator::advect for every entity kind (0 = Cell/q, 1.. = faces) in one launch,
+// i.e. the whole advection of TimeIntegrator::step.
 struct AdvectArgs
 {
     const double* cur[4];
     double* next[4];
 };
 
-// TILED ("advect_tile" tuning key, off until measured): a block owns a 32 x 2 x 2 (3-D) / 32 x 4 (2-D) tile of
-// entities instead of 128 consecutive ones of a row, so that the 4^D-point neighbourhoods of its threads overlap
-// in y and z as well as in x (fewer distinct rows pulled from the L2 per output).  Only the thread -> entity map
-// changes: the same values.
+// Work decomposition.  One block per work item, items in launch order = (chunk of the volume, entity) with the
+// ENTITY FASTEST: the blocks resident at any moment work on the same few planes of the volume for all D + 1 entity
+// kinds, so the velocity planes they gather from are pulled from HBM once and shared through the L2 (the round-1
+// form — a capped grid-stride launch with the entity in blockIdx.y — spread its resident blocks over the whole
+// volume and swept it once per entity kind: 40 GB of DRAM reads for 8.6 GB compulsory, profiles/r2_advect_*).
+// An item is 128 consecutive entities of the flattened (i, j, k) index of its kind, or — TILED ("advect_tile"
+// tuning key) — a 32 x 2 x 2 (3-D) / 32 x 4 (2-D) tile, whose 4^D-point neighbourhoods overlap in y and z too.
+// Only the thread -> entity map differs: the same values.
 template <int D, int ORDER, bool TILED>
 __global__ void __launch_bounds__( 128 )
     advect_kernel( const __grid_constant__ Geo g, const __grid_constant__ AdvectArgs a, int quirk_v0 )
 {
-    const int ent = blockIdx.y;
+    const int ent = (int)( blockIdx.x % (unsigned)( D + 1 ) );
+    const long long item = (long long)( blockIdx.x / (unsigned)( D + 1 ) );
     const int ex = ent == 1 ? g.nf[0] : g.n[0];
     const int ey = ent == 2 ? g.nf[1] : g.n[1];
     const int ez = D == 3 ? ( ent == 3 ? g.nf[2] : g.n[2] ) : 1;
@@ -96,25 +101,26 @@ __global__ void __launch_bounds__( 128 )
     double* fn = a.next[ent];
     const double dt = g.dt;
     constexpr int TY = D == 3 ? 2 : 4, TZ = D == 3 ? 2 : 1;
-    const int nbx = ( ex + 31 ) / 32, nby = ( ey + TY - 1 ) / TY, nbz = ( ez + TZ - 1 ) / TZ;
-    // work items: entities (flat) or tiles; a tiled block handles one tile per round
-    const long long total = TILED ? (long long)nbx * nby * nbz : (long long)ex * ey * ez;
-    for ( long long t = TILED ? (long long)blockIdx.x : blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-          t += TILED ? (long long)gridDim.x : (long long)gridDim.x * blockDim.x )
     {
         int i, j, k;
         if ( TILED )
         {
-            const int bx = (int)( t % nbx ), by = (int)( ( t / nbx ) % nby ), bz = (int)( t / ( (long long)nbx * nby ) );
+            const int nbx = ( ex + 31 ) / 32, nby = ( ey + TY - 1 ) / TY, nbz = ( ez + TZ - 1 ) / TZ;
+            if ( item >= (long long)nbx * nby * nbz )
+                return;
+            const int bx = (int)( item % nbx ), by = (int)( ( item / nbx ) % nby ), bz = (int)( item / ( (long long)nbx * nby ) );
             const int tid = threadIdx.x;
             i = bx * 32 + ( tid & 31 );
             j = by * TY + ( ( tid >> 5 ) % TY );
             k = bz * TZ + ( tid >> 5 ) / TY;
             if ( i >= ex || j >= ey || k >= ez )
-                continue;
+                return;
         }
         else
         {
+            const long long t = item * 128 + threadIdx.x;
+            if ( t >= (long long)ex * ey * ez )
+                return;
             i = (int)( t % ex );
             j = (int)( ( t / ex ) % ey );
             k = (int)( t / ( (long long)ex * ey ) );
@@ -293,16 +299,35 @@ int launch_advect( cfb_ctx* c )
         a.cur[e] = field_ptr( c, e, CFB_CURRENT );
         a.next[e] = field_ptr( c, e, CFB_NEXT );
     }
-    long long total = (long long)( g.n[0] + 1 ) * ( g.n[1] + 1 ) * ( g.D == 3 ? g.n[2] + 1 : 1 );
     const int qv0 = c->cfg.quirk_rk3_stage3_v0;
     const int order = c->cfg.field_interp_order;
+    // items per entity kind (the largest kind decides; the others leave their surplus blocks at once)
+    long long items;
+    if ( c->advect_tile )
+        items = (long long)( ( g.n[0] + 1 + 31 ) / 32 ) * ( ( g.n[1] + 1 + ( g.D == 3 ? 1 : 3 ) ) / ( g.D == 3 ? 2 : 4 ) ) *
+                ( g.D == 3 ? ( g.n[2] + 1 + 1 ) / 2 : 1 );
+    else
+    {
+        // the largest flattened entity count among cells and faces
+        long long mx = 0;
+        for ( int e = 0; e <= g.D; ++e )
+        {
+            long long t = 1;
+            for ( int d = 0; d < g.D; ++d )
+                t *= ( e - 1 == d ) ? g.nf[d] : g.n[d];
+            mx = t > mx ? t : mx;
+        }
+        items = ( mx + 127 ) / 128;
+    }
+    const long long blocks = items * ( g.D + 1 );
+    if ( blocks > 2147483647ll )
+    {
+        note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "advection: block too large for one launch" ) );
+        return 0;
+    }
+    const dim3 grid( (unsigned)blocks );
     if ( c->advect_tile )
     {
-        // one block per 128-entity tile (the largest entity extents: faces)
-        const long long tiles = (long long)( ( g.n[0] + 1 + 31 ) / 32 ) * ( ( g.n[1] + 1 + ( g.D == 3 ? 1 : 3 ) ) / ( g.D == 3 ? 2 : 4 ) ) *
-                                ( g.D == 3 ? ( g.n[2] + 1 + 1 ) / 2 : 1 );
-        const long long cap = (long long)c->sm_count * 64;
-        dim3 grid( (unsigned)( tiles < cap ? tiles : cap ), g.D + 1 );
         if ( g.D == 2 && order == 1 )
             advect_kernel<2, 1, true><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
         else if ( g.D == 2 )
@@ -313,7 +338,6 @@ int launch_advect( cfb_ctx* c )
             advect_kernel<3, 3, true><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
         return 1;
     }
-    dim3 grid( grid_for( total, 128, c->sm_count ), g.D + 1 );
     if ( g.D == 2 && order == 1 )
         advect_kernel<2, 1, false><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
     else if ( g.D == 2 )

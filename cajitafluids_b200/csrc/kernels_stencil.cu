@@ -23,6 +23,7 @@
 #include "device_reduce.cuh"
 #include "device_tma.cuh"
 #include "device_peer.cuh"
+#include "device_cg1.cuh"
 
 namespace
 {
@@ -65,6 +66,7 @@ struct StencilArgs
     double* partials;
     int tiles_x, tiles_y, zc, hx;
     int pstride; // entries per value in the partial-sum scratch (cfb_ctx::partials_cap)
+    int init;    // MODE 2: the launch that starts a solve (sets alpha, beta; counts no iteration)
 };
 
 // MODE 0: q = A p, sum p.q (CG kernel 4).
@@ -73,6 +75,10 @@ struct StencilArgs
 //         (reads p through TMA and r with 128-bit loads, writes r: 24 B/cell, and phase B no longer writes q).
 //         Statement for statement cg_rupdate_kernel with q recomputed by the same row expression that
 //         produced it, hence bit-identical.
+// MODE 2: the stencil kernel of the single-reduction CG (cg_variant 3, kernels_cg1.cu): the planes staged by TMA are
+//         those of r; u = M^-1 r is formed on the fly for the centre and its six neighbours (the diagonal is a
+//         function of the cell's wall count, so nothing is stored), w = A u is written, and the THREE sums of the
+//         iteration's only reduction point are taken on the march: sum r^2, sum r.u, sum w.u (16 B/cell).
 // FLAT: two-dimensional runs (one owned plane between two zero ghost planes): the z neighbours are zero by
 // construction and their planes are not loaded.  A template flag: the 3-D instantiations are untouched.
 // PF (MODE 1 only, "peer_fused"): the faces of the new r go into the neighbours' ghost layers from here and the
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
 {
     constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
     double nalpha = 0.0;
-    if ( MODE == 0 )
+    if ( MODE != 1 )
     {
         if ( a.S->done )
             return;
@@ -179,6 +185,16 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         wyc[r] = wall_count( g, 1, j + g.off[1] );
     }
     const double ns = op.neg_scale;
+    // MODE 2: wall counts of the x and y neighbours (their M^-1 differs from the centre's next to a wall)
+    const int wxm = wall_count( g, 0, i0 - 1 + g.off[0] ), wxp = wall_count( g, 0, i0 + 2 + g.off[0] );
+    int wym[RY], wyp[RY];
+#pragma unroll
+    for ( int r = 0; r < RY; ++r )
+    {
+        const int j = y0 + wy + r * WY;
+        wym[r] = wall_count( g, 1, j - 1 + g.off[1] );
+        wyp[r] = wall_count( g, 1, j + 1 + g.off[1] );
+    }
 
     double2 zm[RY], cc[RY];
     if ( !FLAT )
@@ -191,6 +207,15 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         zm[r] = FLAT ? make_double2( 0.0, 0.0 ) : *reinterpret_cast<const double2*>( stage0 + row * PX + 2 * lx + 2 );
         cc[r] = *reinterpret_cast<const double2*>( stage0 + ( 1 % NS ) * ( C::STAGE_BYTES / 8 ) + row * PX +
                                                    2 * lx + 2 );
+        if ( MODE == 2 )
+        {
+            // r -> u = M^-1 r of planes kbeg - 1 and kbeg
+            const int wzl = wall_count( g, 2, kbeg - 1 + g.off[2] ), wz0 = wall_count( g, 2, kbeg + g.off[2] );
+            zm[r].x = op.minv[wx0 + wyc[r] + wzl] * zm[r].x;
+            zm[r].y = op.minv[wx1 + wyc[r] + wzl] * zm[r].y;
+            cc[r].x = op.minv[wx0 + wyc[r] + wz0] * cc[r].x;
+            cc[r].y = op.minv[wx1 + wyc[r] + wz0] * cc[r].y;
+        }
     }
 
     // slot 0 (plane kbeg-1) only feeds the zm registers: once every thread has read it, it takes
@@ -203,8 +228,8 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         tma_load_3d( smem_base, &tmap, bar, cx, cy, cz + NS );
     }
 
-    dd_t acc = { 0.0, 0.0 }, acc2 = { 0.0, 0.0 }; // MODE 0: p.q | MODE 1: r.r, r.M^-1 r
-    double* qrow = ( MODE == 0 ? a.q : a.r ) + geo_off( g, i0, y0 + wy, kbeg );
+    dd_t acc = { 0.0, 0.0 }, acc2 = { 0.0, 0.0 }, acc3 = { 0.0, 0.0 }; // MODE 0: p.q | 1: r.r, r.M^-1 r | 2: r.r, r.u, w.u
+    double* qrow = ( MODE != 1 ? a.q : a.r ) + geo_off( g, i0, y0 + wy, kbeg );
     // MODE 1: r is streamed with 128-bit loads one plane ahead of its use (the loads of plane k + 1 are in
     // flight while plane k waits for its TMA stage and is computed), like x in phase B
     double2 rcur[RY], rnxt[RY];
@@ -241,11 +266,24 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         {
             const int row = wy + r * WY + 1;
             const double* pc = P + row * PX + 2 * lx + 2;
-            const double2 zp = FLAT ? make_double2( 0.0, 0.0 ) : *reinterpret_cast<const double2*>( N + row * PX + 2 * lx + 2 );
-            const double xl = pc[-1];
-            const double xr = pc[2];
-            const double2 ym = *reinterpret_cast<const double2*>( pc - PX );
-            const double2 yp = *reinterpret_cast<const double2*>( pc + PX );
+            double2 zp = FLAT ? make_double2( 0.0, 0.0 ) : *reinterpret_cast<const double2*>( N + row * PX + 2 * lx + 2 );
+            double xl = pc[-1];
+            double xr = pc[2];
+            double2 ym = *reinterpret_cast<const double2*>( pc - PX );
+            double2 yp = *reinterpret_cast<const double2*>( pc + PX );
+            if ( MODE == 2 )
+            {
+                // the staged values are r: u = M^-1 r of every neighbour, each with its own wall count
+                const int wzn = wall_count( g, 2, kbeg + it + 1 + g.off[2] );
+                zp.x = op.minv[wx0 + wyc[r] + wzn] * zp.x;
+                zp.y = op.minv[wx1 + wyc[r] + wzn] * zp.y;
+                xl = op.minv[wxm + wyc[r] + wz] * xl;
+                xr = op.minv[wxp + wyc[r] + wz] * xr;
+                ym.x = op.minv[wx0 + wym[r] + wz] * ym.x;
+                ym.y = op.minv[wx1 + wym[r] + wz] * ym.y;
+                yp.x = op.minv[wx0 + wyp[r] + wz] * yp.x;
+                yp.y = op.minv[wx1 + wyp[r] + wz] * yp.y;
+            }
             const double2 c = cc[r];
             const double d0 = op.diag[wx0 + wyc[r] + wz];
             const double d1 = op.diag[wx1 + wyc[r] + wz];
@@ -266,6 +304,27 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
                     {
                         *qp = a0;
                         dd_acc( acc, c.x * a0 );
+                    }
+                }
+                else if ( MODE == 2 )
+                {
+                    const double2 rc = *reinterpret_cast<const double2*>( pc ); // r of my pair
+                    if ( vx1 )
+                    {
+                        *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
+                        dd_acc( acc, rc.x * rc.x );
+                        dd_acc( acc2, c.x * rc.x );
+                        dd_acc( acc3, c.x * a0 );
+                        dd_acc( acc, rc.y * rc.y );
+                        dd_acc( acc2, c.y * rc.y );
+                        dd_acc( acc3, c.y * a1 );
+                    }
+                    else if ( vx0 )
+                    {
+                        *qp = a0;
+                        dd_acc( acc, rc.x * rc.x );
+                        dd_acc( acc2, c.x * rc.x );
+                        dd_acc( acc3, c.x * a0 );
                     }
                 }
                 else
@@ -325,6 +384,30 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
         {
             if ( tid == 0 )
                 publish_pAp( a.S, vals[0] );
+        }
+    }
+    else if ( MODE == 2 )
+    {
+        dd_t vals[3] = { acc, acc2, acc3 }; // r.r, gamma = r.u, delta = w.u
+        if ( block_reduce_finalize<C::NT, 3>( vals, a.partials, a.pstride, &a.S->ticket[1] ) )
+        {
+            CgState* S = a.S;
+            if ( tid == 0 && S->world > 1 )
+                for ( int v = 0; v < 3; ++v )
+                {
+                    S->loc[2 * v] = vals[v].hi;
+                    S->loc[2 * v + 1] = vals[v].lo;
+                }
+            if constexpr ( PF )
+            {
+                dd_t sum[3];
+                peer_mail_exchange<3>( S, pf, 1, 0, sum );
+                if ( tid == 0 )
+                    cg1_finish( S, sum[0].hi + sum[0].lo, sum[1].hi + sum[1].lo, sum[2].hi + sum[2].lo, a.init );
+            }
+            else if ( tid == 0 && S->world == 1 )
+                cg1_finish( S, vals[0].hi + vals[0].lo, vals[1].hi + vals[1].lo, vals[2].hi + vals[2].lo, a.init );
+            // (several ranks over NCCL: cg_global_sum( c, 2 + init ) combines the local sums and finishes)
         }
     }
     else
@@ -443,23 +526,34 @@ int launch_tma_mode( cfb_ctx* c, const StencilArgs& a, int grid, const PeerFused
     {
         cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
         cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
-        if ( MODE == 1 )
-            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        if constexpr ( MODE != 0 )
+            cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
         attr_set = true;
     }
     const NoPeerArgs none{};
-    if ( MODE == 1 && pf ) // (launch_stencil_rupdate_peer has made sure that flat does not apply)
-        stencil7_dot_tma<C, 1, false, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a, *pf );
-    else if ( c->g.D == 2 && c->flat_2d )
-        stencil7_dot_tma<C, MODE, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a, none );
+    const CUtensorMap& tm = MODE == 2 ? c->tmap_sr : c->tmap_p; // MODE 2 marches over r, the others over p
+    if constexpr ( MODE != 0 )
+    {
+        if ( pf ) // (the callers have made sure that flat does not apply)
+        {
+            stencil7_dot_tma<C, MODE, false, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->g, c->op, a, *pf );
+            return 1;
+        }
+    }
+    if ( c->g.D == 2 && c->flat_2d )
+        stencil7_dot_tma<C, MODE, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->g, c->op, a, none );
     else
-        stencil7_dot_tma<C, MODE, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_p, c->g, c->op, a, none );
+        stencil7_dot_tma<C, MODE, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->g, c->op, a, none );
     return 1;
 }
 template <class C>
 int launch_tma( cfb_ctx* c, const StencilArgs& a, int grid, int mode, const PeerFusedArgs* pf )
 {
-    return mode == 0 ? launch_tma_mode<C, 0>( c, a, grid, nullptr ) : launch_tma_mode<C, 1>( c, a, grid, pf );
+    if ( mode == 0 )
+        return launch_tma_mode<C, 0>( c, a, grid, nullptr );
+    if ( mode == 1 )
+        return launch_tma_mode<C, 1>( c, a, grid, pf );
+    return launch_tma_mode<C, 2>( c, a, grid, pf );
 }
 
 } // namespace
@@ -490,18 +584,26 @@ int stencil_setup( cfb_ctx* c )
         if ( r != CUDA_SUCCESS )
             return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string( (int)r ) );
     }
+    {
+        CUresult r = encode( &c->tmap_sr, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->cg_r, gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+        if ( r != CUDA_SUCCESS )
+            return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string( (int)r ) );
+    }
     c->tmap_p = c->tmap_pbuf[c->pcur];
     c->tmap_ok = true;
     return CFB_OK;
 }
 
-static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullptr )
+static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullptr, int init = 0 )
 {
     const Geo& g = c->g;
     StencilArgs a{};
     a.r = c->cg_r;
     a.q = c->cg_q;
     a.S = c->d_state;
+    a.init = init;
     a.hx = 16;
     const int tx = c->st_variant == 1 ? 64 : c->st_tx;
     const int ty = c->st_variant == 1 ? 8 : c->st_ty;
@@ -526,7 +628,7 @@ static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullp
     {
         if ( mode != 0 )
         {
-            note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "the LDG stencil variant has no phase A' form" ) );
+            note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "the LDG stencil variant has no phase A' / single-reduction form" ) );
             return 0;
         }
         stencil7_dot_ldg<<<grid, 256, 0, c->stream>>>( g, c->op, c->cg_p, a );
@@ -560,6 +662,28 @@ static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullp
 }
 
 int launch_stencil_dot( cfb_ctx* c ) { return launch_stencil( c, 0 ); }
+
+// cg_variant 3 (single-reduction CG): w = A M^-1 r, sum r^2, sum r.u, sum w.u
+int launch_cg1_stencil( cfb_ctx* c, int init, bool mail )
+{
+    if ( c->st_variant == 1 )
+    {
+        note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "the LDG stencil variant has no single-reduction form" ) );
+        return 0;
+    }
+    if ( mail )
+    {
+        if ( c->g.D == 2 && c->flat_2d )
+        {
+            note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "flat_2d has no mailbox instantiation" ) );
+            return 0;
+        }
+        PeerFusedArgs pf{};
+        peer_mail_only( c, pf );
+        return launch_stencil( c, 2, &pf, init );
+    }
+    return launch_stencil( c, 2, nullptr, init );
+}
 
 // phase A' of the 64-byte iteration (cg_variant 2): r -= alpha (A p) with q recomputed, sum r^2, sum r.M^-1 r
 int launch_stencil_rupdate( cfb_ctx* c ) { return launch_stencil( c, 1 ); }

@@ -160,6 +160,8 @@ struct cfo_ctx
     std::vector<double> A;  // (cell, c) c fastest  -- getMatrixValues()
     std::vector<double> Mi; // getPreconditionerValues()
     Arr cg_p, cg_z, cg_r, cg_q;
+    Arr cg_s;          // single-reduction CG only (cg_single_reduction): s = A p by recurrence; allocated on first use
+    int cg_algorithm = 0; // 0 = Cajita's ReferenceConjugateGradient loop, 1 = single-reduction (Chronopoulos-Gear) form
     int num_iter;
     double resid; // sqrt(sum r^2)
     std::vector<double> hist;
@@ -802,8 +804,11 @@ void mg_apply( cfo_ctx& c, const Arr& r, Arr& z )
 // driven from src/VelocityCorrector.hpp:276 with tol 1e-6 / max_iter 2000 (:103-104),
 // diagonal preconditioner (:166-179).  Absolute 2-norm stopping test.
 // gather ids: 1 = x halo, 2 = r halo (width 0 for a diagonal M: no-op), 3 = p halo.
+int cg_solve_single_reduction( cfo_ctx& c );
 int cg_solve( cfo_ctx& c )
 {
+    if ( c.cg_algorithm == 1 && c.precond == 0 )
+        return cg_solve_single_reduction( c );
     auto t0 = clk::now();
     Space s = own_space( c, 0 );
     const Arr& b = c.rhs;
@@ -973,6 +978,122 @@ int cg_solve( cfo_ctx& c )
                     for ( int i = s.lo[0]; i < s.hi[0]; ++i )
                         x( i, j, k ) = x( i, j, k ) - shift;
         }
+    }
+    c.cg_total += c.num_iter;
+    if ( c.cfg.cg_print_level > 0 && c.cfg.world_rank == 0 )
+        std::printf( "Cajita CG Finished in %d iterations, |r|_2 = %g\n", c.num_iter, c.resid );
+    c.t_phase[3] += std::chrono::duration<double>( clk::now() - t0 ).count();
+    if ( !converged && !fixed )
+    {
+        c.err = "Cajita CG solver did not converge";
+        return CFB_ERR_NOT_CONVERGED;
+    }
+    return CFB_OK;
+}
+
+// Opt-in single-reduction form of the same Jacobi-PCG (NOT the reference's loop: Chronopoulos and
+// Gear's rearrangement, "s-step iterative methods for symmetric linear systems", J. Comput. Appl. Math. 25, 1989).
+// In exact arithmetic the iterates equal those of cg_solve; per iteration there is ONE point where global sums are
+// needed (r.r, r.u, w.u together) instead of three (two in the product's default form):
+//     u = M^-1 r ; w = A u ; gamma = r.u ; delta = w.u ; [r.r]                    <- the one reduction
+//     beta = gamma / gamma_old ; alpha = gamma / ( delta - beta gamma / alpha_old )   (first: beta = 0, alpha = gamma / delta)
+//     p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s
+// Statement order and fma placement are the product's (kernels_cg1.cu); single block (the r halo a decomposed run
+// needs before w = A u is gather id 2).
+int cg_solve_single_reduction( cfo_ctx& c )
+{
+    auto t0 = clk::now();
+    Space sp = own_space( c, 0 );
+    const Arr& b = c.rhs;
+    Arr& x = c.lhs;
+    Arr &p = c.cg_p, &u = c.cg_z, &r = c.cg_r, &w = c.cg_q, &s = c.cg_s;
+    if ( s.a.size() != r.a.size() )
+        s.alloc( r.e ); // same ghosted extents as the other CG vectors
+    const double tol = c.cfg.cg_tolerance;
+    const int max_iter = c.cfg.cg_fixed_iters > 0 ? c.cfg.cg_fixed_iters : c.cfg.cg_max_iter;
+    const bool fixed = c.cfg.cg_fixed_iters > 0;
+    c.num_iter = 0;
+    c.hist.clear();
+    double thresh = tol;
+    // x0 = 0 is the product's contract for this form: r0 = b
+#pragma omp parallel for collapse( 2 ) schedule( static )
+    for ( int k = sp.lo[2]; k < sp.hi[2]; ++k )
+        for ( int j = sp.lo[1]; j < sp.hi[1]; ++j )
+            for ( int i = sp.lo[0]; i < sp.hi[0]; ++i )
+            {
+                x( i, j, k ) = 0.0;
+                r( i, j, k ) = b( i, j, k );
+            }
+    double gamma_old = 0.0, alpha = 0.0, beta = 0.0;
+    bool converged = false;
+    for ( ;; )
+    {
+        // u = M^-1 r (ghost cells of a single block: zero) ; w = A u ; the three sums
+        do_gather( c, 2 );
+#pragma omp parallel for collapse( 2 ) schedule( static )
+        for ( int k = sp.lo[2]; k < sp.hi[2]; ++k )
+            for ( int j = sp.lo[1]; j < sp.hi[1]; ++j )
+                for ( int i = sp.lo[0]; i < sp.hi[0]; ++i )
+                    u( i, j, k ) = c.Mi[r.idx( i, j, k )] * r( i, j, k );
+        acc_t rr_acc( c.accum_exact ), g_acc( c.accum_exact ), d_acc( c.accum_exact );
+#pragma omp parallel for collapse( 2 ) schedule( static ) reduction( accsum : rr_acc, g_acc, d_acc )
+        for ( int k = sp.lo[2]; k < sp.hi[2]; ++k )
+            for ( int j = sp.lo[1]; j < sp.hi[1]; ++j )
+                for ( int i = sp.lo[0]; i < sp.hi[0]; ++i )
+                {
+                    const double Au = apply_A( c, u, i, j, k );
+                    w( i, j, k ) = Au;
+                    const double rv = r( i, j, k ), uv = u( i, j, k );
+                    rr_acc.add( rv * rv );
+                    g_acc.add( uv * rv );
+                    d_acc.add( uv * Au );
+                }
+        double sums[3] = { rr_acc.value(), g_acc.value(), d_acc.value() };
+        do_allreduce( c, sums, 3 );
+        const double rr = sums[0], gamma = sums[1], delta = sums[2];
+        c.resid = std::sqrt( rr );
+        if ( c.num_iter == 0 )
+        {
+            if ( c.cfg.cg_stop_rule == CFB_STOP_REL )
+                thresh = tol * c.resid;
+            if ( !fixed && c.resid <= thresh )
+            {
+                converged = true;
+                break;
+            }
+            beta = 0.0;
+            alpha = gamma / delta;
+        }
+        else
+        {
+            c.hist.push_back( c.resid );
+            if ( c.cfg.cg_print_level == 2 && c.cfg.world_rank == 0 )
+                std::printf( "Cajita CG Iteration %d: |r|_2 = %g\n", c.num_iter, c.resid );
+            if ( !fixed && c.resid <= thresh )
+            {
+                converged = true;
+                break;
+            }
+            if ( c.num_iter >= max_iter )
+                break;
+            beta = gamma / gamma_old;
+            alpha = gamma / ( delta - ( beta * gamma ) / alpha );
+        }
+        gamma_old = gamma;
+        const bool first = c.num_iter == 0;
+#pragma omp parallel for collapse( 2 ) schedule( static )
+        for ( int k = sp.lo[2]; k < sp.hi[2]; ++k )
+            for ( int j = sp.lo[1]; j < sp.hi[1]; ++j )
+                for ( int i = sp.lo[0]; i < sp.hi[0]; ++i )
+                {
+                    const double pv = first ? u( i, j, k ) : std::fma( beta, p( i, j, k ), u( i, j, k ) );
+                    const double sv = first ? w( i, j, k ) : std::fma( beta, s( i, j, k ), w( i, j, k ) );
+                    p( i, j, k ) = pv;
+                    s( i, j, k ) = sv;
+                    x( i, j, k ) = std::fma( alpha, pv, x( i, j, k ) );
+                    r( i, j, k ) = std::fma( -alpha, sv, r( i, j, k ) );
+                }
+        ++c.num_iter;
     }
     c.cg_total += c.num_iter;
     if ( c.cfg.cg_print_level > 0 && c.cfg.world_rank == 0 )
@@ -1491,6 +1612,15 @@ int cfo_num_threads( void )
 #else
     return 1;
 #endif
+}
+
+// 0: Cajita's ReferenceConjugateGradient loop (default) ; 1: the single-reduction form (the product's cg_variant 3)
+int cfo_set_cg_algorithm( cfo_ctx* c, int algorithm )
+{
+    if ( algorithm != 0 && algorithm != 1 )
+        return CFB_ERR_INVALID;
+    c->cg_algorithm = algorithm;
+    return CFB_OK;
 }
 
 // Fixed-iteration mode of the following solves (0: back to the stopping test); the benchmark's CPU arm times solves

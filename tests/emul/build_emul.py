@@ -17,8 +17,8 @@ OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libcfb_emul.so")
 LIB_TMA = os.path.join(OUT, "libcfb_emul_tma.so")  # the TMA kernels themselves instead of plain-loop stand-ins
 TMA_SOURCES = ["kernels_stencil.cu", "kernels_fused.cu"]
-SOURCES = ["cfb_api.cu", "kernels_fields.cu", "kernels_cg.cu", "mg.cu", "output.cu", "halo.cu"]
-HEADERS = ["cfb_internal.h", "device_geo.cuh", "device_peer.cuh"]
+SOURCES = ["cfb_api.cu", "kernels_fields.cu", "kernels_cg.cu", "kernels_cg1.cu", "mg.cu", "output.cu", "halo.cu"]
+HEADERS = ["cfb_internal.h", "device_geo.cuh", "device_peer.cuh", "device_cg1.cuh"]
 # kernels whose threads meet at __syncthreads() for real: one fiber per CUDA thread
 # (a name with its template arguments selects that instantiation only: phase A meets at barriers only when it
 # runs the mailbox exchange itself)

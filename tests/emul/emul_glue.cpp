@@ -7,6 +7,7 @@
 //     threads), the NVLink peer-memory path reports "not available" (cudaIpc stand-ins fail)
 #include "cfb_internal.h"
 #include "device_geo.cuh"
+#include "device_cg1.cuh"
 #include "device_reduce.cuh"
 
 #include <chrono>
@@ -394,6 +395,50 @@ int launch_stencil_rupdate( cfb_ctx* c )
         S->rr = rr.hi + rr.lo;
         S->rz_new = rz.hi + rz.lo;
     }
+    return 1;
+}
+
+// the stencil kernel of the single-reduction CG (kernels_stencil.cu MODE 2): u = M^-1 r, w = A u, three sums
+int launch_cg1_stencil( cfb_ctx* c, int init, bool mail )
+{
+    const Geo& g = c->g;
+    const OpConst& op = c->op;
+    CgState* S = c->d_state;
+    if ( mail )
+    {
+        note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "plain-loop stand-in: no mailbox form of the single-reduction stencil" ) );
+        return 0;
+    }
+    if ( S->done )
+        return 1;
+    const double* r = c->cg_r;
+    double* w = c->cg_q;
+    auto u_at = [&]( int i, int j, int k ) { return op.minv[walls_at( g, i, j, k )] * r[geo_off( g, i, j, k )]; };
+    dd_t rr{ 0.0, 0.0 }, gm{ 0.0, 0.0 }, dl{ 0.0, 0.0 };
+    for ( int k = 0; k < g.n[2]; ++k )
+        for ( int j = 0; j < g.n[1]; ++j )
+            for ( int i = 0; i < g.n[0]; ++i )
+            {
+                const long long o = geo_off( g, i, j, k );
+                const double uc = u_at( i, j, k );
+                const double a = apply_row( op.diag[walls_at( g, i, j, k )], op.neg_scale, uc, u_at( i - 1, j, k ), u_at( i + 1, j, k ),
+                                            u_at( i, j - 1, k ), u_at( i, j + 1, k ), u_at( i, j, k - 1 ), u_at( i, j, k + 1 ) );
+                w[o] = a;
+                dd_acc( rr, r[o] * r[o] );
+                dd_acc( gm, uc * r[o] );
+                dd_acc( dl, uc * a );
+            }
+    if ( S->world > 1 )
+    {
+        const dd_t v[3] = { rr, gm, dl };
+        for ( int q = 0; q < 3; ++q )
+        {
+            S->loc[2 * q] = v[q].hi;
+            S->loc[2 * q + 1] = v[q].lo;
+        }
+    }
+    else
+        cg1_finish( S, rr.hi + rr.lo, gm.hi + gm.lo, dl.hi + dl.lo, init );
     return 1;
 }
 

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="only the PCG section, three exchange modes")
     ap.add_argument("--mg", action="store_true", help="only the multigrid-preconditioner section")
     ap.add_argument("--fused", action="store_true", help="only the PCG section, exchange inside the kernels (peer_fused)")
+    ap.add_argument("--cg1", action="store_true", help="only the single-reduction CG section (cg_variant 3)")
     ap.add_argument("--overlap", action="store_true",
                     help="the PCG section and whole steps with the overlapped exchange (peer_overlap) on and off")
     args = ap.parse_args()
@@ -72,6 +73,8 @@ def main():
         section_5(args, rank, blocks, gcfg, rank_cfg, rng, check)
     elif args.fused:
         section_3(args, rank, gcfg, rank_cfg, rng, check)
+    elif args.cg1:
+        section_6(args, rank, gcfg, rank_cfg, rng, check)
     elif args.overlap:
         section_3(args, rank, gcfg, rank_cfg, rng, check)
         for on in (1, 0):
@@ -261,6 +264,39 @@ def section_5(args, rank, blocks, gcfg, rank_cfg, rng, check):
     check("mg-pcg residual history bit-exact", np.array_equal(gpu.residual_history(), ho))
     gpu.close()
     ora.close()
+
+
+def section_6(args, rank, gcfg, rank_cfg, rng, check):
+    # 6. opt-in single-reduction CG (cg_variant 3): one reduction point and one ghost exchange per iteration ------
+    for fixed in (0, 11):
+        ora = Oracle(gcfg(fixed_iters=fixed))
+        ora.set_cg_algorithm(1)
+        vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
+        for f, a in vel.items():
+            ora.set(f, a)
+        ora.add_inputs()
+        ora.build_rhs()
+        io, ro = ora.pcg_solve()
+        po, ho = ora.get(K.PRESSURE), ora.residual_history()
+        for name, tune in (("mailboxes in the stencil kernel's last block", {"peer_halo": 1}), ("NCCL all-gather", {"peer_halo": 0})):
+            gpu = Solver(rank_cfg(fixed_iters=fixed))
+            gpu.set_tuning("cg_variant", 3)
+            for k, v in tune.items():
+                gpu.set_tuning(k, v)
+            for rep in range(2):
+                for f, a in vel.items():
+                    gpu.set(f, a[block_slices(gpu, f)])
+                gpu.add_inputs()
+                gpu.build_rhs()
+                ig, rg = gpu.pcg_solve()
+                tag = f"[{name}, fixed={fixed}, solve {rep}]"
+                check(f"cg1 iterations {tag}", abs(ig - io) <= 1, f"{ig} vs {io}")
+                e = rel_l2(gpu.get(K.PRESSURE), po[block_slices(gpu, K.PRESSURE)])
+                check(f"cg1 pressure 1e-10 {tag}", e < 1e-10, f"rel l2 {e}")
+                check(f"cg1 pressure bit-exact {tag}", np.array_equal(gpu.get(K.PRESSURE), po[block_slices(gpu, K.PRESSURE)]))
+                check(f"cg1 residual history bit-exact {tag}", ig == io and np.array_equal(gpu.residual_history(), ho))
+            gpu.close()
+        ora.close()
 
 
 if __name__ == "__main__":

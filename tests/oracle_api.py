@@ -47,6 +47,7 @@ def load():
         d.cfo_set_num_threads.argtypes = [C.c_int]
         d.cfo_set_num_threads.restype = C.c_int
         d.cfo_set_fixed_iters.argtypes = [C.c_void_p, C.c_int]
+        d.cfo_set_cg_algorithm.argtypes = [C.c_void_p, C.c_int]
         d.cfo_set_accumulation.argtypes = [C.c_void_p, C.c_int]
         d.cfo_set_mg_max_levels.argtypes = [C.c_void_p, C.c_int]
         d.cfo_mg_num_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
@@ -71,6 +72,11 @@ class Oracle(Context):
     def set_accumulation(self, exact):
         """exact=True (default): double-double sums; False: plain double like the reference."""
         self.lib.dll.cfo_set_accumulation(self.h, 1 if exact else 0)
+
+    def set_cg_algorithm(self, algorithm):
+        """0: Cajita's ReferenceConjugateGradient loop (default); 1: the single-reduction form (the product's
+        cg_variant 3), the same iterates in exact arithmetic."""
+        self.lib.check(self.lib.dll.cfo_set_cg_algorithm(self.h, int(algorithm)), self.h)
 
     def set_fixed_iters(self, iters):
         """the following solves run exactly `iters` iterations (0: back to the stopping test)."""

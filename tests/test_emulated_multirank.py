@@ -584,3 +584,41 @@ def test_exchange_inside_the_kernels_whole_steps(emul):
 
     for exact, err in run_ranks(emul, cfg, 8, body, None, peer=True):
         assert exact == [] and max(err.values()) < 1e-12, (exact, err)
+
+
+@pytest.mark.parametrize("peer", [True, False], ids=["peer mailboxes", "NCCL all-gather"])
+@pytest.mark.parametrize("world,blocks,cells", [(8, None, (24, 20, 18)), (2, (2, 1, 1), (128, 24, 20)), (4, (1, 2, 2), (23, 20, 21))])
+def test_single_reduction_cg_block_decomposed(emul, world, blocks, cells, peer):
+    """cg_variant 3 on several blocks: ONE reduction point (three sums through the mailboxes in the stencil kernel's
+    last block, or one all-gather) and one ghost exchange (the faces of r) per iteration; bit for bit the
+    single-block checker's statement of the same algorithm, to convergence and with fixed iterations."""
+    if not emul.tma:
+        pytest.skip("the plain-loop stand-in has no mailbox form")
+    for fixed in (0, 9):
+        cfg = cfg3(cells=cells, fixed_iters=fixed)
+        ora = Oracle(cfg)
+        ora.set_cg_algorithm(1)
+        rng = np.random.default_rng(85)
+        vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
+        for f, a in vel.items():
+            ora.set(f, a)
+        ora.add_inputs()
+        ora.build_rhs()
+        io, ro = ora.pcg_solve()
+        po, ho = ora.get(K.PRESSURE), ora.residual_history()
+
+        def body(ctx, rank):
+            ctx.set_tuning("cg_variant", 3)
+            out = []
+            for _ in range(2):  # twice: sequence numbers and vectors carry over
+                for f, a in vel.items():
+                    ctx.set(f, a[block_slices(ctx, f)])
+                ctx.add_inputs()
+                ctx.build_rhs()
+                ig, rg = ctx.pcg_solve()
+                out.append((ig, rg, np.array_equal(ctx.get(K.PRESSURE), po[block_slices(ctx, K.PRESSURE)]),
+                            np.array_equal(ctx.residual_history(), ho)))
+            return out
+
+        for out in run_ranks(emul, cfg, world, body, blocks, peer=peer):
+            assert out == [(io, ro, True, True)] * 2, (fixed, out)

@@ -34,3 +34,11 @@ def test_overlapped_exchange_matches_single_block_oracle(world, blocks):
     (tests/test_emulated_multirank.py::test_overlapped_exchange_on_every_block_grid on the CPU.)"""
     extra = ["--overlap"] + (["--blocks"] + [str(b) for b in blocks] if blocks else [])
     _run_worker(world, extra, cells=(128, 24, 20) if blocks == (2, 1, 1) else (48, 40, 36))
+
+
+@pytest.mark.parametrize("world,blocks", [(2, None), (2, (2, 1, 1)), (4, None), (8, None)])
+def test_single_reduction_cg_matches_single_block_oracle(world, blocks):
+    """`cg_variant` 3 (opt-in): one reduction point (three sums) and one ghost exchange (faces of r) per iteration, over
+    the NVLink mailboxes and over NCCL; bit for bit the single-block checker's statement of the same algorithm."""
+    extra = ["--cg1"] + (["--blocks"] + [str(b) for b in blocks] if blocks else [])
+    _run_worker(world, extra, cells=(128, 24, 20) if blocks == (2, 1, 1) else (48, 40, 36))

@@ -443,7 +443,8 @@ def multi_gpu_extras(args, s, extra, dist, torch, np, rank, world, local, blocks
         s.set_tuning("peer_overlap", int(DEFAULT_PEER_OVERLAP))
         extra["exchange_schedules"] = sched
 
-    # 2. strong scaling (BASELINE configs[3]): cells^3 global over all ranks
+    # 2. strong scaling (BASELINE configs[3]): cells^3 global over all ranks, each exchange schedule and the opt-in
+    #    single-reduction form
     if args.scaling == "weak":
         try:
             cfg_s, g_s = make_config(args, rank, world, blocks, scaling="strong")
@@ -452,14 +453,25 @@ def multi_gpu_extras(args, s, extra, dist, torch, np, rank, world, local, blocks
             ss = Solver(cfg_s)
             ss.fill_synthetic_velocity(0)
             ss.build_rhs()
-            r = timed(ss, steps=5, warm=3)
-            if "iterations_per_s" in r:
-                r.update({"global_cells": list(g_s), "blocks": list(blocks), "cg_iters_per_step": args.iters,
-                          "cells_local": int(np.prod(ss.owned_extent(K.QUANTITY))), "peer_mode": ss.stats()["peer_mode"],
-                          "peer_overlap": ss.stats()["peer_overlap"],
-                          "note": "global CG iterations/s of the fixed %d^3 problem on %d GPUs; divide by the N = 1 "
-                                  "headline value for the speed-up" % (args.cells, world)})
-            extra["strong_scaling"] = r
+            out = {"global_cells": list(g_s), "blocks": list(blocks), "cg_iters_per_step": args.iters,
+                   "cells_local": int(np.prod(ss.owned_extent(K.QUANTITY))), "peer_mode": ss.stats()["peer_mode"],
+                   "unit": "global CG iterations/s of the fixed %d^3 problem on %d GPUs (divide by the N = 1 headline "
+                           "value for the speed-up)" % (args.cells, world)}
+            for name, tune in (("peer_exchange_kernel_after_each_phase", {"cg_variant": 1, "peer_overlap": 0}),
+                               ("peer_overlapped", {"cg_variant": 1, "peer_overlap": 1}),
+                               ("single_reduction_cg_variant3", {"cg_variant": 3}),
+                               ("nccl_sendrecv_allgather", {"cg_variant": 1, "peer_overlap": 0, "peer_halo": 0})):
+                try:
+                    for k, v in tune.items():
+                        ss.set_tuning(k, v)
+                    out[name] = timed(ss, steps=5, warm=3)
+                except Exception as e:  # noqa: BLE001
+                    out[name] = {"error": repr(e)[:300]}
+            default_key = "peer_overlapped" if DEFAULT_PEER_OVERLAP else "peer_exchange_kernel_after_each_phase"
+            if "iterations_per_s" in out.get(default_key, {}):
+                out["iterations_per_s"] = out[default_key]["iterations_per_s"]
+                out["schedule"] = default_key
+            extra["strong_scaling"] = out
             ss.close()
         except Exception as e:  # noqa: BLE001
             extra["strong_scaling"] = {"error": repr(e)[:300]}

@@ -178,17 +178,23 @@ int enqueue_iteration( cfb_ctx* c )
             cudaEventRecord( e[0], c->stream );
         if ( peer_overlapped( c ) )
         {
-            // Overlapped exchange.  Main stream: phase A (its last block runs the (r.z, r.r) mailboxes) ->
-            // interior units of phase B -> [ghosts have landed] -> boundary units (their last block runs the p.Ap
-            // mailboxes).  Side stream: the faces of r under the interior units, the faces of the new search
-            // direction under the next phase A and interior units.
+            // Overlapped exchange.
+            //   main stream: phase A (its last block runs the (r.z, r.r) mailboxes) -> interior units of phase B
+            //                -> [boundary units done] -> next phase A ...
+            //   side stream: [phase A done] -> faces of r to the neighbours, wait for theirs -> boundary units of phase B
+            //                -> faces of the new search direction, wait for theirs (under the interior units and the
+            //                next phase A) -> ...
+            // The side stream has the higher priority, so the boundary units are scheduled ahead of the interior
+            // units still waiting; the two launches of phase B run concurrently and share one ticket counter: the
+            // block that draws the last ticket, whichever launch it belongs to, runs the p.Ap mailboxes.
             // Nobody overwrites a ghost layer that may still be read.  A rank stores its r faces after its own
             // phase A, which it enters only behind the p.Ap mailboxes of the previous iteration, i.e. after every
             // rank's boundary units — the readers of the old r ghosts — are done.  It stores the faces of the new
-            // search direction after its boundary units, hence behind the (r.z, r.r) mailboxes of this iteration,
-            // i.e. after every rank's boundary units of the previous iteration — the last readers of that
-            // buffer's ghosts (the direction is double-buffered).  The x staging slots (one for r, one per
-            // direction buffer) follow the same argument: the receiver scatters a slot before its boundary units.
+            // search direction after its boundary units, which ran behind the r-face handshake with its
+            // neighbours, who raised their flag after their own phase A, i.e. after their boundary units of the
+            // previous iteration — the last readers of that buffer's ghosts (the direction is double-buffered).
+            // The x staging slots (one for r, one per direction buffer) follow the same argument: the receiver
+            // scatters a slot on its side stream before its boundary units.
             n += launch_cg_rupdate_mail( c );
             note_rc( c, check_cuda( c, cudaEventRecord( c->ev_phase[0], c->stream ) ) );
             if ( e )
@@ -198,11 +204,11 @@ int enqueue_iteration( cfb_ctx* c )
                 cudaEventRecord( e[2], c->stream );
             }
             note_rc( c, peer_faces_async( c, 0, -1, c->ev_phase[0] ) );
-            n += launch_cg_fused( c, 1 );
-            note_rc( c, peer_faces_join( c ) );
-            n += launch_cg_fused_mail( c, 2 );
-            note_rc( c, check_cuda( c, cudaEventRecord( c->ev_phase[1], c->stream ) ) );
-            note_rc( c, peer_faces_async( c, 1, c->pcur ^ 1, c->ev_phase[1] ) );
+            n += launch_cg_fused_mail( c, 2, true );
+            note_rc( c, check_cuda( c, cudaEventRecord( c->ev_bnd, c->comm_stream ) ) );
+            note_rc( c, peer_faces_async( c, 1, c->pcur ^ 1, nullptr ) );
+            n += launch_cg_fused_mail( c, 1, false );
+            note_rc( c, check_cuda( c, cudaStreamWaitEvent( c->stream, c->ev_bnd, 0 ) ) );
             cg_select_p( c, c->pcur ^ 1 );
             if ( e )
             {
@@ -211,22 +217,17 @@ int enqueue_iteration( cfb_ctx* c )
             }
             return n;
         }
-        const bool fusedA = peer && c->peer_fused; // exchange inside phase A / A'
         if ( c->cg_variant == 2 )
         {
             if ( c->cfg.use_nccl && !peer )
                 note_rc( c, halo_exchange_cells( c, c->cg_p, 1 ) );
-            n += fusedA ? launch_stencil_rupdate_peer( c ) : launch_stencil_rupdate( c );
+            n += launch_stencil_rupdate( c );
         }
-        else if ( fusedA )
-            n += launch_cg_rupdate_peer( c );
         else
             n += launch_cg_rupdate( c );
         if ( e )
             cudaEventRecord( e[4], c->stream );
-        if ( fusedA )
-            ;
-        else if ( peer )
+        if ( peer )
             note_rc( c, peer_exchange( c, 1, true, -1, !peer_xstaged( c ) ) ); // r faces -> neighbours, (rz_new, rr) -> all
         else if ( c->cfg.use_nccl )
             note_rc( c, cg_global_sum( c, 1 ) );
@@ -235,9 +236,7 @@ int enqueue_iteration( cfb_ctx* c )
             cudaEventRecord( e[1], c->stream );
             cudaEventRecord( e[2], c->stream );
         }
-        if ( peer && c->peer_fused )
-            n += launch_cg_fused_peer( c ); // the same, exchange inside the kernel
-        else if ( peer )
+        if ( peer )
         {
             n += launch_cg_fused( c, 0 );
             if ( e )
@@ -269,7 +268,7 @@ int enqueue_iteration( cfb_ctx* c )
         cg_select_p( c, c->pcur ^ 1 ); // phase B wrote the new p into the other buffer
         if ( e )
         {
-            if ( !( peer || c->cfg.use_nccl ) || ( peer && c->peer_fused ) )
+            if ( !( peer || c->cfg.use_nccl ) )
                 cudaEventRecord( e[5], c->stream );
             cudaEventRecord( e[3], c->stream );
         }
@@ -528,6 +527,7 @@ int cfb_create( const cfb_config* cfg, cfb_ctx** out )
     c->sm_count = prop.multiProcessorCount;
     CFB_CUDA( c, cudaSetDevice( c->device ) );
 
+    c->flat_2d = D == 2;
     Geo& g = c->g;
     g.D = D;
     g.h = cfg->halo_cell_width;
@@ -728,7 +728,7 @@ int cfb_destroy( cfb_ctx* c )
     for ( auto& e : c->ev )
         if ( e )
             cudaEventDestroy( e );
-    for ( cudaEvent_t e : { c->ev_phase[0], c->ev_phase[1], c->ev_ghost } )
+    for ( cudaEvent_t e : { c->ev_phase[0], c->ev_phase[1], c->ev_ghost, c->ev_bnd } )
         if ( e )
             cudaEventDestroy( e );
     for ( auto& row : c->kev )
@@ -1128,10 +1128,13 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->flat_2d = value != 0;
     else if ( k == "advect_tile" )
         c->advect_tile = value != 0;
-    else if ( k == "peer_fused" )
-        c->peer_fused = value != 0;
     else if ( k == "peer_overlap" )
         c->peer_overlap = value != 0;
+    else if ( k == "mg_inorder" )
+    {
+        c->mg_inorder = value != 0;
+        return mg_set_coarse_kernel( c, c->mg_coarse ); // (drops a captured cycle: it holds the old launch shapes)
+    }
     else if ( k == "mg_graph" )
         return mg_set_graph( c, value != 0 );
     else if ( k == "mg_coarse_kernel" )

@@ -146,19 +146,18 @@ struct cfb_ctx
     int st_tx = 64, st_ty = 16, st_stages = 4, st_zc = 64;
     int poll_every = 0; // 0 = auto
     // "flat_2d" tuning key: two-dimensional runs skip the loads of the two zero ghost planes in the TMA kernels
-    // (FLAT instantiations); off until it has run on a B200
-    bool flat_2d = false;
+    // (FLAT instantiations).  On for every 2-D context since it was measured (8192^2, 50 fixed iterations:
+    // 658 vs 581 iterations/s, profiles/r2_bench_n1.json extra.flat_2d_probe); same values bit for bit.
+    bool flat_2d = false; // set in cfb_create
     // "advect_tile" tuning key: 32 x 2 x 2 entity tiles per block in the advection kernel instead of rows
     bool advect_tile = false;
-    // "peer_fused" tuning key (several blocks, NVLink peer memory): phase B stores its block-face cells into the
-    // neighbours' ghost layers itself and its last block runs the mailbox exchange — no exchange kernel after it
-    bool peer_fused = false;
     // "peer_overlap" tuning key (several blocks, NVLink peer memory, two-kernel form): the reduction of each phase
     // runs in the last block of the compute kernel (mailboxes), the faces travel on the side stream under the
     // interior units of phase B (r) and under the next phase A (search direction); boundary units run last
     bool peer_overlap = false;
     cudaEvent_t ev_phase[2] = { nullptr, nullptr }; // main stream: phase A / phase B of the running iteration done
-    cudaEvent_t ev_ghost = nullptr;                 // side stream: every face transfer enqueued so far has landed
+    cudaEvent_t ev_ghost = nullptr;                 // side stream: everything enqueued there so far is done
+    cudaEvent_t ev_bnd = nullptr;                   // side stream: the boundary units of the running phase B are done
     bool side_busy = false;                         // face transfers enqueued since the last join
 
     // two-kernel CG iteration (kernels_fused.cu): tensor maps of cg_r / cg_p, tiling, unit list
@@ -227,6 +226,7 @@ struct cfb_ctx
     int precond = CFB_PRECOND_JACOBI;
     int mg_max_levels = 0; // 0 = as many as the block allows
     bool mg_graph = false; // "mg_graph" tuning key: replay the V-cycle as a CUDA graph (one block)
+    bool mg_inorder = false; // "mg_inorder" tuning key: non-reducing multigrid launches use one block per 256 cells, in order
     bool mg_coarse = false; // "mg_coarse_kernel" tuning key: the coarse end of the cycle in one single-CTA kernel
     MgStage* mg = nullptr;
 };
@@ -312,7 +312,7 @@ inline bool cg_peer_mode( const cfb_ctx* c )
 inline bool peer_xstaged( const cfb_ctx* c );
 inline bool peer_overlapped( const cfb_ctx* c )
 {
-    return cg_peer_mode( c ) && c->peer_overlap && c->cg_variant == 1 && !c->peer_fused && !c->peer_xstage_reads &&
+    return cg_peer_mode( c ) && c->peer_overlap && c->cg_variant == 1 && !c->peer_xstage_reads &&
            !( c->g.D == 2 && c->flat_2d );
 }
 // peer mode with x neighbours and tiles that end exactly on the block: phase B reads its x ghosts
@@ -339,11 +339,8 @@ int cg1_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid );
 int fused_setup( cfb_ctx* c );                // tensor maps of cg_r, cg_p + the unit list
 int launch_cg_rupdate( cfb_ctx* c );          // phase A: r -= alpha q, sum r^2, sum r.Minv r
 int launch_cg_fused( cfb_ctx* c, int which ); // phase B: 0 = all units, 1 = interior, 2 = boundary
-int launch_cg_fused_peer( cfb_ctx* c );        // phase B + its ghost / reduction exchange in one kernel (peer_fused)
 int launch_cg_rupdate_mail( cfb_ctx* c );      // phase A, its last block runs the mailbox reduction (peer_overlap)
-int launch_cg_fused_mail( cfb_ctx* c, int which ); // phase B units (1 interior / 2 boundary), the same (peer_overlap)
-int launch_cg_rupdate_peer( cfb_ctx* c );      // phase A + its ghost / reduction exchange in one kernel (peer_fused)
-int launch_stencil_rupdate_peer( cfb_ctx* c ); // phase A' of the 64-byte iteration, the same
+int launch_cg_fused_mail( cfb_ctx* c, int which, bool side ); // phase B units (1 interior / 2 boundary), the same
 int launch_cg_finish( cfb_ctx* c );
 // output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
 int output_write( cfb_ctx* c, const char* dir, int time_step );
@@ -374,7 +371,7 @@ int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpac
 // boundary layers of cg_r (kind 0) or of search-direction buffer `pbuf` (kind 1) into the neighbours' ghost
 // layers, tell each neighbour, wait until each neighbour has told me, scatter the x faces I received; then record
 // c->ev_ghost.  No reduction here: the compute kernels' last blocks run the mailboxes (device_peer.cuh).
-int peer_faces_async( cfb_ctx* c, int kind, int pbuf, cudaEvent_t after );
+int peer_faces_async( cfb_ctx* c, int kind, int pbuf, cudaEvent_t after ); // after == nullptr: no wait
 int peer_faces_join( cfb_ctx* c ); // main stream waits for everything peer_faces_async has enqueued
 int halo_exchange_fields( cfb_ctx* c, int version );             // width-h exchange of q,u,v,w
 int halo_sendrecv_slots( cfb_ctx* c, const size_t counts[6], cudaStream_t st ); // d_halo_send/recv[s] <-> nbr[s]

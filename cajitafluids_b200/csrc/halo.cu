@@ -567,6 +567,7 @@ int peer_setup( cfb_ctx* c )
         CFB_CUDA( c, cudaEventCreateWithFlags( &c->ev_ghost, cudaEventDisableTiming ) );
         CFB_CUDA( c, cudaEventCreateWithFlags( &c->ev_phase[0], cudaEventDisableTiming ) );
         CFB_CUDA( c, cudaEventCreateWithFlags( &c->ev_phase[1], cudaEventDisableTiming ) );
+        CFB_CUDA( c, cudaEventCreateWithFlags( &c->ev_bnd, cudaEventDisableTiming ) );
     }
     return CFB_OK;
 }
@@ -731,7 +732,8 @@ int peer_faces_async( cfb_ctx* c, int kind, int pbuf, cudaEvent_t after )
         }
         cells += (long long)f.ext[0] * f.ext[1] * f.ext[2];
     }
-    CFB_CUDA( c, cudaStreamWaitEvent( c->comm_stream, after, 0 ) );
+    if ( after )
+        CFB_CUDA( c, cudaStreamWaitEvent( c->comm_stream, after, 0 ) );
     const int grid = (int)std::min<long long>( std::max<long long>( ( cells + 1023 ) / 1024, 1 ), 2ll * c->sm_count );
     cg_face_kernel<<<grid, 256, 0, c->comm_stream>>>( g, a );
     c->stats.kernel_launches += 1;

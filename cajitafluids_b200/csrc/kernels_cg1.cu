@@ -13,7 +13,7 @@
 //
 // 88 B/cell against 72: slower where bandwidth rules, meant for small blocks per GPU where the reduction latency
 // does.  Not bit-identical to the other forms (different recurrences): iteration counts within +-1, pressure to
-// rounding; bit-identical to the checker's statement of the same algorithm (cfo_set_cg_algorithm( 1 )).
+// rounding; bit-identical to the checker's statement of the same algorithm.
 // Arrays: p = cg_pbuf[0], s = cg_pbuf[1] (the search direction needs no double buffer here), w = cg_q.
 #include "cfb_internal.h"
 #include "device_geo.cuh"

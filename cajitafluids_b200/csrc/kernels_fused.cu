@@ -72,15 +72,12 @@ __global__ void __launch_bounds__( NT, 3 )
     const int batch = tyr * RU;
     const bool odd = g.n[0] & 1;
     dd_t rr = { 0.0, 0.0 }, rz = { 0.0, 0.0 };
-    bool stored = false; // PF: this thread has written into a neighbour's ghost layer
     for ( int row0 = blockIdx.x * batch; row0 < rows; row0 += gridDim.x * batch )
     {
         // rows of this thread: row0 + ry + u * tyr
         int cyz[RU];
         long long ro[RU];
         bool ok[RU];
-        int rj[RU], rk[RU];     // PF: the row's (j, k)
-        unsigned rmask[RU];     // PF: faces whose (j, k) range holds the row
 #pragma unroll
         for ( int u = 0; u < RU; ++u )
         {
@@ -90,18 +87,6 @@ __global__ void __launch_bounds__( NT, 3 )
             const int j = row - k * g.n[1];
             cyz[u] = wall_count( g, 1, j + g.off[1] ) + wall_count( g, 2, k + g.off[2] );
             ro[u] = geo_off( g, 0, j, k );
-            if constexpr ( PF )
-            {
-                rj[u] = j;
-                rk[u] = k;
-                rmask[u] = 0u;
-                for ( int f = 0; f < pf.nface; ++f )
-                {
-                    const PeerFace& F = pf.f[f];
-                    if ( j >= F.lo[1] && j < F.lo[1] + F.ext[1] && k >= F.lo[2] && k < F.lo[2] + F.ext[2] )
-                        rmask[u] |= 1u << f;
-                }
-            }
         }
         for ( int ip = lx; ip < npx; ip += txp )
         {
@@ -146,25 +131,8 @@ __global__ void __launch_bounds__( NT, 3 )
                 }
                 else
                     r[ro[u] + i] = v.x;
-                if constexpr ( PF )
-                {
-                    if ( rmask[u] )
-                    {
-                        peer_store_cell( pf, rmask[u], i, rj[u], rk[u], v.x );
-                        if ( two )
-                            peer_store_cell( pf, rmask[u], i + 1, rj[u], rk[u], v.y );
-                        stored = true;
-                    }
-                }
             }
         }
-    }
-    if constexpr ( PF )
-    {
-        // my ghost stores are performed system-wide before the block's ticket is drawn (the barriers inside the
-        // block reduction stand between this fence and thread 0's ticket)
-        if ( stored )
-            __threadfence_system();
     }
     dd_t vals[2] = { rr, rz };
     if ( block_reduce_finalize<NT, 2>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
@@ -248,7 +216,8 @@ struct FusedArgs
 // FLAT: two-dimensional runs (one owned plane between two zero ghost planes, see Geo): the z neighbours are
 // zero by construction, so the two ghost planes are neither loaded nor recomputed — the 2-D traffic of r and p
 // drops from three planes to the one that exists.  A template flag: the 3-D instantiations are untouched.
-// PF: the exchange inside (see PeerFusedArgs); a template flag, the other instantiations are untouched.
+// PF: the block that draws the phase's last ticket runs the mailbox reduction of p.Ap (device_peer.cuh); a template
+// flag, the other instantiations are untouched.
 template <class C, bool XS, bool FLAT, bool PF>
 __global__ void __launch_bounds__( C::NT, C::CTAS )
     cg_fused_kernel( const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_p,
@@ -284,19 +253,6 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     const int kend = min( kbeg + a.zc, g.n[2] );
     const int nplanes = kend - kbeg;
     const int nloads = nplanes + 2; // planes kbeg-1 .. kend
-
-    // PF: which block faces does this unit touch?  (uniform over the CTA; 0 for the interior units)
-    unsigned fmask = 0u;
-    if constexpr ( PF )
-    {
-        for ( int f = 0; f < pf.nface; ++f )
-        {
-            const PeerFace& F = pf.f[f];
-            if ( x0 < F.lo[0] + F.ext[0] && x0 + TX > F.lo[0] && y0 < F.lo[1] + F.ext[1] && y0 + TY > F.lo[1] &&
-                 kbeg < F.lo[2] + F.ext[2] && kend > F.lo[2] )
-                fmask |= 1u << f;
-        }
-    }
 
     const int i0 = x0 + 2 * lx;
     const bool vx0 = i0 < g.n[0], vx1 = i0 + 1 < g.n[0];
@@ -466,17 +422,6 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
                         prow[go] = v.x;
                         xrow[go] = fma( alpha, pv.x, xc[r].x );
                     }
-                    if constexpr ( PF )
-                    {
-                        if ( fmask )
-                        {
-                            const int j = y0 + wy + r * WY, k = kbeg + l - 1;
-                            if ( vx0 )
-                                peer_store_cell( pf, fmask, i0, j, k, v.x );
-                            if ( vx1 )
-                                peer_store_cell( pf, fmask, i0 + 1, j, k, v.y );
-                        }
-                    }
                 }
             }
         }
@@ -605,13 +550,6 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     {
         __shared__ dd_t s_red[C::NT / 32];
         __shared__ bool s_last;
-        if constexpr ( PF )
-        {
-            // my ghost stores are performed system-wide before the ticket is drawn (the barrier inside the block
-            // sum stands between this fence and thread 0's ticket)
-            if ( fmask )
-                __threadfence_system();
-        }
         dd_t s = dd_block_sum<C::NT>( acc, s_red );
         const unsigned bid = (unsigned)a.unit_base + blockIdx.x;
         if ( tid == 0 )
@@ -663,7 +601,7 @@ typedef CUresult ( *PFN_encodeTiled )( CUtensorMap*, CUtensorMapDataType, cuuint
                                        CUtensorMapFloatOOBfill );
 
 template <class C>
-int launch_fused_cfg( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedArgs* pf )
+int launch_fused_cfg( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedArgs* pf, cudaStream_t st )
 {
     static bool attr_set = false;
     if ( !attr_set )
@@ -678,47 +616,49 @@ int launch_fused_cfg( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedA
     const bool xs = a.gxr[0] || a.gxr[1];
     const bool flat = c->g.D == 2 && c->flat_2d; // one owned plane between two zero ghost planes
     const NoPeerArgs none{};
-    if ( pf ) // (launch_cg_fused_peer has made sure that neither xs nor flat applies)
-        cg_fused_kernel<C, false, false, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+    if ( pf ) // (peer_overlapped() has made sure that neither xs nor flat applies)
+        cg_fused_kernel<C, false, false, true><<<grid, C::NT, C::SMEM_BYTES, st>>>( c->tmap_fr, c->tmap_fp[c->pcur],
                                                                                           c->g, c->op, a, *pf );
     else if ( xs && flat )
-        cg_fused_kernel<C, true, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+        cg_fused_kernel<C, true, true, false><<<grid, C::NT, C::SMEM_BYTES, st>>>( c->tmap_fr, c->tmap_fp[c->pcur],
                                                                                          c->g, c->op, a, none );
     else if ( xs )
-        cg_fused_kernel<C, true, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+        cg_fused_kernel<C, true, false, false><<<grid, C::NT, C::SMEM_BYTES, st>>>( c->tmap_fr, c->tmap_fp[c->pcur],
                                                                                           c->g, c->op, a, none );
     else if ( flat )
-        cg_fused_kernel<C, false, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+        cg_fused_kernel<C, false, true, false><<<grid, C::NT, C::SMEM_BYTES, st>>>( c->tmap_fr, c->tmap_fp[c->pcur],
                                                                                           c->g, c->op, a, none );
     else
-        cg_fused_kernel<C, false, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( c->tmap_fr, c->tmap_fp[c->pcur],
+        cg_fused_kernel<C, false, false, false><<<grid, C::NT, C::SMEM_BYTES, st>>>( c->tmap_fr, c->tmap_fp[c->pcur],
                                                                                            c->g, c->op, a, none );
     return 1;
 }
 
-int dispatch_fused( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedArgs* pf = nullptr )
+int dispatch_fused( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedArgs* pf = nullptr, cudaStream_t st = nullptr )
 {
+    if ( !st )
+        st = c->stream;
     const int key = c->fu_tx * 10000 + c->fu_ty * 100 + c->fu_stages;
     switch ( key )
     {
     case 641603:
-        return launch_fused_cfg<FusedCfg<64, 16, 3>>( c, a, grid, pf );
+        return launch_fused_cfg<FusedCfg<64, 16, 3>>( c, a, grid, pf, st );
     case 641604:
-        return launch_fused_cfg<FusedCfg<64, 16, 4>>( c, a, grid, pf );
+        return launch_fused_cfg<FusedCfg<64, 16, 4>>( c, a, grid, pf, st );
     case 640803:
-        return launch_fused_cfg<FusedCfg<64, 8, 3>>( c, a, grid, pf );
+        return launch_fused_cfg<FusedCfg<64, 8, 3>>( c, a, grid, pf, st );
     case 640804:
-        return launch_fused_cfg<FusedCfg<64, 8, 4>>( c, a, grid, pf );
+        return launch_fused_cfg<FusedCfg<64, 8, 4>>( c, a, grid, pf, st );
     case 643202:
-        return launch_fused_cfg<FusedCfg<64, 32, 2>>( c, a, grid, pf );
+        return launch_fused_cfg<FusedCfg<64, 32, 2>>( c, a, grid, pf, st );
     case 643203:
-        return launch_fused_cfg<FusedCfg<64, 32, 3>>( c, a, grid, pf );
+        return launch_fused_cfg<FusedCfg<64, 32, 3>>( c, a, grid, pf, st );
     case 1280803:
-        return launch_fused_cfg<FusedCfg<128, 8, 3>>( c, a, grid, pf );
+        return launch_fused_cfg<FusedCfg<128, 8, 3>>( c, a, grid, pf, st );
     case 1280804:
-        return launch_fused_cfg<FusedCfg<128, 8, 4>>( c, a, grid, pf );
+        return launch_fused_cfg<FusedCfg<128, 8, 4>>( c, a, grid, pf, st );
     case 1281603:
-        return launch_fused_cfg<FusedCfg<128, 16, 3>>( c, a, grid, pf );
+        return launch_fused_cfg<FusedCfg<128, 16, 3>>( c, a, grid, pf, st );
     default:
         note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "unsupported fused tile configuration" ) );
         return 0;
@@ -857,20 +797,6 @@ static int launch_rupdate_impl( cfb_ctx* c, const PeerFusedArgs* pf )
 
 int launch_cg_rupdate( cfb_ctx* c ) { return launch_rupdate_impl( c, nullptr ); }
 
-// Phase A with the exchange inside: replaces  launch_cg_rupdate( c ); peer_exchange( c, 1, true, -1, ... );
-int launch_cg_rupdate_peer( cfb_ctx* c )
-{
-    if ( peer_xstaged( c ) )
-    {
-        const int n = launch_cg_rupdate( c );
-        peer_exchange( c, 1, true, -1, false );
-        return n;
-    }
-    PeerFusedArgs pf{};
-    peer_faces( c, pf, c->peer_r );
-    return launch_rupdate_impl( c, &pf );
-}
-
 // Phase A whose last block runs the mailbox reduction of (r.z, r.r); no faces ("peer_overlap")
 int launch_cg_rupdate_mail( cfb_ctx* c )
 {
@@ -887,7 +813,7 @@ int launch_cg_finish( cfb_ctx* c )
 
 // phase B over all units (which = 0), or over the device unit list `c->d_units` split into
 // interior units [0, n_interior) (which = 1) and boundary units [n_interior, n_units) (which = 2).
-static int launch_cg_fused_impl( cfb_ctx* c, int which, const PeerFusedArgs* pf )
+static int launch_cg_fused_impl( cfb_ctx* c, int which, const PeerFusedArgs* pf, cudaStream_t st = nullptr )
 {
     FusedArgs a{};
     a.x = c->lhs;
@@ -927,49 +853,18 @@ static int launch_cg_fused_impl( cfb_ctx* c, int which, const PeerFusedArgs* pf 
         if ( grid == 0 )
             return 0;
     }
-    return dispatch_fused( c, a, grid, pf );
+    return dispatch_fused( c, a, grid, pf, st );
 }
 
 int launch_cg_fused( cfb_ctx* c, int which ) { return launch_cg_fused_impl( c, which, nullptr ); }
 
-// Phase B units whose last block (the one that draws the last of ALL the phase's tickets, i.e. a block of the
-// launch that comes last) runs the mailbox reduction of p.Ap; no faces ("peer_overlap").  Interior units read
-// no ghosts and are launched plain; the caller launches the boundary units through here.
-int launch_cg_fused_mail( cfb_ctx* c, int which )
+// Phase B units whose last block (the one that draws the last of ALL the phase's tickets, whichever launch it
+// belongs to) runs the mailbox reduction of p.Ap ("peer_overlap").  which = 1: interior units on the main stream,
+// 2: boundary units — `side`: on the side stream, behind the face transfers that deliver their ghosts; the two
+// launches run concurrently and share the ticket, so splitting the phase costs no extra wave of blocks.
+int launch_cg_fused_mail( cfb_ctx* c, int which, bool side )
 {
     PeerFusedArgs pf{};
     peer_mail_only( c, pf );
-    return launch_cg_fused_impl( c, which, &pf );
-}
-
-// Phase B over all units with the exchange inside (PeerFusedArgs): replaces
-//   launch_cg_fused( c, 0 ); peer_exchange( c, 0, false, c->pcur ^ 1, ... );
-// Falls back to exactly that pair when the fused form does not apply (x ghosts read from the staging areas,
-// two-dimensional runs without the ghost-plane loads).
-int launch_cg_fused_peer( cfb_ctx* c )
-{
-    const Geo& g = c->g;
-    if ( peer_xstaged( c ) || ( g.D == 2 && c->flat_2d ) )
-    {
-        const int n = launch_cg_fused( c, 0 );
-        peer_exchange( c, 0, false, c->pcur ^ 1, !peer_xstaged( c ) );
-        return n;
-    }
-    FusedArgs a{};
-    a.x = c->lhs;
-    a.p_old = c->cg_pbuf[c->pcur];
-    a.p = c->cg_pbuf[c->pcur ^ 1];
-    a.q = c->cg_q;
-    a.S = c->d_state;
-    a.partials = c->d_partials;
-    a.hx = 16;
-    int chunks;
-    fused_tiling( c, a.tiles_x, a.tiles_y, a.zc, chunks );
-    const int total = a.tiles_x * a.tiles_y * chunks;
-    a.units_total = total;
-    a.reverse = c->fu_reverse ? 1 : 0;
-    a.store_q = c->cg_variant == 2 ? 0 : 1;
-    PeerFusedArgs pf{};
-    peer_faces( c, pf, c->peer_p[c->pcur ^ 1] );
-    return dispatch_fused( c, a, total, &pf );
+    return launch_cg_fused_impl( c, which, &pf, side ? c->comm_stream : c->stream );
 }

@@ -81,8 +81,8 @@ struct StencilArgs
 //         iteration's only reduction point are taken on the march: sum r^2, sum r.u, sum w.u (16 B/cell).
 // FLAT: two-dimensional runs (one owned plane between two zero ghost planes): the z neighbours are zero by
 // construction and their planes are not loaded.  A template flag: the 3-D instantiations are untouched.
-// PF (MODE 1 only, "peer_fused"): the faces of the new r go into the neighbours' ghost layers from here and the
-// last block runs the mailbox exchange of (r.z, r.r) — device_peer.cuh; no exchange kernel after phase A'.
+// PF (MODE 1 and 2): the block that draws the last ticket runs the mailbox reduction of the kernel's sums over NVLink
+// peer memory (device_peer.cuh).
 template <class C, int MODE, bool FLAT, bool PF>
 __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) )
     stencil7_dot_tma( const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geo g,
@@ -132,18 +132,6 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     const int kend = min( kbeg + a.zc, g.n[2] );
     const int nplanes = kend - kbeg; // planes to compute
     const int nloads = nplanes + 2;  // planes kbeg-1 .. kend
-    // PF: which block faces does this unit touch?  (uniform over the CTA; 0 for the interior units)
-    unsigned fmask = 0u;
-    if constexpr ( PF )
-    {
-        for ( int f = 0; f < pf.nface; ++f )
-        {
-            const PeerFace& F = pf.f[f];
-            if ( x0 < F.lo[0] + F.ext[0] && x0 + TX > F.lo[0] && y0 < F.lo[1] + F.ext[1] && y0 + TY > F.lo[1] &&
-                 kbeg < F.lo[2] + F.ext[2] && kend > F.lo[2] )
-                fmask |= 1u << f;
-        }
-    }
 
     // TMA box origin (array coordinates): 2 columns left of the tile, 1 row below, plane kbeg-1
     const int cx = a.hx + x0 - 2;
@@ -349,17 +337,6 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
                         dd_acc( acc, rv * rv );
                         dd_acc( acc2, ( op.minv[w0] * rv ) * rv );
                     }
-                    if constexpr ( PF )
-                    {
-                        if ( fmask )
-                        {
-                            const int j = y0 + wy + r * WY, k = kbeg + it;
-                            if ( vx0 )
-                                peer_store_cell( pf, fmask, i0, j, k, fma( nalpha, a0, rcur[r].x ) );
-                            if ( vx1 )
-                                peer_store_cell( pf, fmask, i0 + 1, j, k, fma( nalpha, a1, rcur[r].y ) );
-                        }
-                    }
                 }
             }
             zm[r] = c;
@@ -412,12 +389,6 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     }
     else
     {
-        if constexpr ( PF )
-        {
-            // my ghost stores are performed system-wide before the block's ticket is drawn
-            if ( fmask )
-                __threadfence_system();
-        }
         dd_t vals[2] = { acc, acc2 };
         if ( block_reduce_finalize<C::NT, 2>( vals, a.partials, a.pstride, &a.S->ticket[1] ) )
         {
@@ -687,18 +658,3 @@ int launch_cg1_stencil( cfb_ctx* c, int init, bool mail )
 
 // phase A' of the 64-byte iteration (cg_variant 2): r -= alpha (A p) with q recomputed, sum r^2, sum r.M^-1 r
 int launch_stencil_rupdate( cfb_ctx* c ) { return launch_stencil( c, 1 ); }
-
-// the same with the ghost exchange of r and the (r.z, r.r) exchange inside: replaces
-//   launch_stencil_rupdate( c ); peer_exchange( c, 1, true, -1, ... );
-int launch_stencil_rupdate_peer( cfb_ctx* c )
-{
-    if ( peer_xstaged( c ) || ( c->g.D == 2 && c->flat_2d ) || c->st_variant == 1 )
-    {
-        const int n = launch_stencil_rupdate( c );
-        peer_exchange( c, 1, true, -1, !peer_xstaged( c ) );
-        return n;
-    }
-    PeerFusedArgs pf{};
-    peer_faces( c, pf, c->peer_r );
-    return launch_stencil( c, 1, &pf );
-}

@@ -309,17 +309,23 @@ int cfb_get_stats( const cfb_ctx* ctx, cfb_stats* out );
 int cfb_reset_stats( cfb_ctx* ctx );
 /* CG residual history of the last solve (sqrt(sum r^2) after each iteration), up to n entries. */
 int cfb_residual_history( const cfb_ctx* ctx, double* hist, int n, int* count );
-/* Tuning hook (never changes results; unknown keys return CFB_ERR_INVALID).  Keys:
- *   cg_variant 1|0|2      CG iteration form: two kernels 72 B/cell (default), three kernels 88 B, two kernels 64 B
+/* Tuning hook (unknown keys and out-of-range values return CFB_ERR_INVALID; a tile combination nobody instantiated is
+ * refused by the solve that would use it).  No key changes results, except that cg_variant 3 is a different —
+ * mathematically equivalent — recurrence (iteration counts within +-1 of the others).  Keys:
+ *   cg_variant 1|0|2|3    CG iteration form: two kernels 72 B/cell (default), three kernels 88 B, two kernels 64 B
+ *                         (q never stored), 3 = opt-in single-reduction (Chronopoulos-Gear) form: two kernels 88 B,
+ *                         ONE reduction point and one ghost exchange per iteration
  *   stencil_variant, stencil_tx, stencil_ty, stencil_stages, stencil_zc      tiling of the stencil7 + dot kernel
  *   fused_auto, fused_tx, fused_ty, fused_stages, fused_zc, fused_reverse, rupdate_ctas   tiling of the two-kernel form
- *   flat_2d 0|1           2-D runs: do not load the two zero ghost planes in the TMA kernels (default 0)
+ *   flat_2d 0|1           2-D runs: do not load the two zero ghost planes in the TMA kernels (default 1 in 2-D)
  *   advect_tile 0|1       advection kernel: 32 x 2 x 2 entity tiles per block instead of rows (default 0)
  *   poll_every n          convergence polling interval in iterations (0 = auto)
  *   peer_halo 0|1         ghost exchange over NVLink peer memory (default when available) or NCCL send/recv
- *   overlap_halo, peer_xstage      exchange schedules (see csrc/halo.cu)
- *   peer_fused 0|1        phase B of the CG iteration does its ghost / reduction exchange itself (default 0)
- *   mg_graph, mg_coarse_kernel     multigrid V-cycle as a CUDA graph / coarse levels in one kernel (one block)
+ *   peer_overlap 0|1      NVLink path: faces on a side stream under interior work, reductions through mailboxes in the
+ *                         compute kernels' last blocks, instead of one exchange kernel after each phase
+ *   overlap_halo, peer_xstage      further exchange schedules (see csrc/halo.cu)
+ *   mg_graph, mg_coarse_kernel, mg_inorder   multigrid V-cycle as a CUDA graph / coarse levels in one kernel (one
+ *                         block) / non-reducing kernels launched one block per 256 cells, in order
  *   time_kernels 0|1      record CUDA events around each CG kernel (cfb_stats.ms_k_*) */
 int cfb_set_tuning( cfb_ctx* ctx, const char* key, int value );
 /* ReferenceConjugateGradient::setTolerance / setMaxIter / setPrintLevel

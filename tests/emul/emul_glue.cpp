@@ -532,31 +532,12 @@ int launch_cg_rupdate_mail( cfb_ctx* c )
     peer_exchange( c, 1, false, -1, false );
     return n;
 }
-int launch_cg_fused_mail( cfb_ctx* c, int which )
+int launch_cg_fused_mail( cfb_ctx* c, int which, bool )
 {
     if ( which != 2 )
         return 0;
     const int n = launch_cg_fused( c, 0 );
     peer_exchange( c, 0, false, -1, false );
-    return n;
-}
-// "peer_fused" with the plain-loop stand-ins: the unfused pair it replaces
-int launch_cg_fused_peer( cfb_ctx* c )
-{
-    const int n = launch_cg_fused( c, 0 );
-    peer_exchange( c, 0, false, c->pcur ^ 1, !peer_xstaged( c ) );
-    return n;
-}
-int launch_cg_rupdate_peer( cfb_ctx* c )
-{
-    const int n = launch_cg_rupdate( c );
-    peer_exchange( c, 1, true, -1, !peer_xstaged( c ) );
-    return n;
-}
-int launch_stencil_rupdate_peer( cfb_ctx* c )
-{
-    const int n = launch_stencil_rupdate( c );
-    peer_exchange( c, 1, true, -1, !peer_xstaged( c ) );
     return n;
 }
 #endif // !CFB_EMUL_REAL_TMA

@@ -41,7 +41,7 @@ for case in range(ncase):
     peer=bool(rng.integers(2)); variant=int(rng.choice([0,1,2]))
     rng2=np.random.default_rng(seed0+case+1000003)  # its own stream: earlier cases stay what they were
     flat=int(rng2.integers(2)); fusedx=int(rng2.integers(2))
-    desc=f"case {seed0+case}: dim={dim} blocks={bl} cells={cells} bt={bt} fixed={fixed} peer={peer} variant={variant} mg={mg} flat_2d={flat} peer_fused={fusedx}"
+    desc=f"case {seed0+case}: dim={dim} blocks={bl} cells={cells} bt={bt} fixed={fixed} peer={peer} variant={variant} mg={mg} flat_2d={flat} peer_overlap={fusedx}"
     try:
         cfg=make_cfg(dim,cells,box=box,boundary_type=bt,fixed_iters=fixed,max_iter=4000)
         ora=Oracle(cfg)
@@ -58,7 +58,7 @@ for case in range(ncase):
         def body(ctx,rank):
             ctx.set_tuning("cg_variant",variant)
             ctx.set_tuning("flat_2d",flat)
-            ctx.set_tuning("peer_fused",fusedx)
+            ctx.set_tuning("peer_overlap",fusedx)
             if mg: ctx.set_preconditioner("mg")
             for f,a in vel.items(): ctx.set(f,a[block_slices(ctx,f)])
             ctx.add_inputs(); ctx.build_rhs()

@@ -41,7 +41,6 @@ def main():
     ap.add_argument("--skip-steps", action="store_true", help="only the stencil / gather / PCG sections")
     ap.add_argument("--quick", action="store_true", help="only the PCG section, three exchange modes")
     ap.add_argument("--mg", action="store_true", help="only the multigrid-preconditioner section")
-    ap.add_argument("--fused", action="store_true", help="only the PCG section, exchange inside the kernels (peer_fused)")
     ap.add_argument("--cg1", action="store_true", help="only the single-reduction CG section (cg_variant 3)")
     ap.add_argument("--overlap", action="store_true",
                     help="the PCG section and whole steps with the overlapped exchange (peer_overlap) on and off")
@@ -71,8 +70,6 @@ def main():
     rng = np.random.default_rng(77)
     if args.mg:
         section_5(args, rank, blocks, gcfg, rank_cfg, rng, check)
-    elif args.fused:
-        section_3(args, rank, gcfg, rank_cfg, rng, check)
     elif args.cg1:
         section_6(args, rank, gcfg, rank_cfg, rng, check)
     elif args.overlap:
@@ -158,16 +155,6 @@ def section_3(args, rank, gcfg, rank_cfg, rng, check):
              ("two-kernel without a stored q (64 B/cell), NCCL", {"cg_variant": 2, "peer_halo": 0})]
     if args.quick:
         modes = [modes[0], modes[1], modes[2], modes[4]]
-    if args.fused:
-        # written after the round's GPU budget was spent: run by tests/test_zzz_multigpu_late.py only
-        modes = [modes[0],
-                 ("two-kernel, NVLink peer stores, exchange inside the kernels",
-                  {"cg_variant": 1, "peer_halo": 1, "peer_fused": 1}),
-                 ("exchange inside the kernels, small tiles",
-                  {"cg_variant": 1, "peer_halo": 1, "peer_fused": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64,
-                   "fused_ty": 8}),
-                 ("two-kernel without a stored q, exchange inside the kernels",
-                  {"cg_variant": 2, "peer_halo": 1, "peer_fused": 1})]
     if args.overlap:
         modes = [("overlapped exchange (faces on the side stream, reductions in the kernels' last blocks)",
                   {"cg_variant": 1, "peer_halo": 1, "peer_overlap": 1}),

@@ -376,10 +376,6 @@ def test_64_byte_iteration_block_decomposed(emul, world, blocks, peer):
 
 MODES = [("peer, small tiles", True, {"fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
          ("peer, phase B reads the x ghosts from the staging areas", True, {"peer_xstage": 1}),
-         ("peer, exchange inside phase B", True, {"peer_fused": 1}),
-         ("peer, exchange inside phase B, small tiles", True,
-          {"peer_fused": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
-         ("peer, exchange inside the kernels, 64-byte iteration", True, {"peer_fused": 1, "cg_variant": 2}),
          ("peer, faces on the side stream under interior work, reductions in the kernels' last blocks", True,
           {"peer_overlap": 1}),
          ("peer, overlapped exchange, small tiles", True,
@@ -511,71 +507,6 @@ def test_overlapped_exchange_whole_steps(emul):
 
     def body(ctx, rank):
         ctx.set_tuning("peer_overlap", 1)
-        ctx.setup()
-        exact = [f for f in want0 if not np.array_equal(ctx.get(f), want0[f][block_slices(ctx, f)])]
-        ctx.step()
-        err = {f: float(np.linalg.norm((ctx.get(f) - want[f][block_slices(ctx, f)]).ravel()) / gl[f]) for f in want}
-        return exact, err
-
-    for exact, err in run_ranks(emul, cfg, 8, body, None, peer=True):
-        assert exact == [] and max(err.values()) < 1e-12, (exact, err)
-
-
-@pytest.mark.parametrize("world,blocks,fixed", GRIDS_FUSED)
-def test_exchange_inside_the_kernels_on_every_block_grid(emul, world, blocks, fixed):
-    """"peer_fused": the boundary tiles of phase B store their block-face cells of the new search direction straight
-    into the neighbours' ghost layers and the last block of the kernel runs the mailbox exchange of p.Ap — no exchange
-    kernel after phase B.  Converged and repeated solves (sequence numbers and p buffers carry over), uneven blocks."""
-    if not emul.tma:
-        pytest.skip("the exchange lives in the TMA kernel (the plain-loop stand-in runs the unfused pair)")
-    cfg = cfg3(cells=(23, 20, 21), fixed_iters=fixed)
-    ora = Oracle(cfg)
-    rng = np.random.default_rng(81)
-    vel = {f: rng.uniform(-1, 1, size=ora.shape(f)) for f in fields_of(3)[1:]}
-    for f, a in vel.items():
-        ora.set(f, a)
-    ora.add_inputs()
-    ora.build_rhs()
-    io, ro = ora.pcg_solve()
-    po, ho = ora.get(K.PRESSURE), ora.residual_history()
-
-    def body(ctx, rank):
-        for f, a in vel.items():
-            ctx.set(f, a[block_slices(ctx, f)])
-        out, launches = [], []
-        for fused in (1, 0, 1):  # the two forms share the mailboxes and their sequence numbers
-            ctx.set_tuning("peer_fused", fused)
-            ctx.add_inputs()
-            ctx.build_rhs()
-            l0 = ctx.stats()["kernel_launches"]
-            ig, rg = ctx.pcg_solve()
-            launches.append(ctx.stats()["kernel_launches"] - l0)
-            out.append((ig, rg, np.array_equal(ctx.get(K.PRESSURE), po[block_slices(ctx, K.PRESSURE)]),
-                        np.array_equal(ctx.residual_history(), ho)))
-        return ctx.stats()["peer_mode"], out, launches
-
-    for peer, out, launches in run_ranks(emul, cfg, world, body, blocks, peer=True):
-        assert peer == 1
-        assert out == [(io, ro, True, True)] * 3, out
-        # two exchange launches (and the x-unpack launches) less per iteration
-        assert launches[0] == launches[2] and launches[1] >= launches[0] + 2 * io - 4, launches
-
-
-def test_exchange_inside_the_kernels_whole_steps(emul):
-    """(same bar as test_peer_memory_exchange_steps_and_fixed_iterations: the projection of the setup bit for bit,
-    a whole step to 1e-12 of the global norm)"""
-    if not emul.tma:
-        pytest.skip("the exchange lives in the TMA kernels")
-    cfg = cfg3(cells=(32, 24, 16), fixed_iters=20)
-    ora = Oracle(cfg)
-    ora.setup()
-    want0 = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
-    ora.step()
-    want = {f: ora.get(f) for f in fields_of(3) + [K.PRESSURE]}
-    gl = {f: max(np.linalg.norm(want[f].ravel()), 1e-300) for f in want}
-
-    def body(ctx, rank):
-        ctx.set_tuning("peer_fused", 1)
         ctx.setup()
         exact = [f for f in want0 if not np.array_equal(ctx.get(f), want0[f][block_slices(ctx, f)])]
         ctx.step()

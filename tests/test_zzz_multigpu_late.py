@@ -1,7 +1,7 @@
-"""Multi-GPU tests of what was written after the round's GPU budget was spent (sorted last on purpose; see
-tests/test_multigpu.py for the established ones): the block-decomposed multigrid preconditioner and the ghost /
-reduction exchange inside the two kernels of the CG iteration (`peer_fused`).  Both are bit-identical to the
-single-block oracle in the multi-rank emulation (tests/test_emulated_multirank.py)."""
+"""Multi-GPU tests of the opt-in paths (see tests/test_multigpu.py for the default ones): the block-decomposed multigrid
+preconditioner, the overlapped exchange schedule of the CG iterations (`peer_overlap`) and the single-reduction CG
+(`cg_variant` 3).  All are bit-identical to the single-block oracle in the multi-rank emulation
+(tests/test_emulated_multirank.py)."""
 import pytest
 
 from test_multigpu import _run_worker
@@ -15,15 +15,6 @@ def test_block_decomposed_multigrid_matches_single_block_oracle(world):
     face exchange per operator application): V-cycle and MG-PCG bit for bit against the single-block oracle.
     (Checked on the CPU by tests/test_emulated_multirank.py; first GPU run pending.)"""
     _run_worker(world, ["--mg"], cells=(64, 32, 32))
-
-
-@pytest.mark.parametrize("world,blocks", [(2, None), (2, (2, 1, 1)), (2, (1, 2, 1)), (4, None), (8, None)])
-def test_exchange_inside_the_kernels_matches_single_block_oracle(world, blocks):
-    """`peer_fused`: the boundary tiles of phase A / phase B store their block-face cells into the neighbours' ghost
-    layers themselves and the last block of each kernel runs the mailbox exchange — no exchange kernel in the
-    iteration.  Every CG form, bit for bit against the single-block oracle."""
-    extra = ["--fused"] + (["--blocks"] + [str(b) for b in blocks] if blocks else [])
-    _run_worker(world, extra, cells=(128, 24, 20) if blocks == (2, 1, 1) else (48, 40, 36))
 
 
 @pytest.mark.parametrize("world,blocks", [(2, None), (2, (2, 1, 1)), (2, (1, 2, 1)), (4, None), (8, None)])

@@ -151,6 +151,7 @@ struct cfb_ctx
     bool flat_2d = false; // set in cfb_create
     // "advect_tile" tuning key: 32 x 2 x 2 entity tiles per block in the advection kernel instead of rows
     bool advect_tile = false;
+    int advect_occ = 5; // "advect_occ" tuning key: minimum resident blocks per SM the advection kernel is compiled for (5 | 6 | 8)
     // "peer_overlap" tuning key (several blocks, NVLink peer memory, two-kernel form): the reduction of each phase
     // runs in the last block of the compute kernel (mailboxes), the faces travel on the side stream under the
     // interior units of phase B (r) and under the next phase A (search direction); boundary units run last

@@ -88,8 +88,10 @@ struct AdvectArgs
 // An item is 128 consecutive entities of the flattened (i, j, k) index of its kind, or — TILED ("advect_tile"
 // tuning key) — a 32 x 2 x 2 (3-D) / 32 x 4 (2-D) tile, whose 4^D-point neighbourhoods overlap in y and z too.
 // Only the thread -> entity map differs: the same values.
-template <int D, int ORDER, bool TILED>
-__global__ void __launch_bounds__( 128 )
+// MINB: resident blocks per SM the compiler must allow ("advect_occ" tuning key: 5 -> 96 registers, no spill; 6 -> 80;
+// 8 -> 64 with a few spilled values) — the kernel hides its gather latency with warps, not with unrolling.
+template <int D, int ORDER, bool TILED, int MINB>
+__global__ void __launch_bounds__( 128, MINB )
     advect_kernel( const __grid_constant__ Geo g, const __grid_constant__ AdvectArgs a, int quirk_v0 )
 {
     const int ent = (int)( blockIdx.x % (unsigned)( D + 1 ) );
@@ -326,26 +328,45 @@ int launch_advect( cfb_ctx* c )
         return 0;
     }
     const dim3 grid( (unsigned)blocks );
-    if ( c->advect_tile )
+    const int key = ( g.D == 3 ? 100 : 0 ) + ( order == 3 ? 10 : 0 ) + ( c->advect_tile ? 1 : 0 );
+#define CFB_ADVECT( D_, O_, T_ )                                                                                          \
+    do                                                                                                                    \
+    {                                                                                                                     \
+        if ( c->advect_occ >= 8 )                                                                                         \
+            advect_kernel<D_, O_, T_, 8><<<grid, 128, 0, c->stream>>>( g, a, qv0 );                                       \
+        else if ( c->advect_occ >= 6 )                                                                                    \
+            advect_kernel<D_, O_, T_, 6><<<grid, 128, 0, c->stream>>>( g, a, qv0 );                                       \
+        else                                                                                                              \
+            advect_kernel<D_, O_, T_, 5><<<grid, 128, 0, c->stream>>>( g, a, qv0 );                                       \
+    } while ( 0 )
+    switch ( key )
     {
-        if ( g.D == 2 && order == 1 )
-            advect_kernel<2, 1, true><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
-        else if ( g.D == 2 )
-            advect_kernel<2, 3, true><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
-        else if ( order == 1 )
-            advect_kernel<3, 1, true><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
-        else
-            advect_kernel<3, 3, true><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
-        return 1;
+    case 0:
+        CFB_ADVECT( 2, 1, false );
+        break;
+    case 1:
+        CFB_ADVECT( 2, 1, true );
+        break;
+    case 10:
+        CFB_ADVECT( 2, 3, false );
+        break;
+    case 11:
+        CFB_ADVECT( 2, 3, true );
+        break;
+    case 100:
+        CFB_ADVECT( 3, 1, false );
+        break;
+    case 101:
+        CFB_ADVECT( 3, 1, true );
+        break;
+    case 110:
+        CFB_ADVECT( 3, 3, false );
+        break;
+    default:
+        CFB_ADVECT( 3, 3, true );
+        break;
     }
-    if ( g.D == 2 && order == 1 )
-        advect_kernel<2, 1, false><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
-    else if ( g.D == 2 )
-        advect_kernel<2, 3, false><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
-    else if ( order == 1 )
-        advect_kernel<3, 1, false><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
-    else
-        advect_kernel<3, 3, false><<<grid, 128, 0, c->stream>>>( g, a, qv0 );
+#undef CFB_ADVECT
     return 1;
 }
 

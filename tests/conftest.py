@@ -34,6 +34,10 @@ def pytest_cmdline_main(config):
     if getattr(config.option, "numprocesses", None) in (None, 0) and getattr(config.option, "dist", "no") == "no":
         n = int(os.environ.get("CFB_TEST_WORKERS", "0") or 0) or max(1, min(4, (os.cpu_count() or 2) // 2))
         if n > 1:
+            # the checker is an OpenMP code and the multi-rank emulation runs one thread per rank: share the cores
+            # among the workers instead of letting every worker spin on all of them
+            os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 2) // n)))
+            os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
             config.option.numprocesses = n
             config.option.tx = ["popen"] * n
             config.option.dist = "load"

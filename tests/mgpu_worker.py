@@ -42,6 +42,9 @@ def main():
     ap.add_argument("--quick", action="store_true", help="only the PCG section, three exchange modes")
     ap.add_argument("--mg", action="store_true", help="only the multigrid-preconditioner section")
     ap.add_argument("--cg1", action="store_true", help="only the single-reduction CG section (cg_variant 3)")
+    ap.add_argument("--everything", action="store_true",
+                    help="every section in one launch (default sections, multigrid, overlapped exchange, single-reduction CG): "
+                         "one rendezvous instead of four when GPU time is charged per GPU")
     ap.add_argument("--overlap", action="store_true",
                     help="the PCG section and whole steps with the overlapped exchange (peer_overlap) on and off")
     args = ap.parse_args()
@@ -68,7 +71,17 @@ def main():
             failures.append(f"rank {rank}: {name} {detail}")
 
     rng = np.random.default_rng(77)
-    if args.mg:
+    if args.everything:
+        sections_1_2(args, rank, gcfg, rank_cfg, rng, check)
+        section_3(args, rank, gcfg, rank_cfg, rng, check)
+        section_4(args, rank, gcfg, rank_cfg, check)
+        args.overlap = True
+        section_3(args, rank, gcfg, rank_cfg, rng, check)
+        section_4(args, rank, gcfg, rank_cfg, check, tune={"peer_overlap": 1})
+        section_6(args, rank, gcfg, rank_cfg, rng, check)
+        if all(c % (2 * b) == 0 for c, b in zip(cells, blocks)):
+            section_5(args, rank, blocks, gcfg, rank_cfg, rng, check)
+    elif args.mg:
         section_5(args, rank, blocks, gcfg, rank_cfg, rng, check)
     elif args.cg1:
         section_6(args, rank, gcfg, rank_cfg, rng, check)

@@ -1062,8 +1062,7 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     static const Range ranges[] = { { "stencil_variant", 0, 1 }, { "stencil_tx", 64, 128 }, { "stencil_ty", 8, 32 },
                                     { "stencil_stages", 3, 6 },  { "stencil_zc", 0, 1 << 20 }, { "poll_every", 0, 1 << 20 },
                                     { "cg_variant", 0, 3 },      { "fused_tx", 64, 128 },   { "fused_ty", 8, 32 },
-                                    { "fused_stages", 2, 4 },    { "fused_zc", 0, 1 << 20 }, { "rupdate_ctas", 1, 8 },
-                                    { "advect_occ", 5, 8 } };
+                                    { "fused_stages", 2, 4 },    { "fused_zc", 0, 1 << 20 }, { "rupdate_ctas", 1, 8 } };
     for ( const Range& r : ranges )
         if ( k == r.key && ( value < r.lo || value > r.hi ) )
             return cfb_fail( c, CFB_ERR_INVALID,
@@ -1129,15 +1128,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->flat_2d = value != 0;
     else if ( k == "advect_tile" )
         c->advect_tile = value != 0;
-    else if ( k == "advect_occ" )
-        c->advect_occ = value;
     else if ( k == "peer_overlap" )
         c->peer_overlap = value != 0;
-    else if ( k == "mg_inorder" )
-    {
-        c->mg_inorder = value != 0;
-        return mg_set_coarse_kernel( c, c->mg_coarse ); // (drops a captured cycle: it holds the old launch shapes)
-    }
     else if ( k == "mg_graph" )
         return mg_set_graph( c, value != 0 );
     else if ( k == "mg_coarse_kernel" )

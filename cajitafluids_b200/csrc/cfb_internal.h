@@ -151,7 +151,6 @@ struct cfb_ctx
     bool flat_2d = false; // set in cfb_create
     // "advect_tile" tuning key: 32 x 2 x 2 entity tiles per block in the advection kernel instead of rows
     bool advect_tile = false;
-    int advect_occ = 5; // "advect_occ" tuning key: minimum resident blocks per SM the advection kernel is compiled for (5 | 6 | 8)
     // "peer_overlap" tuning key (several blocks, NVLink peer memory, two-kernel form): the reduction of each phase
     // runs in the last block of the compute kernel (mailboxes), the faces travel on the side stream under the
     // interior units of phase B (r) and under the next phase A (search direction); boundary units run last
@@ -227,7 +226,6 @@ struct cfb_ctx
     int precond = CFB_PRECOND_JACOBI;
     int mg_max_levels = 0; // 0 = as many as the block allows
     bool mg_graph = false; // "mg_graph" tuning key: replay the V-cycle as a CUDA graph (one block)
-    bool mg_inorder = false; // "mg_inorder" tuning key: non-reducing multigrid launches use one block per 256 cells, in order
     bool mg_coarse = false; // "mg_coarse_kernel" tuning key: the coarse end of the cycle in one single-CTA kernel
     MgStage* mg = nullptr;
 };

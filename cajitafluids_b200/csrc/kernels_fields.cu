@@ -88,10 +88,10 @@ struct AdvectArgs
 // An item is 128 consecutive entities of the flattened (i, j, k) index of its kind, or — TILED ("advect_tile"
 // tuning key) — a 32 x 2 x 2 (3-D) / 32 x 4 (2-D) tile, whose 4^D-point neighbourhoods overlap in y and z too.
 // Only the thread -> entity map differs: the same values.
-// MINB: resident blocks per SM the compiler must allow ("advect_occ" tuning key: 5 -> 96 registers, no spill; 6 -> 80;
-// 8 -> 64 with a few spilled values) — the kernel hides its gather latency with warps, not with unrolling.
-template <int D, int ORDER, bool TILED, int MINB>
-__global__ void __launch_bounds__( 128, MINB )
+// 5 resident blocks per SM (96 registers, nothing spilled).  Compiled for 6 (80 registers) and 8 (64, a few values
+// spilled) it measured slower at every size: 38.2 / 40.9 / 46.7 ms at 512^3 (profiles/r2_advect_occupancy_variants.json).
+template <int D, int ORDER, bool TILED>
+__global__ void __launch_bounds__( 128, 5 )
     advect_kernel( const __grid_constant__ Geo g, const __grid_constant__ AdvectArgs a, int quirk_v0 )
 {
     const int ent = (int)( blockIdx.x % (unsigned)( D + 1 ) );
@@ -332,12 +332,7 @@ int launch_advect( cfb_ctx* c )
 #define CFB_ADVECT( D_, O_, T_ )                                                                                          \
     do                                                                                                                    \
     {                                                                                                                     \
-        if ( c->advect_occ >= 8 )                                                                                         \
-            advect_kernel<D_, O_, T_, 8><<<grid, 128, 0, c->stream>>>( g, a, qv0 );                                       \
-        else if ( c->advect_occ >= 6 )                                                                                    \
-            advect_kernel<D_, O_, T_, 6><<<grid, 128, 0, c->stream>>>( g, a, qv0 );                                       \
-        else                                                                                                              \
-            advect_kernel<D_, O_, T_, 5><<<grid, 128, 0, c->stream>>>( g, a, qv0 );                                       \
+        advect_kernel<D_, O_, T_><<<grid, 128, 0, c->stream>>>( g, a, qv0 );                                              \
     } while ( 0 )
     switch ( key )
     {

@@ -802,19 +802,8 @@ inline int grid_for( const cfb_ctx* c, long long cells )
     return (int)( b < 1 ? 1 : ( b > cap ? cap : b ) );
 }
 
-// Launches without a reduction.  "mg_inorder" tuning key: one block per 256 cells, launched in order, instead of a
-// capped grid whose threads stride through the level — the resident blocks then form a window of ~1 plane that
-// moves through the level, so the z neighbours a sweep reads were read a moment ago by the wave before (L2 hits)
-// instead of being scattered over the whole level (profiles/r2_launches_mg512.csv: the strided form reaches
-// 1.5 - 3.4 TB/s on the fine level).  Same cells, same values.
-inline int grid_stream( const cfb_ctx* c, long long cells )
-{
-    if ( !c->mg_inorder )
-        return grid_for( c, cells );
-    const long long b = ( cells + NT - 1 ) / NT;
-    return (int)( b < 1 ? 1 : ( b > 2147483647ll ? 2147483647ll : b ) );
-}
-
+// (Launch order: one block per 256 cells launched in order, instead of this capped grid whose threads stride through the
+// level, was measured and is slower — 9.88 vs 9.48 ms per MG-PCG iteration at 512^3, profiles/r2_mg_launch_order.log.)
 void mg_free( cfb_ctx* c )
 {
     MgStage* m = c->mg;
@@ -1097,7 +1086,7 @@ int mg_global_sum( cfb_ctx* c, int what, int* launches )
 // (nullptr: the coarsest level's fixed damping)
 int launch_presmooth( cfb_ctx* c, MgLevelHost& H, int sweeps, const double* w, int* n )
 {
-    const int grid = grid_stream( c, H.cells );
+    const int grid = grid_for( c, H.cells );
     const double wc = c->mg->wc;
     int done;
     if ( sweeps >= 2 )
@@ -1172,7 +1161,7 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
         return CFB_OK;
     MgLevelHost& C = m->lv[l + 1];
     MG_TRY( mg_exchange( c, H, H.x[H.cur], n ) ); // the residual reads x of the six neighbours
-    mg_restrict_kernel<<<grid_stream( c, C.cells ), NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.b );
+    mg_restrict_kernel<<<grid_for( c, C.cells ), NT, 0, c->stream>>>( H.d, C.d, H.b, H.x[H.cur], C.b );
     *n += 1;
     MG_TRY( vcycle( c, l + 1, false, nullptr, n ) );
     if ( m->nu2 == 0 )
@@ -1188,7 +1177,7 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
         mg_prolong_smooth_kernel<true><<<grid, NT, 0, c->stream>>>( H.d, C.d, m->wpost[0], H.b, H.x[H.cur], C.x[C.cur],
                                                                    H.x[1 - H.cur], c->d_state, c->d_partials );
     else
-        mg_prolong_smooth_kernel<false><<<grid_stream( c, H.cells ), NT, 0, c->stream>>>( H.d, C.d, m->wpost[0], H.b, H.x[H.cur],
+        mg_prolong_smooth_kernel<false><<<grid_for( c, H.cells ), NT, 0, c->stream>>>( H.d, C.d, m->wpost[0], H.b, H.x[H.cur],
                                                                                          C.x[C.cur], H.x[1 - H.cur], c->d_state,
                                                                                          c->d_partials );
     H.cur = 1 - H.cur;
@@ -1200,7 +1189,7 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
             mg_smooth_dot_kernel<<<grid, NT, 0, c->stream>>>( H.d, m->wpost[s], H.b, H.x[H.cur], H.x[1 - H.cur], c->d_state,
                                                              c->d_partials );
         else
-            mg_smooth_kernel<<<grid_stream( c, H.cells ), NT, 0, c->stream>>>( H.d, m->wpost[s], H.b, H.x[H.cur], H.x[1 - H.cur] );
+            mg_smooth_kernel<<<grid_for( c, H.cells ), NT, 0, c->stream>>>( H.d, m->wpost[s], H.b, H.x[H.cur], H.x[1 - H.cur] );
         H.cur = 1 - H.cur;
         *n += 1;
     }

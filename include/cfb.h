@@ -324,8 +324,7 @@ int cfb_residual_history( const cfb_ctx* ctx, double* hist, int n, int* count );
  *   peer_overlap 0|1      NVLink path: faces on a side stream under interior work, reductions through mailboxes in the
  *                         compute kernels' last blocks, instead of one exchange kernel after each phase
  *   overlap_halo, peer_xstage      further exchange schedules (see csrc/halo.cu)
- *   mg_graph, mg_coarse_kernel, mg_inorder   multigrid V-cycle as a CUDA graph / coarse levels in one kernel (one
- *                         block) / non-reducing kernels launched one block per 256 cells, in order
+ *   mg_graph, mg_coarse_kernel     multigrid V-cycle as a CUDA graph / coarse levels in one kernel (one block)
  *   time_kernels 0|1      record CUDA events around each CG kernel (cfb_stats.ms_k_*) */
 int cfb_set_tuning( cfb_ctx* ctx, const char* key, int value );
 /* ReferenceConjugateGradient::setTolerance / setMaxIter / setPrintLevel

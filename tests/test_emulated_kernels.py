@@ -565,25 +565,3 @@ def test_emulated_single_reduction_cg(emul, dim, cells, kw):
         res = g2.pcg_solve()
         assert res == o2.pcg_solve() and np.isfinite(res[1]), variant
         assert np.array_equal(g2.get(K.PRESSURE), o2.get(K.PRESSURE)), variant
-
-
-@pytest.mark.parametrize("dim,cells", [(3, (32, 24, 16)), (2, (64, 48))])
-def test_emulated_multigrid_launches_in_order(emul, dim, cells):
-    """"mg_inorder": the non-reducing multigrid kernels with one block per 256 cells launched in order instead of a
-    capped grid-stride launch — the same cells, the same values (and again after switching back, graph included)."""
-    if emul.tma:
-        pytest.skip("no TMA kernel involved")
-    cfg = make_cfg(dim, cells, box=box_of(cells))
-    g, o = Context(emul, cfg), Oracle(cfg)
-    for s in (g, o):
-        s.set_preconditioner("mg")
-        s.add_inputs()
-        s.build_rhs()
-    want = o.pcg_solve()
-    po = o.get(K.PRESSURE)
-    for inorder, graph in ((1, 0), (1, 1), (0, 1), (0, 0)):
-        g.set_tuning("mg_inorder", inorder)
-        g.set_tuning("mg_graph", graph)
-        g.build_rhs()
-        assert g.pcg_solve() == want, (inorder, graph)
-        assert np.array_equal(g.get(K.PRESSURE), po), (inorder, graph)

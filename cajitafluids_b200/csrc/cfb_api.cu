@@ -354,7 +354,8 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     };
     if ( c->sticky_rc )
         return bail();
-    const int batch = poll_batch( c );
+    const bool persist = cg_persist_applies( c ); // small block: batches of iterations in one cooperative launch
+    const int batch = persist ? std::max( poll_batch( c ), 32 ) : poll_batch( c );
     int enq = 0;
     bool done = false;
     // Pipelined polling: the state of batch i is inspected while batch i+1 is already queued, so
@@ -364,8 +365,14 @@ int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
     while ( enq < max_it && !done )
     {
         int b = std::min( batch, max_it - enq );
-        for ( int i = 0; i < b && !c->sticky_rc; ++i )
-            launches += enqueue_iteration( c );
+        if ( persist )
+        {
+            launches += launch_cg_persistent( c, b );
+            cg_select_p( c, c->pcur ^ ( b & 1 ) ); // every iteration writes the new direction into the other buffer
+        }
+        else
+            for ( int i = 0; i < b && !c->sticky_rc; ++i )
+                launches += enqueue_iteration( c );
         if ( c->sticky_rc )
             return bail();
         enq += b;
@@ -1061,7 +1068,7 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     };
     static const Range ranges[] = { { "stencil_variant", 0, 1 }, { "stencil_tx", 64, 128 }, { "stencil_ty", 8, 32 },
                                     { "stencil_stages", 3, 6 },  { "stencil_zc", 0, 1 << 20 }, { "poll_every", 0, 1 << 20 },
-                                    { "cg_variant", 0, 3 },      { "fused_tx", 64, 128 },   { "fused_ty", 8, 32 },
+                                    { "cg_variant", 0, 3 },      { "cg_persist", -1, 1 },      { "fused_tx", 64, 128 },   { "fused_ty", 8, 32 },
                                     { "fused_stages", 2, 4 },    { "fused_zc", 0, 1 << 20 }, { "rupdate_ctas", 1, 8 } };
     for ( const Range& r : ranges )
         if ( k == r.key && ( value < r.lo || value > r.hi ) )
@@ -1100,6 +1107,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->poll_every = value;
     else if ( k == "cg_variant" )
         c->cg_variant = value;
+    else if ( k == "cg_persist" )
+        c->cg_persist = value;
     else if ( k == "fused_tx" )
         return set_checked( c->fu_tx, fused_setup );
     else if ( k == "fused_ty" )

@@ -172,6 +172,10 @@ struct cfb_ctx
     int fu_tx = 64, fu_ty = 16, fu_stages = 3, fu_zc = 64;
     int* d_units = nullptr; // (tile_x, tile_y, chunk) triples: interior units first, then boundary
     int n_units = 0, n_interior = 0;
+    // "cg_persist" tuning key: 1 = run batches of iterations of the two-kernel form in ONE cooperative launch
+    // (kernels_fused.cu: cg_persistent_kernel), 0 = never, -1 = where it pays: one block whose five CG vectors stay
+    // in the L2 (the launch-per-phase kernels are latency-bound there)
+    int cg_persist = -1;
     bool fu_reverse = false;  // phase B walks the units top-down (L2 reuse between the phases)
     int ru_ctas = 3;          // phase A: CTAs per SM of the grid-stride launch
     // NCCL path: run interior units while the r/p ghosts are in flight (measured slower than
@@ -341,6 +345,19 @@ int launch_cg_fused( cfb_ctx* c, int which ); // phase B: 0 = all units, 1 = int
 int launch_cg_rupdate_mail( cfb_ctx* c );      // phase A, its last block runs the mailbox reduction (peer_overlap)
 int launch_cg_fused_mail( cfb_ctx* c, int which, bool side ); // phase B units (1 interior / 2 boundary), the same
 int launch_cg_finish( cfb_ctx* c );
+bool cg_persist_supported( const cfb_ctx* c ); // tile shape instantiated for the persistent kernel
+int launch_cg_persistent( cfb_ctx* c, int iters ); // `iters` iterations in one cooperative launch
+// the persistent form applies: two-kernel form, Jacobi, one block, no per-kernel timing; automatic choice by size
+inline bool cg_persist_applies( const cfb_ctx* c )
+{
+    if ( c->cg_variant != 1 || c->cfg.use_nccl || c->time_kernels || c->cg_persist == 0 || !cg_persist_supported( c ) )
+        return false;
+    if ( c->cg_persist > 0 )
+        return true;
+    // automatic: five vectors of the block within ~2/3 of the 126 MB L2 (<= ~128^3 cells)
+    const double cells = (double)c->g.n[0] * c->g.n[1] * c->g.n[2];
+    return cells * 8.0 * 5.0 <= 90.0e6;
+}
 // output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
 int output_write( cfb_ctx* c, const char* dir, int time_step );
 int output_flush( cfb_ctx* c );

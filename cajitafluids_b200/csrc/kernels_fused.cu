@@ -28,6 +28,7 @@
 #include "device_peer.cuh"
 
 #include <algorithm>
+#include <cooperative_groups.h>
 
 namespace
 {
@@ -46,33 +47,19 @@ __device__ __forceinline__ bool cg_converged( const CgState* S )
 // reuse at all, it lives on memory-level parallelism), one integer division per RU column pairs.
 constexpr int RU = 4;
 
-template <bool PF>
-__global__ void __launch_bounds__( NT, 3 )
-    cg_rupdate_kernel( const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
-                       const double* __restrict__ q, double* __restrict__ r, CgState* S, double* partials,
-                       int txp_log2, const __grid_constant__ typename PeerSel<PF>::type pf )
+// The rows of phase A for one block of a grid of `nblocks`: r -= alpha q on the block's batches of rows, the thread's
+// shares of sum r^2 and sum r.M^-1 r added to rr / rz.  Shared by cg_rupdate_kernel and the persistent kernel.
+__device__ __forceinline__ void rupdate_rows( const Geo& g, const OpConst& op, const double* __restrict__ q, double* __restrict__ r,
+                                              const double nalpha, const int txp_log2, const int block, const int nblocks,
+                                              dd_t& rr, dd_t& rz )
 {
-    // `done` is only ever written by this kernel, cg_check0 and cg_finish (never by phase B, whose
-    // late CTAs would otherwise see it mid-launch); phase B of the iteration that met the tolerance
-    // has already applied its x update, so there is nothing left to do.
-    if ( S->done || ( S->iter > 0 && cg_converged( S ) ) )
-    {
-        if ( blockIdx.x == 0 && threadIdx.x == 0 )
-            S->done = 1;
-        return;
-    }
-    const double alpha = S->rz_old / S->pAp;
-    const double nalpha = -alpha;
-    if ( blockIdx.x == 0 && threadIdx.x == 0 )
-        S->alpha = alpha;
     const int txp = 1 << txp_log2, tyr = NT >> txp_log2;
     const int lx = threadIdx.x & ( txp - 1 ), ry = threadIdx.x >> txp_log2;
     const int npx = ( g.n[0] + 1 ) >> 1;
     const int rows = g.n[1] * g.n[2];
     const int batch = tyr * RU;
     const bool odd = g.n[0] & 1;
-    dd_t rr = { 0.0, 0.0 }, rz = { 0.0, 0.0 };
-    for ( int row0 = blockIdx.x * batch; row0 < rows; row0 += gridDim.x * batch )
+    for ( int row0 = block * batch; row0 < rows; row0 += nblocks * batch )
     {
         // rows of this thread: row0 + ry + u * tyr
         int cyz[RU];
@@ -134,6 +121,29 @@ __global__ void __launch_bounds__( NT, 3 )
             }
         }
     }
+}
+
+template <bool PF>
+__global__ void __launch_bounds__( NT, 3 )
+    cg_rupdate_kernel( const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
+                       const double* __restrict__ q, double* __restrict__ r, CgState* S, double* partials,
+                       int txp_log2, const __grid_constant__ typename PeerSel<PF>::type pf )
+{
+    // `done` is only ever written by this kernel, cg_check0 and cg_finish (never by phase B, whose
+    // late CTAs would otherwise see it mid-launch); phase B of the iteration that met the tolerance
+    // has already applied its x update, so there is nothing left to do.
+    if ( S->done || ( S->iter > 0 && cg_converged( S ) ) )
+    {
+        if ( blockIdx.x == 0 && threadIdx.x == 0 )
+            S->done = 1;
+        return;
+    }
+    const double alpha = S->rz_old / S->pAp;
+    const double nalpha = -alpha;
+    if ( blockIdx.x == 0 && threadIdx.x == 0 )
+        S->alpha = alpha;
+    dd_t rr = { 0.0, 0.0 }, rz = { 0.0, 0.0 };
+    rupdate_rows( g, op, q, r, nalpha, txp_log2, (int)blockIdx.x, (int)gridDim.x, rr, rz );
     dd_t vals[2] = { rr, rz };
     if ( block_reduce_finalize<NT, 2>( vals, partials, CFB_MAX_PARTIALS, &S->ticket[0] ) )
     {
@@ -213,47 +223,22 @@ struct FusedArgs
     int units_total; // units of all launches that make up one phase B (last-block ticket target)
 };
 
-// FLAT: two-dimensional runs (one owned plane between two zero ghost planes, see Geo): the z neighbours are
-// zero by construction, so the two ghost planes are neither loaded nor recomputed — the 2-D traffic of r and p
-// drops from three planes to the one that exists.  A template flag: the 3-D instantiations are untouched.
-// PF: the block that draws the phase's last ticket runs the mailbox reduction of p.Ap (device_peer.cuh); a template
-// flag, the other instantiations are untouched.
-template <class C, bool XS, bool FLAT, bool PF>
-__global__ void __launch_bounds__( C::NT, C::CTAS )
-    cg_fused_kernel( const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_p,
-                     const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
-                     const __grid_constant__ FusedArgs a, const __grid_constant__ typename PeerSel<PF>::type pf )
+// One unit of phase B: the z-march over the planes [kbeg, kend) of tile (x0, y0) — new search direction on the tile
+// and its halo ring, x += alpha p_old, q = A p_new — for the calling block; returns the thread's share of p.q.
+// Shared by the one-unit-per-block kernel (lbase == 0) and by the persistent kernel of the small grids, whose blocks
+// walk through several units with the same shared-memory ring and stage barriers (lbase: loads issued so far).
+template <class C, bool XS, bool FLAT>
+__device__ __forceinline__ dd_t fused_unit( const CUtensorMap& tmap_r, const CUtensorMap& tmap_p, const Geo& g, const OpConst& op,
+                                            const FusedArgs& a, const int x0, const int y0, const int kbeg, const int kend,
+                                            const double alpha, const double beta, double* stage0, double* pn0,
+                                            unsigned long long* full_bar, const uint32_t smem_base, const int lbase )
 {
     constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
     constexpr int BOXD = C::BOX_PAD / 8, STAGED = C::STAGE_BYTES / 8;
-    CgState* S = a.S;
-    if ( S->done )
-        return;
-
     const int tid = threadIdx.x;
     const int lx = tid % LX, wy = tid / LX;
-
-    // unit -> (tile_x, tile_y, z chunk)
-    int tx, ty, ch;
-    if ( a.units )
-    {
-        tx = a.units[3 * blockIdx.x + 0];
-        ty = a.units[3 * blockIdx.x + 1];
-        ch = a.units[3 * blockIdx.x + 2];
-    }
-    else
-    {
-        const int u = a.reverse ? a.units_total - 1 - (int)blockIdx.x : (int)blockIdx.x;
-        tx = u % a.tiles_x;
-        ty = ( u / a.tiles_x ) % a.tiles_y;
-        ch = u / ( a.tiles_x * a.tiles_y );
-    }
-    const int x0 = tx * TX, y0 = ty * TY;
-    const int kbeg = ch * a.zc;
-    const int kend = min( kbeg + a.zc, g.n[2] );
     const int nplanes = kend - kbeg;
     const int nloads = nplanes + 2; // planes kbeg-1 .. kend
-
     const int i0 = x0 + 2 * lx;
     const bool vx0 = i0 < g.n[0], vx1 = i0 + 1 < g.n[0];
     bool vy[RY];
@@ -261,71 +246,21 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     for ( int r = 0; r < RY; ++r )
         vy[r] = y0 + wy + r * WY < g.n[1];
 
-    // ---- convergence bookkeeping of the iteration (the reference's test after kernel 1) ----------
-    const double alpha = S->alpha;
-    const double resid = sqrt( S->rr );
-    const bool conv = !S->fixed && resid <= S->thresh;
-    if ( a.unit_base + blockIdx.x == 0 && tid == 0 )
-    {
-        const int it = S->iter;
-        if ( it < CFB_HIST_MAX )
-            S->hist[it] = resid;
-        S->iter = it + 1;
-    }
-    if ( conv )
-    {
-        // x += alpha p of the converged iteration; nothing else (the loop breaks here)
-        for ( int k = kbeg; k < kend; ++k )
-#pragma unroll
-            for ( int r = 0; r < RY; ++r )
-            {
-                if ( !vy[r] || !vx0 )
-                    continue;
-                const long long o = geo_off( g, i0, y0 + wy + r * WY, k );
-                if ( vx1 )
-                {
-                    const double2 pv = *reinterpret_cast<const double2*>( a.p_old + o );
-                    double2 xv = *reinterpret_cast<double2*>( a.x + o );
-                    xv.x = fma( alpha, pv.x, xv.x );
-                    xv.y = fma( alpha, pv.y, xv.y );
-                    *reinterpret_cast<double2*>( a.x + o ) = xv;
-                }
-                else
-                    a.x[o] = fma( alpha, a.p_old[o], a.x[o] );
-            }
-        return;
-    }
-    const double beta = S->rz_new / S->rz_old;
-
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__( 8 ) unsigned long long full_bar[NS];
-    const uint32_t smem_base = ( smem_u32( smem_raw ) + 127u ) & ~127u;
-    double* stage0 = reinterpret_cast<double*>( smem_raw + ( smem_base - smem_u32( smem_raw ) ) );
-    double* pn0 = stage0 + NS * STAGED;
-
     // TMA box origin (array coordinates): 2 columns left of the tile, 1 row below, plane kbeg-1
     const int cx = a.hx + x0 - 2;
     const int cy = g.h + y0 - 1;
     const int cz = g.h + kbeg - 1;
 
+    // load index across the units a persistent block walks through: every stage barrier completes once per load, so
+    // the parity a waiter needs is that of the running index (lbase == 0 in the one-unit-per-block kernels)
     auto issue = [&]( int l ) {
-        const int s = l % NS;
+        const int s = ( lbase + l ) % NS;
         const uint32_t bar = smem_u32( &full_bar[s] );
         mbar_expect_tx( bar, 2 * C::BOX_BYTES );
         tma_load_3d( smem_base + s * C::STAGE_BYTES, &tmap_r, bar, cx, cy, cz + l );
         tma_load_3d( smem_base + s * C::STAGE_BYTES + C::BOX_PAD, &tmap_p, bar, cx, cy, cz + l );
     };
 
-    if ( tid == 0 )
-    {
-        prefetch_tmap( &tmap_r );
-        prefetch_tmap( &tmap_p );
-#pragma unroll
-        for ( int s = 0; s < NS; ++s )
-            mbar_init( smem_u32( &full_bar[s] ), 1 );
-        fence_barrier_init();
-    }
-    __syncthreads();
     if ( tid == 0 )
     {
         if ( FLAT )
@@ -380,7 +315,7 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     // into the shared new-p plane, and p, x of my cells are written back (plane owned by this chunk).
     double2 zm[RY], cc[RY], zp[RY];
     auto new_p = [&]( int l, double2 out[RY], bool full ) {
-        const double* R = stage0 + ( l % NS ) * STAGED;
+        const double* R = stage0 + ( ( lbase + l ) % NS ) * STAGED;
         const double* P = R + BOXD;
         double* PN = pn0 + ( l % C::NPN ) * BOXD;
         const int wz = wall_count( g, 2, kbeg + l - 1 + g.off[2] );
@@ -474,10 +409,10 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     }
     else
     {
-        mbar_wait( smem_u32( &full_bar[0] ), 0 );
+        mbar_wait( smem_u32( &full_bar[lbase % NS] ), ( lbase / NS ) & 1 );
         new_p( 0, zm, false );
     }
-    mbar_wait( smem_u32( &full_bar[1 % NS] ), ( 1 / NS ) & 1 );
+    mbar_wait( smem_u32( &full_bar[( lbase + 1 ) % NS] ), ( ( lbase + 1 ) / NS ) & 1 );
     new_p( 1, cc, true );
     __syncthreads();
     if ( tid == 0 && !FLAT )
@@ -500,7 +435,7 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
         }
         else
         {
-            mbar_wait( smem_u32( &full_bar[l % NS] ), ( l / NS ) & 1 );
+            mbar_wait( smem_u32( &full_bar[( lbase + l ) % NS] ), ( ( lbase + l ) / NS ) & 1 );
             new_p( l, zp, l <= nplanes );
         }
         // q = A p on plane k = kbeg + it: x/y neighbours from the shared new-p plane of load it+1
@@ -544,6 +479,111 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
         if ( tid == 0 && !FLAT && l + NS < nloads )
             issue( l + NS );
     }
+
+    return acc;
+}
+
+// FLAT: two-dimensional runs (one owned plane between two zero ghost planes, see Geo): the z neighbours are
+// zero by construction, so the two ghost planes are neither loaded nor recomputed — the 2-D traffic of r and p
+// drops from three planes to the one that exists.  A template flag: the 3-D instantiations are untouched.
+// PF: the block that draws the phase's last ticket runs the mailbox reduction of p.Ap (device_peer.cuh); a template
+// flag, the other instantiations are untouched.
+template <class C, bool XS, bool FLAT, bool PF>
+__global__ void __launch_bounds__( C::NT, C::CTAS )
+    cg_fused_kernel( const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_p,
+                     const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
+                     const __grid_constant__ FusedArgs a, const __grid_constant__ typename PeerSel<PF>::type pf )
+{
+    constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
+    constexpr int BOXD = C::BOX_PAD / 8, STAGED = C::STAGE_BYTES / 8;
+    CgState* S = a.S;
+    if ( S->done )
+        return;
+
+    const int tid = threadIdx.x;
+    const int lx = tid % LX, wy = tid / LX;
+
+    // unit -> (tile_x, tile_y, z chunk)
+    int tx, ty, ch;
+    if ( a.units )
+    {
+        tx = a.units[3 * blockIdx.x + 0];
+        ty = a.units[3 * blockIdx.x + 1];
+        ch = a.units[3 * blockIdx.x + 2];
+    }
+    else
+    {
+        const int u = a.reverse ? a.units_total - 1 - (int)blockIdx.x : (int)blockIdx.x;
+        tx = u % a.tiles_x;
+        ty = ( u / a.tiles_x ) % a.tiles_y;
+        ch = u / ( a.tiles_x * a.tiles_y );
+    }
+    const int x0 = tx * TX, y0 = ty * TY;
+    const int kbeg = ch * a.zc;
+    const int kend = min( kbeg + a.zc, g.n[2] );
+    const int nplanes = kend - kbeg;
+    const int nloads = nplanes + 2; // planes kbeg-1 .. kend
+
+    const int i0 = x0 + 2 * lx;
+    const bool vx0 = i0 < g.n[0], vx1 = i0 + 1 < g.n[0];
+    bool vy[RY];
+#pragma unroll
+    for ( int r = 0; r < RY; ++r )
+        vy[r] = y0 + wy + r * WY < g.n[1];
+
+    // ---- convergence bookkeeping of the iteration (the reference's test after kernel 1) ----------
+    const double alpha = S->alpha;
+    const double resid = sqrt( S->rr );
+    const bool conv = !S->fixed && resid <= S->thresh;
+    if ( a.unit_base + blockIdx.x == 0 && tid == 0 )
+    {
+        const int it = S->iter;
+        if ( it < CFB_HIST_MAX )
+            S->hist[it] = resid;
+        S->iter = it + 1;
+    }
+    if ( conv )
+    {
+        // x += alpha p of the converged iteration; nothing else (the loop breaks here)
+        for ( int k = kbeg; k < kend; ++k )
+#pragma unroll
+            for ( int r = 0; r < RY; ++r )
+            {
+                if ( !vy[r] || !vx0 )
+                    continue;
+                const long long o = geo_off( g, i0, y0 + wy + r * WY, k );
+                if ( vx1 )
+                {
+                    const double2 pv = *reinterpret_cast<const double2*>( a.p_old + o );
+                    double2 xv = *reinterpret_cast<double2*>( a.x + o );
+                    xv.x = fma( alpha, pv.x, xv.x );
+                    xv.y = fma( alpha, pv.y, xv.y );
+                    *reinterpret_cast<double2*>( a.x + o ) = xv;
+                }
+                else
+                    a.x[o] = fma( alpha, a.p_old[o], a.x[o] );
+            }
+        return;
+    }
+    const double beta = S->rz_new / S->rz_old;
+
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__( 8 ) unsigned long long full_bar[NS];
+    const uint32_t smem_base = ( smem_u32( smem_raw ) + 127u ) & ~127u;
+    double* stage0 = reinterpret_cast<double*>( smem_raw + ( smem_base - smem_u32( smem_raw ) ) );
+    double* pn0 = stage0 + NS * STAGED;
+
+    if ( tid == 0 )
+    {
+        prefetch_tmap( &tmap_r );
+        prefetch_tmap( &tmap_p );
+#pragma unroll
+        for ( int s = 0; s < NS; ++s )
+            mbar_init( smem_u32( &full_bar[s] ), 1 );
+        fence_barrier_init();
+    }
+    __syncthreads();
+    dd_t acc = fused_unit<C, XS, FLAT>( tmap_r, tmap_p, g, op, a, x0, y0, kbeg, kend, alpha, beta, stage0, pn0, full_bar, smem_base, 0 );
 
     // p.Ap: block partials at [unit_base + blockIdx.x], the block drawing the last of
     // `units_total` tickets finalises (deterministic: double-double sums, order-independent)
@@ -592,6 +632,195 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
             if ( tid == 0 )
                 S->pAp = sum[0].hi + sum[0].lo;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent form of the two-kernel iteration for blocks whose CG vectors stay in the L2 (64^3 ... ~160^3): there
+// an iteration is not bandwidth- but latency-bound — every kernel of the launch-per-phase form pays its launch, its
+// prologue and the tail of its last-block reduction (~12.7 us per kernel whatever the size, measured at 64^3:
+// profiles/r1_sweep_fused2.log), i.e. ~25 of the ~41 us of an iteration at 128^3.  Here ONE cooperative launch runs
+// a batch of iterations: phase A on the block's rows, grid barrier, every block adds the block partials (exact
+// double-double sums: the same value everywhere), phase B on the block's units (fused_unit above, the shared-memory
+// ring and its stage barriers carried from unit to unit), grid barrier, sums again.  The CG scalars live in
+// registers, identical in every block; block 0 writes them back at the end, in the layout the launch-per-phase
+// kernels read, so the two forms can take turns inside one solve.  Same statements on the same values: the results
+// are bit-identical to the other forms and to the checker.
+struct PersistArgs
+{
+    double *x, *r, *q;
+    double* pbuf[2];
+    int pcur; // pbuf[pcur] holds the search direction when the launch starts
+    CgState* S;
+    double* partials;
+    int pstride; // entries per value of the partial-sum scratch: values 0, 1 phase A, value 2 phase B, per BLOCK
+    int tiles_x, tiles_y, zc, hx, units_total;
+    int txp_log2;
+    int niters; // iterations of this launch (fewer when the tolerance is met)
+};
+
+__device__ __forceinline__ void fence_proxy_async_global()
+{
+#ifdef __CUDA_ARCH__
+    // my generic-proxy stores (r, p, x, q) before the TMA (async-proxy) loads other blocks issue behind the barrier
+    asm volatile( "fence.proxy.async;" ::: "memory" );
+#endif
+}
+
+template <class C, bool FLAT>
+__global__ void __launch_bounds__( C::NT, C::CTAS )
+    cg_persistent_kernel( const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_p0,
+                          const __grid_constant__ CUtensorMap tmap_p1, const __grid_constant__ Geo g,
+                          const __grid_constant__ OpConst op, const __grid_constant__ PersistArgs a )
+{
+    constexpr int TX = C::TX, TY = C::TY, NS = C::NS;
+    constexpr int STAGED = C::STAGE_BYTES / 8;
+    namespace cgx = cooperative_groups;
+    cgx::grid_group grid = cgx::this_grid();
+    CgState* S = a.S;
+    const int tid = threadIdx.x;
+    const int bid = (int)blockIdx.x, nb = (int)gridDim.x;
+
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__( 8 ) unsigned long long full_bar[NS];
+    __shared__ dd_t s_red[C::NT / 32];
+    __shared__ double s_bc[2];
+    const uint32_t smem_base = ( smem_u32( smem_raw ) + 127u ) & ~127u;
+    double* stage0 = reinterpret_cast<double*>( smem_raw + ( smem_base - smem_u32( smem_raw ) ) );
+    double* pn0 = stage0 + NS * STAGED;
+    if ( tid == 0 )
+    {
+        prefetch_tmap( &tmap_r );
+        prefetch_tmap( &tmap_p0 );
+        prefetch_tmap( &tmap_p1 );
+#pragma unroll
+        for ( int s = 0; s < NS; ++s )
+            mbar_init( smem_u32( &full_bar[s] ), 1 );
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // the CG scalars: the same in every block at every moment
+    double rz_old = S->rz_old, pAp = S->pAp, rr = S->rr, rz_new = S->rz_new, alpha = S->alpha;
+    int iter = S->iter;
+    const int fixed = S->fixed;
+    const double thresh = S->thresh;
+    bool done = S->done != 0;
+    int pc = a.pcur, lbase = 0;
+
+    // sum of one value's block partials, the same double in every thread of every block
+    auto total = [&]( int value ) -> double {
+        dd_t t = { 0.0, 0.0 };
+        for ( int b = tid; b < nb; b += C::NT )
+        {
+            dd_t w;
+            w.hi = __ldcg( a.partials + ( (size_t)value * a.pstride + b ) * 2 + 0 );
+            w.lo = __ldcg( a.partials + ( (size_t)value * a.pstride + b ) * 2 + 1 );
+            t = dd_add( t, w );
+        }
+        t = dd_block_sum<C::NT>( t, s_red );
+        if ( tid == 0 )
+            s_bc[value & 1] = t.hi + t.lo;
+        __syncthreads();
+        return s_bc[value & 1];
+    };
+    auto publish = [&]( int value, dd_t v ) {
+        v = dd_block_sum<C::NT>( v, s_red );
+        if ( tid == 0 )
+        {
+            a.partials[( (size_t)value * a.pstride + bid ) * 2 + 0] = v.hi;
+            a.partials[( (size_t)value * a.pstride + bid ) * 2 + 1] = v.lo;
+        }
+    };
+
+    for ( int n = 0; n < a.niters && !done; ++n )
+    {
+        // ---- phase A (cg_rupdate_kernel): the tolerance met by the previous iteration ends the solve
+        if ( iter > 0 && !fixed && sqrt( rr ) <= thresh )
+        {
+            done = true;
+            break;
+        }
+        alpha = rz_old / pAp;
+        dd_t arr = { 0.0, 0.0 }, arz = { 0.0, 0.0 };
+        rupdate_rows( g, op, a.q, a.r, -alpha, a.txp_log2, bid, nb, arr, arz );
+        publish( 0, arr );
+        publish( 1, arz );
+        fence_proxy_async_global();
+        grid.sync();
+        rr = total( 0 );
+        rz_new = total( 1 );
+
+        // ---- phase B (cg_fused_kernel)
+        const double resid = sqrt( rr );
+        const bool conv = !fixed && resid <= thresh;
+        if ( bid == 0 && tid == 0 && iter < CFB_HIST_MAX )
+            S->hist[iter] = resid;
+        ++iter;
+        const double* p_old = a.pbuf[pc];
+        if ( conv )
+        {
+            // x += alpha p of the converged iteration; nothing else (the loop breaks here)
+            const unsigned npx = (unsigned)( ( g.n[0] + 1 ) >> 1 );
+            const unsigned tot = npx * (unsigned)g.n[1] * (unsigned)g.n[2];
+            for ( unsigned t = (unsigned)bid * C::NT + tid; t < tot; t += (unsigned)nb * C::NT )
+            {
+                const unsigned row = t / npx;
+                const int i = 2 * (int)( t - row * npx );
+                const int k = (int)( row / (unsigned)g.n[1] );
+                const int j = (int)( row - (unsigned)k * (unsigned)g.n[1] );
+                const long long o = geo_off( g, i, j, k );
+                if ( i + 1 < g.n[0] )
+                {
+                    const double2 pv = *reinterpret_cast<const double2*>( p_old + o );
+                    double2 xv = *reinterpret_cast<double2*>( a.x + o );
+                    xv.x = fma( alpha, pv.x, xv.x );
+                    xv.y = fma( alpha, pv.y, xv.y );
+                    *reinterpret_cast<double2*>( a.x + o ) = xv;
+                }
+                else
+                    a.x[o] = fma( alpha, p_old[o], a.x[o] );
+            }
+            done = true;
+            break;
+        }
+        const double beta = rz_new / rz_old;
+        FusedArgs fa{};
+        fa.x = a.x;
+        fa.p = a.pbuf[pc ^ 1];
+        fa.q = a.q;
+        fa.p_old = p_old;
+        fa.hx = a.hx;
+        fa.zc = a.zc;
+        fa.store_q = 1;
+        dd_t acc = { 0.0, 0.0 };
+        for ( int u = bid; u < a.units_total; u += nb )
+        {
+            const int tx = u % a.tiles_x, ty = ( u / a.tiles_x ) % a.tiles_y, ch = u / ( a.tiles_x * a.tiles_y );
+            const int kbeg = ch * a.zc, kend = min( kbeg + a.zc, g.n[2] );
+            const dd_t au = fused_unit<C, false, FLAT>( tmap_r, pc ? tmap_p1 : tmap_p0, g, op, fa, tx * TX, ty * TY, kbeg, kend,
+                                                        alpha, beta, stage0, pn0, full_bar, smem_base, lbase );
+            acc = dd_add( acc, au );
+            // every load index of the unit was issued and consumed (FLAT: the one plane there is, at index 1)
+            lbase = ( lbase + ( FLAT ? NS : kend - kbeg + 2 ) ) % ( 2 * NS );
+        }
+        publish( 2, acc );
+        fence_proxy_async_global();
+        grid.sync();
+        pAp = total( 2 );
+        rz_old = rz_new;
+        pc ^= 1;
+    }
+    if ( bid == 0 && tid == 0 )
+    {
+        S->rz_old = rz_old;
+        S->pAp = pAp;
+        S->rr = rr;
+        S->rz_new = rz_new;
+        S->alpha = alpha;
+        S->iter = iter;
+        if ( done )
+            S->done = 1;
     }
 }
 
@@ -809,6 +1038,87 @@ int launch_cg_finish( cfb_ctx* c )
 {
     cg_finish_kernel<<<1, 1, 0, c->stream>>>( c->d_state );
     return 1;
+}
+
+// ---- persistent form (small blocks, one GPU) ---------------------------------------------------
+namespace
+{
+template <class C, bool FLAT>
+int launch_persist_cfg( cfb_ctx* c, PersistArgs& a )
+{
+    auto* fn = &cg_persistent_kernel<C, FLAT>;
+    static int occ = -1;
+    if ( occ < 0 )
+    {
+        if ( cudaFuncSetAttribute( fn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES ) != cudaSuccess ||
+             cudaOccupancyMaxActiveBlocksPerMultiprocessor( &occ, fn, C::NT, C::SMEM_BYTES ) != cudaSuccess || occ < 1 )
+        {
+            occ = -1;
+            cudaGetLastError();
+            note_rc( c, cfb_fail( c, CFB_ERR_CUDA, "persistent CG kernel: no resident block fits an SM" ) );
+            return 0;
+        }
+    }
+    // every block resident at once (the grid barrier needs it; the cooperative launch checks it)
+    const int grid = std::min( occ * c->sm_count, CFB_MAX_PARTIALS );
+    void* args[] = { (void*)&c->tmap_fr, (void*)&c->tmap_fp[0], (void*)&c->tmap_fp[1], (void*)&c->g, (void*)&c->op, (void*)&a };
+    const cudaError_t e = cudaLaunchCooperativeKernel( fn, dim3( grid ), dim3( C::NT ), args, C::SMEM_BYTES, c->stream );
+    if ( e != cudaSuccess )
+    {
+        cudaGetLastError();
+        note_rc( c, cfb_fail( c, CFB_ERR_CUDA, std::string( "persistent CG kernel: " ) + cudaGetErrorString( e ) ) );
+        return 0;
+    }
+    return 1;
+}
+} // namespace
+
+// the tile shapes the persistent kernel is instantiated for (those fused_setup picks for small blocks)
+bool cg_persist_supported( const cfb_ctx* c )
+{
+    const int key = c->fu_tx * 10000 + c->fu_ty * 100 + c->fu_stages;
+    return key == 641603 || key == 640804 || key == 640803 || key == 1281603;
+}
+
+// `iters` iterations of the two-kernel form in one cooperative launch (the caller has checked cg_persist_applies)
+int launch_cg_persistent( cfb_ctx* c, int iters )
+{
+    const Geo& g = c->g;
+    PersistArgs a{};
+    a.x = c->lhs;
+    a.r = c->cg_r;
+    a.q = c->cg_q;
+    a.pbuf[0] = c->cg_pbuf[0];
+    a.pbuf[1] = c->cg_pbuf[1];
+    a.pcur = c->pcur;
+    a.S = c->d_state;
+    a.partials = c->d_partials;
+    a.pstride = c->partials_cap;
+    a.hx = 16;
+    int chunks;
+    fused_tiling( c, a.tiles_x, a.tiles_y, a.zc, chunks );
+    a.units_total = a.tiles_x * a.tiles_y * chunks;
+    const int npx = ( g.n[0] + 1 ) / 2;
+    a.txp_log2 = 5;
+    while ( ( 1 << a.txp_log2 ) < npx && a.txp_log2 < 8 )
+        ++a.txp_log2;
+    a.niters = iters;
+    const bool flat = g.D == 2 && c->flat_2d;
+    const int key = c->fu_tx * 10000 + c->fu_ty * 100 + c->fu_stages;
+    switch ( key )
+    {
+    case 641603:
+        return flat ? launch_persist_cfg<FusedCfg<64, 16, 3>, true>( c, a ) : launch_persist_cfg<FusedCfg<64, 16, 3>, false>( c, a );
+    case 640804:
+        return flat ? launch_persist_cfg<FusedCfg<64, 8, 4>, true>( c, a ) : launch_persist_cfg<FusedCfg<64, 8, 4>, false>( c, a );
+    case 640803:
+        return flat ? launch_persist_cfg<FusedCfg<64, 8, 3>, true>( c, a ) : launch_persist_cfg<FusedCfg<64, 8, 3>, false>( c, a );
+    case 1281603:
+        return flat ? launch_persist_cfg<FusedCfg<128, 16, 3>, true>( c, a ) : launch_persist_cfg<FusedCfg<128, 16, 3>, false>( c, a );
+    default:
+        note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "persistent CG kernel: tile configuration not instantiated" ) );
+        return 0;
+    }
 }
 
 // phase B over all units (which = 0), or over the device unit list `c->d_units` split into

@@ -22,9 +22,10 @@ HEADERS = ["cfb_internal.h", "device_geo.cuh", "device_peer.cuh", "device_cg1.cu
 # kernels whose threads meet at __syncthreads() for real: one fiber per CUDA thread
 # (a name with its template arguments selects that instantiation only: phase A meets at barriers only when it
 # runs the mailbox exchange itself)
-COOP_KERNELS = {"cg_xchg_kernel", "cg_face_kernel", "stencil7_dot_tma", "cg_fused_kernel", "cg_rupdate_kernel<true>", "mg_coarse_cycle_kernel",
+COOP_KERNELS = {"cg_xchg_kernel", "cg_persistent_kernel", "cg_face_kernel", "stencil7_dot_tma", "cg_fused_kernel", "cg_rupdate_kernel<true>", "mg_coarse_cycle_kernel",
                 "mg_xchg_kernel"}
-STANDINS = ["cuda_runtime.h", "cuda.h", "nccl.h", "device_reduce.cuh", "device_tma.cuh", "emul_glue.cpp", "nccl_emul.cpp"]
+STANDINS = ["cuda_runtime.h", "cuda.h", "nccl.h", "cooperative_groups.h", "device_reduce.cuh", "device_tma.cuh", "emul_glue.cpp",
+            "nccl_emul.cpp"]
 
 
 def _match(s, i, open_c, close_c):

@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <utility>
+#include <type_traits>
 
 #define CFB_HOST_EMUL 1
 #define __global__
@@ -200,6 +202,25 @@ inline long long clock64() { return cfb_emul::clock_ns(); }
 inline cudaError_t cudaStreamCreateWithFlags( cudaStream_t* s, unsigned )
 {
     *s = reinterpret_cast<cudaStream_t>( std::malloc( 1 ) );
+    return cudaSuccess;
+}
+// cooperative launch: one block of fibers (see cooperative_groups.h in this directory); the argument pointers are
+// dereferenced by the kernel's own parameter types
+template <class... A, size_t... I>
+inline void cfb_emul_call( void ( *f )( A... ), void** args, std::index_sequence<I...> )
+{
+    f( *static_cast<typename std::remove_cv<typename std::remove_reference<A>::type>::type*>( args[I] )... );
+}
+template <class... A>
+inline cudaError_t cudaLaunchCooperativeKernel( void ( *f )( A... ), dim3, dim3 block, void** args, size_t, cudaStream_t )
+{
+    cfb_emul::launch_coop( dim3( 1 ), block, [=]() { cfb_emul_call( f, args, std::index_sequence_for<A...>() ); } );
+    return cudaSuccess;
+}
+template <class F>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor( int* n, F, int, size_t )
+{
+    *n = 1;
     return cudaSuccess;
 }
 inline cudaError_t cudaDeviceGetStreamPriorityRange( int* lo, int* hi )

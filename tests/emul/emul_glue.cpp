@@ -442,6 +442,14 @@ int launch_cg1_stencil( cfb_ctx* c, int init, bool mail )
     return 1;
 }
 
+// the persistent form exists in the TMA kernels only: never chosen with the plain-loop stand-ins
+bool cg_persist_supported( const cfb_ctx* ) { return false; }
+int launch_cg_persistent( cfb_ctx* c, int )
+{
+    note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "plain-loop stand-in: no persistent form" ) );
+    return 0;
+}
+
 int launch_cg_finish( cfb_ctx* c )
 {
     CgState* S = c->d_state;

@@ -565,3 +565,50 @@ def test_emulated_single_reduction_cg(emul, dim, cells, kw):
         res = g2.pcg_solve()
         assert res == o2.pcg_solve() and np.isfinite(res[1]), variant
         assert np.array_equal(g2.get(K.PRESSURE), o2.get(K.PRESSURE)), variant
+
+
+@pytest.mark.parametrize("dim,cells,kw", [(3, 32, {}), (3, (70, 33, 21), dict(boundary_type=[K.SOLID, K.FREE, K.SOLID, K.SOLID, K.SOLID, K.FREE])),
+                                          (3, (130, 20, 9), {}), (2, (150, 90), {}), (2, 64, dict(boundary_type=[K.FREE, K.SOLID, K.SOLID, K.FREE]))])
+def test_emulated_persistent_cg_iterations(emul, dim, cells, kw):
+    """"cg_persist": batches of iterations of the two-kernel form in ONE cooperative launch (phase A, grid barrier,
+    phase B over the block's units with the shared-memory ring carried from unit to unit, grid barrier) — what small,
+    L2-resident blocks run by default.  Emulated with one block of fibers, which walks through EVERY unit: the
+    carried ring indices, the state hand-over between launches (batches of 32) and to / from the launch-per-phase
+    kernels, convergence inside a batch, fixed iteration counts, whole steps; bit for bit against the oracle."""
+    if not emul.tma:
+        pytest.skip("the persistent kernel is built from the TMA kernels' device functions")
+    cfg = make_cfg(dim, cells, box=box_of(cells), **kw)
+    g, o = Context(emul, cfg), Oracle(cfg)
+    g.set_tuning("cg_persist", 1)
+    rng = np.random.default_rng(51)
+    vel = {f: rng.uniform(-1, 1, size=g.shape(f)) for f in fields_of(dim)[1:]}
+    for s in (g, o):
+        for f, a in vel.items():
+            s.set(f, a)
+        s.add_inputs()
+        s.build_rhs()
+    l0 = g.stats()["kernel_launches"]
+    res = g.pcg_solve()
+    launches = g.stats()["kernel_launches"] - l0
+    assert res == o.pcg_solve() and res[0] > 40
+    assert launches < 12 + res[0] // 16, (launches, res)  # one launch per batch of 32, not two per iteration
+    assert np.array_equal(g.get(K.PRESSURE), o.get(K.PRESSURE)) and np.array_equal(g.residual_history(), o.residual_history())
+    # fixed iteration counts (odd: the direction ends in the other buffer), then the launch-per-phase form on the same
+    # context, then persistent again
+    g2, o2 = Context(emul, make_cfg(dim, cells, box=box_of(cells), fixed_iters=37, **kw)), Oracle(make_cfg(dim, cells, box=box_of(cells), fixed_iters=37, **kw))
+    for persist in (1, 0, 1, 1):
+        g2.set_tuning("cg_persist", persist)
+        for s in (g2, o2):
+            for f, a in vel.items():
+                s.set(f, a)
+            s.add_inputs()
+            s.build_rhs()
+        assert g2.pcg_solve() == o2.pcg_solve(), persist
+        assert np.array_equal(g2.get(K.PRESSURE), o2.get(K.PRESSURE)), persist
+        assert np.array_equal(g2.get(K.CG_R), o2.get(K.CG_R)), persist
+    if dim == 3 and cells != 32:
+        return  # (fibers are slow: whole steps on one 3-D case)
+    g3, o3 = Context(emul, cfg), Oracle(cfg)
+    g3.set_tuning("cg_persist", 1)
+    assert run(g3, 2) == run(o3, 2)
+    same_state(g3, o3, dim)

@@ -856,6 +856,14 @@ def main():
                                          "frac_of_peak": gbs5 / peak, "bytes_per_cell": BYTES_ITER[args.cg_variant],
                                          "final_residual": r5,
                                          "note": "at 256^3 a vector (134 MB) is about the size of the L2: not an HBM-only number"}
+            try:  # ncu DRAM bytes of the two kernels at this size, committed constants like roofline.traffic
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                extra["config2_pcg_only"]["ncu_dram_bytes_per_launch"] = {
+                    "cg_fused_kernel": tj.get(f"cg_variant1_dominant_{n2}"), "cg_rupdate_kernel": tj.get(f"cg_variant1_rupdate_{n2}"),
+                    "algorithmic": {"cg_fused_kernel": 48 * n2 ** 3, "cg_rupdate_kernel": 24 * n2 ** 3},
+                    "source": "profiles/r2_launches_cg%d.csv (ncu, L2 flushed before every launch)" % n2}
+            except Exception:  # noqa: BLE001
+                pass
             s5.close()
         except Exception as e:  # noqa: BLE001
             extra["config2_pcg_only"] = {"error": repr(e)[:300]}

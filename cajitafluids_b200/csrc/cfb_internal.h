@@ -76,6 +76,7 @@ struct CgState
     int fixed;                      // fixed-iteration mode: never set done
     int pad;
     unsigned int ticket[4];         // last-block tickets: [0] init/axpy, [1] stencil
+    unsigned int gbar[2];           // persistent kernel: grid barrier (arrivals of the running barrier | generation)
     double hist[CFB_HIST_MAX];
 };
 

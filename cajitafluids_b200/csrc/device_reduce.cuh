@@ -1,14 +1,17 @@
-// device_reduce.cuh — order-independent (to the last bit) grid reductions.
+// device_reduce.cuh — grid reductions whose result does not depend on the summation order (to ~2^-104).
 //
 // The CG scalars (r.r, z.r, p.Ap) steer the whole solve; a 1-ulp difference in one of them is
 // amplified by ~1e4-1e5 over a few hundred iterations.  The reference leaves their summation order
 // to Kokkos::parallel_reduce.  Here every thread accumulates the (double-rounded) products in
-// double-double (TwoSum error-free transformation, ~2^-104 relative error), warps/blocks/grid
-// combine double-doubles, and only the final value is rounded to double.  The result is the
-// correctly rounded exact sum of the products — independent of thread count, tile shape, launch
-// configuration or block decomposition — so the CPU checker (which does the same) and any
-// multi-GPU split produce bit-identical alpha/beta.  Cost: 7 FP64 adds per term, invisible in
-// HBM-bound kernels.  No floating-point atomics anywhere.
+// double-double (TwoSum error-free transformation; the low word is a plain sum of the error terms, so
+// the pair carries ~106 bits: relative error ~2^-104), warps / blocks / grid combine double-doubles, and
+// only the final value is rounded to double.  That is not an exact (Kulisch) accumulator: two orders of
+// summation can differ in the ~106th bit and hence, with probability ~2^-50 per sum, in the rounded
+// double.  In practice — and in every test, 1 to 8 blocks, every tiling — thread count, tile shape,
+// launch configuration and block decomposition do not change a bit of alpha / beta, and the CPU checker,
+// which accumulates the same way, agrees bit for bit; the tests assert the stated bar (iterations +-1,
+// 1e-10) first and bit-identity second.  Cost: 7 FP64 adds per term, invisible in HBM-bound kernels.
+// No floating-point atomics anywhere.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -28,7 +28,6 @@
 #include "device_peer.cuh"
 
 #include <algorithm>
-#include <cooperative_groups.h>
 
 namespace
 {
@@ -640,7 +639,7 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
 // an iteration is not bandwidth- but latency-bound — every kernel of the launch-per-phase form pays its launch, its
 // prologue and the tail of its last-block reduction (~12.7 us per kernel whatever the size, measured at 64^3:
 // profiles/r1_sweep_fused2.log), i.e. ~25 of the ~41 us of an iteration at 128^3.  Here ONE cooperative launch runs
-// a batch of iterations: phase A on the block's rows, grid barrier, every block adds the block partials (exact
+// a batch of iterations: phase A on the block's rows, grid barrier (grid_barrier below), every block adds the block partials (exact
 // double-double sums: the same value everywhere), phase B on the block's units (fused_unit above, the shared-memory
 // ring and its stage barriers carried from unit to unit), grid barrier, sums again.  The CG scalars live in
 // registers, identical in every block; block 0 writes them back at the end, in the layout the launch-per-phase
@@ -667,6 +666,40 @@ __device__ __forceinline__ void fence_proxy_async_global()
 #endif
 }
 
+// Barrier over the blocks of a cooperative launch (all resident): arrivals are counted, the last arrival resets the
+// count and bumps the generation the others spin on.  One atomic and one spinning thread per block — cheaper than
+// the general-purpose cooperative-groups barrier where an iteration has ~10 us to spend on two of them.  The fences
+// make every thread's earlier global stores visible to every block behind the barrier (cumulativity through the
+// block barriers on either side).  Bounded: a block that never arrives surfaces as an error, not as a hung GPU.
+__device__ __forceinline__ void grid_barrier( CgState* S, const unsigned nblocks, unsigned& gen )
+{
+    __syncthreads();
+    if ( threadIdx.x == 0 )
+    {
+        __threadfence();
+        volatile unsigned* vgen = &S->gbar[1];
+        if ( atomicAdd( &S->gbar[0], 1u ) == nblocks - 1 )
+        {
+            S->gbar[0] = 0u;
+            __threadfence();
+            atomicAdd( &S->gbar[1], 1u );
+        }
+        else
+        {
+            const long long t0 = clock64();
+            while ( *vgen == gen )
+                if ( clock64() - t0 > 8000000000ll )
+                {
+                    S->xerror = 1;
+                    break;
+                }
+        }
+        __threadfence();
+    }
+    ++gen;
+    __syncthreads();
+}
+
 template <class C, bool FLAT>
 __global__ void __launch_bounds__( C::NT, C::CTAS )
     cg_persistent_kernel( const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_p0,
@@ -675,11 +708,10 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
 {
     constexpr int TX = C::TX, TY = C::TY, NS = C::NS;
     constexpr int STAGED = C::STAGE_BYTES / 8;
-    namespace cgx = cooperative_groups;
-    cgx::grid_group grid = cgx::this_grid();
     CgState* S = a.S;
     const int tid = threadIdx.x;
     const int bid = (int)blockIdx.x, nb = (int)gridDim.x;
+    unsigned gen = *reinterpret_cast<volatile unsigned*>( &S->gbar[1] ); // read before this block's first arrival
 
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__( 8 ) unsigned long long full_bar[NS];
@@ -708,21 +740,35 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     bool done = S->done != 0;
     int pc = a.pcur, lbase = 0;
 
-    // sum of one value's block partials, the same double in every thread of every block
-    auto total = [&]( int value ) -> double {
-        dd_t t = { 0.0, 0.0 };
+    // sums of the block partials of values v0 (and v1 >= 0), the same doubles in every thread of every block; the
+    // loads of both values are in flight together
+    auto totals = [&]( int v0, int v1, double& out0, double& out1 ) {
+        dd_t t0 = { 0.0, 0.0 }, t1 = { 0.0, 0.0 };
         for ( int b = tid; b < nb; b += C::NT )
         {
-            dd_t w;
-            w.hi = __ldcg( a.partials + ( (size_t)value * a.pstride + b ) * 2 + 0 );
-            w.lo = __ldcg( a.partials + ( (size_t)value * a.pstride + b ) * 2 + 1 );
-            t = dd_add( t, w );
+            dd_t w0, w1 = { 0.0, 0.0 };
+            w0.hi = __ldcg( a.partials + ( (size_t)v0 * a.pstride + b ) * 2 + 0 );
+            w0.lo = __ldcg( a.partials + ( (size_t)v0 * a.pstride + b ) * 2 + 1 );
+            if ( v1 >= 0 )
+            {
+                w1.hi = __ldcg( a.partials + ( (size_t)v1 * a.pstride + b ) * 2 + 0 );
+                w1.lo = __ldcg( a.partials + ( (size_t)v1 * a.pstride + b ) * 2 + 1 );
+            }
+            t0 = dd_add( t0, w0 );
+            t1 = dd_add( t1, w1 );
         }
-        t = dd_block_sum<C::NT>( t, s_red );
+        t0 = dd_block_sum<C::NT>( t0, s_red );
+        if ( v1 >= 0 )
+            t1 = dd_block_sum<C::NT>( t1, s_red );
         if ( tid == 0 )
-            s_bc[value & 1] = t.hi + t.lo;
+        {
+            s_bc[0] = t0.hi + t0.lo;
+            s_bc[1] = t1.hi + t1.lo;
+        }
         __syncthreads();
-        return s_bc[value & 1];
+        out0 = s_bc[0];
+        out1 = s_bc[1];
+        __syncthreads(); // s_bc is free again
     };
     auto publish = [&]( int value, dd_t v ) {
         v = dd_block_sum<C::NT>( v, s_red );
@@ -747,9 +793,8 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
         publish( 0, arr );
         publish( 1, arz );
         fence_proxy_async_global();
-        grid.sync();
-        rr = total( 0 );
-        rz_new = total( 1 );
+        grid_barrier( S, (unsigned)nb, gen );
+        totals( 0, 1, rr, rz_new );
 
         // ---- phase B (cg_fused_kernel)
         const double resid = sqrt( rr );
@@ -806,8 +851,11 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
         }
         publish( 2, acc );
         fence_proxy_async_global();
-        grid.sync();
-        pAp = total( 2 );
+        grid_barrier( S, (unsigned)nb, gen );
+        {
+            double unused;
+            totals( 2, -1, pAp, unused );
+        }
         rz_old = rz_new;
         pc ^= 1;
     }

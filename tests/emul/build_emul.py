@@ -24,7 +24,7 @@ HEADERS = ["cfb_internal.h", "device_geo.cuh", "device_peer.cuh", "device_cg1.cu
 # runs the mailbox exchange itself)
 COOP_KERNELS = {"cg_xchg_kernel", "cg_persistent_kernel", "cg_face_kernel", "stencil7_dot_tma", "cg_fused_kernel", "cg_rupdate_kernel<true>", "mg_coarse_cycle_kernel",
                 "mg_xchg_kernel"}
-STANDINS = ["cuda_runtime.h", "cuda.h", "nccl.h", "cooperative_groups.h", "device_reduce.cuh", "device_tma.cuh", "emul_glue.cpp",
+STANDINS = ["cuda_runtime.h", "cuda.h", "nccl.h", "device_reduce.cuh", "device_tma.cuh", "emul_glue.cpp",
             "nccl_emul.cpp"]
 
 

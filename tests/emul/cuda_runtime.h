@@ -204,7 +204,8 @@ inline cudaError_t cudaStreamCreateWithFlags( cudaStream_t* s, unsigned )
     *s = reinterpret_cast<cudaStream_t>( std::malloc( 1 ) );
     return cudaSuccess;
 }
-// cooperative launch: one block of fibers (see cooperative_groups.h in this directory); the argument pointers are
+// cooperative launch: ONE block of fibers (a kernel with a grid barrier must work for any grid size, which is what lets
+// it be checked here: its barrier degenerates to the block barrier); the argument pointers are
 // dereferenced by the kernel's own parameter types
 template <class... A, size_t... I>
 inline void cfb_emul_call( void ( *f )( A... ), void** args, std::index_sequence<I...> )

@@ -19,7 +19,7 @@ def box_of(cells):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dim,cells,kw", [(3, 64, {}), (3, (70, 50, 21), dict(boundary_type=[K.SOLID, K.FREE, K.SOLID, K.SOLID, K.SOLID, K.FREE])),
                                           (3, (130, 36, 5), {}), (3, (128, 96, 80), {}), (2, (150, 90), {}),
-                                          (2, 512, dict(boundary_type=[K.FREE, K.SOLID, K.SOLID, K.FREE]))])
+                                          (2, 256, dict(boundary_type=[K.FREE, K.SOLID, K.SOLID, K.FREE]))])
 def test_cuda_persistent_iterations_against_the_oracle(dim, cells, kw):
     from cajitafluids_b200 import Solver
     cfg = make_cfg(dim, cells, box=box_of(cells), **kw)

@@ -174,8 +174,8 @@ struct cfb_ctx
     int* d_units = nullptr; // (tile_x, tile_y, chunk) triples: interior units first, then boundary
     int n_units = 0, n_interior = 0;
     // "cg_persist" tuning key: 1 = run batches of iterations of the two-kernel form in ONE cooperative launch
-    // (kernels_fused.cu: cg_persistent_kernel), 0 = never, -1 = where it pays: one block whose five CG vectors stay
-    // in the L2 (the launch-per-phase kernels are latency-bound there)
+    // (kernels_fused.cu: cg_persistent_kernel), 0 = never, -1 = where it pays: one block of ~80^3 ... ~170^3 cells
+    // (the launch-per-phase kernels are latency-bound there; cg_persist_applies below)
     int cg_persist = -1;
     bool fu_reverse = false;  // phase B walks the units top-down (L2 reuse between the phases)
     int ru_ctas = 3;          // phase A: CTAs per SM of the grid-stride launch
@@ -355,9 +355,11 @@ inline bool cg_persist_applies( const cfb_ctx* c )
         return false;
     if ( c->cg_persist > 0 )
         return true;
-    // automatic: five vectors of the block within ~2/3 of the 126 MB L2 (<= ~128^3 cells)
+    // automatic: where it measured faster than the launch-per-phase kernels (profiles/r2_small_grids.json: 96^3
+    // 22.8 vs 28.9 us per iteration, 128^3 35.6 vs 41.0, 160^3 85.0 vs 87.9; 64^3 21.9 vs 20.7 and 192^3 and above
+    // no gain: there the data movement, not the launch / reduction latency, is what an iteration costs)
     const double cells = (double)c->g.n[0] * c->g.n[1] * c->g.n[2];
-    return cells * 8.0 * 5.0 <= 90.0e6;
+    return cells >= 4.0e5 && cells <= 5.0e6;
 }
 // output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
 int output_write( cfb_ctx* c, const char* dir, int time_step );

@@ -476,11 +476,70 @@ def multi_gpu_extras(args, s, extra, dist, torch, np, rank, world, local, blocks
         except Exception as e:  # noqa: BLE001
             extra["strong_scaling"] = {"error": repr(e)[:300]}
 
+    # 2b. the same strong-scaled problem on a block grid that does not split x (its faces are strided in memory and
+    #     travel through a staging area): 8 GPUs as 1 x 2 x 4 instead of 2 x 2 x 2
+    if args.scaling == "weak" and world == 8 and not args.blocks:
+        try:
+            alt = (1, 2, 4)
+            cfg_a, g_a = make_config(args, rank, world, alt, scaling="strong")
+            cfg_a.device_id = local
+            attach_nccl(cfg_a, dist)
+            sa = Solver(cfg_a)
+            sa.fill_synthetic_velocity(0)
+            sa.build_rhs()
+            r = timed(sa, steps=5, warm=3)
+            r.update({"global_cells": list(g_a), "blocks": list(alt), "cells_local": int(np.prod(sa.owned_extent(K.QUANTITY)))})
+            extra["strong_scaling_blocks_1x2x4"] = r
+            sa.close()
+        except Exception as e:  # noqa: BLE001
+            extra["strong_scaling_blocks_1x2x4"] = {"error": repr(e)[:300]}
+
     # 3. decomposition parity against the single-block oracle
     try:
         extra["decomposition_parity"] = decomposition_parity(dist, torch, np, rank, world, local, blocks)
     except Exception as e:  # noqa: BLE001
         extra["decomposition_parity"] = {"error": repr(e)[:300]}
+
+    # 4. whole timesteps with the opt-in multigrid preconditioner, weak-scaled: timestep_cells^3 per GPU of the default
+    #    inflow problem (box edge = blocks, h = 1 / timestep_cells), the same global V-cycle block-decomposed
+    if args.timestep_cells > 0:
+        try:
+            from cajitafluids_b200 import default_config
+            from cajitafluids_b200.distributed import decompose
+            n = args.timestep_cells
+            gcfg = default_config(3, tuple(n * b for b in blocks), box=tuple(float(b) for b in blocks))
+            cfg_m = decompose(gcfg, rank, world, blocks)
+            cfg_m.device_id = local
+            attach_nccl(cfg_m, dist)
+            sm = Solver(cfg_m)
+            sm.set_preconditioner("mg")
+            err, dt_m, its = None, 0.0, 0
+            try:
+                sm.setup()
+                for _ in range(2):
+                    sm.step()
+                barrier()
+                it0 = sm.stats()["cg_iterations"]
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    sm.step()
+                barrier()
+                dt_m = time.perf_counter() - t0
+                its = sm.stats()["cg_iterations"] - it0
+            except Exception as e:  # noqa: BLE001
+                err = e
+            if all_ranks_ok(err is None):
+                t = torch.tensor([dt_m], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                extra["timesteps_per_s_mg"] = {"global_cells": [n * b for b in blocks], "cells_per_gpu": [n] * 3,
+                                               "value": 5 / float(t[0]), "cg_iters_per_step": its / 5, "interp_order": 3,
+                                               "mg_levels": sm.mg_num_levels(), "peer_mode": sm.stats()["peer_mode"],
+                                               "preconditioner": "opt-in multigrid V(2,2), the global cycle block-decomposed"}
+            else:
+                extra["timesteps_per_s_mg"] = {"error": repr(err)[:300] if err is not None else "another rank failed"}
+            sm.close()
+        except Exception as e:  # noqa: BLE001
+            extra["timesteps_per_s_mg"] = {"error": repr(e)[:300]}
 
 
 def decomposition_parity(dist, torch, np, rank, world, local, blocks, n=96, steps=3):

@@ -645,10 +645,12 @@ int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpac
                 f.lo[d] = g.n[d] - 1; // my last layer -> the high neighbour's low ghost (index -1)
                 f.shift[d] = g.n[d];
             }
-            if ( d == 0 )
+            if ( d == 0 && !c->peer_xdirect )
             {
                 // x faces travel packed into the neighbour's staging slot [its side facing me]; what the
                 // neighbour left in mine is scattered into my ghost column after the barrier
+                // ("peer_xdirect": stored straight into the neighbour's ghost column instead — 8-byte stores at the
+                // row stride over NVLink, no staging, no scatter launch on the receiver)
                 f.packed = 1;
                 f.dst = c->peer_xstage[s] + xslot( g, 1 - side, kind );
                 if ( unpack )
@@ -720,7 +722,7 @@ int peer_faces_async( cfb_ctx* c, int kind, int pbuf, cudaEvent_t after )
             f.lo[d] = g.n[d] - 1; // my last layer -> the high neighbour's low ghost (index -1)
             f.shift[d] = g.n[d];
         }
-        if ( d == 0 )
+        if ( d == 0 && !c->peer_xdirect )
         {
             // x faces travel packed (see peer_exchange) and are scattered by the receiver behind the flag wait
             f.packed = 1;

@@ -1145,8 +1145,6 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         return mg_set_coarse_kernel( c, value != 0 );
     else if ( k == "peer_xstage" )
         c->peer_xstage_reads = value != 0;
-    else if ( k == "peer_xdirect" )
-        c->peer_xdirect = value != 0;
     else if ( k == "time_kernels" )
     {
         c->time_kernels = value != 0;

@@ -218,9 +218,6 @@ struct cfb_ctx
     // "peer_xstage" tuning key; measured slower than scattering into the ghost columns (x split of 2 x
     // 512^3: 539 vs 581 it/s): the halo warp waits for the global loads plane by plane
     bool peer_xstage_reads = false;
-    // "peer_xdirect" tuning key: x faces stored straight into the neighbour's ghost column (strided 8-byte NVLink
-    // stores) instead of packed into its staging area and scattered there by one more launch
-    bool peer_xdirect = false;
     double* peer_xstage[2] = { nullptr, nullptr };
     PeerMail* mail_self = nullptr;
     PeerMail* mail[CFB_MAX_PEERS] = { nullptr };
@@ -327,7 +324,7 @@ inline bool peer_overlapped( const cfb_ctx* c )
 inline bool peer_xstaged( const cfb_ctx* c )
 {
     // (not with cg_variant 2: its phase A' reads the x ghosts of p from the ghost columns through TMA)
-    return cg_peer_mode( c ) && c->peer_xstage_reads && !c->peer_xdirect && c->cg_variant == 1 && ( c->nbr[0] >= 0 || c->nbr[1] >= 0 ) &&
+    return cg_peer_mode( c ) && c->peer_xstage_reads && c->cg_variant == 1 && ( c->nbr[0] >= 0 || c->nbr[1] >= 0 ) &&
            c->g.n[0] % c->fu_tx == 0;
 }
 int launch_cg_axpy( cfb_ctx* c );             // kernel 1 (+ fused kernel-2 reduction)

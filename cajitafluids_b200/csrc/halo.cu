@@ -645,12 +645,13 @@ int peer_exchange( cfb_ctx* c, int which, bool copy_r, int copy_pbuf, bool unpac
                 f.lo[d] = g.n[d] - 1; // my last layer -> the high neighbour's low ghost (index -1)
                 f.shift[d] = g.n[d];
             }
-            if ( d == 0 && !c->peer_xdirect )
+            if ( d == 0 )
             {
                 // x faces travel packed into the neighbour's staging slot [its side facing me]; what the
-                // neighbour left in mine is scattered into my ghost column after the barrier
-                // ("peer_xdirect": stored straight into the neighbour's ghost column instead — 8-byte stores at the
-                // row stride over NVLink, no staging, no scatter launch on the receiver)
+                // neighbour left in mine is scattered into my ghost column after the barrier.  (Storing them
+                // straight into the neighbour's ghost column — 8-byte stores at the row stride over NVLink, no
+                // staging, no scatter launch — was measured and is slower: 1071 vs 1151 iterations/s on an x split of
+                // 2 x 512^3, 170 vs 44 us exposed after phase B; profiles/r2_bench_n2_blocks211_xdirect{0,1}.json.)
                 f.packed = 1;
                 f.dst = c->peer_xstage[s] + xslot( g, 1 - side, kind );
                 if ( unpack )
@@ -722,7 +723,7 @@ int peer_faces_async( cfb_ctx* c, int kind, int pbuf, cudaEvent_t after )
             f.lo[d] = g.n[d] - 1; // my last layer -> the high neighbour's low ghost (index -1)
             f.shift[d] = g.n[d];
         }
-        if ( d == 0 && !c->peer_xdirect )
+        if ( d == 0 )
         {
             // x faces travel packed (see peer_exchange) and are scattered by the receiver behind the flag wait
             f.packed = 1;

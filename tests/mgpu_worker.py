@@ -157,8 +157,6 @@ def section_3(args, rank, gcfg, rank_cfg, rng, check):
               {"cg_variant": 1, "peer_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
              ("two-kernel, NVLink peer stores, phase B reads the x ghosts from the staging areas",
               {"cg_variant": 1, "peer_halo": 1, "peer_xstage": 1}),
-             ("two-kernel, NVLink peer stores, x faces straight into the ghost columns",
-              {"cg_variant": 1, "peer_halo": 1, "peer_xdirect": 1}),
              ("two-kernel, NCCL, interior overlapped with the r/p halo",
               {"cg_variant": 1, "peer_halo": 0, "overlap_halo": 1}),
              ("two-kernel, NCCL, halo first", {"cg_variant": 1, "peer_halo": 0, "overlap_halo": 0}),
@@ -169,7 +167,7 @@ def section_3(args, rank, gcfg, rank_cfg, rng, check):
              ("two-kernel without a stored q (64 B/cell), NVLink peer stores", {"cg_variant": 2, "peer_halo": 1}),
              ("two-kernel without a stored q (64 B/cell), NCCL", {"cg_variant": 2, "peer_halo": 0})]
     if args.quick:
-        modes = [modes[0], modes[1], modes[2], modes[3], modes[5]]
+        modes = [modes[0], modes[1], modes[2], modes[4]]
     if args.overlap:
         modes = [("overlapped exchange (faces on the side stream, reductions in the kernels' last blocks)",
                   {"cg_variant": 1, "peer_halo": 1, "peer_overlap": 1}),

@@ -380,8 +380,6 @@ MODES = [("peer, small tiles", True, {"fused_stages": 4, "fused_zc": 4, "fused_t
           {"peer_overlap": 1}),
          ("peer, overlapped exchange, small tiles", True,
           {"peer_overlap": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),
-         ("peer, x faces stored straight into the neighbours' ghost columns", True, {"peer_xdirect": 1}),
-         ("peer, overlapped exchange, x faces stored straight", True, {"peer_overlap": 1, "peer_xdirect": 1}),
          ("NCCL, interior overlapped with the r/p halo", False, {"overlap_halo": 1}),
          ("NCCL, overlap, small tiles, several boundary units", False,
           {"overlap_halo": 1, "fused_stages": 4, "fused_zc": 4, "fused_tx": 64, "fused_ty": 8}),

@@ -215,6 +215,20 @@ __device__ __forceinline__ void cell_smooth02( const MgLevelDev& L, double omega
 {
     const int i = cu.i, j = cu.j, k = cu.k;
     const long long o = mg_off( L, i, j, k );
+    // Fast path (all but the two outermost layers of the block, i.e. ~98 % of a 512^3 level): neither the cell nor
+    // any of its six neighbours touches a wall, so every D^-1 is minv[0] and every neighbour exists — the same
+    // products and the same row as below, without seven wall counts (this kernel is issue-bound, not HBM-bound:
+    // profiles/r2_launches_mg512.csv)
+    if ( i >= 2 && i < L.n[0] - 2 && j >= 2 && j < L.n[1] - 2 && k >= 2 && k < L.n[2] - 2 )
+    {
+        const double m1 = omega1 * L.minv[0];
+        const double bc = b[o];
+        const double xc = m1 * bc;
+        const double res = bc - apply_row( L.diag[0], L.ns, xc, m1 * b[o - 1], m1 * b[o + 1], m1 * b[o - L.sy], m1 * b[o + L.sy],
+                                           m1 * b[o - L.sz], m1 * b[o + L.sz] );
+        xo[o] = fma( omega2 * L.minv[0], res, xc );
+        return;
+    }
     const int w = mg_walls( L, i, j, k );
     const double bc = b[o];
     const double xc = ( omega1 * L.minv[w] ) * bc;
@@ -338,8 +352,29 @@ __device__ __forceinline__ double cell_prolong_smooth( const MgLevelDev& F, cons
 {
     const int i = cu.i, j = cu.j, k = cu.k;
     const long long o = mg_off( F, i, j, k );
-    const int w = mg_walls( F, i, j, k );
     const int I = i / 2, J = j / 2, K = k / F.cz;
+    // Fast path (cells with all six neighbours inside the block and no wall: every layer but the outermost): the
+    // parents of the neighbours sit at +-1 / +-sy / +-sz from the cell's own parent, chosen by the parity of the
+    // index — one coarse offset instead of seven; the same sums and the same row as below.
+    if ( i >= 1 && i < F.n[0] - 1 && j >= 1 && j < F.n[1] - 1 && k >= 1 && k < F.n[2] - 1 )
+    {
+        const long long oc = mg_off( C, I, J, K );
+        const long long cxm = ( i & 1 ) ? 0 : -1, cxp = ( i & 1 ) ? 1 : 0;
+        const long long cym = ( j & 1 ) ? 0 : -C.sy, cyp = ( j & 1 ) ? C.sy : 0;
+        const long long czm = F.cz == 1 ? -C.sz : ( ( k & 1 ) ? 0 : -C.sz ), czp = F.cz == 1 ? C.sz : ( ( k & 1 ) ? C.sz : 0 );
+        const double xc = xi[o] + ec[oc];
+        const double xm = xi[o - 1] + ec[oc + cxm], xp = xi[o + 1] + ec[oc + cxp];
+        const double ym = xi[o - F.sy] + ec[oc + cym], yp = xi[o + F.sy] + ec[oc + cyp];
+        const double zm = xi[o - F.sz] + ec[oc + czm], zp = xi[o + F.sz] + ec[oc + czp];
+        const double bv = b[o];
+        const double res = bv - apply_row( F.diag[0], F.ns, xc, xm, xp, ym, yp, zm, zp );
+        const double z = fma( omega * F.minv[0], res, xc );
+        xo[o] = z;
+        if ( bv_out )
+            *bv_out = bv;
+        return z;
+    }
+    const int w = mg_walls( F, i, j, k );
     const double xc = xi[o] + ec[mg_off( C, I, J, K )];
     // across a block interface: the ghost entries of x and of the coarse correction (both exchanged)
     const double xm = ( i > 0 || F.nlo[0] ) ? xi[o - 1] + ec[mg_off( C, mg_parent( i - 1, 2 ), J, K )] : 0.0;

@@ -428,7 +428,8 @@ def multi_gpu_extras(args, s, extra, dist, torch, np, rank, world, local, blocks
     if s.stats()["peer_mode"] and not fallback:
         for name, tune in (("peer_exchange_kernel_after_each_phase", {"peer_overlap": 0}),
                            ("peer_overlapped", {"peer_overlap": 1}),
-                           ("nccl_sendrecv_allgather", {"peer_halo": 0})):
+                           ("peer_exchange_kernel_64_byte_form_cg_variant2", {"peer_overlap": 0, "cg_variant": 2}),
+                           ("nccl_sendrecv_allgather", {"cg_variant": args.cg_variant, "peer_halo": 0})):
             try:
                 for k, v in tune.items():
                     s.set_tuning(k, v)
@@ -440,6 +441,7 @@ def multi_gpu_extras(args, s, extra, dist, torch, np, rank, world, local, blocks
             except Exception as e:  # noqa: BLE001
                 sched[name] = {"error": repr(e)[:300]}
         s.set_tuning("peer_halo", 1)
+        s.set_tuning("cg_variant", args.cg_variant)
         s.set_tuning("peer_overlap", int(DEFAULT_PEER_OVERLAP))
         extra["exchange_schedules"] = sched
 
@@ -459,6 +461,7 @@ def multi_gpu_extras(args, s, extra, dist, torch, np, rank, world, local, blocks
                            "value for the speed-up)" % (args.cells, world)}
             for name, tune in (("peer_exchange_kernel_after_each_phase", {"cg_variant": 1, "peer_overlap": 0}),
                                ("peer_overlapped", {"cg_variant": 1, "peer_overlap": 1}),
+                               ("peer_exchange_kernel_64_byte_form_cg_variant2", {"cg_variant": 2, "peer_overlap": 0}),
                                ("single_reduction_cg_variant3", {"cg_variant": 3}),
                                ("nccl_sendrecv_allgather", {"cg_variant": 1, "peer_overlap": 0, "peer_halo": 0})):
                 try:

@@ -6,6 +6,4 @@ mkdir -p "$O"
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node 8"
 timeout 500 $TR --master-port 29651 bench.py --gpus 8 > "$O/bench_n8.json" 2> "$O/bench_n8.err"
 echo "bench rc=$?" >> "$O/summary.txt"
-timeout 120 $TR --master-port 29652 bench.py --impl reference --gpus 8 --steps 3 --warmup 1 > "$O/bench_reference_n8.json" 2> "$O/bench_reference_n8.err"
-echo "reference rc=$?" >> "$O/summary.txt"
 ls -la "$O" > "$O/listing.txt"

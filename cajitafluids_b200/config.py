@@ -74,6 +74,8 @@ class Stats(C.Structure):
         ("ms_k_exch_a", C.c_double),
         ("ms_k_exch_b", C.c_double),
         ("peer_overlap", C.c_int64),
+        ("cg_variant", C.c_int64),
+        ("cg_persist", C.c_int64),
     ]
 
 

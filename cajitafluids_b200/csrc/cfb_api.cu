@@ -322,10 +322,23 @@ void collect_kernel_times( cfb_ctx* c )
 constexpr size_t STATE_HEAD = offsetof( CgState, hist );
 
 // Jacobi-PCG from x0 = 0 on the current RHS.  `fixed_iters` > 0: exactly that many iterations.
+int pcg_solve_form( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid );
+
+// Jacobi-PCG from x0 = 0 on the current RHS in the CG form in force: the one chosen with "cg_variant", or the
+// automatic choice for this block and these options (cg_variant_auto), fixed for the duration of the solve.
 int pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
 {
     if ( c->precond == CFB_PRECOND_MG )
         return mg_pcg_solve( c, fixed_iters, num_iter, resid );
+    const int chosen = c->cg_variant;
+    c->cg_variant = cg_variant_auto( c );
+    const int rc = pcg_solve_form( c, fixed_iters, num_iter, resid );
+    c->cg_variant = chosen;
+    return rc;
+}
+
+int pcg_solve_form( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid )
+{
     if ( c->cg_variant == 3 )
         return cg1_pcg_solve( c, fixed_iters, num_iter, resid ); // opt-in single-reduction form (kernels_cg1.cu)
     const int fixed = fixed_iters > 0;
@@ -1016,8 +1029,16 @@ int cfb_get_stats( const cfb_ctx* c, cfb_stats* out )
     for ( int s = 0; s < PH_COUNT; ++s )
         timer_collect( m, s );
     *out = c->stats;
-    out->peer_mode = cg_peer_mode( c ) ? 1 : 0;
-    out->peer_overlap = peer_overlapped( c ) ? 1 : 0;
+    {
+        // what a solve would run with the options as they are now
+        const int chosen = m->cg_variant;
+        m->cg_variant = cg_variant_auto( c );
+        out->peer_mode = cg_peer_mode( c ) ? 1 : 0;
+        out->peer_overlap = peer_overlapped( c ) ? 1 : 0;
+        out->cg_variant = m->cg_variant;
+        out->cg_persist = cg_persist_applies( c ) ? 1 : 0;
+        m->cg_variant = chosen;
+    }
     return CFB_OK;
 }
 int cfb_reset_stats( cfb_ctx* c )
@@ -1068,7 +1089,7 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     };
     static const Range ranges[] = { { "stencil_variant", 0, 1 }, { "stencil_tx", 64, 128 }, { "stencil_ty", 8, 32 },
                                     { "stencil_stages", 3, 6 },  { "stencil_zc", 0, 1 << 20 }, { "poll_every", 0, 1 << 20 },
-                                    { "cg_variant", 0, 3 },      { "cg_persist", -1, 1 },      { "fused_tx", 64, 128 },   { "fused_ty", 8, 32 },
+                                    { "cg_variant", -1, 3 },      { "cg_persist", -1, 1 },      { "fused_tx", 64, 128 },   { "fused_ty", 8, 32 },
                                     { "fused_stages", 2, 4 },    { "fused_zc", 0, 1 << 20 }, { "rupdate_ctas", 1, 8 } };
     for ( const Range& r : ranges )
         if ( k == r.key && ( value < r.lo || value > r.hi ) )

@@ -162,11 +162,11 @@ struct cfb_ctx
     bool side_busy = false;                         // face transfers enqueued since the last join
 
     // two-kernel CG iteration (kernels_fused.cu): tensor maps of cg_r / cg_p, tiling, unit list
-    // 1 = two kernels / 72 B per cell (default), 0 = three kernels / 88 B, 2 = two kernels / 64 B: q is
+    // 1 = two kernels / 72 B per cell, 0 = three kernels / 88 B, 2 = two kernels / 64 B: q is
     // never stored, phase A' recomputes A p (kernels_stencil.cu MODE 1); 3 = single-reduction (Chronopoulos-Gear)
     // form, opt-in: two kernels / 88 B per cell, ONE reduction point and one ghost exchange per iteration
     // (kernels_cg1.cu; iteration counts within +-1 of the other forms, which are bit-identical to one another)
-    int cg_variant = 1;
+    int cg_variant = -1; // -1: chosen per solve by cg_variant_auto() below
     CUtensorMap tmap_fr{}, tmap_fp[2] = {}; // fused-box maps of cg_r and of cg_pbuf[0 / 1]
     bool fused_ok = false;
     bool fu_auto = true; // pick the tiling from the block size; any "fused_*" tuning key turns it off
@@ -349,9 +349,9 @@ int launch_cg_finish( cfb_ctx* c );
 bool cg_persist_supported( const cfb_ctx* c ); // tile shape instantiated for the persistent kernel
 int launch_cg_persistent( cfb_ctx* c, int iters ); // `iters` iterations in one cooperative launch
 // the persistent form applies: two-kernel form, Jacobi, one block, no per-kernel timing; automatic choice by size
-inline bool cg_persist_applies( const cfb_ctx* c )
+inline bool cg_persist_eligible( const cfb_ctx* c ) // ... apart from the CG form
 {
-    if ( c->cg_variant != 1 || c->cfg.use_nccl || c->time_kernels || c->cg_persist == 0 || !cg_persist_supported( c ) )
+    if ( c->cfg.use_nccl || c->time_kernels || c->cg_persist == 0 || !cg_persist_supported( c ) )
         return false;
     if ( c->cg_persist > 0 )
         return true;
@@ -360,6 +360,21 @@ inline bool cg_persist_applies( const cfb_ctx* c )
     // no gain: there the data movement, not the launch / reduction latency, is what an iteration costs)
     const double cells = (double)c->g.n[0] * c->g.n[1] * c->g.n[2];
     return cells >= 4.0e5 && cells <= 5.0e6;
+}
+inline bool cg_persist_applies( const cfb_ctx* c ) { return c->cg_variant == 1 && cg_persist_eligible( c ); }
+// The CG form a solve runs when none was chosen ("cg_variant" -1, the default).  Forms 0, 1 and 2 produce identical bits,
+// so this is a pure performance choice: the 64-byte form (2) wherever the iteration is bandwidth-bound — measured
+// 638 vs 614 iterations/s at 512^3 on one GPU, 4783 vs 4512 on 8 (profiles/r2_bench_n1_*.json, r2_bench_n8_final.json)
+// — and the 72-byte form (1) where one of its own schedules applies: the persistent single-launch form of small
+// blocks, the overlapped exchange or the staging-area reads when asked for.
+inline int cg_variant_auto( const cfb_ctx* c )
+{
+    if ( c->cg_variant >= 0 )
+        return c->cg_variant;
+    const bool peer = c->cfg.use_nccl && c->peer_ok && c->use_peer;
+    if ( cg_persist_eligible( c ) || ( peer && ( c->peer_overlap || c->peer_xstage_reads ) ) )
+        return 1;
+    return 2;
 }
 // output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
 int output_write( cfb_ctx* c, const char* dir, int time_step );

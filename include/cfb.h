@@ -195,6 +195,10 @@ typedef struct cfb_stats
     double ms_k_exch_b;
     /* 1 = overlapped exchange schedule in use for the CG iterations (see the "peer_overlap" tuning key) */
     int64_t peer_overlap;
+    /* the CG form a solve runs with the options as they are ("cg_variant": the chosen one, or the automatic choice),
+     * and whether batches of its iterations run in the persistent single-launch kernel ("cg_persist") */
+    int64_t cg_variant;
+    int64_t cg_persist;
 } cfb_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------ */
@@ -312,9 +316,10 @@ int cfb_residual_history( const cfb_ctx* ctx, double* hist, int n, int* count );
 /* Tuning hook (unknown keys and out-of-range values return CFB_ERR_INVALID; a tile combination nobody instantiated is
  * refused by the solve that would use it).  No key changes results, except that cg_variant 3 is a different —
  * mathematically equivalent — recurrence (iteration counts within +-1 of the others).  Keys:
- *   cg_variant 1|0|2|3    CG iteration form: two kernels 72 B/cell (default), three kernels 88 B, two kernels 64 B
- *                         (q never stored), 3 = opt-in single-reduction (Chronopoulos-Gear) form: two kernels 88 B,
- *                         ONE reduction point and one ghost exchange per iteration
+ *   cg_variant -1|0|1|2|3 CG iteration form: 1 = two kernels 72 B/cell, 0 = three kernels 88 B, 2 = two kernels 64 B (q never
+ *                         stored); -1 (default) = 2, except 1 where its persistent / overlapped schedules apply (the three
+ *                         produce identical bits); 3 = opt-in single-reduction (Chronopoulos-Gear) form: two kernels
+ *                         88 B, ONE reduction point and one ghost exchange per iteration
  *   stencil_variant, stencil_tx, stencil_ty, stencil_stages, stencil_zc      tiling of the stencil7 + dot kernel
  *   fused_auto, fused_tx, fused_ty, fused_stages, fused_zc, fused_reverse, rupdate_ctas   tiling of the two-kernel form
  *   flat_2d 0|1           2-D runs: do not load the two zero ghost planes in the TMA kernels (default 1 in 2-D)

@@ -363,10 +363,12 @@ inline bool cg_persist_eligible( const cfb_ctx* c ) // ... apart from the CG for
 }
 inline bool cg_persist_applies( const cfb_ctx* c ) { return c->cg_variant == 1 && cg_persist_eligible( c ); }
 // The CG form a solve runs when none was chosen ("cg_variant" -1, the default).  Forms 0, 1 and 2 produce identical bits,
-// so this is a pure performance choice: the 64-byte form (2) wherever the iteration is bandwidth-bound — measured
-// 638 vs 614 iterations/s at 512^3 on one GPU, 4783 vs 4512 on 8 (profiles/r2_bench_n1_*.json, r2_bench_n8_final.json)
-// — and the 72-byte form (1) where one of its own schedules applies: the persistent single-launch form of small
-// blocks, the overlapped exchange or the staging-area reads when asked for.
+// so this is a pure performance choice, made from measurements (profiles/r2_bench_n1_final.json, r2_bench_n8_final.json,
+// r2_small_grids.json): the 64-byte form (2) for three-dimensional blocks of 10^8 cells and more, where the iteration
+// is bandwidth-bound and q's 8 bytes per cell count — 639 vs 618 iterations/s at 512^3 on one GPU, 4783 vs 4512 on 8;
+// the 72-byte form (1) everywhere else: at 256^3 it is 2 % ahead (4502 vs 4418), in two dimensions far ahead (8192^2:
+// 658 vs 462), small blocks run its persistent single-launch form, and the overlapped exchange and the staging-area
+// reads are schedules of this form.
 inline int cg_variant_auto( const cfb_ctx* c )
 {
     if ( c->cg_variant >= 0 )
@@ -374,7 +376,8 @@ inline int cg_variant_auto( const cfb_ctx* c )
     const bool peer = c->cfg.use_nccl && c->peer_ok && c->use_peer;
     if ( cg_persist_eligible( c ) || ( peer && ( c->peer_overlap || c->peer_xstage_reads ) ) )
         return 1;
-    return 2;
+    const double cells = (double)c->g.n[0] * c->g.n[1] * c->g.n[2];
+    return ( c->g.D == 3 && cells >= 1.0e8 ) ? 2 : 1;
 }
 // output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
 int output_write( cfb_ctx* c, const char* dir, int time_step );

@@ -55,10 +55,10 @@ def test_bench_line_carries_the_contract_keys():
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "algorithmic_bytes_per_cell",
               "algorithmic_bytes_per_launch", "avg_launch_ms", "iteration"):
         assert k in r, k
-    # no CG form asked for: the library's choice, which is the 64-byte form here (phase B: 40 B/cell)
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["algorithmic_bytes_per_cell"] == 40
-    assert r["algorithmic_bytes_per_launch"] == 40 * 32 ** 3 and r["iteration"]["bytes_per_cell"] == 64
-    assert "64 B/cell" in d["config"]["cg_form"]
+    # no CG form asked for: the library's choice, which is the 72-byte form at this size (phase B: 48 B/cell)
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["algorithmic_bytes_per_cell"] == 48
+    assert r["algorithmic_bytes_per_launch"] == 48 * 32 ** 3 and r["iteration"]["bytes_per_cell"] == 72
+    assert "72 B/cell" in d["config"]["cg_form"]
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "iterations/s" and "sample" in c
     assert c["timesteps_per_s"]["value"] > 0 and c["timesteps_per_s"]["cells"] == [32, 32, 32]

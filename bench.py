@@ -849,7 +849,7 @@ def main():
                 from cajitafluids_b200.distributed import attach_nccl
                 attach_nccl(cfg_t, dist)
             st_ = Solver(cfg_t)
-            st_.set_tuning("cg_variant", args.cg_variant)
+            st_.set_tuning("cg_variant", args.cg_variant_requested)
             st_.setup()
             st_.step()
             barrier()
@@ -910,7 +910,8 @@ def main():
             c5.cg_fixed_iters = 200
             c5.cg_print_level = 0
             s5 = Solver(c5)
-            s5.set_tuning("cg_variant", args.cg_variant)
+            s5.set_tuning("cg_variant", args.cg_variant_requested)  # (-1: the library's choice at THIS size)
+            v5 = int(s5.stats()["cg_variant"])
             s5.fill_synthetic_velocity(0)
             s5.build_rhs()
             for _ in range(3):
@@ -919,17 +920,17 @@ def main():
             for _ in range(3):
                 m, r5 = s5.pcg_fixed(200)
                 ms5 += m
-            gbs5 = n2 ** 3 * BYTES_ITER[args.cg_variant] * 600 / (ms5 * 1e-3) / 1e9
+            gbs5 = n2 ** 3 * BYTES_ITER[v5] * 600 / (ms5 * 1e-3) / 1e9
             extra["config2_pcg_only"] = {"cells": [n2] * 3, "cg_iters_per_step": 200, "steps": 3,
                                          "iterations_per_s": 600 / (ms5 * 1e-3), "achieved_gbs": gbs5,
-                                         "frac_of_peak": gbs5 / peak, "bytes_per_cell": BYTES_ITER[args.cg_variant],
+                                         "frac_of_peak": gbs5 / peak, "bytes_per_cell": BYTES_ITER[v5], "cg_variant": v5,
                                          "final_residual": r5,
                                          "note": "at 256^3 a vector (134 MB) is about the size of the L2: not an HBM-only number"}
             try:  # ncu DRAM bytes of the two kernels at this size, committed constants like roofline.traffic
                 tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
                 extra["config2_pcg_only"]["ncu_dram_bytes_per_launch"] = {
-                    "cg_fused_kernel": tj.get(f"cg_variant1_dominant_{n2}"), "cg_rupdate_kernel": tj.get(f"cg_variant1_rupdate_{n2}"),
-                    "algorithmic": {"cg_fused_kernel": 48 * n2 ** 3, "cg_rupdate_kernel": 24 * n2 ** 3},
+                    "cg_fused_kernel": tj.get(f"cg_variant{v5}_dominant_{n2}"), "cg_rupdate_kernel": tj.get(f"cg_variant{v5}_rupdate_{n2}"),
+                    "algorithmic": {"cg_fused_kernel": BYTES_DOMINANT[v5] * n2 ** 3, "cg_rupdate_kernel": 24 * n2 ** 3},
                     "source": "profiles/r2_launches_cg%d.csv (ncu, L2 flushed before every launch)" % n2}
             except Exception:  # noqa: BLE001
                 pass

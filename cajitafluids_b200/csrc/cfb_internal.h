@@ -145,6 +145,7 @@ struct cfb_ctx
     bool tmap_ok = false;
     int st_variant = 0; // 0 = TMA z-march (default)
     int st_tx = 64, st_ty = 16, st_stages = 4, st_zc = 64;
+    bool st_zc_auto = true; // shorten the 64-plane chunks of the stencil kernel until every SM has its units ("stencil_zc" turns it off)
     int poll_every = 0; // 0 = auto
     // "flat_2d" tuning key: two-dimensional runs skip the loads of the two zero ghost planes in the TMA kernels
     // (FLAT instantiations).  On for every 2-D context since it was measured (8192^2, 50 fixed iterations:

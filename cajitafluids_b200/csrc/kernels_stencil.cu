@@ -585,7 +585,14 @@ static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullp
     }
     a.tiles_x = ( g.n[0] + tx - 1 ) / tx;
     a.tiles_y = ( g.n[1] + ty - 1 ) / ty;
-    const int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
+    int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
+    if ( c->st_zc_auto )
+    {
+        // 64-plane chunks, halved until the launch has a unit for every resident CTA slot (3 per SM) — blocks of
+        // 256^3 and below would otherwise leave SMs idle; every chunk re-reads two planes, so not below 8
+        while ( zc > 8 && (long long)a.tiles_x * a.tiles_y * ( ( g.n[2] + zc - 1 ) / zc ) < 3ll * c->sm_count )
+            zc /= 2;
+    }
     a.zc = zc;
     // one block per unit, one partial sum per block: the scratch follows the unit count (large cross-sections,
     // e.g. two-dimensional grids beyond 2048^2, have more than CFB_MAX_PARTIALS tiles in a single plane)

@@ -145,7 +145,6 @@ struct cfb_ctx
     bool tmap_ok = false;
     int st_variant = 0; // 0 = TMA z-march (default)
     int st_tx = 64, st_ty = 16, st_stages = 4, st_zc = 64;
-    bool st_zc_auto = true; // shorten the 64-plane chunks of the stencil kernel until every SM has its units ("stencil_zc" turns it off)
     int poll_every = 0; // 0 = auto
     // "flat_2d" tuning key: two-dimensional runs skip the loads of the two zero ghost planes in the TMA kernels
     // (FLAT instantiations).  On for every 2-D context since it was measured (8192^2, 50 fixed iterations:
@@ -365,11 +364,11 @@ inline bool cg_persist_eligible( const cfb_ctx* c ) // ... apart from the CG for
 inline bool cg_persist_applies( const cfb_ctx* c ) { return c->cg_variant == 1 && cg_persist_eligible( c ); }
 // The CG form a solve runs when none was chosen ("cg_variant" -1, the default).  Forms 0, 1 and 2 produce identical bits,
 // so this is a pure performance choice, made from measurements (profiles/r2_bench_n1_final.json, r2_bench_n8_final.json,
-// r2_small_grids.json): the 64-byte form (2) for three-dimensional blocks of 10^8 cells and more, where the iteration
-// is bandwidth-bound and q's 8 bytes per cell count — 639 vs 618 iterations/s at 512^3 on one GPU, 4783 vs 4512 on 8;
-// the 72-byte form (1) everywhere else: at 256^3 it is 2 % ahead (4502 vs 4418), in two dimensions far ahead (8192^2:
-// 658 vs 462), small blocks run its persistent single-launch form, and the overlapped exchange and the staging-area
-// reads are schedules of this form.
+// r2_cg_forms_by_size.json, r2_small_grids.json): the 64-byte form (2) for three-dimensional blocks of 4.5e7 cells and
+// more, where the iteration is bandwidth-bound and q's 8 bytes per cell count — 639 vs 618 iterations/s at 512^3 on one
+// GPU (ratio 1.03 - 1.04), 1.05 at 448^3, 1.12 at 384^3, 4783 vs 4512 on 8 GPUs; the 72-byte form (1) everywhere else:
+// level at 320^3 (0.995), 2 - 5 % ahead at 256^3, in two dimensions far ahead (8192^2: 658 vs 462), small blocks run
+// its persistent single-launch form, and the overlapped exchange and the staging-area reads are schedules of this form.
 inline int cg_variant_auto( const cfb_ctx* c )
 {
     if ( c->cg_variant >= 0 )
@@ -378,7 +377,7 @@ inline int cg_variant_auto( const cfb_ctx* c )
     if ( cg_persist_eligible( c ) || ( peer && ( c->peer_overlap || c->peer_xstage_reads ) ) )
         return 1;
     const double cells = (double)c->g.n[0] * c->g.n[1] * c->g.n[2];
-    return ( c->g.D == 3 && cells >= 1.0e8 ) ? 2 : 1;
+    return ( c->g.D == 3 && cells >= 4.5e7 ) ? 2 : 1;
 }
 // output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
 int output_write( cfb_ctx* c, const char* dir, int time_step );

@@ -585,14 +585,10 @@ static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullp
     }
     a.tiles_x = ( g.n[0] + tx - 1 ) / tx;
     a.tiles_y = ( g.n[1] + ty - 1 ) / ty;
-    int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
-    if ( c->st_zc_auto )
-    {
-        // 64-plane chunks, halved until the launch has a unit for every resident CTA slot (3 per SM) — blocks of
-        // 256^3 and below would otherwise leave SMs idle; every chunk re-reads two planes, so not below 8
-        while ( zc > 8 && (long long)a.tiles_x * a.tiles_y * ( ( g.n[2] + zc - 1 ) / zc ) < 3ll * c->sm_count )
-            zc /= 2;
-    }
+    // (64-plane chunks whatever the block: shortening them until every CTA slot has a unit was measured and loses at
+    // 256^3 — 4262 vs 4418 iterations/s in the 64-byte form, profiles/r2_cg_forms_by_size.json — every chunk re-reads
+    // two planes)
+    const int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
     a.zc = zc;
     // one block per unit, one partial sum per block: the scratch follows the unit count (large cross-sections,
     // e.g. two-dimensional grids beyond 2048^2, have more than CFB_MAX_PARTIALS tiles in a single plane)

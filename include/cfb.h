@@ -317,7 +317,7 @@ int cfb_residual_history( const cfb_ctx* ctx, double* hist, int n, int* count );
  * refused by the solve that would use it).  No key changes results, except that cg_variant 3 is a different —
  * mathematically equivalent — recurrence (iteration counts within +-1 of the others).  Keys:
  *   cg_variant -1|0|1|2|3 CG iteration form: 1 = two kernels 72 B/cell, 0 = three kernels 88 B, 2 = two kernels 64 B (q never
- *                         stored); -1 (default) = 2 for 3-D blocks of >= 1e8 cells, 1 elsewhere (the three produce
+ *                         stored); -1 (default) = 2 for 3-D blocks of >= 4.5e7 cells, 1 elsewhere (the three produce
  *                         identical bits: a choice by measurement); 3 = opt-in single-reduction (Chronopoulos-Gear) form: two kernels
  *                         88 B, ONE reduction point and one ghost exchange per iteration
  *   stencil_variant, stencil_tx, stencil_ty, stencil_stages, stencil_zc      tiling of the stencil7 + dot kernel

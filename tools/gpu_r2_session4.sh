@@ -1,5 +1,6 @@
 #!/bin/bash
 # Round 2, fourth GPU call (1 GPU): the whole GPU suite again, advection occupancy variants + ncu after the remap,
+# (record of what ran: the advect_occ and mg_inorder keys measured here lost and were removed afterwards)
 # multigrid launch order
 set -u
 O=gpurun_out/r2s4

@@ -1,5 +1,6 @@
 #!/bin/bash
 # Round 2, sixth GPU call (2 GPUs): x faces stored straight into the neighbours' ghost columns (peer_xdirect), the new
+# (record of what ran: the peer_xdirect key measured here lost and was removed afterwards)
 # bench extras (multigrid timesteps weak-scaled)
 set -u
 O=gpurun_out/r2s6

@@ -1123,7 +1123,12 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     else if ( k == "stencil_stages" )
         c->st_stages = value;
     else if ( k == "stencil_zc" )
+    {
         c->st_zc = value;
+        c->st_zc_auto = false;
+    }
+    else if ( k == "stencil_rtma" )
+        c->st_rtma = value != 0;
     else if ( k == "poll_every" )
         c->poll_every = value;
     else if ( k == "cg_variant" )

@@ -142,9 +142,14 @@ struct cfb_ctx
     CUtensorMap tmap_p{};
     CUtensorMap tmap_pbuf[2] = {}; // stencil-box maps of cg_pbuf[0 / 1]
     CUtensorMap tmap_sr{};         // stencil-box map of cg_r (single-reduction form: the stencil runs on M^-1 r)
+    CUtensorMap tmap_r1{};         // halo-free tile map of cg_r (phase A' of the 64-byte form with r staged by TMA)
     bool tmap_ok = false;
+    // "stencil_rtma" tuning key: phase A' of the 64-byte form stages r through the TMA ring (1) or streams it with
+    // 128-bit loads one plane ahead (0)
+    bool st_rtma = true;
     int st_variant = 0; // 0 = TMA z-march (default)
     int st_tx = 64, st_ty = 16, st_stages = 4, st_zc = 64;
+    bool st_zc_auto = true; // phase A' picks its own z chunk (stencil_zc_for below) until "stencil_zc" is set
     int poll_every = 0; // 0 = auto
     // "flat_2d" tuning key: two-dimensional runs skip the loads of the two zero ghost planes in the TMA kernels
     // (FLAT instantiations).  On for every 2-D context since it was measured (8192^2, 50 fixed iterations:

@@ -55,6 +55,11 @@ struct TileCfg
     static constexpr int BOX_BYTES = PX * PY * 8;
     static constexpr int STAGE_BYTES = ( BOX_BYTES + 127 ) / 128 * 128;
     static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 128;
+    // phase A' with r staged by TMA as well (RT): every stage carries the TX x TY tile of r behind the box of p
+    static constexpr int R_BYTES = TX * TY * 8;
+    static constexpr int STAGE_RT_BYTES = STAGE_BYTES + R_BYTES;
+    static constexpr int SMEM_RT_BYTES = NS * STAGE_RT_BYTES + 128;
+    static_assert( R_BYTES % 128 == 0, "r tile must keep the stages 128-byte aligned" );
     static_assert( TX % 2 == 0 && NT % LX == 0 && TY % WY == 0 && RY >= 1, "bad tile" );
 };
 
@@ -83,13 +88,31 @@ struct StencilArgs
 // construction and their planes are not loaded.  A template flag: the 3-D instantiations are untouched.
 // PF (MODE 1 and 2): the block that draws the last ticket runs the mailbox reduction of the kernel's sums over NVLink
 // peer memory (device_peer.cuh).
-template <class C, int MODE, bool FLAT, bool PF>
-__global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) )
-    stencil7_dot_tma( const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geo g,
-                      const __grid_constant__ OpConst op, const __grid_constant__ StencilArgs a,
-                      const __grid_constant__ typename PeerSel<PF>::type pf )
+// RT (MODE 1): the TX x TY tile of r of every plane travels through the TMA ring too (second tensor map, same
+// mbarrier as the plane of p it is consumed with) instead of 128-bit loads one plane ahead — the loads then run
+// NS - 1 planes ahead whatever the number of resident warps (ncu of the LDG form at 512^3: long_scoreboard 4.3
+// stalled warps per issue, 79 % of the measured bandwidth; tiles with one or two CTAs per SM fell to 38 %).
+template <class C, int MODE, bool RT>
+constexpr int stencil_smem_bytes()
 {
+    return ( MODE == 1 && RT ) ? C::SMEM_RT_BYTES : C::SMEM_BYTES;
+}
+template <class C, int MODE, bool RT>
+constexpr int stencil_min_ctas()
+{
+    // 228 KB of shared memory per SM, 1 KB reserved per resident CTA
+    return ( MODE == 1 && RT ) ? ( C::SMEM_RT_BYTES <= 75 * 1024 ? 3 : ( C::SMEM_RT_BYTES <= 113 * 1024 ? 2 : 1 ) )
+                               : ( C::SMEM_BYTES <= 56 * 1024 ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) );
+}
+template <class C, int MODE, bool FLAT, bool PF, bool RT = false>
+__global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE, RT>() )
+    stencil7_dot_tma( const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_r,
+                      const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
+                      const __grid_constant__ StencilArgs a, const __grid_constant__ typename PeerSel<PF>::type pf )
+{
+    static_assert( !RT || MODE == 1, "only phase A' stages r" );
     constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
+    constexpr int STAGE = RT ? C::STAGE_RT_BYTES : C::STAGE_BYTES; // bytes per ring slot
     double nalpha = 0.0;
     if ( MODE != 1 )
     {
@@ -138,9 +161,22 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     const int cy = g.h + y0 - 1;
     const int cz = g.h + kbeg - 1;
 
+    // load l = plane kbeg - 1 + l of p into slot l % NS; RT: with it the tile of r of the same plane, which is
+    // consumed in the same iteration (planes kbeg .. kend - 1 only: l = 1 .. nplanes)
+    auto issue = [&]( int l ) {
+        const int s = l % NS;
+        const uint32_t bar = smem_u32( &full_bar[s] );
+        const bool with_r = RT && l >= 1 && l <= nplanes;
+        mbar_expect_tx( bar, C::BOX_BYTES + ( with_r ? C::R_BYTES : 0 ) );
+        tma_load_3d( smem_base + s * STAGE, &tmap, bar, cx, cy, cz + l );
+        if ( with_r )
+            tma_load_3d( smem_base + s * STAGE + C::STAGE_BYTES, &tmap_r, bar, a.hx + x0, g.h + y0, cz + l );
+    };
     if ( tid == 0 )
     {
         prefetch_tmap( &tmap );
+        if ( RT )
+            prefetch_tmap( &tmap_r );
 #pragma unroll
         for ( int s = 0; s < NS; ++s )
             mbar_init( smem_u32( &full_bar[s] ), 1 );
@@ -151,11 +187,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     {
         const int n0 = nloads < NS ? nloads : NS;
         for ( int l = FLAT ? 1 : 0; l < ( FLAT ? 2 : n0 ); ++l )
-        {
-            const uint32_t bar = smem_u32( &full_bar[l % NS] );
-            mbar_expect_tx( bar, C::BOX_BYTES );
-            tma_load_3d( smem_base + ( l % NS ) * C::STAGE_BYTES, &tmap, bar, cx, cy, cz + l );
-        }
+            issue( l );
     }
 
     // per-thread constants: validity and SOLID-wall counts of my cells
@@ -193,8 +225,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     {
         const int row = wy + r * WY + 1;
         zm[r] = FLAT ? make_double2( 0.0, 0.0 ) : *reinterpret_cast<const double2*>( stage0 + row * PX + 2 * lx + 2 );
-        cc[r] = *reinterpret_cast<const double2*>( stage0 + ( 1 % NS ) * ( C::STAGE_BYTES / 8 ) + row * PX +
-                                                   2 * lx + 2 );
+        cc[r] = *reinterpret_cast<const double2*>( stage0 + ( 1 % NS ) * ( STAGE / 8 ) + row * PX + 2 * lx + 2 );
         if ( MODE == 2 )
         {
             // r -> u = M^-1 r of planes kbeg - 1 and kbeg
@@ -210,11 +241,7 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
     // load NS.  From here on slot (it+1) % NS is released at the end of iteration `it`.
     __syncthreads();
     if ( tid == 0 && !FLAT && NS < nloads )
-    {
-        const uint32_t bar = smem_u32( &full_bar[0] );
-        mbar_expect_tx( bar, C::BOX_BYTES );
-        tma_load_3d( smem_base, &tmap, bar, cx, cy, cz + NS );
-    }
+        issue( NS );
 
     dd_t acc = { 0.0, 0.0 }, acc2 = { 0.0, 0.0 }, acc3 = { 0.0, 0.0 }; // MODE 0: p.q | 1: r.r, r.M^-1 r | 2: r.r, r.u, w.u
     double* qrow = ( MODE != 1 ? a.q : a.r ) + geo_off( g, i0, y0 + wy, kbeg );
@@ -236,18 +263,18 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
             }
         }
     };
-    if ( MODE == 1 && nplanes > 0 )
+    if ( MODE == 1 && !RT && nplanes > 0 )
         load_r( rcur, qrow );
     for ( int it = 0; it < nplanes; ++it )
     {
         const int lc = it + 1, ln = it + 2; // load indices of plane k and plane k+1
         const int sc = lc % NS, sn = ln % NS;
-        if ( MODE == 1 && it + 1 < nplanes )
+        if ( MODE == 1 && !RT && it + 1 < nplanes )
             load_r( rnxt, qrow + g.sz );
         if ( !FLAT )
             mbar_wait( smem_u32( &full_bar[sn] ), ( ln / NS ) & 1 );
-        const double* P = stage0 + sc * ( C::STAGE_BYTES / 8 );
-        const double* N = stage0 + sn * ( C::STAGE_BYTES / 8 );
+        const double* P = stage0 + sc * ( STAGE / 8 );
+        const double* N = stage0 + sn * ( STAGE / 8 );
         const int wz = wall_count( g, 2, kbeg + it + g.off[2] );
 #pragma unroll
         for ( int r = 0; r < RY; ++r )
@@ -319,6 +346,8 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
                 {
                     // kernel 1's residual update + kernel 2's reduction (z = M^-1 r is never stored)
                     const int w0 = wx0 + wyc[r] + wz, w1 = wx1 + wyc[r] + wz;
+                    if ( RT ) // my pair of r from the tile behind the box of p (slot sc: its barrier has been waited on)
+                        rcur[r] = *reinterpret_cast<const double2*>( P + C::STAGE_BYTES / 8 + ( row - 1 ) * TX + 2 * lx );
                     if ( vx1 )
                     {
                         double2 rv = rcur[r];
@@ -341,17 +370,13 @@ __global__ void __launch_bounds__( C::NT, ( C::SMEM_BYTES <= 56 * 1024 ) ? 3 : (
             }
             zm[r] = c;
             cc[r] = zp;
-            if ( MODE == 1 )
+            if ( MODE == 1 && !RT )
                 rcur[r] = rnxt[r];
         }
         qrow += g.sz;
         __syncthreads(); // every thread is done with slot sc -> it can be refilled
         if ( tid == 0 && !FLAT && lc + NS < nloads )
-        {
-            const uint32_t bar = smem_u32( &full_bar[sc] );
-            mbar_expect_tx( bar, C::BOX_BYTES );
-            tma_load_3d( smem_base + sc * C::STAGE_BYTES, &tmap, bar, cx, cy, cz + lc + NS );
-        }
+            issue( lc + NS );
     }
 
     if ( MODE == 0 )
@@ -499,22 +524,46 @@ int launch_tma_mode( cfb_ctx* c, const StencilArgs& a, int grid, const PeerFused
         cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
         if constexpr ( MODE != 0 )
             cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        if constexpr ( MODE == 1 )
+        {
+            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_RT_BYTES );
+            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_RT_BYTES );
+            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_RT_BYTES );
+            // three (two) CTAs of the small (medium) tilings fill the SM's shared memory: ask for all of it
+            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared );
+            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared );
+            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared );
+        }
         attr_set = true;
     }
     const NoPeerArgs none{};
     const CUtensorMap& tm = MODE == 2 ? c->tmap_sr : c->tmap_p; // MODE 2 marches over r, the others over p
-    if constexpr ( MODE != 0 )
+    const bool flat = c->g.D == 2 && c->flat_2d;
+    if constexpr ( MODE == 1 )
     {
-        if ( pf ) // (the callers have made sure that flat does not apply)
+        if ( c->st_rtma ) // r through the TMA ring as well
         {
-            stencil7_dot_tma<C, MODE, false, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->g, c->op, a, *pf );
+            if ( pf ) // (the callers have made sure that flat does not apply)
+                stencil7_dot_tma<C, 1, false, true, true><<<grid, C::NT, C::SMEM_RT_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, *pf );
+            else if ( flat )
+                stencil7_dot_tma<C, 1, true, false, true><<<grid, C::NT, C::SMEM_RT_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
+            else
+                stencil7_dot_tma<C, 1, false, false, true><<<grid, C::NT, C::SMEM_RT_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
             return 1;
         }
     }
-    if ( c->g.D == 2 && c->flat_2d )
-        stencil7_dot_tma<C, MODE, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->g, c->op, a, none );
+    if constexpr ( MODE != 0 )
+    {
+        if ( pf )
+        {
+            stencil7_dot_tma<C, MODE, false, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, *pf );
+            return 1;
+        }
+    }
+    if ( flat )
+        stencil7_dot_tma<C, MODE, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
     else
-        stencil7_dot_tma<C, MODE, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->g, c->op, a, none );
+        stencil7_dot_tma<C, MODE, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
     return 1;
 }
 template <class C>
@@ -562,6 +611,15 @@ int stencil_setup( cfb_ctx* c )
         if ( r != CUDA_SUCCESS )
             return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string( (int)r ) );
     }
+    {
+        // phase A' (RT): the tile of r without its halo
+        cuuint32_t box1[3] = { (cuuint32_t)c->st_tx, (cuuint32_t)c->st_ty, 1 };
+        CUresult r = encode( &c->tmap_r1, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->cg_r, gdim, gstride, box1, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+        if ( r != CUDA_SUCCESS )
+            return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string( (int)r ) );
+    }
     c->tmap_p = c->tmap_pbuf[c->pcur];
     c->tmap_ok = true;
     return CFB_OK;
@@ -588,7 +646,17 @@ static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullp
     // (64-plane chunks whatever the block: shortening them until every CTA slot has a unit was measured and loses at
     // 256^3 — 4262 vs 4418 iterations/s in the 64-byte form, profiles/r2_cg_forms_by_size.json — every chunk re-reads
     // two planes)
-    const int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
+    int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
+    // phase A' with r in the TMA ring: 32-plane chunks once they give every CTA slot (3 per SM with the default
+    // tiling) three units or more — the tail of the last wave then costs less than the two extra planes per chunk
+    // (512^3: 539 vs 560 us, 384^3: 242 vs 267 us; 256^3, 1.15 waves of 32-plane chunks: 100 vs 80 us with 64;
+    // profiles/r2_sweep_rtma.log)
+    if ( mode == 1 && c->st_rtma && c->st_zc_auto && g.D == 3 )
+    {
+        const long long u32 = (long long)a.tiles_x * a.tiles_y * ( ( g.n[2] + 31 ) / 32 );
+        if ( u32 >= 9LL * c->sm_count )
+            zc = 32;
+    }
     a.zc = zc;
     // one block per unit, one partial sum per block: the scratch follows the unit count (large cross-sections,
     // e.g. two-dimensional grids beyond 2048^2, have more than CFB_MAX_PARTIALS tiles in a single plane)

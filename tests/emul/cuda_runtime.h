@@ -117,7 +117,8 @@ inline cudaExtent make_cudaExtent( size_t w, size_t h, size_t d ) { return { w, 
 
 enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
 enum { cudaEnableDefault = 0 };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+enum { cudaSharedmemCarveoutMaxShared = 100 };
 cudaError_t cudaGetDriverEntryPoint( const char* name, void** fn, unsigned long long flags,
                                      cudaDriverEntryPointQueryResult* res );
 template <class F>

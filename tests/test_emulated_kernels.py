@@ -308,6 +308,35 @@ def test_emulated_64_byte_iteration_matches_the_oracle(emul, dim, cells, kw):
         assert np.array_equal(g2.residual_history(), o2.residual_history())
 
 
+@pytest.mark.parametrize("dim,cells", [(3, (70, 50, 21)), (3, (130, 36, 9)), (2, (150, 47))])
+def test_emulated_phase_a_prime_tilings_with_and_without_staged_r(emul, dim, cells):
+    """Phase A' of the 64-byte form (kernels_stencil.cu MODE 1) on every stencil tiling, with the tile of r travelling
+    through the TMA ring behind the plane of p ("stencil_rtma" 1, the default) and streamed by 128-bit loads (0):
+    ragged tiles on both axes, z chunks shorter than the ring and longer than the block, 2-D (FLAT)."""
+    if not emul.tma:
+        pytest.skip("the plain-loop stand-ins have no tiles")
+    cfg = make_cfg(dim, cells, box=box_of(cells), fixed_iters=4)
+    g, o = Context(emul, cfg), Oracle(cfg)
+    g.fill_synthetic_velocity(1, 7)
+    for f in fields_of(dim)[1:]:
+        o.set(f, g.get(f))
+    o.build_rhs()
+    ro = o.pcg_solve()
+    po, rr = o.get(K.PRESSURE), o.get(K.CG_R)
+    g.set_tuning("cg_variant", 2)
+    tilings = [(64, 16, 4), (64, 16, 6), (64, 8, 4), (64, 32, 4), (64, 32, 3), (128, 16, 4), (128, 16, 3), (128, 32, 3),
+               (128, 8, 4)]
+    for rtma in (1, 0):
+        g.set_tuning("stencil_rtma", rtma)
+        for tx, ty, st in tilings:
+            for zc in ((2, 64) if dim == 3 else (64,)):
+                for k, v in (("stencil_stages", st), ("stencil_ty", ty), ("stencil_tx", tx), ("stencil_zc", zc)):
+                    g.set_tuning(k, v)
+                g.build_rhs()
+                assert g.pcg_solve() == ro, (rtma, tx, ty, st, zc)
+                assert np.array_equal(g.get(K.PRESSURE), po) and np.array_equal(g.get(K.CG_R), rr), (rtma, tx, ty, st, zc)
+
+
 def test_emulated_bench_tiling_is_what_runs_at_512(emul):
     """A slab with the x / y extents of the benchmark grid takes the tiling rules' 128 x 16 x 3 phase-B tiles and
     the 64 x 16 x 4 stencil tiles: the configuration every headline number was measured with."""

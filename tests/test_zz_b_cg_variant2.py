@@ -69,3 +69,34 @@ def test_cuda_64_byte_iteration_whole_steps():
         assert list(run(g, 3)) == list(run(o, 3))
         for f in ALL(dim):
             assert np.array_equal(g.get(f), o.get(f)), f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells", [(70, 50, 21), (130, 36, 70), (150, 47)])
+def test_cuda_phase_a_prime_tilings_with_and_without_staged_r(cells):
+    """Phase A' on every stencil tiling with the tile of r travelling through the TMA ring ("stencil_rtma" 1, the
+    default) and streamed with 128-bit loads (0): the asynchronous side of the ring — stage reuse, one mbarrier
+    for the two boxes of a slot, chunks shorter and longer than the ring — which the host emulation cannot see."""
+    from cajitafluids_b200 import Solver
+    dim = len(cells)
+    cfg = make_cfg(dim, cells, box=tuple(c / cells[0] for c in cells), fixed_iters=6)
+    g, o = Solver(cfg), Oracle(cfg)
+    g.fill_synthetic_velocity(1, 7)
+    for f in fields_of(dim)[1:]:
+        o.set(f, g.get(f))
+    o.build_rhs()
+    ro = o.pcg_solve()
+    po, rr = o.get(K.PRESSURE), o.get(K.CG_R)
+    g.set_tuning("cg_variant", 2)
+    tilings = [(64, 16, 4), (64, 16, 6), (64, 8, 4), (64, 32, 4), (64, 32, 3), (128, 16, 4), (128, 16, 3), (128, 32, 3),
+               (128, 8, 4)]
+    for rtma in (1, 0):
+        g.set_tuning("stencil_rtma", rtma)
+        for tx, ty, st in tilings:
+            for zc in ((2, 5, 64) if dim == 3 else (64,)):
+                for k, v in (("stencil_stages", st), ("stencil_ty", ty), ("stencil_tx", tx), ("stencil_zc", zc)):
+                    g.set_tuning(k, v)
+                g.build_rhs()
+                assert g.pcg_solve() == ro, (rtma, tx, ty, st, zc)
+                assert np.array_equal(g.get(K.PRESSURE), po) and np.array_equal(g.get(K.CG_R), rr), (rtma, tx, ty, st, zc)
+    g.close()

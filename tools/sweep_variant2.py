@@ -39,9 +39,14 @@ for n in sizes:
               f"resid {res:.6e}", flush=True)
 
     run("variant 1 (72 B)", 1, 72, 24, 48)
-    for tx, ty, st in [(64, 16, 4), (64, 8, 4), (128, 8, 4), (128, 16, 4), (128, 16, 3), (128, 32, 3), (64, 16, 6), (64, 32, 4), (64, 32, 3)]:
-        for zc in ([16, 32, 64, 128] if n >= 256 else [8, 16, 32]):
-            for k, v in (("stencil_stages", st), ("stencil_ty", ty), ("stencil_tx", tx), ("stencil_zc", zc)):
-                s.set_tuning(k, v)
-            run(f"variant 2 (64 B) A' tile={tx}x{ty} st={st} zc={zc}", 2, 64, 24, 40)
+    # phase A' with r streamed by 128-bit loads (the round-2 form) at its shipped tiling, then with r staged by TMA
+    for rtma, tilings in ((0, [(64, 16, 4)]),
+                          (1, [(64, 16, 4), (64, 8, 4), (128, 8, 4), (128, 16, 4), (128, 16, 3), (128, 32, 3), (64, 16, 6),
+                               (64, 32, 4), (64, 32, 3)])):
+        s.set_tuning("stencil_rtma", rtma)
+        for tx, ty, st in tilings:
+            for zc in ([32, 64, 128] if n >= 256 else [8, 16, 32]):
+                for k, v in (("stencil_stages", st), ("stencil_ty", ty), ("stencil_tx", tx), ("stencil_zc", zc)):
+                    s.set_tuning(k, v)
+                run(f"variant 2 (64 B) rtma={rtma} A' tile={tx}x{ty} st={st} zc={zc}", 2, 64, 24, 40)
     s.close()

@@ -1127,8 +1127,6 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->st_zc = value;
         c->st_zc_auto = false;
     }
-    else if ( k == "stencil_rtma" )
-        c->st_rtma = value != 0;
     else if ( k == "poll_every" )
         c->poll_every = value;
     else if ( k == "cg_variant" )
@@ -1146,6 +1144,12 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     }
     else if ( k == "fused_zc" )
         return set_checked( c->fu_zc, fused_setup );
+    else if ( k == "fused_nt" )
+    {
+        if ( value != 256 && value != 512 )
+            return cfb_fail( c, CFB_ERR_INVALID, "tuning key fused_nt: 256 or 512" );
+        c->fu_nt = value;
+    }
     else if ( k == "fused_reverse" )
         c->fu_reverse = value != 0;
     else if ( k == "rupdate_ctas" )

@@ -144,12 +144,9 @@ struct cfb_ctx
     CUtensorMap tmap_sr{};         // stencil-box map of cg_r (single-reduction form: the stencil runs on M^-1 r)
     CUtensorMap tmap_r1{};         // halo-free tile map of cg_r (phase A' of the 64-byte form with r staged by TMA)
     bool tmap_ok = false;
-    // "stencil_rtma" tuning key: phase A' of the 64-byte form stages r through the TMA ring (1) or streams it with
-    // 128-bit loads one plane ahead (0)
-    bool st_rtma = true;
     int st_variant = 0; // 0 = TMA z-march (default)
     int st_tx = 64, st_ty = 16, st_stages = 4, st_zc = 64;
-    bool st_zc_auto = true; // phase A' picks its own z chunk (stencil_zc_for below) until "stencil_zc" is set
+    bool st_zc_auto = true; // phase A' picks its own z chunk (launch_stencil) until "stencil_zc" is set
     int poll_every = 0; // 0 = auto
     // "flat_2d" tuning key: two-dimensional runs skip the loads of the two zero ghost planes in the TMA kernels
     // (FLAT instantiations).  On for every 2-D context since it was measured (8192^2, 50 fixed iterations:
@@ -176,6 +173,7 @@ struct cfb_ctx
     bool fused_ok = false;
     bool fu_auto = true; // pick the tiling from the block size; any "fused_*" tuning key turns it off
     int fu_tx = 64, fu_ty = 16, fu_stages = 3, fu_zc = 64;
+    int fu_nt = 256; // "fused_nt": threads per CTA of phase B (512 exists for the 128 x 16 x 3 tiling only)
     int* d_units = nullptr; // (tile_x, tile_y, chunk) triples: interior units first, then boundary
     int n_units = 0, n_interior = 0;
     // "cg_persist" tuning key: 1 = run batches of iterations of the two-kernel form in ONE cooperative launch
@@ -368,12 +366,13 @@ inline bool cg_persist_eligible( const cfb_ctx* c ) // ... apart from the CG for
 }
 inline bool cg_persist_applies( const cfb_ctx* c ) { return c->cg_variant == 1 && cg_persist_eligible( c ); }
 // The CG form a solve runs when none was chosen ("cg_variant" -1, the default).  Forms 0, 1 and 2 produce identical bits,
-// so this is a pure performance choice, made from measurements (profiles/r2_bench_n1_final.json, r2_bench_n8_final.json,
-// r2_cg_forms_by_size.json, r2_small_grids.json): the 64-byte form (2) for three-dimensional blocks of 4.5e7 cells and
-// more, where the iteration is bandwidth-bound and q's 8 bytes per cell count — 639 vs 618 iterations/s at 512^3 on one
-// GPU (ratio 1.03 - 1.04), 1.05 at 448^3, 1.12 at 384^3, 4783 vs 4512 on 8 GPUs; the 72-byte form (1) everywhere else:
-// level at 320^3 (0.995), 2 - 5 % ahead at 256^3, in two dimensions far ahead (8192^2: 658 vs 462), small blocks run
-// its persistent single-launch form, and the overlapped exchange and the staging-area reads are schedules of this form.
+// so this is a pure performance choice, made from measurements (profiles/r2_sweep_forms2.log, r2_sweep_rtma.log,
+// r2_small_grids.json): the 64-byte form (2) for three-dimensional blocks of 7e6 cells (192^3) and more — since its
+// phase A' stages r by TMA it is ahead at every size measured there: 131 vs 143 us per iteration at 192^3, 191 vs 202 at
+// 224^3, 229 vs 257 at 256^3, 415 vs 471 at 320^3, 652 vs 755 at 384^3, 1014 vs 1136 at 448^3, 1526 vs 1658 at 512^3; the
+// 72-byte form (1) everywhere else: in two dimensions far ahead (8192^2: 1526 vs 1870 us: the one-plane z-march of phase
+// A' has nothing to pipeline), small blocks run its persistent single-launch form, and the overlapped exchange and the
+// staging-area reads are schedules of this form.
 inline int cg_variant_auto( const cfb_ctx* c )
 {
     if ( c->cg_variant >= 0 )
@@ -382,7 +381,7 @@ inline int cg_variant_auto( const cfb_ctx* c )
     if ( cg_persist_eligible( c ) || ( peer && ( c->peer_overlap || c->peer_xstage_reads ) ) )
         return 1;
     const double cells = (double)c->g.n[0] * c->g.n[1] * c->g.n[2];
-    return ( c->g.D == 3 && cells >= 4.5e7 ) ? 2 : 1;
+    return ( c->g.D == 3 && cells >= 7.0e6 ) ? 2 : 1;
 }
 // output.cu: SiloWriter::siloWrite re-designed (extraction kernel + asynchronous copy now, files later)
 int output_write( cfb_ctx* c, const char* dir, int time_step );

@@ -185,11 +185,11 @@ __global__ void cg_finish_kernel( CgState* S )
 
 // ---------------------------------------------------------------------------------------------
 // phase B
-template <int TX_, int TY_, int NS_>
+template <int TX_, int TY_, int NS_, int NT_ = 256>
 struct FusedCfg
 {
     static constexpr int TX = TX_, TY = TY_, NS = NS_;
-    static constexpr int NT = 256;
+    static constexpr int NT = NT_; // (the persistent kernel's phase A assumes 256)
     static constexpr int LX = TX / 2;  // threads along x (one column pair each)
     static constexpr int WY = NT / LX; // thread rows
     static constexpr int RY = TY / WY; // rows per thread
@@ -284,7 +284,7 @@ __device__ __forceinline__ dd_t fused_unit( const CUtensorMap& tmap_r, const CUt
     const int yh_row = ( wy == 0 ) ? 0 : TY + 1;
     const int yh_w = wall_count( g, 1, y0 + yh_row - 1 + g.off[1] );
     // x halo columns: 2 * TY single cells, taken by the lanes of one middle warp
-    constexpr int XH_WARP = ( NT / 32 ) / 2;
+    constexpr int XH_WARP = ( C::NT / 32 ) / 2;
     const bool do_xh = ( tid >> 5 ) == XH_WARP;
     const double ns = op.neg_scale;
 
@@ -915,9 +915,11 @@ int dispatch_fused( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedArg
 {
     if ( !st )
         st = c->stream;
-    const int key = c->fu_tx * 10000 + c->fu_ty * 100 + c->fu_stages;
+    const int key = c->fu_tx * 10000 + c->fu_ty * 100 + c->fu_stages + ( c->fu_nt == 512 ? 100000000 : 0 );
     switch ( key )
     {
+    case 101281603: // "fused_nt" 512: sixteen warps on the one resident CTA
+        return launch_fused_cfg<FusedCfg<128, 16, 3, 512>>( c, a, grid, pf, st );
     case 641603:
         return launch_fused_cfg<FusedCfg<64, 16, 3>>( c, a, grid, pf, st );
     case 641604:

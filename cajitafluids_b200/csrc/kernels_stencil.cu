@@ -18,12 +18,14 @@
 //   * p.q is accumulated per thread over its z-march, reduced with warp shuffles + one smem pass
 //     per CTA, and finalised deterministically by the last CTA (device_reduce.cuh).
 //   * a second variant (LDG, no shared memory) is kept for A/B measurements via cfb_set_tuning.
+//   * phase A' of the 64-byte CG form is this kernel in MODE 1: every ring slot then also carries the tile of r.
 #include "cfb_internal.h"
 #include "device_geo.cuh"
 #include "device_reduce.cuh"
 #include "device_tma.cuh"
 #include "device_peer.cuh"
 #include "device_cg1.cuh"
+#include <algorithm>
 
 namespace
 {
@@ -77,7 +79,7 @@ struct StencilArgs
 // MODE 0: q = A p, sum p.q (CG kernel 4).
 // MODE 1: phase A' of the 64-byte iteration (cg_variant 2): the same march over p, but q = A p is consumed
 //         on the spot instead of being stored: alpha = zr_old / pAp ; r -= alpha (A p) ; sum r^2 ; sum r.M^-1 r
-//         (reads p through TMA and r with 128-bit loads, writes r: 24 B/cell, and phase B no longer writes q).
+//         (reads p and r through TMA, writes r: 24 B/cell, and phase B no longer writes q).
 //         Statement for statement cg_rupdate_kernel with q recomputed by the same row expression that
 //         produced it, hence bit-identical.
 // MODE 2: the stencil kernel of the single-reduction CG (cg_variant 3, kernels_cg1.cu): the planes staged by TMA are
@@ -86,31 +88,33 @@ struct StencilArgs
 //         iteration's only reduction point are taken on the march: sum r^2, sum r.u, sum w.u (16 B/cell).
 // FLAT: two-dimensional runs (one owned plane between two zero ghost planes): the z neighbours are zero by
 // construction and their planes are not loaded.  A template flag: the 3-D instantiations are untouched.
-// PF (MODE 1 and 2): the block that draws the last ticket runs the mailbox reduction of the kernel's sums over NVLink
+// PF (MODE 2): the block that draws the last ticket runs the mailbox reduction of the kernel's sums over NVLink
 // peer memory (device_peer.cuh).
-// RT (MODE 1): the TX x TY tile of r of every plane travels through the TMA ring too (second tensor map, same
-// mbarrier as the plane of p it is consumed with) instead of 128-bit loads one plane ahead — the loads then run
-// NS - 1 planes ahead whatever the number of resident warps (ncu of the LDG form at 512^3: long_scoreboard 4.3
-// stalled warps per issue, 79 % of the measured bandwidth; tiles with one or two CTAs per SM fell to 38 %).
-template <class C, int MODE, bool RT>
+// MODE 1 stages the TX x TY tile of r of every plane through the TMA ring too (second tensor map, same mbarrier as
+// the plane of p it is consumed with): the loads then run NS - 1 planes ahead whatever the number of resident warps.
+// Round 2 streamed r with 128-bit loads one plane ahead: long_scoreboard 4.3 stalled warps per issue, 629 us = 77 %
+// of the measured bandwidth at 512^3 against 528 - 540 us = 91 - 93 % now (profiles/r2_sweep_rtma.log, measured
+// side by side through the "stencil_rtma" key, which went with the loser).
+template <class C, int MODE>
 constexpr int stencil_smem_bytes()
 {
-    return ( MODE == 1 && RT ) ? C::SMEM_RT_BYTES : C::SMEM_BYTES;
+    return MODE == 1 ? C::SMEM_RT_BYTES : C::SMEM_BYTES;
 }
-template <class C, int MODE, bool RT>
+template <class C, int MODE>
 constexpr int stencil_min_ctas()
 {
     // 228 KB of shared memory per SM, 1 KB reserved per resident CTA
-    return ( MODE == 1 && RT ) ? ( C::SMEM_RT_BYTES <= 75 * 1024 ? 3 : ( C::SMEM_RT_BYTES <= 113 * 1024 ? 2 : 1 ) )
-                               : ( C::SMEM_BYTES <= 56 * 1024 ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) );
+    return MODE == 1 ? ( C::SMEM_RT_BYTES <= 75 * 1024 ? 3 : ( C::SMEM_RT_BYTES <= 113 * 1024 ? 2 : 1 ) )
+                     : ( C::SMEM_BYTES <= 56 * 1024 ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) );
 }
-template <class C, int MODE, bool FLAT, bool PF, bool RT = false>
-__global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE, RT>() )
+template <class C, int MODE, bool FLAT, bool PF>
+__global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
     stencil7_dot_tma( const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_r,
                       const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
                       const __grid_constant__ StencilArgs a, const __grid_constant__ typename PeerSel<PF>::type pf )
 {
-    static_assert( !RT || MODE == 1, "only phase A' stages r" );
+    static_assert( !PF || MODE == 2, "only the single-reduction form reduces over the mailboxes from this kernel" );
+    constexpr bool RT = MODE == 1;
     constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
     constexpr int STAGE = RT ? C::STAGE_RT_BYTES : C::STAGE_BYTES; // bytes per ring slot
     double nalpha = 0.0;
@@ -244,33 +248,11 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE, RT>() )
         issue( NS );
 
     dd_t acc = { 0.0, 0.0 }, acc2 = { 0.0, 0.0 }, acc3 = { 0.0, 0.0 }; // MODE 0: p.q | 1: r.r, r.M^-1 r | 2: r.r, r.u, w.u
-    double* qrow = ( MODE != 1 ? a.q : a.r ) + geo_off( g, i0, y0 + wy, kbeg );
-    // MODE 1: r is streamed with 128-bit loads one plane ahead of its use (the loads of plane k + 1 are in
-    // flight while plane k waits for its TMA stage and is computed), like x in phase B
-    double2 rcur[RY], rnxt[RY];
-    auto load_r = [&]( double2* dst, const double* row0 ) {
-#pragma unroll
-        for ( int r = 0; r < RY; ++r )
-        {
-            dst[r] = make_double2( 0.0, 0.0 );
-            if ( vy[r] )
-            {
-                const double* rp = row0 + (long long)( r * WY ) * g.sy;
-                if ( vx1 )
-                    dst[r] = *reinterpret_cast<const double2*>( rp );
-                else if ( vx0 )
-                    dst[r].x = *rp;
-            }
-        }
-    };
-    if ( MODE == 1 && !RT && nplanes > 0 )
-        load_r( rcur, qrow );
+    double* qrow = ( MODE != 1 ? a.q : a.r ) + geo_off( g, i0, y0 + wy, kbeg ); // MODE 1 writes r back in place
     for ( int it = 0; it < nplanes; ++it )
     {
         const int lc = it + 1, ln = it + 2; // load indices of plane k and plane k+1
         const int sc = lc % NS, sn = ln % NS;
-        if ( MODE == 1 && !RT && it + 1 < nplanes )
-            load_r( rnxt, qrow + g.sz );
         if ( !FLAT )
             mbar_wait( smem_u32( &full_bar[sn] ), ( ln / NS ) & 1 );
         const double* P = stage0 + sc * ( STAGE / 8 );
@@ -346,11 +328,11 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE, RT>() )
                 {
                     // kernel 1's residual update + kernel 2's reduction (z = M^-1 r is never stored)
                     const int w0 = wx0 + wyc[r] + wz, w1 = wx1 + wyc[r] + wz;
-                    if ( RT ) // my pair of r from the tile behind the box of p (slot sc: its barrier has been waited on)
-                        rcur[r] = *reinterpret_cast<const double2*>( P + C::STAGE_BYTES / 8 + ( row - 1 ) * TX + 2 * lx );
+                    // my pair of r from the tile behind the box of p (slot sc: its barrier has been waited on)
+                    const double2 rcur = *reinterpret_cast<const double2*>( P + C::STAGE_BYTES / 8 + ( row - 1 ) * TX + 2 * lx );
                     if ( vx1 )
                     {
-                        double2 rv = rcur[r];
+                        double2 rv = rcur;
                         rv.x = fma( nalpha, a0, rv.x );
                         rv.y = fma( nalpha, a1, rv.y );
                         *reinterpret_cast<double2*>( qp ) = rv;
@@ -361,7 +343,7 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE, RT>() )
                     }
                     else if ( vx0 )
                     {
-                        const double rv = fma( nalpha, a0, rcur[r].x );
+                        const double rv = fma( nalpha, a0, rcur.x );
                         *qp = rv;
                         dd_acc( acc, rv * rv );
                         dd_acc( acc2, ( op.minv[w0] * rv ) * rv );
@@ -370,8 +352,6 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE, RT>() )
             }
             zm[r] = c;
             cc[r] = zp;
-            if ( MODE == 1 && !RT )
-                rcur[r] = rnxt[r];
         }
         qrow += g.sz;
         __syncthreads(); // every thread is done with slot sc -> it can be refilled
@@ -432,16 +412,6 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE, RT>() )
                 {
                     S->rr = vals[0].hi + vals[0].lo;
                     S->rz_new = vals[1].hi + vals[1].lo;
-                }
-            }
-            if constexpr ( PF )
-            {
-                dd_t sum[2]; // reduction point 1: (r.z, r.r) from S->loc[2..5]
-                peer_mail_exchange<2>( a.S, pf, 1, 2, sum );
-                if ( tid == 0 )
-                {
-                    a.S->rz_new = sum[0].hi + sum[0].lo;
-                    a.S->rr = sum[1].hi + sum[1].lo;
                 }
             }
         }
@@ -517,53 +487,36 @@ typedef CUresult ( *PFN_encodeTiled )( CUtensorMap*, CUtensorMapDataType, cuuint
 template <class C, int MODE>
 int launch_tma_mode( cfb_ctx* c, const StencilArgs& a, int grid, const PeerFusedArgs* pf )
 {
+    constexpr int SMEM = stencil_smem_bytes<C, MODE>();
     static bool attr_set = false;
     if ( !attr_set )
     {
-        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
-        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
-        if constexpr ( MODE != 0 )
-            cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM );
+        cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM );
+        if constexpr ( MODE == 2 )
+            cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM );
         if constexpr ( MODE == 1 )
         {
-            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_RT_BYTES );
-            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_RT_BYTES );
-            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_RT_BYTES );
             // three (two) CTAs of the small (medium) tilings fill the SM's shared memory: ask for all of it
-            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared );
-            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared );
-            cudaFuncSetAttribute( stencil7_dot_tma<C, 1, false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared );
+            cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared );
+            cudaFuncSetAttribute( stencil7_dot_tma<C, MODE, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared );
         }
         attr_set = true;
     }
     const NoPeerArgs none{};
     const CUtensorMap& tm = MODE == 2 ? c->tmap_sr : c->tmap_p; // MODE 2 marches over r, the others over p
-    const bool flat = c->g.D == 2 && c->flat_2d;
-    if constexpr ( MODE == 1 )
+    if constexpr ( MODE == 2 )
     {
-        if ( c->st_rtma ) // r through the TMA ring as well
+        if ( pf ) // (the callers have made sure that flat does not apply)
         {
-            if ( pf ) // (the callers have made sure that flat does not apply)
-                stencil7_dot_tma<C, 1, false, true, true><<<grid, C::NT, C::SMEM_RT_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, *pf );
-            else if ( flat )
-                stencil7_dot_tma<C, 1, true, false, true><<<grid, C::NT, C::SMEM_RT_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
-            else
-                stencil7_dot_tma<C, 1, false, false, true><<<grid, C::NT, C::SMEM_RT_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
+            stencil7_dot_tma<C, MODE, false, true><<<grid, C::NT, SMEM, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, *pf );
             return 1;
         }
     }
-    if constexpr ( MODE != 0 )
-    {
-        if ( pf )
-        {
-            stencil7_dot_tma<C, MODE, false, true><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, *pf );
-            return 1;
-        }
-    }
-    if ( flat )
-        stencil7_dot_tma<C, MODE, true, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
+    if ( c->g.D == 2 && c->flat_2d )
+        stencil7_dot_tma<C, MODE, true, false><<<grid, C::NT, SMEM, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
     else
-        stencil7_dot_tma<C, MODE, false, false><<<grid, C::NT, C::SMEM_BYTES, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
+        stencil7_dot_tma<C, MODE, false, false><<<grid, C::NT, SMEM, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
     return 1;
 }
 template <class C>
@@ -572,7 +525,7 @@ int launch_tma( cfb_ctx* c, const StencilArgs& a, int grid, int mode, const Peer
     if ( mode == 0 )
         return launch_tma_mode<C, 0>( c, a, grid, nullptr );
     if ( mode == 1 )
-        return launch_tma_mode<C, 1>( c, a, grid, pf );
+        return launch_tma_mode<C, 1>( c, a, grid, nullptr );
     return launch_tma_mode<C, 2>( c, a, grid, pf );
 }
 
@@ -647,15 +600,22 @@ static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullp
     // 256^3 — 4262 vs 4418 iterations/s in the 64-byte form, profiles/r2_cg_forms_by_size.json — every chunk re-reads
     // two planes)
     int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
-    // phase A' with r in the TMA ring: 32-plane chunks once they give every CTA slot (3 per SM with the default
-    // tiling) three units or more — the tail of the last wave then costs less than the two extra planes per chunk
-    // (512^3: 539 vs 560 us, 384^3: 242 vs 267 us; 256^3, 1.15 waves of 32-plane chunks: 100 vs 80 us with 64;
-    // profiles/r2_sweep_rtma.log)
-    if ( mode == 1 && c->st_rtma && c->st_zc_auto && g.D == 3 )
+    // phase A' picks its own chunks unless "stencil_zc" was set (profiles/r2_sweep_forms2.log, 64 x 16 x 4 tiles, three
+    // CTAs per SM): 16-plane chunks once they make three waves or more — many short units keep the tail of the last
+    // wave short (512^3: 529 us against 540 / 570 with 32 / 64 planes; 320^3: 149 against 157 / 175) —, otherwise
+    // ONE wave of at most two units per SM, chunks of equal length (256^3: 4 chunks of 64 planes 81 us, 1.15 waves of
+    // 32-plane chunks 103 us; 192^3: 8 chunks of 24 planes 42.5 us against 56 with 64-plane chunks)
+    if ( mode == 1 && c->st_zc_auto && g.D == 3 )
     {
-        const long long u32 = (long long)a.tiles_x * a.tiles_y * ( ( g.n[2] + 31 ) / 32 );
-        if ( u32 >= 9LL * c->sm_count )
-            zc = 32;
+        const long long tiles = (long long)a.tiles_x * a.tiles_y;
+        if ( tiles * ( ( g.n[2] + 15 ) / 16 ) >= 9LL * c->sm_count )
+            zc = 16;
+        else
+        {
+            long long nch = 2LL * c->sm_count / tiles;
+            nch = std::max( 1LL, std::min( nch, (long long)( g.n[2] + 7 ) / 8 ) );
+            zc = (int)( ( g.n[2] + nch - 1 ) / nch );
+        }
     }
     a.zc = zc;
     // one block per unit, one partial sum per block: the scratch follows the unit count (large cross-sections,

@@ -271,6 +271,14 @@ def test_emulated_tma_tile_configurations(emul):
             g.set_tuning("fused_reverse", rev)
             g.build_rhs()
             assert g.pcg_solve() == ro and np.array_equal(g.get(K.PRESSURE), po), (tx, ty, st, zc, rev)
+    # sixteen warps on the 128 x 16 x 3 tiling ("fused_nt" 512: two rows per thread instead of four)
+    g.set_tuning("fused_reverse", 0)
+    for k, v in (("fused_stages", 3), ("fused_ty", 16), ("fused_tx", 128), ("fused_zc", 3), ("fused_nt", 512)):
+        g.set_tuning(k, v)
+    for variant in (1, 2):
+        g.set_tuning("cg_variant", variant)
+        g.build_rhs()
+        assert g.pcg_solve() == ro and np.array_equal(g.get(K.PRESSURE), po), ("nt 512", variant)
 
 
 @pytest.mark.parametrize("dim,cells,kw", [(3, (70, 50, 21), {}), (2, (33, 47), {}), (3, (130, 36, 5), dict(
@@ -309,10 +317,10 @@ def test_emulated_64_byte_iteration_matches_the_oracle(emul, dim, cells, kw):
 
 
 @pytest.mark.parametrize("dim,cells", [(3, (70, 50, 21)), (3, (130, 36, 9)), (2, (150, 47))])
-def test_emulated_phase_a_prime_tilings_with_and_without_staged_r(emul, dim, cells):
-    """Phase A' of the 64-byte form (kernels_stencil.cu MODE 1) on every stencil tiling, with the tile of r travelling
-    through the TMA ring behind the plane of p ("stencil_rtma" 1, the default) and streamed by 128-bit loads (0):
-    ragged tiles on both axes, z chunks shorter than the ring and longer than the block, 2-D (FLAT)."""
+def test_emulated_phase_a_prime_tilings_with_staged_r(emul, dim, cells):
+    """Phase A' of the 64-byte form (kernels_stencil.cu MODE 1) on every stencil tiling, the tile of r travelling
+    through the TMA ring behind the plane of p: ragged tiles on both axes, z chunks shorter than the ring and longer
+    than the block, the library's own choice of chunk, 2-D (FLAT)."""
     if not emul.tma:
         pytest.skip("the plain-loop stand-ins have no tiles")
     cfg = make_cfg(dim, cells, box=box_of(cells), fixed_iters=4)
@@ -326,8 +334,7 @@ def test_emulated_phase_a_prime_tilings_with_and_without_staged_r(emul, dim, cel
     g.set_tuning("cg_variant", 2)
     tilings = [(64, 16, 4), (64, 16, 6), (64, 8, 4), (64, 32, 4), (64, 32, 3), (128, 16, 4), (128, 16, 3), (128, 32, 3),
                (128, 8, 4)]
-    for rtma in (1, 0):
-        g.set_tuning("stencil_rtma", rtma)
+    for rtma in (1,):  # (the form that streamed r with 128-bit loads was measured against this one and removed)
         for tx, ty, st in tilings:
             for zc in ((2, 64) if dim == 3 else (64,)):
                 for k, v in (("stencil_stages", st), ("stencil_ty", ty), ("stencil_tx", tx), ("stencil_zc", zc)):
@@ -335,6 +342,14 @@ def test_emulated_phase_a_prime_tilings_with_and_without_staged_r(emul, dim, cel
                 g.build_rhs()
                 assert g.pcg_solve() == ro, (rtma, tx, ty, st, zc)
                 assert np.array_equal(g.get(K.PRESSURE), po) and np.array_equal(g.get(K.CG_R), rr), (rtma, tx, ty, st, zc)
+    # a fresh context: the chunk the library picks when "stencil_zc" was never set
+    g2 = Context(emul, cfg)
+    g2.set_tuning("cg_variant", 2)
+    for f in fields_of(dim)[1:]:
+        g2.set(f, o.get(f))
+    g2.build_rhs()
+    assert g2.pcg_solve() == ro
+    assert np.array_equal(g2.get(K.PRESSURE), po) and np.array_equal(g2.get(K.CG_R), rr)
 
 
 def test_emulated_bench_tiling_is_what_runs_at_512(emul):

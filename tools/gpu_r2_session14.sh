@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, session 14: phase A' of the 64-byte form with r staged by TMA ("stencil_rtma") against the LDG form,
+# Round 2, session 14: phase A' of the 64-byte form with r staged by TMA ("stencil_rtma") against the LDG form (the key was removed with that form after this measurement),
 # every stencil tiling, at 512^3 / 384^3 / 256^3 (one GPU, CUDA-event times per phase)
 set -u
 O=gpurun_out/r2s14

@@ -1,4 +1,4 @@
-"""Which CG form and which z chunk of phase A' by block size, with r of phase A' staged by TMA ("stencil_rtma"):
+"""Which CG form and which z chunk of phase A' by block size, with r of phase A' staged by TMA:
 72-byte form against the 64-byte form on one GPU, cubes and two-dimensional grids.
 Usage: python tools/sweep_forms2.py [3:n | 2:n ...]   (CUDA-event times per phase)"""
 import os

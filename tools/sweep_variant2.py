@@ -40,10 +40,9 @@ for n in sizes:
 
     run("variant 1 (72 B)", 1, 72, 24, 48)
     # phase A' with r streamed by 128-bit loads (the round-2 form) at its shipped tiling, then with r staged by TMA
-    for rtma, tilings in ((0, [(64, 16, 4)]),
-                          (1, [(64, 16, 4), (64, 8, 4), (128, 8, 4), (128, 16, 4), (128, 16, 3), (128, 32, 3), (64, 16, 6),
-                               (64, 32, 4), (64, 32, 3)])):
-        s.set_tuning("stencil_rtma", rtma)
+    # ("stencil_rtma" existed for this measurement only — profiles/r2_sweep_rtma.log — and went with the 128-bit-load form)
+    for rtma, tilings in ((1, [(64, 16, 4), (64, 8, 4), (128, 8, 4), (128, 16, 4), (128, 16, 3), (128, 32, 3), (64, 16, 6),
+                               (64, 32, 4), (64, 32, 3)]),):
         for tx, ty, st in tilings:
             for zc in ([32, 64, 128] if n >= 256 else [8, 16, 32]):
                 for k, v in (("stencil_stages", st), ("stencil_ty", ty), ("stencil_tx", tx), ("stencil_zc", zc)):

@@ -1146,8 +1146,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         return set_checked( c->fu_zc, fused_setup );
     else if ( k == "fused_nt" )
     {
-        if ( value != 256 && value != 512 )
-            return cfb_fail( c, CFB_ERR_INVALID, "tuning key fused_nt: 256 or 512" );
+        if ( value != 0 && value != 256 && value != 512 )
+            return cfb_fail( c, CFB_ERR_INVALID, "tuning key fused_nt: 0 (automatic), 256 or 512" );
         c->fu_nt = value;
     }
     else if ( k == "fused_reverse" )

@@ -915,11 +915,33 @@ int dispatch_fused( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedArg
 {
     if ( !st )
         st = c->stream;
-    const int key = c->fu_tx * 10000 + c->fu_ty * 100 + c->fu_stages + ( c->fu_nt == 512 ? 100000000 : 0 );
+    const int key = c->fu_tx * 10000 + c->fu_ty * 100 + c->fu_stages;
+    // "fused_nt": sixteen warps instead of eight on the one CTA an SM holds of the 128 x 16 x 3 tiling (two rows per
+    // thread instead of four).  Measured at 512^3 (profiles/r2_sweep_phase_b.log): without the q store (64-byte form)
+    // 871 - 880 us against 904 - 917, with it (72-byte form) 1122 - 1125 against 1083 - 1084 — so the automatic
+    // choice (0) takes it in the 64-byte form only.  Plain instantiation only: the 64-byte form has no x-staging
+    // reads and no in-kernel mailbox reduction, and two-dimensional runs use the 72-byte form.
+    const bool plain = !pf && !( a.gxr[0] || a.gxr[1] ) && !( c->g.D == 2 && c->flat_2d );
+    if ( c->fu_nt == 512 && !( key == 1281603 && plain ) )
+    {
+        note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "fused_nt 512 exists for the plain 128 x 16 x 3 tiling only" ) );
+        return 0;
+    }
+    if ( key == 1281603 && plain && ( c->fu_nt == 512 || ( c->fu_nt == 0 && !a.store_q ) ) )
+    {
+        using C = FusedCfg<128, 16, 3, 512>;
+        static bool attr_set = false;
+        if ( !attr_set )
+        {
+            cudaFuncSetAttribute( cg_fused_kernel<C, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES );
+            attr_set = true;
+        }
+        const NoPeerArgs none{};
+        cg_fused_kernel<C, false, false, false><<<grid, C::NT, C::SMEM_BYTES, st>>>( c->tmap_fr, c->tmap_fp[c->pcur], c->g, c->op, a, none );
+        return 1;
+    }
     switch ( key )
     {
-    case 101281603: // "fused_nt" 512: sixteen warps on the one resident CTA
-        return launch_fused_cfg<FusedCfg<128, 16, 3, 512>>( c, a, grid, pf, st );
     case 641603:
         return launch_fused_cfg<FusedCfg<64, 16, 3>>( c, a, grid, pf, st );
     case 641604:

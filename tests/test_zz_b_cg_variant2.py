@@ -99,3 +99,26 @@ def test_cuda_phase_a_prime_tilings_with_staged_r(cells):
                 assert g.pcg_solve() == ro, (rtma, tx, ty, st, zc)
                 assert np.array_equal(g.get(K.PRESSURE), po) and np.array_equal(g.get(K.CG_R), rr), (rtma, tx, ty, st, zc)
     g.close()
+
+
+@pytest.mark.gpu
+def test_cuda_phase_b_with_sixteen_warps():
+    """"fused_nt" 512: the 128 x 16 x 3 tiling of phase B with two rows per thread instead of four — same values."""
+    from cajitafluids_b200 import Solver
+    cells = (300, 50, 21)
+    cfg = make_cfg(3, cells, box=tuple(c / cells[0] for c in cells), fixed_iters=6)
+    g, o = Solver(cfg), Oracle(cfg)
+    g.fill_synthetic_velocity(1, 7)
+    for f in fields_of(3)[1:]:
+        o.set(f, g.get(f))
+    o.build_rhs()
+    ro = o.pcg_solve()
+    po = o.get(K.PRESSURE)
+    for k, v in (("fused_stages", 3), ("fused_ty", 16), ("fused_tx", 128), ("fused_zc", 8), ("fused_nt", 512)):
+        g.set_tuning(k, v)
+    for variant in (1, 2):
+        g.set_tuning("cg_variant", variant)
+        g.build_rhs()
+        assert g.pcg_solve() == ro, variant
+        assert np.array_equal(g.get(K.PRESSURE), po), variant
+    g.close()

@@ -7,7 +7,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cajitafluids_b200 import Solver, default_config
 
-sizes = [int(a) for a in sys.argv[1:]] or [192, 256, 320, 384, 448, 512]
+sizes = [int(a) for a in sys.argv[1:]] or [192, 224, 256, 320, 384, 448, 512]
 for n in sizes:
     row = {"cells": n}
     for v in (1, 2):

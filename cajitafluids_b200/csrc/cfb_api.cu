@@ -1144,6 +1144,25 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     }
     else if ( k == "fused_zc" )
         return set_checked( c->fu_zc, fused_setup );
+    else if ( k == "fused_yc" )
+    {
+        if ( value < 1 || value > 4096 )
+            return cfb_fail( c, CFB_ERR_INVALID, "tuning key fused_yc: 1 ... 4096 tile rows per unit" );
+        const bool old_auto = c->fu_yc_auto;
+        const int old = c->fu_yc;
+        c->fu_yc_auto = false;
+        c->fu_yc = value;
+        const int rc = fused_setup( c ); // the unit list follows
+        if ( rc )
+        {
+            const std::string msg = c->err;
+            c->fu_yc_auto = old_auto;
+            c->fu_yc = old;
+            fused_setup( c );
+            return cfb_fail( c, rc, msg );
+        }
+        return CFB_OK;
+    }
     else if ( k == "fused_nt" )
     {
         if ( value != 0 && value != 256 && value != 512 )
@@ -1164,7 +1183,18 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
             CFB_CUDA( c, cudaMemsetAsync( &c->d_state->xerror, 0, sizeof( int ), c->stream ) );
     }
     else if ( k == "flat_2d" )
+    {
+        // the unit list follows the kernels in use (runs of tile rows with the FLAT kernels)
+        const bool old = c->flat_2d;
         c->flat_2d = value != 0;
+        const int rc = fused_setup( c );
+        if ( rc )
+        {
+            c->flat_2d = old;
+            fused_setup( c );
+        }
+        return rc;
+    }
     else if ( k == "advect_tile" )
         c->advect_tile = value != 0;
     else if ( k == "peer_overlap" )

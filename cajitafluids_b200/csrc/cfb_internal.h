@@ -173,6 +173,10 @@ struct cfb_ctx
     bool fused_ok = false;
     bool fu_auto = true; // pick the tiling from the block size; any "fused_*" tuning key turns it off
     int fu_tx = 64, fu_ty = 16, fu_stages = 3, fu_zc = 64;
+    // two-dimensional runs (FLAT kernels): tile rows a unit of phase B marches through along y ("fused_yc"; picked by
+    // fused_setup until the key is set)
+    int fu_yc = 1;
+    bool fu_yc_auto = true;
     int fu_nt = 0; // "fused_nt": threads per CTA of phase B: 256, 512 (128 x 16 x 3 tiling only), 0 = dispatch_fused picks
     int* d_units = nullptr; // (tile_x, tile_y, chunk) triples: interior units first, then boundary
     int n_units = 0, n_interior = 0;

@@ -212,6 +212,7 @@ struct FusedArgs
     double* partials;
     const int* units; // optional unit list (tile_x, tile_y, chunk) triples; nullptr = all units in order
     int tiles_x, tiles_y, zc, hx;
+    int yc;          // two-dimensional runs (FLAT): tile rows a unit marches through along y (fused_unit_flat); else 1
     int reverse;     // walk the units from the top of the block down (see launch_cg_fused)
     // XS kernels (peer mode, x neighbours): the x ghosts of r and of the old p are read from the dense
     // staging areas [k * ny + j] the x neighbours fill over NVLink, [0] low side, [1] high side
@@ -226,7 +227,7 @@ struct FusedArgs
 // and its halo ring, x += alpha p_old, q = A p_new — for the calling block; returns the thread's share of p.q.
 // Shared by the one-unit-per-block kernel (lbase == 0) and by the persistent kernel of the small grids, whose blocks
 // walk through several units with the same shared-memory ring and stage barriers (lbase: loads issued so far).
-template <class C, bool XS, bool FLAT>
+template <class C, bool XS>
 __device__ __forceinline__ dd_t fused_unit( const CUtensorMap& tmap_r, const CUtensorMap& tmap_p, const Geo& g, const OpConst& op,
                                             const FusedArgs& a, const int x0, const int y0, const int kbeg, const int kend,
                                             const double alpha, const double beta, double* stage0, double* pn0,
@@ -262,14 +263,9 @@ __device__ __forceinline__ dd_t fused_unit( const CUtensorMap& tmap_r, const CUt
 
     if ( tid == 0 )
     {
-        if ( FLAT )
-            issue( 1 ); // the one plane there is
-        else
-        {
-            const int n0 = nloads < NS ? nloads : NS;
-            for ( int l = 0; l < n0; ++l )
-                issue( l );
-        }
+        const int n0 = nloads < NS ? nloads : NS;
+        for ( int l = 0; l < n0; ++l )
+            issue( l );
     }
 
     // per-thread constants: SOLID-wall counts of my cells and of my share of the halo ring
@@ -400,21 +396,12 @@ __device__ __forceinline__ dd_t fused_unit( const CUtensorMap& tmap_r, const CUt
     };
 
     // prologue: plane kbeg-1 (z neighbour only), plane kbeg (first owned plane)
-    if ( FLAT )
-    {
-#pragma unroll
-        for ( int r = 0; r < RY; ++r )
-            zm[r] = make_double2( 0.0, 0.0 ); // new p of the ghost plane: fma( beta, 0, minv * 0 )
-    }
-    else
-    {
-        mbar_wait( smem_u32( &full_bar[lbase % NS] ), ( lbase / NS ) & 1 );
-        new_p( 0, zm, false );
-    }
+    mbar_wait( smem_u32( &full_bar[lbase % NS] ), ( lbase / NS ) & 1 );
+    new_p( 0, zm, false );
     mbar_wait( smem_u32( &full_bar[( lbase + 1 ) % NS] ), ( ( lbase + 1 ) / NS ) & 1 );
     new_p( 1, cc, true );
     __syncthreads();
-    if ( tid == 0 && !FLAT )
+    if ( tid == 0 )
     {
         if ( NS < nloads )
             issue( NS );
@@ -426,17 +413,8 @@ __device__ __forceinline__ dd_t fused_unit( const CUtensorMap& tmap_r, const CUt
     for ( int it = 0; it < nplanes; ++it )
     {
         const int l = it + 2; // plane k+1
-        if ( FLAT )
-        {
-#pragma unroll
-            for ( int r = 0; r < RY; ++r )
-                zp[r] = make_double2( 0.0, 0.0 );
-        }
-        else
-        {
-            mbar_wait( smem_u32( &full_bar[( lbase + l ) % NS] ), ( ( lbase + l ) / NS ) & 1 );
-            new_p( l, zp, l <= nplanes );
-        }
+        mbar_wait( smem_u32( &full_bar[( lbase + l ) % NS] ), ( ( lbase + l ) / NS ) & 1 );
+        new_p( l, zp, l <= nplanes );
         // q = A p on plane k = kbeg + it: x/y neighbours from the shared new-p plane of load it+1
         const double* PN = pn0 + ( ( it + 1 ) % C::NPN ) * BOXD;
         const int wz = wall_count( g, 2, kbeg + it + g.off[2] );
@@ -475,10 +453,212 @@ __device__ __forceinline__ dd_t fused_unit( const CUtensorMap& tmap_r, const CUt
         }
         qrow += g.sz;
         __syncthreads(); // stage of load l is consumed, new-p plane of load l is complete
-        if ( tid == 0 && !FLAT && l + NS < nloads )
+        if ( tid == 0 && l + NS < nloads )
             issue( l + NS );
     }
 
+    return acc;
+}
+
+// One unit of phase B of a two-dimensional run (FLAT): there is ONE owned plane, so the march goes along y instead —
+// a unit is a run of `ntile` tiles (x0, y0 + t TY), their boxes of r and p travel through the same shared-memory ring
+// NS - 1 tiles ahead of the one being computed, and the prologue, the reduction and the launch of a block are paid
+// once per run instead of once per tile.  (One tile per block, the round-2 form, sat at 2.7 TB/s whatever the tile
+// shape — profiles/r2_sweep_2d_tilings.log: a block's life was one load latency after the other.)  Every tile
+// recomputes its own halo ring of the new search direction like a 3-D plane does; z neighbours are the zero ghost
+// planes.  Same statements on the same values as the one-tile form: the same bits.
+template <class C, bool XS>
+__device__ __forceinline__ dd_t fused_unit_flat( const CUtensorMap& tmap_r, const CUtensorMap& tmap_p, const Geo& g, const OpConst& op,
+                                                 const FusedArgs& a, const int x0, const int y0, const int ntile,
+                                                 const double alpha, const double beta, double* stage0, double* pn0,
+                                                 unsigned long long* full_bar, const uint32_t smem_base, const int lbase )
+{
+    constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
+    constexpr int BOXD = C::BOX_PAD / 8, STAGED = C::STAGE_BYTES / 8;
+    const int tid = threadIdx.x;
+    const int lx = tid % LX, wy = tid / LX;
+    const int i0 = x0 + 2 * lx;
+    const bool vx0 = i0 < g.n[0], vx1 = i0 + 1 < g.n[0];
+
+    // TMA box origin of tile 0 (array coordinates): 2 columns left of the tile, 1 row below, the owned plane
+    const int cx = a.hx + x0 - 2;
+    const int cy = g.h + y0 - 1;
+    const int cz = g.h;
+    // load t = tile t of the run; running index across the units a persistent block walks through (see fused_unit)
+    auto issue = [&]( int t ) {
+        const int s = ( lbase + t ) % NS;
+        const uint32_t bar = smem_u32( &full_bar[s] );
+        mbar_expect_tx( bar, 2 * C::BOX_BYTES );
+        tma_load_3d( smem_base + s * C::STAGE_BYTES, &tmap_r, bar, cx, cy + t * TY, cz );
+        tma_load_3d( smem_base + s * C::STAGE_BYTES + C::BOX_PAD, &tmap_p, bar, cx, cy + t * TY, cz );
+    };
+    if ( tid == 0 )
+    {
+        const int n0 = ntile < NS ? ntile : NS;
+        for ( int t = 0; t < n0; ++t )
+            issue( t );
+    }
+
+    const int wx0 = wall_count( g, 0, i0 + g.off[0] );
+    const int wx1 = wall_count( g, 0, i0 + 1 + g.off[0] );
+    const int wz = wall_count( g, 2, g.off[2] );
+    const bool do_yh = ( wy == 0 ) || ( wy == WY - 1 );
+    const int yh_row = ( wy == 0 ) ? 0 : TY + 1;
+    constexpr int XH_WARP = ( C::NT / 32 ) / 2;
+    const bool do_xh = ( tid >> 5 ) == XH_WARP;
+    const double ns = op.neg_scale;
+
+    // x of my cells, prefetched one tile ahead
+    double2 xn[RY];
+    double* xrow = a.x + geo_off( g, i0, y0 + wy, 0 );
+    double* prow = a.p + geo_off( g, i0, y0 + wy, 0 );
+    double* qrow = a.q + geo_off( g, i0, y0 + wy, 0 );
+    auto load_x = [&]( const double* xr, int yt ) {
+#pragma unroll
+        for ( int r = 0; r < RY; ++r )
+        {
+            xn[r] = make_double2( 0.0, 0.0 );
+            if ( yt + wy + r * WY < g.n[1] )
+            {
+                const double* xp = xr + (long long)( r * WY ) * g.sy;
+                if ( vx1 )
+                    xn[r] = *reinterpret_cast<const double2*>( xp );
+                else if ( vx0 )
+                    xn[r].x = *xp;
+            }
+        }
+    };
+    load_x( xrow, y0 );
+
+    dd_t acc = { 0.0, 0.0 };
+    for ( int t = 0; t < ntile; ++t )
+    {
+        const int yt = y0 + t * TY;
+        const long long tstep = (long long)TY * g.sy;
+        mbar_wait( smem_u32( &full_bar[( lbase + t ) % NS] ), ( ( lbase + t ) / NS ) & 1 );
+        const double* R = stage0 + ( ( lbase + t ) % NS ) * STAGED;
+        const double* P = R + BOXD;
+        double* PN = pn0 + ( t % C::NPN ) * BOXD;
+        double2 xc[RY], cc[RY];
+        bool vy[RY];
+        int wyc[RY];
+#pragma unroll
+        for ( int r = 0; r < RY; ++r )
+        {
+            xc[r] = xn[r];
+            vy[r] = yt + wy + r * WY < g.n[1];
+            wyc[r] = wall_count( g, 1, yt + wy + r * WY + g.off[1] );
+        }
+        if ( t + 1 < ntile )
+            load_x( xrow + tstep, yt + TY );
+        // new search direction of the tile: my cells (-> registers, shared plane, global; x += alpha p_old) ...
+#pragma unroll
+        for ( int r = 0; r < RY; ++r )
+        {
+            const int o = ( wy + r * WY + 1 ) * PX + 2 * lx + 2;
+            const double2 rv = *reinterpret_cast<const double2*>( R + o );
+            const double2 pv = *reinterpret_cast<const double2*>( P + o );
+            double2 v;
+            v.x = fma( beta, pv.x, op.minv[wx0 + wyc[r] + wz] * rv.x );
+            v.y = fma( beta, pv.y, op.minv[wx1 + wyc[r] + wz] * rv.y );
+            cc[r] = v;
+            *reinterpret_cast<double2*>( PN + o ) = v;
+            if ( vy[r] )
+            {
+                const long long go = (long long)( r * WY ) * g.sy;
+                if ( vx1 )
+                {
+                    *reinterpret_cast<double2*>( prow + go ) = v;
+                    double2 xv = xc[r];
+                    xv.x = fma( alpha, pv.x, xv.x );
+                    xv.y = fma( alpha, pv.y, xv.y );
+                    *reinterpret_cast<double2*>( xrow + go ) = xv;
+                }
+                else if ( vx0 )
+                {
+                    prow[go] = v.x;
+                    xrow[go] = fma( alpha, pv.x, xc[r].x );
+                }
+            }
+        }
+        // ... and my share of its halo ring (shared plane only)
+        if ( do_yh )
+        {
+            const int yh_w = wall_count( g, 1, yt + yh_row - 1 + g.off[1] );
+            const int o = yh_row * PX + 2 * lx + 2;
+            const double2 rv = *reinterpret_cast<const double2*>( R + o );
+            const double2 pv = *reinterpret_cast<const double2*>( P + o );
+            double2 v;
+            v.x = fma( beta, pv.x, op.minv[wx0 + yh_w + wz] * rv.x );
+            v.y = fma( beta, pv.y, op.minv[wx1 + yh_w + wz] * rv.y );
+            *reinterpret_cast<double2*>( PN + o ) = v;
+        }
+        if ( do_xh )
+        {
+            for ( int it = tid & 31; it < 2 * TY; it += 32 )
+            {
+                const int side = it / TY, row = it - side * TY; // side 0: column x0-1, 1: x0+TX
+                const int col = side ? TX + 2 : 1;
+                const int gi = x0 + ( side ? TX : -1 ) + g.off[0];
+                const int cw = wall_count( g, 0, gi ) + wall_count( g, 1, yt + row + g.off[1] ) + wz;
+                const int o = ( row + 1 ) * PX + col;
+                double rv = R[o], pv = P[o];
+                if ( XS )
+                {
+                    const bool ghost = side ? ( x0 + TX == g.n[0] && a.gxr[1] ) : ( x0 == 0 && a.gxr[0] );
+                    if ( ghost && yt + row < g.n[1] )
+                    {
+                        const size_t e = (size_t)( yt + row );
+                        rv = a.gxr[side][e];
+                        pv = a.gxp[side][e];
+                    }
+                }
+                PN[o] = fma( beta, pv, op.minv[cw] * rv );
+            }
+        }
+        __syncthreads(); // the stage of tile t is consumed, its new-p plane is complete
+        if ( tid == 0 && t + NS < ntile )
+            issue( t + NS );
+        // q = A p on the tile: x/y neighbours from the shared new-p plane, z neighbours are the zero ghost planes
+        // (plane t % NPN is written again by tile t + NPN, two block barriers after this one: NPN >= 2 suffices)
+#pragma unroll
+        for ( int r = 0; r < RY; ++r )
+        {
+            const double* pc = PN + ( wy + r * WY + 1 ) * PX + 2 * lx + 2;
+            const double xl = pc[-1];
+            const double xr = pc[2];
+            const double2 ym = *reinterpret_cast<const double2*>( pc - PX );
+            const double2 yp = *reinterpret_cast<const double2*>( pc + PX );
+            const double2 c = cc[r];
+            const double d0 = op.diag[wx0 + wyc[r] + wz];
+            const double d1 = op.diag[wx1 + wyc[r] + wz];
+            const double a0 = apply_row( d0, ns, c.x, xl, c.y, ym.x, yp.x, 0.0, 0.0 );
+            const double a1 = apply_row( d1, ns, c.y, c.x, xr, ym.y, yp.y, 0.0, 0.0 );
+            if ( vy[r] )
+            {
+                double* qp = qrow + (long long)( r * WY ) * g.sy;
+                if ( vx1 )
+                {
+                    if ( a.store_q )
+                        *reinterpret_cast<double2*>( qp ) = make_double2( a0, a1 );
+                    dd_acc( acc, c.x * a0 );
+                    dd_acc( acc, c.y * a1 );
+                }
+                else if ( vx0 )
+                {
+                    if ( a.store_q )
+                        *qp = a0;
+                    dd_acc( acc, c.x * a0 );
+                }
+            }
+        }
+        xrow += tstep;
+        prow += tstep;
+        qrow += tstep;
+    }
+    // a persistent block goes on to its next run: its first tile writes new-p plane 0, which the last tile of a short
+    // run (ntile = 1, 4, ...) may still be reading
+    __syncthreads();
     return acc;
 }
 
@@ -517,18 +697,14 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
         ty = ( u / a.tiles_x ) % a.tiles_y;
         ch = u / ( a.tiles_x * a.tiles_y );
     }
-    const int x0 = tx * TX, y0 = ty * TY;
+    // FLAT: `ty` counts runs of a.yc tile rows (the unit marches along y: fused_unit_flat)
+    const int x0 = tx * TX, y0 = ty * ( FLAT ? a.yc : 1 ) * TY;
+    const int ntile = FLAT ? min( a.yc, ( g.n[1] + TY - 1 ) / TY - ty * a.yc ) : 1;
     const int kbeg = ch * a.zc;
     const int kend = min( kbeg + a.zc, g.n[2] );
-    const int nplanes = kend - kbeg;
-    const int nloads = nplanes + 2; // planes kbeg-1 .. kend
 
     const int i0 = x0 + 2 * lx;
     const bool vx0 = i0 < g.n[0], vx1 = i0 + 1 < g.n[0];
-    bool vy[RY];
-#pragma unroll
-    for ( int r = 0; r < RY; ++r )
-        vy[r] = y0 + wy + r * WY < g.n[1];
 
     // ---- convergence bookkeeping of the iteration (the reference's test after kernel 1) ----------
     const double alpha = S->alpha;
@@ -545,12 +721,14 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
     {
         // x += alpha p of the converged iteration; nothing else (the loop breaks here)
         for ( int k = kbeg; k < kend; ++k )
+          for ( int t = 0; t < ntile; ++t )
 #pragma unroll
             for ( int r = 0; r < RY; ++r )
             {
-                if ( !vy[r] || !vx0 )
+                const int j = y0 + t * TY + wy + r * WY;
+                if ( j >= g.n[1] || !vx0 )
                     continue;
-                const long long o = geo_off( g, i0, y0 + wy + r * WY, k );
+                const long long o = geo_off( g, i0, j, k );
                 if ( vx1 )
                 {
                     const double2 pv = *reinterpret_cast<const double2*>( a.p_old + o );
@@ -582,7 +760,11 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
         fence_barrier_init();
     }
     __syncthreads();
-    dd_t acc = fused_unit<C, XS, FLAT>( tmap_r, tmap_p, g, op, a, x0, y0, kbeg, kend, alpha, beta, stage0, pn0, full_bar, smem_base, 0 );
+    dd_t acc;
+    if constexpr ( FLAT )
+        acc = fused_unit_flat<C, XS>( tmap_r, tmap_p, g, op, a, x0, y0, ntile, alpha, beta, stage0, pn0, full_bar, smem_base, 0 );
+    else
+        acc = fused_unit<C, XS>( tmap_r, tmap_p, g, op, a, x0, y0, kbeg, kend, alpha, beta, stage0, pn0, full_bar, smem_base, 0 );
 
     // p.Ap: block partials at [unit_base + blockIdx.x], the block drawing the last of
     // `units_total` tickets finalises (deterministic: double-double sums, order-independent)
@@ -654,6 +836,7 @@ struct PersistArgs
     double* partials;
     int pstride; // entries per value of the partial-sum scratch: values 0, 1 phase A, value 2 phase B, per BLOCK
     int tiles_x, tiles_y, zc, hx, units_total;
+    int yc; // FLAT: tile rows per unit (see FusedArgs)
     int txp_log2;
     int niters; // iterations of this launch (fewer when the tolerance is met)
 };
@@ -843,11 +1026,23 @@ __global__ void __launch_bounds__( C::NT, C::CTAS )
         {
             const int tx = u % a.tiles_x, ty = ( u / a.tiles_x ) % a.tiles_y, ch = u / ( a.tiles_x * a.tiles_y );
             const int kbeg = ch * a.zc, kend = min( kbeg + a.zc, g.n[2] );
-            const dd_t au = fused_unit<C, false, FLAT>( tmap_r, pc ? tmap_p1 : tmap_p0, g, op, fa, tx * TX, ty * TY, kbeg, kend,
-                                                        alpha, beta, stage0, pn0, full_bar, smem_base, lbase );
+            dd_t au;
+            int nloads;
+            if constexpr ( FLAT )
+            {
+                nloads = min( a.yc, ( g.n[1] + TY - 1 ) / TY - ty * a.yc ); // tiles of the run
+                au = fused_unit_flat<C, false>( tmap_r, pc ? tmap_p1 : tmap_p0, g, op, fa, tx * TX, ty * a.yc * TY, nloads, alpha, beta,
+                                                stage0, pn0, full_bar, smem_base, lbase );
+            }
+            else
+            {
+                nloads = kend - kbeg + 2;
+                au = fused_unit<C, false>( tmap_r, pc ? tmap_p1 : tmap_p0, g, op, fa, tx * TX, ty * TY, kbeg, kend, alpha, beta,
+                                           stage0, pn0, full_bar, smem_base, lbase );
+            }
             acc = dd_add( acc, au );
-            // every load index of the unit was issued and consumed (FLAT: the one plane there is, at index 1)
-            lbase = ( lbase + ( FLAT ? NS : kend - kbeg + 2 ) ) % ( 2 * NS );
+            // every load index of the unit was issued and consumed
+            lbase = ( lbase + nloads ) % ( 2 * NS );
         }
         publish( 2, acc );
         fence_proxy_async_global();
@@ -969,11 +1164,15 @@ int dispatch_fused( cfb_ctx* c, const FusedArgs& a, int grid, const PeerFusedArg
 } // namespace
 
 // Tiling of phase B for the current block: tiles in x/y, z chunk, number of units.
-void fused_tiling( const cfb_ctx* c, int& tiles_x, int& tiles_y, int& zc, int& chunks )
+// Two-dimensional runs with the FLAT kernels: a unit is a run of `yc` tile rows (fused_unit_flat) and `tiles_y`
+// counts runs; everywhere else yc = 1.
+void fused_tiling( const cfb_ctx* c, int& tiles_x, int& tiles_y, int& zc, int& chunks, int& yc )
 {
     const Geo& g = c->g;
     tiles_x = ( g.n[0] + c->fu_tx - 1 ) / c->fu_tx;
     tiles_y = ( g.n[1] + c->fu_ty - 1 ) / c->fu_ty;
+    yc = ( g.D == 2 && c->flat_2d ) ? std::max( 1, std::min( c->fu_yc, tiles_y ) ) : 1;
+    tiles_y = ( tiles_y + yc - 1 ) / yc;
     zc = c->fu_zc > 0 ? c->fu_zc : g.n[2];
     chunks = ( g.n[2] + zc - 1 ) / zc;
 }
@@ -1025,6 +1224,15 @@ int fused_setup( cfb_ctx* c )
         c->fu_stages = st;
         c->fu_zc = zc;
     }
+    if ( c->fu_yc_auto )
+    {
+        // two-dimensional runs: runs of up to 32 tile rows per unit, halved until every SM has two units
+        const long long tiles_x = ( g.n[0] + c->fu_tx - 1 ) / c->fu_tx, tiles_y = ( g.n[1] + c->fu_ty - 1 ) / c->fu_ty;
+        int yc = 32;
+        while ( yc > 1 && tiles_x * ( ( tiles_y + yc - 1 ) / yc ) < 2LL * c->sm_count )
+            yc /= 2;
+        c->fu_yc = yc;
+    }
     cuuint64_t gdim[3] = { (cuuint64_t)g.sy, (cuuint64_t)g.ay, (cuuint64_t)g.az };
     cuuint64_t gstride[2] = { (cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8 };
     cuuint32_t box[3] = { (cuuint32_t)( c->fu_tx + 4 ), (cuuint32_t)( c->fu_ty + 2 ), 1 };
@@ -1041,8 +1249,8 @@ int fused_setup( cfb_ctx* c )
     }
     // unit list: units whose tile touches a face with a neighbour rank (they read exchanged ghosts)
     // go last, so that everything before them can run while the ghosts are in flight
-    int tiles_x, tiles_y, zc, chunks;
-    fused_tiling( c, tiles_x, tiles_y, zc, chunks );
+    int tiles_x, tiles_y, zc, chunks, yc;
+    fused_tiling( c, tiles_x, tiles_y, zc, chunks, yc );
     {
         const int rc = ensure_partials( c, (long long)tiles_x * tiles_y * chunks );
         if ( rc )
@@ -1168,7 +1376,7 @@ int launch_cg_persistent( cfb_ctx* c, int iters )
     a.pstride = c->partials_cap;
     a.hx = 16;
     int chunks;
-    fused_tiling( c, a.tiles_x, a.tiles_y, a.zc, chunks );
+    fused_tiling( c, a.tiles_x, a.tiles_y, a.zc, chunks, a.yc );
     a.units_total = a.tiles_x * a.tiles_y * chunks;
     const int npx = ( g.n[0] + 1 ) / 2;
     a.txp_log2 = 5;
@@ -1206,7 +1414,7 @@ static int launch_cg_fused_impl( cfb_ctx* c, int which, const PeerFusedArgs* pf,
     a.partials = c->d_partials;
     a.hx = 16;
     int chunks;
-    fused_tiling( c, a.tiles_x, a.tiles_y, a.zc, chunks );
+    fused_tiling( c, a.tiles_x, a.tiles_y, a.zc, chunks, a.yc );
     const int total = a.tiles_x * a.tiles_y * chunks;
     a.units_total = total;
     // optional top-down walk (phase A sweeps bottom-up and leaves the top of r in the L2); measured

@@ -352,6 +352,57 @@ def test_emulated_phase_a_prime_tilings_with_staged_r(emul, dim, cells):
     assert np.array_equal(g2.get(K.PRESSURE), po) and np.array_equal(g2.get(K.CG_R), rr)
 
 
+@pytest.mark.parametrize("cells,walls", [((150, 47), None), ((70, 200), [K.FREE, K.SOLID, K.SOLID, K.FREE]), ((33, 16), None)])
+def test_emulated_two_dimensional_units_march_along_y(emul, cells, walls):
+    """Two-dimensional runs: a unit of phase B is a run of "fused_yc" tile rows whose boxes travel through the ring
+    NS - 1 tiles ahead (fused_unit_flat) — every tiling, runs shorter and longer than the ring and than the grid, ragged
+    last tiles, the one-unit-per-block kernel and the persistent kernel (whose blocks carry the ring from run to run),
+    both two-kernel CG forms, and the 3-D kernels on the same grid ("flat_2d" 0)."""
+    if not emul.tma:
+        pytest.skip("the plain-loop stand-ins have no tiles")
+    cfg = make_cfg(2, cells, box=box_of(cells), fixed_iters=5, **(dict(boundary_type=walls) if walls else {}))
+    g, o = Context(emul, cfg), Oracle(cfg)
+    g.fill_synthetic_velocity(1, 3)
+    for f in fields_of(2)[1:]:
+        o.set(f, g.get(f))
+    o.build_rhs()
+    ro = o.pcg_solve()
+    po = o.get(K.PRESSURE)
+
+    def check(tag):
+        g.build_rhs()
+        assert g.pcg_solve() == ro, tag
+        assert np.array_equal(g.get(K.PRESSURE), po), tag
+
+    g.set_tuning("cg_persist", 0)
+    for tx, ty, st in [(64, 16, 3), (64, 8, 4), (128, 16, 3), (64, 32, 2), (128, 8, 3)]:
+        for k, v in (("fused_stages", st), ("fused_ty", ty), ("fused_tx", tx)):
+            g.set_tuning(k, v)
+        for yc in (1, 2, 3, 5, 64):
+            g.set_tuning("fused_yc", yc)
+            for variant in (1, 2):
+                g.set_tuning("cg_variant", variant)
+                check((tx, ty, st, yc, variant))
+    g.set_tuning("cg_variant", 1)
+    for tx, ty, st in [(64, 16, 3), (64, 8, 4)]:
+        for k, v in (("fused_stages", st), ("fused_ty", ty), ("fused_tx", tx), ("cg_persist", 1)):
+            g.set_tuning(k, v)
+        for yc in (1, 2, 4):
+            g.set_tuning("fused_yc", yc)
+            check(("persistent", tx, ty, st, yc))
+    g.set_tuning("cg_persist", 0)
+    g.set_tuning("flat_2d", 0)
+    check("3-D kernels")
+    g.set_tuning("flat_2d", 1)
+    check("back to the FLAT kernels")
+    # a fresh context: the run length the library picks
+    g2 = Context(emul, cfg)
+    for f in fields_of(2)[1:]:
+        g2.set(f, o.get(f))
+    g2.build_rhs()
+    assert g2.pcg_solve() == ro and np.array_equal(g2.get(K.PRESSURE), po)
+
+
 def test_emulated_bench_tiling_is_what_runs_at_512(emul):
     """A slab with the x / y extents of the benchmark grid takes the tiling rules' 128 x 16 x 3 phase-B tiles and
     the 64 x 16 x 4 stencil tiles: the configuration every headline number was measured with."""

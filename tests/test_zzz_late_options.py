@@ -133,3 +133,44 @@ def test_two_dimensional_8192_squared():
             else:
                 assert res == ref[0] and np.array_equal(x, ref[1]), (flat, variant)
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells,walls", [((150, 47), None), ((700, 520), [K.FREE, K.SOLID, K.SOLID, K.FREE]), ((1500, 900), None)])
+def test_cuda_two_dimensional_units_march_along_y(cells, walls):
+    """Two-dimensional runs: a unit of phase B is a run of "fused_yc" tile rows travelling through the TMA ring
+    (fused_unit_flat): stage reuse and barrier parities over runs shorter and longer than the ring, in the
+    one-unit-per-block kernel and in the persistent kernel (ring carried from run to run), against the oracle."""
+    from cajitafluids_b200 import Solver
+    cfg = make_cfg(2, cells, box=box_of(cells), fixed_iters=8, **(dict(boundary_type=walls) if walls else {}))
+    g, o = Solver(cfg), Oracle(cfg)
+    g.fill_synthetic_velocity(1, 3)
+    for f in fields_of(2)[1:]:
+        o.set(f, g.get(f))
+    o.build_rhs()
+    ro = o.pcg_solve()
+    po = o.get(K.PRESSURE)
+
+    def check(tag):
+        g.build_rhs()
+        assert g.pcg_solve() == ro, tag
+        assert np.array_equal(g.get(K.PRESSURE), po), tag
+
+    check("library's choices")
+    g.set_tuning("cg_persist", 0)
+    for tx, ty, st in [(64, 16, 3), (64, 8, 4), (128, 16, 3), (64, 32, 2), (128, 8, 3)]:
+        for k, v in (("fused_stages", st), ("fused_ty", ty), ("fused_tx", tx)):
+            g.set_tuning(k, v)
+        for yc in (1, 2, 3, 7, 64):
+            g.set_tuning("fused_yc", yc)
+            for variant in (1, 2):
+                g.set_tuning("cg_variant", variant)
+                check((tx, ty, st, yc, variant))
+    g.set_tuning("cg_variant", 1)
+    for tx, ty, st in [(64, 16, 3), (64, 8, 4)]:
+        for k, v in (("fused_stages", st), ("fused_ty", ty), ("fused_tx", tx), ("cg_persist", 1)):
+            g.set_tuning(k, v)
+        for yc in (1, 2, 5):
+            g.set_tuning("fused_yc", yc)
+            check(("persistent", tx, ty, st, yc))
+    g.close()

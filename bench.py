@@ -928,10 +928,12 @@ def main():
                                          "note": "at 256^3 a vector (134 MB) is about the size of the L2: not an HBM-only number"}
             try:  # ncu DRAM bytes of the two kernels at this size, committed constants like roofline.traffic
                 tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                ka = "stencil7_dot_tma MODE 1 (phase A')" if v5 == 2 else "cg_rupdate_kernel"
                 extra["config2_pcg_only"]["ncu_dram_bytes_per_launch"] = {
-                    "cg_fused_kernel": tj.get(f"cg_variant{v5}_dominant_{n2}"), "cg_rupdate_kernel": tj.get(f"cg_variant{v5}_rupdate_{n2}"),
-                    "algorithmic": {"cg_fused_kernel": BYTES_DOMINANT[v5] * n2 ** 3, "cg_rupdate_kernel": 24 * n2 ** 3},
-                    "source": "profiles/r2_launches_cg%d.csv (ncu, L2 flushed before every launch)" % n2}
+                    "cg_fused_kernel": tj.get(f"cg_variant{v5}_dominant_{n2}"), ka: tj.get(f"cg_variant{v5}_rupdate_{n2}"),
+                    "algorithmic": {"cg_fused_kernel": BYTES_DOMINANT[v5] * n2 ** 3, ka: 24 * n2 ** 3},
+                    "source": tj.get(f"_source_cg_variant{v5}_{n2}",
+                                     "profiles/r2_launches_cg%d.csv (ncu, L2 flushed before every launch)" % n2)}
             except Exception:  # noqa: BLE001
                 pass
             s5.close()

@@ -1226,12 +1226,25 @@ int fused_setup( cfb_ctx* c )
     }
     if ( c->fu_yc_auto )
     {
-        // two-dimensional runs: runs of up to 32 tile rows per unit, halved until every SM has two units
+        // Two-dimensional runs: the run length that needs the fewest rounds of resident blocks, a run costing its tiles
+        // plus about two for filling the ring.  Matches the measured best at every size (profiles/r2_sweep_2d_march.log,
+        // 128 x 16 x 3 tiles, one block per SM): 8192^2 -> 32 (532 us; 16: 534, 8: 552, 64: 566), 4096^2 -> 64 (143;
+        // 32: 147, 8: 153), 2048^2 -> 16 (47; 8: 49, 32: 65), 1024^2 -> 4 (20; 8: 26, 1: 28).
         const long long tiles_x = ( g.n[0] + c->fu_tx - 1 ) / c->fu_tx, tiles_y = ( g.n[1] + c->fu_ty - 1 ) / c->fu_ty;
-        int yc = 32;
-        while ( yc > 1 && tiles_x * ( ( tiles_y + yc - 1 ) / yc ) < 2LL * c->sm_count )
-            yc /= 2;
-        c->fu_yc = yc;
+        const long long box = ( (long long)( c->fu_tx + 4 ) * ( c->fu_ty + 2 ) * 8 + 127 ) / 128 * 128;
+        const long long smem = ( 2LL * c->fu_stages + 3 ) * box + 128; // FusedCfg::SMEM_BYTES
+        const long long slots = (long long)c->sm_count * ( smem <= 56 * 1024 ? 4 : ( smem <= 75 * 1024 ? 3 : ( smem <= 113 * 1024 ? 2 : 1 ) ) );
+        long long best = -1;
+        for ( int yc = 64; yc >= 1; yc /= 2 )
+        {
+            const long long units = tiles_x * ( ( tiles_y + yc - 1 ) / yc );
+            const long long cost = ( ( units + slots - 1 ) / slots ) * ( std::min<long long>( yc, tiles_y ) + 2 );
+            if ( best < 0 || cost < best )
+            {
+                best = cost;
+                c->fu_yc = yc;
+            }
+        }
     }
     cuuint64_t gdim[3] = { (cuuint64_t)g.sy, (cuuint64_t)g.ay, (cuuint64_t)g.az };
     cuuint64_t gstride[2] = { (cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8 };

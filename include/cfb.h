@@ -317,11 +317,14 @@ int cfb_residual_history( const cfb_ctx* ctx, double* hist, int n, int* count );
  * refused by the solve that would use it).  No key changes results, except that cg_variant 3 is a different —
  * mathematically equivalent — recurrence (iteration counts within +-1 of the others).  Keys:
  *   cg_variant -1|0|1|2|3 CG iteration form: 1 = two kernels 72 B/cell, 0 = three kernels 88 B, 2 = two kernels 64 B (q never
- *                         stored); -1 (default) = 2 for 3-D blocks of >= 4.5e7 cells, 1 elsewhere (the three produce
+ *                         stored); -1 (default) = 2 for 3-D blocks of >= 7e6 cells (192^3), 1 elsewhere (the three produce
  *                         identical bits: a choice by measurement); 3 = opt-in single-reduction (Chronopoulos-Gear) form: two kernels
  *                         88 B, ONE reduction point and one ghost exchange per iteration
- *   stencil_variant, stencil_tx, stencil_ty, stencil_stages, stencil_zc      tiling of the stencil7 + dot kernel
+ *   stencil_variant, stencil_tx, stencil_ty, stencil_stages, stencil_zc      tiling of the stencil7 + dot kernel (and of
+ *                         phase A' of the 64-byte form, which picks its own z chunk until stencil_zc is set)
  *   fused_auto, fused_tx, fused_ty, fused_stages, fused_zc, fused_reverse, rupdate_ctas   tiling of the two-kernel form
+ *   fused_nt 0|256|512    threads per block of phase B (512: the 128 x 16 x 3 tiling only; 0 = 512 in the 64-byte form there)
+ *   fused_yc n            2-D runs: tile rows a unit of phase B marches through along y (default: picked from the grid)
  *   flat_2d 0|1           2-D runs: do not load the two zero ghost planes in the TMA kernels (default 1 in 2-D)
  *   advect_tile 0|1       advection kernel: 32 x 2 x 2 entity tiles per block instead of rows (default 0)
  *   poll_every n          convergence polling interval in iterations (0 = auto)

@@ -1199,6 +1199,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->advect_tile = value != 0;
     else if ( k == "peer_overlap" )
         c->peer_overlap = value != 0;
+    else if ( k == "mg_tma" )
+        c->mg_tma = value != 0;
     else if ( k == "mg_graph" )
         return mg_set_graph( c, value != 0 );
     else if ( k == "mg_coarse_kernel" )

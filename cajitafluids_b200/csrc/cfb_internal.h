@@ -237,6 +237,11 @@ struct cfb_ctx
     // opt-in multigrid preconditioner (mg.cu; cfb_set_preconditioner)
     int precond = CFB_PRECOND_JACOBI;
     int mg_max_levels = 0; // 0 = as many as the block allows
+    // "mg_tma" tuning key: the fine-level smoothing sweeps of three-dimensional runs on the TMA z-march
+    // (kernels_stencil.cu MODE 3 / 4) instead of the one-thread-per-cell kernels
+    bool mg_tma = true;
+    CUtensorMap mg_map_box[3] = {}, mg_map_tile_b{}; // stencil boxes of the fine level's b, x[0], x[1]; tile of b
+    double* mg_map_ptr[3] = { nullptr, nullptr, nullptr };
     bool mg_graph = false; // "mg_graph" tuning key: replay the V-cycle as a CUDA graph (one block)
     bool mg_coarse = false; // "mg_coarse_kernel" tuning key: the coarse end of the cycle in one single-CTA kernel
     MgStage* mg = nullptr;
@@ -343,6 +348,11 @@ int launch_stencil_rupdate( cfb_ctx* c );     // cg_variant 2, phase A': r -= al
 // cg_variant 3: w = A M^-1 r with the three sums of the iteration (init: the launch that starts a solve); mail: the
 // last block runs the mailbox reduction (NVLink peer path)
 int launch_cg1_stencil( cfb_ctx* c, int init, bool mail );
+// multigrid: fine-level sweeps on the TMA march (-1: does not apply, the caller runs its own kernels)
+bool mg_tma_applies( const cfb_ctx* c );
+int mg_tma_prepare( cfb_ctx* c );
+int launch_mg_smooth_tma( cfb_ctx* c, const OpConst& op, double omega, double* b, double* x0, double* x1, int xi_is, int dot );
+int launch_mg_smooth02_tma( cfb_ctx* c, const OpConst& op, double omega1, double omega2, double* b, double* x0, double* x1 );
 // kernels_cg1.cu: p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s
 int launch_cg1_update( cfb_ctx* c );
 int cg1_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid );

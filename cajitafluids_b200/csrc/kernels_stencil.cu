@@ -74,6 +74,10 @@ struct StencilArgs
     int tiles_x, tiles_y, zc, hx;
     int pstride; // entries per value in the partial-sum scratch (cfb_ctx::partials_cap)
     int init;    // MODE 2: the launch that starts a solve (sets alpha, beta; counts no iteration)
+    // MODE 3 / 4 (fine-level smoothing sweeps of the multigrid preconditioner, mg.cu): damping of the sweep(s); the
+    // result goes to `q`; dot != 0: the sweep also leaves sum z.b in S->rz_new (mg_smooth_dot_kernel's job)
+    double om1, om2;
+    int dot;
 };
 
 // MODE 0: q = A p, sum p.q (CG kernel 4).
@@ -86,6 +90,14 @@ struct StencilArgs
 //         those of r; u = M^-1 r is formed on the fly for the centre and its six neighbours (the diagonal is a
 //         function of the cell's wall count, so nothing is stored), w = A u is written, and the THREE sums of the
 //         iteration's only reduction point are taken on the march: sum r^2, sum r.u, sum w.u (16 B/cell).
+// MODE 3: one damped-Jacobi sweep of the multigrid preconditioner on the fine level (mg.cu: cell_smooth): the planes
+//         staged by TMA are those of the iterate xi, every slot also carries the tile of the right-hand side b (as in
+//         MODE 1); xo = xi + (omega D^-1)(b - A xi) is written to `q` (24 B/cell), optionally with sum xo.b.
+// MODE 4: the first TWO sweeps from a zero initial guess in one pass (mg.cu: cell_smooth02): the planes are those of b;
+//         x1 = (omega1 D^-1) b for the centre and its six neighbours (each with its own wall count, as MODE 2 forms
+//         M^-1 r), xo = x1 + (omega2 D^-1)(b - A x1) (16 B/cell).  Statement for statement the one-thread-per-cell
+//         kernels they replace on the fine level — which reached 42 - 50 % of the bandwidth this march reaches —
+//         hence bit-identical.
 // FLAT: two-dimensional runs (one owned plane between two zero ghost planes): the z neighbours are zero by
 // construction and their planes are not loaded.  A template flag: the 3-D instantiations are untouched.
 // PF (MODE 2): the block that draws the last ticket runs the mailbox reduction of the kernel's sums over NVLink
@@ -98,14 +110,14 @@ struct StencilArgs
 template <class C, int MODE>
 constexpr int stencil_smem_bytes()
 {
-    return MODE == 1 ? C::SMEM_RT_BYTES : C::SMEM_BYTES;
+    return ( MODE == 1 || MODE == 3 ) ? C::SMEM_RT_BYTES : C::SMEM_BYTES;
 }
 template <class C, int MODE>
 constexpr int stencil_min_ctas()
 {
     // 228 KB of shared memory per SM, 1 KB reserved per resident CTA
-    return MODE == 1 ? ( C::SMEM_RT_BYTES <= 75 * 1024 ? 3 : ( C::SMEM_RT_BYTES <= 113 * 1024 ? 2 : 1 ) )
-                     : ( C::SMEM_BYTES <= 56 * 1024 ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) );
+    return ( MODE == 1 || MODE == 3 ) ? ( C::SMEM_RT_BYTES <= 75 * 1024 ? 3 : ( C::SMEM_RT_BYTES <= 113 * 1024 ? 2 : 1 ) )
+                                      : ( C::SMEM_BYTES <= 56 * 1024 ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) );
 }
 template <class C, int MODE, bool FLAT, bool PF>
 __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
@@ -114,16 +126,16 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
                       const __grid_constant__ StencilArgs a, const __grid_constant__ typename PeerSel<PF>::type pf )
 {
     static_assert( !PF || MODE == 2, "only the single-reduction form reduces over the mailboxes from this kernel" );
-    constexpr bool RT = MODE == 1;
+    constexpr bool RT = MODE == 1 || MODE == 3; // the slots also carry a halo-free tile (of r / of b)
     constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
     constexpr int STAGE = RT ? C::STAGE_RT_BYTES : C::STAGE_BYTES; // bytes per ring slot
     double nalpha = 0.0;
-    if ( MODE != 1 )
+    if ( MODE == 0 || MODE == 2 )
     {
         if ( a.S->done )
             return;
     }
-    else
+    else if ( MODE == 1 )
     {
         // as in cg_rupdate_kernel: `done` is only ever written here, by cg_check0 and by cg_finish
         CgState* S = a.S;
@@ -220,6 +232,9 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
         wyp[r] = wall_count( g, 1, j + 1 + g.off[1] );
     }
 
+    // MODE 2: M^-1 of a cell with `idx` walls; MODE 4: the first sweep's factor omega1 D^-1 (the product first, as in
+    // mg.cu's cell_smooth02)
+    auto mfac = [&]( int idx ) { return MODE == 4 ? a.om1 * op.minv[idx] : op.minv[idx]; };
     double2 zm[RY], cc[RY];
     if ( !FLAT )
         mbar_wait( smem_u32( &full_bar[0] ), 0 );
@@ -230,14 +245,14 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
         const int row = wy + r * WY + 1;
         zm[r] = FLAT ? make_double2( 0.0, 0.0 ) : *reinterpret_cast<const double2*>( stage0 + row * PX + 2 * lx + 2 );
         cc[r] = *reinterpret_cast<const double2*>( stage0 + ( 1 % NS ) * ( STAGE / 8 ) + row * PX + 2 * lx + 2 );
-        if ( MODE == 2 )
+        if ( MODE == 2 || MODE == 4 )
         {
-            // r -> u = M^-1 r of planes kbeg - 1 and kbeg
+            // r -> u = M^-1 r (MODE 4: b -> x1 = (omega1 D^-1) b) of planes kbeg - 1 and kbeg
             const int wzl = wall_count( g, 2, kbeg - 1 + g.off[2] ), wz0 = wall_count( g, 2, kbeg + g.off[2] );
-            zm[r].x = op.minv[wx0 + wyc[r] + wzl] * zm[r].x;
-            zm[r].y = op.minv[wx1 + wyc[r] + wzl] * zm[r].y;
-            cc[r].x = op.minv[wx0 + wyc[r] + wz0] * cc[r].x;
-            cc[r].y = op.minv[wx1 + wyc[r] + wz0] * cc[r].y;
+            zm[r].x = mfac( wx0 + wyc[r] + wzl ) * zm[r].x;
+            zm[r].y = mfac( wx1 + wyc[r] + wzl ) * zm[r].y;
+            cc[r].x = mfac( wx0 + wyc[r] + wz0 ) * cc[r].x;
+            cc[r].y = mfac( wx1 + wyc[r] + wz0 ) * cc[r].y;
         }
     }
 
@@ -268,18 +283,19 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
             double xr = pc[2];
             double2 ym = *reinterpret_cast<const double2*>( pc - PX );
             double2 yp = *reinterpret_cast<const double2*>( pc + PX );
-            if ( MODE == 2 )
+            if ( MODE == 2 || MODE == 4 )
             {
-                // the staged values are r: u = M^-1 r of every neighbour, each with its own wall count
+                // the staged values are r (b): u = M^-1 r (x1 = omega1 D^-1 b) of every neighbour, each with its own
+                // wall count
                 const int wzn = wall_count( g, 2, kbeg + it + 1 + g.off[2] );
-                zp.x = op.minv[wx0 + wyc[r] + wzn] * zp.x;
-                zp.y = op.minv[wx1 + wyc[r] + wzn] * zp.y;
-                xl = op.minv[wxm + wyc[r] + wz] * xl;
-                xr = op.minv[wxp + wyc[r] + wz] * xr;
-                ym.x = op.minv[wx0 + wym[r] + wz] * ym.x;
-                ym.y = op.minv[wx1 + wym[r] + wz] * ym.y;
-                yp.x = op.minv[wx0 + wyp[r] + wz] * yp.x;
-                yp.y = op.minv[wx1 + wyp[r] + wz] * yp.y;
+                zp.x = mfac( wx0 + wyc[r] + wzn ) * zp.x;
+                zp.y = mfac( wx1 + wyc[r] + wzn ) * zp.y;
+                xl = mfac( wxm + wyc[r] + wz ) * xl;
+                xr = mfac( wxp + wyc[r] + wz ) * xr;
+                ym.x = mfac( wx0 + wym[r] + wz ) * ym.x;
+                ym.y = mfac( wx1 + wym[r] + wz ) * ym.y;
+                yp.x = mfac( wx0 + wyp[r] + wz ) * yp.x;
+                yp.y = mfac( wx1 + wyp[r] + wz ) * yp.y;
             }
             const double2 c = cc[r];
             const double d0 = op.diag[wx0 + wyc[r] + wz];
@@ -323,6 +339,43 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
                         dd_acc( acc2, c.x * rc.x );
                         dd_acc( acc3, c.x * a0 );
                     }
+                }
+                else if ( MODE == 3 )
+                {
+                    // cell_smooth (mg.cu): xo = xi + (omega D^-1)(b - A xi), b from the tile behind the box of xi
+                    const int w0 = wx0 + wyc[r] + wz, w1 = wx1 + wyc[r] + wz;
+                    const double2 bv = *reinterpret_cast<const double2*>( P + C::STAGE_BYTES / 8 + ( row - 1 ) * TX + 2 * lx );
+                    const double z0 = fma( a.om1 * op.minv[w0], bv.x - a0, c.x );
+                    if ( vx1 )
+                    {
+                        const double z1 = fma( a.om1 * op.minv[w1], bv.y - a1, c.y );
+                        *reinterpret_cast<double2*>( qp ) = make_double2( z0, z1 );
+                        if ( a.dot )
+                        {
+                            dd_acc( acc, z0 * bv.x );
+                            dd_acc( acc, z1 * bv.y );
+                        }
+                    }
+                    else if ( vx0 )
+                    {
+                        *qp = z0;
+                        if ( a.dot )
+                            dd_acc( acc, z0 * bv.x );
+                    }
+                }
+                else if ( MODE == 4 )
+                {
+                    // cell_smooth02 (mg.cu): c = x1 of my pair; xo = x1 + (omega2 D^-1)(b - A x1), b from the plane itself
+                    const int w0 = wx0 + wyc[r] + wz, w1 = wx1 + wyc[r] + wz;
+                    const double2 bv = *reinterpret_cast<const double2*>( pc );
+                    const double z0 = fma( a.om2 * op.minv[w0], bv.x - a0, c.x );
+                    if ( vx1 )
+                    {
+                        const double z1 = fma( a.om2 * op.minv[w1], bv.y - a1, c.y );
+                        *reinterpret_cast<double2*>( qp ) = make_double2( z0, z1 );
+                    }
+                    else if ( vx0 )
+                        *qp = z0;
                 }
                 else
                 {
@@ -391,6 +444,30 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
                 cg1_finish( S, vals[0].hi + vals[0].lo, vals[1].hi + vals[1].lo, vals[2].hi + vals[2].lo, a.init );
             // (several ranks over NCCL: cg_global_sum( c, 2 + init ) combines the local sums and finishes)
         }
+    }
+    else if ( MODE == 3 )
+    {
+        if ( a.dot ) // (uniform over the grid) sum z.b -> rz_new, as mg_smooth_dot_kernel / mg_publish leave it
+        {
+            dd_t vals[1] = { acc };
+            if ( block_reduce_finalize<C::NT, 1>( vals, a.partials, a.pstride, &a.S->ticket[1] ) )
+            {
+                if ( tid == 0 )
+                {
+                    CgState* S = a.S;
+                    if ( S->world > 1 )
+                    {
+                        S->loc[0] = vals[0].hi;
+                        S->loc[1] = vals[0].lo;
+                    }
+                    else
+                        S->rz_new = vals[0].hi + vals[0].lo;
+                }
+            }
+        }
+    }
+    else if ( MODE == 4 )
+    {
     }
     else
     {
@@ -531,8 +608,8 @@ int launch_tma( cfb_ctx* c, const StencilArgs& a, int grid, int mode, const Peer
 
 } // namespace
 
-// (Re)build the tensor map of cg_p for the current tile shape.
-int stencil_setup( cfb_ctx* c )
+// One 3-D float64 tensor map over an array in the layout of the CG vectors (Geo): boxes of bx x by x 1 entries.
+static int encode_map( cfb_ctx* c, CUtensorMap* map, double* base, int bx, int by )
 {
     static PFN_encodeTiled encode = nullptr;
     if ( !encode )
@@ -547,35 +624,44 @@ int stencil_setup( cfb_ctx* c )
     const Geo& g = c->g;
     cuuint64_t gdim[3] = { (cuuint64_t)g.sy, (cuuint64_t)g.ay, (cuuint64_t)g.az };
     cuuint64_t gstride[2] = { (cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8 };
-    cuuint32_t box[3] = { (cuuint32_t)( c->st_tx + 4 ), (cuuint32_t)( c->st_ty + 2 ), 1 };
+    cuuint32_t box[3] = { (cuuint32_t)bx, (cuuint32_t)by, 1 };
     cuuint32_t estr[3] = { 1, 1, 1 };
+    CUresult r = encode( map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+    if ( r != CUDA_SUCCESS )
+        return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string( (int)r ) );
+    return CFB_OK;
+}
+
+// (Re)build the tensor maps of the CG vectors for the current tile shape: the stencil box (tile + halo) of both
+// buffers of the search direction and of r (single-reduction form), the halo-free tile of r (phase A').
+int stencil_setup( cfb_ctx* c )
+{
     for ( int b = 0; b < 2; ++b )
-    {
-        CUresult r = encode( &c->tmap_pbuf[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->cg_pbuf[b], gdim, gstride, box,
-                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
-        if ( r != CUDA_SUCCESS )
-            return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string( (int)r ) );
-    }
-    {
-        CUresult r = encode( &c->tmap_sr, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->cg_r, gdim, gstride, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
-        if ( r != CUDA_SUCCESS )
-            return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string( (int)r ) );
-    }
-    {
-        // phase A' (RT): the tile of r without its halo
-        cuuint32_t box1[3] = { (cuuint32_t)c->st_tx, (cuuint32_t)c->st_ty, 1 };
-        CUresult r = encode( &c->tmap_r1, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, c->cg_r, gdim, gstride, box1, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
-        if ( r != CUDA_SUCCESS )
-            return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string( (int)r ) );
-    }
+        if ( int rc = encode_map( c, &c->tmap_pbuf[b], c->cg_pbuf[b], c->st_tx + 4, c->st_ty + 2 ) )
+            return rc;
+    if ( int rc = encode_map( c, &c->tmap_sr, c->cg_r, c->st_tx + 4, c->st_ty + 2 ) )
+        return rc;
+    if ( int rc = encode_map( c, &c->tmap_r1, c->cg_r, c->st_tx, c->st_ty ) )
+        return rc;
     c->tmap_p = c->tmap_pbuf[c->pcur];
     c->tmap_ok = true;
     return CFB_OK;
+}
+
+// z chunk of the marches that run three CTAs per SM on 64 x 16 tiles (phase A', the multigrid sweeps) — measured with
+// phase A' (profiles/r2_sweep_forms2.log): 16-plane chunks once they make three waves or more — many short units keep
+// the tail of the last wave short (512^3: 529 us against 540 / 570 with 32 / 64 planes; 320^3: 149 against 157 / 175)
+// —, otherwise ONE wave of at most two units per SM, chunks of equal length (256^3: 4 chunks of 64 planes 81 us, 1.15
+// waves of 32-plane chunks 103 us; 192^3: 8 chunks of 24 planes 42.5 us against 56 with 64-plane chunks)
+static int march_chunk( const cfb_ctx* c, long long tiles )
+{
+    const Geo& g = c->g;
+    if ( tiles * ( ( g.n[2] + 15 ) / 16 ) >= 9LL * c->sm_count )
+        return 16;
+    long long nch = 2LL * c->sm_count / tiles;
+    nch = std::max( 1LL, std::min( nch, (long long)( g.n[2] + 7 ) / 8 ) );
+    return (int)( ( g.n[2] + nch - 1 ) / nch );
 }
 
 static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullptr, int init = 0 )
@@ -600,23 +686,9 @@ static int launch_stencil( cfb_ctx* c, int mode, const PeerFusedArgs* pf = nullp
     // 256^3 — 4262 vs 4418 iterations/s in the 64-byte form, profiles/r2_cg_forms_by_size.json — every chunk re-reads
     // two planes)
     int zc = c->st_zc > 0 ? c->st_zc : g.n[2];
-    // phase A' picks its own chunks unless "stencil_zc" was set (profiles/r2_sweep_forms2.log, 64 x 16 x 4 tiles, three
-    // CTAs per SM): 16-plane chunks once they make three waves or more — many short units keep the tail of the last
-    // wave short (512^3: 529 us against 540 / 570 with 32 / 64 planes; 320^3: 149 against 157 / 175) —, otherwise
-    // ONE wave of at most two units per SM, chunks of equal length (256^3: 4 chunks of 64 planes 81 us, 1.15 waves of
-    // 32-plane chunks 103 us; 192^3: 8 chunks of 24 planes 42.5 us against 56 with 64-plane chunks)
+    // phase A' picks its own chunks unless "stencil_zc" was set
     if ( mode == 1 && c->st_zc_auto && g.D == 3 )
-    {
-        const long long tiles = (long long)a.tiles_x * a.tiles_y;
-        if ( tiles * ( ( g.n[2] + 15 ) / 16 ) >= 9LL * c->sm_count )
-            zc = 16;
-        else
-        {
-            long long nch = 2LL * c->sm_count / tiles;
-            nch = std::max( 1LL, std::min( nch, (long long)( g.n[2] + 7 ) / 8 ) );
-            zc = (int)( ( g.n[2] + nch - 1 ) / nch );
-        }
-    }
+        zc = march_chunk( c, (long long)a.tiles_x * a.tiles_y );
     a.zc = zc;
     // one block per unit, one partial sum per block: the scratch follows the unit count (large cross-sections,
     // e.g. two-dimensional grids beyond 2048^2, have more than CFB_MAX_PARTIALS tiles in a single plane)
@@ -689,3 +761,108 @@ int launch_cg1_stencil( cfb_ctx* c, int init, bool mail )
 
 // phase A' of the 64-byte iteration (cg_variant 2): r -= alpha (A p) with q recomputed, sum r^2, sum r.M^-1 r
 int launch_stencil_rupdate( cfb_ctx* c ) { return launch_stencil( c, 1 ); }
+
+// ---------------------------------------------------------------------------------------------
+// Fine-level smoothing sweeps of the multigrid preconditioner on the TMA z-march (MODE 3 / 4 above; mg.cu calls these
+// for level 0 of three-dimensional runs, whose arrays live in the layout of the CG vectors).  64 x 16 tiles, four
+// stages, three CTAs per SM, the chunk rule of phase A'.  Returns the number of launches, or -1 when the march does
+// not apply (mg.cu then runs its one-thread-per-cell kernels).
+namespace
+{
+using MgTile = TileCfg<64, 16, 4>;
+
+template <int MODE>
+int launch_mg_mode( cfb_ctx* c, const CUtensorMap& box, const CUtensorMap& tile, const OpConst& op, StencilArgs& a )
+{
+    constexpr int SMEM = stencil_smem_bytes<MgTile, MODE>();
+    static bool attr_set = false;
+    if ( !attr_set )
+    {
+        cudaFuncSetAttribute( stencil7_dot_tma<MgTile, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM );
+        cudaFuncSetAttribute( stencil7_dot_tma<MgTile, MODE, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared );
+        attr_set = true;
+    }
+    const Geo& g = c->g;
+    a.S = c->d_state;
+    a.hx = 16;
+    a.tiles_x = ( g.n[0] + MgTile::TX - 1 ) / MgTile::TX;
+    a.tiles_y = ( g.n[1] + MgTile::TY - 1 ) / MgTile::TY;
+    a.zc = march_chunk( c, (long long)a.tiles_x * a.tiles_y );
+    const long long units = (long long)a.tiles_x * a.tiles_y * ( ( g.n[2] + a.zc - 1 ) / a.zc );
+    // (the scratch was sized by mg_tma_prepare when the hierarchy was built: nothing is allocated here, where a
+    // graph capture may be under way)
+    if ( units > c->partials_cap )
+    {
+        note_rc( c, cfb_fail( c, CFB_ERR_INVALID, "multigrid march: partial-sum scratch not prepared" ) );
+        return 0;
+    }
+    a.partials = c->d_partials;
+    a.pstride = c->partials_cap;
+    stencil7_dot_tma<MgTile, MODE, false, false><<<(int)units, MgTile::NT, SMEM, c->stream>>>( box, tile, g, op, a, NoPeerArgs{} );
+    return 1;
+}
+
+// the tensor maps of the three fine-level arrays a cycle touches, rebuilt when the arrays change (a new hierarchy)
+int mg_maps( cfb_ctx* c, double* b, double* x0, double* x1 )
+{
+    if ( c->mg_map_ptr[0] == b && c->mg_map_ptr[1] == x0 && c->mg_map_ptr[2] == x1 )
+        return CFB_OK;
+    double* base[3] = { b, x0, x1 };
+    for ( int m = 0; m < 3; ++m )
+        if ( int rc = encode_map( c, &c->mg_map_box[m], base[m], MgTile::TX + 4, MgTile::TY + 2 ) )
+            return rc;
+    if ( int rc = encode_map( c, &c->mg_map_tile_b, b, MgTile::TX, MgTile::TY ) )
+        return rc;
+    for ( int m = 0; m < 3; ++m )
+        c->mg_map_ptr[m] = base[m];
+    return CFB_OK;
+}
+} // namespace
+
+// the partial-sum scratch for the march's unit count, before any launch (mg_build)
+int mg_tma_prepare( cfb_ctx* c )
+{
+    if ( !mg_tma_applies( c ) )
+        return CFB_OK;
+    const Geo& g = c->g;
+    const long long tiles = (long long)( ( g.n[0] + MgTile::TX - 1 ) / MgTile::TX ) * ( ( g.n[1] + MgTile::TY - 1 ) / MgTile::TY );
+    const int zc = march_chunk( c, tiles );
+    return ensure_partials( c, tiles * ( ( g.n[2] + zc - 1 ) / zc ) );
+}
+
+bool mg_tma_applies( const cfb_ctx* c )
+{
+    return c->mg_tma && c->g.D == 3 && c->st_variant == 0 && c->g.n[0] >= 16 && c->g.n[1] >= 4;
+}
+
+// xo = xi + (omega D^-1)(b - A xi) on the fine level; dot: also sum xo.b -> rz_new (mg_smooth_kernel / mg_smooth_dot_kernel).
+// b, x0, x1: the level's right-hand side and its two iterate buffers; xi / xo are x0 / x1 in one order or the other.
+int launch_mg_smooth_tma( cfb_ctx* c, const OpConst& op, double omega, double* b, double* x0, double* x1, int xi_is, int dot )
+{
+    if ( !mg_tma_applies( c ) )
+        return -1;
+    if ( note_rc( c, mg_maps( c, b, x0, x1 ) ) )
+        return 0;
+    StencilArgs a{};
+    a.q = xi_is == 0 ? x1 : x0;
+    a.om1 = omega;
+    a.dot = dot;
+    return launch_mg_mode<3>( c, c->mg_map_box[1 + xi_is], c->mg_map_tile_b, op, a );
+}
+
+// the first two sweeps from a zero initial guess in one pass: xo = x1 + (omega2 D^-1)(b - A x1), x1 = (omega1 D^-1) b
+// (mg_smooth02_kernel); the result goes to the level's second buffer
+int launch_mg_smooth02_tma( cfb_ctx* c, const OpConst& op, double omega1, double omega2, double* b, double* x0, double* x1 )
+{
+    if ( !mg_tma_applies( c ) )
+        return -1;
+    if ( note_rc( c, mg_maps( c, b, x0, x1 ) ) )
+        return 0;
+    StencilArgs a{};
+    a.q = x1;
+    a.om1 = omega1;
+    a.om2 = omega2;
+    return launch_mg_mode<4>( c, c->mg_map_box[0], c->mg_map_tile_b, op, a );
+}
+

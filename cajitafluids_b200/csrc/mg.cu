@@ -1006,6 +1006,8 @@ int mg_build( cfb_ctx* c, int nu1, int nu2, int nuc, double omega, int max_level
         if ( rc )
             return rc;
     }
+    if ( int rc = mg_tma_prepare( c ) ) // the partial-sum scratch of the fine level's TMA sweeps
+        return rc;
     m->coarse_start = -1;
     for ( int l = 0; l < (int)m->lv.size(); ++l )
         if ( m->lv[l].cells <= MG_COARSE_CELLS && (int)m->lv.size() - l <= MG_COARSE_LEVELS )
@@ -1119,15 +1121,32 @@ int mg_global_sum( cfb_ctx* c, int what, int* launches )
 
 // the first `sweeps` (>= 1) smoothing sweeps of a level from a zero initial guess; w[s] = damping of sweep s
 // (nullptr: the coarsest level's fixed damping)
+// the level's operator constants in the form the TMA stencil kernels take
+static OpConst level_op( const MgLevelDev& L )
+{
+    OpConst op{};
+    op.neg_scale = L.ns;
+    op.scale = -L.ns;
+    for ( int i = 0; i < 8; ++i )
+    {
+        op.diag[i] = L.diag[i];
+        op.minv[i] = L.minv[i];
+    }
+    return op;
+}
+
 int launch_presmooth( cfb_ctx* c, MgLevelHost& H, int sweeps, const double* w, int* n )
 {
     const int grid = grid_for( c, H.cells );
     const double wc = c->mg->wc;
     int done;
+    const bool fine = &H == &c->mg->lv[0];
     if ( sweeps >= 2 )
     {
         MG_TRY( mg_exchange( c, H, H.b, n ) ); // the fused pair reads b of the six neighbours
-        mg_smooth02_kernel<<<grid, NT, 0, c->stream>>>( H.d, w ? w[0] : wc, w ? w[1] : wc, H.b, H.x[1] );
+        // fine level of a 3-D run: the TMA z-march (kernels_stencil.cu MODE 4), same statements
+        if ( !fine || launch_mg_smooth02_tma( c, level_op( H.d ), w ? w[0] : wc, w ? w[1] : wc, H.b, H.x[0], H.x[1] ) < 0 )
+            mg_smooth02_kernel<<<grid, NT, 0, c->stream>>>( H.d, w ? w[0] : wc, w ? w[1] : wc, H.b, H.x[1] );
         H.cur = 1; // where the unfused pair of sweeps leaves its result
         done = 2;
     }
@@ -1141,7 +1160,8 @@ int launch_presmooth( cfb_ctx* c, MgLevelHost& H, int sweeps, const double* w, i
     for ( ; done < sweeps; ++done )
     {
         MG_TRY( mg_exchange( c, H, H.x[H.cur], n ) );
-        mg_smooth_kernel<<<grid, NT, 0, c->stream>>>( H.d, w ? w[done] : wc, H.b, H.x[H.cur], H.x[1 - H.cur] );
+        if ( !fine || launch_mg_smooth_tma( c, level_op( H.d ), w ? w[done] : wc, H.b, H.x[0], H.x[1], H.cur, 0 ) < 0 )
+            mg_smooth_kernel<<<grid, NT, 0, c->stream>>>( H.d, w ? w[done] : wc, H.b, H.x[H.cur], H.x[1 - H.cur] );
         H.cur = 1 - H.cur;
         *n += 1;
     }
@@ -1220,7 +1240,10 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
     for ( int s = 1; s < m->nu2; ++s )
     {
         MG_TRY( mg_exchange( c, H, H.x[H.cur], n ) );
-        if ( dot && s == m->nu2 - 1 )
+        const bool dot_now = dot && s == m->nu2 - 1;
+        if ( l == 0 && launch_mg_smooth_tma( c, level_op( H.d ), m->wpost[s], H.b, H.x[0], H.x[1], H.cur, dot_now ? 1 : 0 ) >= 0 )
+            ; // fine level of a 3-D run: the TMA z-march (kernels_stencil.cu MODE 3), same statements
+        else if ( dot_now )
             mg_smooth_dot_kernel<<<grid, NT, 0, c->stream>>>( H.d, m->wpost[s], H.b, H.x[H.cur], H.x[1 - H.cur], c->d_state,
                                                              c->d_partials );
         else

@@ -254,6 +254,12 @@ cudaError_t cudaGetDriverEntryPoint( const char* name, void** fn, unsigned long 
 }
 
 #ifndef CFB_EMUL_REAL_TMA
+// the multigrid's fine-level sweeps on the TMA march exist in the "tma" library only: here mg.cu keeps its own kernels
+bool mg_tma_applies( const cfb_ctx* ) { return false; }
+int mg_tma_prepare( cfb_ctx* ) { return CFB_OK; }
+int launch_mg_smooth_tma( cfb_ctx*, const OpConst&, double, double*, double*, double*, int, int ) { return -1; }
+int launch_mg_smooth02_tma( cfb_ctx*, const OpConst&, double, double, double*, double*, double* ) { return -1; }
+
 int stencil_setup( cfb_ctx* c )
 {
     c->tmap_ok = true;

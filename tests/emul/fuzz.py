@@ -56,6 +56,21 @@ def one_case(lib, which, seed):
     g.set_tuning("flat_2d", flat)
     g.set_tuning("advect_tile", tile)
     desc += f" flat_2d={flat} advect_tile={tile}"
+    # round 2, second half: run length of the 2-D march, phase B tiling, persistent kernel, sixteen-warp phase B
+    rng3 = np.random.default_rng(seed + 2000003)
+    yc, tiling, persist = int(rng3.choice([0, 1, 2, 3, 7])), int(rng3.integers(6)), int(rng3.choice([-1, 0, 1]))
+    tilings = [None, (64, 16, 3), (64, 8, 4), (128, 16, 3), (64, 8, 3), (128, 8, 4)]
+    if which == "tma":
+        if tilings[tiling]:
+            for k, v in zip(("fused_tx", "fused_ty", "fused_stages"), tilings[tiling]):
+                g.set_tuning(k, v)
+            if tilings[tiling] == (128, 16, 3) and variant == 2 and not (dim == 2 and flat):
+                g.set_tuning("fused_nt", int(rng3.choice([0, 256, 512])))
+        if yc:
+            g.set_tuning("fused_yc", yc)
+        if tilings[tiling] in (None, (64, 16, 3), (64, 8, 4), (64, 8, 3), (128, 16, 3)):
+            g.set_tuning("cg_persist", persist)
+        desc += f" fused_yc={yc} tiling={tilings[tiling]} cg_persist={persist}"
     if prec == "mg":
         om = 0.0 if nu[0] == nu[1] else 0.7  # unsymmetric cycles: a damping that keeps CG going
         g.set_preconditioner("mg", *nu, om)

@@ -149,6 +149,33 @@ def test_emulated_vcycle_alone_and_parameters(emul):
             assert np.array_equal(g.mg_apply(r), o.mg_apply(r)), (cells, nu)
 
 
+@pytest.mark.parametrize("cells,walls", [((72, 36, 24), None), ((130, 20, 12), [K.SOLID, K.FREE, K.SOLID, K.SOLID, K.FREE, K.SOLID]),
+                                         ((64, 64, 6), None)])
+def test_emulated_multigrid_fine_level_sweeps_on_the_tma_march(emul, cells, walls):
+    """"mg_tma" (default on, 3-D): the fine level's fused pair of pre-smoothing sweeps and its post-smoothing sweeps —
+    with and without the z.r sum — run on the TMA z-march (kernels_stencil.cu MODE 4 / 3) instead of the
+    one-thread-per-cell kernels: ragged tiles, several chunks, walls of both kinds, every sweep-count combination."""
+    if not emul.tma:
+        pytest.skip("the march exists in the TMA library only")
+    cfg = make_cfg(3, cells, box=box_of(cells), **(dict(boundary_type=walls) if walls else {}))
+    g, o = Context(emul, cfg), Oracle(cfg)
+    rng = np.random.default_rng(3)
+    for nu in ((2, 2, 8, 0.0), (1, 1, 2, 0.0), (3, 2, 4, 0.7), (2, 0, 1, 0.0), (4, 4, 3, 0.0), (1, 3, 2, 0.6)):
+        o.set_preconditioner("mg", *nu)
+        r = rng.standard_normal(o.shape(K.PRESSURE))
+        z = o.mg_apply(r)
+        for tma in (1, 0):
+            g.set_tuning("mg_tma", tma)
+            g.set_preconditioner("mg", *nu)
+            assert np.array_equal(g.mg_apply(r), z), (nu, tma)
+    g.set_tuning("mg_tma", 1)
+    for s in (g, o):
+        s.set_preconditioner("mg")
+    assert run(g, 1) == run(o, 1)
+    same_state(g, o, 3)
+    assert np.array_equal(g.residual_history(), o.residual_history())
+
+
 def test_emulated_multigrid_fixed_iterations_and_back_to_jacobi(emul):
     cfg = make_cfg(3, 32, fixed_iters=4)
     g, o = Context(emul, cfg), Oracle(cfg)

@@ -164,8 +164,8 @@ def mg_levels_of(cells, blocks):
 @pytest.mark.parametrize("world,blocks,cells", MG_GRIDS)
 @pytest.mark.parametrize("nu", [(2, 2, 8), (1, 1, 3), (3, 0, 2), (2, 0, 1)])
 def test_decomposed_vcycle_is_bit_identical_to_the_single_block_oracle(emul, world, blocks, cells, nu, peer):
-    if emul.tma:
-        pytest.skip("nothing TMA-specific")
+    if emul.tma and (world, blocks) not in ((8, None), (2, (2, 1, 1))):
+        pytest.skip("the fine-level sweeps on the TMA march: all axes split, and an x split")
     from cajitafluids_b200.distributed import block_grid
     cfg = cfg3(cells=cells)
     bl = blocks or block_grid(world, 3)

@@ -256,3 +256,33 @@ def test_cuda_mg_beats_jacobi_at_128_cubed():
         g.close()
     print("128^3 projection:", t)
     assert t["mg"][1] * 10 < t["jacobi"][1] and t["mg"][0] * 1.5 < t["jacobi"][0], t
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells,walls", [((72, 36, 24), None), ((130, 20, 12), [K.SOLID, K.FREE, K.SOLID, K.SOLID, K.FREE, K.SOLID]),
+                                         ((192, 160, 96), None)])
+def test_cuda_mg_fine_level_sweeps_on_the_tma_march(cells, walls):
+    """"mg_tma" (default on, 3-D): the fine level's smoothing sweeps on the TMA z-march (kernels_stencil.cu MODE 4 / 3)
+    against the one-thread-per-cell kernels and the checker, every sweep-count combination; then a whole step."""
+    from cajitafluids_b200 import Solver
+    cfg = make_cfg(3, cells, box=tuple(c / cells[0] for c in cells), **(dict(boundary_type=walls) if walls else {}))
+    g, o = Solver(cfg), Oracle(cfg)
+    rng = np.random.default_rng(3)
+    big = cells[0] * cells[1] * cells[2] > 1_000_000
+    for nu in ((2, 2, 8, 0.0),) if big else ((2, 2, 8, 0.0), (1, 1, 2, 0.0), (3, 2, 4, 0.7), (2, 0, 1, 0.0), (4, 4, 3, 0.0), (1, 3, 2, 0.6)):
+        o.set_preconditioner("mg", *nu)
+        r = rng.standard_normal(o.shape(K.PRESSURE))
+        z = o.mg_apply(r)
+        for tma in (1, 0):
+            g.set_tuning("mg_tma", tma)
+            g.set_preconditioner("mg", *nu)
+            assert np.array_equal(g.mg_apply(r), z), (nu, tma)
+    g.set_tuning("mg_tma", 1)
+    if not big:
+        for s in (g, o):
+            s.set_preconditioner("mg")
+        assert list(run(g, 1)) == list(run(o, 1))
+        for f in ALL(3):
+            assert np.array_equal(g.get(f), o.get(f)), f
+        assert np.array_equal(g.residual_history(), o.residual_history())
+    g.close()

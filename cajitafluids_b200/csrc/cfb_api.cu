@@ -1201,6 +1201,8 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->peer_overlap = value != 0;
     else if ( k == "mg_tma" )
         c->mg_tma = value != 0;
+    else if ( k == "mg_tma_prolong" )
+        c->mg_tma_prolong = value != 0;
     else if ( k == "mg_graph" )
         return mg_set_graph( c, value != 0 );
     else if ( k == "mg_coarse_kernel" )

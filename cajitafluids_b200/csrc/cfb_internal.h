@@ -242,6 +242,11 @@ struct cfb_ctx
     bool mg_tma = true;
     CUtensorMap mg_map_box[3] = {}, mg_map_tile_b{}; // stencil boxes of the fine level's b, x[0], x[1]; tile of b
     double* mg_map_ptr[3] = { nullptr, nullptr, nullptr };
+    // "mg_tma_prolong" tuning key: prolongation + first post-sweep on the march too (MODE 5); maps of the coarse
+    // level's two iterate buffers
+    bool mg_tma_prolong = true;
+    CUtensorMap mg_map_e[2] = {};
+    double* mg_map_e_ptr[2] = { nullptr, nullptr };
     bool mg_graph = false; // "mg_graph" tuning key: replay the V-cycle as a CUDA graph (one block)
     bool mg_coarse = false; // "mg_coarse_kernel" tuning key: the coarse end of the cycle in one single-CTA kernel
     MgStage* mg = nullptr;
@@ -353,6 +358,8 @@ bool mg_tma_applies( const cfb_ctx* c );
 int mg_tma_prepare( cfb_ctx* c );
 int launch_mg_smooth_tma( cfb_ctx* c, const OpConst& op, double omega, double* b, double* x0, double* x1, int xi_is, int dot );
 int launch_mg_smooth02_tma( cfb_ctx* c, const OpConst& op, double omega1, double omega2, double* b, double* x0, double* x1 );
+int launch_mg_prolong_smooth_tma( cfb_ctx* c, const OpConst& op, double omega, double* b, double* x0, double* x1, int xi_is,
+                                  double* e, long long csy, long long csz, const int cn[3], int dot );
 // kernels_cg1.cu: p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s
 int launch_cg1_update( cfb_ctx* c );
 int cg1_pcg_solve( cfb_ctx* c, int fixed_iters, int* num_iter, double* resid );

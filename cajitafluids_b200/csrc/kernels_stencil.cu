@@ -62,6 +62,14 @@ struct TileCfg
     static constexpr int STAGE_RT_BYTES = STAGE_BYTES + R_BYTES;
     static constexpr int SMEM_RT_BYTES = NS * STAGE_RT_BYTES + 128;
     static_assert( R_BYTES % 128 == 0, "r tile must keep the stages 128-byte aligned" );
+    // MODE 5 (multigrid: prolongation + first post-sweep): behind them the box of the coarse correction whose cells are
+    // the parents of the tile and of its halo ring, (TX / 2 + 2) x (TY / 2 + 2) entries of one coarse plane
+    static constexpr int EX = TX / 2 + 2, EY = TY / 2 + 2;
+    static constexpr int E_BYTES = EX * EY * 8;
+    static constexpr int E_PAD = ( E_BYTES + 127 ) / 128 * 128;
+    static constexpr int STAGE_E_BYTES = STAGE_RT_BYTES + E_PAD;
+    static constexpr int SMEM_E_BYTES = NS * STAGE_E_BYTES + 128;
+    static_assert( E_BYTES % 16 == 0, "coarse box rows must be multiples of 16 bytes" );
     static_assert( TX % 2 == 0 && NT % LX == 0 && TY % WY == 0 && RY >= 1, "bad tile" );
 };
 
@@ -78,6 +86,7 @@ struct StencilArgs
     // result goes to `q`; dot != 0: the sweep also leaves sum z.b in S->rz_new (mg_smooth_dot_kernel's job)
     double om1, om2;
     int dot;
+    int ehz; // MODE 5: ghost width of the coarse array (array plane of coarse plane K = K + ehz; likewise rows, columns)
 };
 
 // MODE 0: q = A p, sum p.q (CG kernel 4).
@@ -98,6 +107,10 @@ struct StencilArgs
 //         M^-1 r), xo = x1 + (omega2 D^-1)(b - A x1) (16 B/cell).  Statement for statement the one-thread-per-cell
 //         kernels they replace on the fine level — which reached 42 - 50 % of the bandwidth this march reaches —
 //         hence bit-identical.
+// MODE 5: prolongation + correction + the first post-smoothing sweep in one pass (mg.cu: cell_prolong_smooth): MODE 3
+//         on x' = xi + P e, the piecewise-constant prolongation of the coarse correction e added on the fly to the cell
+//         and to its six neighbours; every ring slot also carries the box of e with the parents of the plane's tile and
+//         halo ring (third tensor map, over the coarse level's own array).
 // FLAT: two-dimensional runs (one owned plane between two zero ghost planes): the z neighbours are zero by
 // construction and their planes are not loaded.  A template flag: the 3-D instantiations are untouched.
 // PF (MODE 2): the block that draws the last ticket runs the mailbox reduction of the kernel's sums over NVLink
@@ -110,25 +123,26 @@ struct StencilArgs
 template <class C, int MODE>
 constexpr int stencil_smem_bytes()
 {
-    return ( MODE == 1 || MODE == 3 ) ? C::SMEM_RT_BYTES : C::SMEM_BYTES;
+    return MODE == 5 ? C::SMEM_E_BYTES : ( ( MODE == 1 || MODE == 3 ) ? C::SMEM_RT_BYTES : C::SMEM_BYTES );
 }
 template <class C, int MODE>
 constexpr int stencil_min_ctas()
 {
     // 228 KB of shared memory per SM, 1 KB reserved per resident CTA
-    return ( MODE == 1 || MODE == 3 ) ? ( C::SMEM_RT_BYTES <= 75 * 1024 ? 3 : ( C::SMEM_RT_BYTES <= 113 * 1024 ? 2 : 1 ) )
-                                      : ( C::SMEM_BYTES <= 56 * 1024 ? 3 : ( C::SMEM_BYTES <= 110 * 1024 ? 2 : 1 ) );
+    constexpr int B = stencil_smem_bytes<C, MODE>();
+    return ( MODE == 1 || MODE == 3 || MODE == 5 ) ? ( B <= 75 * 1024 ? 3 : ( B <= 113 * 1024 ? 2 : 1 ) )
+                                                   : ( B <= 56 * 1024 ? 3 : ( B <= 110 * 1024 ? 2 : 1 ) );
 }
 template <class C, int MODE, bool FLAT, bool PF>
 __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
     stencil7_dot_tma( const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_r,
-                      const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
+                      const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ Geo g, const __grid_constant__ OpConst op,
                       const __grid_constant__ StencilArgs a, const __grid_constant__ typename PeerSel<PF>::type pf )
 {
     static_assert( !PF || MODE == 2, "only the single-reduction form reduces over the mailboxes from this kernel" );
-    constexpr bool RT = MODE == 1 || MODE == 3; // the slots also carry a halo-free tile (of r / of b)
+    constexpr bool RT = MODE == 1 || MODE == 3 || MODE == 5; // the slots also carry a halo-free tile (of r / of b)
     constexpr int TX = C::TX, TY = C::TY, NS = C::NS, PX = C::PX, RY = C::RY, WY = C::WY, LX = C::LX;
-    constexpr int STAGE = RT ? C::STAGE_RT_BYTES : C::STAGE_BYTES; // bytes per ring slot
+    constexpr int STAGE = MODE == 5 ? C::STAGE_E_BYTES : ( RT ? C::STAGE_RT_BYTES : C::STAGE_BYTES ); // bytes per ring slot
     double nalpha = 0.0;
     if ( MODE == 0 || MODE == 2 )
     {
@@ -183,16 +197,21 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
         const int s = l % NS;
         const uint32_t bar = smem_u32( &full_bar[s] );
         const bool with_r = RT && l >= 1 && l <= nplanes;
-        mbar_expect_tx( bar, C::BOX_BYTES + ( with_r ? C::R_BYTES : 0 ) );
+        mbar_expect_tx( bar, C::BOX_BYTES + ( with_r ? C::R_BYTES : 0 ) + ( MODE == 5 ? C::E_BYTES : 0 ) );
         tma_load_3d( smem_base + s * STAGE, &tmap, bar, cx, cy, cz + l );
         if ( with_r )
             tma_load_3d( smem_base + s * STAGE + C::STAGE_BYTES, &tmap_r, bar, a.hx + x0, g.h + y0, cz + l );
+        if ( MODE == 5 ) // the coarse plane of the parents of plane kbeg - 1 + l (floor division: ghost -1 -> ghost -1)
+            tma_load_3d( smem_base + s * STAGE + C::STAGE_RT_BYTES, &tmap_e, bar, x0 / 2 - 1 + a.ehz, y0 / 2 - 1 + a.ehz,
+                         ( ( kbeg - 1 + l + 2 ) >> 1 ) - 1 + a.ehz );
     };
     if ( tid == 0 )
     {
         prefetch_tmap( &tmap );
         if ( RT )
             prefetch_tmap( &tmap_r );
+        if ( MODE == 5 )
+            prefetch_tmap( &tmap_e );
 #pragma unroll
         for ( int s = 0; s < NS; ++s )
             mbar_init( smem_u32( &full_bar[s] ), 1 );
@@ -232,6 +251,18 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
         wyp[r] = wall_count( g, 1, j + 1 + g.off[1] );
     }
 
+    // MODE 5: rows of the coarse box holding the parents of my rows and of their y neighbours (box row 0 = coarse row
+    // y0 / 2 - 1); my pair's parent sits in box column lx + 1, its x neighbours' parents in columns lx and lx + 2
+    int jc[RY], jm[RY], jp[RY];
+#pragma unroll
+    for ( int r = 0; r < RY; ++r )
+    {
+        const int t = wy + r * WY; // row of the tile
+        jc[r] = ( t >> 1 ) + 1;
+        jm[r] = ( t + 1 ) >> 1;
+        jp[r] = ( ( t + 1 ) >> 1 ) + 1;
+    }
+    auto ebox = [&]( int slot ) { return stage0 + slot * ( STAGE / 8 ) + C::STAGE_RT_BYTES / 8; };
     // MODE 2: M^-1 of a cell with `idx` walls; MODE 4: the first sweep's factor omega1 D^-1 (the product first, as in
     // mg.cu's cell_smooth02)
     auto mfac = [&]( int idx ) { return MODE == 4 ? a.om1 * op.minv[idx] : op.minv[idx]; };
@@ -245,6 +276,15 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
         const int row = wy + r * WY + 1;
         zm[r] = FLAT ? make_double2( 0.0, 0.0 ) : *reinterpret_cast<const double2*>( stage0 + row * PX + 2 * lx + 2 );
         cc[r] = *reinterpret_cast<const double2*>( stage0 + ( 1 % NS ) * ( STAGE / 8 ) + row * PX + 2 * lx + 2 );
+        if ( MODE == 5 )
+        {
+            // xi -> x' = xi + P e of planes kbeg - 1 and kbeg (my pair shares its parent)
+            const double e0 = ebox( 0 )[jc[r] * C::EX + lx + 1], e1 = ebox( 1 % NS )[jc[r] * C::EX + lx + 1];
+            zm[r].x = zm[r].x + e0;
+            zm[r].y = zm[r].y + e0;
+            cc[r].x = cc[r].x + e1;
+            cc[r].y = cc[r].y + e1;
+        }
         if ( MODE == 2 || MODE == 4 )
         {
             // r -> u = M^-1 r (MODE 4: b -> x1 = (omega1 D^-1) b) of planes kbeg - 1 and kbeg
@@ -283,6 +323,22 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
             double xr = pc[2];
             double2 ym = *reinterpret_cast<const double2*>( pc - PX );
             double2 yp = *reinterpret_cast<const double2*>( pc + PX );
+            if ( MODE == 5 )
+            {
+                // the staged values are xi: x' = xi + P e of every neighbour, each with its own parent
+                const double* En = ebox( sn );
+                const double* Ec = ebox( sc );
+                const double en = En[jc[r] * C::EX + lx + 1];
+                zp.x = zp.x + en;
+                zp.y = zp.y + en;
+                xl = xl + Ec[jc[r] * C::EX + lx];
+                xr = xr + Ec[jc[r] * C::EX + lx + 2];
+                const double em = Ec[jm[r] * C::EX + lx + 1], ep = Ec[jp[r] * C::EX + lx + 1];
+                ym.x = ym.x + em;
+                ym.y = ym.y + em;
+                yp.x = yp.x + ep;
+                yp.y = yp.y + ep;
+            }
             if ( MODE == 2 || MODE == 4 )
             {
                 // the staged values are r (b): u = M^-1 r (x1 = omega1 D^-1 b) of every neighbour, each with its own
@@ -340,9 +396,10 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
                         dd_acc( acc3, c.x * a0 );
                     }
                 }
-                else if ( MODE == 3 )
+                else if ( MODE == 3 || MODE == 5 )
                 {
-                    // cell_smooth (mg.cu): xo = xi + (omega D^-1)(b - A xi), b from the tile behind the box of xi
+                    // cell_smooth / cell_prolong_smooth (mg.cu): xo = x + (omega D^-1)(b - A x) with x = xi (MODE 5: xi + P e),
+                    // b from the tile behind the box of xi
                     const int w0 = wx0 + wyc[r] + wz, w1 = wx1 + wyc[r] + wz;
                     const double2 bv = *reinterpret_cast<const double2*>( P + C::STAGE_BYTES / 8 + ( row - 1 ) * TX + 2 * lx );
                     const double z0 = fma( a.om1 * op.minv[w0], bv.x - a0, c.x );
@@ -445,7 +502,7 @@ __global__ void __launch_bounds__( C::NT, stencil_min_ctas<C, MODE>() )
             // (several ranks over NCCL: cg_global_sum( c, 2 + init ) combines the local sums and finishes)
         }
     }
-    else if ( MODE == 3 )
+    else if ( MODE == 3 || MODE == 5 )
     {
         if ( a.dot ) // (uniform over the grid) sum z.b -> rz_new, as mg_smooth_dot_kernel / mg_publish leave it
         {
@@ -586,14 +643,14 @@ int launch_tma_mode( cfb_ctx* c, const StencilArgs& a, int grid, const PeerFused
     {
         if ( pf ) // (the callers have made sure that flat does not apply)
         {
-            stencil7_dot_tma<C, MODE, false, true><<<grid, C::NT, SMEM, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, *pf );
+            stencil7_dot_tma<C, MODE, false, true><<<grid, C::NT, SMEM, c->stream>>>( tm, c->tmap_r1, c->tmap_r1, c->g, c->op, a, *pf );
             return 1;
         }
     }
     if ( c->g.D == 2 && c->flat_2d )
-        stencil7_dot_tma<C, MODE, true, false><<<grid, C::NT, SMEM, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
+        stencil7_dot_tma<C, MODE, true, false><<<grid, C::NT, SMEM, c->stream>>>( tm, c->tmap_r1, c->tmap_r1, c->g, c->op, a, none );
     else
-        stencil7_dot_tma<C, MODE, false, false><<<grid, C::NT, SMEM, c->stream>>>( tm, c->tmap_r1, c->g, c->op, a, none );
+        stencil7_dot_tma<C, MODE, false, false><<<grid, C::NT, SMEM, c->stream>>>( tm, c->tmap_r1, c->tmap_r1, c->g, c->op, a, none );
     return 1;
 }
 template <class C>
@@ -609,7 +666,13 @@ int launch_tma( cfb_ctx* c, const StencilArgs& a, int grid, int mode, const Peer
 } // namespace
 
 // One 3-D float64 tensor map over an array in the layout of the CG vectors (Geo): boxes of bx x by x 1 entries.
+static int encode_map_dims( cfb_ctx* c, CUtensorMap* map, double* base, int bx, int by, long long sy, long long sz, int ay, int az );
 static int encode_map( cfb_ctx* c, CUtensorMap* map, double* base, int bx, int by )
+{
+    return encode_map_dims( c, map, base, bx, by, c->g.sy, c->g.sz, c->g.ay, c->g.az );
+}
+// ... over any x-fastest array with row stride sy, plane stride sz (doubles), ay rows, az planes
+static int encode_map_dims( cfb_ctx* c, CUtensorMap* map, double* base, int bx, int by, long long sy, long long sz, int ay, int az )
 {
     static PFN_encodeTiled encode = nullptr;
     if ( !encode )
@@ -621,9 +684,8 @@ static int encode_map( cfb_ctx* c, CUtensorMap* map, double* base, int bx, int b
             return cfb_fail( c, CFB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available" );
         encode = (PFN_encodeTiled)fn;
     }
-    const Geo& g = c->g;
-    cuuint64_t gdim[3] = { (cuuint64_t)g.sy, (cuuint64_t)g.ay, (cuuint64_t)g.az };
-    cuuint64_t gstride[2] = { (cuuint64_t)g.sy * 8, (cuuint64_t)g.sz * 8 };
+    cuuint64_t gdim[3] = { (cuuint64_t)sy, (cuuint64_t)ay, (cuuint64_t)az };
+    cuuint64_t gstride[2] = { (cuuint64_t)sy * 8, (cuuint64_t)sz * 8 };
     cuuint32_t box[3] = { (cuuint32_t)bx, (cuuint32_t)by, 1 };
     cuuint32_t estr[3] = { 1, 1, 1 };
     CUresult r = encode( map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -772,7 +834,8 @@ namespace
 using MgTile = TileCfg<64, 16, 4>;
 
 template <int MODE>
-int launch_mg_mode( cfb_ctx* c, const CUtensorMap& box, const CUtensorMap& tile, const OpConst& op, StencilArgs& a )
+int launch_mg_mode( cfb_ctx* c, const CUtensorMap& box, const CUtensorMap& tile, const CUtensorMap& ebox, const OpConst& op,
+                    StencilArgs& a )
 {
     constexpr int SMEM = stencil_smem_bytes<MgTile, MODE>();
     static bool attr_set = false;
@@ -799,7 +862,7 @@ int launch_mg_mode( cfb_ctx* c, const CUtensorMap& box, const CUtensorMap& tile,
     }
     a.partials = c->d_partials;
     a.pstride = c->partials_cap;
-    stencil7_dot_tma<MgTile, MODE, false, false><<<(int)units, MgTile::NT, SMEM, c->stream>>>( box, tile, g, op, a, NoPeerArgs{} );
+    stencil7_dot_tma<MgTile, MODE, false, false><<<(int)units, MgTile::NT, SMEM, c->stream>>>( box, tile, ebox, g, op, a, NoPeerArgs{} );
     return 1;
 }
 
@@ -816,6 +879,7 @@ int mg_maps( cfb_ctx* c, double* b, double* x0, double* x1 )
         return rc;
     for ( int m = 0; m < 3; ++m )
         c->mg_map_ptr[m] = base[m];
+    c->mg_map_e_ptr[0] = c->mg_map_e_ptr[1] = nullptr; // (the coarse level's buffers belong to the same hierarchy)
     return CFB_OK;
 }
 } // namespace
@@ -848,7 +912,7 @@ int launch_mg_smooth_tma( cfb_ctx* c, const OpConst& op, double omega, double* b
     a.q = xi_is == 0 ? x1 : x0;
     a.om1 = omega;
     a.dot = dot;
-    return launch_mg_mode<3>( c, c->mg_map_box[1 + xi_is], c->mg_map_tile_b, op, a );
+    return launch_mg_mode<3>( c, c->mg_map_box[1 + xi_is], c->mg_map_tile_b, c->mg_map_tile_b, op, a );
 }
 
 // the first two sweeps from a zero initial guess in one pass: xo = x1 + (omega2 D^-1)(b - A x1), x1 = (omega1 D^-1) b
@@ -863,6 +927,35 @@ int launch_mg_smooth02_tma( cfb_ctx* c, const OpConst& op, double omega1, double
     a.q = x1;
     a.om1 = omega1;
     a.om2 = omega2;
-    return launch_mg_mode<4>( c, c->mg_map_box[0], c->mg_map_tile_b, op, a );
+    return launch_mg_mode<4>( c, c->mg_map_box[0], c->mg_map_tile_b, c->mg_map_tile_b, op, a );
+}
+
+// prolongation + correction + first post-smoothing sweep: xo = x' + (omega D^-1)(b - A x'), x' = xi + P e
+// (mg_prolong_smooth_kernel).  e: the coarse level's current iterate, an array with one ghost layer, row stride csy,
+// plane stride csz, cn[] owned cells.  The coarse rows must be multiples of 16 bytes (TMA): fine extents divisible by 4.
+int launch_mg_prolong_smooth_tma( cfb_ctx* c, const OpConst& op, double omega, double* b, double* x0, double* x1, int xi_is,
+                                  double* e, long long csy, long long csz, const int cn[3], int dot )
+{
+    if ( !mg_tma_applies( c ) || !c->mg_tma_prolong || ( csy & 1 ) || ( csz & 1 ) || ( c->g.n[2] & 1 ) )
+        return -1;
+    if ( note_rc( c, mg_maps( c, b, x0, x1 ) ) )
+        return 0;
+    int slot = -1;
+    for ( int q = 0; q < 2; ++q )
+        if ( c->mg_map_e_ptr[q] == e )
+            slot = q;
+    if ( slot < 0 )
+    {
+        slot = c->mg_map_e_ptr[0] ? 1 : 0; // the coarse level has two iterate buffers
+        if ( note_rc( c, encode_map_dims( c, &c->mg_map_e[slot], e, MgTile::EX, MgTile::EY, csy, csz, cn[1] + 2, cn[2] + 2 ) ) )
+            return 0;
+        c->mg_map_e_ptr[slot] = e;
+    }
+    StencilArgs a{};
+    a.q = xi_is == 0 ? x1 : x0;
+    a.om1 = omega;
+    a.dot = dot;
+    a.ehz = 1;
+    return launch_mg_mode<5>( c, c->mg_map_box[1 + xi_is], c->mg_map_tile_b, c->mg_map_e[slot], op, a );
 }
 

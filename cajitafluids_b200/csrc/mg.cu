@@ -1228,7 +1228,11 @@ int vcycle( cfb_ctx* c, int l, bool dot, bool* dotted, int* n )
     // x[cur] still has the ghosts exchanged for the restriction; the coarse correction needs its own
     MG_TRY( mg_exchange( c, C, C.x[C.cur], n ) );
     const bool dot_here = dot && m->nu2 == 1;
-    if ( dot_here )
+    // fine level of a 3-D run: the TMA z-march (kernels_stencil.cu MODE 5), same statements
+    if ( l == 0 && launch_mg_prolong_smooth_tma( c, level_op( H.d ), m->wpost[0], H.b, H.x[0], H.x[1], H.cur, C.x[C.cur], C.d.sy, C.d.sz,
+                                                 C.d.n, dot_here ? 1 : 0 ) >= 0 )
+        ;
+    else if ( dot_here )
         mg_prolong_smooth_kernel<true><<<grid, NT, 0, c->stream>>>( H.d, C.d, m->wpost[0], H.b, H.x[H.cur], C.x[C.cur],
                                                                    H.x[1 - H.cur], c->d_state, c->d_partials );
     else

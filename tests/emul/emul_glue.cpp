@@ -259,6 +259,11 @@ bool mg_tma_applies( const cfb_ctx* ) { return false; }
 int mg_tma_prepare( cfb_ctx* ) { return CFB_OK; }
 int launch_mg_smooth_tma( cfb_ctx*, const OpConst&, double, double*, double*, double*, int, int ) { return -1; }
 int launch_mg_smooth02_tma( cfb_ctx*, const OpConst&, double, double, double*, double*, double* ) { return -1; }
+int launch_mg_prolong_smooth_tma( cfb_ctx*, const OpConst&, double, double*, double*, double*, int, double*, long long, long long,
+                                  const int*, int )
+{
+    return -1;
+}
 
 int stencil_setup( cfb_ctx* c )
 {

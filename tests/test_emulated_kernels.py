@@ -150,7 +150,7 @@ def test_emulated_vcycle_alone_and_parameters(emul):
 
 
 @pytest.mark.parametrize("cells,walls", [((72, 36, 24), None), ((130, 20, 12), [K.SOLID, K.FREE, K.SOLID, K.SOLID, K.FREE, K.SOLID]),
-                                         ((64, 64, 6), None)])
+                                         ((64, 64, 6), None), ((132, 40, 10), [K.FREE, K.SOLID, K.SOLID, K.FREE, K.SOLID, K.SOLID])])
 def test_emulated_multigrid_fine_level_sweeps_on_the_tma_march(emul, cells, walls):
     """"mg_tma" (default on, 3-D): the fine level's fused pair of pre-smoothing sweeps and its post-smoothing sweeps —
     with and without the z.r sum — run on the TMA z-march (kernels_stencil.cu MODE 4 / 3) instead of the
@@ -164,11 +164,13 @@ def test_emulated_multigrid_fine_level_sweeps_on_the_tma_march(emul, cells, wall
         o.set_preconditioner("mg", *nu)
         r = rng.standard_normal(o.shape(K.PRESSURE))
         z = o.mg_apply(r)
-        for tma in (1, 0):
+        for tma, prolong in ((1, 1), (1, 0), (0, 0)):
             g.set_tuning("mg_tma", tma)
+            g.set_tuning("mg_tma_prolong", prolong)  # prolongation + first post-sweep on the march as well (MODE 5)
             g.set_preconditioner("mg", *nu)
-            assert np.array_equal(g.mg_apply(r), z), (nu, tma)
+            assert np.array_equal(g.mg_apply(r), z), (nu, tma, prolong)
     g.set_tuning("mg_tma", 1)
+    g.set_tuning("mg_tma_prolong", 1)
     for s in (g, o):
         s.set_preconditioner("mg")
     assert run(g, 1) == run(o, 1)

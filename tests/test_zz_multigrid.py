@@ -273,11 +273,13 @@ def test_cuda_mg_fine_level_sweeps_on_the_tma_march(cells, walls):
         o.set_preconditioner("mg", *nu)
         r = rng.standard_normal(o.shape(K.PRESSURE))
         z = o.mg_apply(r)
-        for tma in (1, 0):
+        for tma, prolong in ((1, 1), (1, 0), (0, 0)):
             g.set_tuning("mg_tma", tma)
+            g.set_tuning("mg_tma_prolong", prolong)  # prolongation + first post-sweep on the march as well (MODE 5)
             g.set_preconditioner("mg", *nu)
-            assert np.array_equal(g.mg_apply(r), z), (nu, tma)
+            assert np.array_equal(g.mg_apply(r), z), (nu, tma, prolong)
     g.set_tuning("mg_tma", 1)
+    g.set_tuning("mg_tma_prolong", 1)
     if not big:
         for s in (g, o):
             s.set_preconditioner("mg")

@@ -1200,7 +1200,11 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
     else if ( k == "peer_overlap" )
         c->peer_overlap = value != 0;
     else if ( k == "mg_tma" )
+    {
         c->mg_tma = value != 0;
+        if ( c->mg_tma && c->mg ) // a hierarchy built while the key was off: size the march's scratch now
+            return mg_tma_prepare( c );
+    }
     else if ( k == "mg_tma_prolong" )
         c->mg_tma_prolong = value != 0;
     else if ( k == "mg_graph" )

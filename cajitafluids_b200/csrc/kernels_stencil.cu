@@ -833,19 +833,27 @@ namespace
 {
 using MgTile = TileCfg<64, 16, 4>;
 
+// shared-memory attributes of a mode's kernel, once per process — from mg_tma_prepare (when the hierarchy is built), not
+// from the first launch, which may sit inside the stream capture of "mg_graph"
+template <int MODE>
+void mg_mode_attrs()
+{
+    static bool attr_set = false;
+    if ( attr_set )
+        return;
+    cudaFuncSetAttribute( stencil7_dot_tma<MgTile, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          stencil_smem_bytes<MgTile, MODE>() );
+    cudaFuncSetAttribute( stencil7_dot_tma<MgTile, MODE, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                          cudaSharedmemCarveoutMaxShared );
+    attr_set = true;
+}
+
 template <int MODE>
 int launch_mg_mode( cfb_ctx* c, const CUtensorMap& box, const CUtensorMap& tile, const CUtensorMap& ebox, const OpConst& op,
                     StencilArgs& a )
 {
     constexpr int SMEM = stencil_smem_bytes<MgTile, MODE>();
-    static bool attr_set = false;
-    if ( !attr_set )
-    {
-        cudaFuncSetAttribute( stencil7_dot_tma<MgTile, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM );
-        cudaFuncSetAttribute( stencil7_dot_tma<MgTile, MODE, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                              cudaSharedmemCarveoutMaxShared );
-        attr_set = true;
-    }
+    mg_mode_attrs<MODE>();
     const Geo& g = c->g;
     a.S = c->d_state;
     a.hx = 16;
@@ -889,6 +897,9 @@ int mg_tma_prepare( cfb_ctx* c )
 {
     if ( !mg_tma_applies( c ) )
         return CFB_OK;
+    mg_mode_attrs<3>();
+    mg_mode_attrs<4>();
+    mg_mode_attrs<5>();
     const Geo& g = c->g;
     const long long tiles = (long long)( ( g.n[0] + MgTile::TX - 1 ) / MgTile::TX ) * ( ( g.n[1] + MgTile::TY - 1 ) / MgTile::TY );
     const int zc = march_chunk( c, tiles );

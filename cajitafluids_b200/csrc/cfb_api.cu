@@ -1201,7 +1201,9 @@ int cfb_set_tuning( cfb_ctx* c, const char* key, int value )
         c->peer_overlap = value != 0;
     else if ( k == "mg_tma" )
     {
-        c->mg_tma = value != 0;
+        if ( value < -1 || value > 1 )
+            return cfb_fail( c, CFB_ERR_INVALID, "tuning key mg_tma: -1 (automatic), 0 or 1" );
+        c->mg_tma = value;
         if ( c->mg_tma && c->mg ) // a hierarchy built while the key was off: size the march's scratch now
             return mg_tma_prepare( c );
     }

@@ -239,7 +239,9 @@ struct cfb_ctx
     int mg_max_levels = 0; // 0 = as many as the block allows
     // "mg_tma" tuning key: the fine-level smoothing sweeps of three-dimensional runs on the TMA z-march
     // (kernels_stencil.cu MODE 3 / 4) instead of the one-thread-per-cell kernels
-    bool mg_tma = true;
+    // -1 (default): on for one block — measured and validated on a B200 — and off for several blocks, where the march
+    // has run in the host emulation only (every block grid, bit-identical) but not yet on several GPUs; 1 forces it on
+    int mg_tma = -1;
     CUtensorMap mg_map_box[3] = {}, mg_map_tile_b{}; // stencil boxes of the fine level's b, x[0], x[1]; tile of b
     double* mg_map_ptr[3] = { nullptr, nullptr, nullptr };
     // "mg_tma_prolong" tuning key: prolongation + first post-sweep on the march too (MODE 5); maps of the coarse

@@ -908,7 +908,8 @@ int mg_tma_prepare( cfb_ctx* c )
 
 bool mg_tma_applies( const cfb_ctx* c )
 {
-    return c->mg_tma && c->g.D == 3 && c->st_variant == 0 && c->g.n[0] >= 16 && c->g.n[1] >= 4;
+    const bool on = c->mg_tma > 0 || ( c->mg_tma < 0 && !c->cfg.use_nccl );
+    return on && c->g.D == 3 && c->st_variant == 0 && c->g.n[0] >= 16 && c->g.n[1] >= 4;
 }
 
 // xo = xi + (omega D^-1)(b - A xi) on the fine level; dot: also sum xo.b -> rz_new (mg_smooth_kernel / mg_smooth_dot_kernel).

@@ -333,8 +333,9 @@ int cfb_residual_history( const cfb_ctx* ctx, double* hist, int n, int* count );
  *                         compute kernels' last blocks, instead of one exchange kernel after each phase
  *   overlap_halo, peer_xstage      further exchange schedules (see csrc/halo.cu)
  *   mg_graph, mg_coarse_kernel     multigrid V-cycle as a CUDA graph / coarse levels in one kernel (one block)
- *   mg_tma 0|1, mg_tma_prolong 0|1   multigrid, 3-D: the fine level's smoothing sweeps / its prolongation + first
- *                         post-sweep on the TMA z-march (default 1)
+ *   mg_tma -1|0|1, mg_tma_prolong 0|1   multigrid, 3-D: the fine level's smoothing sweeps / its prolongation + first
+ *                         post-sweep on the TMA z-march (mg_tma -1, the default: on for one block, off for several
+ *                         blocks, where it has not run on hardware yet; mg_tma_prolong default 1)
  *   time_kernels 0|1      record CUDA events around each CG kernel (cfb_stats.ms_k_*) */
 int cfb_set_tuning( cfb_ctx* ctx, const char* key, int value );
 /* ReferenceConjugateGradient::setTolerance / setMaxIter / setPrintLevel

@@ -59,7 +59,7 @@ for case in range(ncase):
             ctx.set_tuning("cg_variant",variant)
             ctx.set_tuning("flat_2d",flat)
             ctx.set_tuning("peer_overlap",fusedx)
-            if mg: ctx.set_preconditioner("mg")
+            if mg: ctx.set_tuning("mg_tma", 1); ctx.set_preconditioner("mg")
             for f,a in vel.items(): ctx.set(f,a[block_slices(ctx,f)])
             ctx.add_inputs(); ctx.build_rhs()
             try: rg=ctx.pcg_solve()

@@ -252,6 +252,13 @@ def section_5(args, rank, blocks, gcfg, rank_cfg, rng, check):
     zg = gpu.mg_apply(r[sl])
     check("V-cycle 1e-13", rel_l2(zg, z[sl]) < 1e-13, f"rel l2 {rel_l2(zg, z[sl])}")
     check("V-cycle bit-exact", np.array_equal(zg, z[sl]))
+    # the fine level on the TMA march ("mg_tma" 1: off by default for several blocks until this section has run on GPUs)
+    gpu.set_tuning("mg_tma", 1)
+    gpu.set_preconditioner("mg")
+    zt = gpu.mg_apply(r[sl])
+    check("V-cycle on the TMA march bit-exact", np.array_equal(zt, z[sl]))
+    gpu.set_tuning("mg_tma", -1)
+    gpu.set_preconditioner("mg")
     for f, a in vel.items():
         gpu.set(f, a[block_slices(gpu, f)])
     gpu.add_inputs()

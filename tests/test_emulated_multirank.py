@@ -176,6 +176,7 @@ def test_decomposed_vcycle_is_bit_identical_to_the_single_block_oracle(emul, wor
     z = ora.mg_apply(r)
 
     def body(ctx, rank):
+        ctx.set_tuning("mg_tma", 1)  # the fine level on the TMA march: off by default for several blocks (not yet on several GPUs)
         ctx.set_preconditioner("mg", *nu)
         sl = block_slices(ctx, K.PRESSURE)
         ok = [np.array_equal(ctx.mg_apply(r[sl]), z[sl]) for _ in range(2)]  # twice: sequence numbers carry over
@@ -204,6 +205,7 @@ def test_decomposed_mg_pcg_is_bit_identical_to_the_single_block_oracle(emul, wor
     assert io < 40
 
     def body(ctx, rank):
+        ctx.set_tuning("mg_tma", 1)
         ctx.set_preconditioner("mg")
         for f, a in vel.items():
             ctx.set(f, a[block_slices(ctx, f)])
@@ -231,6 +233,7 @@ def test_decomposed_mg_steps_match_the_single_block_oracle(emul):
     its = ora.stats()["cg_iterations"]
 
     def body(ctx, rank):
+        ctx.set_tuning("mg_tma", 1)
         ctx.set_preconditioner("mg")
         ctx.setup()
         exact = [f for f in want0 if not np.array_equal(ctx.get(f), want0[f][block_slices(ctx, f)])]

@@ -432,6 +432,21 @@ def test_emulated_two_dimensional_units_march_along_y(emul, cells, walls):
     assert g2.pcg_solve() == ro and np.array_equal(g2.get(K.PRESSURE), po)
 
 
+def test_emulated_automatic_choice_of_the_cg_form(emul):
+    """`cg_variant` -1: the 64-byte form for three-dimensional blocks of 7e6 cells and more (measured 192^3 ... 512^3,
+    profiles/r2_cg_forms_by_size_rtma.json), the 72-byte form below (where its persistent kernel runs) and in 2-D;
+    cfb_stats reports the choice without running a solve."""
+    if emul.tma:
+        pytest.skip("host logic only")
+    for dim, cells, want in ((3, (64, 64, 64), 1), (3, (160, 160, 160), 1), (3, (448, 128, 128), 2), (2, (512, 512), 1),
+                             (2, (3000, 2500), 1)):
+        g = Context(emul, make_cfg(dim, cells, box=box_of(cells)))
+        assert g.stats()["cg_variant"] == want, (cells, g.stats()["cg_variant"])
+        g.set_tuning("cg_variant", 1)
+        assert g.stats()["cg_variant"] == 1
+        g.close()
+
+
 def test_emulated_bench_tiling_is_what_runs_at_512(emul):
     """A slab with the x / y extents of the benchmark grid takes the tiling rules' 128 x 16 x 3 phase-B tiles and
     the 64 x 16 x 4 stencil tiles: the configuration every headline number was measured with."""
